@@ -1,0 +1,156 @@
+"""ctypes binding of the CPU oracle (oracle/libssd_oracle.so).  TEST INFRASTRUCTURE ONLY: imported by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by the
+product package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libssd_oracle.so")
+
+OK, EKEY, EMALFORMED, EINDEX, ENOMEM = 0, -1, -2, -3, -4
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("whitelist", C.c_char_p), ("wl_len", C.POINTER(C.c_uint8)), ("n_whitelist", C.c_int),
+                ("umi_start", C.c_int), ("umi_end", C.c_int), ("bc1_start", C.c_int), ("bc1_end", C.c_int),
+                ("bc2_start", C.c_int), ("bc2_end", C.c_int), ("bc3_start", C.c_int), ("bc3_end", C.c_int),
+                ("errors", C.c_int), ("bin_reads", C.c_long)]
+
+
+class _Cell(C.Structure):
+    _fields_ = [("cell", C.c_char * 64), ("reads", C.c_uint64), ("distinct_umis", C.c_uint64), ("passing", C.c_int)]
+
+
+class _Out(C.Structure):
+    _fields_ = [("merged1", C.POINTER(C.c_char)), ("merged1_len", C.c_size_t),
+                ("passing", C.POINTER(C.c_char)), ("passing_len", C.c_size_t),
+                ("rec_cell", C.POINTER(C.c_int32)), ("n_records", C.c_uint64),
+                ("n_matched", C.c_uint64), ("n_retained", C.c_uint64),
+                ("cells", C.POINTER(_Cell)), ("n_cells", C.c_uint64), ("n_passing_cells", C.c_uint64),
+                ("error", C.c_int), ("error_msg", C.c_char * 256)]
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(HERE, "ssd_oracle.c"), os.path.join(HERE, "ssd_oracle.h")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
+        subprocess.check_call(["make", "-C", HERE, "-B", "libssd_oracle.so"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.ssd_oracle_demultiplex.argtypes = [C.POINTER(_Cfg), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(_Out)]
+        _lib.ssd_oracle_calc_demux_results.argtypes = [C.POINTER(_Out), C.c_long]
+        _lib.ssd_oracle_run_cli.argtypes = [C.POINTER(_Cfg), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_long, C.c_int, C.c_long, C.POINTER(_Out)]
+        _lib.ssd_oracle_learn_positions.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
+        _lib.ssd_oracle_collapse_map.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint32)]
+        _lib.ssd_oracle_collapse_map.restype = None
+        _lib.ssd_oracle_free.argtypes = [C.POINTER(_Out)]
+        _lib.ssd_oracle_free.restype = None
+    return _lib
+
+
+class OracleError(Exception):
+    def __init__(self, code: int, msg: str):
+        super().__init__("%d: %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+@dataclass
+class OracleResult:
+    merged1: bytes = b""
+    passing: bytes = b""
+    rec_cell: List[int] = field(default_factory=list)
+    n_records: int = 0
+    n_matched: int = 0
+    n_retained: int = 0
+    cells: Dict[bytes, Tuple[int, int, bool]] = field(default_factory=dict)  # cell -> (reads, distinct, passing)
+    n_cells: int = 0
+    n_passing_cells: int = 0
+
+
+DEFAULT_POSITIONS = dict(umi=(0, 10), bc3=(10, 18), bc2=(48, 56), bc1=(86, 94))  # V2:155-162
+
+
+def _cfg(whitelist: List[str], e: int, bin_reads: int, positions: Optional[dict]):
+    pos = dict(DEFAULT_POSITIONS)
+    if positions:
+        pos.update(positions)
+    raw = b"".join(w.encode().ljust(8, b"\0")[:8] for w in whitelist)
+    lens = (C.c_uint8 * len(whitelist))(*[min(len(w), 8) for w in whitelist])
+    cfg = _Cfg(raw, lens, len(whitelist), pos["umi"][0], pos["umi"][1], pos["bc1"][0], pos["bc1"][1],
+               pos["bc2"][0], pos["bc2"][1], pos["bc3"][0], pos["bc3"][1], e, bin_reads)
+    cfg._keep = (raw, lens)
+    return cfg
+
+
+def _collect(out: _Out, want_rec_cell: bool) -> OracleResult:
+    res = OracleResult()
+    res.merged1 = C.string_at(out.merged1, out.merged1_len) if out.merged1_len else b""
+    res.passing = C.string_at(out.passing, out.passing_len) if out.passing_len else b""
+    res.n_records, res.n_matched, res.n_retained = out.n_records, out.n_matched, out.n_retained
+    res.n_cells, res.n_passing_cells = out.n_cells, out.n_passing_cells
+    if want_rec_cell and out.n_records:
+        res.rec_cell = list(out.rec_cell[: out.n_records])
+    for i in range(out.n_cells):
+        c = out.cells[i]
+        res.cells[c.cell] = (c.reads, c.distinct_umis, bool(c.passing))
+    return res
+
+
+def demultiplex(r1: bytes, r2: bytes, whitelist: List[str], e: int, m: int, *, bin_reads: int = 100000,
+                positions: Optional[dict] = None, want_rec_cell: bool = True) -> OracleResult:
+    """demultiplex_fun followed by calc_demux_results (V2:32-462)."""
+    L = lib()
+    cfg = _cfg(whitelist, e, bin_reads, positions)
+    out = _Out()
+    try:
+        rc = L.ssd_oracle_demultiplex(C.byref(cfg), r1, len(r1), r2, len(r2), C.byref(out))
+        if rc == OK:
+            rc = L.ssd_oracle_calc_demux_results(C.byref(out), m)
+        if rc != OK:
+            raise OracleError(rc, out.error_msg.decode(errors="replace"))
+        return _collect(out, want_rec_cell)
+    finally:
+        L.ssd_oracle_free(C.byref(out))
+
+
+def run_cli(r1: bytes, r2: bytes, whitelist: List[str], e: int, m: int, *, n_workers: int, length_fastq: int,
+            bin_reads: int = 100000, positions: Optional[dict] = None) -> OracleResult:
+    """splitseqdemultiplex_0.2.3.py:52-70 with OpenMP threads as the joblib workers."""
+    L = lib()
+    cfg = _cfg(whitelist, e, bin_reads, positions)
+    out = _Out()
+    try:
+        rc = L.ssd_oracle_run_cli(C.byref(cfg), r1, len(r1), r2, len(r2), length_fastq, n_workers, m, C.byref(out))
+        if rc != OK:
+            raise OracleError(rc, out.error_msg.decode(errors="replace"))
+        return _collect(out, False)
+    finally:
+        L.ssd_oracle_free(C.byref(out))
+
+
+def learn_positions(sample: bytes) -> Tuple[int, int, int]:
+    pos = (C.c_int * 3)()
+    rc = lib().ssd_oracle_learn_positions(sample, len(sample), pos)
+    if rc != OK:
+        raise OracleError(rc, "ValueError: max() arg is an empty sequence")
+    return pos[0], pos[1], pos[2]
+
+
+def collapse_map(present: bytes, n: int, n_pairs: int) -> List[int]:
+    remap = (C.c_uint32 * (n * n * n))()
+    lib().ssd_oracle_collapse_map(present, n, n_pairs, remap)
+    return list(remap)

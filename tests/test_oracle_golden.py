@@ -1,0 +1,152 @@
+"""Pins the CPU oracle (oracle/ssd_oracle.c) against golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py): SURVEY.md Appendix A digests on the bundled FASTQs, the
+Appendix B rule cases, seeded adversarial sets and the position learner."""
+import hashlib
+import json
+import os
+
+import pytest
+
+import fastq_util as fu
+from oracle import ssd_oracle_py as orc
+
+WL = fu.load_whitelist()
+
+
+def test_whitelist_shape():
+    assert len(WL) == 96 and len(set(WL)) == 96 and all(len(w) == 8 and set(w) <= set("ACGT") for w in WL)
+    assert WL[0] == "AACGTGAT" and WL[14] == "AACGCTTA"
+
+
+@pytest.fixture(scope="module")
+def bundled():
+    return fu.load_bundled()
+
+
+@pytest.fixture(scope="module")
+def digests():
+    with open(os.path.join(fu.GOLDEN_DIR, "bundled_digests.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("e", [0, 1, 2, 3])
+@pytest.mark.parametrize("m", [1, 10])
+def test_bundled_digests(bundled, digests, e, m):
+    gold = digests["e%d_m%d" % (e, m)]
+    res = orc.demultiplex(bundled[0], bundled[1], WL, e, m)
+    assert res.n_matched == gold["matched"]
+    assert res.n_cells == gold["cells"]
+    assert res.n_passing_cells == gold["passing_cells"]
+    assert res.n_retained == gold["retained"]
+    assert fu.canonical_sha(res.merged1) == gold["merged1_sha"]
+    assert fu.canonical_sha(res.passing) == gold["passing_sha"]
+    assert hashlib.sha256(fu.counts_table(res.merged1)).hexdigest() == gold["counts_sha"]
+    table = b"".join(b"%s\t%d\t%d\n" % (c, v[0], v[1]) for c, v in sorted(res.cells.items()))
+    assert hashlib.sha256(table).hexdigest() == gold["counts_sha"]
+
+
+def test_bundled_headline_digest(bundled):
+    # BASELINE.md config 1 / SURVEY Appendix A bold row, hard-coded so a regenerated fixture cannot drift
+    res = orc.demultiplex(bundled[0], bundled[1], WL, 1, 10)
+    assert (res.n_matched, res.n_cells, res.n_passing_cells, res.n_retained) == (3541, 430, 83, 2780)
+    assert fu.canonical_sha(res.passing) == "56027fce91e05c9542e61c9dd2cfe1f0d01793a406ac39846c94fc82951dc751"
+
+
+@pytest.mark.parametrize("bin_reads", [777, 1, 100000])
+def test_bundled_bins(bundled, digests, bin_reads):
+    res = orc.demultiplex(bundled[0], bundled[1], WL, 1, 10, bin_reads=bin_reads)
+    assert fu.canonical_sha(res.passing) == digests["e1_m10"]["passing_sha"]
+
+
+@pytest.mark.parametrize("workers", [1, 3, 4, 8])
+def test_bundled_cli_workers(bundled, digests, workers):
+    # CLI3 at -n 1,3,4 gives the same canonical output (SURVEY Appendix A note)
+    res = orc.run_cli(bundled[0], bundled[1], WL, 1, 10, n_workers=workers, length_fastq=20000)
+    assert fu.canonical_sha(res.passing) == digests["e1_m10"]["passing_sha"]
+    assert res.n_retained == 2780
+
+
+RULES = fu.load_json_gz("rule_cases.json.gz")
+
+
+@pytest.mark.parametrize("case", RULES, ids=["%s-e%d" % (c["name"], c["e"]) for c in RULES])
+def test_rule_cases(case):
+    r1, r2 = case["r1"].encode(), case["r2"].encode()
+    if "error" in case:
+        with pytest.raises(orc.OracleError) as ei:
+            orc.demultiplex(r1, r2, WL, case["e"], case["m"], bin_reads=case.get("bin", 100000))
+        assert case["error"] == "KeyError" and ei.value.code == orc.EKEY
+        assert ei.value.msg == case["error_arg"].strip("'")
+        return
+    res = orc.demultiplex(r1, r2, WL, case["e"], case["m"], bin_reads=case.get("bin", 100000))
+    assert fu.canonical(res.merged1).decode() == case["merged1"]
+    assert fu.canonical(res.passing).decode() == case["passing"]
+    assert case["stdout_tail"][0].endswith(" %d" % res.n_cells)
+    assert case["stdout_tail"][1].endswith(" %d" % res.n_passing_cells)
+
+
+ADV = fu.load_json_gz("adversarial.json.gz")
+
+
+@pytest.mark.parametrize("g", ADV, ids=["%s-e%d-m%d" % (g["name"], g["e"], g["m"]) for g in ADV])
+def test_adversarial(g):
+    r1, r2 = fu.make_pairs(g["seed"], g["n"], WL, **g["kwargs"])
+    assert hashlib.sha256(r1 + b"|" + r2).hexdigest() == g["input_sha"], "generator drifted; rerun make_golden.py"
+    res = orc.demultiplex(r1, r2, WL, g["e"], g["m"])
+    assert (res.n_matched, res.n_cells, res.n_passing_cells, res.n_retained) == (g["matched"], g["cells"], g["passing_cells"], g["retained"])
+    assert fu.canonical_sha(res.merged1) == g["merged1_sha"]
+    assert fu.canonical_sha(res.passing) == g["passing_sha"]
+    assert fu.counts_table(res.merged1).decode() == g["counts_table"]
+
+
+def test_learner_cases():
+    with open(os.path.join(fu.GOLDEN_DIR, "learner_cases.json")) as fh:
+        cases = json.load(fh)
+    for c in cases:
+        shift = c["shift"]
+        seq = "T" * shift + "ACGTACGTAC" + WL[3] + fu.LINKER_3_2 + WL[7] + fu.LINKER_2_1 + WL[50] + "ACGT" * 10
+        recs = "".join("@l%d %d/2\n%s\n+\n%s\n" % (i, i, seq, "A" * len(seq)) for i in range(300))
+        sample = "".join(l + "\n" for l in recs.split("\n")[:1001]).encode()
+        p1, p2, p3 = orc.learn_positions(sample)
+        printed = "\n".join(c["printed"])
+        assert "UMI position has been extracted as %d:%d" % (p3 - 18, p3 - 8) in printed
+        assert "Barcode3 position has been extracted as %d:%d" % (p3 - 8, p3) in printed
+        assert "Barcode2 position has been extracted as %d:%d" % (p2 - 8, p2) in printed
+        assert "Barcode1 position has been extracted as %d:%d" % (p1 + 6, p1 + 14) in printed
+
+
+def test_learner_bundled_equals_defaults(bundled):
+    sample = b"".join(l + b"\n" for l in bundled[1].split(b"\n")[:1001])
+    assert orc.learn_positions(sample) == (80, 56, 18)
+
+
+def test_learner_empty_raises():
+    with pytest.raises(orc.OracleError):
+        orc.learn_positions(b"@a\nACGT\n+\nEEEE\n")
+
+
+def test_hammingtest_vectors():
+    # InDevOptimizations/HammingTest.py:6-20: distances 5,3,6,1; the single <=1 hit is the 4th entry
+    green = ["GGCGCATG", "ACTGAAAT", "ATGCCCGT", "ACTGAGTG"]
+    seq = "A" * 10 + "ACTGACTG" + "C" * 30 + "ACTGACTG" + "C" * 30 + "ACTGACTG"
+    r1 = b"@h 1/1\nACGT\n+\nEEEE\n"
+    r2 = ("@h 1/2\n%s\n+\n%s\n" % (seq, "E" * len(seq))).encode()
+    for e, expect in ((0, -1), (1, 3), (2, 3), (3, 1), (4, 1), (5, 0)):
+        res = orc.demultiplex(r1, r2, green, e, 1)
+        want = -1 if expect < 0 else (expect * 4 + expect) * 4 + expect
+        assert res.rec_cell == [want]
+
+
+def test_collapse_rule():
+    # Collapse_RanHex_Odt.py:44-71 — RanHex[k] (idx 48+k) folds into OligoDT[k] (idx k) only when both exist
+    n, pairs = 96, 48
+    present = bytearray(n * n * n)
+    cid = lambda a, b, c: (a * n + b) * n + c  # noqa: E731
+    for cell in (cid(0, 5, 6), cid(48, 5, 6), cid(48, 5, 7), cid(49, 5, 6), cid(2, 1, 1)):
+        present[cell] = 1
+    remap = orc.collapse_map(bytes(present), n, pairs)
+    assert remap[cid(48, 5, 6)] == cid(0, 5, 6)
+    assert remap[cid(48, 5, 7)] == cid(48, 5, 7)
+    assert remap[cid(49, 5, 6)] == cid(49, 5, 6)
+    assert remap[cid(0, 5, 6)] == cid(0, 5, 6)
+    assert sum(1 for i, r in enumerate(remap) if r != i) == 1
