@@ -1,0 +1,187 @@
+/*
+ * ssd_b200.h — C ABI of libssd_b200.so, the B200 (sm_100a) implementation of the `--version fast`
+ * demultiplexing hot path of paulranum11/SPLiT-Seq_demultiplexing.
+ *
+ * The reference has no FFI: its seam is the Python function surface that
+ * python_only_tool/splitseqdemultiplex_0.2.3.py calls.  Each entry point below names the reference
+ * interface (file:line, relative to the reference root) whose work it takes over; INTEGRATION.md
+ * shows the ctypes stub that binds them from the reference's own modules.
+ *
+ *   V2   = python_only_tool/DemultiplexUsingBarcodes_New_V2.py
+ *   LIB  = python_only_tool/Splitseq_fun_lib.py
+ *   CLI3 = python_only_tool/splitseqdemultiplex_0.2.3.py
+ *
+ * Conventions: plain pointers and sizes only.  Every function returns SSD_OK (0) or a negative
+ * SSD_E* code; ssd_last_error() gives the message.  A context is bound to one CUDA device and is not
+ * thread safe.  All device work is enqueued on the context's stream (ssd_set_stream); functions that
+ * return host-visible numbers synchronise that stream.  There is no CPU fallback: ssd_create fails
+ * when no CUDA device is usable.
+ */
+#ifndef SSD_B200_H
+#define SSD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSD_ABI_VERSION 1
+
+#define SSD_OK 0
+#define SSD_EINVAL (-1)     /* bad argument / unsupported configuration                              */
+#define SSD_ECUDA (-2)      /* CUDA runtime failure                       -> RuntimeError             */
+#define SSD_EKEY (-3)       /* matched read-2 record without its read-1 mate (V2:350) -> KeyError     */
+#define SSD_EMALFORMED (-4) /* FASTQ outside the input contract           -> ValueError               */
+#define SSD_ENOMEM (-5)
+#define SSD_ESTATE (-6)     /* call sequence violated                                                 */
+#define SSD_ERANGE (-7)     /* output buffer too small                                                */
+
+/* -m semantics.  V2:411 keeps a cell when len(set(UMIs)) >= m; the bash pipeline's step 1
+ * (demultiplex_using_barcodes.py:409) counts reads instead. */
+#define SSD_FILTER_DISTINCT_UMI 0
+#define SSD_FILTER_READS 1
+
+/* ssd_emit selector */
+#define SSD_EMIT_MATCHED 0 /* MergedCells_1.fastq      (V2:367-370)  every barcode-matched pair  */
+#define SSD_EMIT_PASSING 1 /* MergedCells_passing.fastq (V2:415-454)  pairs of cells passing -m   */
+
+#define SSD_MAX_WHITELIST 128
+#define SSD_BARCODE_LEN 8
+
+typedef struct ssd_ctx ssd_ctx;
+
+/* Replaces the constants and file reads at the top of V2.demultiplex_fun (V2:51-68 whitelist,
+ * V2:155-199 slice offsets) and the -e / -m options of CLI3:23-24. */
+typedef struct ssd_config {
+    uint32_t struct_size;     /* = sizeof(ssd_config), for ABI growth                                 */
+    int32_t device;           /* CUDA ordinal; -1 = current device                                    */
+    int32_t n_whitelist;      /* 1..SSD_MAX_WHITELIST; one list serves all three rounds (V2:302-304)  */
+    const char *whitelist;    /* n_whitelist x 8 bytes (file order = match priority)                  */
+    const uint8_t *whitelist_len; /* per-entry length 0..8, NULL = all 8                              */
+    int32_t umi_start, umi_end;   /* Python slice bounds into the read-2 sequence, 0 <= start <= end  */
+    int32_t bc1_start, bc1_end;   /* Round1 window (defaults 86:94)                                   */
+    int32_t bc2_start, bc2_end;   /* Round2 window (defaults 48:56)                                   */
+    int32_t bc3_start, bc3_end;   /* Round3 window (defaults 10:18)                                   */
+    int32_t errors;           /* -e                                                                    */
+    int64_t min_count;        /* -m                                                                    */
+    int32_t filter_mode;      /* SSD_FILTER_*                                                          */
+    int32_t collapse_pairs;   /* 0 = off; k = whitelist[k+i] (RanHex) folds into whitelist[i] (OligoDT)
+                                 for i < k when both cells survive the filter (Collapse_RanHex_Odt.py:44-71) */
+    int32_t record_bytes_hint;/* lower bound on bytes per FASTQ record used to size tables; 0 = 24     */
+    int32_t reserved;
+} ssd_config;
+
+typedef struct ssd_stats {
+    uint64_t n_records_r1, n_records_r2; /* complete 4-line records found                             */
+    uint64_t n_matched;        /* records whose three barcodes matched (MergedCells_1 records)         */
+    uint64_t n_cells;          /* "total number of unique barcodes detected" (V2:458)                  */
+    uint64_t n_passing_cells;  /* "barcodes passing the minimum UMI threshold" (V2:459)                */
+    uint64_t n_retained;       /* records of passing cells                                             */
+    uint64_t bytes_matched;    /* size of the SSD_EMIT_MATCHED text                                    */
+    uint64_t bytes_passing;    /* size of the SSD_EMIT_PASSING text                                    */
+    uint64_t n_regular_keys, n_irregular_keys; /* (cell,UMI) keys: ACGT-only full-length UMIs / others */
+} ssd_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int ssd_abi_version(void);
+int ssd_create(const ssd_config *cfg, ssd_ctx **out);
+void ssd_destroy(ssd_ctx *ctx);
+const char *ssd_last_error(const ssd_ctx *ctx); /* ctx may be NULL: error of the last failed ssd_create */
+/* cudaStream_t to enqueue on (0/NULL = the context's own stream). */
+int ssd_set_stream(ssd_ctx *ctx, void *cuda_stream);
+
+/* ---- phase 1: V2.demultiplex_fun minus the file writing (V2:207-358) ------------------------- */
+/* FASTQ record-boundary scan of both mates, UMI/barcode extraction at the configured offsets,
+ * Hamming<=e first-hit matching, mate-id check, per-cell read histogram, (cell,UMI) key capture.
+ * d_r1/d_r2 are DEVICE pointers, 16-byte aligned, to the whole text of the two files (or of the same
+ * record range of both); they must stay valid and unchanged until the last ssd_emit of this batch.
+ * Starts a new batch: previous per-batch results are discarded. */
+int ssd_demux_device(ssd_ctx *ctx, const void *d_r1, size_t r1_len, const void *d_r2, size_t r2_len);
+
+/* ---- phase 2: the -m decision, V2.calc_demux_results pass 1 (V2:389-412) ---------------------- */
+/* Device pointers to the n^3 uint32 per-cell read counts / distinct-UMI counts of this context.
+ * A multi-GPU host all-reduces (sums) them in place between the calls below. */
+int ssd_cell_space(const ssd_ctx *ctx, uint64_t *n_cells_total);
+int ssd_reads_histogram_device(ssd_ctx *ctx, uint32_t **d_hist);
+int ssd_distinct_histogram_device(ssd_ctx *ctx, uint32_t **d_distinct);
+
+/* Sort + deduplicate this batch's (cell,UMI) keys.  Regular keys are uint64 (cell << umi_bits | 2-bit
+ * UMI code), irregular keys (UMI shorter than the window or containing non-ACGT) are 16-byte records
+ * {uint64 hi = cell<<36 | len<<32 | bytes[0..4), uint64 lo = bytes[4..10)}.  Both come back sorted and
+ * unique; the arrays stay owned by the context. */
+int ssd_local_unique_keys(ssd_ctx *ctx, uint64_t **d_keys, uint64_t *n_keys, void **d_irregular,
+                          uint64_t *n_irregular);
+/* Count distinct keys per cell into the distinct histogram (overwrites it).  Inputs are device arrays
+ * in the formats above, not necessarily unique or sorted (e.g. the concatenation of what peers sent
+ * after an all-to-all by cell range); they are sorted in place. */
+int ssd_count_distinct(ssd_ctx *ctx, uint64_t *d_keys, uint64_t n_keys, void *d_irregular,
+                       uint64_t n_irregular);
+/* Bit width of the 2-bit-packed UMI inside a regular key (cell id = key >> umi_bits). */
+int ssd_key_layout(const ssd_ctx *ctx, int *umi_bits, int *cell_bits);
+
+/* Decide which cells pass from the (possibly all-reduced) histograms, apply the optional
+ * RanHex->OligoDT collapse, size both outputs.  Fills `stats` (may be NULL).  n_cells and
+ * n_passing_cells count over the whole (all-reduced) histogram; the record counts are this batch's. */
+int ssd_build_filter(ssd_ctx *ctx, ssd_stats *stats);
+
+/* Single-GPU convenience: ssd_local_unique_keys + ssd_count_distinct (distinct mode only) +
+ * ssd_build_filter. */
+int ssd_filter_single(ssd_ctx *ctx, ssd_stats *stats);
+
+/* ---- phase 3: the writers, V2:134-141 + V2:367-370 and V2:415-454 ----------------------------- */
+/* Write the annotated FASTQ text of this batch, records in input order, into the DEVICE buffer d_out
+ * (capacity `cap` bytes, 16-byte aligned).  *written receives stats.bytes_matched / bytes_passing. */
+int ssd_emit_device(ssd_ctx *ctx, int which, void *d_out, size_t cap, size_t *written);
+
+/* ---- host-buffer convenience (the end-to-end path) -------------------------------------------- */
+/* Whole pipeline on HOST buffers: chunked H2D into context-owned device staging, phases 1-3, D2H of
+ * the selected output into `out` (capacity out_cap).  Pinned host memory makes the copies async. */
+int ssd_run_host(ssd_ctx *ctx, const void *r1, size_t r1_len, const void *r2, size_t r2_len, int which,
+                 void *out, size_t out_cap, size_t *written, ssd_stats *stats);
+/* After ssd_run_host (or the phase calls): emit the selected output of the current batch into a HOST
+ * buffer.  ssd_run_host with out == NULL and out_cap == 0 stops after the filter so the caller can size
+ * the buffer from stats->bytes_* and then call this. */
+int ssd_emit_host(ssd_ctx *ctx, int which, void *out, size_t out_cap, size_t *written);
+/* Size query for ssd_run_host callers: upper bound of the output text for these input sizes. */
+size_t ssd_output_bound(const ssd_ctx *ctx, size_t r1_len, size_t r2_len);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so that non-CUDA hosts can get async copies. */
+int ssd_host_alloc(void **p, size_t bytes);
+int ssd_host_free(void *p);
+
+/* ---- per-record results (tests, split mode, downstream hand-off) ------------------------------ */
+/* Copy the per-record cell ids of the batch to the host: (i1*n + i2)*n + i3, or -1 when rejected. */
+int ssd_record_cells(ssd_ctx *ctx, int32_t *cells_host, uint64_t capacity, uint64_t *n_records);
+
+/* ---- synthetic read pairs (bench / tests) ---------------------------------------- */
+typedef struct ssd_synth_spec {
+    uint32_t struct_size;
+    uint64_t seed;
+    uint64_t first_index;     /* 1-based global index of the first pair                               */
+    uint64_t n_pairs;
+    int32_t read_len;         /* bases per mate (150)                                                  */
+    int32_t n_whitelist;
+    const char *whitelist;    /* n_whitelist x 8                                                       */
+    uint32_t cell_pool;       /* number of distinct planted cells                                      */
+    uint32_t p_sub_ppm;       /* per-base substitution probability inside barcode windows, ppm        */
+    uint32_t p_n_ppm;         /* per-base N probability over read 2, ppm                               */
+    uint32_t p_junk_ppm;      /* reads with random barcodes, ppm                                       */
+    uint32_t p_dup_umi_ppm;   /* reads that reuse a low-entropy UMI of their cell, ppm                 */
+    uint32_t p_tie_ppm;       /* reads with a barcode at the midpoint of a distance-4 whitelist pair   */
+    uint32_t p_trunc_ppm;     /* read 2 truncated to 40..93 bases, ppm                                 */
+    uint32_t p_atqual_ppm;    /* quality lines starting with '@', ppm                                  */
+} ssd_synth_spec;
+
+/* Exact byte sizes of the two files the spec describes. */
+int ssd_synth_sizes(const ssd_synth_spec *spec, uint64_t *r1_bytes, uint64_t *r2_bytes);
+/* Generate on the device (pointers from the caller, sizes from ssd_synth_sizes). */
+int ssd_synth_generate_device(ssd_ctx *ctx, const ssd_synth_spec *spec, void *d_r1, void *d_r2);
+/* Same bytes on the host (plain C++ twin of the device generator, for CPU-side tests). */
+int ssd_synth_generate_host(const ssd_synth_spec *spec, void *r1, void *r2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,866 @@
+// ssd_b200.cu — host side of libssd_b200.so: the C ABI declared in include/ssd_b200.h, device memory
+// management, kernel launches and the synthetic read generator.  Everything that touches bytes of the
+// FASTQ files runs in the kernels of ssd_kernels.cuh; there is no CPU implementation of the path here.
+#include "../../include/ssd_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "ssd_kernels.cuh"
+#include "ssd_synth.cuh"
+
+using namespace ssd;
+
+namespace {
+
+thread_local char g_create_error[512] = "";
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct ssd_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    ssd_config cfg{};
+    DevCfg dcfg{};
+    uint64_t n_cells_total = 0;
+    int record_hint = 48;
+    char err[512] = "";
+
+    DevCounters* d_cnt = nullptr;
+    unsigned long long* d_err_off = nullptr;
+    uint8_t* d_lut = nullptr;
+    uint8_t* d_wl_len = nullptr;
+    uint32_t* d_hist = nullptr;
+    uint32_t* d_distinct = nullptr;
+    uint32_t* d_remap = nullptr;
+    uint8_t* d_pass = nullptr;
+
+    // current batch
+    const uint8_t* r1 = nullptr;
+    const uint8_t* r2 = nullptr;
+    size_t r1_len = 0, r2_len = 0;
+    bool wide = false;  // 64-bit record offsets
+    uint64_t rec_cap = 0;
+    uint64_t n_rec_r1 = 0, n_rec_r2 = 0, n_rec = 0, n_keys = 0, n_irr = 0;
+    bool phase1_done = false, filter_done = false, unique_done = false;
+    uint64_t* uniq_keys = nullptr;
+    uint64_t n_uniq = 0;
+    IrrKey* uniq_irr = nullptr;
+    uint64_t n_uniq_irr = 0;
+    ssd_stats stats{};
+
+    DevBuf b_status1, b_status2, b_r1_start, b_r1_base, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
+        b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
+    DevBuf b_in1, b_in2, b_out;
+};
+
+namespace {
+
+int fail(ssd_ctx* c, int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_create_error, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(c, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return fail((c), SSD_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int ensure(ssd_ctx* c, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return SSD_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(&b.p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) return fail(c, SSD_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    b.cap = want;
+    return SSD_OK;
+}
+
+void release(DevBuf& b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+#define OKR(x)                     \
+    do {                           \
+        int rc_ = (x);             \
+        if (rc_ != SSD_OK) return rc_; \
+    } while (0)
+
+inline uint32_t blocks_for(uint64_t n, uint32_t per) { return (uint32_t)((n + per - 1) / per); }
+
+// ---- device-wide exclusive scan (out has n + 1 entries) ----------------------------------------
+template <typename T, class F>
+int exclusive_scan(ssd_ctx* c, F f, uint64_t n, T* out)
+{
+    const uint32_t nb = (uint32_t)(n / kScanBlock + 1);
+    OKR(ensure(c, c->b_bsums, (size_t)nb * sizeof(T)));
+    T* bs = (T*)c->b_bsums.p;
+    k_scan_reduce<T, F><<<nb, kThreads, 0, c->stream>>>(f, n, bs);
+    k_scan_block_sums<T><<<1, kThreads, 0, c->stream>>>(bs, nb, (T*)nullptr);
+    k_scan_apply<T, F><<<nb, kThreads, 0, c->stream>>>(f, n, bs, out);
+    CU(c, cudaGetLastError());
+    return SSD_OK;
+}
+
+struct LoadU32 {
+    const uint32_t* p;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return p[i]; }
+};
+
+// ---- LSD radix sort of 64-bit keys over bits [0, bits); returns where the sorted data ended up ----
+template <bool HV>
+int radix_sort64(ssd_ctx* c, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* vb, uint64_t n, int bits, uint64_t** sorted,
+                 uint32_t** sorted_vals)
+{
+    *sorted = a;
+    if (sorted_vals) *sorted_vals = va;
+    if (n == 0) return SSD_OK;
+    const uint32_t nb = blocks_for(n, kSortBlock);
+    const size_t ncount = (size_t)256 * nb;
+    OKR(ensure(c, c->b_counts, ncount * sizeof(uint32_t)));
+    OKR(ensure(c, c->b_offsets, (ncount + 1) * sizeof(uint32_t)));
+    uint32_t* counts = (uint32_t*)c->b_counts.p;
+    uint32_t* offsets = (uint32_t*)c->b_offsets.p;
+    for (int bit = 0; bit < bits; bit += 8) {
+        k_sort_hist<uint64_t><<<nb, kThreads, 0, c->stream>>>(a, n, bit, counts, nb);
+        OKR(exclusive_scan<uint32_t>(c, LoadU32{counts}, ncount, offsets));
+        k_sort_scatter<uint64_t, HV><<<nb, kThreads, 0, c->stream>>>(a, b, va, vb, n, bit, offsets, nb);
+        std::swap(a, b);
+        std::swap(va, vb);
+    }
+    CU(c, cudaGetLastError());
+    *sorted = a;
+    if (sorted_vals) *sorted_vals = va;
+    return SSD_OK;
+}
+
+// sort + unique of regular keys.  `keys` holds n keys; result: *uniq (a context buffer or `keys`), *n_uniq
+int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint64_t* n_uniq)
+{
+    *uniq = keys;
+    *n_uniq = 0;
+    if (n == 0) return SSD_OK;
+    OKR(ensure(c, c->b_keys_alt, n * sizeof(uint64_t)));
+    uint64_t* sorted = nullptr;
+    OKR(radix_sort64<false>(c, keys, (uint64_t*)c->b_keys_alt.p, nullptr, nullptr, n, c->dcfg.umi_bits + c->dcfg.cell_bits, &sorted,
+                            nullptr));
+    uint64_t* other = sorted == keys ? (uint64_t*)c->b_keys_alt.p : keys;
+    OKR(ensure(c, c->b_pos, (n + 1) * sizeof(uint32_t)));
+    uint32_t* pos = (uint32_t*)c->b_pos.p;
+    OKR(exclusive_scan<uint32_t>(c, HeadFlag64{sorted}, n, pos));
+    k_compact64<<<blocks_for(n, kThreads), kThreads, 0, c->stream>>>(sorted, pos, n, other);
+    uint32_t total = 0;
+    CU(c, cudaMemcpyAsync(&total, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    *uniq = other;
+    *n_uniq = total;
+    return SSD_OK;
+}
+
+// sort + unique of irregular keys through an index permutation (128-bit LSD: low word, then high word)
+int sort_unique_irr(ssd_ctx* c, IrrKey* keys, uint64_t n, IrrKey** uniq, uint64_t* n_uniq)
+{
+    *uniq = keys;
+    *n_uniq = 0;
+    if (n == 0) return SSD_OK;
+    OKR(ensure(c, c->b_perm, n * sizeof(uint32_t)));
+    OKR(ensure(c, c->b_perm_alt, n * sizeof(uint32_t)));
+    OKR(ensure(c, c->b_tmp64a, n * sizeof(uint64_t)));
+    OKR(ensure(c, c->b_tmp64b, n * sizeof(uint64_t)));
+    OKR(ensure(c, c->b_irr_alt, n * sizeof(IrrKey)));
+    uint32_t* perm = (uint32_t*)c->b_perm.p;
+    uint32_t* perm_alt = (uint32_t*)c->b_perm_alt.p;
+    uint64_t* ta = (uint64_t*)c->b_tmp64a.p;
+    uint64_t* tb = (uint64_t*)c->b_tmp64b.p;
+    const uint32_t nb = blocks_for(n, kThreads);
+    k_iota<<<nb, kThreads, 0, c->stream>>>(perm, n);
+    uint64_t* sk = nullptr;
+    uint32_t* sv = nullptr;
+    for (int word = 0; word < 2; word++) {
+        k_gather_irr_word<<<nb, kThreads, 0, c->stream>>>(keys, perm, n, word, ta);
+        OKR(radix_sort64<true>(c, ta, tb, perm, perm_alt, n, word ? kIrrHiBits : kIrrLoBits, &sk, &sv));
+        if (sv != perm) std::swap(perm, perm_alt);
+        if (sk != ta) std::swap(ta, tb);
+    }
+    OKR(ensure(c, c->b_pos, (n + 1) * sizeof(uint32_t)));
+    uint32_t* pos = (uint32_t*)c->b_pos.p;
+    OKR(exclusive_scan<uint32_t>(c, HeadFlagIrr{keys, perm}, n, pos));
+    IrrKey* out = (IrrKey*)c->b_irr_alt.p;
+    k_compact_irr<<<nb, kThreads, 0, c->stream>>>(keys, perm, pos, n, out);
+    uint32_t total = 0;
+    CU(c, cudaMemcpyAsync(&total, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    *uniq = out;
+    *n_uniq = total;
+    return SSD_OK;
+}
+
+int count_cells(ssd_ctx* c, const uint64_t* uniq, uint64_t n_uniq, const IrrKey* uirr, uint64_t n_uirr)
+{
+    CU(c, cudaMemsetAsync(c->d_distinct, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
+    if (n_uniq) k_count_cells64<<<blocks_for(n_uniq, kThreads), kThreads, 0, c->stream>>>(uniq, n_uniq, c->dcfg.umi_bits, c->d_distinct);
+    if (n_uirr) k_count_cells_irr<<<blocks_for(n_uirr, kThreads), kThreads, 0, c->stream>>>(uirr, n_uirr, c->d_distinct);
+    CU(c, cudaGetLastError());
+    return SSD_OK;
+}
+
+template <typename OffT>
+int launch_scans(ssd_ctx* c)
+{
+    ScanArgs<OffT> a{};
+    a.cnt = c->d_cnt;
+    a.err_off = c->d_err_off;
+    a.rec_cap = c->rec_cap;
+    a.r1_start = (OffT*)c->b_r1_start.p;
+    a.r1_base = (uint32_t*)c->b_r1_base.p;
+    a.r1buf = c->r1;
+    a.r1_len = c->r1_len;
+    a.ann = (uint64_t*)c->b_ann.p;
+    a.hist = c->d_hist;
+    a.keys = (uint64_t*)c->b_keys.p;
+    a.irr = (IrrKey*)c->b_irr.p;
+    a.lut = c->d_lut + (size_t)c->dcfg.e * 65536u;
+
+    const uint32_t nt1 = blocks_for(c->r1_len, kTile), nt2 = blocks_for(c->r2_len, kTile);
+    if (nt1) {
+        a.buf = c->r1;
+        a.len = c->r1_len;
+        a.status = (unsigned long long*)c->b_status1.p;
+        a.n_tiles = nt1;
+        k_scan<kScanR1, OffT><<<nt1, kThreads, 0, c->stream>>>(a, c->dcfg);
+    }
+    if (nt2) {
+        a.buf = c->r2;
+        a.len = c->r2_len;
+        a.status = (unsigned long long*)c->b_status2.p;
+        a.n_tiles = nt2;
+        k_scan<kScanR2, OffT><<<nt2, kThreads, 0, c->stream>>>(a, c->dcfg);
+    }
+    CU(c, cudaGetLastError());
+    return SSD_OK;
+}
+
+template <typename OffT>
+int launch_emit(ssd_ctx* c, int which, uint8_t* d_out)
+{
+    EmitArgs<OffT> a{};
+    a.r1buf = c->r1;
+    a.r1_len = c->r1_len;
+    a.r2buf = c->r2;
+    a.r2_len = c->r2_len;
+    a.r1_start = (const OffT*)c->b_r1_start.p;
+    a.ann = (const uint64_t*)c->b_ann.p;
+    a.out_off = (const uint64_t*)c->b_out_off.p;
+    a.remap = (which == SSD_EMIT_PASSING && c->cfg.collapse_pairs > 0) ? c->d_remap : nullptr;
+    a.out = d_out;
+    a.n_rec = c->n_rec;
+    a.n_rec_r1 = c->n_rec_r1;
+    a.cnt = c->d_cnt;
+    const uint64_t avg_in = c->n_rec_r1 ? c->r1_len / c->n_rec_r1 : 1;
+    uint64_t rpb = (uint64_t)(kEmitIn * 3 / 4) / (avg_in + 48);
+    a.rpb = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rpb, 1), 128);
+    const uint32_t nb = blocks_for(c->n_rec, a.rpb);
+    if (nb) k_emit<OffT><<<nb, kThreads, 0, c->stream>>>(a, c->dcfg);
+    CU(c, cudaGetLastError());
+    return SSD_OK;
+}
+
+OutLen make_outlen(ssd_ctx* c, int which)
+{
+    OutLen f{};
+    f.ann = (const uint64_t*)c->b_ann.p;
+    f.r1_base = (const uint32_t*)c->b_r1_base.p;
+    f.pass = which == SSD_EMIT_PASSING ? c->d_pass : nullptr;
+    f.remap = (which == SSD_EMIT_PASSING && c->cfg.collapse_pairs > 0) ? c->d_remap : nullptr;
+    f.wl_len = c->d_wl_len;
+    f.n = c->dcfg.n_wl;
+    f.umi_len = c->dcfg.umi_len;
+    return f;
+}
+
+int fetch_counters(ssd_ctx* c, DevCounters* h)
+{
+    CU(c, cudaMemcpyAsync(h, c->d_cnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SSD_OK;
+}
+
+std::string token_at(ssd_ctx* c, const uint8_t* d_buf, size_t len, unsigned long long off)
+{
+    char tmp[257];
+    size_t n = std::min<size_t>(256, len > off ? len - off : 0);
+    if (!n || cudaMemcpy(tmp, d_buf + off, n, cudaMemcpyDeviceToHost) != cudaSuccess) return "?";
+    size_t k = 0;
+    while (k < n && !((unsigned char)tmp[k] >= 9 && (unsigned char)tmp[k] <= 13) && !((unsigned char)tmp[k] >= 28 && (unsigned char)tmp[k] <= 32)) k++;
+    (void)c;
+    return std::string(tmp, k);
+}
+
+}  // namespace
+
+// ================================================================================================
+// lifetime
+// ================================================================================================
+extern "C" int ssd_abi_version(void) { return SSD_ABI_VERSION; }
+
+extern "C" const char* ssd_last_error(const ssd_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
+{
+    if (!cfg || !out) return fail(nullptr, SSD_EINVAL, "ssd_create: null argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(ssd_config)) return fail(nullptr, SSD_EINVAL, "ssd_config.struct_size %u != %zu", cfg->struct_size, sizeof(ssd_config));
+    if (cfg->n_whitelist < 1 || cfg->n_whitelist > SSD_MAX_WHITELIST || !cfg->whitelist)
+        return fail(nullptr, SSD_EINVAL, "whitelist must hold 1..%d entries", SSD_MAX_WHITELIST);
+    const int32_t bounds[8] = {cfg->umi_start, cfg->umi_end, cfg->bc1_start, cfg->bc1_end, cfg->bc2_start, cfg->bc2_end, cfg->bc3_start, cfg->bc3_end};
+    for (int i = 0; i < 8; i += 2)
+        if (bounds[i] < 0 || bounds[i + 1] < bounds[i])
+            return fail(nullptr, SSD_EINVAL, "slice bounds must satisfy 0 <= start <= end (got %d:%d)", bounds[i], bounds[i + 1]);
+    if (cfg->umi_end - cfg->umi_start > 10) return fail(nullptr, SSD_EINVAL, "UMI windows longer than 10 bases are not supported");
+    for (int i = 2; i < 8; i += 2)
+        if (bounds[i + 1] - bounds[i] > 8) return fail(nullptr, SSD_EINVAL, "barcode windows longer than 8 bases are not supported");
+    if (cfg->errors < 0 || cfg->errors > 8) return fail(nullptr, SSD_EINVAL, "errors must be in 0..8");
+    if (cfg->filter_mode != SSD_FILTER_DISTINCT_UMI && cfg->filter_mode != SSD_FILTER_READS) return fail(nullptr, SSD_EINVAL, "unknown filter_mode");
+    if (cfg->collapse_pairs < 0 || 2 * cfg->collapse_pairs > cfg->n_whitelist) return fail(nullptr, SSD_EINVAL, "collapse_pairs out of range");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SSD_ECUDA, "no usable CUDA device (%s); libssd_b200 has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+
+    ssd_ctx* c = new ssd_ctx();
+    c->cfg = *cfg;
+    c->cfg.whitelist = nullptr;
+    c->cfg.whitelist_len = nullptr;
+    if (cfg->device >= 0) {
+        c->device = cfg->device;
+    } else if (cudaGetDevice(&c->device) != cudaSuccess) {
+        c->device = 0;
+    }
+    auto bail = [&](int code) {
+        strncpy(g_create_error, c->err, sizeof g_create_error - 1);
+        ssd_destroy(c);
+        return code;
+    };
+#define CUB_(call)                                                                                   \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            fail(c, SSD_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                      \
+            return bail(SSD_ECUDA);                                                                  \
+        }                                                                                            \
+    } while (0)
+    CUB_(cudaSetDevice(c->device));
+    CUB_(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+
+    DevCfg& d = c->dcfg;
+    memset(&d, 0, sizeof d);
+    d.n_wl = cfg->n_whitelist;
+    d.e = cfg->errors;
+    d.us = cfg->umi_start;
+    d.ue = cfg->umi_end;
+    d.b1s = cfg->bc1_start;
+    d.b1e = cfg->bc1_end;
+    d.b2s = cfg->bc2_start;
+    d.b2e = cfg->bc2_end;
+    d.b3s = cfg->bc3_start;
+    d.b3e = cfg->bc3_end;
+    d.umi_len = d.ue - d.us;
+    d.umi_bits = 2 * d.umi_len;
+    c->n_cells_total = (uint64_t)d.n_wl * d.n_wl * d.n_wl;
+    d.cell_bits = 1;
+    while ((1ull << d.cell_bits) < c->n_cells_total) d.cell_bits++;
+    d.fast_wl = 1;
+    for (int i = 0; i < d.n_wl; i++) {
+        int len = cfg->whitelist_len ? std::min<int>(cfg->whitelist_len[i], 8) : 8;
+        d.wl_len[i] = (uint8_t)len;
+        uint32_t code = 0;
+        for (int j = 0; j < 8; j++) {
+            unsigned char ch = j < len ? (unsigned char)cfg->whitelist[i * 8 + j] : 0;
+            d.wl[i * 8 + j] = ch;
+            bool acgt = ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T';
+            if (!acgt) d.fast_wl = 0;
+            code |= ((uint32_t)(ch >> 1) & 3u) << (2 * j);
+        }
+        if (len != 8) d.fast_wl = 0;
+        d.wl_code[i] = (uint16_t)code;
+    }
+    // all three barcode windows must be 8 wide for the LUT path; shorter windows use the generic loop anyway
+    c->record_hint = cfg->record_bytes_hint > 0 ? cfg->record_bytes_hint : 48;
+
+    CUB_(cudaMalloc(&c->d_cnt, sizeof(DevCounters)));
+    CUB_(cudaMalloc(&c->d_err_off, 2 * sizeof(unsigned long long)));
+    CUB_(cudaMalloc(&c->d_lut, (size_t)(d.e + 1) * 65536u));
+    CUB_(cudaMalloc(&c->d_wl_len, kMaxWl));
+    CUB_(cudaMalloc(&c->d_hist, c->n_cells_total * sizeof(uint32_t)));
+    CUB_(cudaMalloc(&c->d_distinct, c->n_cells_total * sizeof(uint32_t)));
+    CUB_(cudaMalloc(&c->d_remap, c->n_cells_total * sizeof(uint32_t)));
+    CUB_(cudaMalloc(&c->d_pass, c->n_cells_total));
+    CUB_(cudaMemcpyAsync(c->d_wl_len, d.wl_len, kMaxWl, cudaMemcpyHostToDevice, c->stream));
+    CUB_(cudaMemsetAsync(c->d_hist, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
+    CUB_(cudaMemsetAsync(c->d_distinct, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
+    CUB_(cudaMemsetAsync(c->d_pass, 0, c->n_cells_total, c->stream));
+    CUB_(cudaMemsetAsync(c->d_cnt, 0, sizeof(DevCounters), c->stream));
+    if (d.fast_wl) k_build_lut<<<256, 256, 0, c->stream>>>(d, c->d_lut, d.e + 1);
+    CUB_(cudaGetLastError());
+    CUB_(cudaStreamSynchronize(c->stream));
+#undef CUB_
+    *out = c;
+    return SSD_OK;
+}
+
+extern "C" void ssd_destroy(ssd_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_r1_start, &c->b_r1_base, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
+                      &c->b_irr_alt, &c->b_perm, &c->b_perm_alt, &c->b_tmp64a, &c->b_tmp64b, &c->b_counts, &c->b_offsets, &c->b_bsums,
+                      &c->b_pos, &c->b_out_off, &c->b_cells, &c->b_in1, &c->b_in2, &c->b_out};
+    for (DevBuf* b : bufs) release(*b);
+    cudaFree(c->d_cnt);
+    cudaFree(c->d_err_off);
+    cudaFree(c->d_lut);
+    cudaFree(c->d_wl_len);
+    cudaFree(c->d_hist);
+    cudaFree(c->d_distinct);
+    cudaFree(c->d_remap);
+    cudaFree(c->d_pass);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int ssd_set_stream(ssd_ctx* c, void* cuda_stream)
+{
+    if (!c) return SSD_EINVAL;
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return SSD_OK;
+}
+
+// ================================================================================================
+// phase 1
+// ================================================================================================
+extern "C" int ssd_demux_device(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, size_t r2_len)
+{
+    if (!c) return SSD_EINVAL;
+    if ((r1_len && !d_r1) || (r2_len && !d_r2)) return fail(c, SSD_EINVAL, "null input pointer");
+    if (((uintptr_t)d_r1 & 15u) || ((uintptr_t)d_r2 & 15u)) return fail(c, SSD_EINVAL, "device inputs must be 16-byte aligned");
+    CU(c, cudaSetDevice(c->device));
+    c->r1 = (const uint8_t*)d_r1;
+    c->r2 = (const uint8_t*)d_r2;
+    c->r1_len = r1_len;
+    c->r2_len = r2_len;
+    c->wide = std::max(r1_len, r2_len) >= (1ull << 32);
+    c->phase1_done = c->filter_done = c->unique_done = false;
+    if (std::max(r1_len, r2_len) >= (1ull << 36)) return fail(c, SSD_EINVAL, "a batch is limited to 64 GiB per file");
+
+    const uint32_t nt1 = blocks_for(r1_len, kTile), nt2 = blocks_for(r2_len, kTile);
+    uint64_t cap = std::max(r1_len, r2_len) / (uint64_t)c->record_hint + 1024;
+    DevCounters h{};
+    for (int attempt = 0; attempt < 2; attempt++) {
+        c->rec_cap = cap;
+        OKR(ensure(c, c->b_status1, (size_t)(nt1 + 1) * 8));
+        OKR(ensure(c, c->b_status2, (size_t)(nt2 + 1) * 8));
+        OKR(ensure(c, c->b_r1_start, (cap + 1) * (c->wide ? 8 : 4)));
+        OKR(ensure(c, c->b_r1_base, cap * 4));
+        OKR(ensure(c, c->b_ann, cap * 8));
+        OKR(ensure(c, c->b_keys, cap * 8));
+        OKR(ensure(c, c->b_irr, cap * sizeof(IrrKey)));
+        CU(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(DevCounters), c->stream));
+        CU(c, cudaMemsetAsync(c->d_err_off, 0xFF, 2 * sizeof(unsigned long long), c->stream));
+        CU(c, cudaMemsetAsync(c->d_hist, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
+        CU(c, cudaMemsetAsync(c->b_status1.p, 0, (size_t)(nt1 + 1) * 8, c->stream));
+        CU(c, cudaMemsetAsync(c->b_status2.p, 0, (size_t)(nt2 + 1) * 8, c->stream));
+        OKR(c->wide ? launch_scans<uint64_t>(c) : launch_scans<uint32_t>(c));
+        OKR(fetch_counters(c, &h));
+        if (!(h.err_flags & kErrOverflow)) break;
+        if (attempt == 1) return fail(c, SSD_EINVAL, "record tables overflowed twice (internal)");
+        cap = std::max(h.n_records[0], h.n_records[1]) + 1;
+    }
+    if (h.err_flags & (kErrNoAt | kErrKey | kErrDense)) {
+        unsigned long long off[2];
+        CU(c, cudaMemcpy(off, c->d_err_off, sizeof off, cudaMemcpyDeviceToHost));
+        if (h.err_flags & kErrDense) return fail(c, SSD_EMALFORMED, "FASTQ records shorter than 16 bytes on average are not supported");
+        if (h.err_flags & kErrNoAt) {
+            int f = off[0] != ~0ull ? 0 : 1;
+            return fail(c, SSD_EMALFORMED, "read %d: record at byte %llu does not start with '@'", f + 1, off[f]);
+        }
+        std::string tok = token_at(c, c->r2, c->r2_len, off[1]);
+        return fail(c, SSD_EKEY, "%s", tok.c_str());
+    }
+    c->n_rec_r1 = h.n_records[0];
+    c->n_rec_r2 = h.n_records[1];
+    c->n_rec = std::min(c->n_rec_r1, c->n_rec_r2);
+    c->n_keys = h.n_keys;
+    c->n_irr = h.n_irr;
+    c->phase1_done = true;
+    memset(&c->stats, 0, sizeof c->stats);
+    c->stats.n_records_r1 = c->n_rec_r1;
+    c->stats.n_records_r2 = c->n_rec_r2;
+    c->stats.n_regular_keys = c->n_keys;
+    c->stats.n_irregular_keys = c->n_irr;
+    return SSD_OK;
+}
+
+// ================================================================================================
+// phase 2
+// ================================================================================================
+extern "C" int ssd_cell_space(const ssd_ctx* c, uint64_t* n)
+{
+    if (!c || !n) return SSD_EINVAL;
+    *n = c->n_cells_total;
+    return SSD_OK;
+}
+
+extern "C" int ssd_reads_histogram_device(ssd_ctx* c, uint32_t** p)
+{
+    if (!c || !p) return SSD_EINVAL;
+    *p = c->d_hist;
+    return SSD_OK;
+}
+
+extern "C" int ssd_distinct_histogram_device(ssd_ctx* c, uint32_t** p)
+{
+    if (!c || !p) return SSD_EINVAL;
+    *p = c->d_distinct;
+    return SSD_OK;
+}
+
+extern "C" int ssd_key_layout(const ssd_ctx* c, int* umi_bits, int* cell_bits)
+{
+    if (!c) return SSD_EINVAL;
+    if (umi_bits) *umi_bits = c->dcfg.umi_bits;
+    if (cell_bits) *cell_bits = c->dcfg.cell_bits;
+    return SSD_OK;
+}
+
+extern "C" int ssd_local_unique_keys(ssd_ctx* c, uint64_t** d_keys, uint64_t* n_keys, void** d_irregular, uint64_t* n_irregular)
+{
+    if (!c) return SSD_EINVAL;
+    if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_local_unique_keys before ssd_demux_device");
+    CU(c, cudaSetDevice(c->device));
+    if (!c->unique_done) {
+        OKR(sort_unique64(c, (uint64_t*)c->b_keys.p, c->n_keys, &c->uniq_keys, &c->n_uniq));
+        OKR(sort_unique_irr(c, (IrrKey*)c->b_irr.p, c->n_irr, &c->uniq_irr, &c->n_uniq_irr));
+        c->unique_done = true;
+    }
+    if (d_keys) *d_keys = c->uniq_keys;
+    if (n_keys) *n_keys = c->n_uniq;
+    if (d_irregular) *d_irregular = c->uniq_irr;
+    if (n_irregular) *n_irregular = c->n_uniq_irr;
+    return SSD_OK;
+}
+
+extern "C" int ssd_count_distinct(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys, void* d_irregular, uint64_t n_irregular)
+{
+    if (!c) return SSD_EINVAL;
+    CU(c, cudaSetDevice(c->device));
+    uint64_t *uk = nullptr, nuk = 0, nui = 0;
+    IrrKey* ui = nullptr;
+    if (c->unique_done && d_keys == c->uniq_keys && n_keys == c->n_uniq && d_irregular == (void*)c->uniq_irr && n_irregular == c->n_uniq_irr) {
+        uk = c->uniq_keys;  // already sorted and unique: only count
+        nuk = c->n_uniq;
+        ui = c->uniq_irr;
+        nui = c->n_uniq_irr;
+    } else {
+        c->unique_done = false;  // the context's buffers are reused as scratch below
+        OKR(sort_unique64(c, d_keys, n_keys, &uk, &nuk));
+        OKR(sort_unique_irr(c, (IrrKey*)d_irregular, n_irregular, &ui, &nui));
+    }
+    return count_cells(c, uk, nuk, ui, nui);
+}
+
+extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
+{
+    if (!c) return SSD_EINVAL;
+    if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_build_filter before ssd_demux_device");
+    CU(c, cudaSetDevice(c->device));
+    DevCounters h{};
+    CU(c, cudaMemsetAsync((char*)c->d_cnt + offsetof(DevCounters, n_matched), 0, 6 * sizeof(unsigned long long), c->stream));
+    const uint32_t nbc = blocks_for(c->n_cells_total, kThreads);
+    k_filter<<<nbc, kThreads, 0, c->stream>>>(c->d_hist, c->d_distinct, c->n_cells_total, (long long)c->cfg.min_count, c->cfg.filter_mode, c->d_pass,
+                                              c->d_cnt);
+    if (c->cfg.collapse_pairs > 0) k_collapse_map<<<nbc, kThreads, 0, c->stream>>>(c->d_pass, c->dcfg.n_wl, c->cfg.collapse_pairs, c->d_remap);
+    if (c->n_rec)
+        k_plan_totals<<<blocks_for(c->n_rec, kThreads), kThreads, 0, c->stream>>>(make_outlen(c, SSD_EMIT_MATCHED), make_outlen(c, SSD_EMIT_PASSING),
+                                                                                 c->n_rec, c->d_cnt);
+    CU(c, cudaGetLastError());
+    OKR(fetch_counters(c, &h));
+    c->stats.n_matched = h.n_matched;
+    c->stats.n_cells = h.n_cells;
+    c->stats.n_passing_cells = h.n_passing_cells;
+    c->stats.n_retained = h.n_retained;
+    c->stats.bytes_matched = h.bytes_matched;
+    c->stats.bytes_passing = h.bytes_passing;
+    c->filter_done = true;
+    if (stats) *stats = c->stats;
+    return SSD_OK;
+}
+
+extern "C" int ssd_filter_single(ssd_ctx* c, ssd_stats* stats)
+{
+    if (!c) return SSD_EINVAL;
+    if (c->cfg.filter_mode == SSD_FILTER_DISTINCT_UMI) {
+        uint64_t *k = nullptr, nk = 0, ni = 0;
+        void* ik = nullptr;
+        OKR(ssd_local_unique_keys(c, &k, &nk, &ik, &ni));
+        OKR(ssd_count_distinct(c, k, nk, ik, ni));
+    }
+    return ssd_build_filter(c, stats);
+}
+
+// ================================================================================================
+// phase 3
+// ================================================================================================
+extern "C" int ssd_emit_device(ssd_ctx* c, int which, void* d_out, size_t cap, size_t* written)
+{
+    if (!c) return SSD_EINVAL;
+    if (!c->filter_done) return fail(c, SSD_ESTATE, "ssd_emit_device before ssd_build_filter");
+    if (which != SSD_EMIT_MATCHED && which != SSD_EMIT_PASSING) return fail(c, SSD_EINVAL, "unknown output selector");
+    CU(c, cudaSetDevice(c->device));
+    const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
+    if (written) *written = (size_t)need;
+    if (need > cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, cap);
+    if (need == 0) return SSD_OK;
+    if (!d_out) return fail(c, SSD_EINVAL, "null output pointer");
+    OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
+    OKR(exclusive_scan<uint64_t>(c, make_outlen(c, which), c->n_rec, (uint64_t*)c->b_out_off.p));
+    OKR(c->wide ? launch_emit<uint64_t>(c, which, (uint8_t*)d_out) : launch_emit<uint32_t>(c, which, (uint8_t*)d_out));
+    DevCounters h{};
+    OKR(fetch_counters(c, &h));
+    if (h.err_flags & kErrEmitLen) return fail(c, SSD_ECUDA, "internal: emitted record length differs from the planned length");
+    return SSD_OK;
+}
+
+extern "C" size_t ssd_output_bound(const ssd_ctx* c, size_t r1_len, size_t r2_len)
+{
+    (void)c;
+    (void)r2_len;
+    return r1_len + 48 * (r1_len / 16 + 1);
+}
+
+extern "C" int ssd_host_alloc(void** p, size_t bytes)
+{
+    if (!p) return SSD_EINVAL;
+    return cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? SSD_OK : SSD_ENOMEM;
+}
+
+extern "C" int ssd_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? SSD_OK : SSD_ECUDA; }
+
+extern "C" int ssd_emit_host(ssd_ctx* c, int which, void* out, size_t out_cap, size_t* written)
+{
+    if (!c) return SSD_EINVAL;
+    if (!c->filter_done) return fail(c, SSD_ESTATE, "ssd_emit_host before the filter was built");
+    const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
+    if (written) *written = (size_t)need;
+    if (need > out_cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, out_cap);
+    if (!need) return SSD_OK;
+    OKR(ensure(c, c->b_out, need + 32));
+    OKR(ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, nullptr));
+    CU(c, cudaMemcpyAsync(out, c->b_out.p, need, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SSD_OK;
+}
+
+extern "C" int ssd_run_host(ssd_ctx* c, const void* r1, size_t r1_len, const void* r2, size_t r2_len, int which, void* out, size_t out_cap,
+                            size_t* written, ssd_stats* stats)
+{
+    if (!c) return SSD_EINVAL;
+    CU(c, cudaSetDevice(c->device));
+    OKR(ensure(c, c->b_in1, r1_len + 32));
+    OKR(ensure(c, c->b_in2, r2_len + 32));
+    // chunked so that a pageable source does not stall the whole transfer behind one staging copy
+    const size_t chunk = (size_t)64 << 20;
+    for (size_t o = 0; o < r1_len; o += chunk)
+        CU(c, cudaMemcpyAsync((uint8_t*)c->b_in1.p + o, (const uint8_t*)r1 + o, std::min(chunk, r1_len - o), cudaMemcpyHostToDevice, c->stream));
+    for (size_t o = 0; o < r2_len; o += chunk)
+        CU(c, cudaMemcpyAsync((uint8_t*)c->b_in2.p + o, (const uint8_t*)r2 + o, std::min(chunk, r2_len - o), cudaMemcpyHostToDevice, c->stream));
+    OKR(ssd_demux_device(c, c->b_in1.p, r1_len, c->b_in2.p, r2_len));
+    OKR(ssd_filter_single(c, stats));
+    if (!out && !out_cap) {
+        if (written) *written = (size_t)(which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing);
+        return SSD_OK;
+    }
+    return ssd_emit_host(c, which, out, out_cap, written);
+}
+
+extern "C" int ssd_record_cells(ssd_ctx* c, int32_t* cells_host, uint64_t capacity, uint64_t* n_records)
+{
+    if (!c) return SSD_EINVAL;
+    if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_record_cells before ssd_demux_device");
+    if (n_records) *n_records = c->n_rec_r2;
+    if (!cells_host) return SSD_OK;
+    if (capacity < c->n_rec_r2) return fail(c, SSD_ERANGE, "need room for %llu records", (unsigned long long)c->n_rec_r2);
+    if (!c->n_rec_r2) return SSD_OK;
+    CU(c, cudaSetDevice(c->device));
+    OKR(ensure(c, c->b_cells, c->n_rec_r2 * sizeof(int32_t)));
+    k_record_cells<<<blocks_for(c->n_rec_r2, kThreads), kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, c->n_rec_r2, (int32_t*)c->b_cells.p);
+    CU(c, cudaMemcpyAsync(cells_host, c->b_cells.p, c->n_rec_r2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SSD_OK;
+}
+
+// ================================================================================================
+// synthetic read pairs
+// ================================================================================================
+namespace {
+
+struct SynthPrep {
+    ssd_synth::Params p;
+    std::vector<char> ties;
+};
+
+int synth_prepare(const ssd_synth_spec* s, SynthPrep& out)
+{
+    if (!s || s->struct_size != sizeof(ssd_synth_spec) || !s->whitelist || s->n_whitelist < 1 || s->n_whitelist > SSD_MAX_WHITELIST) return SSD_EINVAL;
+    if (s->read_len < 94 || s->read_len > 1000 || s->cell_pool < 1) return SSD_EINVAL;
+    ssd_synth::Params& p = out.p;
+    p.seed = s->seed;
+    p.read_len = s->read_len;
+    p.n_wl = s->n_whitelist;
+    p.cell_pool = s->cell_pool;
+    p.cell_octaves = 1;
+    while ((1ull << p.cell_octaves) <= s->cell_pool) p.cell_octaves++;
+    p.p_sub = s->p_sub_ppm;
+    p.p_n = s->p_n_ppm;
+    p.p_junk = s->p_junk_ppm;
+    p.p_dup = s->p_dup_umi_ppm;
+    p.p_tie = s->p_tie_ppm;
+    p.p_trunc = s->p_trunc_ppm;
+    p.p_atqual = s->p_atqual_ppm;
+    // midpoints of whitelist pairs at distance exactly 4: two of the differing positions taken from b
+    out.ties.clear();
+    for (int a = 0; a < s->n_whitelist && out.ties.size() < 8 * 512; a++)
+        for (int b = a + 1; b < s->n_whitelist && out.ties.size() < 8 * 512; b++) {
+            const char *x = s->whitelist + 8 * a, *y = s->whitelist + 8 * b;
+            int diff[8], nd = 0;
+            for (int j = 0; j < 8; j++)
+                if (x[j] != y[j]) diff[nd++] = j;
+            if (nd != 4) continue;
+            char t[8];
+            memcpy(t, x, 8);
+            t[diff[0]] = y[diff[0]];
+            t[diff[2]] = y[diff[2]];
+            out.ties.insert(out.ties.end(), t, t + 8);
+        }
+    p.n_ties = (uint32_t)(out.ties.size() / 8);
+    return SSD_OK;
+}
+
+struct SynthLen {
+    ssd_synth::Params p;
+    uint64_t first;
+    int mate;
+    __device__ __forceinline__ uint32_t operator()(uint64_t k) const
+    {
+        return mate == 1 ? ssd_synth::r1_record_len(p, first + k) : ssd_synth::r2_record_len(p, first + k);
+    }
+};
+
+__global__ void __launch_bounds__(kThreads) k_synth_write(ssd_synth::Params p, uint64_t first, uint64_t n, const uint64_t* off1, const uint64_t* off2,
+                                                          const char* wl, const char* ties, uint8_t* r1, uint8_t* r2)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t k = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    if (k >= n) return;
+    const uint64_t i = first + k;
+    {
+        uint8_t* dst = r1 + off1[k];
+        const uint32_t len = (uint32_t)(off1[k + 1] - off1[k]);
+        for (uint32_t b = lane; b < len; b += 32) dst[b] = (uint8_t)ssd_synth::r1_byte(p, i, b);
+    }
+    {
+        ssd_synth::R2Plan pl = ssd_synth::plan_r2(p, i, wl, ties);
+        uint8_t* dst = r2 + off2[k];
+        const uint32_t len = (uint32_t)(off2[k + 1] - off2[k]);
+        for (uint32_t b = lane; b < len; b += 32) dst[b] = (uint8_t)ssd_synth::r2_byte(p, i, pl, b);
+    }
+}
+
+}  // namespace
+
+extern "C" int ssd_synth_sizes(const ssd_synth_spec* spec, uint64_t* r1_bytes, uint64_t* r2_bytes)
+{
+    SynthPrep sp;
+    if (synth_prepare(spec, sp) != SSD_OK) return SSD_EINVAL;
+    uint64_t a = 0, b = 0;
+    for (uint64_t k = 0; k < spec->n_pairs; k++) {
+        a += ssd_synth::r1_record_len(sp.p, spec->first_index + k);
+        b += ssd_synth::r2_record_len(sp.p, spec->first_index + k);
+    }
+    if (r1_bytes) *r1_bytes = a;
+    if (r2_bytes) *r2_bytes = b;
+    return SSD_OK;
+}
+
+extern "C" int ssd_synth_generate_host(const ssd_synth_spec* spec, void* r1, void* r2)
+{
+    SynthPrep sp;
+    if (synth_prepare(spec, sp) != SSD_OK || !r1 || !r2) return SSD_EINVAL;
+    char *o1 = (char*)r1, *o2 = (char*)r2;
+    for (uint64_t k = 0; k < spec->n_pairs; k++) {
+        const uint64_t i = spec->first_index + k;
+        uint32_t l1 = ssd_synth::r1_record_len(sp.p, i);
+        for (uint32_t b = 0; b < l1; b++) *o1++ = ssd_synth::r1_byte(sp.p, i, b);
+        ssd_synth::R2Plan pl = ssd_synth::plan_r2(sp.p, i, spec->whitelist, sp.ties.data());
+        uint32_t l2 = ssd_synth::r2_record_len(sp.p, i);
+        for (uint32_t b = 0; b < l2; b++) *o2++ = ssd_synth::r2_byte(sp.p, i, pl, b);
+    }
+    return SSD_OK;
+}
+
+extern "C" int ssd_synth_generate_device(ssd_ctx* c, const ssd_synth_spec* spec, void* d_r1, void* d_r2)
+{
+    if (!c) return SSD_EINVAL;
+    SynthPrep sp;
+    if (synth_prepare(spec, sp) != SSD_OK || !d_r1 || !d_r2) return fail(c, SSD_EINVAL, "bad synthetic spec");
+    CU(c, cudaSetDevice(c->device));
+    const uint64_t n = spec->n_pairs;
+    if (!n) return SSD_OK;
+    DevBuf off1, off2, tab;
+    int rc = SSD_OK;
+    do {
+        if ((rc = ensure(c, off1, (n + 1) * 8)) != SSD_OK) break;
+        if ((rc = ensure(c, off2, (n + 1) * 8)) != SSD_OK) break;
+        const size_t wl_bytes = (size_t)spec->n_whitelist * 8, tie_bytes = sp.ties.size();
+        if ((rc = ensure(c, tab, wl_bytes + tie_bytes + 16)) != SSD_OK) break;
+        cudaMemcpyAsync(tab.p, spec->whitelist, wl_bytes, cudaMemcpyHostToDevice, c->stream);
+        if (tie_bytes) cudaMemcpyAsync((char*)tab.p + wl_bytes, sp.ties.data(), tie_bytes, cudaMemcpyHostToDevice, c->stream);
+        if ((rc = exclusive_scan<uint64_t>(c, SynthLen{sp.p, spec->first_index, 1}, n, (uint64_t*)off1.p)) != SSD_OK) break;
+        if ((rc = exclusive_scan<uint64_t>(c, SynthLen{sp.p, spec->first_index, 2}, n, (uint64_t*)off2.p)) != SSD_OK) break;
+        k_synth_write<<<blocks_for(n * 32, kThreads), kThreads, 0, c->stream>>>(sp.p, spec->first_index, n, (const uint64_t*)off1.p, (const uint64_t*)off2.p,
+                                                                              (const char*)tab.p, (const char*)tab.p + wl_bytes, (uint8_t*)d_r1, (uint8_t*)d_r2);
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, SSD_ECUDA, "synthetic generation failed");
+    } while (0);
+    release(off1);
+    release(off2);
+    release(tab);
+    return rc;
+}

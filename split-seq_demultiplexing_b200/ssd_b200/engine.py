@@ -1,0 +1,241 @@
+"""Host-side driver of the B200 demultiplexer: owns a library context, moves buffers, maps library
+error codes onto the exception types the reference raises."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from . import _lib as L
+
+DEFAULT_POSITIONS = {"umi": (0, 10), "bc3": (10, 18), "bc2": (48, 56), "bc1": (86, 94)}  # V2:155-162
+
+
+class MalformedFastq(ValueError):
+    pass
+
+
+def _raise(code: int, msg: str):
+    if code == L.EKEY:
+        raise KeyError(msg)                       # V2:350
+    if code == L.EMALFORMED:
+        raise MalformedFastq(msg)
+    if code == L.EINVAL:
+        raise ValueError(msg)
+    if code == L.ENOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError("libssd_b200 error %d: %s" % (code, msg))
+
+
+class _DevArray:
+    """Zero-copy view of library-owned device memory for torch.as_tensor()."""
+
+    def __init__(self, ptr: int, n: int, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+        self._owner = owner
+
+
+class Demultiplexer:
+    """One library context = one GPU.  Mirrors the knobs of V2.demultiplex_fun / calc_demux_results."""
+
+    def __init__(self, whitelist: Sequence[str], errors: int = 1, min_count: int = 10,
+                 positions: Optional[Dict[str, Tuple[int, int]]] = None, filter_mode: str = "distinct_umi",
+                 collapse_pairs: int = 0, device: Optional[int] = None, record_bytes_hint: int = 0):
+        self.lib = L.load()
+        pos = dict(DEFAULT_POSITIONS)
+        if positions:
+            pos.update(positions)
+        for k, (a, b) in pos.items():
+            if a < 0 or b < a:
+                raise ValueError("slice %s=%d:%d is outside the supported contract (0 <= start <= end)" % (k, a, b))
+        self.whitelist = [w if isinstance(w, str) else w.decode() for w in whitelist]
+        self.positions = pos
+        raw = b"".join(w.encode().ljust(8, b"\0")[:8] for w in self.whitelist)
+        lens = (C.c_uint8 * len(self.whitelist))(*[min(len(w), 8) for w in self.whitelist])
+        cfg = L.Config()
+        cfg.struct_size = C.sizeof(L.Config)
+        cfg.device = -1 if device is None else int(device)
+        cfg.n_whitelist = len(self.whitelist)
+        cfg.whitelist = raw
+        cfg.whitelist_len = lens
+        cfg.umi_start, cfg.umi_end = pos["umi"]
+        cfg.bc1_start, cfg.bc1_end = pos["bc1"]
+        cfg.bc2_start, cfg.bc2_end = pos["bc2"]
+        cfg.bc3_start, cfg.bc3_end = pos["bc3"]
+        cfg.errors = int(errors)
+        cfg.min_count = int(min_count)
+        cfg.filter_mode = {"distinct_umi": L.FILTER_DISTINCT_UMI, "reads": L.FILTER_READS}[filter_mode]
+        cfg.collapse_pairs = int(collapse_pairs)
+        cfg.record_bytes_hint = int(record_bytes_hint)
+        self.filter_mode = filter_mode
+        self._ctx = C.c_void_p()
+        rc = self.lib.ssd_create(C.byref(cfg), C.byref(self._ctx))
+        if rc != L.OK:
+            self._ctx = C.c_void_p()
+            _raise(rc, self.lib.ssd_last_error(None).decode(errors="replace"))
+        n = C.c_uint64()
+        self.lib.ssd_cell_space(self._ctx, C.byref(n))
+        self.n_cells_total = n.value
+        ub, cb = C.c_int(), C.c_int()
+        self.lib.ssd_key_layout(self._ctx, C.byref(ub), C.byref(cb))
+        self.umi_bits, self.cell_bits = ub.value, cb.value
+        self._keep = []  # device tensors the current batch reads from
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.ssd_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _check(self, rc: int):
+        if rc != L.OK:
+            _raise(rc, self.lib.ssd_last_error(self._ctx).decode(errors="replace"))
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.ssd_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def cell_string(self, cell: int) -> str:
+        n = len(self.whitelist)
+        return self.whitelist[cell // (n * n)] + self.whitelist[(cell // n) % n] + self.whitelist[cell % n]
+
+    # -- phases on device-resident inputs ---------------------------------------------------------
+    def demux_device(self, r1_ptr: int, r1_len: int, r2_ptr: int, r2_len: int, keep=()):
+        """Phase 1 (V2:207-358).  `keep` holds whatever owns the device memory, until the next batch."""
+        self._keep = list(keep)
+        self._check(self.lib.ssd_demux_device(self._ctx, C.c_void_p(r1_ptr), r1_len, C.c_void_p(r2_ptr), r2_len))
+
+    def reads_histogram(self):
+        import torch
+        p = C.c_void_p()
+        self._check(self.lib.ssd_reads_histogram_device(self._ctx, C.byref(p)))
+        return torch.as_tensor(_DevArray(p.value, self.n_cells_total, "<i4", self), device="cuda")
+
+    def distinct_histogram(self):
+        import torch
+        p = C.c_void_p()
+        self._check(self.lib.ssd_distinct_histogram_device(self._ctx, C.byref(p)))
+        return torch.as_tensor(_DevArray(p.value, self.n_cells_total, "<i4", self), device="cuda")
+
+    def local_unique_keys(self):
+        """Sorted unique (cell,UMI) keys of this batch as torch views: int64[n] and int64[n_irr, 2]."""
+        import torch
+        pk, pi, nk, ni = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.ssd_local_unique_keys(self._ctx, C.byref(pk), C.byref(nk), C.byref(pi), C.byref(ni)))
+        keys = torch.as_tensor(_DevArray(pk.value, nk.value, "<i8", self), device="cuda") if nk.value else torch.empty(0, dtype=torch.int64, device="cuda")
+        irr = (torch.as_tensor(_DevArray(pi.value, 2 * ni.value, "<i8", self), device="cuda").view(-1, 2)
+               if ni.value else torch.empty((0, 2), dtype=torch.int64, device="cuda"))
+        return keys, irr
+
+    def count_distinct(self, keys, irr):
+        """Per-cell distinct counts from int64 key tensors (any order, duplicates allowed; reordered in place)."""
+        self._check(self.lib.ssd_count_distinct(self._ctx, C.c_void_p(keys.data_ptr() if keys.numel() else 0), keys.numel(),
+                                                C.c_void_p(irr.data_ptr() if irr.numel() else 0), irr.numel() // 2))
+
+    def build_filter(self) -> dict:
+        st = L.Stats()
+        self._check(self.lib.ssd_build_filter(self._ctx, C.byref(st)))
+        return st.as_dict()
+
+    def filter_single(self) -> dict:
+        st = L.Stats()
+        self._check(self.lib.ssd_filter_single(self._ctx, C.byref(st)))
+        return st.as_dict()
+
+    def emit_device(self, which: int, out_ptr: int, cap: int) -> int:
+        n = C.c_size_t()
+        self._check(self.lib.ssd_emit_device(self._ctx, which, C.c_void_p(out_ptr), cap, C.byref(n)))
+        return n.value
+
+    def record_cells(self):
+        import numpy as np
+        n = C.c_uint64()
+        self._check(self.lib.ssd_record_cells(self._ctx, None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            self._check(self.lib.ssd_record_cells(self._ctx, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return out
+
+    # -- whole pipeline ---------------------------------------------------------------------------
+    def run_device(self, r1, r2, which: int = L.EMIT_PASSING):
+        """r1/r2: torch uint8 CUDA tensors holding the two files.  Returns (uint8 CUDA tensor, stats)."""
+        import torch
+        self.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.demux_device(r1.data_ptr(), r1.numel(), r2.data_ptr(), r2.numel(), keep=(r1, r2))
+        stats = self.filter_single()
+        need = stats["bytes_matched"] if which == L.EMIT_MATCHED else stats["bytes_passing"]
+        out = torch.empty(need + 16, dtype=torch.uint8, device=r1.device)
+        n = self.emit_device(which, out.data_ptr(), out.numel())
+        return out[:n], stats
+
+    def run_host(self, r1, r2, which: int = L.EMIT_PASSING, out=None):
+        """r1/r2: objects exposing the buffer protocol (bytes, numpy, pinned torch .numpy()).
+        Returns (bytes-like numpy uint8 array, stats).  H2D and D2H copies happen inside the library."""
+        import numpy as np
+        a1 = np.frombuffer(r1, dtype=np.uint8) if not isinstance(r1, np.ndarray) else r1
+        a2 = np.frombuffer(r2, dtype=np.uint8) if not isinstance(r2, np.ndarray) else r2
+        st = L.Stats()
+        n = C.c_size_t()
+        self._check(self.lib.ssd_run_host(self._ctx, a1.ctypes.data_as(C.c_void_p), a1.size, a2.ctypes.data_as(C.c_void_p), a2.size,
+                                          which, None, 0, C.byref(n), C.byref(st)))
+        if out is None or out.size < n.value:
+            out = np.empty(n.value, dtype=np.uint8)
+        if n.value:
+            self._check(self.lib.ssd_emit_host(self._ctx, which, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)))
+        return out[: n.value], st.as_dict()
+
+    def cell_table(self) -> Dict[str, Tuple[int, int]]:
+        """{cell string: (reads, distinct UMIs)} for every detected cell (small outputs / tests)."""
+        hist = self.reads_histogram().cpu().numpy()
+        dist = self.distinct_histogram().cpu().numpy()
+        import numpy as np
+        return {self.cell_string(int(c)): (int(hist[c]), int(dist[c])) for c in np.nonzero(hist)[0]}
+
+
+def synth_spec(whitelist: Sequence[str], n_pairs: int, seed: int = 0x5EED0001, first_index: int = 1, read_len: int = 150,
+               cell_pool: int = 100000, p_sub: float = 0.01, p_n: float = 0.002, p_junk: float = 0.10, p_dup_umi: float = 0.05,
+               p_tie: float = 0.0, p_trunc: float = 0.0, p_atqual: float = 0.02):
+    """ssd_synth_spec for the synthetic read pairs of SURVEY.md 8d."""
+    raw = b"".join(w.encode()[:8] for w in whitelist)
+    s = L.SynthSpec()
+    s.struct_size = C.sizeof(L.SynthSpec)
+    s.seed, s.first_index, s.n_pairs, s.read_len = seed, first_index, n_pairs, read_len
+    s.n_whitelist, s.whitelist, s.cell_pool = len(whitelist), raw, cell_pool
+    ppm = lambda p: int(round(p * 1e6))  # noqa: E731
+    s.p_sub_ppm, s.p_n_ppm, s.p_junk_ppm, s.p_dup_umi_ppm = ppm(p_sub), ppm(p_n), ppm(p_junk), ppm(p_dup_umi)
+    s.p_tie_ppm, s.p_trunc_ppm, s.p_atqual_ppm = ppm(p_tie), ppm(p_trunc), ppm(p_atqual)
+    s._keep = raw
+    return s
+
+
+def synth_sizes(spec) -> Tuple[int, int]:
+    a, b = C.c_uint64(), C.c_uint64()
+    rc = L.load().ssd_synth_sizes(C.byref(spec), C.byref(a), C.byref(b))
+    if rc != L.OK:
+        raise ValueError("bad synthetic spec")
+    return a.value, b.value
+
+
+def synth_host(spec) -> Tuple[bytes, bytes]:
+    """CPU twin of the device generator (same bytes)."""
+    n1, n2 = synth_sizes(spec)
+    b1, b2 = C.create_string_buffer(n1 + 1), C.create_string_buffer(n2 + 1)
+    rc = L.load().ssd_synth_generate_host(C.byref(spec), b1, b2)
+    if rc != L.OK:
+        raise ValueError("bad synthetic spec")
+    return b1.raw[:n1], b2.raw[:n2]
+
+
+def synth_device(dm: Demultiplexer, spec):
+    """Generate on dm's GPU; returns two uint8 CUDA tensors."""
+    import torch
+    n1, n2 = synth_sizes(spec)
+    t1 = torch.empty(n1 + 16, dtype=torch.uint8, device="cuda")
+    t2 = torch.empty(n2 + 16, dtype=torch.uint8, device="cuda")
+    rc = dm.lib.ssd_synth_generate_device(dm._ctx, C.byref(spec), C.c_void_p(t1.data_ptr()), C.c_void_p(t2.data_ptr()))
+    dm._check(rc)
+    return t1[:n1], t2[:n2]

@@ -1,0 +1,232 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle and the
+golden vectors of the reference.  Bit-exact on the canonical (sorted-record) form, on the per-cell
+counts and on the per-record cell ids."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import fastq_util as fu
+
+pytestmark = pytest.mark.gpu
+
+WL = fu.load_whitelist()
+
+
+@pytest.fixture(scope="module")
+def ssd():
+    import ssd_b200
+    return ssd_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import ssd_oracle_py
+    return ssd_oracle_py
+
+
+@pytest.fixture(scope="module")
+def bundled():
+    return fu.load_bundled()
+
+
+@pytest.fixture(scope="module")
+def digests():
+    with open(os.path.join(fu.GOLDEN_DIR, "bundled_digests.json")) as fh:
+        return json.load(fh)
+
+
+def run_both(ssd, r1, r2, e, m, **kw):
+    dm = ssd.Demultiplexer(WL, errors=e, min_count=m, **kw)
+    passing, stats = dm.run_host(r1, r2, ssd.EMIT_PASSING)
+    merged = np.empty(stats["bytes_matched"], dtype=np.uint8)
+    import ctypes as C
+    n = C.c_size_t()
+    if merged.size:
+        dm._check(dm.lib.ssd_emit_host(dm._ctx, ssd.EMIT_MATCHED, merged.ctypes.data_as(C.c_void_p), merged.size, C.byref(n)))
+    return dm, merged.tobytes(), passing.tobytes(), stats
+
+
+def table_bytes(dm):
+    return b"".join(b"%s\t%d\t%d\n" % (c.encode(), v[0], v[1]) for c, v in sorted(dm.cell_table().items()))
+
+
+@pytest.mark.parametrize("e", [0, 1, 2, 3])
+@pytest.mark.parametrize("m", [1, 10])
+def test_bundled_digests(ssd, bundled, digests, e, m):
+    gold = digests["e%d_m%d" % (e, m)]
+    dm, merged, passing, stats = run_both(ssd, bundled[0], bundled[1], e, m)
+    assert stats["n_records_r1"] == stats["n_records_r2"] == 5000
+    assert (stats["n_matched"], stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]) == (
+        gold["matched"], gold["cells"], gold["passing_cells"], gold["retained"])
+    assert len(merged) == stats["bytes_matched"] and len(passing) == stats["bytes_passing"]
+    assert fu.canonical_sha(merged) == gold["merged1_sha"]
+    assert fu.canonical_sha(passing) == gold["passing_sha"]
+    assert hashlib.sha256(table_bytes(dm)).hexdigest() == gold["counts_sha"]
+
+
+def test_bundled_order_is_input_order(ssd, orc, bundled):
+    # the reference's order is arbitrary (set iteration); ours is the input order, like the oracle's
+    _, merged, passing, _ = run_both(ssd, bundled[0], bundled[1], 1, 10)
+    ref = orc.demultiplex(bundled[0], bundled[1], WL, 1, 10)
+    assert merged == ref.merged1
+    assert passing == ref.passing
+
+
+def test_record_cells(ssd, orc, bundled):
+    dm, _, _, _ = run_both(ssd, bundled[0], bundled[1], 2, 1)
+    ref = orc.demultiplex(bundled[0], bundled[1], WL, 2, 1)
+    assert dm.record_cells().tolist() == ref.rec_cell
+
+
+RULES = fu.load_json_gz("rule_cases.json.gz")
+
+
+@pytest.mark.parametrize("case", RULES, ids=["%s-e%d" % (c["name"], c["e"]) for c in RULES])
+def test_rule_cases(ssd, case):
+    r1, r2 = case["r1"].encode(), case["r2"].encode()
+    if "error" in case:
+        with pytest.raises(KeyError) as ei:
+            run_both(ssd, r1, r2, case["e"], case["m"])
+        assert ei.value.args[0] == case["error_arg"].strip("'")
+        return
+    dm, merged, passing, stats = run_both(ssd, r1, r2, case["e"], case["m"])
+    assert fu.canonical(merged).decode() == case["merged1"]
+    assert fu.canonical(passing).decode() == case["passing"]
+    assert case["stdout_tail"][0].endswith(" %d" % stats["n_cells"])
+    assert case["stdout_tail"][1].endswith(" %d" % stats["n_passing_cells"])
+
+
+ADV = fu.load_json_gz("adversarial.json.gz")
+
+
+@pytest.mark.parametrize("g", ADV, ids=["%s-e%d-m%d" % (g["name"], g["e"], g["m"]) for g in ADV])
+def test_adversarial(ssd, g):
+    r1, r2 = fu.make_pairs(g["seed"], g["n"], WL, **g["kwargs"])
+    dm, merged, passing, stats = run_both(ssd, r1, r2, g["e"], g["m"])
+    assert (stats["n_matched"], stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]) == (
+        g["matched"], g["cells"], g["passing_cells"], g["retained"])
+    assert fu.canonical_sha(merged) == g["merged1_sha"]
+    assert fu.canonical_sha(passing) == g["passing_sha"]
+    assert table_bytes(dm).decode() == g["counts_table"]
+
+
+@pytest.mark.parametrize("e,m,kw", [
+    (1, 10, {}),
+    (0, 3, {"p_n": 0.02}),
+    (2, 5, {"p_tie": 0.05, "p_trunc": 0.02, "p_n": 0.01}),
+    (3, 2, {"p_sub": 0.05, "p_junk": 0.3, "cell_pool": 300}),
+])
+def test_synthetic_vs_oracle(ssd, orc, e, m, kw):
+    spec = ssd.synth_spec(WL, 30000, seed=0xABC0 + e, cell_pool=kw.pop("cell_pool", 2000), **kw)
+    r1, r2 = ssd.synth_host(spec)
+    dm, merged, passing, stats = run_both(ssd, r1, r2, e, m)
+    ref = orc.demultiplex(r1, r2, WL, e, m)
+    assert dm.record_cells().tolist() == ref.rec_cell
+    assert merged == ref.merged1
+    assert passing == ref.passing
+    assert (stats["n_matched"], stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]) == (
+        ref.n_matched, ref.n_cells, ref.n_passing_cells, ref.n_retained)
+    want = {c.decode(): (v[0], v[1]) for c, v in ref.cells.items()}
+    assert dm.cell_table() == want
+
+
+def test_device_generator_matches_host_twin(ssd):
+    import torch
+    spec = ssd.synth_spec(WL, 5000, seed=77, first_index=999990, p_tie=0.02, p_trunc=0.02)
+    h1, h2 = ssd.synth_host(spec)
+    dm = ssd.Demultiplexer(WL)
+    d1, d2 = ssd.synth_device(dm, spec)
+    torch.cuda.synchronize()
+    assert d1.cpu().numpy().tobytes() == h1
+    assert d2.cpu().numpy().tobytes() == h2
+
+
+def test_device_resident_path_1m(ssd, orc):
+    """1 M synthetic pairs generated on the device, demultiplexed device-resident, checked record for record."""
+    import torch
+    spec = ssd.synth_spec(WL, 1_000_000, seed=0x5EED0001, cell_pool=20000)
+    dm = ssd.Demultiplexer(WL, errors=1, min_count=10)
+    d1, d2 = ssd.synth_device(dm, spec)
+    out, stats = dm.run_device(d1, d2, ssd.EMIT_PASSING)
+    torch.cuda.synchronize()
+    r1, r2 = d1.cpu().numpy().tobytes(), d2.cpu().numpy().tobytes()
+    ref = orc.demultiplex(r1, r2, WL, 1, 10)
+    assert (stats["n_matched"], stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]) == (
+        ref.n_matched, ref.n_cells, ref.n_passing_cells, ref.n_retained)
+    assert hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest() == hashlib.sha256(ref.passing).hexdigest()
+    assert dm.record_cells().tolist() == ref.rec_cell
+
+
+def test_reads_filter_mode(ssd, orc):
+    # SSD_FILTER_READS keeps cells with >= m READS (the north_star histogram filter); V2 counts distinct UMIs
+    spec = ssd.synth_spec(WL, 20000, seed=5, cell_pool=300, p_dup_umi=0.6)
+    r1, r2 = ssd.synth_host(spec)
+    ref = orc.demultiplex(r1, r2, WL, 1, 8)
+    dm, merged, passing, stats = run_both(ssd, r1, r2, 1, 8, filter_mode="reads")
+    keep = {c for c, v in ref.cells.items() if v[0] >= 8}
+    want = [r for r in fu.records(ref.merged1) if r.split(b"\n", 1)[0].split(b"_")[1] in keep]
+    assert fu.records(passing) == want
+    assert stats["n_passing_cells"] == len(keep)
+    assert len(keep) != ref.n_passing_cells  # the two semantics differ on this input
+
+
+def test_collapse(ssd, orc):
+    # Collapse_RanHex_Odt.py:44-71: RanHex (idx 48+k) folds into OligoDT (idx k) when both cells pass
+    spec = ssd.synth_spec(WL, 40000, seed=9, cell_pool=40)
+    r1, r2 = ssd.synth_host(spec)
+    ref = orc.demultiplex(r1, r2, WL, 1, 5)
+    n = len(WL)
+    idx = {w: i for i, w in enumerate(WL)}
+    present = bytearray(n * n * n)
+    for c, v in ref.cells.items():
+        if v[2]:
+            s = c.decode()
+            present[(idx[s[0:8]] * n + idx[s[8:16]]) * n + idx[s[16:24]]] = 1
+    remap = orc.collapse_map(bytes(present), n, 48)
+    want = []
+    for rec in fu.records(ref.passing):
+        hdr, rest = rec.split(b"\n", 1)
+        a, cell, umi = hdr.split(b"_")
+        s = cell.decode()
+        cid = remap[(idx[s[0:8]] * n + idx[s[8:16]]) * n + idx[s[16:24]]]
+        cell2 = (WL[cid // (n * n)] + WL[(cid // n) % n] + WL[cid % n]).encode()
+        want.append(a + b"_" + cell2 + b"_" + umi + b"\n" + rest)
+    dm, merged, passing, stats = run_both(ssd, r1, r2, 1, 5, collapse_pairs=48)
+    assert fu.records(passing) == want
+    assert merged == ref.merged1  # the pre-filter output is never collapsed
+
+
+@pytest.mark.parametrize("bad", [b"@a 1/1\nACGT\n+\nEEEE\nXa 2/1\nACGT\n+\nEEEE\n"])
+def test_malformed_raises(ssd, bad):
+    good = b"@a 1/2\nACGT\n+\nEEEE\n@b 2/2\nACGT\n+\nEEEE\n"
+    with pytest.raises(ssd.MalformedFastq):
+        run_both(ssd, bad, good, 1, 1)
+    with pytest.raises(ssd.MalformedFastq):
+        run_both(ssd, good.replace(b"/2", b"/1"), bad, 1, 1)
+
+
+def test_empty_and_tiny_inputs(ssd):
+    dm, merged, passing, stats = run_both(ssd, b"", b"", 1, 1)
+    assert merged == b"" and passing == b"" and stats["n_records_r1"] == 0
+    dm, merged, passing, stats = run_both(ssd, b"@a\nAC\n+\nEE", b"@a\nAC\n+\nEE", 1, 1)
+    assert stats["n_records_r2"] == 1 and merged == b"@a_AACGTGATAACGTGATAACGTGAT_AC\nAC\n+\nEE\n"
+
+
+def test_long_reads_take_the_slow_path(ssd, orc):
+    # records longer than the 2 KiB halo / the emit staging buffers go through the global-memory path
+    import random
+    rng = random.Random(3)
+    f, r = [], []
+    for i in range(200):
+        L = rng.choice([100, 3000, 9000, 30000])
+        s1 = "".join(rng.choice("ACGT") for _ in range(L))
+        s2 = "ACGTACGTAC" + WL[i % 96] + fu.LINKER_3_2 + WL[(i * 7) % 96] + fu.LINKER_2_1 + WL[(i * 3) % 96] + "".join(rng.choice("ACGT") for _ in range(L))
+        f.append("@L.%d %d/1\n%s\n+\n%s\n" % (i, i, s1, "E" * L))
+        r.append("@L.%d %d/2\n%s\n+\n%s\n" % (i, i, s2, "A" * len(s2)))
+    r1, r2 = "".join(f).encode(), "".join(r).encode()
+    ref = orc.demultiplex(r1, r2, WL, 1, 1)
+    dm, merged, passing, stats = run_both(ssd, r1, r2, 1, 1)
+    assert merged == ref.merged1 and passing == ref.passing and stats["n_matched"] == 200
