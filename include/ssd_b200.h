@@ -155,6 +155,23 @@ int ssd_host_free(void *p);
 /* Copy the per-record cell ids of the batch to the host: (i1*n + i2)*n + i3, or -1 when rejected. */
 int ssd_record_cells(ssd_ctx *ctx, int32_t *cells_host, uint64_t capacity, uint64_t *n_records);
 
+/* ---- instrumentation -------------------------------------------------------------------------- */
+/* Pipeline stages for ssd_read_timings. */
+#define SSD_STAGE_SCAN_R1 0   /* record-boundary scan of read 1 + output-length planning              */
+#define SSD_STAGE_SCAN_R2 1   /* scan of read 2 fused with extraction, matching, histogram, key capture */
+#define SSD_STAGE_DISTINCT 2  /* radix sort + unique + per-cell distinct-UMI count                       */
+#define SSD_STAGE_FILTER 3    /* pass decision, collapse map, output sizing                              */
+#define SSD_STAGE_PLAN 4      /* exclusive scan of output lengths                                        */
+#define SSD_STAGE_EMIT 5      /* the writer                                                              */
+#define SSD_N_STAGES 6
+/* When enabled, every stage is bracketed by a CUDA-event pair on the context's stream. */
+int ssd_set_timing(ssd_ctx *ctx, int enabled);
+/* Synchronises the stream, sums the recorded spans per stage (milliseconds, number of spans) and
+ * clears them. */
+int ssd_read_timings(ssd_ctx *ctx, double *ms_per_stage, uint32_t *spans_per_stage, int n_stages);
+/* Number of kernels this context has launched since it was created. */
+uint64_t ssd_launch_count(const ssd_ctx *ctx);
+
 /* ---- synthetic read pairs (bench / tests) ---------------------------------------- */
 typedef struct ssd_synth_spec {
     uint32_t struct_size;

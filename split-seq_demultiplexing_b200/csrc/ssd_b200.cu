@@ -64,6 +64,15 @@ struct ssd_ctx {
     DevBuf b_status1, b_status2, b_r1_start, b_r1_base, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
         b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
     DevBuf b_in1, b_in2, b_out;
+
+    // instrumentation: kernel launch counter and optional per-stage CUDA-event timing
+    uint64_t n_launches = 0;
+    bool timing = false;
+    struct Span {
+        int stage;
+        cudaEvent_t a, b;
+    };
+    std::vector<Span> spans;
 };
 
 namespace {
@@ -76,6 +85,24 @@ int fail(ssd_ctx* c, int code, const char* fmt, ...)
     va_end(ap);
     return code;
 }
+
+struct StageTimer {  // records a CUDA-event pair around a pipeline stage when timing is on
+    ssd_ctx* c;
+    cudaEvent_t b = nullptr;
+    StageTimer(ssd_ctx* ctx, int stage) : c(ctx)
+    {
+        if (!c->timing) return;
+        cudaEvent_t a;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+        c->spans.push_back({stage, a, b});
+    }
+    ~StageTimer()
+    {
+        if (b) cudaEventRecord(b, c->stream);
+    }
+};
 
 #define CU(c, call)                                                                                          \
     do {                                                                                                     \
@@ -125,6 +152,7 @@ int exclusive_scan(ssd_ctx* c, F f, uint64_t n, T* out)
     k_scan_reduce<T, F><<<nb, kThreads, 0, c->stream>>>(f, n, bs);
     k_scan_block_sums<T><<<1, kThreads, 0, c->stream>>>(bs, nb, (T*)nullptr);
     k_scan_apply<T, F><<<nb, kThreads, 0, c->stream>>>(f, n, bs, out);
+    c->n_launches += 3;
     CU(c, cudaGetLastError());
     return SSD_OK;
 }
@@ -152,6 +180,7 @@ int radix_sort64(ssd_ctx* c, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* v
         k_sort_hist<uint64_t><<<nb, kThreads, 0, c->stream>>>(a, n, bit, counts, nb);
         OKR(exclusive_scan<uint32_t>(c, LoadU32{counts}, ncount, offsets));
         k_sort_scatter<uint64_t, HV><<<nb, kThreads, 0, c->stream>>>(a, b, va, vb, n, bit, offsets, nb);
+        c->n_launches += 2;
         std::swap(a, b);
         std::swap(va, vb);
     }
@@ -176,6 +205,7 @@ int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint6
     uint32_t* pos = (uint32_t*)c->b_pos.p;
     OKR(exclusive_scan<uint32_t>(c, HeadFlag64{sorted}, n, pos));
     k_compact64<<<blocks_for(n, kThreads), kThreads, 0, c->stream>>>(sorted, pos, n, other);
+    c->n_launches += 1;
     uint32_t total = 0;
     CU(c, cudaMemcpyAsync(&total, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -201,6 +231,7 @@ int sort_unique_irr(ssd_ctx* c, IrrKey* keys, uint64_t n, IrrKey** uniq, uint64_
     uint64_t* tb = (uint64_t*)c->b_tmp64b.p;
     const uint32_t nb = blocks_for(n, kThreads);
     k_iota<<<nb, kThreads, 0, c->stream>>>(perm, n);
+    c->n_launches += 4;  // iota, two gathers, compaction
     uint64_t* sk = nullptr;
     uint32_t* sv = nullptr;
     for (int word = 0; word < 2; word++) {
@@ -227,6 +258,7 @@ int count_cells(ssd_ctx* c, const uint64_t* uniq, uint64_t n_uniq, const IrrKey*
     CU(c, cudaMemsetAsync(c->d_distinct, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
     if (n_uniq) k_count_cells64<<<blocks_for(n_uniq, kThreads), kThreads, 0, c->stream>>>(uniq, n_uniq, c->dcfg.umi_bits, c->d_distinct);
     if (n_uirr) k_count_cells_irr<<<blocks_for(n_uirr, kThreads), kThreads, 0, c->stream>>>(uirr, n_uirr, c->d_distinct);
+    c->n_launches += (n_uniq ? 1 : 0) + (n_uirr ? 1 : 0);
     CU(c, cudaGetLastError());
     return SSD_OK;
 }
@@ -254,14 +286,18 @@ int launch_scans(ssd_ctx* c)
         a.len = c->r1_len;
         a.status = (unsigned long long*)c->b_status1.p;
         a.n_tiles = nt1;
+        StageTimer t(c, 0);
         k_scan<kScanR1, OffT><<<nt1, kThreads, 0, c->stream>>>(a, c->dcfg);
+        c->n_launches++;
     }
     if (nt2) {
         a.buf = c->r2;
         a.len = c->r2_len;
         a.status = (unsigned long long*)c->b_status2.p;
         a.n_tiles = nt2;
+        StageTimer t(c, 1);
         k_scan<kScanR2, OffT><<<nt2, kThreads, 0, c->stream>>>(a, c->dcfg);
+        c->n_launches++;
     }
     CU(c, cudaGetLastError());
     return SSD_OK;
@@ -287,7 +323,9 @@ int launch_emit(ssd_ctx* c, int which, uint8_t* d_out)
     uint64_t rpb = (uint64_t)(kEmitIn * 3 / 4) / (avg_in + 48);
     a.rpb = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rpb, 1), 128);
     const uint32_t nb = blocks_for(c->n_rec, a.rpb);
+    StageTimer t(c, 5);
     if (nb) k_emit<OffT><<<nb, kThreads, 0, c->stream>>>(a, c->dcfg);
+    c->n_launches += nb ? 1 : 0;
     CU(c, cudaGetLastError());
     return SSD_OK;
 }
@@ -567,6 +605,7 @@ extern "C" int ssd_local_unique_keys(ssd_ctx* c, uint64_t** d_keys, uint64_t* n_
     if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_local_unique_keys before ssd_demux_device");
     CU(c, cudaSetDevice(c->device));
     if (!c->unique_done) {
+        StageTimer t(c, 2);
         OKR(sort_unique64(c, (uint64_t*)c->b_keys.p, c->n_keys, &c->uniq_keys, &c->n_uniq));
         OKR(sort_unique_irr(c, (IrrKey*)c->b_irr.p, c->n_irr, &c->uniq_irr, &c->n_uniq_irr));
         c->unique_done = true;
@@ -584,6 +623,7 @@ extern "C" int ssd_count_distinct(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys,
     CU(c, cudaSetDevice(c->device));
     uint64_t *uk = nullptr, nuk = 0, nui = 0;
     IrrKey* ui = nullptr;
+    StageTimer t(c, 2);
     if (c->unique_done && d_keys == c->uniq_keys && n_keys == c->n_uniq && d_irregular == (void*)c->uniq_irr && n_irregular == c->n_uniq_irr) {
         uk = c->uniq_keys;  // already sorted and unique: only count
         nuk = c->n_uniq;
@@ -603,6 +643,8 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
     if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_build_filter before ssd_demux_device");
     CU(c, cudaSetDevice(c->device));
     DevCounters h{};
+    StageTimer t(c, 3);
+    c->n_launches += 1 + (c->cfg.collapse_pairs > 0 ? 1 : 0) + (c->n_rec ? 1 : 0);
     CU(c, cudaMemsetAsync((char*)c->d_cnt + offsetof(DevCounters, n_matched), 0, 6 * sizeof(unsigned long long), c->stream));
     const uint32_t nbc = blocks_for(c->n_cells_total, kThreads);
     k_filter<<<nbc, kThreads, 0, c->stream>>>(c->d_hist, c->d_distinct, c->n_cells_total, (long long)c->cfg.min_count, c->cfg.filter_mode, c->d_pass,
@@ -651,7 +693,10 @@ extern "C" int ssd_emit_device(ssd_ctx* c, int which, void* d_out, size_t cap, s
     if (need == 0) return SSD_OK;
     if (!d_out) return fail(c, SSD_EINVAL, "null output pointer");
     OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
-    OKR(exclusive_scan<uint64_t>(c, make_outlen(c, which), c->n_rec, (uint64_t*)c->b_out_off.p));
+    {
+        StageTimer t(c, 4);
+        OKR(exclusive_scan<uint64_t>(c, make_outlen(c, which), c->n_rec, (uint64_t*)c->b_out_off.p));
+    }
     OKR(c->wide ? launch_emit<uint64_t>(c, which, (uint8_t*)d_out) : launch_emit<uint32_t>(c, which, (uint8_t*)d_out));
     DevCounters h{};
     OKR(fetch_counters(c, &h));
@@ -721,6 +766,7 @@ extern "C" int ssd_record_cells(ssd_ctx* c, int32_t* cells_host, uint64_t capaci
     if (!c->n_rec_r2) return SSD_OK;
     CU(c, cudaSetDevice(c->device));
     OKR(ensure(c, c->b_cells, c->n_rec_r2 * sizeof(int32_t)));
+    c->n_launches++;
     k_record_cells<<<blocks_for(c->n_rec_r2, kThreads), kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, c->n_rec_r2, (int32_t*)c->b_cells.p);
     CU(c, cudaMemcpyAsync(cells_host, c->b_cells.p, c->n_rec_r2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -864,3 +910,37 @@ extern "C" int ssd_synth_generate_device(ssd_ctx* c, const ssd_synth_spec* spec,
     release(tab);
     return rc;
 }
+
+// ================================================================================================
+// instrumentation
+// ================================================================================================
+extern "C" int ssd_set_timing(ssd_ctx* c, int enabled)
+{
+    if (!c) return SSD_EINVAL;
+    c->timing = enabled != 0;
+    return SSD_OK;
+}
+
+extern "C" int ssd_read_timings(ssd_ctx* c, double* ms_per_stage, uint32_t* launches_per_stage, int n_stages)
+{
+    if (!c) return SSD_EINVAL;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n_stages; i++) {
+        if (ms_per_stage) ms_per_stage[i] = 0.0;
+        if (launches_per_stage) launches_per_stage[i] = 0;
+    }
+    for (auto& sp : c->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.stage < n_stages) {
+            if (ms_per_stage) ms_per_stage[sp.stage] += ms;
+            if (launches_per_stage) launches_per_stage[sp.stage]++;
+        }
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    c->spans.clear();
+    return SSD_OK;
+}
+
+extern "C" uint64_t ssd_launch_count(const ssd_ctx* c) { return c ? c->n_launches : 0; }

@@ -99,6 +99,9 @@ _SIGS = {
     "ssd_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "ssd_host_free": (C.c_int, [C.c_void_p]),
     "ssd_record_cells": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "ssd_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "ssd_read_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_int]),
+    "ssd_launch_count": (C.c_uint64, [C.c_void_p]),
     "ssd_synth_sizes": (C.c_int, [C.POINTER(SynthSpec), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ssd_synth_generate_device": (C.c_int, [C.c_void_p, C.POINTER(SynthSpec), C.c_void_p, C.c_void_p]),
     "ssd_synth_generate_host": (C.c_int, [C.POINTER(SynthSpec), C.c_void_p, C.c_void_p]),

@@ -160,11 +160,29 @@ class Demultiplexer:
             self._check(self.lib.ssd_record_cells(self._ctx, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
         return out
 
+    # -- instrumentation -------------------------------------------------------------------------
+    STAGES = ("scan_r1", "scan_r2", "distinct", "filter", "plan", "emit")
+
+    def set_timing(self, on: bool):
+        self._check(self.lib.ssd_set_timing(self._ctx, 1 if on else 0))
+
+    def read_timings(self) -> Dict[str, Tuple[float, int]]:
+        ms = (C.c_double * len(self.STAGES))()
+        cnt = (C.c_uint32 * len(self.STAGES))()
+        self._check(self.lib.ssd_read_timings(self._ctx, ms, cnt, len(self.STAGES)))
+        return {s: (ms[i], cnt[i]) for i, s in enumerate(self.STAGES)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.ssd_launch_count(self._ctx))
+
     # -- whole pipeline ---------------------------------------------------------------------------
     def run_device(self, r1, r2, which: int = L.EMIT_PASSING):
         """r1/r2: torch uint8 CUDA tensors holding the two files.  Returns (uint8 CUDA tensor, stats)."""
         import torch
-        self.set_stream(torch.cuda.current_stream().cuda_stream)
+        handle = torch.cuda.current_stream().cuda_stream
+        if handle == 0:
+            torch.cuda.current_stream().synchronize()  # the library then runs on its own stream
+        self.set_stream(handle)
         self.demux_device(r1.data_ptr(), r1.numel(), r2.data_ptr(), r2.numel(), keep=(r1, r2))
         stats = self.filter_single()
         need = stats["bytes_matched"] if which == L.EMIT_MATCHED else stats["bytes_passing"]
