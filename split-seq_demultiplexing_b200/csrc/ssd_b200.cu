@@ -36,6 +36,7 @@ struct ssd_ctx {
     DevCfg dcfg{};
     uint64_t n_cells_total = 0;
     int record_hint = 48;
+    int bc_const = 0;  // 3 * whitelist entry length when all entries have the same length
     char err[512] = "";
 
     DevCounters* d_cnt = nullptr;
@@ -55,13 +56,14 @@ struct ssd_ctx {
     uint64_t rec_cap = 0;
     uint64_t n_rec_r1 = 0, n_rec_r2 = 0, n_rec = 0, n_keys = 0, n_irr = 0;
     bool phase1_done = false, filter_done = false, unique_done = false;
+    int planned = -1;  // which output b_out_off currently describes (-1 = none)
     uint64_t* uniq_keys = nullptr;
     uint64_t n_uniq = 0;
     IrrKey* uniq_irr = nullptr;
     uint64_t n_uniq_irr = 0;
     ssd_stats stats{};
 
-    DevBuf b_status1, b_status2, b_r1_start, b_r1_base, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
+    DevBuf b_status1, b_status2, b_r1_start, b_r1_meta, b_r1_base, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
         b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
     DevBuf b_in1, b_in2, b_out;
 
@@ -271,6 +273,7 @@ int launch_scans(ssd_ctx* c)
     a.err_off = c->d_err_off;
     a.rec_cap = c->rec_cap;
     a.r1_start = (OffT*)c->b_r1_start.p;
+    a.r1_meta = (uint4*)c->b_r1_meta.p;
     a.r1_base = (uint32_t*)c->b_r1_base.p;
     a.r1buf = c->r1;
     a.r1_len = c->r1_len;
@@ -278,7 +281,7 @@ int launch_scans(ssd_ctx* c)
     a.hist = c->d_hist;
     a.keys = (uint64_t*)c->b_keys.p;
     a.irr = (IrrKey*)c->b_irr.p;
-    a.lut = c->d_lut + (size_t)c->dcfg.e * 65536u;
+    a.lut = c->d_lut;
 
     const uint32_t nt1 = blocks_for(c->r1_len, kTile), nt2 = blocks_for(c->r2_len, kTile);
     if (nt1) {
@@ -312,16 +315,19 @@ int launch_emit(ssd_ctx* c, int which, uint8_t* d_out)
     a.r2buf = c->r2;
     a.r2_len = c->r2_len;
     a.r1_start = (const OffT*)c->b_r1_start.p;
+    a.r1_meta = (const uint4*)c->b_r1_meta.p;
     a.ann = (const uint64_t*)c->b_ann.p;
     a.out_off = (const uint64_t*)c->b_out_off.p;
     a.remap = (which == SSD_EMIT_PASSING && c->cfg.collapse_pairs > 0) ? c->d_remap : nullptr;
     a.out = d_out;
     a.n_rec = c->n_rec;
-    a.n_rec_r1 = c->n_rec_r1;
     a.cnt = c->d_cnt;
-    const uint64_t avg_in = c->n_rec_r1 ? c->r1_len / c->n_rec_r1 : 1;
-    uint64_t rpb = (uint64_t)(kEmitIn * 3 / 4) / (avg_in + 48);
-    a.rpb = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rpb, 1), 128);
+    // records per block: the block's slice of the output must fit the staging buffer
+    const uint64_t n_out = which == SSD_EMIT_MATCHED ? c->stats.n_matched : c->stats.n_retained;
+    const uint64_t bytes = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
+    const uint64_t avg_out = n_out ? bytes / n_out + 1 : 1;
+    const uint64_t rpb = (uint64_t)(kEmitOut * 7 / 8) / avg_out;
+    a.rpb = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rpb, 1), 256);
     const uint32_t nb = blocks_for(c->n_rec, a.rpb);
     StageTimer t(c, 5);
     if (nb) k_emit<OffT><<<nb, kThreads, 0, c->stream>>>(a, c->dcfg);
@@ -340,6 +346,7 @@ OutLen make_outlen(ssd_ctx* c, int which)
     f.wl_len = c->d_wl_len;
     f.n = c->dcfg.n_wl;
     f.umi_len = c->dcfg.umi_len;
+    f.bc_const = c->bc_const;
     return f;
 }
 
@@ -451,7 +458,11 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
         if (len != 8) d.fast_wl = 0;
         d.wl_code[i] = (uint16_t)code;
     }
-    // all three barcode windows must be 8 wide for the LUT path; shorter windows use the generic loop anyway
+    d.fast_geom = (d.b1e - d.b1s == 8 && d.b2e - d.b2s == 8 && d.b3e - d.b3s == 8) ? 1 : 0;
+    d.need_len = std::max(std::max(d.ue, d.b1e), std::max(d.b2e, d.b3e));
+    c->bc_const = 3 * d.wl_len[0];
+    for (int i = 1; i < d.n_wl; i++)
+        if (d.wl_len[i] != d.wl_len[0]) c->bc_const = 0;
     c->record_hint = cfg->record_bytes_hint > 0 ? cfg->record_bytes_hint : 48;
 
     CUB_(cudaMalloc(&c->d_cnt, sizeof(DevCounters)));
@@ -479,7 +490,7 @@ extern "C" void ssd_destroy(ssd_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_r1_start, &c->b_r1_base, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
+    DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_r1_start, &c->b_r1_meta, &c->b_r1_base, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
                       &c->b_irr_alt, &c->b_perm, &c->b_perm_alt, &c->b_tmp64a, &c->b_tmp64b, &c->b_counts, &c->b_offsets, &c->b_bsums,
                       &c->b_pos, &c->b_out_off, &c->b_cells, &c->b_in1, &c->b_in2, &c->b_out};
     for (DevBuf* b : bufs) release(*b);
@@ -517,6 +528,7 @@ extern "C" int ssd_demux_device(ssd_ctx* c, const void* d_r1, size_t r1_len, con
     c->r2_len = r2_len;
     c->wide = std::max(r1_len, r2_len) >= (1ull << 32);
     c->phase1_done = c->filter_done = c->unique_done = false;
+    c->planned = -1;
     if (std::max(r1_len, r2_len) >= (1ull << 36)) return fail(c, SSD_EINVAL, "a batch is limited to 64 GiB per file");
 
     const uint32_t nt1 = blocks_for(r1_len, kTile), nt2 = blocks_for(r2_len, kTile);
@@ -527,6 +539,7 @@ extern "C" int ssd_demux_device(ssd_ctx* c, const void* d_r1, size_t r1_len, con
         OKR(ensure(c, c->b_status1, (size_t)(nt1 + 1) * 8));
         OKR(ensure(c, c->b_status2, (size_t)(nt2 + 1) * 8));
         OKR(ensure(c, c->b_r1_start, (cap + 1) * (c->wide ? 8 : 4)));
+        OKR(ensure(c, c->b_r1_meta, cap * 16));
         OKR(ensure(c, c->b_r1_base, cap * 4));
         OKR(ensure(c, c->b_ann, cap * 8));
         OKR(ensure(c, c->b_keys, cap * 8));
@@ -644,18 +657,28 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
     CU(c, cudaSetDevice(c->device));
     DevCounters h{};
     StageTimer t(c, 3);
-    c->n_launches += 1 + (c->cfg.collapse_pairs > 0 ? 1 : 0) + (c->n_rec ? 1 : 0);
+    c->n_launches += 4 + (c->cfg.collapse_pairs > 0 ? 1 : 0);
     CU(c, cudaMemsetAsync((char*)c->d_cnt + offsetof(DevCounters, n_matched), 0, 6 * sizeof(unsigned long long), c->stream));
     const uint32_t nbc = blocks_for(c->n_cells_total, kThreads);
     k_filter<<<nbc, kThreads, 0, c->stream>>>(c->d_hist, c->d_distinct, c->n_cells_total, (long long)c->cfg.min_count, c->cfg.filter_mode, c->d_pass,
                                               c->d_cnt);
     if (c->cfg.collapse_pairs > 0) k_collapse_map<<<nbc, kThreads, 0, c->stream>>>(c->d_pass, c->dcfg.n_wl, c->cfg.collapse_pairs, c->d_remap);
-    if (c->n_rec)
-        k_plan_totals<<<blocks_for(c->n_rec, kThreads), kThreads, 0, c->stream>>>(make_outlen(c, SSD_EMIT_MATCHED), make_outlen(c, SSD_EMIT_PASSING),
-                                                                                 c->n_rec, c->d_cnt);
+    {
+        // exclusive scan of the post-filter output lengths; its first kernel also counts the retained records
+        // and sizes the pre-filter output
+        const uint32_t nb = (uint32_t)(c->n_rec / kScanBlock + 1);
+        OKR(ensure(c, c->b_bsums, (size_t)nb * sizeof(unsigned long long)));
+        OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
+        unsigned long long* bs = (unsigned long long*)c->b_bsums.p;
+        OutLen f = make_outlen(c, SSD_EMIT_PASSING);
+        k_plan_reduce<<<nb, kThreads, 0, c->stream>>>(f, c->n_rec, bs, c->d_cnt);
+        k_scan_block_sums<unsigned long long><<<1, kThreads, 0, c->stream>>>(bs, nb, &c->d_cnt->bytes_passing);
+        k_scan_apply<unsigned long long, OutLen><<<nb, kThreads, 0, c->stream>>>(f, c->n_rec, bs, (unsigned long long*)c->b_out_off.p);
+        c->planned = SSD_EMIT_PASSING;
+    }
     CU(c, cudaGetLastError());
     OKR(fetch_counters(c, &h));
-    c->stats.n_matched = h.n_matched;
+    c->stats.n_matched = c->n_keys + c->n_irr;
     c->stats.n_cells = h.n_cells;
     c->stats.n_passing_cells = h.n_passing_cells;
     c->stats.n_retained = h.n_retained;
@@ -692,10 +715,11 @@ extern "C" int ssd_emit_device(ssd_ctx* c, int which, void* d_out, size_t cap, s
     if (need > cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, cap);
     if (need == 0) return SSD_OK;
     if (!d_out) return fail(c, SSD_EINVAL, "null output pointer");
-    OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
-    {
+    if (c->planned != which) {
         StageTimer t(c, 4);
-        OKR(exclusive_scan<uint64_t>(c, make_outlen(c, which), c->n_rec, (uint64_t*)c->b_out_off.p));
+        OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
+        OKR(exclusive_scan<unsigned long long>(c, make_outlen(c, which), c->n_rec, (unsigned long long*)c->b_out_off.p));
+        c->planned = which;
     }
     OKR(c->wide ? launch_emit<uint64_t>(c, which, (uint8_t*)d_out) : launch_emit<uint32_t>(c, which, (uint8_t*)d_out));
     DevCounters h{};

@@ -20,6 +20,8 @@ struct DevCfg {
     int umi_bits;     // 2 * umi_len
     int cell_bits;    // ceil(log2(n_wl^3))
     int fast_wl;      // every whitelist entry is 8 x ACGT -> 2-bit path + LUT
+    int fast_geom;    // all three barcode windows are exactly 8 wide
+    int need_len;     // largest slice end: shorter read-2 sequences take the exact generic path
     uint16_t wl_code[kMaxWl];
     uint8_t wl_len[kMaxWl];
     uint8_t wl[kMaxWl * 8];

@@ -1,0 +1,275 @@
+// ssd_sort.cuh — first-hit LUT builder, device-wide exclusive scan, LSD radix sort, unique compaction and
+// per-cell distinct counting (the len(set(UMIs)) of V2:411).
+#pragma once
+#include "ssd_device.cuh"
+
+namespace ssd {
+
+// ---------------------------------------------------------------------------------------------
+// first-hit LUT: lut[e'][code] for e' = 0..e
+// ---------------------------------------------------------------------------------------------
+__global__ void k_build_lut(const __grid_constant__ DevCfg cfg, uint8_t* lut, int n_levels)
+{
+    uint32_t code = blockIdx.x * blockDim.x + threadIdx.x;
+    if (code >= 65536u) return;
+    for (int lev = 0; lev < n_levels; lev++) {
+        uint32_t hit = 0xFFu;
+        for (int i = 0; i < cfg.n_wl; i++) {
+            uint32_t x = code ^ cfg.wl_code[i];
+            if (__popc((x | (x >> 1)) & 0x5555u) <= lev) {
+                hit = (uint32_t)i;
+                break;
+            }
+        }
+        lut[(size_t)lev * 65536u + code] = (uint8_t)hit;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-wide exclusive scan: out[i] = sum_{j<i} f(j), out[n] = total   (3 kernels)
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanItems = 8;
+constexpr int kScanBlock = kThreads * kScanItems;
+
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* s_tmp, T& total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += u;
+    }
+    if (lane == 31) s_tmp[warp] = incl;
+    __syncthreads();
+    T base = 0;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) {
+        T u = s_tmp[w];
+        if (w < warp) base += u;
+        total += u;
+    }
+    __syncthreads();
+    return base + incl - v;
+}
+
+template <typename T, class F>
+__global__ void __launch_bounds__(kThreads) k_scan_reduce(F f, uint64_t n, T* block_sums)
+{
+    __shared__ T s_tmp[kThreads / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems;
+    T v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++)
+        if (base + k < n) v += (T)f(base + k);
+    T total;
+    block_exclusive_scan(v, s_tmp, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_scan_block_sums(T* block_sums, uint32_t n_blocks, T* total_out)
+{
+    __shared__ T s_tmp[kThreads / 32];
+    __shared__ T s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_blocks; base += kThreads) {
+        uint32_t i = base + threadIdx.x;
+        T v = i < n_blocks ? block_sums[i] : (T)0;
+        T total;
+        T ex = block_exclusive_scan(v, s_tmp, total);
+        T carry = s_carry;
+        if (i < n_blocks) block_sums[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = s_carry;
+}
+
+template <typename T, class F>
+__global__ void __launch_bounds__(kThreads) k_scan_apply(F f, uint64_t n, const T* block_sums, T* out)
+{
+    __shared__ T s_tmp[kThreads / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems;
+    T item[kScanItems];
+    T v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        item[k] = base + k < n ? (T)f(base + k) : (T)0;
+        v += item[k];
+    }
+    T total;
+    T ex = block_exclusive_scan(v, s_tmp, total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += item[k];
+    }
+    if (base <= n && n < base + kScanItems) out[n] = ex;  // items past n are zero, so this is the grand total
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSD radix sort, 8-bit digits, stable.  Pass = per-block digit histogram -> scan -> ranked scatter.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSortItems = 16;
+constexpr int kSortBlock = kThreads * kSortItems;  // 4096 keys per block
+
+template <typename K>
+__device__ __forceinline__ uint32_t digit_of(const K& k, int bit);
+template <>
+__device__ __forceinline__ uint32_t digit_of<uint64_t>(const uint64_t& k, int bit)
+{
+    return (uint32_t)(k >> bit) & 0xFFu;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(kThreads) k_sort_hist(const K* keys, uint64_t n, int bit, uint32_t* counts, uint32_t n_blocks)
+{
+    __shared__ uint32_t s_hist[256];
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * kSortBlock;
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+        uint64_t j = base + (uint64_t)i * kThreads + threadIdx.x;
+        if (j < n) atomicAdd(&s_hist[digit_of(keys[j], bit)], 1u);
+    }
+    __syncthreads();
+    counts[(size_t)threadIdx.x * n_blocks + blockIdx.x] = s_hist[threadIdx.x];
+}
+
+template <typename K, bool HAS_VALS>
+__global__ void __launch_bounds__(kThreads) k_sort_scatter(const K* keys_in, K* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                                                           uint64_t n, int bit, const uint32_t* offsets, uint32_t n_blocks)
+{
+    __shared__ uint32_t s_wcount[kThreads / 32][257];
+    __shared__ uint32_t s_base[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < (kThreads / 32) * 257; i += kThreads) (&s_wcount[0][0])[i] = 0;
+    __syncthreads();
+
+    // warp w owns keys [w*512, (w+1)*512) of the block; iteration i, lane l -> key w*512 + i*32 + l
+    const uint64_t wbase = (uint64_t)blockIdx.x * kSortBlock + (uint64_t)warp * (32 * kSortItems);
+    K key[kSortItems];
+    uint32_t val[kSortItems];
+    uint16_t rank[kSortItems];
+    uint16_t dig[kSortItems];
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+        uint64_t j = wbase + (uint64_t)i * 32 + lane;
+        bool valid = j < n;
+        if (valid) {
+            key[i] = keys_in[j];
+            if (HAS_VALS) val[i] = vals_in[j];
+        }
+        uint32_t d = valid ? digit_of(key[i], bit) : 256u;
+        uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
+        uint32_t pre = 0;
+        if ((uint32_t)lane == leader) pre = s_wcount[warp][d];
+        pre = __shfl_sync(0xFFFFFFFFu, pre, (int)leader);
+        __syncwarp();
+        if ((uint32_t)lane == leader) s_wcount[warp][d] = pre + (uint32_t)__popc(peers);
+        __syncwarp();
+        rank[i] = (uint16_t)(pre + (uint32_t)__popc(peers & ((1u << lane) - 1u)));
+        dig[i] = (uint16_t)d;
+    }
+    __syncthreads();
+    {
+        // exclusive scan over warps for digit `tid`, plus the global base of (digit, block)
+        uint32_t acc = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++) {
+            uint32_t c = s_wcount[w][tid];
+            s_wcount[w][tid] = acc;
+            acc += c;
+        }
+        s_base[tid] = offsets[(size_t)tid * n_blocks + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+        uint32_t d = dig[i];
+        if (d < 256u) {
+            uint64_t dst = (uint64_t)s_base[d] + s_wcount[warp][d] + rank[i];
+            keys_out[dst] = key[i];
+            if (HAS_VALS) vals_out[dst] = val[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// unique compaction of a sorted array + per-cell distinct counts
+// ---------------------------------------------------------------------------------------------
+struct HeadFlag64 {
+    const uint64_t* k;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return i == 0 || k[i] != k[i - 1] ? 1u : 0u; }
+};
+
+struct HeadFlagIrr {  // irregular keys are sorted through an index permutation
+    const IrrKey* k;
+    const uint32_t* perm;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const
+    {
+        if (i == 0) return 1u;
+        IrrKey a = k[perm[i]], b = k[perm[i - 1]];
+        return a.hi != b.hi || a.lo != b.lo ? 1u : 0u;
+    }
+};
+
+__global__ void k_compact64(const uint64_t* in, const uint32_t* pos, uint64_t n, uint64_t* out)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i == 0 || in[i] != in[i - 1]) out[pos[i]] = in[i];
+}
+
+__global__ void k_compact_irr(const IrrKey* in, const uint32_t* perm, const uint32_t* pos, uint64_t n, IrrKey* out)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    IrrKey a = in[perm[i]];
+    bool head = i == 0;
+    if (!head) {
+        IrrKey b = in[perm[i - 1]];
+        head = a.hi != b.hi || a.lo != b.lo;
+    }
+    if (head) out[pos[i]] = a;
+}
+
+// distinct[cell] += (index of the cell's last unique key) + 1 - (index of its first): two atomics per cell run
+__global__ void k_count_cells64(const uint64_t* uniq, uint64_t n, int shift, uint32_t* distinct)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = (uint32_t)(uniq[i] >> shift);
+    if (i == 0 || (uint32_t)(uniq[i - 1] >> shift) != c) atomicSub(&distinct[c], (uint32_t)i);
+    if (i == n - 1 || (uint32_t)(uniq[i + 1] >> shift) != c) atomicAdd(&distinct[c], (uint32_t)i + 1u);
+}
+
+__global__ void k_count_cells_irr(const IrrKey* uniq, uint64_t n, uint32_t* distinct)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = (uint32_t)(uniq[i].hi >> kIrrCellShift);
+    if (i == 0 || (uint32_t)(uniq[i - 1].hi >> kIrrCellShift) != c) atomicSub(&distinct[c], (uint32_t)i);
+    if (i == n - 1 || (uint32_t)(uniq[i + 1].hi >> kIrrCellShift) != c) atomicAdd(&distinct[c], (uint32_t)i + 1u);
+}
+
+__global__ void k_iota(uint32_t* p, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+
+__global__ void k_gather_irr_word(const IrrKey* in, const uint32_t* perm, uint64_t n, int which, uint64_t* out)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = which ? in[perm[i]].hi : in[perm[i]].lo;
+}
+
+}  // namespace ssd
