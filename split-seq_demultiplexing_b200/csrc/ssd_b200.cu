@@ -37,6 +37,7 @@ struct ssd_ctx {
     uint64_t n_cells_total = 0;
     int record_hint = 48;
     int bc_const = 0;  // 3 * whitelist entry length when all entries have the same length
+    uint32_t scan_grid = 296;  // persistent scan blocks: SM count x resident blocks per SM
     char err[512] = "";
 
     DevCounters* d_cnt = nullptr;
@@ -63,7 +64,7 @@ struct ssd_ctx {
     uint64_t n_uniq_irr = 0;
     ssd_stats stats{};
 
-    DevBuf b_status1, b_status2, b_r1_start, b_r1_meta, b_r1_base, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
+    DevBuf b_status1, b_status2, b_r1_start, b_r1_meta, b_r1_base, b_r1_tok, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
         b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
     DevBuf b_in1, b_in2, b_out;
 
@@ -165,6 +166,22 @@ struct LoadU32 {
 };
 
 // ---- LSD radix sort of 64-bit keys over bits [0, bits); returns where the sorted data ended up ----
+template <class Src, bool HV>
+int radix_pass(ssd_ctx* c, Src src, uint64_t n, int bit, uint64_t* dst, const uint32_t* vsrc, uint32_t* vdst)
+{
+    const uint32_t nb = blocks_for(n, kSortBlock);
+    const size_t ncount = (size_t)256 * nb;
+    OKR(ensure(c, c->b_counts, ncount * sizeof(uint32_t)));
+    OKR(ensure(c, c->b_offsets, (ncount + 1) * sizeof(uint32_t)));
+    uint32_t* counts = (uint32_t*)c->b_counts.p;
+    uint32_t* offsets = (uint32_t*)c->b_offsets.p;
+    k_sort_hist<Src><<<nb, kThreads, 0, c->stream>>>(src, n, bit, counts, nb);
+    OKR(exclusive_scan<uint32_t>(c, LoadU32{counts}, ncount, offsets));
+    k_sort_scatter<Src, uint64_t, HV><<<nb, kThreads, 0, c->stream>>>(src, dst, vsrc, vdst, n, bit, offsets, nb);
+    c->n_launches += 2;
+    return SSD_OK;
+}
+
 template <bool HV>
 int radix_sort64(ssd_ctx* c, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* vb, uint64_t n, int bits, uint64_t** sorted,
                  uint32_t** sorted_vals)
@@ -172,17 +189,8 @@ int radix_sort64(ssd_ctx* c, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* v
     *sorted = a;
     if (sorted_vals) *sorted_vals = va;
     if (n == 0) return SSD_OK;
-    const uint32_t nb = blocks_for(n, kSortBlock);
-    const size_t ncount = (size_t)256 * nb;
-    OKR(ensure(c, c->b_counts, ncount * sizeof(uint32_t)));
-    OKR(ensure(c, c->b_offsets, (ncount + 1) * sizeof(uint32_t)));
-    uint32_t* counts = (uint32_t*)c->b_counts.p;
-    uint32_t* offsets = (uint32_t*)c->b_offsets.p;
     for (int bit = 0; bit < bits; bit += 8) {
-        k_sort_hist<uint64_t><<<nb, kThreads, 0, c->stream>>>(a, n, bit, counts, nb);
-        OKR(exclusive_scan<uint32_t>(c, LoadU32{counts}, ncount, offsets));
-        k_sort_scatter<uint64_t, HV><<<nb, kThreads, 0, c->stream>>>(a, b, va, vb, n, bit, offsets, nb);
-        c->n_launches += 2;
+        OKR((radix_pass<KeysArray, HV>(c, KeysArray{a}, n, bit, b, va, vb)));
         std::swap(a, b);
         std::swap(va, vb);
     }
@@ -192,16 +200,30 @@ int radix_sort64(ssd_ctx* c, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* v
     return SSD_OK;
 }
 
-// sort + unique of regular keys.  `keys` holds n keys; result: *uniq (a context buffer or `keys`), *n_uniq
-int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint64_t* n_uniq)
+// sort + unique of regular keys.  `keys` holds n keys (or, when from_ann, the keys are taken from the
+// annotation words of the batch and `keys` only is the buffer they are compacted into by the first pass);
+// result: *uniq (a context buffer or `keys`), *n_uniq
+int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint64_t* n_uniq, bool from_ann = false)
 {
     *uniq = keys;
     *n_uniq = 0;
     if (n == 0) return SSD_OK;
     OKR(ensure(c, c->b_keys_alt, n * sizeof(uint64_t)));
     uint64_t* sorted = nullptr;
-    OKR(radix_sort64<false>(c, keys, (uint64_t*)c->b_keys_alt.p, nullptr, nullptr, n, c->dcfg.umi_bits + c->dcfg.cell_bits, &sorted,
-                            nullptr));
+    const int bits = c->dcfg.umi_bits + c->dcfg.cell_bits;
+    if (from_ann) {
+        // pass 1 reads the annotations of all records, drops what is not a regular key, lands n keys in b_keys_alt
+        OKR((radix_pass<KeysFromAnn, false>(c, KeysFromAnn{(const uint64_t*)c->b_ann.p, c->dcfg.umi_bits}, c->n_rec_r2, 0,
+                                            (uint64_t*)c->b_keys_alt.p, nullptr, nullptr)));
+        uint64_t *a = (uint64_t*)c->b_keys_alt.p, *b = keys;
+        for (int bit = 8; bit < bits; bit += 8) {
+            OKR((radix_pass<KeysArray, false>(c, KeysArray{a}, n, bit, b, nullptr, nullptr)));
+            std::swap(a, b);
+        }
+        sorted = a;
+    } else {
+        OKR(radix_sort64<false>(c, keys, (uint64_t*)c->b_keys_alt.p, nullptr, nullptr, n, bits, &sorted, nullptr));
+    }
     uint64_t* other = sorted == keys ? (uint64_t*)c->b_keys_alt.p : keys;
     OKR(ensure(c, c->b_pos, (n + 1) * sizeof(uint32_t)));
     uint32_t* pos = (uint32_t*)c->b_pos.p;
@@ -275,11 +297,11 @@ int launch_scans(ssd_ctx* c)
     a.r1_start = (OffT*)c->b_r1_start.p;
     a.r1_meta = (uint4*)c->b_r1_meta.p;
     a.r1_base = (uint32_t*)c->b_r1_base.p;
+    a.r1_tok = (unsigned long long*)c->b_r1_tok.p;
     a.r1buf = c->r1;
     a.r1_len = c->r1_len;
     a.ann = (uint64_t*)c->b_ann.p;
     a.hist = c->d_hist;
-    a.keys = (uint64_t*)c->b_keys.p;
     a.irr = (IrrKey*)c->b_irr.p;
     a.lut = c->d_lut;
 
@@ -290,7 +312,7 @@ int launch_scans(ssd_ctx* c)
         a.status = (unsigned long long*)c->b_status1.p;
         a.n_tiles = nt1;
         StageTimer t(c, 0);
-        k_scan<kScanR1, OffT><<<nt1, kThreads, 0, c->stream>>>(a, c->dcfg);
+        k_scan<kScanR1, OffT><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         c->n_launches++;
     }
     if (nt2) {
@@ -299,7 +321,7 @@ int launch_scans(ssd_ctx* c)
         a.status = (unsigned long long*)c->b_status2.p;
         a.n_tiles = nt2;
         StageTimer t(c, 1);
-        k_scan<kScanR2, OffT><<<nt2, kThreads, 0, c->stream>>>(a, c->dcfg);
+        k_scan<kScanR2, OffT><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         c->n_launches++;
     }
     CU(c, cudaGetLastError());
@@ -460,11 +482,28 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
     }
     d.fast_geom = (d.b1e - d.b1s == 8 && d.b2e - d.b2s == 8 && d.b3e - d.b3s == 8) ? 1 : 0;
     d.need_len = std::max(std::max(d.ue, d.b1e), std::max(d.b2e, d.b3e));
+    d.magic_n = ((1ull << 43) + (unsigned long long)d.n_wl - 1) / (unsigned long long)d.n_wl;
+    d.magic_nn = ((1ull << 43) + (unsigned long long)d.n_wl * d.n_wl - 1) / ((unsigned long long)d.n_wl * d.n_wl);
+    d.bc8 = 1;
+    for (int i = 0; i < d.n_wl; i++)
+        if (d.wl_len[i] != 8) d.bc8 = 0;
     c->bc_const = 3 * d.wl_len[0];
     for (int i = 1; i < d.n_wl; i++)
         if (d.wl_len[i] != d.wl_len[0]) c->bc_const = 0;
     c->record_hint = cfg->record_bytes_hint > 0 ? cfg->record_bytes_hint : 48;
 
+    {
+        // the scan kernels are persistent: one wave of blocks, each looping over tiles
+        cudaDeviceProp prop;
+        CUB_(cudaGetDeviceProperties(&prop, c->device));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        int per_sm = 0;
+        CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<kScanR2, uint32_t>, kScanThreads, sizeof(ScanSmem)));
+        c->scan_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
+    }
     CUB_(cudaMalloc(&c->d_cnt, sizeof(DevCounters)));
     CUB_(cudaMalloc(&c->d_err_off, 2 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_lut, (size_t)(d.e + 1) * 65536u));
@@ -490,7 +529,7 @@ extern "C" void ssd_destroy(ssd_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_r1_start, &c->b_r1_meta, &c->b_r1_base, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
+    DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_r1_start, &c->b_r1_meta, &c->b_r1_base, &c->b_r1_tok, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
                       &c->b_irr_alt, &c->b_perm, &c->b_perm_alt, &c->b_tmp64a, &c->b_tmp64b, &c->b_counts, &c->b_offsets, &c->b_bsums,
                       &c->b_pos, &c->b_out_off, &c->b_cells, &c->b_in1, &c->b_in2, &c->b_out};
     for (DevBuf* b : bufs) release(*b);
@@ -541,6 +580,7 @@ extern "C" int ssd_demux_device(ssd_ctx* c, const void* d_r1, size_t r1_len, con
         OKR(ensure(c, c->b_r1_start, (cap + 1) * (c->wide ? 8 : 4)));
         OKR(ensure(c, c->b_r1_meta, cap * 16));
         OKR(ensure(c, c->b_r1_base, cap * 4));
+        OKR(ensure(c, c->b_r1_tok, cap * 8));
         OKR(ensure(c, c->b_ann, cap * 8));
         OKR(ensure(c, c->b_keys, cap * 8));
         OKR(ensure(c, c->b_irr, cap * sizeof(IrrKey)));
@@ -619,7 +659,14 @@ extern "C" int ssd_local_unique_keys(ssd_ctx* c, uint64_t** d_keys, uint64_t* n_
     CU(c, cudaSetDevice(c->device));
     if (!c->unique_done) {
         StageTimer t(c, 2);
-        OKR(sort_unique64(c, (uint64_t*)c->b_keys.p, c->n_keys, &c->uniq_keys, &c->n_uniq));
+        OKR(sort_unique64(c, (uint64_t*)c->b_keys.p, c->n_keys, &c->uniq_keys, &c->n_uniq, true));
+        if (c->n_irr) {
+            unsigned long long* cursor = (unsigned long long*)c->d_err_off;  // free after phase 1 (errors were read)
+            CU(c, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), c->stream));
+            k_collect_irr<<<blocks_for(c->n_rec_r2, kThreads), kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, c->n_rec_r2, c->r2, (IrrKey*)c->b_irr.p,
+                                                                                       cursor);
+            c->n_launches++;
+        }
         OKR(sort_unique_irr(c, (IrrKey*)c->b_irr.p, c->n_irr, &c->uniq_irr, &c->n_uniq_irr));
         c->unique_done = true;
     }
@@ -968,3 +1015,16 @@ extern "C" int ssd_read_timings(ssd_ctx* c, double* ms_per_stage, uint32_t* laun
 }
 
 extern "C" uint64_t ssd_launch_count(const ssd_ctx* c) { return c ? c->n_launches : 0; }
+
+#ifdef SSD_SCAN_PROFILE
+// debug builds only: per-phase clock totals of the scan kernels (phases 0..4, tiles in [7]) for read 1 / read 2
+extern "C" int ssd_debug_scan_profile(unsigned long long* out16, int reset)
+{
+    if (out16 && cudaMemcpyFromSymbol(out16, ssd::g_scan_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return SSD_ECUDA;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(ssd::g_scan_prof, z, sizeof z) != cudaSuccess) return SSD_ECUDA;
+    }
+    return SSD_OK;
+}
+#endif

@@ -22,6 +22,8 @@ struct DevCfg {
     int fast_wl;      // every whitelist entry is 8 x ACGT -> 2-bit path + LUT
     int fast_geom;    // all three barcode windows are exactly 8 wide
     int need_len;     // largest slice end: shorter read-2 sequences take the exact generic path
+    int bc8;          // every whitelist entry is exactly 8 bytes long
+    unsigned long long magic_n, magic_nn;  // ceil(2^43 / n), ceil(2^43 / n^2): exact division of cell ids < 2^21
     uint16_t wl_code[kMaxWl];
     uint8_t wl_len[kMaxWl];
     uint8_t wl[kMaxWl * 8];
@@ -274,28 +276,51 @@ __device__ __forceinline__ void load_window(uint8_t* dst, const uint8_t* src, ui
     __syncthreads();
 }
 
-// Newline bitmap of win[0, nbytes): mask16[c] gets one bit per byte of 16-byte chunk c.  `nchunks`
-// entries are written (zeros beyond the data).  Also builds nothing else; callers sync afterwards.
-__device__ __forceinline__ uint32_t nl_bits4(uint32_t x)
+// 0x80 in every byte of x that is '\n' (exact for any byte values)
+__device__ __forceinline__ uint32_t nl_flags(uint32_t x)
 {
-    uint32_t t = x ^ 0x0A0A0A0Au;                                         // zero byte where '\n'
-    uint32_t y = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);  // 0x80 in every zero byte (exact)
-    return (y * 0x00204081u) >> 28;                                       // gather bits 7,15,23,31
+    uint32_t t = x ^ 0x0A0A0A0Au;
+    return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);
 }
 
+// Newline bitmap of win[0, nbytes): mask16[c] gets one bit per byte of 16-byte chunk c, for all `nchunks`
+// chunks (zeros beyond the data).  The four flag words of a chunk are gathered with two dp4a each.
+template <int NT, int ITERS>
 __device__ __forceinline__ void build_nl_mask(const uint8_t* win, uint32_t nbytes, uint16_t* mask16, uint32_t nchunks)
 {
     const uint4* w4 = reinterpret_cast<const uint4*>(win);
-    for (uint32_t c = threadIdx.x; c < nchunks; c += blockDim.x) {
-        uint32_t m = 0;
-        if (c * 16u < nbytes) {
-            uint4 v = w4[c];
-            m = nl_bits4(v.x) | (nl_bits4(v.y) << 4) | (nl_bits4(v.z) << 8) | (nl_bits4(v.w) << 12);
-            uint32_t rem = nbytes - c * 16u;
-            if (rem < 16u) m &= (1u << rem) - 1u;
+    const uint32_t nfull = nbytes >> 4;
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+        const uint32_t c = (uint32_t)it * NT + threadIdx.x;
+        if (c < nfull) {
+            const uint4 v = w4[c];
+            const uint32_t lo = __dp4a(nl_flags(v.x), 0x08040201u, __dp4a(nl_flags(v.y), 0x80402010u, 0u));
+            const uint32_t hi = __dp4a(nl_flags(v.z), 0x08040201u, __dp4a(nl_flags(v.w), 0x80402010u, 0u));
+            mask16[c] = (uint16_t)((lo >> 7) | ((hi >> 7) << 8));
+        } else if (c < nchunks) {
+            uint32_t m = 0;
+            if (c == nfull && (nbytes & 15u)) {  // the chunk the data ends in
+                const uint4 v = w4[c];
+                const uint32_t lo = __dp4a(nl_flags(v.x), 0x08040201u, __dp4a(nl_flags(v.y), 0x80402010u, 0u));
+                const uint32_t hi = __dp4a(nl_flags(v.z), 0x08040201u, __dp4a(nl_flags(v.w), 0x80402010u, 0u));
+                m = ((lo >> 7) | ((hi >> 7) << 8)) & ((1u << (nbytes & 15u)) - 1u);
+            }
+            mask16[c] = (uint16_t)m;
         }
-        mask16[c] = (uint16_t)m;
     }
+}
+
+// exact division of x < 2^21 by the divisor behind `magic` (= ceil(2^43 / d), d <= 2^14)
+__device__ __forceinline__ uint32_t div_magic(uint32_t x, unsigned long long magic) { return (uint32_t)(((unsigned long long)x * magic) >> 43); }
+
+__device__ __forceinline__ void cell_indices(const DevCfg& c, uint32_t cell, uint32_t& i1, uint32_t& i2, uint32_t& i3)
+{
+    const uint32_t n = (uint32_t)c.n_wl;
+    i1 = div_magic(cell, c.magic_nn);
+    const uint32_t rem = cell - i1 * n * n;
+    i2 = div_magic(rem, c.magic_n);
+    i3 = rem - i2 * n;
 }
 
 }  // namespace ssd

@@ -182,8 +182,9 @@ __device__ __forceinline__ uint32_t emit_record_generic(const Acc& a, const Emit
     const uint64_t an = args.ann[r];
     uint32_t cell = ann_cell(an);
     if (args.remap) cell = args.remap[cell];
-    const uint32_t n = (uint32_t)cfg.n_wl;
-    const uint32_t idx[3] = {cell / (n * n), (cell / n) % n, cell % n};
+    uint32_t ci1, ci2, ci3;
+    cell_indices(cfg, cell, ci1, ci2, ci3);
+    const uint32_t idx[3] = {ci1, ci2, ci3};
     if (lane == 0) dst[o] = '_';
     o += 1;
 #pragma unroll
@@ -234,31 +235,39 @@ __device__ __forceinline__ uint4 ldg16_safe(const uint8_t* buf, size_t off, size
 // Copy n bytes from global memory (file offset src) to shared memory (byte offset d of s_out) with one
 // eight-lane group: byte copies up to the next 16-byte boundary of the destination, 16-byte chunks
 // (two aligned 16-byte loads funnel-shifted into one aligned 16-byte store), byte copies for the rest.
+// Head and tail are at most 15 bytes each: two predicated byte copies per lane, no variable-trip loops.
 __device__ __forceinline__ void group_copy(uint8_t* s_out, uint32_t d, const uint8_t* buf, size_t src, size_t len, uint32_t n, int gl)
 {
     uint32_t head = (16u - (d & 15u)) & 15u;
     head = head < n ? head : n;
-    for (uint32_t i = gl; i < head; i += kGroup) s_out[d + i] = buf[src + i];
-    const uint32_t nchunks = (n - head) >> 4;
-    if (nchunks) {
-        const size_t s = src + head;
-        const size_t sal = s & ~(size_t)15;
-        const uint32_t ws = (uint32_t)(s & 15) >> 2, bs = ((uint32_t)s & 3u) * 8u;
-        uint4* dst = reinterpret_cast<uint4*>(s_out + d + head);
-        for (uint32_t c = gl; c < nchunks; c += kGroup) {
-            const uint4 A = ldg16_safe(buf, sal + 16u * c, len);
-            const uint4 B = ldg16_safe(buf, sal + 16u * c + 16u, len);
-            uint32_t w0, w1, w2, w3, w4;
-            if (ws == 0) { w0 = A.x; w1 = A.y; w2 = A.z; w3 = A.w; w4 = B.x; }
-            else if (ws == 1) { w0 = A.y; w1 = A.z; w2 = A.w; w3 = B.x; w4 = B.y; }
-            else if (ws == 2) { w0 = A.z; w1 = A.w; w2 = B.x; w3 = B.y; w4 = B.z; }
-            else { w0 = A.w; w1 = B.x; w2 = B.y; w3 = B.z; w4 = B.w; }
-            dst[c] = make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs),
-                                __funnelshift_r(w3, w4, bs));
-        }
+    const uint8_t* sp = buf + src;
+    uint8_t* dp = s_out + d;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const uint32_t i = (uint32_t)gl + 8u * t;
+        if (i < head) dp[i] = sp[i];
     }
-    const uint32_t done = head + (nchunks << 4);
-    for (uint32_t i = done + gl; i < n; i += kGroup) s_out[d + i] = buf[src + i];
+    const uint32_t nchunks = (n - head) >> 4;
+    const size_t s = src + head;
+    const size_t sal = s & ~(size_t)15;
+    const uint32_t ws = (uint32_t)(s & 15) >> 2, bs = ((uint32_t)s & 3u) * 8u;
+    uint4* dst = reinterpret_cast<uint4*>(dp + head);
+    for (uint32_t c = gl; c < nchunks; c += kGroup) {
+        const uint4 A = ldg16_safe(buf, sal + 16u * c, len);
+        const uint4 B = ldg16_safe(buf, sal + 16u * c + 16u, len);
+        // words [ws, ws + 5) of A:B, selected without branches (ws differs between the groups of a warp)
+        const bool s2 = ws & 2u, s1 = ws & 1u;
+        const uint32_t t0 = s2 ? A.z : A.x, t1 = s2 ? A.w : A.y, t2 = s2 ? B.x : A.z, t3 = s2 ? B.y : A.w, t4 = s2 ? B.z : B.x,
+                       t5 = s2 ? B.w : B.y;
+        const uint32_t w0 = s1 ? t1 : t0, w1 = s1 ? t2 : t1, w2 = s1 ? t3 : t2, w3 = s1 ? t4 : t3, w4 = s1 ? t5 : t4;
+        dst[c] = make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
+    }
+    const uint32_t done = head + (nchunks << 4), tail = n - done;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const uint32_t i = (uint32_t)gl + 8u * t;
+        if (i < tail) dp[done + i] = sp[done + i];
+    }
 }
 
 // Eight lanes write one output record into the staging buffer at byte offset d; returns its length.
@@ -298,24 +307,51 @@ __device__ __forceinline__ uint32_t emit_group(const EmitArgs<OffT>& args, const
     const uint64_t an = args.ann[r];
     uint32_t cell = ann_cell(an);
     if (args.remap) cell = args.remap[cell];
-    const uint32_t n = (uint32_t)cfg.n_wl;
-    const uint32_t i1 = cell / (n * n), i2 = (cell / n) % n, i3 = cell % n;
-    const uint32_t l1 = cfg.wl_len[i1], l2 = cfg.wl_len[i2], l3 = cfg.wl_len[i3];
-    const uint32_t ulen = ann_umi_len(an, cfg.umi_len);
-    const uint32_t c1 = 1u, c2 = c1 + l1, c3 = c2 + l2, c4 = c3 + l3, c5 = c4 + 1u, c6 = c5 + ulen, lit = c6 + 1u;
+    uint32_t i1, i2, i3;
+    cell_indices(cfg, cell, i1, i2, i3);
     const bool regular = ann_state(an) == 1;
     const uint64_t payload = ann_payload(an);
-    for (uint32_t k = gl; k < lit; k += kGroup) {
-        uint32_t ch;
-        if (k == 0u || k == c4) ch = '_';
-        else if (k < c2) ch = cfg.wl[i1 * 8u + (k - c1)];
-        else if (k < c3) ch = cfg.wl[i2 * 8u + (k - c2)];
-        else if (k < c4) ch = cfg.wl[i3 * 8u + (k - c3)];
-        else if (k < c6) ch = regular ? (uint32_t)base2_char((uint32_t)(payload >> (2u * (k - c5)))) : (uint32_t)args.r2buf[(size_t)(payload >> 5) + (k - c5)];
-        else ch = '\n';
-        s_out[d + o + k] = (uint8_t)ch;
+    if (cfg.bc8 && regular && cfg.umi_len == 10) {
+        // fixed layout, 37 bytes: k = 0 '_', 1..24 barcodes, 25 '_', 26..35 UMI, 36 '\n'; lane gl writes k = gl + 8t
+        uint8_t* q = s_out + d + o;
+#pragma unroll
+        for (uint32_t t = 0; t < 3; t++) {
+            const uint32_t k = (uint32_t)gl + 8u * t;
+            uint32_t ch = '_';
+            if (k) {
+                const uint32_t which = (k - 1u) >> 3, idx = which == 0u ? i1 : (which == 1u ? i2 : i3);
+                ch = cfg.wl[idx * 8u + ((k - 1u) & 7u)];
+            }
+            q[k] = (uint8_t)ch;
+        }
+        {
+            const uint32_t k = 24u + (uint32_t)gl;  // 24: last barcode byte, 25: '_', 26..31: UMI 0..5
+            uint32_t ch = gl == 0 ? (uint32_t)cfg.wl[i3 * 8u + 7u] : (uint32_t)'_';
+            if (gl >= 2) ch = __byte_perm(0x47544341u, 0u, (uint32_t)(payload >> (2u * (uint32_t)(gl - 2))) & 3u) & 0xFFu;
+            q[k] = (uint8_t)ch;
+        }
+        if (gl < 5) {  // 32..35: UMI 6..9, 36: '\n'
+            uint32_t ch = '\n';
+            if (gl < 4) ch = __byte_perm(0x47544341u, 0u, (uint32_t)(payload >> (2u * (uint32_t)(gl + 6))) & 3u) & 0xFFu;
+            q[32 + gl] = (uint8_t)ch;
+        }
+        o += 37u;
+    } else {
+        const uint32_t l1 = cfg.wl_len[i1], l2 = cfg.wl_len[i2], l3 = cfg.wl_len[i3];
+        const uint32_t ulen = ann_umi_len(an, cfg.umi_len);
+        const uint32_t c1 = 1u, c2 = c1 + l1, c3 = c2 + l2, c4 = c3 + l3, c5 = c4 + 1u, c6 = c5 + ulen, lit = c6 + 1u;
+        for (uint32_t k = gl; k < lit; k += kGroup) {
+            uint32_t ch;
+            if (k == 0u || k == c4) ch = '_';
+            else if (k < c2) ch = cfg.wl[i1 * 8u + (k - c1)];
+            else if (k < c3) ch = cfg.wl[i2 * 8u + (k - c2)];
+            else if (k < c4) ch = cfg.wl[i3 * 8u + (k - c3)];
+            else if (k < c6) ch = regular ? (uint32_t)base2_char((uint32_t)(payload >> (2u * (k - c5)))) : (uint32_t)args.r2buf[(size_t)(payload >> 5) + (k - c5)];
+            else ch = '\n';
+            s_out[d + o + k] = (uint8_t)ch;
+        }
+        o += lit;
     }
-    o += lit;
 
     // read, "+", quality — each rstrip()ped (V2:246, 249)
     group_copy(s_out, d + o, args.r1buf, start + seq_rel, args.r1_len, seq_len, gl);

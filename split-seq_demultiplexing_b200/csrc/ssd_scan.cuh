@@ -19,13 +19,22 @@
 
 namespace ssd {
 
-constexpr int kTile = 32768;   // bytes of the file owned by one scan block
-constexpr int kHalo = 2048;    // extra bytes loaded so records that start in the tile are whole
+#ifndef SSD_SCAN_TILE
+#define SSD_SCAN_TILE 24576
+#endif
+#ifndef SSD_SCAN_SLOTS
+#define SSD_SCAN_SLOTS 3
+#endif
+constexpr int kTile = SSD_SCAN_TILE;  // bytes of the file owned by one tile
+constexpr int kHalo = 2048;           // extra bytes loaded so records that start in the tile are whole
+constexpr int kWinSlots = SSD_SCAN_SLOTS;  // window buffers per block: 1 being filled, kDepth waiting for their line index, 1 in use
+constexpr int kDepth = kWinSlots - 2;      // how many tiles the bitmap/list stage runs ahead of the record stage
+constexpr int kListSlots = kDepth + 1;
 constexpr int kWin = kTile + kHalo;
 constexpr int kWinWords = kWin / 32;
 constexpr int kTileWords = kTile / 32;
 constexpr int kHaloWords = kHalo / 32;
-constexpr int kMaxRecTile = 1024;                 // records starting in one tile (>= 32 bytes each on average)
+constexpr int kMaxRecTile = kTile / 32;            // records starting in one tile (>= 32 bytes each on average)
 constexpr int kMaxLines = 4 * kMaxRecTile + 72;   // line-start list entries (tile + halo)
 
 constexpr unsigned long long kFlagAgg = 1ull << 62;
@@ -56,12 +65,12 @@ struct ScanArgs {
     OffT* r1_start;
     uint4* r1_meta;
     uint32_t* r1_base;
+    unsigned long long* r1_tok;  // read id fingerprint: 64-bit hash of the first header token, low 16 bits = its length
     // read 2 inputs / outputs
     const uint8_t* r1buf;
     size_t r1_len;
     uint64_t* ann;
     uint32_t* hist;
-    uint64_t* keys;
     IrrKey* irr;
     const uint8_t* lut;  // (e + 1) levels of 65536 bytes
 };
@@ -119,6 +128,37 @@ __device__ __forceinline__ uint32_t ldg_word_safe(const uint8_t* buf, size_t off
     return v;
 }
 
+// ---- read-id fingerprint -------------------------------------------------------------------------------
+// The mate join of the reference is by read id (V2:349-350).  Read 1's scan leaves, per record, a 64-bit
+// fingerprint of the id (first whitespace-delimited header token): a hash over the token taken as little-endian
+// 32-bit words from its first byte (last word zero-padded), with the token length in the low 16 bits.  Read 2's
+// scan compares fingerprints instead of chasing read 1's bytes through global memory.
+__device__ __forceinline__ unsigned long long tok_hash_step(unsigned long long h, uint32_t word)
+{
+    h = (h ^ (unsigned long long)word) * 0xFF51AFD7ED558CCDull;
+    return h ^ (h >> 29);
+}
+__device__ __forceinline__ unsigned long long tok_hash_finish(unsigned long long h, uint32_t len)
+{
+    h = (h ^ (unsigned long long)len) * 0xC4CEB9FE1A85EC53ull;
+    h ^= h >> 32;
+    return (h & ~0xFFFFull) | (unsigned long long)(len & 0xFFFFu);
+}
+constexpr unsigned long long kTokSeed = 0x9E3779B97F4A7C15ull;
+
+template <class Acc>
+__device__ __forceinline__ unsigned long long tok_hash_generic(const Acc& a, size_t tok_s, size_t tok_e)
+{
+    unsigned long long h = kTokSeed;
+    for (size_t p = tok_s; p < tok_e; p += 4) {
+        uint32_t w = 0;
+        for (int b = 0; b < 4; b++)
+            if (p + b < tok_e) w |= a.byte(p + b) << (8 * b);
+        h = tok_hash_step(h, w);
+    }
+    return tok_hash_finish(h, (uint32_t)(tok_e - tok_s));
+}
+
 // ======================================================================================================
 // exact generic path (any accessor)
 // ======================================================================================================
@@ -159,37 +199,31 @@ __device__ __noinline__ bool r1_record_generic(const Acc& a, const ScanArgs<OffT
         m.x = m.y = m.z = 0;
         m.w = kMetaLong;
     }
+    size_t tok_e = L.s[0];
+    while (tok_e < L.e[0] && !py_space(a.byte(tok_e))) tok_e++;
     args.r1_start[r] = (OffT)start;
     args.r1_meta[r] = m;
     args.r1_base[r] = kept_at_last_nonspace + (uint32_t)seq_len + (uint32_t)qual_len + 7u;
+    args.r1_tok[r] = tok_hash_generic(a, L.s[0], tok_e);
     return true;
 }
 
 struct R2Out {
     uint64_t ann;  // 0 = rejected
-    uint64_t key;  // regular key
     IrrKey irr;
 };
 
-// Mate join by read id (V2:349-350), exact and bytewise: token [tok_s, tok_e) of read 2 against the first
-// whitespace-delimited token of read-1 record r.
+// Mate join by read id (V2:349-350): read-2 token [tok_s, tok_e) against the fingerprint read 1 left for record r.
 template <class Acc, typename OffT>
-__device__ __forceinline__ bool mate_ok_generic(const Acc& a, const ScanArgs<OffT>& args, uint64_t r, size_t tok_s, size_t tok_e)
+__device__ __forceinline__ bool mate_ok_generic(const Acc& a, const ScanArgs<OffT>& args, uint64_t r, size_t tok_s, size_t tok_e, uint64_t n_rec_r1)
 {
-    if (r >= args.cnt->n_records[0]) return false;
-    const size_t o1 = (size_t)args.r1_start[r];
-    for (size_t j = 0;; j++) {
-        bool e2 = tok_s + j >= tok_e;
-        uint32_t c1 = o1 + j < args.r1_len ? args.r1buf[o1 + j] : (uint32_t)'\n';
-        bool e1 = py_space(c1);
-        if (e1 || e2) return e1 && e2;
-        if (c1 != a.byte(tok_s + j)) return false;
-    }
+    if (r >= n_rec_r1) return false;
+    return args.r1_tok[r] == tok_hash_generic(a, tok_s, tok_e);
 }
 
 template <class Acc, typename OffT>
 __device__ __noinline__ bool r2_record_generic(const Acc& a, const ScanArgs<OffT>& args, const DevCfg& cfg, uint64_t r, size_t start,
-                                               R2Out& out, bool& complete)
+                                               R2Out& out, bool& complete, uint64_t n_rec_r1)
 {
     Lines L;
     out.ann = 0;
@@ -221,7 +255,7 @@ __device__ __noinline__ bool r2_record_generic(const Acc& a, const ScanArgs<OffT
 
     size_t tok_e = L.s[0];
     while (tok_e < L.e[0] && !py_space(a.byte(tok_e))) tok_e++;
-    if (!mate_ok_generic(a, args, r, L.s[0], tok_e)) {
+    if (!mate_ok_generic(a, args, r, L.s[0], tok_e, n_rec_r1)) {
         raise(args.cnt, args.err_off, 1, kErrKey, start);
         return true;
     }
@@ -241,7 +275,6 @@ __device__ __noinline__ bool r2_record_generic(const Acc& a, const ScanArgs<OffT
     }
     if (regular) {
         out.ann = kAnnRegular | ((uint64_t)cell << kAnnCellShift) | code;
-        out.key = ((uint64_t)cell << cfg.umi_bits) | code;
     } else {
         out.ann = kAnnIrregular | ((uint64_t)cell << kAnnCellShift) | ((uint64_t)(seq_s + ulo) << 5) | (uint64_t)ulen;
         out.irr.hi = ((uint64_t)cell << kIrrCellShift) | ((uint64_t)ulen << 32) | hi;
@@ -296,354 +329,473 @@ __device__ __forceinline__ int match8(const DevCfg& cfg, const uint8_t* __restri
 constexpr int kScanR1 = 0;
 constexpr int kScanR2 = 1;
 
-template <int MODE, typename OffT>
-__global__ void __launch_bounds__(kThreads) k_scan(const __grid_constant__ ScanArgs<OffT> args, const __grid_constant__ DevCfg cfg)
-{
-    __shared__ __align__(128) uint8_t s_win[kWin + 16];
-    __shared__ __align__(16) uint32_t s_mask[kWinWords];
-    __shared__ uint16_t s_lstart[kMaxLines];
-    __shared__ uint32_t s_warp[kThreads / 32];
-    __shared__ uint32_t s_halo[2];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ unsigned int s_tile;
-    __shared__ unsigned long long s_line_base;
-    __shared__ unsigned int s_nk, s_ni;
-    __shared__ unsigned long long s_kbase, s_ibase;
+constexpr int kComputeWarps = 8;
+constexpr int kComputeThreads = kComputeWarps * 32;
+constexpr uint32_t kNoTile = 0xFFFFFFFFu;
+constexpr int kScanThreads = kComputeThreads + 64;  // eight compute warps + the copy warp + the prefix warp (works in block 0)
 
+// Shared memory of one persistent scan block.
+constexpr int kWinChunks = kWin / 16;                    // 16-byte chunks of a window
+constexpr int kChunksPerWarp = kWinChunks / kComputeWarps;  // each compute warp owns a contiguous run of chunks
+constexpr int kRows = (kChunksPerWarp + 31) / 32;        // 32-chunk rows per warp
+static_assert(kWinChunks % kComputeWarps == 0, "window size");
+
+struct __align__(128) ScanSmem {
+    uint8_t win[kWinSlots][kWin + 128];       // tile windows (bulk-copy destinations)
+    uint16_t lstart[kListSlots][kMaxLines];   // line-start lists of the tiles between stage A and stage B
+    unsigned long long full[kWinSlots], empty[kWinSlots];  // mbarriers: bytes landed / window may be refilled
+    unsigned long long line_base;
+    uint32_t tile[kWinSlots];
+    uint32_t total[kListSlots], n_listed[kListSlots];
+    uint32_t warp_tile[kComputeWarps], halo_sum[2];
+    uint32_t mask[kWinWords];                 // newline bitmap of the tile in stage A (bit b of word w = byte 32 w + b)
+};
+
+#ifdef SSD_SCAN_PROFILE
+__device__ unsigned long long g_scan_prof[2][8];
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(slot, a, b) if (tid == 0) prof[slot] += (unsigned long long)((b) - (a))
+#else
+#define PROF_T(var)
+#define PROF_ADD(slot, a, b)
+#endif
+
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent, warp-specialised scan: one wave of blocks, tiles are claimed in order through a ticket.
+//   copy warp     claims tiles and keeps kWinSlots bulk copies (TMA) in flight / in use
+//   prefix warp   (block 0) walks the per-tile newline counts in tile order and turns each into the inclusive
+//                 prefix, so a tile learns its global line index with one poll of its own entry
+//   compute warps stage A(i + kDepth): newline bitmap (kept in registers), count (published), line-start list
+//                 stage B(i)         : poll the line index, process the records that start in the tile
+template <int MODE, typename OffT>
+__global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant__ ScanArgs<OffT> args, const __grid_constant__ DevCfg cfg)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    ScanSmem& S = *reinterpret_cast<ScanSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        s_tile = atomicAdd(&args.cnt->ticket[MODE], 1u);  // tiles are claimed in order: look-back never waits on an unstarted tile
-        mbar_init(&s_bar, 1);
-        s_nk = 0;
-        s_ni = 0;
-    }
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const size_t tile_lo = (size_t)tile * kTile;
-    const uint32_t win_bytes = (uint32_t)(args.len - tile_lo < (size_t)kWin ? args.len - tile_lo : (size_t)kWin);
-
-    load_window(s_win, args.buf + tile_lo, win_bytes, &s_bar, 0);
-    build_nl_mask(s_win, win_bytes, reinterpret_cast<uint16_t*>(s_mask), kWinWords * 2);
-    __syncthreads();
-
-    // ---- newlines owned by this tile: mask words [0, kTileWords), 4 per thread; halo words: 1 per thread of warps 0-1
-    uint32_t m[4], cnt = 0;
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        m[w] = s_mask[4 * tid + w];
-        cnt += __popc(m[w]);
-    }
-    const uint32_t hm = tid < kHaloWords ? s_mask[kTileWords + tid] : 0u;
-    uint32_t incl = cnt, hincl = __popc(hm);
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        uint32_t hv = __shfl_up_sync(0xFFFFFFFFu, hincl, d);
-        if (lane >= d) {
-            incl += v;
-            hincl += hv;
+        for (int s = 0; s < kWinSlots; s++) {
+            mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), 1);
+            mbar_init(reinterpret_cast<uint64_t*>(&S.empty[s]), 1);
         }
     }
-    if (lane == 31) {
-        s_warp[warp] = incl;
-        if (warp < 2) s_halo[warp] = hincl;
-    }
     __syncthreads();
-    uint32_t warp_base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; w++) {
-        uint32_t v = s_warp[w];
-        if (w < warp) warp_base += v;
-        total += v;
-    }
-    const uint32_t excl = warp_base + incl - cnt;
-    const uint32_t halo_total = s_halo[0] + s_halo[1];
-    const uint32_t hexcl = total + (warp == 1 ? s_halo[0] : 0u) + hincl - (uint32_t)__popc(hm);
+    volatile unsigned long long* st = args.status;
 
-    // ---- decoupled look-back over the tile newline counts, 32 predecessors per probe (warp 0) ----
-    if (warp == 0) {
-        volatile unsigned long long* st = args.status;
-        unsigned long long excl_lines = 0;
-        if (tile == 0) {
-            if (lane == 0) st[0] = kFlagPrefix | total;
-        } else {
-            if (lane == 0) st[tile] = kFlagAgg | total;
-            long long base = (long long)tile - 1;
-            for (;;) {
-                const long long idx = base - lane;
-                unsigned long long v = 2ull << 62;  // before tile 0: an inclusive prefix of 0
-                if (idx >= 0) v = st[idx];
-                const uint32_t flag = (uint32_t)(v >> 62);
-                const uint32_t ready = __ballot_sync(0xFFFFFFFFu, flag != 0u);
-                const uint32_t pref = __ballot_sync(0xFFFFFFFFu, flag == 2u);
-                const uint32_t first_pref = pref ? (uint32_t)__ffs((int)pref) - 1u : 31u;
-                const uint32_t need = first_pref >= 31u ? 0xFFFFFFFFu : ((2u << first_pref) - 1u);  // lanes 0..first_pref
-                if ((ready & need) != need) continue;  // a closer tile has not published yet: probe again
-                unsigned long long contrib = ((need >> lane) & 1u) ? (v & kStatusValue) : 0ull;
+    if (warp == kComputeWarps + 1) {
+        // ================================ prefix warp (block 0 only) ================================
+        if (blockIdx.x != 0) return;
+        // every lane takes 8 consecutive entries (256 tiles per round trip to L2)
+        unsigned long long running = 0;
+        uint32_t next = 0, ns = 20;
+        while (next < args.n_tiles) {
+            unsigned long long v[8];
+            const uint32_t first = next + 8u * (uint32_t)lane;
 #pragma unroll
-                for (int d = 16; d; d >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, d);
-                excl_lines += contrib;
-                if (pref) break;
-                base -= 32;
+            for (int k = 0; k < 8; k++) v[k] = first + k < args.n_tiles ? st[first + k] : 0ull;
+            // leading published entries of this lane, then of the whole warp
+            uint32_t mine = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (mine == (uint32_t)k && (v[k] >> 62) != 0ull) mine = k + 1u;
+            const uint32_t full = __ballot_sync(0xFFFFFFFFu, mine == 8u);
+            const uint32_t lead = full == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~full) - 1u;  // lanes whose 8 entries are all published
+            const uint32_t partial = __shfl_sync(0xFFFFFFFFu, mine, lead < 32u ? (int)lead : 31);
+            const uint32_t take = (uint32_t)lane < lead ? 8u : ((uint32_t)lane == lead ? partial : 0u);  // entries this lane finalises
+            unsigned long long sum = 0, pre[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if ((uint32_t)k < take) sum += v[k] & kStatusValue;
+                pre[k] = sum;
             }
-            if (lane == 0) st[tile] = kFlagPrefix | (excl_lines + total);
+            unsigned long long incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += u;
+            }
+            const unsigned long long lane_base = running + incl - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if ((uint32_t)k < take) st[first + k] = kFlagPrefix | (lane_base + pre[k]);
+            running += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            const uint32_t advanced = 8u * lead + (lead < 32u ? partial : 0u);
+            next += advanced;
+            if (advanced == 0) {
+                __nanosleep(ns);
+                if (ns < 200u) ns += ns;
+            } else {
+                ns = 20;
+            }
         }
-        if (lane == 0) {
-            s_line_base = excl_lines;
+        return;
+    }
+    if (warp == kComputeWarps) {
+        // ================================ copy warp ================================
+        for (uint32_t it = 0;; it++) {
+            const uint32_t ws = it % kWinSlots;
+            if (it >= (uint32_t)kWinSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.empty[ws]), ((it / kWinSlots) - 1u) & 1u);
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(&args.cnt->ticket[MODE], 1u);  // tiles are claimed in order: nobody waits on an unclaimed tile
+            t = __shfl_sync(0xFFFFFFFFu, t, 0);
+            if (t >= args.n_tiles) {
+                if (lane == 0) {
+                    S.tile[ws] = kNoTile;
+                    mbar_arrive(&S.full[ws]);
+                }
+                break;
+            }
+            const size_t tile_lo = (size_t)t * kTile;
+            const uint32_t wb = (uint32_t)(args.len - tile_lo < (size_t)kWin ? args.len - tile_lo : (size_t)kWin);
+            const uint32_t bulk = wb & ~15u;
+            for (uint32_t i = bulk + lane; i < wb; i += 32u) S.win[ws][i] = args.buf[tile_lo + i];
+            __syncwarp();
+            if (lane == 0) {
+                S.tile[ws] = t;
+                if (bulk) {
+                    mbar_expect_tx(reinterpret_cast<uint64_t*>(&S.full[ws]), bulk);
+                    bulk_g2s(S.win[ws], args.buf + tile_lo, bulk, reinterpret_cast<uint64_t*>(&S.full[ws]));
+                } else {
+                    mbar_arrive(&S.full[ws]);
+                }
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ================================ compute warps ================================
+#ifdef SSD_SCAN_PROFILE
+    unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    const uint64_t n_rec_r1 = MODE == kScanR2 ? args.cnt->n_records[0] : 0;  // read 1 was scanned by the previous launch
+
+    // stage A: newline bitmap, count, line-start list of the block's it-th tile; false when the tiles are exhausted
+    auto stage_a = [&](uint32_t it) -> bool {
+        const uint32_t ws = it % kWinSlots, ls = it % kListSlots;
+        PROF_T(t0);
+        mbar_wait(reinterpret_cast<uint64_t*>(&S.full[ws]), (it / kWinSlots) & 1u);
+        PROF_T(t1);
+        PROF_ADD(0, t0, t1);
+        const uint32_t tile = S.tile[ws];
+        if (tile == kNoTile) return false;
+        const size_t tile_lo = (size_t)tile * kTile;
+        const uint32_t win_bytes = (uint32_t)(args.len - tile_lo < (size_t)kWin ? args.len - tile_lo : (size_t)kWin);
+        const uint8_t* s_win = S.win[ws];
+        uint32_t* s_mask = S.mask;
+        uint16_t* s_lstart = S.lstart[ls];
+        build_nl_mask<kComputeThreads, (kWinWords * 2 + kComputeThreads - 1) / kComputeThreads>(s_win, win_bytes, reinterpret_cast<uint16_t*>(s_mask),
+                                                                                                 kWinWords * 2);
+        compute_sync();
+        PROF_T(t2);
+        PROF_ADD(1, t1, t2);
+        // newlines owned by this tile: mask words [0, kTileWords), WPT consecutive ones per thread; halo words: 1 per thread of warps 0-1
+        constexpr int WPT = kTileWords / kComputeThreads;  // 2, 3 or 4 mask words per thread (16 / 24 / 32 KiB tiles)
+        static_assert(WPT >= 2 && WPT <= 4 && WPT * kComputeThreads == kTileWords, "tile size");
+        static_assert(kHaloWords <= 64, "halo size");
+        uint32_t m[4] = {0u, 0u, 0u, 0u}, cnt = 0;
+#pragma unroll
+        for (int w = 0; w < WPT; w++) {
+            m[w] = s_mask[WPT * tid + w];
+            cnt += __popc(m[w]);
+        }
+        const uint32_t hm = tid < kHaloWords ? s_mask[kTileWords + tid] : 0u;
+        uint32_t incl = cnt, hincl = __popc(hm);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            uint32_t hv = __shfl_up_sync(0xFFFFFFFFu, hincl, d);
+            if (lane >= d) {
+                incl += v;
+                hincl += hv;
+            }
+        }
+        if (lane == 31) {
+            S.warp_tile[warp] = incl;
+            if (warp < 2) S.halo_sum[warp] = hincl;
+        }
+        compute_sync();
+        uint32_t warp_base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kComputeWarps; w++) {
+            uint32_t v = S.warp_tile[w];
+            if (w < warp) warp_base += v;
+            total += v;
+        }
+        const uint32_t excl = warp_base + incl - cnt;
+        const uint32_t halo0 = S.halo_sum[0], halo_total = halo0 + S.halo_sum[1];
+        const uint32_t hexcl = total + (warp == 1 ? halo0 : 0u) + hincl - (uint32_t)__popc(hm);
+        if (tid == 0) {
+            S.total[ls] = total;
+            S.n_listed[ls] = total + halo_total;
+            st[tile] = kFlagAgg | total;  // published: the prefix warp takes it from here
+            s_lstart[0] = 0;
+        }
+        // line-start list: s_lstart[1 + k] = byte after the k-th newline of the window (tile first, then halo);
+        // one newline per iteration for every lane that still has one: warp-uniform trip count
+        {
+            unsigned long long lo = (unsigned long long)m[0] | ((unsigned long long)m[1] << 32);
+            unsigned long long hi = (unsigned long long)m[2] | ((unsigned long long)m[3] << 32);
+            const uint32_t trip_nl = __reduce_max_sync(0xFFFFFFFFu, cnt);
+            for (uint32_t k = 0; k < trip_nl; k++) {
+                if (k < cnt) {
+                    uint32_t b;
+                    if (lo) {
+                        b = (uint32_t)__ffsll((long long)lo) - 1u;
+                        lo &= lo - 1ull;
+                    } else {
+                        b = 64u + (uint32_t)__ffsll((long long)hi) - 1u;
+                        hi &= hi - 1ull;
+                    }
+                    const uint32_t idx = excl + k + 1u;
+                    if (idx < (uint32_t)kMaxLines) s_lstart[idx] = (uint16_t)(tid * (32 * WPT) + b + 1);
+                }
+            }
+            uint32_t hrank = hexcl, mm = hm;
+            while (mm) {
+                uint32_t b = (uint32_t)__ffs((int)mm) - 1u;
+                mm &= mm - 1u;
+                if (hrank + 1u < (uint32_t)kMaxLines) s_lstart[hrank + 1u] = (uint16_t)((kTileWords + tid) * 32 + b + 1);
+                hrank++;
+            }
+        }
+        compute_sync();  // list complete; warp_tile / halo_sum / mask may be reused
+        PROF_T(t3);
+        PROF_ADD(2, t2, t3);
+        return true;
+    };
+
+    // stage B: the records that start in the block's it-th tile
+    auto stage_b = [&](uint32_t it) {
+        const uint32_t ws = it % kWinSlots, ls = it % kListSlots;
+        const uint32_t tile = S.tile[ws];
+        const size_t tile_lo = (size_t)tile * kTile;
+        const uint32_t win_bytes = (uint32_t)(args.len - tile_lo < (size_t)kWin ? args.len - tile_lo : (size_t)kWin);
+        const uint8_t* s_win = S.win[ws];
+        const uint16_t* s_lstart = S.lstart[ls];
+        const uint32_t total = S.total[ls];
+        const uint32_t n_listed = S.n_listed[ls];
+        PROF_T(t4);
+        if (tid == 0) {
+            // the inclusive newline prefix of this tile, written by the prefix warp
+            unsigned long long v;
+            uint32_t ns = 20;
+            while (((v = st[tile]) >> 62) != 2ull) {
+                __nanosleep(ns);
+                if (ns < 200u) ns += ns;
+            }
+            const unsigned long long excl_lines = (v & kStatusValue) - total;
+            S.line_base = excl_lines;
             if (tile == args.n_tiles - 1) {
                 unsigned long long n_lines = excl_lines + total + ((args.len && s_win[win_bytes - 1] != '\n') ? 1ull : 0ull);
                 args.cnt->n_lines[MODE] = n_lines;
                 args.cnt->n_records[MODE] = n_lines >> 2;
             }
         }
-    }
+        compute_sync();
+        PROF_T(t5);
+        PROF_ADD(3, t4, t5);
+        const unsigned long long line_base = S.line_base;
 
-    // ---- line-start list: s_lstart[1 + k] = byte after the k-th newline of the window (tile first, then halo) ----
-    const uint32_t n_listed = total + halo_total;  // newlines listed when everything fits
-    {
-        uint32_t rank = excl;
-#pragma unroll
-        for (int w = 0; w < 4; w++) {
-            uint32_t mm = m[w];
-            while (mm) {
-                uint32_t b = (uint32_t)__ffs((int)mm) - 1u;
-                mm &= mm - 1u;
-                if (rank + 1u < (uint32_t)kMaxLines) s_lstart[rank + 1u] = (uint16_t)((4 * tid + w) * 32 + b + 1);
-                rank++;
-            }
+        // records that start in this tile: the line after a newline whose next-line index is 0 mod 4
+        const unsigned long long r_first = tile == 0 ? 0ull : (line_base + 4) >> 2;
+        const unsigned long long r_end = ((line_base + total) >> 2) + 1;  // exclusive
+        uint32_t n_rec = r_end > r_first ? (uint32_t)(r_end - r_first) : 0u;
+        if (tile == 0 && args.len == 0) n_rec = 0;
+        if (n_rec > (uint32_t)kMaxRecTile || n_listed + 1u > (uint32_t)kMaxLines) {
+            if (tid == 0) atomicOr(&args.cnt->err_flags, kErrDense);
+            n_rec = 0;
         }
-        uint32_t hrank = hexcl, mm = hm;
-        while (mm) {
-            uint32_t b = (uint32_t)__ffs((int)mm) - 1u;
-            mm &= mm - 1u;
-            if (hrank + 1u < (uint32_t)kMaxLines) s_lstart[hrank + 1u] = (uint16_t)((kTileWords + tid) * 32 + b + 1);
-            hrank++;
-        }
-        if (tid == 0) s_lstart[0] = 0;
-    }
-    __syncthreads();
-    const unsigned long long line_base = s_line_base;
+        const uint32_t j_first = (uint32_t)(4ull * r_first - line_base);  // list index of the first record's start
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(s_win);
+        GlobAcc ga{args.buf, args.len};
 
-    // records that start in this tile: the line after a newline whose next-line index is 0 mod 4
-    const unsigned long long r_first = tile == 0 ? 0ull : (line_base + 4) >> 2;
-    const unsigned long long r_end = ((line_base + total) >> 2) + 1;  // exclusive
-    uint32_t n_rec = r_end > r_first ? (uint32_t)(r_end - r_first) : 0u;
-    if (tile == 0 && args.len == 0) n_rec = 0;
-    if (n_rec > (uint32_t)kMaxRecTile || n_listed + 1u > (uint32_t)kMaxLines) {
-        if (tid == 0) atomicOr(&args.cnt->err_flags, kErrDense);
-        return;
-    }
-    const uint32_t j_first = (uint32_t)(4ull * r_first - line_base);  // list index of the first record's start
-
-    const uint32_t* words = reinterpret_cast<const uint32_t*>(s_win);
-    WinAcc wa{s_win, s_mask, tile_lo, win_bytes, args.len};
-    GlobAcc ga{args.buf, args.len};
-
-    for (uint32_t base = 0; base < n_rec; base += kThreads) {
-        const uint32_t i = base + tid;
-        const bool have = i < n_rec;
-        const uint64_t r = r_first + i;
-        const uint32_t j0 = j_first + 4u * i;
-        uint32_t s0 = 0, s1 = 1, s2 = 1, s3 = 1, s4 = 1;
-        bool fast = false;
-        if (have) {
-            s0 = s_lstart[j0];
-            if (j0 + (MODE == kScanR1 ? 4u : 3u) <= n_listed) {
-                s1 = s_lstart[j0 + 1];
-                s2 = s_lstart[j0 + 2];
-                s3 = s_lstart[j0 + 3];
-                if (MODE == kScanR1) s4 = s_lstart[j0 + 4];
-                fast = MODE == kScanR1 ? true : tile_lo + s3 < args.len;  // line 3 must exist
-                if (r >= args.rec_cap) {
-                    atomicOr(&args.cnt->err_flags, kErrOverflow);
-                    fast = false;
+        for (uint32_t base = 0; base < n_rec; base += kComputeThreads) {
+            const uint32_t i = base + tid;
+            const bool have = i < n_rec;
+            const uint64_t r = r_first + i;
+            const uint32_t j0 = j_first + 4u * i;
+            uint32_t s0 = 0, s1 = 1, s2 = 1, s3 = 1, s4 = 1;
+            bool fast = false;
+            if (have) {
+                s0 = s_lstart[j0];
+                if (j0 + (MODE == kScanR1 ? 4u : 3u) <= n_listed) {
+                    s1 = s_lstart[j0 + 1];
+                    s2 = s_lstart[j0 + 2];
+                    s3 = s_lstart[j0 + 3];
+                    if (MODE == kScanR1) s4 = s_lstart[j0 + 4];
+                    // read 2 only needs line 3 to exist; the generic path raises the overflow flag
+                    fast = (MODE == kScanR1 || tile_lo + s3 < args.len) && r < args.rec_cap;
                 }
             }
-        }
-        // header geometry shared by both modes: bytes [s0, s0 + hdr_len), one trailing '\r' dropped
-        uint32_t hdr_len = fast ? s1 - 1u - s0 : 0u;
-        if (fast && hdr_len && s_win[s0 + hdr_len - 1u] == '\r') hdr_len--;
-        const uint32_t a = s0 & 3u, nbytes = a + hdr_len, nwords = fast ? (nbytes + 3u) >> 2 : 0u;
-        const uint32_t trip = __reduce_max_sync(0xFFFFFFFFu, nwords);
-
-        if (MODE == kScanR1) {
-            // ---- name.split("/")[0].replace(" ", "").strip() as counts (V2:135-138) ----
-            uint32_t cut = hdr_len, spaces = 0, bad = 0;
-            bool found = false;
-            for (uint32_t w = 0; w < trip; w++) {
-                if (w < nwords) {
-                    const uint32_t x = words[(s0 >> 2) + w];
-                    const uint32_t rem = nbytes - 4u * w;
-                    const uint32_t V = byte_range_flags(w == 0 ? a : 0u, rem < 4u ? rem : 4u);
-                    bad |= lt_flags(x, 0x20202020u) & V;
-                    if (!found) {
-                        const uint32_t zs = zero_flags(x ^ 0x2F2F2F2Fu) & V, zp = zero_flags(x ^ 0x20202020u) & V;
-                        if (zs) {
-                            const uint32_t bit = (uint32_t)__ffs((int)zs) - 1u;
-                            cut = 4u * w + (bit >> 3) - a;
-                            spaces += (uint32_t)__popc(zp & ((1u << bit) - 1u));
-                            found = true;
-                        } else {
-                            spaces += (uint32_t)__popc(zp);
-                        }
-                    }
-                }
-            }
-            uint32_t seq_e = s2 - 1u, qual_e = s4 - 1u;
-            bool ok = fast && bad == 0u;
-            if (ok) ok = rstrip2(s_win, s1, seq_e) && rstrip2(s_win, s3, qual_e);
-            if (ok) {
-                if (s_win[s0] != '@') raise(args.cnt, args.err_off, 0, kErrNoAt, tile_lo + s0);
-                uint4 mt;
-                mt.x = cut | ((cut - spaces) << 16);
-                mt.y = (s1 - s0) | ((seq_e - s1) << 16);
-                mt.z = (s3 - s0) | ((qual_e - s3) << 16);
-                mt.w = 0;
-                args.r1_start[r] = (OffT)(tile_lo + s0);
-                args.r1_meta[r] = mt;
-                args.r1_base[r] = (cut - spaces) + (seq_e - s1) + (qual_e - s3) + 7u;
-            }
-            __syncwarp();
-            if (have && !ok) {
-                const size_t start = tile_lo + s0;
-                if (!r1_record_generic(wa, args, r, start)) r1_record_generic(ga, args, r, start);
-            }
-            __syncwarp();
-        } else {
-            // ---- read id = first whitespace-delimited token of the header (V2:281-283) ----
-            uint32_t tok_len = hdr_len, ctl = 0;
+            // header bytes [s0, s0 + hdr_len), one trailing '\r' dropped; token = bytes before the first byte <= 0x20
+            uint32_t hdr_len = fast ? s1 - 1u - s0 : 0u;
+            if (fast && hdr_len && s_win[s0 + hdr_len - 1u] == '\r') hdr_len--;
+            const uint32_t a = s0 & 3u, nwords = fast ? (hdr_len + 3u) >> 2 : 0u;
+            const uint32_t trip = __reduce_max_sync(0xFFFFFFFFu, nwords);
+            // one pass over the header, four bytes at a time from its first byte (word w = bytes 4w .. 4w+3): id fingerprint
+            // (both mates), and for read 1 the pieces of name.split("/")[0].replace(" ", "").strip() (V2:135-138)
+            uint32_t cut = hdr_len, spaces = 0, bad = 0, tok_len = hdr_len;
+            bool found_slash = false, found_tok = false;
+            unsigned long long h = kTokSeed;
             {
-                bool found = false;
+                uint32_t prev = nwords ? words[s0 >> 2] : 0u;
                 for (uint32_t w = 0; w < trip; w++) {
-                    if (w < nwords && !found) {
-                        const uint32_t x = words[(s0 >> 2) + w];
-                        const uint32_t rem = nbytes - 4u * w;
-                        const uint32_t V = byte_range_flags(w == 0 ? a : 0u, rem < 4u ? rem : 4u);
-                        const uint32_t le = lt_flags(x, 0x21212121u) & V;
-                        if (le) {
-                            const uint32_t bit = (uint32_t)__ffs((int)le) - 1u;
-                            tok_len = 4u * w + (bit >> 3) - a;
-                            ctl = lt_flags(x, 0x20202020u) & V & ((2u << bit) - 1u);  // the delimiter must be a plain blank
-                            found = true;
+                    if (w < nwords) {
+                        const uint32_t nxt = words[(s0 >> 2) + w + 1u];
+                        const uint32_t x = __funnelshift_r(prev, nxt, a * 8u);
+                        prev = nxt;
+                        const uint32_t rem = hdr_len - 4u * w;
+                        const uint32_t V = byte_range_flags(0u, rem < 4u ? rem : 4u);
+                        bad |= lt_flags(x, 0x20202020u) & V;
+                        if (!found_tok) {
+                            const uint32_t le = lt_flags(x, 0x21212121u) & V;
+                            uint32_t tw = x;
+                            if (le) {
+                                const uint32_t bit = (uint32_t)__ffs((int)le) - 1u;  // 7, 15, 23 or 31
+                                tok_len = 4u * w + (bit >> 3);
+                                found_tok = true;
+                                tw &= (1u << (bit - 7u)) - 1u;  // bytes before the delimiter
+                            } else if (rem < 4u) {
+                                tw &= (1u << (8u * rem)) - 1u;  // the line ends inside this word
+                            }
+                            if (4u * w < tok_len) h = tok_hash_step(h, tw);
+                        }
+                        if (MODE == kScanR1 && !found_slash) {
+                            const uint32_t zs = zero_flags(x ^ 0x2F2F2F2Fu) & V, zp = zero_flags(x ^ 0x20202020u) & V;
+                            if (zs) {
+                                const uint32_t bit = (uint32_t)__ffs((int)zs) - 1u;
+                                cut = 4u * w + (bit >> 3);
+                                spaces += (uint32_t)__popc(zp & ((1u << bit) - 1u));
+                                found_slash = true;
+                            } else {
+                                spaces += (uint32_t)__popc(zp);
+                            }
                         }
                     }
                 }
             }
-            // ---- lineRead = line.rstrip(); the four windows (V2:293-301) ----
-            uint32_t seq_e = s2 - 1u;
-            bool ok = fast && ctl == 0u && cfg.fast_wl != 0 && cfg.fast_geom != 0;
-            if (ok) ok = rstrip2(s_win, s1, seq_e);
-            if (ok) ok = seq_e - s1 >= (uint32_t)cfg.need_len;  // truncated read 2 goes the exact way
-            R2Out o;
-            o.ann = 0;
-            bool complete = false;
-            uint32_t cell = 0, nw_tok = 0;
-            bool matched = false;
-            uint32_t u0 = 0, u1 = 0, u2 = 0;
-            if (ok) {
-                complete = true;
-                if (s_win[s0] != '@') raise(args.cnt, args.err_off, 1, kErrNoAt, tile_lo + s0);
-                uint32_t x0, x1, d0, d1, code;
-                load8(words, s1 + (uint32_t)cfg.b1s, x0, x1);
-                code = pack4(x0, d0) | (pack4(x1, d1) << 8);
-                const int i1 = match8(cfg, args.lut, code, d0, d1);
-                load8(words, s1 + (uint32_t)cfg.b2s, x0, x1);
-                code = pack4(x0, d0) | (pack4(x1, d1) << 8);
-                const int i2 = i1 < 0 ? -1 : match8(cfg, args.lut, code, d0, d1);
-                load8(words, s1 + (uint32_t)cfg.b3s, x0, x1);
-                code = pack4(x0, d0) | (pack4(x1, d1) << 8);
-                const int i3 = i2 < 0 ? -1 : match8(cfg, args.lut, code, d0, d1);
-                matched = i3 >= 0;  // V2:310-321: all three lists non-empty
-                cell = matched ? (uint32_t)((i1 * cfg.n_wl + i2) * cfg.n_wl + i3) : 0u;
-                nw_tok = matched ? (tok_len + 3u) >> 2 : 0u;
-            }
-            // ---- mate join by read id (V2:349-350): compare the token with read 1's, four bytes at a time ----
-            const uint32_t trip2 = __reduce_max_sync(0xFFFFFFFFu, nw_tok);
-            if (trip2) {
-                bool same = matched && r < args.cnt->n_records[0];
-                size_t o1 = 0, g = 0;
-                uint32_t sh1 = 0, prev1 = 0, prev2 = 0;
-                const uint32_t sh2 = a * 8u;
-                if (same) {
-                    o1 = (size_t)args.r1_start[r];
-                    g = o1 & ~(size_t)3;
-                    sh1 = (uint32_t)(o1 & 3) * 8u;
-                    prev1 = ldg_word_safe(args.r1buf, g, args.r1_len);
-                    prev2 = words[s0 >> 2];
+            const unsigned long long fp = tok_hash_finish(h, tok_len);
+
+            if (MODE == kScanR1) {
+                uint32_t seq_e = s2 - 1u, qual_e = s4 - 1u;
+                bool ok = fast && bad == 0u;
+                if (ok) ok = rstrip2(s_win, s1, seq_e) && rstrip2(s_win, s3, qual_e);
+                if (ok) {
+                    if (s_win[s0] != '@') raise(args.cnt, args.err_off, 0, kErrNoAt, tile_lo + s0);
+                    uint4 mt;
+                    mt.x = cut | ((cut - spaces) << 16);
+                    mt.y = (s1 - s0) | ((seq_e - s1) << 16);
+                    mt.z = (s3 - s0) | ((qual_e - s3) << 16);
+                    mt.w = 0;
+                    args.r1_start[r] = (OffT)(tile_lo + s0);
+                    args.r1_meta[r] = mt;
+                    args.r1_base[r] = (cut - spaces) + (seq_e - s1) + (qual_e - s3) + 7u;
+                    args.r1_tok[r] = fp;
                 }
-                for (uint32_t w = 0; w < trip2; w++) {
-                    if (same && w < nw_tok) {
-                        const uint32_t n1 = ldg_word_safe(args.r1buf, g + 4u * (w + 1u), args.r1_len);
-                        const uint32_t n2 = words[(s0 >> 2) + w + 1u];
-                        const uint32_t rem = tok_len - 4u * w;
-                        const uint32_t mask = rem >= 4u ? 0xFFFFFFFFu : (1u << (8u * rem)) - 1u;
-                        if ((__funnelshift_r(prev1, n1, sh1) ^ __funnelshift_r(prev2, n2, sh2)) & mask) same = false;
-                        prev1 = n1;
-                        prev2 = n2;
+                __syncwarp();
+                if (have && !ok) r1_record_generic(ga, args, r, tile_lo + s0);
+                __syncwarp();
+            } else {
+                // the fingerprint read 1 left for this record: requested now, needed after the matching
+                unsigned long long fp1 = 0;
+                const bool have_mate = fast && r < n_rec_r1;
+                if (have_mate) fp1 = args.r1_tok[r];
+                // ---- lineRead = line.rstrip(); the four windows (V2:293-301) ----
+                uint32_t seq_e = s2 - 1u;
+                bool ok = fast && bad == 0u && cfg.fast_wl != 0 && cfg.fast_geom != 0;
+                if (ok) ok = rstrip2(s_win, s1, seq_e);
+                if (ok) ok = seq_e - s1 >= (uint32_t)cfg.need_len;  // truncated read 2 goes the exact way
+                R2Out o;
+                o.ann = 0;
+                bool complete = false;
+                if (ok) {
+                    complete = true;
+                    if (s_win[s0] != '@') raise(args.cnt, args.err_off, 1, kErrNoAt, tile_lo + s0);
+                    uint32_t x0, x1, d0, d1, code;
+                    load8(words, s1 + (uint32_t)cfg.b1s, x0, x1);
+                    code = pack4(x0, d0) | (pack4(x1, d1) << 8);
+                    const int i1 = match8(cfg, args.lut, code, d0, d1);
+                    load8(words, s1 + (uint32_t)cfg.b2s, x0, x1);
+                    code = pack4(x0, d0) | (pack4(x1, d1) << 8);
+                    const int i2 = match8(cfg, args.lut, code, d0, d1);
+                    load8(words, s1 + (uint32_t)cfg.b3s, x0, x1);
+                    code = pack4(x0, d0) | (pack4(x1, d1) << 8);
+                    const int i3 = match8(cfg, args.lut, code, d0, d1);
+                    bool matched = i1 >= 0 && i2 >= 0 && i3 >= 0;  // V2:310-321: all three lists non-empty
+                    if (matched && !(have_mate && fp1 == fp)) {    // V2:349-350: no read-1 mate with this id
+                        raise(args.cnt, args.err_off, 1, kErrKey, tile_lo + s0);
+                        matched = false;
+                    }
+                    if (matched) {
+                        const uint32_t cell = (uint32_t)((i1 * cfg.n_wl + i2) * cfg.n_wl + i3);
+                        // UMI = lineRead[umi_start:umi_end] verbatim (V2:295)
+                        const uint32_t up = s1 + (uint32_t)cfg.us;
+                        const uint32_t i0 = up >> 2, sh = (up & 3u) * 8u;
+                        const uint32_t w0 = words[i0], w1 = words[i0 + 1], w2 = words[i0 + 2], w3 = words[i0 + 3];
+                        const uint32_t ul = (uint32_t)cfg.umi_len;
+                        const uint32_t m0 = ul >= 4u ? 0xFFFFFFFFu : (1u << (8u * ul)) - 1u;
+                        const uint32_t m1 = ul >= 8u ? 0xFFFFFFFFu : (ul > 4u ? (1u << (8u * (ul - 4u))) - 1u : 0u);
+                        const uint32_t m2 = ul > 8u ? (1u << (8u * (ul - 8u))) - 1u : 0u;
+                        const uint32_t u0 = __funnelshift_r(w0, w1, sh) & m0, u1 = __funnelshift_r(w1, w2, sh) & m1,
+                                       u2 = __funnelshift_r(w2, w3, sh) & m2;
+                        uint32_t e0, e1, e2;
+                        const uint64_t ucode = ((uint64_t)pack4(u0, e0) | ((uint64_t)pack4(u1, e1) << 8) | ((uint64_t)pack4(u2, e2) << 16)) &
+                                               ((1ull << cfg.umi_bits) - 1ull);
+                        if (((e0 & m0) | (e1 & m1) | (e2 & m2)) == 0u) {
+                            o.ann = kAnnRegular | ((uint64_t)cell << kAnnCellShift) | ucode;
+                        } else {
+                            o.ann = kAnnIrregular | ((uint64_t)cell << kAnnCellShift) | ((uint64_t)(tile_lo + up) << 5) | (uint64_t)ul;
+                            o.irr.hi = ((uint64_t)cell << kIrrCellShift) | ((uint64_t)ul << 32) | (uint64_t)__byte_perm(u0, 0u, 0x0123u);
+                            o.irr.lo = ((uint64_t)__byte_perm(u1, 0u, 0x0123u) << 16) | (uint64_t)(((u2 & 0xFFu) << 8) | ((u2 >> 8) & 0xFFu));
+                        }
                     }
                 }
-                if (same) {  // read 1's token must end where read 2's does
-                    const size_t p = o1 + tok_len;
-                    same = p >= args.r1_len || py_space(args.r1buf[p]);
-                }
-                if (matched && !same) {
-                    raise(args.cnt, args.err_off, 1, kErrKey, tile_lo + s0);
-                    matched = false;
-                }
+                __syncwarp();
+                if (have && !ok) r2_record_generic(ga, args, cfg, r, tile_lo + s0, o, complete, n_rec_r1);
+                __syncwarp();
+                // ---- results: annotation, histogram, key counts; the regular (cell, UMI) key is the annotation itself
+                //      (the sort reads it from there), irregular keys are rare and appended one by one ----
+                if (complete) args.ann[r] = o.ann;
+                const uint32_t st8 = ann_state(o.ann);
+                if (st8) atomicAdd(&args.hist[ann_cell(o.ann)], 1u);
+                const uint32_t nreg = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 1u)), nirr = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 2u));
+                if (lane == 0 && nreg) atomicAdd(&args.cnt->n_keys, (unsigned long long)nreg);
+                if (lane == 0 && nirr) atomicAdd(&args.cnt->n_irr, (unsigned long long)nirr);  // their keys are collected by k_collect_irr
             }
-            // ---- UMI = lineRead[umi_start:umi_end] verbatim (V2:295) ----
-            if (matched) {
-                const uint32_t up = s1 + (uint32_t)cfg.us;
-                const uint32_t i0 = up >> 2, sh = (up & 3u) * 8u;
-                const uint32_t w0 = words[i0], w1 = words[i0 + 1], w2 = words[i0 + 2], w3 = words[i0 + 3];
-                const uint32_t ul = (uint32_t)cfg.umi_len;
-                const uint32_t m0 = ul >= 4u ? 0xFFFFFFFFu : (1u << (8u * ul)) - 1u;
-                const uint32_t m1 = ul >= 8u ? 0xFFFFFFFFu : (ul > 4u ? (1u << (8u * (ul - 4u))) - 1u : 0u);
-                const uint32_t m2 = ul > 8u ? (1u << (8u * (ul - 8u))) - 1u : 0u;
-                u0 = __funnelshift_r(w0, w1, sh) & m0;
-                u1 = __funnelshift_r(w1, w2, sh) & m1;
-                u2 = __funnelshift_r(w2, w3, sh) & m2;
-                uint32_t d0, d1, d2;
-                const uint64_t code = ((uint64_t)pack4(u0, d0) | ((uint64_t)pack4(u1, d1) << 8) | ((uint64_t)pack4(u2, d2) << 16)) &
-                                      ((1ull << cfg.umi_bits) - 1ull);
-                if (((d0 & m0) | (d1 & m1) | (d2 & m2)) == 0u) {
-                    o.ann = kAnnRegular | ((uint64_t)cell << kAnnCellShift) | code;
-                    o.key = ((uint64_t)cell << cfg.umi_bits) | code;
-                } else {
-                    o.ann = kAnnIrregular | ((uint64_t)cell << kAnnCellShift) | ((uint64_t)(tile_lo + up) << 5) | (uint64_t)ul;
-                    o.irr.hi = ((uint64_t)cell << kIrrCellShift) | ((uint64_t)ul << 32) | (uint64_t)__byte_perm(u0, 0u, 0x0123u);
-                    o.irr.lo = ((uint64_t)__byte_perm(u1, 0u, 0x0123u) << 16) | (uint64_t)(((u2 & 0xFFu) << 8) | ((u2 >> 8) & 0xFFu));
-                }
-            }
-            __syncwarp();
-            if (have && !ok) {
-                const size_t start = tile_lo + s0;
-                if (!r2_record_generic(wa, args, cfg, r, start, o, complete)) r2_record_generic(ga, args, cfg, r, start, o, complete);
-            }
-            __syncwarp();
-
-            // ---- results: annotation, histogram, block-aggregated key append ----
-            uint32_t slot = 0;
-            if (complete) args.ann[r] = o.ann;
-            if (ann_state(o.ann) == 1) slot = atomicAdd(&s_nk, 1u);
-            else if (ann_state(o.ann) == 2) slot = atomicAdd(&s_ni, 1u);
-            if (o.ann) atomicAdd(&args.hist[ann_cell(o.ann)], 1u);
-            __syncthreads();
-            if (tid == 0) {
-                s_kbase = s_nk ? atomicAdd(&args.cnt->n_keys, (unsigned long long)s_nk) : 0ull;
-                s_ibase = s_ni ? atomicAdd(&args.cnt->n_irr, (unsigned long long)s_ni) : 0ull;
-            }
-            __syncthreads();
-            if (ann_state(o.ann) == 1) args.keys[s_kbase + slot] = o.key;
-            else if (ann_state(o.ann) == 2) args.irr[s_ibase + slot] = o.irr;
-            __syncthreads();
-            if (tid == 0) {
-                s_nk = 0;
-                s_ni = 0;
-            }
-            __syncthreads();
         }
+        compute_sync();
+        PROF_T(t6);
+        PROF_ADD(4, t5, t6);
+        if (tid == 0) mbar_arrive(&S.empty[ws]);  // the window may be refilled
+    };
+
+    uint32_t n_a = 0;
+    bool more = true;
+    for (int pre = 0; pre < kDepth && more; pre++) {
+        more = stage_a(n_a);
+        if (more) n_a++;
     }
+    for (uint32_t it = 0;; it++) {
+        if (more) {
+            more = stage_a(n_a);
+            if (more) n_a++;
+        }
+        if (it >= n_a) break;
+        stage_b(it);
+    }
+#ifdef SSD_SCAN_PROFILE
+    if (tid == 0) {
+        for (int k = 0; k < 5; k++) atomicAdd(&g_scan_prof[MODE][k], prof[k]);
+        atomicAdd(&g_scan_prof[MODE][7], (unsigned long long)n_a);
+    }
+#endif
 }
 
 }  // namespace ssd

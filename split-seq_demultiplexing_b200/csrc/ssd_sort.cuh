@@ -126,8 +126,25 @@ __device__ __forceinline__ uint32_t digit_of<uint64_t>(const uint64_t& k, int bi
     return (uint32_t)(k >> bit) & 0xFFu;
 }
 
-template <typename K>
-__global__ void __launch_bounds__(kThreads) k_sort_hist(const K* keys, uint64_t n, int bit, uint32_t* counts, uint32_t n_blocks)
+// Key sources of a sort pass: a plain array, or the annotation words (regular records only; the rest is skipped,
+// which makes the first pass double as the compaction of the keys).
+constexpr uint64_t kNoKey = ~0ull;
+struct KeysArray {
+    const uint64_t* p;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return p[i]; }
+};
+struct KeysFromAnn {
+    const uint64_t* ann;
+    int umi_bits;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const
+    {
+        const uint64_t a = ann[i];
+        return ann_state(a) == 1 ? (((uint64_t)ann_cell(a) << umi_bits) | ann_payload(a)) : kNoKey;
+    }
+};
+
+template <class Src>
+__global__ void __launch_bounds__(kThreads) k_sort_hist(Src keys, uint64_t n, int bit, uint32_t* counts, uint32_t n_blocks)
 {
     __shared__ uint32_t s_hist[256];
     s_hist[threadIdx.x] = 0;
@@ -136,14 +153,17 @@ __global__ void __launch_bounds__(kThreads) k_sort_hist(const K* keys, uint64_t 
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) {
         uint64_t j = base + (uint64_t)i * kThreads + threadIdx.x;
-        if (j < n) atomicAdd(&s_hist[digit_of(keys[j], bit)], 1u);
+        if (j < n) {
+            const uint64_t k = keys(j);
+            if (k != kNoKey) atomicAdd(&s_hist[digit_of(k, bit)], 1u);
+        }
     }
     __syncthreads();
     counts[(size_t)threadIdx.x * n_blocks + blockIdx.x] = s_hist[threadIdx.x];
 }
 
-template <typename K, bool HAS_VALS>
-__global__ void __launch_bounds__(kThreads) k_sort_scatter(const K* keys_in, K* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+template <class Src, typename K, bool HAS_VALS>
+__global__ void __launch_bounds__(kThreads) k_sort_scatter(Src keys_in, K* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
                                                            uint64_t n, int bit, const uint32_t* offsets, uint32_t n_blocks)
 {
     __shared__ uint32_t s_wcount[kThreads / 32][257];
@@ -163,7 +183,8 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(const K* keys_in, K* 
         uint64_t j = wbase + (uint64_t)i * 32 + lane;
         bool valid = j < n;
         if (valid) {
-            key[i] = keys_in[j];
+            key[i] = keys_in(j);
+            valid = key[i] != kNoKey;
             if (HAS_VALS) val[i] = vals_in[j];
         }
         uint32_t d = valid ? digit_of(key[i], bit) : 256u;
@@ -258,6 +279,29 @@ __global__ void k_count_cells_irr(const IrrKey* uniq, uint64_t n, uint32_t* dist
     uint32_t c = (uint32_t)(uniq[i].hi >> kIrrCellShift);
     if (i == 0 || (uint32_t)(uniq[i - 1].hi >> kIrrCellShift) != c) atomicSub(&distinct[c], (uint32_t)i);
     if (i == n - 1 || (uint32_t)(uniq[i + 1].hi >> kIrrCellShift) != c) atomicAdd(&distinct[c], (uint32_t)i + 1u);
+}
+
+// Irregular (cell, UMI) keys are rare: they are gathered after the scan from the annotation words, the UMI bytes
+// re-read from read 2 (the annotation holds their offset and length).
+__global__ void k_collect_irr(const uint64_t* ann, uint64_t n, const uint8_t* r2buf, IrrKey* out, unsigned long long* cursor)
+{
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint64_t a = ann[r];
+    if (ann_state(a) != 2) return;
+    const uint64_t payload = ann_payload(a);
+    const uint32_t ulen = (uint32_t)(payload & 31u);
+    const uint8_t* p = r2buf + (size_t)(payload >> 5);
+    uint64_t hi = 0, lo = 0;
+    for (uint32_t j = 0; j < ulen; j++) {
+        const uint64_t c = p[j];
+        if (j < 4) hi |= c << (8 * (3 - j));
+        else lo |= c << (8 * (9 - j));
+    }
+    IrrKey k;
+    k.hi = ((uint64_t)ann_cell(a) << kIrrCellShift) | ((uint64_t)ulen << 32) | hi;
+    k.lo = lo;
+    out[atomicAdd(cursor, 1ull)] = k;
 }
 
 __global__ void k_iota(uint32_t* p, uint64_t n)

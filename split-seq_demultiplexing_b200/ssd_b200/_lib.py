@@ -12,7 +12,7 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(CSRC, "libssd_b200.so")
+LIB_PATH = os.environ.get("SSD_B200_LIB") or os.path.join(CSRC, "libssd_b200.so")  # override: A/B builds while tuning
 SOURCES = ["ssd_b200.cu", "ssd_kernels.cuh", "ssd_device.cuh", "ssd_synth.cuh"]
 HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "ssd_b200.h")
 
