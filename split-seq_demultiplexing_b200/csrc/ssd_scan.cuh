@@ -617,7 +617,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
         GlobAcc ga{args.buf, args.len};
 
         for (uint32_t base = 0; base < n_rec; base += kComputeThreads) {
-            const uint32_t i = base + tid;
+            // read 2 (global-memory latency in the chain): record i of the batch goes to warp i % 8, lane i / 8, so every warp
+            // gets its share and the stage ends sooner; read 1 keeps records packed into as few warps as possible
+            const uint32_t i = MODE == kScanR2 ? base + (uint32_t)lane * kComputeWarps + (uint32_t)warp : base + (uint32_t)tid;
             const bool have = i < n_rec;
             const uint64_t r = r_first + i;
             const uint32_t j0 = j_first + 4u * i;
@@ -718,16 +720,22 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                 if (ok) {
                     complete = true;
                     if (s_win[s0] != '@') raise(args.cnt, args.err_off, 1, kErrNoAt, tile_lo + s0);
-                    uint32_t x0, x1, d0, d1, code;
+                    // the three windows are packed first so that their LUT lookups are in flight together
+                    uint32_t x0, x1, da0, da1, db0, db1, dc0, dc1;
                     load8(words, s1 + (uint32_t)cfg.b1s, x0, x1);
-                    code = pack4(x0, d0) | (pack4(x1, d1) << 8);
-                    const int i1 = match8(cfg, args.lut, code, d0, d1);
+                    const uint32_t code1 = pack4(x0, da0) | (pack4(x1, da1) << 8);
                     load8(words, s1 + (uint32_t)cfg.b2s, x0, x1);
-                    code = pack4(x0, d0) | (pack4(x1, d1) << 8);
-                    const int i2 = match8(cfg, args.lut, code, d0, d1);
+                    const uint32_t code2 = pack4(x0, db0) | (pack4(x1, db1) << 8);
                     load8(words, s1 + (uint32_t)cfg.b3s, x0, x1);
-                    code = pack4(x0, d0) | (pack4(x1, d1) << 8);
-                    const int i3 = match8(cfg, args.lut, code, d0, d1);
+                    const uint32_t code3 = pack4(x0, dc0) | (pack4(x1, dc1) << 8);
+                    const uint8_t* lute = args.lut + (size_t)cfg.e * 65536u;
+                    const uint32_t v1 = __ldg(lute + code1), v2 = __ldg(lute + code2), v3 = __ldg(lute + code3);
+                    int i1 = v1 == 0xFFu ? -1 : (int)v1, i2 = v2 == 0xFFu ? -1 : (int)v2, i3 = v3 == 0xFFu ? -1 : (int)v3;
+                    if ((da0 | da1 | db0 | db1 | dc0 | dc1) != 0u) {  // some window holds a byte that is not A/C/G/T
+                        if (da0 | da1) i1 = match8(cfg, args.lut, code1, da0, da1);
+                        if (db0 | db1) i2 = match8(cfg, args.lut, code2, db0, db1);
+                        if (dc0 | dc1) i3 = match8(cfg, args.lut, code3, dc0, dc1);
+                    }
                     bool matched = i1 >= 0 && i2 >= 0 && i3 >= 0;  // V2:310-321: all three lists non-empty
                     if (matched && !(have_mate && fp1 == fp)) {    // V2:349-350: no read-1 mate with this id
                         raise(args.cnt, args.err_off, 1, kErrKey, tile_lo + s0);
