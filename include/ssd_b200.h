@@ -37,6 +37,7 @@ extern "C" {
 #define SSD_ENOMEM (-5)
 #define SSD_ESTATE (-6)     /* call sequence violated                                                 */
 #define SSD_ERANGE (-7)     /* output buffer too small                                                */
+#define SSD_EINDEX (-8)     /* annotated header without two '_' (V2:397-398)           -> IndexError        */
 
 /* -m semantics.  V2:411 keeps a cell when len(set(UMIs)) >= m; the bash pipeline's step 1
  * (demultiplex_using_barcodes.py:409) counts reads instead. */
@@ -99,6 +100,16 @@ int ssd_set_stream(ssd_ctx *ctx, void *cuda_stream);
  * record range of both); they must stay valid and unchanged until the last ssd_emit of this batch.
  * Starts a new batch: previous per-batch results are discarded. */
 int ssd_demux_device(ssd_ctx *ctx, const void *d_r1, size_t r1_len, const void *d_r2, size_t r2_len);
+
+/* V2.calc_demux_results' input side (V2:389-404): the batch is one already annotated FASTQ (MergedCells_1.fastq:
+ * headers id_cell_umi).  Cell = the text between the first two '_' (it must be three whitelist entries back to
+ * back), UMI = the text up to the next '_' or the end of the line (at most 10 bytes).  Afterwards phases 2 and 3
+ * work as usual; SSD_EMIT_PASSING then copies the records of passing cells with every line strip()ped
+ * (V2:415-454) and SSD_EMIT_MATCHED copies all records. */
+int ssd_annotated_device(ssd_ctx *ctx, const void *d_text, size_t len);
+/* The same from a HOST buffer, through to the filtered text (out == NULL and out_cap == 0: stop after the filter). */
+int ssd_annotated_host(ssd_ctx *ctx, const void *text, size_t len, void *out, size_t out_cap, size_t *written,
+                       ssd_stats *stats);
 
 /* ---- phase 2: the -m decision, V2.calc_demux_results pass 1 (V2:389-412) ---------------------- */
 /* Device pointers to the n^3 uint32 per-cell read counts / distinct-UMI counts of this context.

@@ -7,6 +7,7 @@
 #include <stdarg.h>
 #include <stddef.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -58,6 +59,7 @@ struct ssd_ctx {
     uint64_t n_rec_r1 = 0, n_rec_r2 = 0, n_rec = 0, n_keys = 0, n_irr = 0;
     bool phase1_done = false, filter_done = false, unique_done = false;
     int planned = -1;  // which output b_out_off currently describes (-1 = none)
+    bool annotated = false;  // the batch is an already annotated FASTQ (V2.calc_demux_results)
     uint64_t* uniq_keys = nullptr;
     uint64_t n_uniq = 0;
     IrrKey* uniq_irr = nullptr;
@@ -305,7 +307,20 @@ int launch_scans(ssd_ctx* c)
     a.irr = (IrrKey*)c->b_irr.p;
     a.lut = c->d_lut;
 
-    const uint32_t nt1 = blocks_for(c->r1_len, kTile), nt2 = blocks_for(c->r2_len, kTile);
+    const uint32_t nt1 = blocks_for(c->r1_len, kTile), nt2 = c->annotated ? 0u : blocks_for(c->r2_len, kTile);
+    if (c->annotated) {
+        if (nt1) {
+            a.buf = c->r1;
+            a.len = c->r1_len;
+            a.status = (unsigned long long*)c->b_status1.p;
+            a.n_tiles = nt1;
+            StageTimer t(c, 0);
+            k_scan<kScanAnn, OffT><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+            c->n_launches++;
+        }
+        CU(c, cudaGetLastError());
+        return SSD_OK;
+    }
     if (nt1) {
         a.buf = c->r1;
         a.len = c->r1_len;
@@ -344,6 +359,7 @@ int launch_emit(ssd_ctx* c, int which, uint8_t* d_out)
     a.out = d_out;
     a.n_rec = c->n_rec;
     a.cnt = c->d_cnt;
+    a.copy_mode = c->annotated ? 1 : 0;
     // records per block: the block's slice of the output must fit the staging buffer
     const uint64_t n_out = which == SSD_EMIT_MATCHED ? c->stats.n_matched : c->stats.n_retained;
     const uint64_t bytes = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
@@ -369,6 +385,7 @@ OutLen make_outlen(ssd_ctx* c, int which)
     f.n = c->dcfg.n_wl;
     f.umi_len = c->dcfg.umi_len;
     f.bc_const = c->bc_const;
+    f.copy_mode = c->annotated ? 1 : 0;
     return f;
 }
 
@@ -500,6 +517,8 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
         CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
         CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
         CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
         int per_sm = 0;
         CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<kScanR2, uint32_t>, kScanThreads, sizeof(ScanSmem)));
         c->scan_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
@@ -555,9 +574,10 @@ extern "C" int ssd_set_stream(ssd_ctx* c, void* cuda_stream)
 // ================================================================================================
 // phase 1
 // ================================================================================================
-extern "C" int ssd_demux_device(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, size_t r2_len)
+namespace {
+
+int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, size_t r2_len, bool annotated)
 {
-    if (!c) return SSD_EINVAL;
     if ((r1_len && !d_r1) || (r2_len && !d_r2)) return fail(c, SSD_EINVAL, "null input pointer");
     if (((uintptr_t)d_r1 & 15u) || ((uintptr_t)d_r2 & 15u)) return fail(c, SSD_EINVAL, "device inputs must be 16-byte aligned");
     CU(c, cudaSetDevice(c->device));
@@ -565,7 +585,8 @@ extern "C" int ssd_demux_device(ssd_ctx* c, const void* d_r1, size_t r1_len, con
     c->r2 = (const uint8_t*)d_r2;
     c->r1_len = r1_len;
     c->r2_len = r2_len;
-    c->wide = std::max(r1_len, r2_len) >= (1ull << 32);
+    c->annotated = annotated;
+    c->wide = std::max(r1_len, r2_len) >= (1ull << 32) || getenv("SSD_FORCE_WIDE") != nullptr;
     c->phase1_done = c->filter_done = c->unique_done = false;
     c->planned = -1;
     if (std::max(r1_len, r2_len) >= (1ull << 36)) return fail(c, SSD_EINVAL, "a batch is limited to 64 GiB per file");
@@ -595,10 +616,13 @@ extern "C" int ssd_demux_device(ssd_ctx* c, const void* d_r1, size_t r1_len, con
         if (attempt == 1) return fail(c, SSD_EINVAL, "record tables overflowed twice (internal)");
         cap = std::max(h.n_records[0], h.n_records[1]) + 1;
     }
-    if (h.err_flags & (kErrNoAt | kErrKey | kErrDense)) {
+    if (h.err_flags & (kErrNoAt | kErrKey | kErrDense | kErrIndex | kErrForeign)) {
         unsigned long long off[2];
         CU(c, cudaMemcpy(off, c->d_err_off, sizeof off, cudaMemcpyDeviceToHost));
-        if (h.err_flags & kErrDense) return fail(c, SSD_EMALFORMED, "FASTQ records shorter than 16 bytes on average are not supported");
+        if (h.err_flags & kErrDense) return fail(c, SSD_EMALFORMED, "FASTQ records shorter than 32 bytes on average are not supported");
+        if (h.err_flags & kErrIndex) return fail(c, SSD_EINDEX, "list index out of range");
+        if (h.err_flags & kErrForeign)
+            return fail(c, SSD_EINVAL, "record at byte %llu: the cell/UMI fields of its header are not made of this whitelist's barcodes", off[0]);
         if (h.err_flags & kErrNoAt) {
             int f = off[0] != ~0ull ? 0 : 1;
             return fail(c, SSD_EMALFORMED, "read %d: record at byte %llu does not start with '@'", f + 1, off[f]);
@@ -607,7 +631,7 @@ extern "C" int ssd_demux_device(ssd_ctx* c, const void* d_r1, size_t r1_len, con
         return fail(c, SSD_EKEY, "%s", tok.c_str());
     }
     c->n_rec_r1 = h.n_records[0];
-    c->n_rec_r2 = h.n_records[1];
+    c->n_rec_r2 = annotated ? h.n_records[0] : h.n_records[1];
     c->n_rec = std::min(c->n_rec_r1, c->n_rec_r2);
     c->n_keys = h.n_keys;
     c->n_irr = h.n_irr;
@@ -618,6 +642,20 @@ extern "C" int ssd_demux_device(ssd_ctx* c, const void* d_r1, size_t r1_len, con
     c->stats.n_regular_keys = c->n_keys;
     c->stats.n_irregular_keys = c->n_irr;
     return SSD_OK;
+}
+
+}  // namespace
+
+extern "C" int ssd_demux_device(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, size_t r2_len)
+{
+    if (!c) return SSD_EINVAL;
+    return run_phase1(c, d_r1, r1_len, d_r2, r2_len, false);
+}
+
+extern "C" int ssd_annotated_device(ssd_ctx* c, const void* d_text, size_t len)
+{
+    if (!c) return SSD_EINVAL;
+    return run_phase1(c, d_text, len, d_text, len, true);
 }
 
 // ================================================================================================
@@ -825,6 +863,23 @@ extern "C" int ssd_run_host(ssd_ctx* c, const void* r1, size_t r1_len, const voi
         return SSD_OK;
     }
     return ssd_emit_host(c, which, out, out_cap, written);
+}
+
+extern "C" int ssd_annotated_host(ssd_ctx* c, const void* text, size_t len, void* out, size_t out_cap, size_t* written, ssd_stats* stats)
+{
+    if (!c) return SSD_EINVAL;
+    CU(c, cudaSetDevice(c->device));
+    OKR(ensure(c, c->b_in1, len + 32));
+    const size_t chunk = (size_t)64 << 20;
+    for (size_t o = 0; o < len; o += chunk)
+        CU(c, cudaMemcpyAsync((uint8_t*)c->b_in1.p + o, (const uint8_t*)text + o, std::min(chunk, len - o), cudaMemcpyHostToDevice, c->stream));
+    OKR(ssd_annotated_device(c, c->b_in1.p, len));
+    OKR(ssd_filter_single(c, stats));
+    if (!out && !out_cap) {
+        if (written) *written = (size_t)c->stats.bytes_passing;
+        return SSD_OK;
+    }
+    return ssd_emit_host(c, SSD_EMIT_PASSING, out, out_cap, written);
 }
 
 extern "C" int ssd_record_cells(ssd_ctx* c, int32_t* cells_host, uint64_t capacity, uint64_t* n_records)

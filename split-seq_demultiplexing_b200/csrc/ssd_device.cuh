@@ -65,6 +65,8 @@ constexpr uint32_t kErrOverflow = 4u;     // more records than the tables were s
 constexpr uint32_t kErrDense = 8u;        // too many records in one tile (records shorter than 16 bytes on average)
 constexpr uint32_t kErrEmitLen = 16u;     // emitted record length differs from the planned one (internal)
 constexpr uint32_t kErrHeaderLong = 32u;  // header line longer than the supported maximum
+constexpr uint32_t kErrIndex = 64u;       // annotated header without two '_' (the reference's IndexError, V2:397-398)
+constexpr uint32_t kErrForeign = 128u;    // annotated header whose cell / UMI fields cannot come from this whitelist
 
 struct DevCounters {
     unsigned long long n_lines[2];     // total lines of read 1 / read 2

@@ -59,6 +59,7 @@ struct OutLen {
     const uint32_t* remap;    // NULL = no collapse
     const uint8_t* wl_len;    // device copy of the per-entry whitelist lengths
     int n, umi_len, bc_const;  // bc_const > 0: all entries have that length, 3 * length is added without lookups
+    int copy_mode;            // annotated input: records are copied as they are, r1_base already is the length
     __device__ __forceinline__ uint32_t bc_len(uint32_t cell, bool collapse) const
     {
         if (bc_const) return (uint32_t)bc_const;
@@ -72,6 +73,7 @@ struct OutLen {
         if (ann_state(a) == 0) return 0u;
         const uint32_t cell = ann_cell(a);
         if (pass && !pass[cell]) return 0u;
+        if (copy_mode) return r1_base[r];
         return r1_base[r] + bc_len(cell, true) + ann_umi_len(a, umi_len);
     }
     // length in the pre-filter output (never collapsed) and in the post-filter output
@@ -81,6 +83,11 @@ struct OutLen {
         matched = passing = 0u;
         if (ann_state(a) == 0) return;
         const uint32_t cell = ann_cell(a);
+        if (copy_mode) {
+            matched = r1_base[r];
+            if (pass[cell]) passing = matched;
+            return;
+        }
         const uint32_t common = r1_base[r] + ann_umi_len(a, umi_len);
         matched = common + bc_len(cell, false);
         if (pass[cell]) passing = common + bc_len(cell, true);
@@ -136,6 +143,7 @@ struct EmitArgs {
     uint8_t* out;
     uint64_t n_rec;           // records of this batch (min of the two files)
     uint32_t rpb;             // records per block
+    int copy_mode;            // annotated input: header, read, third line and quality are copied strip()ped (V2:435-447)
     DevCounters* cnt;
 };
 
@@ -149,6 +157,17 @@ __device__ __forceinline__ uint32_t emit_record_generic(const Acc& a, const Emit
     Lines L;
     find_lines(a, start, args.r1_len, true, L);
     uint32_t o = 0;
+    if (args.copy_mode) {  // the four lines, strip()ped
+        for (int k = 0; k < 4; k++) {
+            size_t le = rstrip_end(a, L.s[k], L.e[k]), ls = L.s[k];
+            while (ls < le && py_space(a.byte(ls))) ls++;
+            for (size_t i = lane; i < le - ls; i += 32) dst[o + i] = (uint8_t)a.byte(ls + i);
+            o += (uint32_t)(le - ls);
+            if (lane == 0) dst[o] = '\n';
+            o += 1;
+        }
+        return o;
+    }
 
     // header: bytes before the first '/', blanks removed, then strip()
     size_t cut = L.e[0];
@@ -279,6 +298,26 @@ __device__ __forceinline__ uint32_t emit_group(const EmitArgs<OffT>& args, const
     const uint4 mt = args.r1_meta[r];
     const uint32_t cut_len = mt.x & 0xFFFFu, seq_rel = mt.y & 0xFFFFu, seq_len = mt.y >> 16, qual_rel = mt.z & 0xFFFFu, qual_len = mt.z >> 16;
     uint32_t o = 0;
+
+    if (args.copy_mode) {
+        const uint32_t plus_rel = mt.w >> 16, plus_len = (mt.w >> 1) & 0x7FFFu;
+        group_copy(s_out, d, args.r1buf, start, args.r1_len, cut_len, gl);
+        o = cut_len;
+        if (gl == 0) s_out[d + o] = '\n';
+        o += 1u;
+        group_copy(s_out, d + o, args.r1buf, start + seq_rel, args.r1_len, seq_len, gl);
+        o += seq_len;
+        if (gl == 0) s_out[d + o] = '\n';
+        o += 1u;
+        group_copy(s_out, d + o, args.r1buf, start + plus_rel, args.r1_len, plus_len, gl);
+        o += plus_len;
+        if (gl == 0) s_out[d + o] = '\n';
+        o += 1u;
+        group_copy(s_out, d + o, args.r1buf, start + qual_rel, args.r1_len, qual_len, gl);
+        o += qual_len;
+        if (gl == 0) s_out[d + o] = '\n';
+        return o + 1u;
+    }
 
     // header: non-blank bytes of the first cut_len bytes (name.split("/")[0].replace(" ", "").strip())
     {

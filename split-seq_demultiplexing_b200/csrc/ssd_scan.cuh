@@ -283,6 +283,83 @@ __device__ __noinline__ bool r2_record_generic(const Acc& a, const ScanArgs<OffT
     return true;
 }
 
+// An annotated record (V2.calc_demux_results, V2:389-454), exact and bytewise.  Returns the annotation word.
+template <class Acc, typename OffT>
+__device__ __noinline__ uint64_t ann_record_generic(const Acc& a, const ScanArgs<OffT>& args, const DevCfg& cfg, uint64_t r, size_t start)
+{
+    Lines L;
+    if (!find_lines(a, start, args.len, true, L) || !L.complete) return 0;
+    if (r >= args.rec_cap) {
+        atomicOr(&args.cnt->err_flags, kErrOverflow);
+        return 0;
+    }
+    // every line is written strip()ped (V2:435-447); the fields come from the rstrip()ped header (V2:395-398)
+    size_t ls[4], le[4];
+    for (int k = 0; k < 4; k++) {
+        le[k] = rstrip_end(a, L.s[k], L.e[k]);
+        ls[k] = L.s[k];
+        while (ls[k] < le[k] && py_space(a.byte(ls[k]))) ls[k]++;
+    }
+    size_t us[3] = {0, 0, 0};
+    int nus = 0;
+    for (size_t p = L.s[0]; p < le[0] && nus < 3; p++)
+        if (a.byte(p) == '_') us[nus++] = p;
+    uint64_t an = 0;
+    if (nus < 2) {
+        raise(args.cnt, args.err_off, 0, kErrIndex, start);
+    } else {
+        const size_t cell_s = us[0] + 1, cell_n = us[1] - us[0] - 1, umi_s = us[1] + 1, umi_e = nus == 3 ? us[2] : le[0];
+        const size_t ulen = umi_e - umi_s;
+        int idx[3] = {-1, -1, -1};
+        // the cell must be three whitelist entries back to back (lengths as configured), matched exactly
+        size_t p = cell_s;
+        bool shape = true;
+        for (int k = 0; k < 3 && shape; k++) {
+            idx[k] = -1;
+            for (int i = 0; i < cfg.n_wl && idx[k] < 0; i++) {
+                const size_t n = cfg.wl_len[i];
+                if (p + n > cell_s + cell_n) continue;
+                bool eq = true;
+                for (size_t j = 0; j < n && eq; j++) eq = a.byte(p + j) == cfg.wl[i * 8 + j];
+                if (eq && (k < 2 || p + n == cell_s + cell_n)) idx[k] = i;
+            }
+            if (idx[k] < 0) shape = false;
+            else p += cfg.wl_len[idx[k]];
+        }
+        if (!shape || ulen > 10) {
+            raise(args.cnt, args.err_off, 0, kErrForeign, start);
+        } else {
+            const uint32_t cell = (uint32_t)((idx[0] * cfg.n_wl + idx[1]) * cfg.n_wl + idx[2]);
+            uint64_t code = 0;
+            bool regular = (int)ulen == cfg.umi_len;
+            for (size_t j = 0; j < ulen; j++) {
+                const uint32_t c = a.byte(umi_s + j);
+                regular = regular && is_acgt(c);
+                code |= (uint64_t)base2(c) << (2 * j);
+            }
+            an = regular ? (kAnnRegular | ((uint64_t)cell << kAnnCellShift) | code)
+                         : (kAnnIrregular | ((uint64_t)cell << kAnnCellShift) | ((uint64_t)umi_s << 5) | (uint64_t)ulen);
+        }
+    }
+    const size_t hl = le[0] - ls[0], sl = le[1] - ls[1], pl = le[2] - ls[2], ql = le[3] - ls[3];
+    uint4 m;
+    if (ls[0] == start && hl < 65536 && ls[1] - start < 65536 && sl < 65536 && ls[2] - start < 65536 && pl < 32768 && ls[3] - start < 65536 &&
+        ql < 65536) {
+        m.x = (uint32_t)hl | ((uint32_t)hl << 16);
+        m.y = (uint32_t)(ls[1] - start) | ((uint32_t)sl << 16);
+        m.z = (uint32_t)(ls[3] - start) | ((uint32_t)ql << 16);
+        m.w = ((uint32_t)pl << 1) | ((uint32_t)(ls[2] - start) << 16);
+    } else {
+        m.x = m.y = m.z = 0;
+        m.w = kMetaLong;
+    }
+    args.r1_start[r] = (OffT)start;
+    args.r1_meta[r] = m;
+    args.r1_base[r] = (uint32_t)(hl + sl + pl + ql) + 4u;
+    args.ann[r] = an;
+    return an;
+}
+
 // ======================================================================================================
 // fast paths (one thread per record, whole warps in lock step)
 // ======================================================================================================
@@ -328,6 +405,8 @@ __device__ __forceinline__ int match8(const DevCfg& cfg, const uint8_t* __restri
 
 constexpr int kScanR1 = 0;
 constexpr int kScanR2 = 1;
+constexpr int kScanAnn = 2;  // an already annotated FASTQ (MergedCells_1.fastq): V2.calc_demux_results
+
 
 constexpr int kComputeWarps = 8;
 constexpr int kComputeThreads = kComputeWarps * 32;
@@ -442,7 +521,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
             const uint32_t ws = it % kWinSlots;
             if (it >= (uint32_t)kWinSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.empty[ws]), ((it / kWinSlots) - 1u) & 1u);
             uint32_t t = 0;
-            if (lane == 0) t = atomicAdd(&args.cnt->ticket[MODE], 1u);  // tiles are claimed in order: nobody waits on an unclaimed tile
+            if (lane == 0) t = atomicAdd(&args.cnt->ticket[MODE == kScanR2 ? 1 : 0], 1u);  // tiles are claimed in order: nobody waits on an unclaimed tile
             t = __shfl_sync(0xFFFFFFFFu, t, 0);
             if (t >= args.n_tiles) {
                 if (lane == 0) {
@@ -594,8 +673,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
             S.line_base = excl_lines;
             if (tile == args.n_tiles - 1) {
                 unsigned long long n_lines = excl_lines + total + ((args.len && s_win[win_bytes - 1] != '\n') ? 1ull : 0ull);
-                args.cnt->n_lines[MODE] = n_lines;
-                args.cnt->n_records[MODE] = n_lines >> 2;
+                args.cnt->n_lines[MODE == kScanR2 ? 1 : 0] = n_lines;
+                args.cnt->n_records[MODE == kScanR2 ? 1 : 0] = n_lines >> 2;
             }
         }
         compute_sync();
@@ -627,13 +706,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
             bool fast = false;
             if (have) {
                 s0 = s_lstart[j0];
-                if (j0 + (MODE == kScanR1 ? 4u : 3u) <= n_listed) {
+                if (j0 + (MODE == kScanR2 ? 3u : 4u) <= n_listed) {
                     s1 = s_lstart[j0 + 1];
                     s2 = s_lstart[j0 + 2];
                     s3 = s_lstart[j0 + 3];
-                    if (MODE == kScanR1) s4 = s_lstart[j0 + 4];
+                    if (MODE != kScanR2) s4 = s_lstart[j0 + 4];
                     // read 2 only needs line 3 to exist; the generic path raises the overflow flag
-                    fast = (MODE == kScanR1 || tile_lo + s3 < args.len) && r < args.rec_cap;
+                    fast = (MODE != kScanR2 || tile_lo + s3 < args.len) && r < args.rec_cap;
                 }
             }
             // header bytes [s0, s0 + hdr_len), one trailing '\r' dropped; token = bytes before the first byte <= 0x20
@@ -644,6 +723,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
             // one pass over the header, four bytes at a time from its first byte (word w = bytes 4w .. 4w+3): id fingerprint
             // (both mates), and for read 1 the pieces of name.split("/")[0].replace(" ", "").strip() (V2:135-138)
             uint32_t cut = hdr_len, spaces = 0, bad = 0, tok_len = hdr_len;
+            uint32_t us1 = 0xFFFFu, us2 = 0xFFFFu, us3 = 0xFFFFu;  // annotated mode: the first three '_' of the header
             bool found_slash = false, found_tok = false;
             unsigned long long h = kTokSeed;
             {
@@ -668,6 +748,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                                 tw &= (1u << (8u * rem)) - 1u;  // the line ends inside this word
                             }
                             if (4u * w < tok_len) h = tok_hash_step(h, tw);
+                        }
+                        if (MODE == kScanAnn && us3 == 0xFFFFu) {
+                            uint32_t zu = zero_flags(x ^ 0x5F5F5F5Fu) & V;
+                            while (zu && us3 == 0xFFFFu) {
+                                const uint32_t p = 4u * w + (((uint32_t)__ffs((int)zu) - 1u) >> 3);
+                                zu &= zu - 1u;
+                                if (us1 == 0xFFFFu) us1 = p;
+                                else if (us2 == 0xFFFFu) us2 = p;
+                                else us3 = p;
+                            }
                         }
                         if (MODE == kScanR1 && !found_slash) {
                             const uint32_t zs = zero_flags(x ^ 0x2F2F2F2Fu) & V, zp = zero_flags(x ^ 0x20202020u) & V;
@@ -704,6 +794,72 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                 __syncwarp();
                 if (have && !ok) r1_record_generic(ga, args, r, tile_lo + s0);
                 __syncwarp();
+            } else if (MODE == kScanAnn) {
+                // ---- an annotated record: header = id _ cell _ umi [_ ...] (V2:395-398); every line is copied strip()ped ----
+                uint32_t seq_e = s2 - 1u, plus_e = s3 - 1u, qual_e = s4 - 1u;
+                bool ok = fast && bad == 0u && cfg.fast_wl != 0 && cfg.bc8 != 0 && hdr_len != 0u && !py_space(s_win[s0]);
+                if (ok) ok = rstrip2(s_win, s1, seq_e) && rstrip2(s_win, s2, plus_e) && rstrip2(s_win, s3, qual_e);
+                // leading blanks of the other lines would have to be stripped too: exact path
+                if (ok) ok = !(seq_e > s1 && py_space(s_win[s1])) && !(plus_e > s2 && py_space(s_win[s2])) && !(qual_e > s3 && py_space(s_win[s3]));
+                uint64_t an = 0;
+                if (ok) {
+                    if (us2 == 0xFFFFu) {
+                        raise(args.cnt, args.err_off, 0, kErrIndex, tile_lo + s0);
+                    } else {
+                        const uint32_t cell_s = us1 + 1u, cell_n = us2 - us1 - 1u;
+                        const uint32_t umi_s = us2 + 1u, ulen = (us3 == 0xFFFFu ? hdr_len : us3) - umi_s;
+                        int idx[3] = {-1, -1, -1};
+                        if (cell_n == 24u) {
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                uint32_t x0, x1, d0, d1;
+                                load8(words, s0 + cell_s + 8u * k, x0, x1);
+                                const uint32_t code = pack4(x0, d0) | (pack4(x1, d1) << 8);
+                                if ((d0 | d1) == 0u) {
+                                    const uint32_t v = __ldg(args.lut + code);  // level 0: exact match
+                                    idx[k] = v == 0xFFu ? -1 : (int)v;
+                                }
+                            }
+                        }
+                        if (idx[0] < 0 || idx[1] < 0 || idx[2] < 0 || ulen > 10u) {
+                            raise(args.cnt, args.err_off, 0, kErrForeign, tile_lo + s0);
+                        } else {
+                            const uint32_t cell = (uint32_t)((idx[0] * cfg.n_wl + idx[1]) * cfg.n_wl + idx[2]);
+                            const uint32_t up = s0 + umi_s;
+                            const uint32_t i0 = up >> 2, sh = (up & 3u) * 8u;
+                            const uint32_t w0 = words[i0], w1 = words[i0 + 1], w2 = words[i0 + 2], w3 = words[i0 + 3];
+                            const uint32_t m0 = ulen >= 4u ? 0xFFFFFFFFu : (1u << (8u * ulen)) - 1u;
+                            const uint32_t m1 = ulen >= 8u ? 0xFFFFFFFFu : (ulen > 4u ? (1u << (8u * (ulen - 4u))) - 1u : 0u);
+                            const uint32_t m2 = ulen > 8u ? (1u << (8u * (ulen - 8u))) - 1u : 0u;
+                            const uint32_t u0 = __funnelshift_r(w0, w1, sh) & m0, u1 = __funnelshift_r(w1, w2, sh) & m1,
+                                           u2 = __funnelshift_r(w2, w3, sh) & m2;
+                            uint32_t e0, e1, e2;
+                            const uint64_t ucode = ((uint64_t)pack4(u0, e0) | ((uint64_t)pack4(u1, e1) << 8) | ((uint64_t)pack4(u2, e2) << 16)) &
+                                                   ((1ull << cfg.umi_bits) - 1ull);
+                            if (ulen == (uint32_t)cfg.umi_len && ((e0 & m0) | (e1 & m1) | (e2 & m2)) == 0u)
+                                an = kAnnRegular | ((uint64_t)cell << kAnnCellShift) | ucode;
+                            else
+                                an = kAnnIrregular | ((uint64_t)cell << kAnnCellShift) | ((uint64_t)(tile_lo + up) << 5) | (uint64_t)ulen;
+                        }
+                    }
+                    uint4 mt;
+                    mt.x = hdr_len | (hdr_len << 16);
+                    mt.y = (s1 - s0) | ((seq_e - s1) << 16);
+                    mt.z = (s3 - s0) | ((qual_e - s3) << 16);
+                    mt.w = ((plus_e - s2) << 1) | ((s2 - s0) << 16);
+                    args.r1_start[r] = (OffT)(tile_lo + s0);
+                    args.r1_meta[r] = mt;
+                    args.r1_base[r] = hdr_len + (seq_e - s1) + (plus_e - s2) + (qual_e - s3) + 4u;
+                    args.ann[r] = an;
+                }
+                __syncwarp();
+                if (have && !ok) an = ann_record_generic(ga, args, cfg, r, tile_lo + s0);
+                __syncwarp();
+                const uint32_t st8 = ann_state(an);
+                if (st8) atomicAdd(&args.hist[ann_cell(an)], 1u);
+                const uint32_t nreg = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 1u)), nirr = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 2u));
+                if (lane == 0 && nreg) atomicAdd(&args.cnt->n_keys, (unsigned long long)nreg);
+                if (lane == 0 && nirr) atomicAdd(&args.cnt->n_irr, (unsigned long long)nirr);
             } else {
                 // the fingerprint read 1 left for this record: requested now, needed after the matching
                 unsigned long long fp1 = 0;
@@ -800,8 +956,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
     }
 #ifdef SSD_SCAN_PROFILE
     if (tid == 0) {
-        for (int k = 0; k < 5; k++) atomicAdd(&g_scan_prof[MODE][k], prof[k]);
-        atomicAdd(&g_scan_prof[MODE][7], (unsigned long long)n_a);
+        for (int k = 0; k < 5; k++) atomicAdd(&g_scan_prof[MODE == kScanR2 ? 1 : 0][k], prof[k]);
+        atomicAdd(&g_scan_prof[MODE == kScanR2 ? 1 : 0][7], (unsigned long long)n_a);
     }
 #endif
 }

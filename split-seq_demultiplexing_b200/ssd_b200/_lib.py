@@ -19,7 +19,7 @@ HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "ssd_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
-OK, EINVAL, ECUDA, EKEY, EMALFORMED, ENOMEM, ESTATE, ERANGE = 0, -1, -2, -3, -4, -5, -6, -7
+OK, EINVAL, ECUDA, EKEY, EMALFORMED, ENOMEM, ESTATE, ERANGE, EINDEX = 0, -1, -2, -3, -4, -5, -6, -7, -8
 FILTER_DISTINCT_UMI, FILTER_READS = 0, 1
 EMIT_MATCHED, EMIT_PASSING = 0, 1
 
@@ -84,6 +84,8 @@ _SIGS = {
     "ssd_last_error": (C.c_char_p, [C.c_void_p]),
     "ssd_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ssd_demux_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "ssd_annotated_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ssd_annotated_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(Stats)]),
     "ssd_cell_space": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "ssd_reads_histogram_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "ssd_distinct_histogram_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

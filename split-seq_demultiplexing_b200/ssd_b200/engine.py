@@ -17,6 +17,8 @@ class MalformedFastq(ValueError):
 def _raise(code: int, msg: str):
     if code == L.EKEY:
         raise KeyError(msg)                       # V2:350
+    if code == L.EINDEX:
+        raise IndexError(msg)                     # V2:397-398
     if code == L.EMALFORMED:
         raise MalformedFastq(msg)
     if code == L.EINVAL:
@@ -204,6 +206,19 @@ class Demultiplexer:
             out = np.empty(n.value, dtype=np.uint8)
         if n.value:
             self._check(self.lib.ssd_emit_host(self._ctx, which, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)))
+        return out[: n.value], st.as_dict()
+
+    def filter_annotated_host(self, text):
+        """V2.calc_demux_results on the text of MergedCells_1.fastq (any buffer-protocol object): returns
+        (uint8 array with the records of passing cells, stats)."""
+        import numpy as np
+        a = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
+        st = L.Stats()
+        n = C.c_size_t()
+        self._check(self.lib.ssd_annotated_host(self._ctx, a.ctypes.data_as(C.c_void_p), a.size, None, 0, C.byref(n), C.byref(st)))
+        out = np.empty(n.value, dtype=np.uint8)
+        if n.value:
+            self._check(self.lib.ssd_emit_host(self._ctx, L.EMIT_PASSING, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)))
         return out[: n.value], st.as_dict()
 
     def cell_table(self) -> Dict[str, Tuple[int, int]]:

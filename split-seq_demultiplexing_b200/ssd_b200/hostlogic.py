@@ -1,0 +1,85 @@
+"""Host-side logic of the reference's fast path that is not byte crunching: whitelist files, the position
+learner and argument conventions.  Mirrors python_only_tool/DemultiplexUsingBarcodes_New_V2.py (V2) and
+python_only_tool/Splitseq_fun_lib.py (LIB) of the reference; file:line citations are relative to its root."""
+from __future__ import annotations
+
+import itertools
+import os
+from collections import Counter
+from typing import Dict, Iterable, List, Tuple
+
+ROUND1_FILE = "Round1_barcodes_new5.txt"   # V2:56  (opened relative to the CWD, like the reference)
+ROUND2_FILE = "Round2_barcodes_new4.txt"   # V2:62
+ROUND3_FILE = "Round3_barcodes_new4.txt"   # V2:66
+LEARNER_FILE = "position_learner_fastqr.fastq"  # V2:171, written by LIB:99-110
+ANCHORS = ("CATTCG", "ATCCAC", "GTGGCC")   # Round1/2/3 static sequences, V2:36-38
+DEFAULT_POSITIONS = {"umi": (0, 10), "bc3": (10, 18), "bc2": (48, 56), "bc1": (86, 94)}  # V2:155-162
+
+
+def load_whitelist(directory: str = ".") -> List[str]:
+    """V2:51-68: one list serves all three rounds — characters [8:16] of every line of the Round-1 file.  The
+    Round-2/3 files are opened (and must exist) but their content is never used."""
+    with open(os.path.join(directory, ROUND1_FILE), "r") as fh:
+        wl = [line.rstrip()[8:16] for line in fh]
+    for name in (ROUND2_FILE, ROUND3_FILE):
+        with open(os.path.join(directory, name), "r") as fh:
+            for _ in fh:
+                pass
+    return wl
+
+
+def learner_sample(fastq_r: str, n_lines: int = 1001) -> List[str]:
+    """LIB:99-110: the first 1001 lines of read 2, each strip()ped."""
+    with open(fastq_r, "r") as fh:
+        return [line.strip() + "\n" for line in itertools.islice(fh, n_lines)]
+
+
+def learn_positions(lines: Iterable[str]) -> Dict[str, Tuple[int, int]]:
+    """V2:164-199.  Over sequence lines (index % 4 == 1) keep find() positions >= 17 of the three static
+    sequences, take the mode of each (first maximum in set iteration order, exactly what
+    max(set(l), key=l.count) returns), derive the four slices.  ValueError when a list is empty."""
+    found: List[List[int]] = [[], [], []]
+    for n, line in enumerate(lines):
+        if n % 4 == 1:
+            for k, anchor in enumerate(ANCHORS):
+                p = line.find(anchor)
+                if p >= 17:
+                    found[k].append(p)
+    modes = []
+    for lst in found:
+        if not lst:
+            raise ValueError("max() arg is an empty sequence")  # what V2:181-183 raises
+        counts = Counter(lst)
+        best = None
+        for v in set(lst):
+            if best is None or counts[v] > counts[best]:
+                best = v
+        modes.append(best)
+    p1, p2, p3 = modes
+    return {"umi": (p3 - 18, p3 - 8), "bc3": (p3 - 8, p3), "bc2": (p2 - 8, p2), "bc1": (p1 + 6, p1 + 14),
+            "_found": (p1, p2, p3)}
+
+
+def positions_report(pos: Dict[str, Tuple[int, int]]) -> List[str]:
+    """The lines V2:184-199 prints."""
+    p1, p2, p3 = pos["_found"]
+    return ["Extracted position1 = %d" % p1, "Extracted position2 = %d" % p2, "Extracted position3 = %d" % p3,
+            "UMI position has been extracted as %d:%d" % pos["umi"],
+            "Barcode3 position has been extracted as %d:%d" % pos["bc3"],
+            "Barcode2 position has been extracted as %d:%d" % pos["bc2"],
+            "Barcode1 position has been extracted as %d:%d" % pos["bc1"]]
+
+
+def tuned_split_size(length_fastq: int, split_num: int, tries: int = 100) -> int:
+    """LIB:11-19 / 58-66: lengthFastq / N bumped until it is a multiple of 4."""
+    size = length_fastq / int(split_num)
+    for _ in range(tries):
+        if size % 4 != 0:
+            size = int(size) + 1
+    return int(size)
+
+
+def summary_lines(n_cells: int, threshold, n_passing: int) -> List[str]:
+    """V2:458-459, verbatim."""
+    return ["The total number of unique barcodes detected was " + str(n_cells),
+            "The number of barcodes passing the minimum UMI threshold of " + str(threshold) + " was " + str(n_passing)]

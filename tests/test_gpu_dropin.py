@@ -1,0 +1,126 @@
+"""GPU tests of the drop-in surface: the reference's module / function / CLI names (V2.demultiplex_fun,
+V2.calc_demux_results, splitseqdemultiplex_0.2.3.py) backed by the CUDA library, checked against the golden
+vectors of the unmodified reference."""
+import contextlib
+import importlib
+import io
+import json
+import os
+import runpy
+import sys
+
+import pytest
+
+import fastq_util as fu
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "split-seq_demultiplexing_b200")
+WL = fu.load_whitelist()
+
+
+@pytest.fixture()
+def workdir(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    fu.write_whitelist_files(str(tmp_path))
+    r1, r2 = fu.load_bundled()
+    open("F.fastq", "wb").write(r1)
+    open("R.fastq", "wb").write(r2)
+    os.makedirs("out")
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    return tmp_path
+
+
+@pytest.fixture(scope="module")
+def digests():
+    with open(os.path.join(fu.GOLDEN_DIR, "bundled_digests.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("e,m", [(1, 10), (2, 10), (0, 1), (3, 10)])
+def test_reference_function_surface(workdir, digests, e, m):
+    V2 = importlib.import_module("DemultiplexUsingBarcodes_New_V2")
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        V2.demultiplex_fun("F.fastq", "R.fastq", "out", 100000, e, True, 10, False, True)
+        V2.calc_demux_results("out", True, str(m))        # CLI3 passes -m through as a string
+    gold = digests["e%d_m%d" % (e, m)]
+    assert fu.canonical_sha(open("out/MergedCells_1.fastq", "rb").read()) == gold["merged1_sha"]
+    assert fu.canonical_sha(open("out/MergedCells_passing.fastq", "rb").read()) == gold["passing_sha"]
+    assert buf.getvalue().strip().split("\n")[-2:] == gold["stdout_tail"]
+
+
+def test_position_detection_path(workdir, digests):
+    V2 = importlib.import_module("DemultiplexUsingBarcodes_New_V2")
+    lib = importlib.import_module("Splitseq_fun_lib")
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        lib.split_fastqR_fun(1, "R.fastq", 20000)          # writes position_learner_fastqr.fastq like CLI3:53
+        V2.demultiplex_fun("F.fastq", "R.fastq", "out", 100000, 1, True, 10, True)
+    assert "Barcode1 position has been extracted as 86:94" in buf.getvalue()
+    assert fu.canonical_sha(open("out/MergedCells_1.fastq", "rb").read()) == digests["e1_m10"]["merged1_sha"]
+
+
+def test_append_mode_like_the_reference(workdir, digests):
+    V2 = importlib.import_module("DemultiplexUsingBarcodes_New_V2")
+    with contextlib.redirect_stdout(io.StringIO()):
+        V2.demultiplex_fun("F.fastq", "R.fastq", "out", 100000, 1, True, 10, False)
+        V2.demultiplex_fun("F.fastq", "R.fastq", "out", 100000, 1, True, 10, False)   # second chunk appends (V2:367)
+    recs = fu.records(open("out/MergedCells_1.fastq", "rb").read())
+    assert len(recs) == 2 * digests["e1_m10"]["matched"]
+
+
+def test_cli_drop_in(workdir, digests):
+    argv = ["-n", "4", "-e", "1", "-m", "10", "-1", "a", "-2", "b", "-3", "c", "-f", "F.fastq", "-r", "R.fastq", "-o", "results",
+            "-a", "", "-b", "100000", "-p", "True", "-l", "20000"]
+    buf = io.StringIO()
+    old = sys.argv
+    sys.argv = ["splitseqdemultiplex_0.2.3.py"] + argv
+    try:
+        with contextlib.redirect_stdout(buf):
+            runpy.run_path(os.path.join(PKG, "splitseqdemultiplex_0.2.3.py"), run_name="__main__")
+    finally:
+        sys.argv = old
+    gold = digests["e1_m10"]
+    assert fu.canonical_sha(open("results/MergedCells_passing.fastq", "rb").read()) == gold["passing_sha"]
+    out = buf.getvalue()
+    assert gold["stdout_tail"][0] in out and gold["stdout_tail"][1] in out
+    assert "Barcode1 position has been extracted as 86:94" in out      # detection is on by default (CLI3:38)
+
+
+RULES = [c for c in fu.load_json_gz("rule_cases.json.gz") if "error" not in c]
+
+
+@pytest.mark.parametrize("case", RULES, ids=["%s-e%d" % (c["name"], c["e"]) for c in RULES])
+def test_calc_demux_results_on_reference_text(case):
+    """The annotated-FASTQ path alone: the reference's own MergedCells_1 text in, its MergedCells_passing out."""
+    import ssd_b200
+    dm = ssd_b200.Demultiplexer(WL, errors=0, min_count=case["m"])
+    out, stats = dm.filter_annotated_host(case["merged1"].encode())
+    assert fu.canonical(out.tobytes()).decode() == case["passing"]
+    assert case["stdout_tail"][0].endswith(" %d" % stats["n_cells"])
+    assert case["stdout_tail"][1].endswith(" %d" % stats["n_passing_cells"])
+
+
+ADV = fu.load_json_gz("adversarial.json.gz")
+
+
+@pytest.mark.parametrize("g", ADV, ids=["%s-e%d-m%d" % (g["name"], g["e"], g["m"]) for g in ADV])
+def test_calc_demux_results_adversarial(g):
+    import ssd_b200
+    from oracle import ssd_oracle_py as orc
+    r1, r2 = fu.make_pairs(g["seed"], g["n"], WL, **g["kwargs"])
+    merged1 = orc.demultiplex(r1, r2, WL, g["e"], g["m"]).merged1     # == the reference's text up to record order
+    assert fu.canonical_sha(merged1) == g["merged1_sha"]
+    dm = ssd_b200.Demultiplexer(WL, errors=0, min_count=g["m"])
+    out, stats = dm.filter_annotated_host(merged1)
+    assert fu.canonical_sha(out.tobytes()) == g["passing_sha"]
+    assert (stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]) == (g["cells"], g["passing_cells"], g["retained"])
+
+
+def test_calc_demux_results_index_error():
+    import ssd_b200
+    dm = ssd_b200.Demultiplexer(WL, errors=0, min_count=1)
+    with pytest.raises(IndexError):
+        dm.filter_annotated_host(b"@noannotation\nACGT\n+\nEEEE\n")

@@ -1,0 +1,133 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/ssd_b200.h declares, the host-side
+logic (position learner, whitelist files, FASTQ splitter, synthetic generator twin) behaves like the reference."""
+import ctypes
+import json
+import os
+import re
+import sys
+
+import pytest
+
+import fastq_util as fu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "split-seq_demultiplexing_b200")
+WL = fu.load_whitelist()
+
+
+@pytest.fixture(scope="module")
+def ssd():
+    import ssd_b200
+    if ssd_b200.needs_build():
+        ssd_b200.build()
+    return ssd_b200
+
+
+def test_library_exports_every_declared_symbol(ssd):
+    header = open(os.path.join(ROOT, "include", "ssd_b200.h")).read()
+    declared = set(re.findall(r"\b(ssd_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ssd_config", "ssd_stats", "ssd_synth_spec", "ssd_ctx"}
+    lib = ctypes.CDLL(ssd.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(ssd.exported_symbols()) <= declared, set(ssd.exported_symbols()) - declared
+    assert len(declared) >= 25
+    assert lib.ssd_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu(ssd):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ssd.Demultiplexer(WL)
+
+
+def test_bad_config_is_rejected_before_touching_the_gpu(ssd):
+    with pytest.raises(ValueError):
+        ssd.Demultiplexer(WL, positions={"umi": (5, 2)})
+    with pytest.raises(ValueError):
+        ssd.Demultiplexer(WL, positions={"bc1": (-2, 6)})
+
+
+def test_learner_matches_golden_cases(ssd):
+    from ssd_b200 import hostlogic
+    with open(os.path.join(fu.GOLDEN_DIR, "learner_cases.json")) as fh:
+        cases = json.load(fh)
+    for c in cases:
+        seq = "T" * c["shift"] + "ACGTACGTAC" + WL[3] + fu.LINKER_3_2 + WL[7] + fu.LINKER_2_1 + WL[50] + "ACGT" * 10
+        recs = "".join("@l%d %d/2\n%s\n+\n%s\n" % (i, i, seq, "A" * len(seq)) for i in range(300))
+        lines = [l + "\n" for l in recs.split("\n")[:1001]]
+        pos = hostlogic.learn_positions(lines)
+        report = hostlogic.positions_report(pos)
+        for printed in c["printed"]:
+            assert printed in report
+
+
+def test_learner_bundled_equals_defaults_and_oracle(ssd):
+    from oracle import ssd_oracle_py as orc
+    from ssd_b200 import hostlogic
+    r2 = fu.load_bundled()[1]
+    lines = [l.decode() + "\n" for l in r2.split(b"\n")[:1001]]
+    pos = hostlogic.learn_positions(lines)
+    assert pos["_found"] == orc.learn_positions("".join(lines).encode()) == (80, 56, 18)
+    pos.pop("_found")
+    assert pos == hostlogic.DEFAULT_POSITIONS
+
+
+def test_learner_empty_raises_value_error(ssd):
+    from ssd_b200 import hostlogic
+    with pytest.raises(ValueError):
+        hostlogic.learn_positions(["@a\n", "ACGT\n", "+\n", "EEEE\n"])
+
+
+def test_whitelist_files(ssd, tmp_path):
+    from ssd_b200 import hostlogic
+    fu.write_whitelist_files(str(tmp_path))
+    assert hostlogic.load_whitelist(str(tmp_path)) == WL
+    os.remove(os.path.join(str(tmp_path), hostlogic.ROUND3_FILE))
+    with pytest.raises(FileNotFoundError):   # the reference opens all three files (V2:56-68)
+        hostlogic.load_whitelist(str(tmp_path))
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 8])
+def test_split_functions_cut_like_the_reference(ssd, tmp_path, monkeypatch, n):
+    from ssd_b200 import hostlogic
+    sys.path.insert(0, PKG)
+    import Splitseq_fun_lib as lib
+    r1, r2 = fu.load_bundled()
+    monkeypatch.chdir(tmp_path)
+    open("F.fastq", "wb").write(r1)
+    open("R.fastq", "wb").write(r2)
+    lib.split_fastqF_fun(n, "F.fastq", 20000)
+    lib.split_fastqR_fun(n, "R.fastq", 20000)
+    size = hostlogic.tuned_split_size(20000, n)
+    assert size % 4 == 0 and size * n >= 20000 and size == {1: 20000, 3: 6668, 4: 5000, 8: 2500}[n]
+    got = b"".join(open("split_fastq_F_%d" % k, "rb").read() for k in range(n))
+    assert got == r1
+    assert all(open("split_fastq_R_%d" % k, "rb").read().count(b"\n") == min(size, 20000 - k * size) for k in range(n))
+    assert open(hostlogic.LEARNER_FILE, "rb").read() == b"".join(l + b"\n" for l in r2.split(b"\n")[:1001])
+
+
+def test_synthetic_generator_twin_is_deterministic_and_well_formed(ssd):
+    spec = ssd.synth_spec(WL, 3000, seed=11, first_index=998, p_tie=0.02, p_trunc=0.02)
+    a1, a2 = ssd.synth_host(spec)
+    b1, b2 = ssd.synth_host(ssd.synth_spec(WL, 3000, seed=11, first_index=998, p_tie=0.02, p_trunc=0.02))
+    assert (a1, a2) == (b1, b2)
+    assert ssd.synth_sizes(spec) == (len(a1), len(a2))
+    l1, l2 = a1.split(b"\n"), a2.split(b"\n")
+    assert len(l1) == len(l2) == 4 * 3000 + 1
+    assert l1[0] == b"@SYN.998 998/1" and l2[0] == b"@SYN.998 998/2" and l1[8] == b"@SYN.1000 1000/1"
+    assert all(len(l1[4 * k + 1]) == 150 == len(l1[4 * k + 3]) for k in range(3000))
+    assert all(len(l2[4 * k + 1]) == len(l2[4 * k + 3]) for k in range(3000))
+    assert any(len(l2[4 * k + 1]) < 94 for k in range(3000))            # truncated read 2 present
+    assert sum(l2[4 * k + 1][18:48] == fu.LINKER_3_2.encode() for k in range(3000)) > 2500
+
+
+def test_oracle_on_synthetic_is_sane(ssd):
+    from oracle import ssd_oracle_py as orc
+    spec = ssd.synth_spec(WL, 20000, seed=5, cell_pool=500)
+    r1, r2 = ssd.synth_host(spec)
+    res = orc.demultiplex(r1, r2, WL, 1, 10)
+    assert res.n_records == 20000 and 0.8 * 20000 < res.n_matched < 20000
+    assert 0 < res.n_passing_cells <= res.n_cells <= 500 + 2000
