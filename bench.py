@@ -168,25 +168,6 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def exchange_distinct(dm, dist, torch, world):
-    """Exact global distinct-UMI counts: local sort+unique, all-to-all by cell range, count, all-reduce."""
-    keys, irr = dm.local_unique_keys()
-    per = (dm.n_cells_total + world - 1) // world
-    edges = torch.arange(0, world + 1, device=keys.device, dtype=torch.int64) * per
-    kb = torch.searchsorted(keys, edges << dm.umi_bits) if keys.numel() else torch.zeros(world + 1, dtype=torch.int64, device=keys.device)
-    ib = torch.searchsorted(irr[:, 0].contiguous(), edges << 36) if irr.numel() else torch.zeros(world + 1, dtype=torch.int64, device=keys.device)
-    send = torch.stack([kb[1:] - kb[:-1], ib[1:] - ib[:-1]], dim=1).contiguous()  # [world, 2]
-    recv = torch.empty_like(send)
-    dist.all_to_all_single(recv, send)
-    send_l, recv_l = send.cpu().tolist(), recv.cpu().tolist()
-    rk = torch.empty(sum(r[0] for r in recv_l), dtype=torch.int64, device=keys.device)
-    dist.all_to_all_single(rk, keys, [r[0] for r in recv_l], [s[0] for s in send_l])
-    ri = torch.empty((sum(r[1] for r in recv_l), 2), dtype=torch.int64, device=keys.device)
-    dist.all_to_all_single(ri, irr.contiguous(), [r[1] for r in recv_l], [s[1] for s in send_l])
-    dm.count_distinct(rk, ri)
-    dist.all_reduce(dm.distinct_histogram())
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,6 +187,7 @@ def main():
     import torch
     import torch.distributed as dist
     import ssd_b200
+    from ssd_b200.distributed import global_filter
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,12 +208,7 @@ def main():
 
     def step():
         dm.demux_device(d1.data_ptr(), d1.numel(), d2.data_ptr(), d2.numel())
-        if world > 1:
-            dist.all_reduce(dm.reads_histogram())
-            exchange_distinct(dm, dist, torch, world)
-            st = dm.build_filter()
-        else:
-            st = dm.filter_single()
+        st = global_filter(dm, world)  # N > 1: all-reduce of the read histogram, all-to-all of the keys, all-reduce of the distinct table
         st["written"] = dm.emit_device(ssd_b200.EMIT_PASSING, out.data_ptr(), out.numel())
         last.update(st)
 

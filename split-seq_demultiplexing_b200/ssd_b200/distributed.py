@@ -1,0 +1,71 @@
+"""Multi-GPU orchestration: one process per GPU (torch.distributed), reads sharded by record range.
+
+The per-cell READ counts are additive, so they are all-reduced (NCCL over NVLink).  The reference's -m, however,
+counts DISTINCT UMIs per cell (V2:411), which is not additive across shards: every rank therefore sorts and
+deduplicates its own (cell, UMI) keys, the keys are exchanged all-to-all by CELL RANGE (rank k owns cells
+[k * ceil(C / W), (k + 1) * ceil(C / W))), every rank counts the distinct keys of the cells it owns, and those
+counts (zero elsewhere) are all-reduced so that all ranks hold the same, exact, global table.
+
+The functions below only use torch ops + collectives on whatever device the tensors live on, so the exchange logic
+is exercised on CPU with the gloo backend in tests/test_distributed_gloo.py.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+IRR_CELL_SHIFT = 36  # irregular key: hi = cell << 36 | len << 32 | bytes[0..4)  (include/ssd_b200.h)
+
+
+def cell_range_edges(n_cells_total: int, world: int, device):
+    import torch
+    per = (n_cells_total + world - 1) // world
+    return torch.arange(0, world + 1, device=device, dtype=torch.int64) * per
+
+
+def split_points(keys, irr, n_cells_total: int, world: int, umi_bits: int):
+    """Where the sorted key arrays have to be cut so that piece k holds the cells rank k owns.
+    keys: int64[n] sorted, cell = key >> umi_bits.  irr: int64[m, 2] sorted by (hi, lo), cell = hi >> 36."""
+    import torch
+    edges = cell_range_edges(n_cells_total, world, keys.device)
+    kb = torch.searchsorted(keys, edges << umi_bits) if keys.numel() else torch.zeros(world + 1, dtype=torch.int64, device=keys.device)
+    ib = (torch.searchsorted(irr[:, 0].contiguous(), edges << IRR_CELL_SHIFT) if irr.numel()
+          else torch.zeros(world + 1, dtype=torch.int64, device=keys.device))
+    return kb, ib
+
+
+def exchange_keys(keys, irr, n_cells_total: int, world: int, umi_bits: int, group=None):
+    """All-to-all of the locally unique keys by cell range.  Returns (received regular keys, received irregular
+    keys): everything any rank holds for the cells this rank owns (duplicates across source ranks included)."""
+    import torch
+    import torch.distributed as dist
+    kb, ib = split_points(keys, irr, n_cells_total, world, umi_bits)
+    send = torch.stack([kb[1:] - kb[:-1], ib[1:] - ib[:-1]], dim=1).contiguous()  # [world, 2]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    send_l, recv_l = send.cpu().tolist(), recv.cpu().tolist()
+    rk = torch.empty(sum(r[0] for r in recv_l), dtype=torch.int64, device=keys.device)
+    dist.all_to_all_single(rk, keys.contiguous(), [r[0] for r in recv_l], [s[0] for s in send_l], group=group)
+    ri = torch.empty((sum(r[1] for r in recv_l), 2), dtype=torch.int64, device=keys.device)
+    dist.all_to_all_single(ri, irr.contiguous(), [r[1] for r in recv_l], [s[1] for s in send_l], group=group)
+    return rk, ri
+
+
+def global_filter(dm, world: int, group=None) -> dict:
+    """After dm.demux_device(...) on every rank: make the -m decision global and exact, return dm's stats.
+    Collectives: all-reduce of the read histogram, all-to-all of the unique keys, all-reduce of the distinct table."""
+    import torch.distributed as dist
+    if world > 1:
+        dist.all_reduce(dm.reads_histogram(), group=group)
+        if dm.filter_mode == "distinct_umi":
+            keys, irr = dm.local_unique_keys()
+            rk, ri = exchange_keys(keys, irr, dm.n_cells_total, world, dm.umi_bits, group=group)
+            dm.count_distinct(rk, ri)
+            dist.all_reduce(dm.distinct_histogram(), group=group)
+        return dm.build_filter()
+    return dm.filter_single()
+
+
+def shard_record_ranges(n_records: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous record ranges per rank (the reference cuts line-aligned chunks the same way, LIB:6-97)."""
+    per = (n_records + world - 1) // world
+    return [(min(k * per, n_records), min((k + 1) * per, n_records)) for k in range(world)]

@@ -1,0 +1,81 @@
+"""world_size-2 (and 3) gloo tests, on CPU, of the multi-GPU exchange logic in ssd_b200/distributed.py: the keys
+every rank receives are exactly the keys of the cells it owns, and per-cell distinct counts computed from them and
+summed over ranks equal the single-process answer."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import conftest  # noqa: F401  (sys.path)
+
+N_CELLS = 96 ** 3
+UMI_BITS = 20
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make_keys(seed):
+    rng = np.random.default_rng(seed)
+    cells = rng.choice(N_CELLS, size=300, replace=False)
+    c = rng.choice(cells, size=20000)
+    u = rng.integers(0, 1 << 12, size=20000)          # few UMIs: plenty of duplicates within and across ranks
+    keys = np.unique((c.astype(np.int64) << UMI_BITS) | u)
+    ci = rng.choice(cells, size=800)
+    hi = (ci.astype(np.int64) << 36) | (rng.integers(0, 11, size=800).astype(np.int64) << 32) | rng.integers(0, 5, size=800)
+    lo = rng.integers(0, 3, size=800).astype(np.int64)
+    irr = np.unique(np.stack([hi, lo], axis=1), axis=0)
+    return keys, irr
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ssd_b200 import distributed as D
+    keys, irr = _make_keys(100 + rank)
+    rk, ri = D.exchange_keys(torch.from_numpy(keys), torch.from_numpy(irr), N_CELLS, world, UMI_BITS)
+    per = (N_CELLS + world - 1) // world
+    lo_cell, hi_cell = rank * per, (rank + 1) * per
+    assert bool(((rk >> UMI_BITS) >= lo_cell).all()) and bool(((rk >> UMI_BITS) < hi_cell).all())
+    assert ri.numel() == 0 or (bool(((ri[:, 0] >> 36) >= lo_cell).all()) and bool(((ri[:, 0] >> 36) < hi_cell).all()))
+    # per-cell distinct counts of the owned cells, then the same all-reduce the GPU path does
+    distinct = torch.zeros(N_CELLS, dtype=torch.int32)
+    uk = torch.unique(rk)
+    distinct.index_add_(0, (uk >> UMI_BITS), torch.ones(uk.numel(), dtype=torch.int32))
+    if ri.numel():
+        ui = torch.unique(ri, dim=0)
+        distinct.index_add_(0, (ui[:, 0] >> 36), torch.ones(ui.shape[0], dtype=torch.int32))
+    dist.all_reduce(distinct)
+    np.save(os.path.join(out_dir, "distinct_%d.npy" % rank), distinct.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_by_cell_range(tmp_path, world):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    tables = [np.load(os.path.join(str(tmp_path), "distinct_%d.npy" % r)) for r in range(world)]
+    for t in tables[1:]:
+        assert (t == tables[0]).all()                     # identical on every rank
+    all_keys = np.unique(np.concatenate([_make_keys(100 + r)[0] for r in range(world)]))
+    all_irr = np.unique(np.concatenate([_make_keys(100 + r)[1] for r in range(world)]), axis=0)
+    want = np.zeros(N_CELLS, dtype=np.int64)
+    np.add.at(want, all_keys >> UMI_BITS, 1)
+    np.add.at(want, all_irr[:, 0] >> 36, 1)
+    assert (tables[0] == want).all()
+
+
+def test_shard_record_ranges():
+    from ssd_b200.distributed import shard_record_ranges
+    assert shard_record_ranges(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert shard_record_ranges(3, 8)[3:] == [(3, 3)] * 5
+    r = shard_record_ranges(1_000_000_007, 8)
+    assert r[0][0] == 0 and r[-1][1] == 1_000_000_007 and all(a[1] == b[0] for a, b in zip(r, r[1:]))

@@ -1,0 +1,73 @@
+"""Two ranks, two GPUs (NCCL): reads sharded by record range, global and exact -m decision.  The concatenation of
+the ranks' outputs must equal the single-GPU output of the concatenated input, byte for byte."""
+import os
+import socket
+
+import pytest
+
+import fastq_util as fu
+
+pytestmark = pytest.mark.gpu
+
+WL = fu.load_whitelist()
+N_PER_RANK = 60000
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir, filter_mode):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import ssd_b200
+    from ssd_b200.distributed import global_filter
+    dm = ssd_b200.Demultiplexer(WL, errors=1, min_count=10, device=rank, filter_mode=filter_mode)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    dm.set_stream(stream.cuda_stream)
+    spec = ssd_b200.synth_spec(WL, N_PER_RANK, seed=77, first_index=1 + rank * N_PER_RANK, cell_pool=3000, p_n=0.01, p_dup_umi=0.3)
+    d1, d2 = ssd_b200.synth_device(dm, spec)
+    dm.demux_device(d1.data_ptr(), d1.numel(), d2.data_ptr(), d2.numel(), keep=(d1, d2))
+    stats = global_filter(dm, world)
+    out = torch.empty(stats["bytes_passing"] + 16, dtype=torch.uint8, device="cuda")
+    n = dm.emit_device(ssd_b200.EMIT_PASSING, out.data_ptr(), out.numel())
+    torch.cuda.synchronize()
+    np.save(os.path.join(out_dir, "out_%d.npy" % rank), out[:n].cpu().numpy())
+    np.save(os.path.join(out_dir, "stats_%d.npy" % rank), np.array([stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("filter_mode", ["distinct_umi", "reads"])
+def test_two_ranks_equal_one(tmp_path, filter_mode):
+    import numpy as np
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import ssd_b200
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), filter_mode), nprocs=world, join=True)
+    parts = [np.load(os.path.join(str(tmp_path), "out_%d.npy" % r)).tobytes() for r in range(world)]
+    st = [np.load(os.path.join(str(tmp_path), "stats_%d.npy" % r)) for r in range(world)]
+    # single GPU on the concatenated input
+    r1 = b"".join(ssd_b200.synth_host(ssd_b200.synth_spec(WL, N_PER_RANK, seed=77, first_index=1 + r * N_PER_RANK, cell_pool=3000,
+                                                          p_n=0.01, p_dup_umi=0.3))[0] for r in range(world))
+    r2 = b"".join(ssd_b200.synth_host(ssd_b200.synth_spec(WL, N_PER_RANK, seed=77, first_index=1 + r * N_PER_RANK, cell_pool=3000,
+                                                          p_n=0.01, p_dup_umi=0.3))[1] for r in range(world))
+    dm = ssd_b200.Demultiplexer(WL, errors=1, min_count=10, filter_mode=filter_mode)
+    out, stats = dm.run_host(r1, r2, ssd_b200.EMIT_PASSING)
+    assert b"".join(parts) == out.tobytes()
+    assert int(st[0][0]) == int(st[1][0]) == stats["n_cells"]               # global cell counts on every rank
+    assert int(st[0][1]) == int(st[1][1]) == stats["n_passing_cells"]
+    assert int(st[0][2]) + int(st[1][2]) == stats["n_retained"]             # retained records are per shard
+    if filter_mode == "distinct_umi":
+        from oracle import ssd_oracle_py as orc
+        assert out.tobytes() == orc.demultiplex(r1, r2, WL, 1, 10).passing
