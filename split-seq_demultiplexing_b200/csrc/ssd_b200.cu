@@ -69,6 +69,10 @@ struct ssd_ctx {
     DevBuf b_status1, b_status2, b_r1_start, b_r1_meta, b_r1_base, b_r1_tok, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
         b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
     DevBuf b_in1, b_in2, b_out;
+    // the irregular-key path runs on its own stream with its own scratch, next to the regular sort
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    DevBuf s_counts, s_offsets, s_bsums, s_pos;
 
     // instrumentation: kernel launch counter and optional per-stage CUDA-event timing
     uint64_t n_launches = 0;
@@ -90,6 +94,7 @@ int fail(ssd_ctx* c, int code, const char* fmt, ...)
     va_end(ap);
     return code;
 }
+
 
 struct StageTimer {  // records a CUDA-event pair around a pipeline stage when timing is on
     ssd_ctx* c;
@@ -172,13 +177,18 @@ template <class Src, bool HV>
 int radix_pass(ssd_ctx* c, Src src, uint64_t n, int bit, uint64_t* dst, const uint32_t* vsrc, uint32_t* vdst)
 {
     const uint32_t nb = blocks_for(n, kSortBlock);
-    const size_t ncount = (size_t)256 * nb;
+    const size_t ncount = (size_t)kRadix * nb;
     OKR(ensure(c, c->b_counts, ncount * sizeof(uint32_t)));
     OKR(ensure(c, c->b_offsets, (ncount + 1) * sizeof(uint32_t)));
     uint32_t* counts = (uint32_t*)c->b_counts.p;
     uint32_t* offsets = (uint32_t*)c->b_offsets.p;
     k_sort_hist<Src><<<nb, kThreads, 0, c->stream>>>(src, n, bit, counts, nb);
-    OKR(exclusive_scan<uint32_t>(c, LoadU32{counts}, ncount, offsets));
+    if (ncount <= kSmallScanMax) {
+        k_scan_small_u32<<<1, kSmallScanThreads, 0, c->stream>>>(counts, (uint32_t)ncount, offsets);
+        c->n_launches++;
+    } else {
+        OKR(exclusive_scan<uint32_t>(c, LoadU32{counts}, ncount, offsets));
+    }
     k_sort_scatter<Src, uint64_t, HV><<<nb, kThreads, 0, c->stream>>>(src, dst, vsrc, vdst, n, bit, offsets, nb);
     c->n_launches += 2;
     return SSD_OK;
@@ -191,7 +201,7 @@ int radix_sort64(ssd_ctx* c, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* v
     *sorted = a;
     if (sorted_vals) *sorted_vals = va;
     if (n == 0) return SSD_OK;
-    for (int bit = 0; bit < bits; bit += 8) {
+    for (int bit = 0; bit < bits; bit += kRadixBits) {
         OKR((radix_pass<KeysArray, HV>(c, KeysArray{a}, n, bit, b, va, vb)));
         std::swap(a, b);
         std::swap(va, vb);
@@ -205,10 +215,11 @@ int radix_sort64(ssd_ctx* c, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* v
 // sort + unique of regular keys.  `keys` holds n keys (or, when from_ann, the keys are taken from the
 // annotation words of the batch and `keys` only is the buffer they are compacted into by the first pass);
 // result: *uniq (a context buffer or `keys`), *n_uniq
-int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint64_t* n_uniq, bool from_ann = false)
+int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint32_t* total_host, bool from_ann = false)
 {
+    // enqueues only: *total_host (pinned or pageable) is valid after the caller synchronised c->stream
     *uniq = keys;
-    *n_uniq = 0;
+    *total_host = 0;
     if (n == 0) return SSD_OK;
     OKR(ensure(c, c->b_keys_alt, n * sizeof(uint64_t)));
     uint64_t* sorted = nullptr;
@@ -218,7 +229,7 @@ int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint6
         OKR((radix_pass<KeysFromAnn, false>(c, KeysFromAnn{(const uint64_t*)c->b_ann.p, c->dcfg.umi_bits}, c->n_rec_r2, 0,
                                             (uint64_t*)c->b_keys_alt.p, nullptr, nullptr)));
         uint64_t *a = (uint64_t*)c->b_keys_alt.p, *b = keys;
-        for (int bit = 8; bit < bits; bit += 8) {
+        for (int bit = kRadixBits; bit < bits; bit += kRadixBits) {
             OKR((radix_pass<KeysArray, false>(c, KeysArray{a}, n, bit, b, nullptr, nullptr)));
             std::swap(a, b);
         }
@@ -232,19 +243,17 @@ int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint6
     OKR(exclusive_scan<uint32_t>(c, HeadFlag64{sorted}, n, pos));
     k_compact64<<<blocks_for(n, kThreads), kThreads, 0, c->stream>>>(sorted, pos, n, other);
     c->n_launches += 1;
-    uint32_t total = 0;
-    CU(c, cudaMemcpyAsync(&total, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpyAsync(total_host, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     *uniq = other;
-    *n_uniq = total;
     return SSD_OK;
 }
 
 // sort + unique of irregular keys through an index permutation (128-bit LSD: low word, then high word)
-int sort_unique_irr(ssd_ctx* c, IrrKey* keys, uint64_t n, IrrKey** uniq, uint64_t* n_uniq)
+int sort_unique_irr(ssd_ctx* c, IrrKey* keys, uint64_t n, IrrKey** uniq, uint32_t* total_host)
 {
+    // enqueues only, like sort_unique64
     *uniq = keys;
-    *n_uniq = 0;
+    *total_host = 0;
     if (n == 0) return SSD_OK;
     OKR(ensure(c, c->b_perm, n * sizeof(uint32_t)));
     OKR(ensure(c, c->b_perm_alt, n * sizeof(uint32_t)));
@@ -271,11 +280,53 @@ int sort_unique_irr(ssd_ctx* c, IrrKey* keys, uint64_t n, IrrKey** uniq, uint64_
     OKR(exclusive_scan<uint32_t>(c, HeadFlagIrr{keys, perm}, n, pos));
     IrrKey* out = (IrrKey*)c->b_irr_alt.p;
     k_compact_irr<<<nb, kThreads, 0, c->stream>>>(keys, perm, pos, n, out);
-    uint32_t total = 0;
-    CU(c, cudaMemcpyAsync(&total, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpyAsync(total_host, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     *uniq = out;
-    *n_uniq = total;
+    return SSD_OK;
+}
+
+// Regular keys on the context's stream, irregular keys (few, launch-latency bound) next to them on the side
+// stream with their own scratch; joined before returning.  from_ann: keys come from the batch's annotations.
+int sort_unique_both(ssd_ctx* c, uint64_t* keys, uint64_t n_keys, IrrKey* irr, uint64_t n_irr, bool from_ann, uint64_t** uk, uint64_t* nuk,
+                     IrrKey** ui, uint64_t* nui)
+{
+    uint32_t tot_k = 0, tot_i = 0;
+    const bool side = n_irr != 0 && c->side_stream != nullptr;
+    if (side) {
+        CU(c, cudaEventRecord(c->ev_fork, c->stream));
+        CU(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+        std::swap(c->stream, c->side_stream);
+        std::swap(c->b_counts, c->s_counts);
+        std::swap(c->b_offsets, c->s_offsets);
+        std::swap(c->b_bsums, c->s_bsums);
+        std::swap(c->b_pos, c->s_pos);
+    }
+    int rc = SSD_OK;
+    if (n_irr) {
+        if (from_ann) {
+            unsigned long long* cursor = (unsigned long long*)c->d_err_off;  // free after phase 1 (errors were read)
+            cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), c->stream);
+            k_collect_irr<<<blocks_for(c->n_rec_r2, kThreads), kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, c->n_rec_r2, c->r2, irr, cursor);
+            c->n_launches++;
+        }
+        rc = sort_unique_irr(c, irr, n_irr, ui, &tot_i);
+    } else {
+        *ui = irr;
+    }
+    if (side) {
+        cudaEventRecord(c->ev_join, c->stream);
+        std::swap(c->stream, c->side_stream);
+        std::swap(c->b_counts, c->s_counts);
+        std::swap(c->b_offsets, c->s_offsets);
+        std::swap(c->b_bsums, c->s_bsums);
+        std::swap(c->b_pos, c->s_pos);
+    }
+    if (rc == SSD_OK) rc = sort_unique64(c, keys, n_keys, uk, &tot_k, from_ann);
+    if (side) cudaStreamWaitEvent(c->stream, c->ev_join, 0);
+    if (rc != SSD_OK) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    *nuk = tot_k;
+    *nui = tot_i;
     return SSD_OK;
 }
 
@@ -464,6 +515,9 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
     CUB_(cudaSetDevice(c->device));
     CUB_(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    CUB_(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    CUB_(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUB_(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 
     DevCfg& d = c->dcfg;
     memset(&d, 0, sizeof d);
@@ -560,6 +614,13 @@ extern "C" void ssd_destroy(ssd_ctx* c)
     cudaFree(c->d_distinct);
     cudaFree(c->d_remap);
     cudaFree(c->d_pass);
+    release(c->s_counts);
+    release(c->s_offsets);
+    release(c->s_bsums);
+    release(c->s_pos);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -697,15 +758,8 @@ extern "C" int ssd_local_unique_keys(ssd_ctx* c, uint64_t** d_keys, uint64_t* n_
     CU(c, cudaSetDevice(c->device));
     if (!c->unique_done) {
         StageTimer t(c, 2);
-        OKR(sort_unique64(c, (uint64_t*)c->b_keys.p, c->n_keys, &c->uniq_keys, &c->n_uniq, true));
-        if (c->n_irr) {
-            unsigned long long* cursor = (unsigned long long*)c->d_err_off;  // free after phase 1 (errors were read)
-            CU(c, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), c->stream));
-            k_collect_irr<<<blocks_for(c->n_rec_r2, kThreads), kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, c->n_rec_r2, c->r2, (IrrKey*)c->b_irr.p,
-                                                                                       cursor);
-            c->n_launches++;
-        }
-        OKR(sort_unique_irr(c, (IrrKey*)c->b_irr.p, c->n_irr, &c->uniq_irr, &c->n_uniq_irr));
+        OKR(sort_unique_both(c, (uint64_t*)c->b_keys.p, c->n_keys, (IrrKey*)c->b_irr.p, c->n_irr, true, &c->uniq_keys, &c->n_uniq, &c->uniq_irr,
+                             &c->n_uniq_irr));
         c->unique_done = true;
     }
     if (d_keys) *d_keys = c->uniq_keys;
@@ -729,8 +783,7 @@ extern "C" int ssd_count_distinct(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys,
         nui = c->n_uniq_irr;
     } else {
         c->unique_done = false;  // the context's buffers are reused as scratch below
-        OKR(sort_unique64(c, d_keys, n_keys, &uk, &nuk));
-        OKR(sort_unique_irr(c, (IrrKey*)d_irregular, n_irregular, &ui, &nui));
+        OKR(sort_unique_both(c, d_keys, n_keys, (IrrKey*)d_irregular, n_irregular, false, &uk, &nuk, &ui, &nui));
     }
     return count_cells(c, uk, nuk, ui, nui);
 }

@@ -271,9 +271,17 @@ __device__ __forceinline__ void group_copy(uint8_t* s_out, uint32_t d, const uin
     const size_t sal = s & ~(size_t)15;
     const uint32_t ws = (uint32_t)(s & 15) >> 2, bs = ((uint32_t)s & 3u) * 8u;
     uint4* dst = reinterpret_cast<uint4*>(dp + head);
+    const bool inside = sal + 16u * (size_t)(nchunks + 1u) <= len;  // every 16-byte load below stays inside the file
+    const uint4* src16 = reinterpret_cast<const uint4*>(buf + sal);
     for (uint32_t c = gl; c < nchunks; c += kGroup) {
-        const uint4 A = ldg16_safe(buf, sal + 16u * c, len);
-        const uint4 B = ldg16_safe(buf, sal + 16u * c + 16u, len);
+        uint4 A, B;
+        if (inside) {
+            A = __ldg(src16 + c);
+            B = __ldg(src16 + c + 1);
+        } else {
+            A = ldg16_safe(buf, sal + 16u * c, len);
+            B = ldg16_safe(buf, sal + 16u * c + 16u, len);
+        }
         // words [ws, ws + 5) of A:B, selected without branches (ws differs between the groups of a warp)
         const bool s2 = ws & 2u, s1 = ws & 1u;
         const uint32_t t0 = s2 ? A.z : A.x, t1 = s2 ? A.w : A.y, t2 = s2 ? B.x : A.z, t3 = s2 ? B.y : A.w, t4 = s2 ? B.z : B.x,
@@ -393,6 +401,11 @@ __device__ __forceinline__ uint32_t emit_group(const EmitArgs<OffT>& args, const
     }
 
     // read, "+", quality — each rstrip()ped (V2:246, 249)
+    if (mt.w & kMetaTail) {  // the source already reads  read "\n+\n" quality "\n"
+        const uint32_t tail_len = qual_rel + qual_len + 1u - seq_rel;
+        group_copy(s_out, d + o, args.r1buf, start + seq_rel, args.r1_len, tail_len, gl);
+        return o + tail_len;
+    }
     group_copy(s_out, d + o, args.r1buf, start + seq_rel, args.r1_len, seq_len, gl);
     o += seq_len;
     if (gl < 3) s_out[d + o + gl] = (uint8_t)"\n+\n"[gl];

@@ -50,6 +50,9 @@ constexpr unsigned long long kStatusValue = (1ull << 62) - 1;
 // next to it r1_base[r] = kept + seq_len + qual_len + 7: the bytes the record contributes to its output
 // record besides barcodes and UMI (header' _ bc _ umi \n seq \n+\n qual \n has 7 fixed bytes)
 constexpr uint32_t kMetaLong = 1u;
+// read 1 only: the bytes from the first base to the end of the record are exactly read "\n+\n" quality "\n"
+// (bare '+' line, nothing to strip), so the writer copies them in one piece
+constexpr uint32_t kMetaTail = 2u;
 
 
 template <typename OffT>
@@ -785,7 +788,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                     mt.x = cut | ((cut - spaces) << 16);
                     mt.y = (s1 - s0) | ((seq_e - s1) << 16);
                     mt.z = (s3 - s0) | ((qual_e - s3) << 16);
-                    mt.w = 0;
+                    mt.w = (seq_e == s2 - 1u && s3 - s2 == 2u && s_win[s2] == '+' && qual_e == s4 - 1u) ? kMetaTail : 0u;
                     args.r1_start[r] = (OffT)(tile_lo + s0);
                     args.r1_meta[r] = mt;
                     args.r1_base[r] = (cut - spaces) + (seq_e - s1) + (qual_e - s3) + 7u;

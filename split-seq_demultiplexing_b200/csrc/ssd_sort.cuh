@@ -112,18 +112,64 @@ __global__ void __launch_bounds__(kThreads) k_scan_apply(F f, uint64_t n, const 
     if (base <= n && n < base + kScanItems) out[n] = ex;  // items past n are zero, so this is the grand total
 }
 
+// Small inputs (the digit counts of a short sort): the whole exclusive scan in one block, one launch.
+constexpr int kSmallScanThreads = 1024;
+constexpr uint32_t kSmallScanMax = 1u << 16;
+__global__ void __launch_bounds__(kSmallScanThreads) k_scan_small_u32(const uint32_t* in, uint32_t n, uint32_t* out)
+{
+    __shared__ uint32_t s_warp[kSmallScanThreads / 32];
+    const uint32_t per = (n + kSmallScanThreads - 1) / kSmallScanThreads;
+    const uint32_t lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += in[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += u;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_warp[lane], w = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t u = __shfl_up_sync(0xFFFFFFFFu, w, d);
+            if (lane >= d) w += u;
+        }
+        s_warp[lane] = w - v;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + incl - sum;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t v = in[i];
+        out[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == kSmallScanThreads - 1) out[n] = run;
+}
+
 // ---------------------------------------------------------------------------------------------
-// LSD radix sort, 8-bit digits, stable.  Pass = per-block digit histogram -> scan -> ranked scatter.
+// LSD radix sort, kRadixBits-bit digits, stable.  Pass = per-block digit histogram -> scan -> ranked scatter.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSortItems = 16;
-constexpr int kSortBlock = kThreads * kSortItems;  // 4096 keys per block
+#ifndef SSD_RADIX_BITS
+#define SSD_RADIX_BITS 10
+#endif
+#ifndef SSD_SORT_ITEMS
+#define SSD_SORT_ITEMS 8
+#endif
+constexpr int kRadixBits = SSD_RADIX_BITS;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortItems = SSD_SORT_ITEMS;
+constexpr int kSortBlock = kThreads * kSortItems;  // keys per block
 
 template <typename K>
 __device__ __forceinline__ uint32_t digit_of(const K& k, int bit);
 template <>
 __device__ __forceinline__ uint32_t digit_of<uint64_t>(const uint64_t& k, int bit)
 {
-    return (uint32_t)(k >> bit) & 0xFFu;
+    return (uint32_t)(k >> bit) & (uint32_t)(kRadix - 1);
 }
 
 // Key sources of a sort pass: a plain array, or the annotation words (regular records only; the rest is skipped,
@@ -146,8 +192,8 @@ struct KeysFromAnn {
 template <class Src>
 __global__ void __launch_bounds__(kThreads) k_sort_hist(Src keys, uint64_t n, int bit, uint32_t* counts, uint32_t n_blocks)
 {
-    __shared__ uint32_t s_hist[256];
-    s_hist[threadIdx.x] = 0;
+    __shared__ uint32_t s_hist[kRadix];
+    for (int d = threadIdx.x; d < kRadix; d += kThreads) s_hist[d] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * kSortBlock;
 #pragma unroll
@@ -159,17 +205,17 @@ __global__ void __launch_bounds__(kThreads) k_sort_hist(Src keys, uint64_t n, in
         }
     }
     __syncthreads();
-    counts[(size_t)threadIdx.x * n_blocks + blockIdx.x] = s_hist[threadIdx.x];
+    for (int d = threadIdx.x; d < kRadix; d += kThreads) counts[(size_t)d * n_blocks + blockIdx.x] = s_hist[d];
 }
 
 template <class Src, typename K, bool HAS_VALS>
 __global__ void __launch_bounds__(kThreads) k_sort_scatter(Src keys_in, K* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
                                                            uint64_t n, int bit, const uint32_t* offsets, uint32_t n_blocks)
 {
-    __shared__ uint32_t s_wcount[kThreads / 32][257];
-    __shared__ uint32_t s_base[256];
+    __shared__ uint32_t s_wcount[kThreads / 32][kRadix + 1];
+    __shared__ uint32_t s_base[kRadix];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < (kThreads / 32) * 257; i += kThreads) (&s_wcount[0][0])[i] = 0;
+    for (int i = tid; i < (kThreads / 32) * (kRadix + 1); i += kThreads) (&s_wcount[0][0])[i] = 0;
     __syncthreads();
 
     // warp w owns keys [w*512, (w+1)*512) of the block; iteration i, lane l -> key w*512 + i*32 + l
@@ -187,7 +233,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(Src keys_in, K* keys_
             valid = key[i] != kNoKey;
             if (HAS_VALS) val[i] = vals_in[j];
         }
-        uint32_t d = valid ? digit_of(key[i], bit) : 256u;
+        uint32_t d = valid ? digit_of(key[i], bit) : (uint32_t)kRadix;
         uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
         uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
         uint32_t pre = 0;
@@ -200,22 +246,22 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(Src keys_in, K* keys_
         dig[i] = (uint16_t)d;
     }
     __syncthreads();
-    {
-        // exclusive scan over warps for digit `tid`, plus the global base of (digit, block)
+    for (int d = tid; d < kRadix; d += kThreads) {
+        // exclusive scan over warps for digit d, plus the global base of (digit, block)
         uint32_t acc = 0;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; w++) {
-            uint32_t c = s_wcount[w][tid];
-            s_wcount[w][tid] = acc;
+            uint32_t c = s_wcount[w][d];
+            s_wcount[w][d] = acc;
             acc += c;
         }
-        s_base[tid] = offsets[(size_t)tid * n_blocks + blockIdx.x];
+        s_base[d] = offsets[(size_t)d * n_blocks + blockIdx.x];
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) {
         uint32_t d = dig[i];
-        if (d < 256u) {
+        if (d < (uint32_t)kRadix) {
             uint64_t dst = (uint64_t)s_base[d] + s_wcount[warp][d] + rank[i];
             keys_out[dst] = key[i];
             if (HAS_VALS) vals_out[dst] = val[i];
