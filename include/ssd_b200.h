@@ -146,6 +146,14 @@ int ssd_filter_single(ssd_ctx *ctx, ssd_stats *stats);
  * (capacity `cap` bytes, 16-byte aligned).  *written receives stats.bytes_matched / bytes_passing. */
 int ssd_emit_device(ssd_ctx *ctx, int which, void *d_out, size_t cap, size_t *written);
 
+/* Split mode (BASELINE config 5; bucket model of demultiplex_using_barcodes.py:350-372, one buffer per cell): the
+ * SSD_EMIT_PASSING records of the batch grouped into per-cell buckets — cells in ascending id, records in input
+ * order inside a cell — written back to back into d_out.  The union of the buckets is the merged output. */
+int ssd_emit_split_device(ssd_ctx *ctx, void *d_out, size_t cap, size_t *written, uint64_t *n_buckets);
+/* Table of the last ssd_emit_split_device: per bucket its cell id ((i1*n + i2)*n + i3), first byte and first
+ * record position in d_out; arrays of `capacity` >= n_buckets entries on the host (any may be NULL). */
+int ssd_split_index(ssd_ctx *ctx, uint32_t *cells_host, uint64_t *offsets_host, uint64_t *first_host, uint64_t capacity);
+
 /* ---- host-buffer convenience (the end-to-end path) -------------------------------------------- */
 /* Whole pipeline on HOST buffers: chunked H2D into context-owned device staging, phases 1-3, D2H of
  * the selected output into `out` (capacity out_cap).  Pinned host memory makes the copies async. */

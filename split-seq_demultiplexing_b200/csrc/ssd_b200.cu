@@ -60,6 +60,8 @@ struct ssd_ctx {
     bool phase1_done = false, filter_done = false, unique_done = false;
     int planned = -1;  // which output b_out_off currently describes (-1 = none)
     bool annotated = false;  // the batch is an already annotated FASTQ (V2.calc_demux_results)
+    uint64_t n_buckets = 0;  // split mode: buckets of the last ssd_emit_split_device
+    uint64_t split_bytes = 0;
     uint64_t* uniq_keys = nullptr;
     uint64_t n_uniq = 0;
     IrrKey* uniq_irr = nullptr;
@@ -69,6 +71,7 @@ struct ssd_ctx {
     DevBuf b_status1, b_status2, b_r1_start, b_r1_meta, b_r1_base, b_r1_tok, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
         b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
     DevBuf b_in1, b_in2, b_out;
+    DevBuf b_sp_cells, b_sp_cells_alt, b_sp_recs, b_sp_recs_alt, b_sp_off, b_bk_cell, b_bk_off, b_bk_first;
     // the irregular-key path runs on its own stream with its own scratch, next to the regular sort
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -395,9 +398,11 @@ int launch_scans(ssd_ctx* c)
 }
 
 template <typename OffT>
-int launch_emit(ssd_ctx* c, int which, uint8_t* d_out)
+int launch_emit(ssd_ctx* c, int which, uint8_t* d_out, const uint32_t* order = nullptr, const unsigned long long* out_off = nullptr,
+                uint64_t n_positions = 0)
 {
     EmitArgs<OffT> a{};
+    a.order = order;
     a.r1buf = c->r1;
     a.r1_len = c->r1_len;
     a.r2buf = c->r2;
@@ -405,19 +410,20 @@ int launch_emit(ssd_ctx* c, int which, uint8_t* d_out)
     a.r1_start = (const OffT*)c->b_r1_start.p;
     a.r1_meta = (const uint4*)c->b_r1_meta.p;
     a.ann = (const uint64_t*)c->b_ann.p;
-    a.out_off = (const uint64_t*)c->b_out_off.p;
+    a.out_off = out_off ? (const uint64_t*)out_off : (const uint64_t*)c->b_out_off.p;
     a.remap = (which == SSD_EMIT_PASSING && c->cfg.collapse_pairs > 0) ? c->d_remap : nullptr;
     a.out = d_out;
-    a.n_rec = c->n_rec;
+    a.n_rec = order ? n_positions : c->n_rec;
     a.cnt = c->d_cnt;
     a.copy_mode = c->annotated ? 1 : 0;
     // records per block: the block's slice of the output must fit the staging buffer
     const uint64_t n_out = which == SSD_EMIT_MATCHED ? c->stats.n_matched : c->stats.n_retained;
     const uint64_t bytes = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
     const uint64_t avg_out = n_out ? bytes / n_out + 1 : 1;
-    const uint64_t rpb = (uint64_t)(kEmitOut * 7 / 8) / avg_out;
+    uint64_t rpb = (uint64_t)(kEmitOut * 7 / 8) / avg_out;
+    if (!order && n_out) rpb = rpb * c->n_rec / n_out;  // input-order blocks also walk over the records that are not written
     a.rpb = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rpb, 1), 256);
-    const uint32_t nb = blocks_for(c->n_rec, a.rpb);
+    const uint32_t nb = blocks_for(a.n_rec, a.rpb);
     StageTimer t(c, 5);
     if (nb) k_emit<OffT><<<nb, kThreads, 0, c->stream>>>(a, c->dcfg);
     c->n_launches += nb ? 1 : 0;
@@ -604,7 +610,8 @@ extern "C" void ssd_destroy(ssd_ctx* c)
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_r1_start, &c->b_r1_meta, &c->b_r1_base, &c->b_r1_tok, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
                       &c->b_irr_alt, &c->b_perm, &c->b_perm_alt, &c->b_tmp64a, &c->b_tmp64b, &c->b_counts, &c->b_offsets, &c->b_bsums,
-                      &c->b_pos, &c->b_out_off, &c->b_cells, &c->b_in1, &c->b_in2, &c->b_out};
+                      &c->b_pos, &c->b_out_off, &c->b_cells, &c->b_in1, &c->b_in2, &c->b_out, &c->b_sp_cells, &c->b_sp_cells_alt, &c->b_sp_recs,
+                      &c->b_sp_recs_alt, &c->b_sp_off, &c->b_bk_cell, &c->b_bk_off, &c->b_bk_first};
     for (DevBuf* b : bufs) release(*b);
     cudaFree(c->d_cnt);
     cudaFree(c->d_err_off);
@@ -863,6 +870,76 @@ extern "C" int ssd_emit_device(ssd_ctx* c, int which, void* d_out, size_t cap, s
     DevCounters h{};
     OKR(fetch_counters(c, &h));
     if (h.err_flags & kErrEmitLen) return fail(c, SSD_ECUDA, "internal: emitted record length differs from the planned length");
+    return SSD_OK;
+}
+
+// Split mode: the post-filter records grouped into per-cell buckets (cells ascending, input order inside a cell).
+extern "C" int ssd_emit_split_device(ssd_ctx* c, void* d_out, size_t cap, size_t* written, uint64_t* n_buckets)
+{
+    if (!c) return SSD_EINVAL;
+    if (!c->filter_done) return fail(c, SSD_ESTATE, "ssd_emit_split_device before ssd_build_filter");
+    CU(c, cudaSetDevice(c->device));
+    const uint64_t need = c->stats.bytes_passing, n = c->stats.n_retained;
+    if (written) *written = (size_t)need;
+    if (n_buckets) *n_buckets = 0;
+    c->n_buckets = 0;
+    c->split_bytes = need;
+    if (need > cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, cap);
+    if (n == 0) return SSD_OK;
+    if (!d_out) return fail(c, SSD_EINVAL, "null output pointer");
+    if (n >= (1ull << 32)) return fail(c, SSD_EINVAL, "split mode is limited to 2^32 records per batch");
+    OutLen f = make_outlen(c, SSD_EMIT_PASSING);
+    // 1. (cell, record) pairs of the written records, in input order
+    OKR(ensure(c, c->b_pos, (c->n_rec + 1) * sizeof(uint32_t)));
+    OKR(ensure(c, c->b_sp_cells, n * 8));
+    OKR(ensure(c, c->b_sp_cells_alt, n * 8));
+    OKR(ensure(c, c->b_sp_recs, n * 4));
+    OKR(ensure(c, c->b_sp_recs_alt, n * 4));
+    OKR(ensure(c, c->b_sp_off, (n + 1) * 8));
+    uint32_t* pos = (uint32_t*)c->b_pos.p;
+    OKR(exclusive_scan<uint32_t>(c, PassFlag{f}, c->n_rec, pos));
+    k_split_pairs<<<blocks_for(c->n_rec, kThreads), kThreads, 0, c->stream>>>(f, pos, c->n_rec, (uint64_t*)c->b_sp_cells.p, (uint32_t*)c->b_sp_recs.p);
+    // 2. stable sort by cell
+    uint64_t* cells = nullptr;
+    uint32_t* order = nullptr;
+    OKR(radix_sort64<true>(c, (uint64_t*)c->b_sp_cells.p, (uint64_t*)c->b_sp_cells_alt.p, (uint32_t*)c->b_sp_recs.p, (uint32_t*)c->b_sp_recs_alt.p, n,
+                           c->dcfg.cell_bits, &cells, &order));
+    // 3. byte offsets in bucket order, 4. the writer through the permutation
+    unsigned long long* off = (unsigned long long*)c->b_sp_off.p;
+    OKR(exclusive_scan<unsigned long long>(c, SplitLen{f, order}, n, off));
+    OKR(c->wide ? launch_emit<uint64_t>(c, SSD_EMIT_PASSING, (uint8_t*)d_out, order, off, n)
+                : launch_emit<uint32_t>(c, SSD_EMIT_PASSING, (uint8_t*)d_out, order, off, n));
+    // 5. bucket table
+    OKR(exclusive_scan<uint32_t>(c, BucketHead{cells}, n, pos));
+    uint32_t nb = 0;
+    CU(c, cudaMemcpyAsync(&nb, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    OKR(ensure(c, c->b_bk_cell, (size_t)nb * 4));
+    OKR(ensure(c, c->b_bk_off, (size_t)nb * 8));
+    OKR(ensure(c, c->b_bk_first, (size_t)nb * 8));
+    k_bucket_table<<<blocks_for(n, kThreads), kThreads, 0, c->stream>>>(cells, pos, off, n, (uint32_t*)c->b_bk_cell.p, (unsigned long long*)c->b_bk_off.p,
+                                                                       (unsigned long long*)c->b_bk_first.p);
+    c->n_launches += 3;
+    DevCounters h{};
+    OKR(fetch_counters(c, &h));
+    if (h.err_flags & kErrEmitLen) return fail(c, SSD_ECUDA, "internal: emitted record length differs from the planned length");
+    c->n_buckets = nb;
+    if (n_buckets) *n_buckets = nb;
+    return SSD_OK;
+}
+
+// Bucket table of the last ssd_emit_split_device: cell id, first byte and first record position of every bucket
+// (bucket b spans bytes [offsets[b], offsets[b+1]) and positions [first[b], first[b+1]); the last one ends at the totals).
+extern "C" int ssd_split_index(ssd_ctx* c, uint32_t* cells_host, uint64_t* offsets_host, uint64_t* first_host, uint64_t capacity)
+{
+    if (!c) return SSD_EINVAL;
+    if (capacity < c->n_buckets) return fail(c, SSD_ERANGE, "need room for %llu buckets", (unsigned long long)c->n_buckets);
+    if (!c->n_buckets) return SSD_OK;
+    CU(c, cudaSetDevice(c->device));
+    if (cells_host) CU(c, cudaMemcpyAsync(cells_host, c->b_bk_cell.p, c->n_buckets * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (offsets_host) CU(c, cudaMemcpyAsync(offsets_host, c->b_bk_off.p, c->n_buckets * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (first_host) CU(c, cudaMemcpyAsync(first_host, c->b_bk_first.p, c->n_buckets * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     return SSD_OK;
 }
 

@@ -143,6 +143,7 @@ struct EmitArgs {
     uint8_t* out;
     uint64_t n_rec;           // records of this batch (min of the two files)
     uint32_t rpb;             // records per block
+    const uint32_t* order;    // split mode: position k of the output holds record order[k] (NULL = input order)
     int copy_mode;            // annotated input: header, read, third line and quality are copied strip()ped (V2:435-447)
     DevCounters* cnt;
 };
@@ -434,9 +435,10 @@ __global__ void __launch_bounds__(kThreads) k_emit(const __grid_constant__ EmitA
     if (!staged) {
         // records too long for the staging buffer: one warp per record, global memory to global memory
         GlobAcc ga{args.r1buf, args.r1_len};
-        for (uint64_t r = r0 + warp; r < r1; r += kThreads / 32) {
-            uint64_t o0 = args.out_off[r], o1 = args.out_off[r + 1];
+        for (uint64_t k = r0 + warp; k < r1; k += kThreads / 32) {
+            uint64_t o0 = args.out_off[k], o1 = args.out_off[k + 1];
             if (o1 == o0) continue;
+            const uint64_t r = args.order ? args.order[k] : k;
             uint32_t wrote = emit_record_generic(ga, args, cfg, r, args.out + o0);
             if (lane == 0 && wrote != (uint32_t)(o1 - o0)) atomicOr(&args.cnt->err_flags, kErrEmitLen);
         }
@@ -445,9 +447,10 @@ __global__ void __launch_bounds__(kThreads) k_emit(const __grid_constant__ EmitA
 
     const int gl = lane & (kGroup - 1);
     const uint32_t gmask = 0xFFu << (lane & ~(kGroup - 1));
-    for (uint64_t r = r0 + (uint32_t)(tid / kGroup); r < r1; r += kThreads / kGroup) {
-        const uint64_t o0 = args.out_off[r], o1 = args.out_off[r + 1];
+    for (uint64_t k = r0 + (uint32_t)(tid / kGroup); k < r1; k += kThreads / kGroup) {
+        const uint64_t o0 = args.out_off[k], o1 = args.out_off[k + 1];
         if (o1 == o0) continue;
+        const uint64_t r = args.order ? args.order[k] : k;
         const uint32_t wrote = emit_group(args, cfg, r, s_out, out_skew + (uint32_t)(o0 - out_lo), gl, gmask);
         if (gl == 0 && wrote != (uint32_t)(o1 - o0)) atomicOr(&args.cnt->err_flags, kErrEmitLen);
     }
@@ -465,6 +468,50 @@ __global__ void __launch_bounds__(kThreads) k_emit(const __grid_constant__ EmitA
         for (uint32_t i = tid; i < body / 16u; i += kThreads) dst[i] = src[i];
     }
     for (uint32_t i = head + body + tid; i < nout; i += kThreads) gdst[i] = s_out[out_skew + i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// split mode: per-cell buckets (demultiplex_using_barcodes.py:350-372 keeps one buffer per cell)
+// ---------------------------------------------------------------------------------------------
+struct PassFlag {  // 1 for records that are written to the post-filter output
+    OutLen f;
+    __device__ __forceinline__ uint32_t operator()(uint64_t r) const { return f(r) ? 1u : 0u; }
+};
+
+// (cell, record) pairs of the written records, in input order: the input of a stable sort by cell
+__global__ void k_split_pairs(OutLen f, const uint32_t* pos, uint64_t n, uint64_t* cells, uint32_t* recs)
+{
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || !f(r)) return;
+    uint32_t cell = ann_cell(f.ann[r]);
+    if (f.remap) cell = f.remap[cell];
+    cells[pos[r]] = cell;
+    recs[pos[r]] = (uint32_t)r;
+}
+
+struct SplitLen {  // output length of the record at position k of the bucketed order
+    OutLen f;
+    const uint32_t* order;
+    __device__ __forceinline__ uint32_t operator()(uint64_t k) const { return f(order[k]); }
+};
+
+struct BucketHead {  // 1 where a new cell starts in the sorted (cell) array
+    const uint64_t* cells;
+    __device__ __forceinline__ uint32_t operator()(uint64_t k) const { return k == 0 || cells[k] != cells[k - 1] ? 1u : 0u; }
+};
+
+// bucket table: for every run of equal cells its cell id, first byte and first position
+__global__ void k_bucket_table(const uint64_t* cells, const uint32_t* bpos, const unsigned long long* out_off, uint64_t n, uint32_t* b_cell,
+                               unsigned long long* b_off, unsigned long long* b_first)
+{
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (k == 0 || cells[k] != cells[k - 1]) {
+        const uint32_t b = bpos[k];
+        b_cell[b] = (uint32_t)cells[k];
+        b_off[b] = out_off[k];
+        b_first[b] = k;
+    }
 }
 
 __global__ void k_record_cells(const uint64_t* ann, uint64_t n, int32_t* cells)

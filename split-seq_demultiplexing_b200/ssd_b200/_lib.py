@@ -95,6 +95,8 @@ _SIGS = {
     "ssd_build_filter": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "ssd_filter_single": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "ssd_emit_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ssd_emit_split_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
+    "ssd_split_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "ssd_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(Stats)]),
     "ssd_emit_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ssd_output_bound": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_size_t]),

@@ -153,6 +153,24 @@ class Demultiplexer:
         self._check(self.lib.ssd_emit_device(self._ctx, which, C.c_void_p(out_ptr), cap, C.byref(n)))
         return n.value
 
+    def emit_split_device(self, out_ptr: int, cap: int):
+        """Per-cell buckets of the post-filter records into the device buffer; returns (bytes, table) where table is
+        a list of (cell string, first byte, n records, n bytes)."""
+        import numpy as np
+        n, nb = C.c_size_t(), C.c_uint64()
+        self._check(self.lib.ssd_emit_split_device(self._ctx, C.c_void_p(out_ptr), cap, C.byref(n), C.byref(nb)))
+        cells = np.empty(nb.value, dtype=np.uint32)
+        offs = np.empty(nb.value, dtype=np.uint64)
+        first = np.empty(nb.value, dtype=np.uint64)
+        if nb.value:
+            self._check(self.lib.ssd_split_index(self._ctx, cells.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
+                                                 first.ctypes.data_as(C.c_void_p), nb.value))
+        table = []
+        for b in range(nb.value):
+            end_off = int(offs[b + 1]) if b + 1 < nb.value else n.value
+            table.append((self.cell_string(int(cells[b])), int(offs[b]), None, end_off - int(offs[b])))
+        return n.value, table, first
+
     def record_cells(self):
         import numpy as np
         n = C.c_uint64()

@@ -230,3 +230,63 @@ def test_long_reads_take_the_slow_path(ssd, orc):
     ref = orc.demultiplex(r1, r2, WL, 1, 1)
     dm, merged, passing, stats = run_both(ssd, r1, r2, 1, 1)
     assert merged == ref.merged1 and passing == ref.passing and stats["n_matched"] == 200
+
+
+@pytest.mark.parametrize("collapse", [0, 48])
+def test_split_mode_buckets(ssd, orc, collapse):
+    """Per-cell buckets (BASELINE config 5): union == merged output, every bucket holds one cell, input order inside."""
+    import torch
+    spec = ssd.synth_spec(WL, 50000, seed=21, cell_pool=400, p_n=0.01)
+    dm = ssd.Demultiplexer(WL, errors=1, min_count=10, collapse_pairs=collapse)
+    d1, d2 = ssd.synth_device(dm, spec)
+    merged, stats = dm.run_device(d1, d2, ssd.EMIT_PASSING)
+    merged = merged.cpu().numpy().tobytes()
+    out = torch.empty(stats["bytes_passing"] + 16, dtype=torch.uint8, device="cuda")
+    n, table, _ = dm.emit_split_device(out.data_ptr(), out.numel())
+    split = out[:n].cpu().numpy().tobytes()
+    assert n == len(merged) == stats["bytes_passing"]
+    by_cell = {}
+    for rec in fu.records(merged):
+        by_cell.setdefault(rec.split(b"\n", 1)[0].split(b"_")[1], []).append(rec)
+    assert [t[0].encode() for t in table] == [c for c in sorted(by_cell, key=lambda s: [WL.index(s[i:i + 8].decode()) for i in (0, 8, 16)])]
+    assert len(table) == stats["n_passing_cells"] or collapse
+    for cell, off, _, nbytes in table:
+        assert fu.records(split[off:off + nbytes]) == by_cell[cell.encode()]
+    if not collapse:
+        r1, r2 = d1.cpu().numpy().tobytes(), d2.cpu().numpy().tobytes()
+        assert merged == orc.demultiplex(r1, r2, WL, 1, 10).passing
+
+
+def test_wide_offsets_path(ssd, orc, monkeypatch):
+    """Files of 4 GiB and more use 64-bit record offsets; SSD_FORCE_WIDE exercises that instantiation on small inputs."""
+    monkeypatch.setenv("SSD_FORCE_WIDE", "1")
+    spec = ssd.synth_spec(WL, 20000, seed=31, cell_pool=300, p_n=0.01, p_trunc=0.01)
+    r1, r2 = ssd.synth_host(spec)
+    dm, merged, passing, stats = run_both(ssd, r1, r2, 1, 5)
+    ref = orc.demultiplex(r1, r2, WL, 1, 5)
+    assert merged == ref.merged1 and passing == ref.passing
+
+
+def test_config3_e2_ties_n_collapse(ssd, orc):
+    """BASELINE config 3 in small: e=2, N bases, planted 2/2 ties, truncated read 2, RanHex/OligoDT collapse on."""
+    spec = ssd.synth_spec(WL, 200000, seed=0x5EED0002, cell_pool=3000, p_n=0.01, p_tie=0.01, p_trunc=0.005)
+    r1, r2 = ssd.synth_host(spec)
+    ref = orc.demultiplex(r1, r2, WL, 2, 10)
+    dm, merged, passing, stats = run_both(ssd, r1, r2, 2, 10)
+    assert merged == ref.merged1 and passing == ref.passing
+    assert dm.record_cells().tolist() == ref.rec_cell
+    # collapse on: same records, RanHex cells renamed when their OligoDT partner also passes
+    dm2, merged2, passing2, stats2 = run_both(ssd, r1, r2, 2, 10, collapse_pairs=48)
+    assert merged2 == ref.merged1 and len(passing2) == len(ref.passing)
+    assert stats2["n_retained"] == ref.n_retained
+    n = len(WL)
+    idx = {w: i for i, w in enumerate(WL)}
+    present = bytearray(n * n * n)
+    for c, v in ref.cells.items():
+        if v[2]:
+            s = c.decode()
+            present[(idx[s[0:8]] * n + idx[s[8:16]]) * n + idx[s[16:24]]] = 1
+    remap = orc.collapse_map(bytes(present), n, 48)
+    renamed = sum(1 for i, r in enumerate(remap) if r != i)
+    cells_after = {rec.split(b"\n", 1)[0].split(b"_")[1] for rec in fu.records(passing2)}
+    assert len(cells_after) == ref.n_passing_cells - renamed
