@@ -22,6 +22,9 @@ namespace ssd {
 #ifndef SSD_SCAN_TILE
 #define SSD_SCAN_TILE 24576
 #endif
+#ifndef SSD_SCAN_MINBLOCKS
+#define SSD_SCAN_MINBLOCKS 2
+#endif
 #ifndef SSD_SCAN_SLOTS
 #define SSD_SCAN_SLOTS 3
 #endif
@@ -413,6 +416,8 @@ constexpr int kScanAnn = 2;  // an already annotated FASTQ (MergedCells_1.fastq)
 
 constexpr int kComputeWarps = 8;
 constexpr int kComputeThreads = kComputeWarps * 32;
+constexpr int kAWarps = 4, kBWarps = kComputeWarps - kAWarps;  // warps 0-3: stage A (bitmap, count, list); warps 4-7: stage B (records)
+constexpr int kAThreads = kAWarps * 32, kBThreads = kBWarps * 32;
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 constexpr int kScanThreads = kComputeThreads + 64;  // eight compute warps + the copy warp + the prefix warp (works in block 0)
 
@@ -426,23 +431,25 @@ struct __align__(128) ScanSmem {
     uint8_t win[kWinSlots][kWin + 128];       // tile windows (bulk-copy destinations)
     uint16_t lstart[kListSlots][kMaxLines];   // line-start lists of the tiles between stage A and stage B
     unsigned long long full[kWinSlots], empty[kWinSlots];  // mbarriers: bytes landed / window may be refilled
+    unsigned long long list_full[kListSlots], list_empty[kListSlots];  // mbarriers: stage A done with a tile / stage B done with it
     unsigned long long line_base;
     uint32_t tile[kWinSlots];
-    uint32_t total[kListSlots], n_listed[kListSlots];
-    uint32_t warp_tile[kComputeWarps], halo_sum[2];
-    uint32_t mask[kWinWords];                 // newline bitmap of the tile in stage A (bit b of word w = byte 32 w + b)
+    uint32_t total[kListSlots], n_listed[kListSlots], list_tile[kListSlots];
+    uint32_t warp_tile[kAWarps], halo_sum[2];
+    alignas(16) uint32_t mask[kWinWords];     // newline bitmap of the tile in stage A (bit b of word w = byte 32 w + b)
 };
 
 #ifdef SSD_SCAN_PROFILE
 __device__ unsigned long long g_scan_prof[2][8];
 #define PROF_T(var) const long long var = clock64()
-#define PROF_ADD(slot, a, b) if (tid == 0) prof[slot] += (unsigned long long)((b) - (a))
+#define PROF_ADD(slot, a, b) if ((threadIdx.x & (kAThreads - 1)) == 0) prof[slot] += (unsigned long long)((b) - (a))
 #else
 #define PROF_T(var)
 #define PROF_ADD(slot, a, b)
 #endif
 
-__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
+__device__ __forceinline__ void sync_a() { asm volatile("bar.sync 1, %0;" ::"n"(kAThreads) : "memory"); }
+__device__ __forceinline__ void sync_b() { asm volatile("bar.sync 2, %0;" ::"n"(kBThreads) : "memory"); }
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {
@@ -456,7 +463,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 //   compute warps stage A(i + kDepth): newline bitmap (kept in registers), count (published), line-start list
 //                 stage B(i)         : poll the line index, process the records that start in the tile
 template <int MODE, typename OffT>
-__global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant__ ScanArgs<OffT> args, const __grid_constant__ DevCfg cfg)
+__global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const __grid_constant__ ScanArgs<OffT> args, const __grid_constant__ DevCfg cfg)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ScanSmem& S = *reinterpret_cast<ScanSmem*>(smem_raw);
@@ -465,6 +472,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
         for (int s = 0; s < kWinSlots; s++) {
             mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), 1);
             mbar_init(reinterpret_cast<uint64_t*>(&S.empty[s]), 1);
+        }
+        for (int s = 0; s < kListSlots; s++) {
+            mbar_init(reinterpret_cast<uint64_t*>(&S.list_full[s]), 1);
+            mbar_init(reinterpret_cast<uint64_t*>(&S.list_empty[s]), 1);
         }
     }
     __syncthreads();
@@ -523,9 +534,15 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
         for (uint32_t it = 0;; it++) {
             const uint32_t ws = it % kWinSlots;
             if (it >= (uint32_t)kWinSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.empty[ws]), ((it / kWinSlots) - 1u) & 1u);
+#ifdef SSD_SCAN_TICKETS
             uint32_t t = 0;
-            if (lane == 0) t = atomicAdd(&args.cnt->ticket[MODE == kScanR2 ? 1 : 0], 1u);  // tiles are claimed in order: nobody waits on an unclaimed tile
+            if (lane == 0) t = atomicAdd(&args.cnt->ticket[MODE == kScanR2 ? 1 : 0], 1u);  // tiles are claimed in order
             t = __shfl_sync(0xFFFFFFFFu, t, 0);
+#else
+            // round robin: block b owns tiles b, b + G, b + 2G, ...  All blocks of the (single-wave) grid are resident, and the
+            // tiles whose counts a tile's line index depends on belong to the same or earlier rounds of the other blocks.
+            const uint32_t t = it * gridDim.x + blockIdx.x;
+#endif
             if (t >= args.n_tiles) {
                 if (lane == 0) {
                     S.tile[ws] = kNoTile;
@@ -558,34 +575,42 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
 #endif
     const uint64_t n_rec_r1 = MODE == kScanR2 ? args.cnt->n_records[0] : 0;  // read 1 was scanned by the previous launch
 
-    // stage A: newline bitmap, count, line-start list of the block's it-th tile; false when the tiles are exhausted
+    // stage A (warps 0-3): newline bitmap, count, line-start list of the block's it-th tile; false when the tiles are exhausted
     auto stage_a = [&](uint32_t it) -> bool {
         const uint32_t ws = it % kWinSlots, ls = it % kListSlots;
+        if (it >= (uint32_t)kListSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.list_empty[ls]), ((it / kListSlots) - 1u) & 1u);
         PROF_T(t0);
         mbar_wait(reinterpret_cast<uint64_t*>(&S.full[ws]), (it / kWinSlots) & 1u);
         PROF_T(t1);
         PROF_ADD(0, t0, t1);
         const uint32_t tile = S.tile[ws];
-        if (tile == kNoTile) return false;
+        if (tile == kNoTile) {
+            if (tid == 0) {
+                S.list_tile[ls] = kNoTile;
+                mbar_arrive(&S.list_full[ls]);
+            }
+            return false;
+        }
         const size_t tile_lo = (size_t)tile * kTile;
         const uint32_t win_bytes = (uint32_t)(args.len - tile_lo < (size_t)kWin ? args.len - tile_lo : (size_t)kWin);
         const uint8_t* s_win = S.win[ws];
         uint32_t* s_mask = S.mask;
         uint16_t* s_lstart = S.lstart[ls];
-        build_nl_mask<kComputeThreads, (kWinWords * 2 + kComputeThreads - 1) / kComputeThreads>(s_win, win_bytes, reinterpret_cast<uint16_t*>(s_mask),
-                                                                                                 kWinWords * 2);
-        compute_sync();
+        build_nl_mask<kAThreads, (kWinWords * 2 + kAThreads - 1) / kAThreads>(s_win, win_bytes, reinterpret_cast<uint16_t*>(s_mask), kWinWords * 2);
+        sync_a();
         PROF_T(t2);
         PROF_ADD(1, t1, t2);
         // newlines owned by this tile: mask words [0, kTileWords), WPT consecutive ones per thread; halo words: 1 per thread of warps 0-1
-        constexpr int WPT = kTileWords / kComputeThreads;  // 2, 3 or 4 mask words per thread (16 / 24 / 32 KiB tiles)
-        static_assert(WPT >= 2 && WPT <= 4 && WPT * kComputeThreads == kTileWords, "tile size");
+        constexpr int WPT = kTileWords / kAThreads;  // 4, 6 or 8 mask words per thread (16 / 24 / 32 KiB tiles)
+        static_assert(WPT >= 2 && WPT <= 8 && WPT % 2 == 0 && WPT * kAThreads == kTileWords, "tile size");
         static_assert(kHaloWords <= 64, "halo size");
-        uint32_t m[4] = {0u, 0u, 0u, 0u}, cnt = 0;
+        unsigned long long q[WPT / 2];
+        uint32_t cnt = 0;
 #pragma unroll
-        for (int w = 0; w < WPT; w++) {
-            m[w] = s_mask[WPT * tid + w];
-            cnt += __popc(m[w]);
+        for (int w = 0; w < WPT / 2; w++) {
+            const uint2 v = *reinterpret_cast<const uint2*>(&s_mask[WPT * tid + 2 * w]);
+            q[w] = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+            cnt += (uint32_t)__popcll(q[w]);
         }
         const uint32_t hm = tid < kHaloWords ? s_mask[kTileWords + tid] : 0u;
         uint32_t incl = cnt, hincl = __popc(hm);
@@ -602,10 +627,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
             S.warp_tile[warp] = incl;
             if (warp < 2) S.halo_sum[warp] = hincl;
         }
-        compute_sync();
+        sync_a();
         uint32_t warp_base = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < kComputeWarps; w++) {
+        for (int w = 0; w < kAWarps; w++) {
             uint32_t v = S.warp_tile[w];
             if (w < warp) warp_base += v;
             total += v;
@@ -616,25 +641,29 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
         if (tid == 0) {
             S.total[ls] = total;
             S.n_listed[ls] = total + halo_total;
+            S.list_tile[ls] = tile;
             st[tile] = kFlagAgg | total;  // published: the prefix warp takes it from here
             s_lstart[0] = 0;
         }
         // line-start list: s_lstart[1 + k] = byte after the k-th newline of the window (tile first, then halo);
         // one newline per iteration for every lane that still has one: warp-uniform trip count
         {
-            unsigned long long lo = (unsigned long long)m[0] | ((unsigned long long)m[1] << 32);
-            unsigned long long hi = (unsigned long long)m[2] | ((unsigned long long)m[3] << 32);
             const uint32_t trip_nl = __reduce_max_sync(0xFFFFFFFFu, cnt);
+            uint32_t cur = 0;  // 64-bit word being drained
             for (uint32_t k = 0; k < trip_nl; k++) {
                 if (k < cnt) {
-                    uint32_t b;
-                    if (lo) {
-                        b = (uint32_t)__ffsll((long long)lo) - 1u;
-                        lo &= lo - 1ull;
-                    } else {
-                        b = 64u + (uint32_t)__ffsll((long long)hi) - 1u;
-                        hi &= hi - 1ull;
-                    }
+#pragma unroll
+                    for (int w = 0; w < WPT / 2 - 1; w++)
+                        if (cur == (uint32_t)w && q[w] == 0ull) cur = w + 1;
+                    unsigned long long v = q[0];
+#pragma unroll
+                    for (int w = 1; w < WPT / 2; w++)
+                        if (cur == (uint32_t)w) v = q[w];
+                    const uint32_t b = 64u * cur + (uint32_t)__ffsll((long long)v) - 1u;
+                    v &= v - 1ull;
+#pragma unroll
+                    for (int w = 0; w < WPT / 2; w++)
+                        if (cur == (uint32_t)w) q[w] = v;
                     const uint32_t idx = excl + k + 1u;
                     if (idx < (uint32_t)kMaxLines) s_lstart[idx] = (uint16_t)(tid * (32 * WPT) + b + 1);
                 }
@@ -647,16 +676,20 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                 hrank++;
             }
         }
-        compute_sync();  // list complete; warp_tile / halo_sum / mask may be reused
+        sync_a();  // list complete; warp_tile / halo_sum / mask may be reused
+        if (tid == 0) mbar_arrive(&S.list_full[ls]);  // hand the tile to stage B
         PROF_T(t3);
         PROF_ADD(2, t2, t3);
         return true;
     };
 
     // stage B: the records that start in the block's it-th tile
-    auto stage_b = [&](uint32_t it) {
+    const int tb = tid - kAThreads, wb = warp - kAWarps;  // thread / warp index inside the stage-B group
+    auto stage_b = [&](uint32_t it) -> bool {
         const uint32_t ws = it % kWinSlots, ls = it % kListSlots;
-        const uint32_t tile = S.tile[ws];
+        mbar_wait(reinterpret_cast<uint64_t*>(&S.list_full[ls]), (it / kListSlots) & 1u);
+        const uint32_t tile = S.list_tile[ls];
+        if (tile == kNoTile) return false;
         const size_t tile_lo = (size_t)tile * kTile;
         const uint32_t win_bytes = (uint32_t)(args.len - tile_lo < (size_t)kWin ? args.len - tile_lo : (size_t)kWin);
         const uint8_t* s_win = S.win[ws];
@@ -664,7 +697,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
         const uint32_t total = S.total[ls];
         const uint32_t n_listed = S.n_listed[ls];
         PROF_T(t4);
-        if (tid == 0) {
+        if (tb == 0) {
             // the inclusive newline prefix of this tile, written by the prefix warp
             unsigned long long v;
             uint32_t ns = 20;
@@ -680,7 +713,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                 args.cnt->n_records[MODE == kScanR2 ? 1 : 0] = n_lines >> 2;
             }
         }
-        compute_sync();
+        sync_b();
         PROF_T(t5);
         PROF_ADD(3, t4, t5);
         const unsigned long long line_base = S.line_base;
@@ -691,17 +724,17 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
         uint32_t n_rec = r_end > r_first ? (uint32_t)(r_end - r_first) : 0u;
         if (tile == 0 && args.len == 0) n_rec = 0;
         if (n_rec > (uint32_t)kMaxRecTile || n_listed + 1u > (uint32_t)kMaxLines) {
-            if (tid == 0) atomicOr(&args.cnt->err_flags, kErrDense);
+            if (tb == 0) atomicOr(&args.cnt->err_flags, kErrDense);
             n_rec = 0;
         }
         const uint32_t j_first = (uint32_t)(4ull * r_first - line_base);  // list index of the first record's start
         const uint32_t* words = reinterpret_cast<const uint32_t*>(s_win);
         GlobAcc ga{args.buf, args.len};
 
-        for (uint32_t base = 0; base < n_rec; base += kComputeThreads) {
+        for (uint32_t base = 0; base < n_rec; base += kBThreads) {
             // read 2 (global-memory latency in the chain): record i of the batch goes to warp i % 8, lane i / 8, so every warp
             // gets its share and the stage ends sooner; read 1 keeps records packed into as few warps as possible
-            const uint32_t i = MODE == kScanR2 ? base + (uint32_t)lane * kComputeWarps + (uint32_t)warp : base + (uint32_t)tid;
+            const uint32_t i = MODE == kScanR2 ? base + (uint32_t)lane * kBWarps + (uint32_t)wb : base + (uint32_t)tb;
             const bool have = i < n_rec;
             const uint64_t r = r_first + i;
             const uint32_t j0 = j_first + 4u * i;
@@ -937,30 +970,26 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                 if (lane == 0 && nirr) atomicAdd(&args.cnt->n_irr, (unsigned long long)nirr);  // their keys are collected by k_collect_irr
             }
         }
-        compute_sync();
+        sync_b();
         PROF_T(t6);
         PROF_ADD(4, t5, t6);
-        if (tid == 0) mbar_arrive(&S.empty[ws]);  // the window may be refilled
+        if (tb == 0) {
+            mbar_arrive(&S.empty[ws]);       // the window may be refilled
+            mbar_arrive(&S.list_empty[ls]);  // and so may the list slot
+        }
+        return true;
     };
 
     uint32_t n_a = 0;
-    bool more = true;
-    for (int pre = 0; pre < kDepth && more; pre++) {
-        more = stage_a(n_a);
-        if (more) n_a++;
-    }
-    for (uint32_t it = 0;; it++) {
-        if (more) {
-            more = stage_a(n_a);
-            if (more) n_a++;
-        }
-        if (it >= n_a) break;
-        stage_b(it);
+    if (warp < kAWarps) {
+        while (stage_a(n_a)) n_a++;
+    } else {
+        while (stage_b(n_a)) n_a++;
     }
 #ifdef SSD_SCAN_PROFILE
-    if (tid == 0) {
+    if (tid == 0 || tb == 0) {
         for (int k = 0; k < 5; k++) atomicAdd(&g_scan_prof[MODE == kScanR2 ? 1 : 0][k], prof[k]);
-        atomicAdd(&g_scan_prof[MODE == kScanR2 ? 1 : 0][7], (unsigned long long)n_a);
+        if (tid == 0) atomicAdd(&g_scan_prof[MODE == kScanR2 ? 1 : 0][7], (unsigned long long)n_a);
     }
 #endif
 }
