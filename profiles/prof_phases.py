@@ -7,12 +7,12 @@ spec=ssd_b200.synth_spec(wl, 10_000_000)
 d1,d2=ssd_b200.synth_device(dm, spec)
 for i in range(3):
     dm.demux_device(d1.data_ptr(), d1.numel(), d2.data_ptr(), d2.numel())
-buf=(C.c_ulonglong*16)()
+buf=(C.c_ulonglong*32)()
 dm.lib.ssd_debug_scan_profile.argtypes=[C.c_void_p, C.c_int]
 dm.lib.ssd_debug_scan_profile(buf, 1)
 dm.demux_device(d1.data_ptr(), d1.numel(), d2.data_ptr(), d2.numel())
 dm.lib.ssd_debug_scan_profile(buf, 0)
-names=['wait_full','mask','count+list','poll_prefix','records']
+names={0:'A.wait_full',1:'A.mask',2:'A.count+list',9:'A.wait_list_empty',5:'B.wait_list',6:'B.compute',3:'B.poll+sync',8:'B.poll_only',4:'B.commit'}
 for m in (0,1):
-    n=buf[m*8+7]
-    print('R%d tiles=%d'%(m+1,n), {names[k]: round(buf[m*8+k]/max(n,1)) for k in range(5)}, 'cycles/tile total', round(sum(buf[m*8+k] for k in range(5))/max(n,1)))
+    n=buf[m*16+7]
+    print('R%d tiles=%d'%(m+1,n), {v: round(buf[m*16+k]/max(n,1)) for k,v in names.items()})

@@ -45,6 +45,7 @@ struct ssd_ctx {
     unsigned long long* d_err_off = nullptr;
     uint8_t* d_lut = nullptr;
     uint8_t* d_wl_len = nullptr;
+    unsigned long long* d_wl64 = nullptr;  // whitelist entries as 8-byte words (tiled writer)
     uint32_t* d_hist = nullptr;
     uint32_t* d_distinct = nullptr;
     uint32_t* d_remap = nullptr;
@@ -423,9 +424,20 @@ int launch_emit(ssd_ctx* c, int which, uint8_t* d_out, const uint32_t* order = n
     uint64_t rpb = (uint64_t)(kEmitOut * 7 / 8) / avg_out;
     if (!order && n_out) rpb = rpb * c->n_rec / n_out;  // input-order blocks also walk over the records that are not written
     a.rpb = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rpb, 1), 256);
+    // input order, plain records, 8-byte whitelist entries: the tiled writer (bulk copies in and out, shared-to-shared assembly)
+    const bool tiled = !order && !a.copy_mode && c->dcfg.bc8 && c->n_rec && !getenv("SSD_EMIT_GROUPS");
+    if (tiled) {
+        const uint64_t avg_in = c->r1_len / c->n_rec + 1, avg_out_in = bytes / c->n_rec + 1;  // per input record
+        const uint64_t rin = (uint64_t)(kTIn * 7 / 8) / avg_in, rout = (uint64_t)(kTOut * 7 / 8) / avg_out_in;
+        a.rpb = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(std::min(rin, rout), 1), kTR);
+        a.wl64 = c->d_wl64;
+        a.cps = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((avg_out > 40 ? avg_out - 40 : 0) / 16, 1), 64);
+        a.cps_magic = ((1u << 20) + a.cps - 1) / a.cps;
+    }
     const uint32_t nb = blocks_for(a.n_rec, a.rpb);
     StageTimer t(c, 5);
-    if (nb) k_emit<OffT><<<nb, kThreads, 0, c->stream>>>(a, c->dcfg);
+    if (nb && tiled) k_emit_tiled<OffT><<<nb, kThreads, sizeof(TileSmem), c->stream>>>(a, c->dcfg);
+    else if (nb) k_emit<OffT><<<nb, kThreads, 0, c->stream>>>(a, c->dcfg);
     c->n_launches += nb ? 1 : 0;
     CU(c, cudaGetLastError());
     return SSD_OK;
@@ -579,6 +591,8 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
         CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
         CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
         CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_emit_tiled<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+        CUB_(cudaFuncSetAttribute(k_emit_tiled<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
         int per_sm = 0;
         CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<kScanR2, uint32_t>, kScanThreads, sizeof(ScanSmem)));
         c->scan_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
@@ -587,11 +601,13 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
     CUB_(cudaMalloc(&c->d_err_off, 2 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_lut, (size_t)(d.e + 1) * 65536u));
     CUB_(cudaMalloc(&c->d_wl_len, kMaxWl));
+    CUB_(cudaMalloc(&c->d_wl64, kMaxWl * 8));
     CUB_(cudaMalloc(&c->d_hist, c->n_cells_total * sizeof(uint32_t)));
     CUB_(cudaMalloc(&c->d_distinct, c->n_cells_total * sizeof(uint32_t)));
     CUB_(cudaMalloc(&c->d_remap, c->n_cells_total * sizeof(uint32_t)));
     CUB_(cudaMalloc(&c->d_pass, c->n_cells_total));
     CUB_(cudaMemcpyAsync(c->d_wl_len, d.wl_len, kMaxWl, cudaMemcpyHostToDevice, c->stream));
+    CUB_(cudaMemcpyAsync(c->d_wl64, d.wl, kMaxWl * 8, cudaMemcpyHostToDevice, c->stream));
     CUB_(cudaMemsetAsync(c->d_hist, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
     CUB_(cudaMemsetAsync(c->d_distinct, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
     CUB_(cudaMemsetAsync(c->d_pass, 0, c->n_cells_total, c->stream));
@@ -617,6 +633,7 @@ extern "C" void ssd_destroy(ssd_ctx* c)
     cudaFree(c->d_err_off);
     cudaFree(c->d_lut);
     cudaFree(c->d_wl_len);
+    cudaFree(c->d_wl64);
     cudaFree(c->d_hist);
     cudaFree(c->d_distinct);
     cudaFree(c->d_remap);
@@ -1205,9 +1222,9 @@ extern "C" uint64_t ssd_launch_count(const ssd_ctx* c) { return c ? c->n_launche
 // debug builds only: per-phase clock totals of the scan kernels (phases 0..4, tiles in [7]) for read 1 / read 2
 extern "C" int ssd_debug_scan_profile(unsigned long long* out16, int reset)
 {
-    if (out16 && cudaMemcpyFromSymbol(out16, ssd::g_scan_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return SSD_ECUDA;
+    if (out16 && cudaMemcpyFromSymbol(out16, ssd::g_scan_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return SSD_ECUDA;
     if (reset) {
-        unsigned long long z[16] = {0};
+        unsigned long long z[32] = {0};
         if (cudaMemcpyToSymbol(ssd::g_scan_prof, z, sizeof z) != cudaSuccess) return SSD_ECUDA;
     }
     return SSD_OK;

@@ -146,6 +146,8 @@ struct EmitArgs {
     const uint32_t* order;    // split mode: position k of the output holds record order[k] (NULL = input order)
     int copy_mode;            // annotated input: header, read, third line and quality are copied strip()ped (V2:435-447)
     DevCounters* cnt;
+    const unsigned long long* wl64;  // tiled writer: the whitelist entries as 8-byte words
+    uint32_t cps, cps_magic;         // tiled writer: 16-byte chunk slots per record, ceil(2^20 / cps)
 };
 
 // One warp writes one output record (V2:134-141).  `dst` is a generic pointer (shared staging buffer or

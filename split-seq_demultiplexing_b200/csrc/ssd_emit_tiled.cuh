@@ -1,0 +1,293 @@
+// ssd_emit_tiled.cuh — the writer for the common case (input order, whitelist entries 8 bytes long), sm_100a.
+//
+// A block owns up to kTR consecutive records.  Their read-1 bytes are one contiguous range of the input and their
+// output is one contiguous range of the result, so both sides move with bulk copies (TMA): global -> shared for the
+// input range, shared -> global for the finished output slice.  In between the records are assembled shared -> shared:
+//   * one thread per record describes it (where its header, literal and read/quality bytes go),
+//   * one thread per record squeezes the header (name.split("/")[0].replace(" ", "").strip(), V2:135-138) and copies
+//     the few bytes of the long segments that do not fill a 16-byte output chunk,
+//   * one thread per record writes "_" barcode1 barcode2 barcode3 "_" umi "\n" (V2:139-141),
+//   * every thread copies whole 16-byte output chunks of the long segments: two aligned 16-byte shared loads,
+//     funnel-shifted into one aligned 16-byte shared store.
+// About 30 warp instructions per record (the eight-lanes-per-record writer in ssd_emit.cuh needs ~150).
+// Blocks that do not fit the staging buffers (very long records) take the exact one-warp-per-record path.
+#pragma once
+#include "ssd_emit.cuh"
+
+namespace ssd {
+
+constexpr int kTR = 64;            // records per block, at most
+constexpr int kTIn = 24 * 1024;    // staged read-1 bytes per block
+constexpr int kTOut = 26 * 1024;   // staged output bytes per block
+constexpr int kTPad = 16;          // bytes in front of the staged input (16-byte loads may start before the first record)
+
+struct __align__(128) TileSmem {
+    uint8_t in[kTPad + kTIn + 48];
+    uint8_t out[kTOut + 32];
+    unsigned long long ann[kTR];   // annotation of the record, 0 = not written
+    uint2 seg[2][kTR];             // long segments {dst | src << 16, length}: read (+ "+" + quality when adjacent), quality
+    uint2 head[kTR];               // {dst | src << 16, cut length | literal dst << 16}
+    unsigned long long bar;        // mbarrier of the input copy
+    unsigned long long g0, g1;     // file range of the block's records
+    uint32_t fits, flags, next[2];
+};
+
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// [b0, b1): the part of the file range [g0, g1) between 16-byte aligned addresses; false when there is none
+__device__ __forceinline__ bool tile_bulk_range(const uint8_t* buf, uint64_t g0, uint64_t g1, uint64_t& b0, uint64_t& b1)
+{
+    const uintptr_t a0 = (uintptr_t)(buf + g0), a1 = (uintptr_t)(buf + g1);
+    const uintptr_t ab0 = (a0 + 15u) & ~(uintptr_t)15, ab1 = a1 & ~(uintptr_t)15;
+    b0 = g0 + (uint64_t)(ab0 - a0);
+    b1 = ab1 > ab0 ? g1 - (uint64_t)(a1 - ab1) : b0;
+    return ab1 > ab0;
+}
+
+// the bytes of a long segment that do not fill a 16-byte output chunk: up to 15 in front, up to 15 behind
+__device__ __forceinline__ void tile_edges(TileSmem& S, uint2 sg)
+{
+    const uint32_t dst = sg.x & 0xFFFFu, src = sg.x >> 16, len = sg.y;
+    uint32_t nh = (16u - (dst & 15u)) & 15u;
+    nh = nh < len ? nh : len;
+    for (uint32_t i = 0; i < nh; i++) S.out[dst + i] = S.in[src + i];
+    const uint32_t e = dst + len;
+    uint32_t t0 = e & ~15u;
+    t0 = t0 > dst + nh ? t0 : dst + nh;
+    for (uint32_t p = t0; p < e; p++) S.out[p] = S.in[src + (p - dst)];
+}
+
+// whole 16-byte output chunks j, j + stride, ... of a long segment
+__device__ __forceinline__ void tile_chunks(TileSmem& S, uint2 sg, uint32_t j, uint32_t stride)
+{
+    const uint32_t dst = sg.x & 0xFFFFu, src = sg.x >> 16, len = sg.y;
+    const uint32_t first = (dst + 15u) & ~15u, last = (dst + len) & ~15u;
+    if (last <= first) return;
+    const uint32_t nfull = (last - first) >> 4;
+    const uint32_t sa0 = src + (first - dst);      // source of the first whole chunk
+    const uint32_t ws = (sa0 & 15u) >> 2, bs = (sa0 & 3u) * 8u;
+    const bool s2 = ws & 2u, s1 = ws & 1u;
+    const uint4* in16 = reinterpret_cast<const uint4*>(S.in + (sa0 & ~15u));
+    uint4* out16 = reinterpret_cast<uint4*>(S.out + first);
+    for (uint32_t c = j; c < nfull; c += stride) {
+        const uint4 A = in16[c], B = in16[c + 1];
+        const uint32_t t0 = s2 ? A.z : A.x, t1 = s2 ? A.w : A.y, t2 = s2 ? B.x : A.z, t3 = s2 ? B.y : A.w, t4 = s2 ? B.z : B.x,
+                       t5 = s2 ? B.w : B.y;
+        const uint32_t w0 = s1 ? t1 : t0, w1 = s1 ? t2 : t1, w2 = s1 ? t3 : t2, w3 = s1 ? t4 : t3, w4 = s1 ? t5 : t4;
+        out16[c] = make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
+    }
+}
+
+// records [r0, r1) one warp each, global memory to global memory (exact, any record)
+template <typename OffT>
+__device__ __noinline__ void emit_block_generic(const EmitArgs<OffT>& args, const DevCfg& cfg, uint64_t r0, uint64_t r1)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    GlobAcc ga{args.r1buf, args.r1_len};
+    for (uint64_t k = r0 + warp; k < r1; k += kThreads / 32) {
+        const uint64_t o0 = args.out_off[k], o1 = args.out_off[k + 1];
+        if (o1 == o0) continue;
+        const uint64_t r = args.order ? args.order[k] : k;
+        const uint32_t wrote = emit_record_generic(ga, args, cfg, r, args.out + o0);
+        if (lane == 0 && wrote != (uint32_t)(o1 - o0)) atomicOr(&args.cnt->err_flags, kErrEmitLen);
+    }
+}
+
+template <typename OffT>
+__global__ void __launch_bounds__(kThreads) k_emit_tiled(const __grid_constant__ EmitArgs<OffT> args, const __grid_constant__ DevCfg cfg)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t r0 = (uint64_t)blockIdx.x * args.rpb;
+    if (r0 >= args.n_rec) return;
+    const uint64_t r1 = r0 + args.rpb < args.n_rec ? r0 + args.rpb : args.n_rec;
+    const uint64_t out_lo = args.out_off[r0], out_hi = args.out_off[r1];
+    if (out_hi == out_lo) return;  // nothing of this block survives the filter: no loads at all
+    const uint32_t nrec = (uint32_t)(r1 - r0);
+    const uint32_t out_skew = (uint32_t)(((uintptr_t)args.out + out_lo) & 15u);
+
+    // ---- the block's input range; its 16-byte aligned middle arrives by bulk copy ----
+    if (tid == 0) {
+        const uint64_t g0 = (uint64_t)args.r1_start[r0];
+        const uint4 ml = args.r1_meta[r1 - 1];
+        uint64_t g1 = (uint64_t)args.r1_start[r1 - 1] + (ml.z & 0xFFFFu) + (ml.z >> 16) + 1u;  // behind the last quality line
+        g1 = g1 < (uint64_t)args.r1_len ? g1 : (uint64_t)args.r1_len;
+        const uint32_t mis = (uint32_t)((uintptr_t)(args.r1buf + g0) & 15u);
+        const bool fits = nrec <= (uint32_t)kTR && g1 > g0 && g1 - g0 + mis <= (uint64_t)kTIn && out_hi - out_lo + out_skew <= (uint64_t)kTOut;
+        S.g0 = g0;
+        S.g1 = g1;
+        S.fits = fits ? 1u : 0u;
+        S.flags = 0;
+        S.next[0] = S.next[1] = 0;
+        mbar_init(reinterpret_cast<uint64_t*>(&S.bar), 1);
+        if (fits) {
+            uint64_t b0, b1;
+            if (tile_bulk_range(args.r1buf, g0, g1, b0, b1)) {
+                mbar_expect_tx(reinterpret_cast<uint64_t*>(&S.bar), (uint32_t)(b1 - b0));
+                bulk_g2s(&S.in[kTPad + mis + (uint32_t)(b0 - g0)], args.r1buf + b0, (uint32_t)(b1 - b0), reinterpret_cast<uint64_t*>(&S.bar));
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&S.bar)) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    if (!S.fits) {
+        emit_block_generic(args, cfg, r0, r1);
+        return;
+    }
+    const uint64_t g0 = S.g0, g1 = S.g1;
+    const uint32_t mis = (uint32_t)((uintptr_t)(args.r1buf + g0) & 15u);
+    const uint32_t in0 = (uint32_t)kTPad + mis;  // S.in[in0 + (x - g0)] holds file byte x
+    if (tid < 32) {
+        // the unaligned ends of the range (the whole range when it has no aligned middle)
+        uint64_t b0, b1;
+        if (tile_bulk_range(args.r1buf, g0, g1, b0, b1)) {
+            if (tid < 16) {
+                const uint64_t x = g0 + (uint32_t)tid;
+                if (x < b0) S.in[in0 + (uint32_t)tid] = args.r1buf[x];
+            } else {
+                const uint64_t x = b1 + (uint32_t)(tid - 16);
+                if (x < g1) S.in[in0 + (uint32_t)(x - g0)] = args.r1buf[x];
+            }
+        } else {
+            const uint64_t x = g0 + (uint32_t)tid;
+            if (x < g1) S.in[in0 + (uint32_t)tid] = args.r1buf[x];
+        }
+    }
+
+    // ---- one thread per record: where its pieces go ----
+    if ((uint32_t)tid < nrec) {
+        const uint64_t r = r0 + (uint32_t)tid;
+        const uint64_t o0 = args.out_off[r], o1 = args.out_off[r + 1];
+        uint2 sa = make_uint2(0u, 0u), sb = make_uint2(0u, 0u), hd = make_uint2(0u, 0u);
+        unsigned long long an = 0;
+        if (o1 != o0) {
+            const uint64_t start = (uint64_t)args.r1_start[r];
+            const uint4 mt = args.r1_meta[r];
+            an = args.ann[r];
+            const uint32_t cut = mt.x & 0xFFFFu, kept = mt.x >> 16, seq_rel = mt.y & 0xFFFFu, seq_len = mt.y >> 16, qual_rel = mt.z & 0xFFFFu,
+                           qual_len = mt.z >> 16;
+            const uint32_t lit = 27u + ann_umi_len(an, cfg.umi_len);
+            if ((mt.w & kMetaLong) || start < g0 || start + qual_rel + qual_len + ((mt.w & kMetaTail) ? 1u : 0u) > g1) {
+                atomicOr(&S.flags, 1u);  // the whole block goes the exact way
+                an = 0;
+            } else if (kept + lit + seq_len + qual_len + 4u != (uint32_t)(o1 - o0)) {
+                atomicOr(&args.cnt->err_flags, kErrEmitLen);
+                an = 0;
+            } else {
+                const uint32_t d = out_skew + (uint32_t)(o0 - out_lo), src0 = in0 + (uint32_t)(start - g0), dA = d + kept + lit;
+                hd = make_uint2(d | (src0 << 16), cut | ((d + kept) << 16));
+                if (mt.w & kMetaTail) {  // the source already reads  read "\n+\n" quality "\n"
+                    sa = make_uint2(dA | ((src0 + seq_rel) << 16), qual_rel + qual_len + 1u - seq_rel);
+                } else {
+                    sa = make_uint2(dA | ((src0 + seq_rel) << 16), seq_len);
+                    uint8_t* q = S.out + dA + seq_len;
+                    q[0] = '\n';
+                    q[1] = '+';
+                    q[2] = '\n';
+                    sb = make_uint2((dA + seq_len + 3u) | ((src0 + qual_rel) << 16), qual_len);
+                    q[3u + qual_len] = '\n';
+                    atomicOr(&S.flags, 2u);
+                }
+            }
+        }
+        S.seg[0][tid] = sa;
+        S.seg[1][tid] = sb;
+        S.head[tid] = hd;
+        S.ann[tid] = an;
+    }
+    __syncthreads();
+    mbar_wait(reinterpret_cast<uint64_t*>(&S.bar), 0);
+    const uint32_t flags = S.flags;
+    if (flags & 1u) {
+        emit_block_generic(args, cfg, r0, r1);
+        return;
+    }
+
+    if (warp < 2) {
+        // ---- header without its blanks, and the ragged ends of the long segments ----
+        const uint32_t k = (uint32_t)tid;
+        if (k < nrec && S.ann[k] != 0ull) {
+            const uint2 hd = S.head[k];
+            const uint32_t d = hd.x & 0xFFFFu, src0 = hd.x >> 16, cut = hd.y & 0xFFFFu;
+            uint32_t o = d;
+            for (uint32_t i = 0; i < cut; i++) {
+                const uint8_t ch = S.in[src0 + i];
+                if (ch != ' ') S.out[o++] = ch;
+            }
+            tile_edges(S, S.seg[0][k]);
+            if (flags & 2u) tile_edges(S, S.seg[1][k]);
+        }
+    } else if (warp < 4) {
+        // ---- '_' + barcode1 + barcode2 + barcode3 + '_' + umi + '\n' ----
+        const uint32_t k = (uint32_t)tid - 64u;
+        const unsigned long long an = k < nrec ? S.ann[k] : 0ull;
+        if (an != 0ull) {
+            uint8_t* q = S.out + (S.head[k].y >> 16);
+            uint32_t cell = ann_cell(an);
+            if (args.remap) cell = args.remap[cell];
+            uint32_t i1, i2, i3;
+            cell_indices(cfg, cell, i1, i2, i3);
+            const unsigned long long b1 = __ldg(args.wl64 + i1), b2 = __ldg(args.wl64 + i2), b3 = __ldg(args.wl64 + i3);
+            q[0] = '_';
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                q[1 + j] = (uint8_t)(b1 >> (8 * j));
+                q[9 + j] = (uint8_t)(b2 >> (8 * j));
+                q[17 + j] = (uint8_t)(b3 >> (8 * j));
+            }
+            q[25] = '_';
+            const uint64_t payload = ann_payload(an);
+            uint32_t ulen;
+            if (ann_state(an) == 1u) {
+                ulen = (uint32_t)cfg.umi_len;
+#pragma unroll
+                for (int j = 0; j < 10; j++)
+                    if ((uint32_t)j < ulen) q[26 + j] = (uint8_t)__byte_perm(0x47544341u, 0u, (uint32_t)(payload >> (2 * j)) & 3u);
+            } else {
+                ulen = (uint32_t)(payload & 31u);
+                const uint8_t* u = args.r2buf + (size_t)(payload >> 5);
+                for (uint32_t j = 0; j < ulen; j++) q[26u + j] = u[j];
+            }
+            q[26u + ulen] = '\n';
+        }
+    }
+
+    // ---- whole 16-byte chunks of the long segments: cps slots per record, a warp takes 32 slots at a time ----
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1 && !(flags & 2u)) break;
+        const uint32_t n_items = nrec * args.cps;
+        for (;;) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&S.next[pass], 32u);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base >= n_items) break;
+            const uint32_t i = base + (uint32_t)lane;
+            const uint32_t k = (uint32_t)(((unsigned long long)i * args.cps_magic) >> 20), j = i - k * args.cps;
+            if (k < nrec) tile_chunks(S, S.seg[pass][k], j, args.cps);
+        }
+    }
+
+    // ---- the finished slice leaves with one bulk copy; shared and global addresses agree modulo 16 ----
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const uint32_t nout = (uint32_t)(out_hi - out_lo);
+    uint8_t* gdst = args.out + out_lo;
+    const uint32_t head = out_skew ? (16u - out_skew < nout ? 16u - out_skew : nout) : 0u;
+    const uint32_t body = (nout - head) & ~15u;
+    if (tid == 0 && body) bulk_s2g(gdst + head, S.out + out_skew + head, body);
+    if ((uint32_t)tid < head) gdst[tid] = S.out[out_skew + tid];
+    if (tid >= 32 && tid < 48) {
+        const uint32_t i = head + body + (uint32_t)(tid - 32);
+        if (i < nout) gdst[i] = S.out[out_skew + i];
+    }
+    if (tid == 0 && body) bulk_wait_read();
+}
+
+}  // namespace ssd

@@ -4,3 +4,4 @@
 #include "ssd_sort.cuh"
 #include "ssd_scan.cuh"
 #include "ssd_emit.cuh"
+#include "ssd_emit_tiled.cuh"

@@ -439,8 +439,13 @@ struct __align__(128) ScanSmem {
     alignas(16) uint32_t mask[kWinWords];     // newline bitmap of the tile in stage A (bit b of word w = byte 32 w + b)
 };
 
+// which scans run the per-record work ahead of the line index (read 2 is issue-bound: nothing to hide there)
+#ifndef SSD_SCAN_SPECULATE
+#define SSD_SCAN_SPECULATE(mode) ((mode) != kScanR2)
+#endif
+
 #ifdef SSD_SCAN_PROFILE
-__device__ unsigned long long g_scan_prof[2][8];
+__device__ unsigned long long g_scan_prof[2][16];
 #define PROF_T(var) const long long var = clock64()
 #define PROF_ADD(slot, a, b) if ((threadIdx.x & (kAThreads - 1)) == 0) prof[slot] += (unsigned long long)((b) - (a))
 #else
@@ -571,15 +576,17 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
 
     // ================================ compute warps ================================
 #ifdef SSD_SCAN_PROFILE
-    unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     const uint64_t n_rec_r1 = MODE == kScanR2 ? args.cnt->n_records[0] : 0;  // read 1 was scanned by the previous launch
 
     // stage A (warps 0-3): newline bitmap, count, line-start list of the block's it-th tile; false when the tiles are exhausted
     auto stage_a = [&](uint32_t it) -> bool {
         const uint32_t ws = it % kWinSlots, ls = it % kListSlots;
+        PROF_T(t9);
         if (it >= (uint32_t)kListSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.list_empty[ls]), ((it / kListSlots) - 1u) & 1u);
         PROF_T(t0);
+        PROF_ADD(9, t9, t0);
         mbar_wait(reinterpret_cast<uint64_t*>(&S.full[ws]), (it / kWinSlots) & 1u);
         PROF_T(t1);
         PROF_ADD(0, t0, t1);
@@ -685,9 +692,20 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
 
     // stage B: the records that start in the block's it-th tile
     const int tb = tid - kAThreads, wb = warp - kAWarps;  // thread / warp index inside the stage-B group
+    // read 2: the mate check still in flight (fingerprint of read 1 requested, not yet compared)
+    bool pend = false;
+    unsigned long long pend_fp1 = 0, pend_fp = 0;
+    size_t pend_off = 0;
+    auto settle = [&]() {
+        if (pend && pend_fp1 != pend_fp) raise(args.cnt, args.err_off, 1, kErrKey, pend_off);
+        pend = false;
+    };
     auto stage_b = [&](uint32_t it) -> bool {
         const uint32_t ws = it % kWinSlots, ls = it % kListSlots;
+        PROF_T(t7);
         mbar_wait(reinterpret_cast<uint64_t*>(&S.list_full[ls]), (it / kListSlots) & 1u);
+        PROF_T(t8);
+        PROF_ADD(5, t7, t8);
         const uint32_t tile = S.list_tile[ls];
         if (tile == kNoTile) return false;
         const size_t tile_lo = (size_t)tile * kTile;
@@ -696,49 +714,29 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         const uint16_t* s_lstart = S.lstart[ls];
         const uint32_t total = S.total[ls];
         const uint32_t n_listed = S.n_listed[ls];
-        PROF_T(t4);
-        if (tb == 0) {
-            // the inclusive newline prefix of this tile, written by the prefix warp
-            unsigned long long v;
-            uint32_t ns = 20;
-            while (((v = st[tile]) >> 62) != 2ull) {
-                __nanosleep(ns);
-                if (ns < 200u) ns += ns;
-            }
-            const unsigned long long excl_lines = (v & kStatusValue) - total;
-            S.line_base = excl_lines;
-            if (tile == args.n_tiles - 1) {
-                unsigned long long n_lines = excl_lines + total + ((args.len && s_win[win_bytes - 1] != '\n') ? 1ull : 0ull);
-                args.cnt->n_lines[MODE == kScanR2 ? 1 : 0] = n_lines;
-                args.cnt->n_records[MODE == kScanR2 ? 1 : 0] = n_lines >> 2;
-            }
-        }
-        sync_b();
-        PROF_T(t5);
-        PROF_ADD(3, t4, t5);
-        const unsigned long long line_base = S.line_base;
-
-        // records that start in this tile: the line after a newline whose next-line index is 0 mod 4
-        const unsigned long long r_first = tile == 0 ? 0ull : (line_base + 4) >> 2;
-        const unsigned long long r_end = ((line_base + total) >> 2) + 1;  // exclusive
-        uint32_t n_rec = r_end > r_first ? (uint32_t)(r_end - r_first) : 0u;
-        if (tile == 0 && args.len == 0) n_rec = 0;
-        if (n_rec > (uint32_t)kMaxRecTile || n_listed + 1u > (uint32_t)kMaxLines) {
-            if (tb == 0) atomicOr(&args.cnt->err_flags, kErrDense);
-            n_rec = 0;
-        }
-        const uint32_t j_first = (uint32_t)(4ull * r_first - line_base);  // list index of the first record's start
         const uint32_t* words = reinterpret_cast<const uint32_t*>(s_win);
         GlobAcc ga{args.buf, args.len};
 
-        for (uint32_t base = 0; base < n_rec; base += kBThreads) {
-            // read 2 (global-memory latency in the chain): record i of the batch goes to warp i % 8, lane i / 8, so every warp
-            // gets its share and the stage ends sooner; read 1 keeps records packed into as few warps as possible
-            const uint32_t i = MODE == kScanR2 ? base + (uint32_t)lane * kBWarps + (uint32_t)wb : base + (uint32_t)tb;
-            const bool have = i < n_rec;
-            const uint64_t r = r_first + i;
+        // ---- per-record work, split in two: compute() needs only the tile (which list entries start records is all it takes
+        //      from the global line index), commit() needs the record number.  When the phase can be guessed from the
+        //      tile, compute() runs before the line index has arrived and hides the wait for it. ----
+        bool have = false, ok = false, complete = false, noat = false, matched = false;
+        uint32_t s0 = 0, base_len = 0, err_code = 0;
+        uint4 mt = make_uint4(0, 0, 0, 0);
+        unsigned long long fp = 0;
+        uint64_t an = 0;
+        R2Out o;
+        o.ann = 0;
+
+        auto compute = [&](uint32_t i, uint32_t j_first, uint32_t n_rec) {
+            have = i < n_rec;
+            ok = complete = noat = matched = false;
+            err_code = 0;
+            an = 0;
+            o.ann = 0;
             const uint32_t j0 = j_first + 4u * i;
-            uint32_t s0 = 0, s1 = 1, s2 = 1, s3 = 1, s4 = 1;
+            uint32_t s1 = 1, s2 = 1, s3 = 1, s4 = 1;
+            s0 = 0;
             bool fast = false;
             if (have) {
                 s0 = s_lstart[j0];
@@ -748,7 +746,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                     s3 = s_lstart[j0 + 3];
                     if (MODE != kScanR2) s4 = s_lstart[j0 + 4];
                     // read 2 only needs line 3 to exist; the generic path raises the overflow flag
-                    fast = (MODE != kScanR2 || tile_lo + s3 < args.len) && r < args.rec_cap;
+                    fast = MODE != kScanR2 || tile_lo + s3 < args.len;
                 }
             }
             // header bytes [s0, s0 + hdr_len), one trailing '\r' dropped; token = bytes before the first byte <= 0x20
@@ -809,38 +807,30 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                     }
                 }
             }
-            const unsigned long long fp = tok_hash_finish(h, tok_len);
+            fp = tok_hash_finish(h, tok_len);
 
             if (MODE == kScanR1) {
                 uint32_t seq_e = s2 - 1u, qual_e = s4 - 1u;
-                bool ok = fast && bad == 0u;
+                ok = fast && bad == 0u;
                 if (ok) ok = rstrip2(s_win, s1, seq_e) && rstrip2(s_win, s3, qual_e);
                 if (ok) {
-                    if (s_win[s0] != '@') raise(args.cnt, args.err_off, 0, kErrNoAt, tile_lo + s0);
-                    uint4 mt;
+                    noat = s_win[s0] != '@';
                     mt.x = cut | ((cut - spaces) << 16);
                     mt.y = (s1 - s0) | ((seq_e - s1) << 16);
                     mt.z = (s3 - s0) | ((qual_e - s3) << 16);
                     mt.w = (seq_e == s2 - 1u && s3 - s2 == 2u && s_win[s2] == '+' && qual_e == s4 - 1u) ? kMetaTail : 0u;
-                    args.r1_start[r] = (OffT)(tile_lo + s0);
-                    args.r1_meta[r] = mt;
-                    args.r1_base[r] = (cut - spaces) + (seq_e - s1) + (qual_e - s3) + 7u;
-                    args.r1_tok[r] = fp;
+                    base_len = (cut - spaces) + (seq_e - s1) + (qual_e - s3) + 7u;
                 }
-                __syncwarp();
-                if (have && !ok) r1_record_generic(ga, args, r, tile_lo + s0);
-                __syncwarp();
             } else if (MODE == kScanAnn) {
                 // ---- an annotated record: header = id _ cell _ umi [_ ...] (V2:395-398); every line is copied strip()ped ----
                 uint32_t seq_e = s2 - 1u, plus_e = s3 - 1u, qual_e = s4 - 1u;
-                bool ok = fast && bad == 0u && cfg.fast_wl != 0 && cfg.bc8 != 0 && hdr_len != 0u && !py_space(s_win[s0]);
+                ok = fast && bad == 0u && cfg.fast_wl != 0 && cfg.bc8 != 0 && hdr_len != 0u && !py_space(s_win[s0]);
                 if (ok) ok = rstrip2(s_win, s1, seq_e) && rstrip2(s_win, s2, plus_e) && rstrip2(s_win, s3, qual_e);
                 // leading blanks of the other lines would have to be stripped too: exact path
                 if (ok) ok = !(seq_e > s1 && py_space(s_win[s1])) && !(plus_e > s2 && py_space(s_win[s2])) && !(qual_e > s3 && py_space(s_win[s3]));
-                uint64_t an = 0;
                 if (ok) {
                     if (us2 == 0xFFFFu) {
-                        raise(args.cnt, args.err_off, 0, kErrIndex, tile_lo + s0);
+                        err_code = kErrIndex;
                     } else {
                         const uint32_t cell_s = us1 + 1u, cell_n = us2 - us1 - 1u;
                         const uint32_t umi_s = us2 + 1u, ulen = (us3 == 0xFFFFu ? hdr_len : us3) - umi_s;
@@ -858,7 +848,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                             }
                         }
                         if (idx[0] < 0 || idx[1] < 0 || idx[2] < 0 || ulen > 10u) {
-                            raise(args.cnt, args.err_off, 0, kErrForeign, tile_lo + s0);
+                            err_code = kErrForeign;
                         } else {
                             const uint32_t cell = (uint32_t)((idx[0] * cfg.n_wl + idx[1]) * cfg.n_wl + idx[2]);
                             const uint32_t up = s0 + umi_s;
@@ -878,40 +868,21 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                                 an = kAnnIrregular | ((uint64_t)cell << kAnnCellShift) | ((uint64_t)(tile_lo + up) << 5) | (uint64_t)ulen;
                         }
                     }
-                    uint4 mt;
                     mt.x = hdr_len | (hdr_len << 16);
                     mt.y = (s1 - s0) | ((seq_e - s1) << 16);
                     mt.z = (s3 - s0) | ((qual_e - s3) << 16);
                     mt.w = ((plus_e - s2) << 1) | ((s2 - s0) << 16);
-                    args.r1_start[r] = (OffT)(tile_lo + s0);
-                    args.r1_meta[r] = mt;
-                    args.r1_base[r] = hdr_len + (seq_e - s1) + (plus_e - s2) + (qual_e - s3) + 4u;
-                    args.ann[r] = an;
+                    base_len = hdr_len + (seq_e - s1) + (plus_e - s2) + (qual_e - s3) + 4u;
                 }
-                __syncwarp();
-                if (have && !ok) an = ann_record_generic(ga, args, cfg, r, tile_lo + s0);
-                __syncwarp();
-                const uint32_t st8 = ann_state(an);
-                if (st8) atomicAdd(&args.hist[ann_cell(an)], 1u);
-                const uint32_t nreg = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 1u)), nirr = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 2u));
-                if (lane == 0 && nreg) atomicAdd(&args.cnt->n_keys, (unsigned long long)nreg);
-                if (lane == 0 && nirr) atomicAdd(&args.cnt->n_irr, (unsigned long long)nirr);
             } else {
-                // the fingerprint read 1 left for this record: requested now, needed after the matching
-                unsigned long long fp1 = 0;
-                const bool have_mate = fast && r < n_rec_r1;
-                if (have_mate) fp1 = args.r1_tok[r];
                 // ---- lineRead = line.rstrip(); the four windows (V2:293-301) ----
                 uint32_t seq_e = s2 - 1u;
-                bool ok = fast && bad == 0u && cfg.fast_wl != 0 && cfg.fast_geom != 0;
+                ok = fast && bad == 0u && cfg.fast_wl != 0 && cfg.fast_geom != 0;
                 if (ok) ok = rstrip2(s_win, s1, seq_e);
                 if (ok) ok = seq_e - s1 >= (uint32_t)cfg.need_len;  // truncated read 2 goes the exact way
-                R2Out o;
-                o.ann = 0;
-                bool complete = false;
                 if (ok) {
                     complete = true;
-                    if (s_win[s0] != '@') raise(args.cnt, args.err_off, 1, kErrNoAt, tile_lo + s0);
+                    noat = s_win[s0] != '@';
                     // the three windows are packed first so that their LUT lookups are in flight together
                     uint32_t x0, x1, da0, da1, db0, db1, dc0, dc1;
                     load8(words, s1 + (uint32_t)cfg.b1s, x0, x1);
@@ -928,11 +899,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                         if (db0 | db1) i2 = match8(cfg, args.lut, code2, db0, db1);
                         if (dc0 | dc1) i3 = match8(cfg, args.lut, code3, dc0, dc1);
                     }
-                    bool matched = i1 >= 0 && i2 >= 0 && i3 >= 0;  // V2:310-321: all three lists non-empty
-                    if (matched && !(have_mate && fp1 == fp)) {    // V2:349-350: no read-1 mate with this id
-                        raise(args.cnt, args.err_off, 1, kErrKey, tile_lo + s0);
-                        matched = false;
-                    }
+                    matched = i1 >= 0 && i2 >= 0 && i3 >= 0;  // V2:310-321: all three lists non-empty (the mate check follows in commit())
                     if (matched) {
                         const uint32_t cell = (uint32_t)((i1 * cfg.n_wl + i2) * cfg.n_wl + i3);
                         // UMI = lineRead[umi_start:umi_end] verbatim (V2:295)
@@ -957,17 +924,140 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                         }
                     }
                 }
+            }
+        };
+
+        auto commit = [&](uint64_t r) {
+            const bool ok2 = ok && r < args.rec_cap;  // beyond the capacity: the exact path raises the overflow flag
+            if (MODE == kScanR2) settle();
+            if (MODE == kScanR1) {
+                if (ok2) {
+                    if (noat) raise(args.cnt, args.err_off, 0, kErrNoAt, tile_lo + s0);
+                    args.r1_start[r] = (OffT)(tile_lo + s0);
+                    args.r1_meta[r] = mt;
+                    args.r1_base[r] = base_len;
+                    args.r1_tok[r] = fp;
+                }
                 __syncwarp();
-                if (have && !ok) r2_record_generic(ga, args, cfg, r, tile_lo + s0, o, complete, n_rec_r1);
+                if (have && !ok2) r1_record_generic(ga, args, r, tile_lo + s0);
+                __syncwarp();
+            } else if (MODE == kScanAnn) {
+                if (ok2) {
+                    if (err_code) raise(args.cnt, args.err_off, 0, err_code, tile_lo + s0);
+                    args.r1_start[r] = (OffT)(tile_lo + s0);
+                    args.r1_meta[r] = mt;
+                    args.r1_base[r] = base_len;
+                    args.ann[r] = an;
+                } else {
+                    an = 0;
+                }
+                __syncwarp();
+                if (have && !ok2) an = ann_record_generic(ga, args, cfg, r, tile_lo + s0);
+                __syncwarp();
+                const uint32_t st8 = ann_state(an);
+                if (st8) atomicAdd(&args.hist[ann_cell(an)], 1u);
+                const uint32_t nreg = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 1u)), nirr = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 2u));
+                if (lane == 0 && nreg) atomicAdd(&args.cnt->n_keys, (unsigned long long)nreg);
+                if (lane == 0 && nirr) atomicAdd(&args.cnt->n_irr, (unsigned long long)nirr);
+            } else {
+                if (ok2) {
+                    if (noat) raise(args.cnt, args.err_off, 1, kErrNoAt, tile_lo + s0);
+                    if (matched) {
+                        // V2:349-350: the read-1 mate must carry the same id (fingerprint compare).  A mismatch fails the whole
+                        // call, so nothing below waits for the fingerprint: it is requested here and compared one tile later.
+                        if (r + 1u <= n_rec_r1) {
+                            pend_fp1 = args.r1_tok[r];
+                            pend_fp = fp;
+                            pend_off = tile_lo + s0;
+                            pend = true;
+                        } else {
+                            raise(args.cnt, args.err_off, 1, kErrKey, tile_lo + s0);
+                        }
+                    }
+                } else {
+                    o.ann = 0;
+                    complete = false;
+                }
+                __syncwarp();
+                if (have && !ok2) r2_record_generic(ga, args, cfg, r, tile_lo + s0, o, complete, n_rec_r1);
                 __syncwarp();
                 // ---- results: annotation, histogram, key counts; the regular (cell, UMI) key is the annotation itself
-                //      (the sort reads it from there), irregular keys are rare and appended one by one ----
+                //      (the sort reads it from there), irregular keys are collected afterwards by k_collect_irr ----
                 if (complete) args.ann[r] = o.ann;
                 const uint32_t st8 = ann_state(o.ann);
                 if (st8) atomicAdd(&args.hist[ann_cell(o.ann)], 1u);
                 const uint32_t nreg = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 1u)), nirr = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 2u));
                 if (lane == 0 && nreg) atomicAdd(&args.cnt->n_keys, (unsigned long long)nreg);
-                if (lane == 0 && nirr) atomicAdd(&args.cnt->n_irr, (unsigned long long)nirr);  // their keys are collected by k_collect_irr
+                if (lane == 0 && nirr) atomicAdd(&args.cnt->n_irr, (unsigned long long)nirr);
+            }
+        };
+
+        // read 2 (global-memory latency in the chain): record i of a batch goes to warp i % 4, lane i / 4, so every warp gets its
+        // share and the stage ends sooner; read 1 keeps records packed into as few warps as possible
+        const uint32_t my_i = MODE == kScanR2 ? (uint32_t)lane * kBWarps + (uint32_t)wb : (uint32_t)tb;
+
+        // ---- the guess: a record starts at the first line (of the four candidates) that begins with '@' and whose second
+        //      next line begins with '+'.  A wrong guess costs a second pass, never a wrong result. ----
+        uint32_t j_guess = 0xFFFFFFFFu, n_guess = 0;
+        if (n_listed + 1u <= (uint32_t)kMaxLines) {
+            if (tile == 0) {
+                j_guess = 0;
+                n_guess = args.len ? (total >> 2) + 1u : 0u;
+            } else {
+                for (uint32_t j = 1; j <= 4u && j <= total && j + 2u <= n_listed; j++) {
+                    if (s_win[s_lstart[j]] == '@' && s_win[s_lstart[j + 2u]] == '+') {
+                        j_guess = j;
+                        n_guess = ((total - j) >> 2) + 1u;
+                        break;
+                    }
+                }
+            }
+        }
+        const bool speculate = SSD_SCAN_SPECULATE(MODE) && j_guess != 0xFFFFFFFFu && n_guess != 0u && n_guess <= (uint32_t)kBThreads;
+        if (speculate) compute(my_i, j_guess, n_guess);
+
+        PROF_T(t4);
+        PROF_ADD(6, t8, t4);
+        if (tb == 0) {
+            // the inclusive newline prefix of this tile, written by the prefix warp
+            unsigned long long v;
+            uint32_t ns = 20;
+            while (((v = st[tile]) >> 62) != 2ull) {
+                __nanosleep(ns);
+                if (ns < 200u) ns += ns;
+            }
+            PROF_T(t10);
+            PROF_ADD(8, t4, t10);
+            const unsigned long long excl_lines = (v & kStatusValue) - total;
+            S.line_base = excl_lines;
+            if (tile == args.n_tiles - 1) {
+                unsigned long long n_lines = excl_lines + total + ((args.len && s_win[win_bytes - 1] != '\n') ? 1ull : 0ull);
+                args.cnt->n_lines[MODE == kScanR2 ? 1 : 0] = n_lines;
+                args.cnt->n_records[MODE == kScanR2 ? 1 : 0] = n_lines >> 2;
+            }
+        }
+        sync_b();
+        PROF_T(t5);
+        PROF_ADD(3, t4, t5);
+        const unsigned long long line_base = S.line_base;
+
+        // records that start in this tile: the line after a newline whose next-line index is 0 mod 4
+        const unsigned long long r_first = tile == 0 ? 0ull : (line_base + 4) >> 2;
+        const unsigned long long r_end = ((line_base + total) >> 2) + 1;  // exclusive
+        uint32_t n_rec = r_end > r_first ? (uint32_t)(r_end - r_first) : 0u;
+        if (tile == 0 && args.len == 0) n_rec = 0;
+        if (n_rec > (uint32_t)kMaxRecTile || n_listed + 1u > (uint32_t)kMaxLines) {
+            if (tb == 0) atomicOr(&args.cnt->err_flags, kErrDense);
+            n_rec = 0;
+        }
+        const uint32_t j_first = (uint32_t)(4ull * r_first - line_base);  // list index of the first record's start
+
+        if (speculate && j_first == j_guess && n_rec == n_guess) {
+            commit(r_first + my_i);
+        } else {
+            for (uint32_t base = 0; base < n_rec; base += kBThreads) {
+                compute(base + my_i, j_first, n_rec);
+                commit(r_first + base + my_i);
             }
         }
         sync_b();
@@ -985,10 +1075,12 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         while (stage_a(n_a)) n_a++;
     } else {
         while (stage_b(n_a)) n_a++;
+        if (MODE == kScanR2) settle();
     }
 #ifdef SSD_SCAN_PROFILE
     if (tid == 0 || tb == 0) {
-        for (int k = 0; k < 5; k++) atomicAdd(&g_scan_prof[MODE == kScanR2 ? 1 : 0][k], prof[k]);
+        for (int k = 0; k < 16; k++)
+            if (k != 7) atomicAdd(&g_scan_prof[MODE == kScanR2 ? 1 : 0][k], prof[k]);
         if (tid == 0) atomicAdd(&g_scan_prof[MODE == kScanR2 ? 1 : 0][7], (unsigned long long)n_a);
     }
 #endif
