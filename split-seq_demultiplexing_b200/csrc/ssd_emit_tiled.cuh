@@ -26,10 +26,11 @@ struct __align__(128) TileSmem {
     uint8_t out[kTOut + 32];
     unsigned long long ann[kTR];   // annotation of the record, 0 = not written
     uint2 seg[2][kTR];             // long segments {dst | src << 16, length}: read (+ "+" + quality when adjacent), quality
+    uint2 chk[2][kTR];             // their whole 16-byte chunks {first dst | aligned src << 16, count | word shift << 16 | bit shift << 24}
     uint2 head[kTR];               // {dst | src << 16, cut length | literal dst << 16}
     unsigned long long bar;        // mbarrier of the input copy
     unsigned long long g0, g1;     // file range of the block's records
-    uint32_t fits, flags, next[2];
+    uint32_t fits, flags;
 };
 
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes)
@@ -62,25 +63,27 @@ __device__ __forceinline__ void tile_edges(TileSmem& S, uint2 sg)
     for (uint32_t p = t0; p < e; p++) S.out[p] = S.in[src + (p - dst)];
 }
 
-// whole 16-byte output chunks j, j + stride, ... of a long segment
-__device__ __forceinline__ void tile_chunks(TileSmem& S, uint2 sg, uint32_t j, uint32_t stride)
+// descriptor of the whole 16-byte output chunks of a long segment
+__device__ __forceinline__ uint2 tile_chunk_desc(uint2 sg)
 {
     const uint32_t dst = sg.x & 0xFFFFu, src = sg.x >> 16, len = sg.y;
     const uint32_t first = (dst + 15u) & ~15u, last = (dst + len) & ~15u;
-    if (last <= first) return;
-    const uint32_t nfull = (last - first) >> 4;
-    const uint32_t sa0 = src + (first - dst);      // source of the first whole chunk
-    const uint32_t ws = (sa0 & 15u) >> 2, bs = (sa0 & 3u) * 8u;
-    const bool s2 = ws & 2u, s1 = ws & 1u;
-    const uint4* in16 = reinterpret_cast<const uint4*>(S.in + (sa0 & ~15u));
-    uint4* out16 = reinterpret_cast<uint4*>(S.out + first);
-    for (uint32_t c = j; c < nfull; c += stride) {
-        const uint4 A = in16[c], B = in16[c + 1];
-        const uint32_t t0 = s2 ? A.z : A.x, t1 = s2 ? A.w : A.y, t2 = s2 ? B.x : A.z, t3 = s2 ? B.y : A.w, t4 = s2 ? B.z : B.x,
-                       t5 = s2 ? B.w : B.y;
-        const uint32_t w0 = s1 ? t1 : t0, w1 = s1 ? t2 : t1, w2 = s1 ? t3 : t2, w3 = s1 ? t4 : t3, w4 = s1 ? t5 : t4;
-        out16[c] = make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
-    }
+    if (last <= first) return make_uint2(0u, 0u);
+    const uint32_t sa0 = src + (first - dst);  // source of the first whole chunk
+    return make_uint2(first | ((sa0 & ~15u) << 16), ((last - first) >> 4) | (((sa0 & 15u) >> 2) << 16) | (((sa0 & 3u) * 8u) << 24));
+}
+
+// whole chunk c of a long segment: two aligned 16-byte loads funnel-shifted into one aligned 16-byte store
+__device__ __forceinline__ void tile_chunk(TileSmem& S, uint2 ck, uint32_t c)
+{
+    const uint32_t bs = ck.y >> 24;
+    const bool s2 = ck.y & 0x20000u, s1 = ck.y & 0x10000u;
+    const uint4* in16 = reinterpret_cast<const uint4*>(S.in + (ck.x >> 16)) + c;
+    const uint4 A = in16[0], B = in16[1];
+    const uint32_t t0 = s2 ? A.z : A.x, t1 = s2 ? A.w : A.y, t2 = s2 ? B.x : A.z, t3 = s2 ? B.y : A.w, t4 = s2 ? B.z : B.x, t5 = s2 ? B.w : B.y;
+    const uint32_t w0 = s1 ? t1 : t0, w1 = s1 ? t2 : t1, w2 = s1 ? t3 : t2, w3 = s1 ? t4 : t3, w4 = s1 ? t5 : t4;
+    reinterpret_cast<uint4*>(S.out + (ck.x & 0xFFFFu))[c] =
+        make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
 }
 
 // records [r0, r1) one warp each, global memory to global memory (exact, any record)
@@ -103,20 +106,27 @@ __global__ void __launch_bounds__(kThreads) k_emit_tiled(const __grid_constant__
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const uint64_t r0 = (uint64_t)blockIdx.x * args.rpb;
     if (r0 >= args.n_rec) return;
     const uint64_t r1 = r0 + args.rpb < args.n_rec ? r0 + args.rpb : args.n_rec;
+    // the block's file range: requested together with the output range (one round trip before the bulk copy can start)
+    uint64_t g0t = 0, g1t = 0;
+    uint4 ml = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        g0t = (uint64_t)args.r1_start[r0];
+        g1t = (uint64_t)args.r1_start[r1 - 1];
+        ml = args.r1_meta[r1 - 1];
+    }
     const uint64_t out_lo = args.out_off[r0], out_hi = args.out_off[r1];
-    if (out_hi == out_lo) return;  // nothing of this block survives the filter: no loads at all
+    if (out_hi == out_lo) return;  // nothing of this block survives the filter
     const uint32_t nrec = (uint32_t)(r1 - r0);
     const uint32_t out_skew = (uint32_t)(((uintptr_t)args.out + out_lo) & 15u);
 
     // ---- the block's input range; its 16-byte aligned middle arrives by bulk copy ----
     if (tid == 0) {
-        const uint64_t g0 = (uint64_t)args.r1_start[r0];
-        const uint4 ml = args.r1_meta[r1 - 1];
-        uint64_t g1 = (uint64_t)args.r1_start[r1 - 1] + (ml.z & 0xFFFFu) + (ml.z >> 16) + 1u;  // behind the last quality line
+        const uint64_t g0 = g0t;
+        uint64_t g1 = g1t + (ml.z & 0xFFFFu) + (ml.z >> 16) + 1u;  // behind the last quality line
         g1 = g1 < (uint64_t)args.r1_len ? g1 : (uint64_t)args.r1_len;
         const uint32_t mis = (uint32_t)((uintptr_t)(args.r1buf + g0) & 15u);
         const bool fits = nrec <= (uint32_t)kTR && g1 > g0 && g1 - g0 + mis <= (uint64_t)kTIn && out_hi - out_lo + out_skew <= (uint64_t)kTOut;
@@ -124,7 +134,6 @@ __global__ void __launch_bounds__(kThreads) k_emit_tiled(const __grid_constant__
         S.g1 = g1;
         S.fits = fits ? 1u : 0u;
         S.flags = 0;
-        S.next[0] = S.next[1] = 0;
         mbar_init(reinterpret_cast<uint64_t*>(&S.bar), 1);
         if (fits) {
             uint64_t b0, b1;
@@ -199,6 +208,8 @@ __global__ void __launch_bounds__(kThreads) k_emit_tiled(const __grid_constant__
         }
         S.seg[0][tid] = sa;
         S.seg[1][tid] = sb;
+        S.chk[0][tid] = tile_chunk_desc(sa);
+        S.chk[1][tid] = tile_chunk_desc(sb);
         S.head[tid] = hd;
         S.ann[tid] = an;
     }
@@ -211,18 +222,17 @@ __global__ void __launch_bounds__(kThreads) k_emit_tiled(const __grid_constant__
     }
 
     if (warp < 2) {
-        // ---- header without its blanks, and the ragged ends of the long segments ----
+        // ---- header without its blanks ----
         const uint32_t k = (uint32_t)tid;
         if (k < nrec && S.ann[k] != 0ull) {
             const uint2 hd = S.head[k];
-            const uint32_t d = hd.x & 0xFFFFu, src0 = hd.x >> 16, cut = hd.y & 0xFFFFu;
-            uint32_t o = d;
+            const uint32_t cut = hd.y & 0xFFFFu;
+            const uint8_t* sp = S.in + (hd.x >> 16);
+            uint8_t* dp = S.out + (hd.x & 0xFFFFu);
             for (uint32_t i = 0; i < cut; i++) {
-                const uint8_t ch = S.in[src0 + i];
-                if (ch != ' ') S.out[o++] = ch;
+                const uint8_t ch = sp[i];
+                if (ch != ' ') *dp++ = ch;
             }
-            tile_edges(S, S.seg[0][k]);
-            if (flags & 2u) tile_edges(S, S.seg[1][k]);
         }
     } else if (warp < 4) {
         // ---- '_' + barcode1 + barcode2 + barcode3 + '_' + umi + '\n' ----
@@ -235,42 +245,59 @@ __global__ void __launch_bounds__(kThreads) k_emit_tiled(const __grid_constant__
             uint32_t i1, i2, i3;
             cell_indices(cfg, cell, i1, i2, i3);
             const unsigned long long b1 = __ldg(args.wl64 + i1), b2 = __ldg(args.wl64 + i2), b3 = __ldg(args.wl64 + i3);
+            const uint32_t b1l = (uint32_t)b1, b1h = (uint32_t)(b1 >> 32), b2l = (uint32_t)b2, b2h = (uint32_t)(b2 >> 32), b3l = (uint32_t)b3,
+                           b3h = (uint32_t)(b3 >> 32);
             q[0] = '_';
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                q[1 + j] = (uint8_t)(b1 >> (8 * j));
-                q[9 + j] = (uint8_t)(b2 >> (8 * j));
-                q[17 + j] = (uint8_t)(b3 >> (8 * j));
+            for (int j = 0; j < 4; j++) {
+                q[1 + j] = (uint8_t)(b1l >> (8 * j));
+                q[5 + j] = (uint8_t)(b1h >> (8 * j));
+                q[9 + j] = (uint8_t)(b2l >> (8 * j));
+                q[13 + j] = (uint8_t)(b2h >> (8 * j));
+                q[17 + j] = (uint8_t)(b3l >> (8 * j));
+                q[21 + j] = (uint8_t)(b3h >> (8 * j));
             }
             q[25] = '_';
-            const uint64_t payload = ann_payload(an);
             uint32_t ulen;
             if (ann_state(an) == 1u) {
                 ulen = (uint32_t)cfg.umi_len;
+                const uint32_t code = (uint32_t)an;  // 2 bits per base, at most 10 bases
 #pragma unroll
                 for (int j = 0; j < 10; j++)
-                    if ((uint32_t)j < ulen) q[26 + j] = (uint8_t)__byte_perm(0x47544341u, 0u, (uint32_t)(payload >> (2 * j)) & 3u);
+                    if ((uint32_t)j < ulen) q[26 + j] = (uint8_t)__byte_perm(0x47544341u, 0u, (code >> (2 * j)) & 3u);
             } else {
+                const uint64_t payload = ann_payload(an);
                 ulen = (uint32_t)(payload & 31u);
                 const uint8_t* u = args.r2buf + (size_t)(payload >> 5);
                 for (uint32_t j = 0; j < ulen; j++) q[26u + j] = u[j];
             }
             q[26u + ulen] = '\n';
         }
+    } else if (warp < 6) {
+        // ---- the ragged ends of the long segments ----
+        const uint32_t k = (uint32_t)tid - 128u;
+        if (k < nrec && S.ann[k] != 0ull) {
+            tile_edges(S, S.seg[0][k]);
+            if (flags & 2u) tile_edges(S, S.seg[1][k]);
+        }
     }
 
-    // ---- whole 16-byte chunks of the long segments: cps slots per record, a warp takes 32 slots at a time ----
-    for (int pass = 0; pass < 2; pass++) {
-        if (pass == 1 && !(flags & 2u)) break;
+    // ---- whole 16-byte chunks of the long segments: cps slots per record, slot i = (record i / cps, chunk i % cps) ----
+    {
         const uint32_t n_items = nrec * args.cps;
-        for (;;) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&S.next[pass], 32u);
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (base >= n_items) break;
-            const uint32_t i = base + (uint32_t)lane;
-            const uint32_t k = (uint32_t)(((unsigned long long)i * args.cps_magic) >> 20), j = i - k * args.cps;
-            if (k < nrec) tile_chunks(S, S.seg[pass][k], j, args.cps);
+        for (uint32_t i = (uint32_t)tid; i < n_items; i += kThreads) {
+            const uint32_t k = (i * args.cps_magic) >> 20, j = i - k * args.cps;
+            const uint2 ck = S.chk[0][k];
+            const uint32_t nfull = ck.y & 0xFFFFu;
+            if (j < nfull) tile_chunk(S, ck, j);
+            for (uint32_t c = j + args.cps; c < nfull; c += args.cps) tile_chunk(S, ck, c);  // segments longer than the slots
+        }
+        if (flags & 2u) {
+            for (uint32_t i = (uint32_t)tid; i < n_items; i += kThreads) {
+                const uint32_t k = (i * args.cps_magic) >> 20, j = i - k * args.cps;
+                const uint2 ck = S.chk[1][k];
+                for (uint32_t c = j; c < (ck.y & 0xFFFFu); c += args.cps) tile_chunk(S, ck, c);
+            }
         }
     }
 

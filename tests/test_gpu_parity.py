@@ -290,3 +290,43 @@ def test_config3_e2_ties_n_collapse(ssd, orc):
     renamed = sum(1 for i, r in enumerate(remap) if r != i)
     cells_after = {rec.split(b"\n", 1)[0].split(b"_")[1] for rec in fu.records(passing2)}
     assert len(cells_after) == ref.n_passing_cells - renamed
+
+
+@pytest.mark.parametrize("skew", [(16, 32, 5), (0, 16, 9), (48, 0, 15)])
+def test_unaligned_output_buffer(ssd, orc, skew):
+    """Output at device addresses that are not 16-byte aligned (inputs must be 16-byte aligned, include/ssd_b200.h): the
+    writer moves its slices with bulk copies between aligned addresses and copies the ragged ends bytewise."""
+    import torch
+    spec = ssd.synth_spec(WL, 30000, seed=77, cell_pool=400)
+    h1, h2 = ssd.synth_host(spec)
+    ref = orc.demultiplex(h1, h2, WL, 1, 3)
+    dm = ssd.Demultiplexer(WL, errors=1, min_count=3)
+    s1, s2, so = skew
+    b1 = torch.zeros(len(h1) + 64, dtype=torch.uint8, device="cuda")
+    b2 = torch.zeros(len(h2) + 64, dtype=torch.uint8, device="cuda")
+    d1, d2 = b1[s1:s1 + len(h1)], b2[s2:s2 + len(h2)]
+    d1.copy_(torch.frombuffer(bytearray(h1), dtype=torch.uint8))
+    d2.copy_(torch.frombuffer(bytearray(h2), dtype=torch.uint8))
+    torch.cuda.synchronize()
+    handle = torch.cuda.current_stream().cuda_stream
+    dm.set_stream(handle)
+    dm.demux_device(d1.data_ptr(), d1.numel(), d2.data_ptr(), d2.numel(), keep=(b1, b2))
+    stats = dm.filter_single()
+    for which, want in ((ssd.EMIT_MATCHED, ref.merged1), (ssd.EMIT_PASSING, ref.passing)):
+        guard = torch.full((len(want) + 96,), 0xA5, dtype=torch.uint8, device="cuda")
+        n = dm.emit_device(which, guard[so:].data_ptr(), len(want) + 16)
+        torch.cuda.synchronize()
+        got = guard.cpu().numpy()
+        assert n == len(want) and got[so:so + n].tobytes() == want
+        assert (got[:so] == 0xA5).all() and (got[so + n:] == 0xA5).all()  # nothing outside the slice is touched
+    assert stats["n_matched"] == ref.n_matched
+
+
+def test_group_writer_matches_tiled_writer(ssd, orc, monkeypatch):
+    """SSD_EMIT_GROUPS=1 selects the eight-lanes-per-record writer (the one split mode and annotated input use)."""
+    spec = ssd.synth_spec(WL, 20000, seed=11, cell_pool=300)
+    h1, h2 = ssd.synth_host(spec)
+    ref = orc.demultiplex(h1, h2, WL, 1, 2)
+    monkeypatch.setenv("SSD_EMIT_GROUPS", "1")
+    dm, merged, passing, stats = run_both(ssd, h1, h2, 1, 2)
+    assert merged == ref.merged1 and passing == ref.passing
