@@ -72,6 +72,7 @@ struct ssd_ctx {
     DevBuf b_status1, b_status2, b_r1_start, b_r1_meta, b_r1_base, b_r1_tok, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
         b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
     DevBuf b_in1, b_in2, b_out;
+    DevBuf b_os, b_irr_table;  // one-kernel-per-pass sort: histograms, tickets, tile status; hash set of the irregular keys
     DevBuf b_sp_cells, b_sp_cells_alt, b_sp_recs, b_sp_recs_alt, b_sp_off, b_bk_cell, b_bk_off, b_bk_first;
     // the irregular-key path runs on its own stream with its own scratch, next to the regular sort
     cudaStream_t side_stream = nullptr;
@@ -340,6 +341,63 @@ int count_cells(ssd_ctx* c, const uint64_t* uniq, uint64_t n_uniq, const IrrKey*
     if (n_uniq) k_count_cells64<<<blocks_for(n_uniq, kThreads), kThreads, 0, c->stream>>>(uniq, n_uniq, c->dcfg.umi_bits, c->d_distinct);
     if (n_uirr) k_count_cells_irr<<<blocks_for(n_uirr, kThreads), kThreads, 0, c->stream>>>(uirr, n_uirr, c->d_distinct);
     c->n_launches += (n_uniq ? 1 : 0) + (n_uirr ? 1 : 0);
+    CU(c, cudaGetLastError());
+    return SSD_OK;
+}
+
+// Per-cell distinct-UMI counts of the batch straight from the annotation words (single GPU: no unique-key lists, no
+// host round trip).  Regular keys: one-kernel-per-pass radix sort + first-occurrence count; irregular keys: hash set
+// on the side stream.
+int distinct_counts_local(ssd_ctx* c)
+{
+    CU(c, cudaMemsetAsync(c->d_distinct, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
+    const uint64_t n_rec = c->n_rec_r2, n_keys = c->n_keys, n_irr = c->n_irr;
+    const uint64_t* ann = (const uint64_t*)c->b_ann.p;
+    const bool side = n_irr != 0 && c->side_stream != nullptr;
+    if (n_irr) {
+        uint64_t slots = 1024;
+        while (slots < 2 * n_irr) slots <<= 1;
+        if (slots > (1ull << 32)) return fail(c, SSD_ERANGE, "too many irregular UMIs in one batch");
+        OKR(ensure(c, c->b_irr_table, slots * sizeof(ulonglong2)));
+        cudaStream_t st = c->stream;
+        if (side) {
+            CU(c, cudaEventRecord(c->ev_fork, c->stream));
+            CU(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+            st = c->side_stream;
+        }
+        CU(c, cudaMemsetAsync(c->b_irr_table.p, 0, slots * sizeof(ulonglong2), st));
+        k_irr_hash<<<blocks_for(n_rec, kThreads), kThreads, 0, st>>>(ann, n_rec, c->r2, (ulonglong2*)c->b_irr_table.p, (uint32_t)(slots - 1), c->d_distinct);
+        c->n_launches++;
+        if (side) CU(c, cudaEventRecord(c->ev_join, st));
+    }
+    if (n_keys) {
+        const int bits = c->dcfg.umi_bits + c->dcfg.cell_bits;
+        const int passes = (bits + kOsBits - 1) / kOsBits;
+        if (passes > kOsMaxPasses || n_keys > (uint64_t)kOsValue) return fail(c, SSD_ERANGE, "key space too large for the radix sort");
+        const uint64_t tiles_first = (n_rec + kOsTile - 1) / kOsTile, tiles_next = (n_keys + kOsTile - 1) / kOsTile;
+        const size_t head_words = (size_t)kOsMaxPasses * kOsRadix + 64;  // histograms, then one ticket per pass
+        const size_t status_words = (size_t)(tiles_first + (uint64_t)(passes - 1) * tiles_next) * kOsRadix;
+        OKR(ensure(c, c->b_os, (head_words + status_words) * sizeof(uint32_t)));
+        OKR(ensure(c, c->b_keys, n_keys * sizeof(uint64_t)));
+        OKR(ensure(c, c->b_keys_alt, n_keys * sizeof(uint64_t)));
+        uint32_t* ghist = (uint32_t*)c->b_os.p;
+        uint32_t* ticket = ghist + (size_t)kOsMaxPasses * kOsRadix;
+        uint32_t* status = ghist + head_words;
+        CU(c, cudaMemsetAsync(c->b_os.p, 0, (head_words + status_words) * sizeof(uint32_t), c->stream));
+        const KeysFromAnn from_ann{ann, c->dcfg.umi_bits};
+        k_os_hist<KeysFromAnn><<<(uint32_t)std::min<uint64_t>(blocks_for(n_rec, kThreads), 148 * 8), kThreads, 0, c->stream>>>(from_ann, n_rec, passes, ghist);
+        uint64_t *a = (uint64_t*)c->b_keys.p, *b = (uint64_t*)c->b_keys_alt.p;
+        k_os_pass<KeysFromAnn><<<(uint32_t)tiles_first, kThreads, 0, c->stream>>>(from_ann, n_rec, 0, a, ghist, status, ticket);
+        status += tiles_first * kOsRadix;
+        for (int p = 1; p < passes; p++) {
+            k_os_pass<KeysArray><<<(uint32_t)tiles_next, kThreads, 0, c->stream>>>(KeysArray{a}, n_keys, p * kOsBits, b, ghist + (size_t)p * kOsRadix, status, ticket + p);
+            status += tiles_next * kOsRadix;
+            std::swap(a, b);
+        }
+        k_count_sorted<<<blocks_for(n_keys, kThreads), kThreads, 0, c->stream>>>(a, n_keys, c->dcfg.umi_bits, c->d_distinct);
+        c->n_launches += 2 + passes;
+    }
+    if (side) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     CU(c, cudaGetLastError());
     return SSD_OK;
 }
@@ -627,7 +685,7 @@ extern "C" void ssd_destroy(ssd_ctx* c)
     DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_r1_start, &c->b_r1_meta, &c->b_r1_base, &c->b_r1_tok, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
                       &c->b_irr_alt, &c->b_perm, &c->b_perm_alt, &c->b_tmp64a, &c->b_tmp64b, &c->b_counts, &c->b_offsets, &c->b_bsums,
                       &c->b_pos, &c->b_out_off, &c->b_cells, &c->b_in1, &c->b_in2, &c->b_out, &c->b_sp_cells, &c->b_sp_cells_alt, &c->b_sp_recs,
-                      &c->b_sp_recs_alt, &c->b_sp_off, &c->b_bk_cell, &c->b_bk_off, &c->b_bk_first};
+                      &c->b_sp_recs_alt, &c->b_sp_off, &c->b_bk_cell, &c->b_bk_off, &c->b_bk_first, &c->b_os, &c->b_irr_table};
     for (DevBuf* b : bufs) release(*b);
     cudaFree(c->d_cnt);
     cudaFree(c->d_err_off);
@@ -855,10 +913,17 @@ extern "C" int ssd_filter_single(ssd_ctx* c, ssd_stats* stats)
 {
     if (!c) return SSD_EINVAL;
     if (c->cfg.filter_mode == SSD_FILTER_DISTINCT_UMI) {
-        uint64_t *k = nullptr, nk = 0, ni = 0;
-        void* ik = nullptr;
-        OKR(ssd_local_unique_keys(c, &k, &nk, &ik, &ni));
-        OKR(ssd_count_distinct(c, k, nk, ik, ni));
+        if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_filter_single before ssd_demux_device");
+        CU(c, cudaSetDevice(c->device));
+        if (c->unique_done || getenv("SSD_DISTINCT_LISTS")) {  // the unique-key lists exist (or are asked for): count those
+            uint64_t *k = nullptr, nk = 0, ni = 0;
+            void* ik = nullptr;
+            OKR(ssd_local_unique_keys(c, &k, &nk, &ik, &ni));
+            OKR(ssd_count_distinct(c, k, nk, ik, ni));
+        } else {
+            StageTimer t(c, 2);
+            OKR(distinct_counts_local(c));
+        }
     }
     return ssd_build_filter(c, stats);
 }

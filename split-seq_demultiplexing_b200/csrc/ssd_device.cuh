@@ -251,14 +251,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+constexpr uint32_t kMbarSuspendNs = 20000u;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok = 0;
     while (!ok) {
         asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)  // the thread may stay suspended this long before it polls again
             : "memory");
     }
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include "ssd_device.cuh"
 #include "ssd_sort.cuh"
+#include "ssd_onesweep.cuh"
 #include "ssd_scan.cuh"
 #include "ssd_emit.cuh"
 #include "ssd_emit_tiled.cuh"

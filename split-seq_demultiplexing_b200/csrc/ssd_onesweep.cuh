@@ -1,0 +1,210 @@
+// ssd_onesweep.cuh — per-cell distinct-UMI counts (the len(set(...)) of V2:411) without unique-key lists, sm_100a.
+//
+// Regular keys (cell << umi_bits | 2-bit UMI, <= 48 bits): LSD radix sort with 8-bit digits where every pass is ONE
+// kernel.  The digit histograms of all passes come from a single read of the keys; a pass then assigns tiles in
+// launch order (ticket), ranks its 4096 keys per digit (match.any), learns the digit offsets of the earlier tiles by a
+// decoupled look-back over per-tile digit counts, reorders the tile in shared memory and writes digit runs
+// contiguously.  The first pass reads the annotation words directly (compaction for free).  A last kernel counts the
+// first occurrences per cell in the sorted keys, one atomic per (warp, cell).
+// Irregular keys (UMI with non-ACGT bytes or short; raw bytes, 128 bits) are few: an open-addressing hash set with
+// 128-bit compare-and-swap, exact, one kernel, on the side stream.
+#pragma once
+#include "ssd_sort.cuh"
+
+namespace ssd {
+
+constexpr int kOsBits = 8;
+constexpr int kOsRadix = 1 << kOsBits;
+constexpr int kOsItems = 16;
+constexpr int kOsTile = kThreads * kOsItems;  // keys per tile
+constexpr int kOsMaxPasses = 6;
+constexpr uint32_t kOsAgg = 1u << 30, kOsPrefix = 2u << 30, kOsValue = (1u << 30) - 1u;
+static_assert(kThreads == kOsRadix, "one thread per digit");
+
+// digit histograms of all passes in one read of the keys
+template <class Src>
+__global__ void __launch_bounds__(kThreads) k_os_hist(Src keys, uint64_t n, int passes, uint32_t* ghist)
+{
+    __shared__ uint32_t s_h[kOsMaxPasses][kOsRadix];
+    for (int j = threadIdx.x; j < kOsMaxPasses * kOsRadix; j += kThreads) (&s_h[0][0])[j] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kThreads) {
+        const uint64_t k = keys(i);
+        if (k != kNoKey) {
+#pragma unroll
+            for (int p = 0; p < kOsMaxPasses; p++)
+                if (p < passes) atomicAdd(&s_h[p][(uint32_t)(k >> (kOsBits * p)) & (kOsRadix - 1)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < passes * kOsRadix; j += kThreads) {
+        const uint32_t v = (&s_h[0][0])[j];
+        if (v) atomicAdd(&ghist[j], v);
+    }
+}
+
+// one pass: stable scatter of the keys by the digit at `shift`
+template <class Src>
+__global__ void __launch_bounds__(kThreads) k_os_pass(Src keys_in, uint64_t n, int shift, uint64_t* keys_out, const uint32_t* ghist,
+                                                      uint32_t* status, uint32_t* ticket)
+{
+    __shared__ uint64_t s_keys[kOsTile];
+    __shared__ uint32_t s_wcount[kThreads / 32][kOsRadix];
+    __shared__ uint32_t s_lstart[kOsRadix];
+    __shared__ unsigned long long s_base[kOsRadix];
+    __shared__ unsigned long long s_wsum[kThreads / 32];
+    __shared__ uint32_t s_tile, s_nvalid;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);  // tiles are taken in launch order: what a tile looks back at is running or done
+    for (int i = tid; i < (kThreads / 32) * kOsRadix; i += kThreads) (&s_wcount[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+
+    // warp w owns keys [w * 512, (w + 1) * 512) of the tile; iteration i, lane l -> key w * 512 + i * 32 + l
+    const uint64_t wbase = (uint64_t)tile * kOsTile + (uint64_t)warp * (32 * kOsItems);
+    uint64_t key[kOsItems];
+    uint16_t rank[kOsItems], dig[kOsItems];
+#pragma unroll
+    for (int i = 0; i < kOsItems; i++) {
+        const uint64_t j = wbase + (uint64_t)i * 32 + lane;
+        bool valid = j < n;
+        key[i] = valid ? keys_in(j) : kNoKey;
+        valid = key[i] != kNoKey;
+        const uint32_t d = valid ? (uint32_t)(key[i] >> shift) & (kOsRadix - 1) : (uint32_t)kOsRadix;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        const uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
+        uint32_t pre = 0;
+        if ((uint32_t)lane == leader && valid) pre = s_wcount[warp][d];
+        pre = __shfl_sync(0xFFFFFFFFu, pre, (int)leader);
+        __syncwarp();
+        if ((uint32_t)lane == leader && valid) s_wcount[warp][d] = pre + (uint32_t)__popc(peers);
+        __syncwarp();
+        rank[i] = (uint16_t)(pre + (uint32_t)__popc(peers & ((1u << lane) - 1u)));
+        dig[i] = (uint16_t)d;
+    }
+    __syncthreads();
+
+    // thread d: the tile's count of digit d (warp counts become exclusive offsets), then the exclusive scans over
+    // the digits of the tile counts (low word) and of the global histogram (high word) in one go
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) {
+        const uint32_t cw = s_wcount[w][tid];
+        s_wcount[w][tid] = cnt;
+        cnt += cw;
+    }
+    const unsigned long long mine = ((unsigned long long)ghist[tid] << 32) | cnt;
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += u;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    // publish the tile count of this digit right away: later tiles are waiting for it
+    volatile uint32_t* st = status + (size_t)tile * kOsRadix + tid;
+    if (tile != 0) *st = kOsAgg | cnt;
+    __syncthreads();
+    unsigned long long before = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++)
+        if (w < warp) before += s_wsum[w];
+    const unsigned long long excl = before + incl - mine;
+    const uint32_t lstart = (uint32_t)excl, gstart = (uint32_t)(excl >> 32);
+    s_lstart[tid] = lstart;
+    if (tid == kOsRadix - 1) s_nvalid = lstart + cnt;
+
+    // decoupled look-back: keys with this digit in all earlier tiles
+    uint32_t prior = 0;
+    for (uint32_t t = tile; t > 0;) {
+        const uint32_t f = *reinterpret_cast<volatile const uint32_t*>(&status[(size_t)(t - 1) * kOsRadix + tid]);
+        if ((f >> 30) == 0u) continue;  // not published yet
+        prior += f & kOsValue;
+        if ((f >> 30) == 2u) break;     // an inclusive prefix: everything before it is counted in
+        t--;
+    }
+    *st = kOsPrefix | (prior + cnt);
+    s_base[tid] = (unsigned long long)gstart + prior - lstart;  // global index of the tile-sorted position 0, per digit (wraps, fine)
+    __syncthreads();
+
+    // tile-sorted order in shared memory, then digit runs go out contiguously
+#pragma unroll
+    for (int i = 0; i < kOsItems; i++) {
+        const uint32_t d = dig[i];
+        if (d < (uint32_t)kOsRadix) s_keys[s_lstart[d] + s_wcount[warp][d] + rank[i]] = key[i];
+    }
+    __syncthreads();
+    const uint32_t nvalid = s_nvalid;
+#pragma unroll
+    for (int i = 0; i < kOsItems; i++) {
+        const uint32_t idx = (uint32_t)tid + (uint32_t)i * kThreads;
+        if (idx < nvalid) {
+            const uint64_t k = s_keys[idx];
+            keys_out[s_base[(uint32_t)(k >> shift) & (kOsRadix - 1)] + idx] = k;
+        }
+    }
+}
+
+// sorted keys -> distinct[cell] += number of first occurrences; one atomic per (warp, cell)
+__global__ void __launch_bounds__(kThreads) k_count_sorted(const uint64_t* keys, uint64_t n, int shift, uint32_t* distinct)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = i < n;
+    const uint64_t k = valid ? keys[i] : 0ull;
+    const bool head = valid && (i == 0 || keys[i - 1] != k);
+    const uint32_t cell = valid ? (uint32_t)(k >> shift) : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cell);
+    const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);
+    if (valid && (uint32_t)lane == (uint32_t)__ffs((int)peers) - 1u) {
+        const uint32_t c = (uint32_t)__popc(heads & peers);
+        if (c) atomicAdd(&distinct[cell], c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// irregular keys: exact hash set, 128-bit compare-and-swap (ATOMG.E.CAS.128)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cas128(void* p, unsigned long long cmp_lo, unsigned long long cmp_hi, unsigned long long new_lo,
+                                       unsigned long long new_hi, unsigned long long& old_lo, unsigned long long& old_hi)
+{
+    asm volatile(
+        "{\n\t.reg .b128 c, s, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 s, {%4, %5};\n\tatom.global.cas.b128 o, [%6], c, s;\n\tmov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(old_lo), "=l"(old_hi)
+        : "l"(cmp_lo), "l"(cmp_hi), "l"(new_lo), "l"(new_hi), "l"(p)
+        : "memory");
+}
+
+// table: slots of {lo, hi | 1 << 63}, zero = empty; n_slots is a power of two >= 2 * (number of irregular records)
+__global__ void __launch_bounds__(kThreads) k_irr_hash(const uint64_t* ann, uint64_t n, const uint8_t* r2buf, ulonglong2* table, uint32_t slot_mask,
+                                                       uint32_t* distinct)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (r >= n) return;
+    const uint64_t a = ann[r];
+    if (ann_state(a) != 2) return;
+    const uint64_t payload = ann_payload(a);
+    const uint32_t ulen = (uint32_t)(payload & 31u);
+    const uint8_t* p = r2buf + (size_t)(payload >> 5);
+    uint64_t hi = 0, lo = 0;
+    for (uint32_t j = 0; j < ulen; j++) {
+        const uint64_t c = p[j];
+        if (j < 4) hi |= c << (8 * (3 - j));
+        else lo |= c << (8 * (9 - j));
+    }
+    const uint32_t cell = ann_cell(a);
+    hi |= ((uint64_t)cell << kIrrCellShift) | ((uint64_t)ulen << 32) | (1ull << 63);
+    unsigned long long h = (hi ^ (lo * 0x9E3779B97F4A7C15ull)) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 31;
+    for (uint32_t s = (uint32_t)h & slot_mask;; s = (s + 1u) & slot_mask) {
+        unsigned long long olo, ohi;
+        cas128(&table[s], 0ull, 0ull, lo, hi, olo, ohi);
+        if (olo == 0ull && ohi == 0ull) {  // first time this (cell, UMI) is seen
+            atomicAdd(&distinct[cell], 1u);
+            return;
+        }
+        if (olo == lo && ohi == hi) return;
+    }
+}
+
+}  // namespace ssd
