@@ -58,6 +58,7 @@ struct ssd_ctx {
     bool wide = false;  // 64-bit record offsets
     uint64_t rec_cap = 0;
     uint64_t n_rec_r1 = 0, n_rec_r2 = 0, n_rec = 0, n_keys = 0, n_irr = 0;
+    uint64_t n_respec = 0;  // scans repeated without guessing (diagnostics)
     bool phase1_done = false, filter_done = false, unique_done = false;
     int planned = -1;  // which output b_out_off currently describes (-1 = none)
     bool annotated = false;  // the batch is an already annotated FASTQ (V2.calc_demux_results)
@@ -402,7 +403,7 @@ int distinct_counts_local(ssd_ctx* c)
     return SSD_OK;
 }
 
-template <typename OffT>
+template <typename OffT, bool DEFER>
 int launch_scans(ssd_ctx* c)
 {
     ScanArgs<OffT> a{};
@@ -428,7 +429,7 @@ int launch_scans(ssd_ctx* c)
             a.status = (unsigned long long*)c->b_status1.p;
             a.n_tiles = nt1;
             StageTimer t(c, 0);
-            k_scan<kScanAnn, OffT><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+            k_scan<kScanAnn, OffT, DEFER><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
             c->n_launches++;
         }
         CU(c, cudaGetLastError());
@@ -440,7 +441,7 @@ int launch_scans(ssd_ctx* c)
         a.status = (unsigned long long*)c->b_status1.p;
         a.n_tiles = nt1;
         StageTimer t(c, 0);
-        k_scan<kScanR1, OffT><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        k_scan<kScanR1, OffT, DEFER><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         c->n_launches++;
     }
     if (nt2) {
@@ -449,7 +450,7 @@ int launch_scans(ssd_ctx* c)
         a.status = (unsigned long long*)c->b_status2.p;
         a.n_tiles = nt2;
         StageTimer t(c, 1);
-        k_scan<kScanR2, OffT><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        k_scan<kScanR2, OffT, DEFER><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         c->n_launches++;
     }
     CU(c, cudaGetLastError());
@@ -643,16 +644,22 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
         // the scan kernels are persistent: one wave of blocks, each looping over tiles
         cudaDeviceProp prop;
         CUB_(cudaGetDeviceProperties(&prop, c->device));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
         CUB_(cudaFuncSetAttribute(k_emit_tiled<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
         CUB_(cudaFuncSetAttribute(k_emit_tiled<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
         int per_sm = 0;
-        CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<kScanR2, uint32_t>, kScanThreads, sizeof(ScanSmem)));
+        CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<kScanR2, uint32_t, true>, kScanThreads, sizeof(ScanSmem)));
         c->scan_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
     }
     CUB_(cudaMalloc(&c->d_cnt, sizeof(DevCounters)));
@@ -737,7 +744,10 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
     const uint32_t nt1 = blocks_for(r1_len, kTile), nt2 = blocks_for(r2_len, kTile);
     uint64_t cap = std::max(r1_len, r2_len) / (uint64_t)c->record_hint + 1024;
     DevCounters h{};
-    for (int attempt = 0; attempt < 2; attempt++) {
+    // the scans park their per-record results until the record numbers arrive and guess the record phase of each tile meanwhile;
+    // a wrong guess (lines that look like record starts where none is) repeats the scan with the variant that waits instead
+    bool defer = getenv("SSD_SCAN_NODEFER") == nullptr;
+    for (int attempt = 0, overflows = 0; attempt < 4; attempt++) {
         c->rec_cap = cap;
         OKR(ensure(c, c->b_status1, (size_t)(nt1 + 1) * 8));
         OKR(ensure(c, c->b_status2, (size_t)(nt2 + 1) * 8));
@@ -753,12 +763,19 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
         CU(c, cudaMemsetAsync(c->d_hist, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
         CU(c, cudaMemsetAsync(c->b_status1.p, 0, (size_t)(nt1 + 1) * 8, c->stream));
         CU(c, cudaMemsetAsync(c->b_status2.p, 0, (size_t)(nt2 + 1) * 8, c->stream));
-        OKR(c->wide ? launch_scans<uint64_t>(c) : launch_scans<uint32_t>(c));
+        if (defer) OKR(c->wide ? (launch_scans<uint64_t, true>(c)) : (launch_scans<uint32_t, true>(c)));
+        else OKR(c->wide ? (launch_scans<uint64_t, false>(c)) : (launch_scans<uint32_t, false>(c)));
         OKR(fetch_counters(c, &h));
+        if (h.err_flags & kErrRespec) {
+            defer = false;
+            c->n_respec++;
+            continue;
+        }
         if (!(h.err_flags & kErrOverflow)) break;
-        if (attempt == 1) return fail(c, SSD_EINVAL, "record tables overflowed twice (internal)");
+        if (++overflows == 2) return fail(c, SSD_EINVAL, "record tables overflowed twice (internal)");
         cap = std::max(h.n_records[0], h.n_records[1]) + 1;
     }
+    if (h.err_flags & (kErrRespec | kErrOverflow)) return fail(c, SSD_EINVAL, "scan did not settle (internal)");
     if (h.err_flags & (kErrNoAt | kErrKey | kErrDense | kErrIndex | kErrForeign)) {
         unsigned long long off[2];
         CU(c, cudaMemcpy(off, c->d_err_off, sizeof off, cudaMemcpyDeviceToHost));

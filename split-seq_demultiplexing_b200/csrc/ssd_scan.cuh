@@ -419,7 +419,11 @@ constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kAWarps = 4, kBWarps = kComputeWarps - kAWarps;  // warps 0-3: stage A (bitmap, count, list); warps 4-7: stage B (records)
 constexpr int kAThreads = kAWarps * 32, kBThreads = kBWarps * 32;
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
-constexpr int kScanThreads = kComputeThreads + 64;  // eight compute warps + the copy warp + the prefix warp (works in block 0)
+constexpr int kScanThreads = kComputeThreads + 96;  // eight compute warps + the copy warp + the prefix warp (works in block 0) + the commit warp
+#ifndef SSD_SCAN_STAGE_SLOTS
+#define SSD_SCAN_STAGE_SLOTS 2
+#endif
+constexpr int kStageSlots = SSD_SCAN_STAGE_SLOTS;  // tiles whose records wait (in shared memory) for their record numbers
 
 // Shared memory of one persistent scan block.
 constexpr int kWinChunks = kWin / 16;                    // 16-byte chunks of a window
@@ -427,8 +431,21 @@ constexpr int kChunksPerWarp = kWinChunks / kComputeWarps;  // each compute warp
 constexpr int kRows = (kChunksPerWarp + 31) / 32;        // 32-chunk rows per warp
 static_assert(kWinChunks % kComputeWarps == 0, "window size");
 
+// What stage B found for the records of one tile, parked until the tile's first record number is known.
+struct StageSlot {
+    uint4 mt[kBThreads];                // read 1 / annotated: the record descriptor
+    unsigned long long fp[kBThreads];   // read-id fingerprint
+    unsigned long long ann[kBThreads];  // read 2 / annotated: the annotation word
+    uint32_t s0f[kBThreads];            // offset of the record in the window | flags << 16
+    uint32_t base[kBThreads];           // read 1 / annotated: output length contribution
+};
+constexpr uint32_t kStHave = 1u, kStOk = 2u, kStNoAt = 4u, kStMatched = 8u, kStComplete = 16u;  // flags; the error code of annotated input sits above
+
 struct __align__(128) ScanSmem {
     uint8_t win[kWinSlots][kWin + 128];       // tile windows (bulk-copy destinations)
+    StageSlot stage[kStageSlots];
+    unsigned long long stage_full[kStageSlots], stage_empty[kStageSlots];  // mbarriers: stage B parked a tile / the commit warp wrote it out
+    uint32_t stage_tile[kStageSlots], stage_total[kStageSlots], stage_guess[kStageSlots], stage_flags[kStageSlots];
     uint16_t lstart[kListSlots][kMaxLines];   // line-start lists of the tiles between stage A and stage B
     unsigned long long full[kWinSlots], empty[kWinSlots];  // mbarriers: bytes landed / window may be refilled
     unsigned long long list_full[kListSlots], list_empty[kListSlots];  // mbarriers: stage A done with a tile / stage B done with it
@@ -467,7 +484,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 //                 prefix, so a tile learns its global line index with one poll of its own entry
 //   compute warps stage A(i + kDepth): newline bitmap (kept in registers), count (published), line-start list
 //                 stage B(i)         : poll the line index, process the records that start in the tile
-template <int MODE, typename OffT>
+template <int MODE, typename OffT, bool DEFER>
 __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const __grid_constant__ ScanArgs<OffT> args, const __grid_constant__ DevCfg cfg)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -482,10 +499,110 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             mbar_init(reinterpret_cast<uint64_t*>(&S.list_full[s]), 1);
             mbar_init(reinterpret_cast<uint64_t*>(&S.list_empty[s]), 1);
         }
+        for (int s = 0; s < kStageSlots; s++) {
+            mbar_init(reinterpret_cast<uint64_t*>(&S.stage_full[s]), 1);
+            mbar_init(reinterpret_cast<uint64_t*>(&S.stage_empty[s]), 1);
+        }
     }
     __syncthreads();
     volatile unsigned long long* st = args.status;
 
+    if (warp == kComputeWarps + 2) {
+        // ================================ commit warp ================================
+        // Stage B parks what it found for a tile's records; this warp waits for the tile's line index, checks that stage B
+        // guessed the record phase right, and writes the records out under their numbers (coalesced).  Nothing else in the
+        // block ever waits for the line index.
+        if (!DEFER) return;
+        GlobAcc ga{args.buf, args.len};
+        const uint64_t n_rec_r1 = MODE == kScanR2 ? args.cnt->n_records[0] : 0;
+        for (uint32_t it = 0;; it++) {
+            const uint32_t ss = it % kStageSlots;
+            mbar_wait(reinterpret_cast<uint64_t*>(&S.stage_full[ss]), (it / kStageSlots) & 1u);
+            const uint32_t tile = S.stage_tile[ss];
+            if (tile == kNoTile) break;
+            const uint32_t total = S.stage_total[ss], guess = S.stage_guess[ss], sflags = S.stage_flags[ss];
+            const size_t tile_lo = (size_t)tile * kTile;
+            unsigned long long v = 0;
+            if (lane == 0) {
+                uint32_t ns = 32;
+                while (((v = st[tile]) >> 62) != 2ull) {
+                    __nanosleep(ns);
+                    if (ns < 256u) ns += ns;
+                }
+            }
+            v = __shfl_sync(0xFFFFFFFFu, v, 0);
+            const unsigned long long line_base = (v & kStatusValue) - total;
+            if (tile == args.n_tiles - 1 && lane == 0) {
+                const unsigned long long n_lines = line_base + total + ((sflags & 2u) ? 1ull : 0ull);
+                args.cnt->n_lines[MODE == kScanR2 ? 1 : 0] = n_lines;
+                args.cnt->n_records[MODE == kScanR2 ? 1 : 0] = n_lines >> 2;
+            }
+            const unsigned long long r_first = tile == 0 ? 0ull : (line_base + 4) >> 2;
+            const unsigned long long r_end = ((line_base + total) >> 2) + 1;  // exclusive
+            uint32_t n_rec = r_end > r_first ? (uint32_t)(r_end - r_first) : 0u;
+            if (tile == 0 && args.len == 0) n_rec = 0;
+            if (n_rec > (uint32_t)kMaxRecTile || (sflags & 1u)) {
+                if (lane == 0) atomicOr(&args.cnt->err_flags, kErrDense);
+                n_rec = 0;
+            }
+            const uint32_t j_first = (uint32_t)(4ull * r_first - line_base);
+            const bool good = guess != 0xFFFFFFFFu ? (n_rec == (guess >> 8) && (n_rec == 0u || j_first == (guess & 0xFFu))) : n_rec == 0u;
+            if (!good) {
+                if (lane == 0) atomicOr(&args.cnt->err_flags, kErrRespec);  // the host repeats the scan without guessing
+                n_rec = 0;
+            }
+            const StageSlot& G = S.stage[ss];
+            for (uint32_t i = (uint32_t)lane; i < n_rec; i += 32u) {
+                const uint64_t r = r_first + i;
+                const uint32_t sf = G.s0f[i], s0 = sf & 0xFFFFu, fl = sf >> 16;
+                const bool have = fl & kStHave, ok2 = (fl & kStOk) && r < args.rec_cap;  // beyond the capacity: the exact path raises the overflow flag
+                if (MODE == kScanR1) {
+                    if (ok2) {
+                        if (fl & kStNoAt) raise(args.cnt, args.err_off, 0, kErrNoAt, tile_lo + s0);
+                        args.r1_start[r] = (OffT)(tile_lo + s0);
+                        args.r1_meta[r] = G.mt[i];
+                        args.r1_base[r] = G.base[i];
+                        args.r1_tok[r] = G.fp[i];
+                    } else if (have) {
+                        r1_record_generic(ga, args, r, tile_lo + s0);
+                    }
+                } else if (MODE == kScanAnn) {
+                    if (ok2) {
+                        if (fl >> 8) raise(args.cnt, args.err_off, 0, fl >> 8, tile_lo + s0);
+                        args.r1_start[r] = (OffT)(tile_lo + s0);
+                        args.r1_meta[r] = G.mt[i];
+                        args.r1_base[r] = G.base[i];
+                        args.ann[r] = G.ann[i];
+                    } else if (have) {
+                        const uint64_t an = ann_record_generic(ga, args, cfg, r, tile_lo + s0);
+                        const uint32_t st8 = ann_state(an);
+                        if (st8) atomicAdd(&args.hist[ann_cell(an)], 1u);
+                        if (st8 == 1u) atomicAdd(&args.cnt->n_keys, 1ull);
+                        if (st8 == 2u) atomicAdd(&args.cnt->n_irr, 1ull);
+                    }
+                } else {
+                    if (ok2) {
+                        if (fl & kStNoAt) raise(args.cnt, args.err_off, 1, kErrNoAt, tile_lo + s0);
+                        // V2:349-350: the read-1 mate must carry the same id (fingerprint compare)
+                        if ((fl & kStMatched) && !(r + 1u <= n_rec_r1 && args.r1_tok[r] == G.fp[i])) raise(args.cnt, args.err_off, 1, kErrKey, tile_lo + s0);
+                        if (fl & kStComplete) args.ann[r] = G.ann[i];
+                    } else if (have) {
+                        R2Out o;
+                        bool complete = false;
+                        r2_record_generic(ga, args, cfg, r, tile_lo + s0, o, complete, n_rec_r1);
+                        if (complete) args.ann[r] = o.ann;
+                        const uint32_t st8 = ann_state(o.ann);
+                        if (st8) atomicAdd(&args.hist[ann_cell(o.ann)], 1u);
+                        if (st8 == 1u) atomicAdd(&args.cnt->n_keys, 1ull);
+                        if (st8 == 2u) atomicAdd(&args.cnt->n_irr, 1ull);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.stage_empty[ss]);
+        }
+        return;
+    }
     if (warp == kComputeWarps + 1) {
         // ================================ prefix warp (block 0 only) ================================
         if (blockIdx.x != 0) return;
@@ -539,7 +656,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         for (uint32_t it = 0;; it++) {
             const uint32_t ws = it % kWinSlots;
             if (it >= (uint32_t)kWinSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.empty[ws]), ((it / kWinSlots) - 1u) & 1u);
-#ifdef SSD_SCAN_TICKETS
+#ifndef SSD_SCAN_ROUNDROBIN
             uint32_t t = 0;
             if (lane == 0) t = atomicAdd(&args.cnt->ticket[MODE == kScanR2 ? 1 : 0], 1u);  // tiles are claimed in order
             t = __shfl_sync(0xFFFFFFFFu, t, 0);
@@ -707,7 +824,15 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         PROF_T(t8);
         PROF_ADD(5, t7, t8);
         const uint32_t tile = S.list_tile[ls];
-        if (tile == kNoTile) return false;
+        const uint32_t ss = it % kStageSlots;
+        if (tile == kNoTile) {
+            if (DEFER && it >= (uint32_t)kStageSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.stage_empty[ss]), ((it / kStageSlots) - 1u) & 1u);
+            if (DEFER && tb == 0) {
+                S.stage_tile[ss] = kNoTile;  // the commit warp stops here too
+                mbar_arrive(&S.stage_full[ss]);
+            }
+            return false;
+        }
         const size_t tile_lo = (size_t)tile * kTile;
         const uint32_t win_bytes = (uint32_t)(args.len - tile_lo < (size_t)kWin ? args.len - tile_lo : (size_t)kWin);
         const uint8_t* s_win = S.win[ws];
@@ -1012,6 +1137,54 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                     }
                 }
             }
+        }
+        if (DEFER) {
+            // ---- park the results; the commit warp writes them out once the tile's first record number is known ----
+            const bool guessed = j_guess != 0xFFFFFFFFu && n_guess <= (uint32_t)kBThreads;
+            if (guessed && n_guess != 0u) {
+                compute(my_i, j_guess, n_guess);
+            } else {
+                have = ok = complete = noat = matched = false;
+                err_code = 0;
+                an = 0;
+                o.ann = 0;
+            }
+            if (it >= (uint32_t)kStageSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.stage_empty[ss]), ((it / kStageSlots) - 1u) & 1u);
+            StageSlot& G = S.stage[ss];
+            const uint32_t fl = (have ? kStHave : 0u) | (ok ? kStOk : 0u) | (noat ? kStNoAt : 0u) | (matched ? kStMatched : 0u) |
+                                (complete ? kStComplete : 0u) | (err_code << 8);
+            G.s0f[my_i] = s0 | (fl << 16);
+            G.fp[my_i] = fp;
+            if (MODE != kScanR2) {
+                G.mt[my_i] = mt;
+                G.base[my_i] = base_len;
+            }
+            if (MODE != kScanR1) {
+                // what does not depend on the record number happens here: histogram, key counts
+                const uint64_t a = !ok ? 0ull : (MODE == kScanR2 ? o.ann : an);
+                G.ann[my_i] = a;
+                const uint32_t st8 = ann_state(a);
+                if (st8) atomicAdd(&args.hist[ann_cell(a)], 1u);
+                const uint32_t nreg = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 1u)), nirr = __popc(__ballot_sync(0xFFFFFFFFu, st8 == 2u));
+                if (lane == 0 && nreg) atomicAdd(&args.cnt->n_keys, (unsigned long long)nreg);
+                if (lane == 0 && nirr) atomicAdd(&args.cnt->n_irr, (unsigned long long)nirr);
+            }
+            if (tb == 0) {
+                S.stage_tile[ss] = tile;
+                S.stage_total[ss] = total;
+                S.stage_guess[ss] = guessed ? (j_guess | (n_guess << 8)) : 0xFFFFFFFFu;
+                S.stage_flags[ss] = (n_listed + 1u > (uint32_t)kMaxLines ? 1u : 0u) |
+                                    ((tile == args.n_tiles - 1 && args.len && s_win[win_bytes - 1] != '\n') ? 2u : 0u);
+            }
+            sync_b();
+            PROF_T(t6d);
+            PROF_ADD(4, t8, t6d);
+            if (tb == 0) {
+                mbar_arrive(&S.stage_full[ss]);  // over to the commit warp
+                mbar_arrive(&S.empty[ws]);       // the window may be refilled
+                mbar_arrive(&S.list_empty[ls]);  // and so may the list slot
+            }
+            return true;
         }
         const bool speculate = SSD_SCAN_SPECULATE(MODE) && j_guess != 0xFFFFFFFFu && n_guess != 0u && n_guess <= (uint32_t)kBThreads;
         if (speculate) compute(my_i, j_guess, n_guess);

@@ -330,3 +330,30 @@ def test_group_writer_matches_tiled_writer(ssd, orc, monkeypatch):
     monkeypatch.setenv("SSD_EMIT_GROUPS", "1")
     dm, merged, passing, stats = run_both(ssd, h1, h2, 1, 2)
     assert merged == ref.merged1 and passing == ref.passing
+
+
+def test_scan_without_guessing_matches(ssd, orc, monkeypatch):
+    """SSD_SCAN_NODEFER=1 runs the scan variant that waits for each tile's line index instead of guessing the record
+    phase and parking the results (the variant the library falls back to when a guess is wrong)."""
+    spec = ssd.synth_spec(WL, 50000, seed=21, cell_pool=500)
+    h1, h2 = ssd.synth_host(spec)
+    ref = orc.demultiplex(h1, h2, WL, 1, 2)
+    monkeypatch.setenv("SSD_SCAN_NODEFER", "1")
+    dm, merged, passing, stats = run_both(ssd, h1, h2, 1, 2)
+    assert merged == ref.merged1 and passing == ref.passing
+    assert dm.record_cells().tolist() == ref.rec_cell
+
+
+def test_misleading_lines_repeat_the_scan(ssd, orc):
+    """Quality lines that start with '@' followed two lines later by a read that starts with '+' cannot be told from a
+    record start inside one tile: the guess fails, the library repeats the scan without guessing, results stay exact."""
+    recs1, recs2 = [], []
+    for i in range(6000):
+        s2 = "ACGTACGTAC" + WL[i % 96] + fu.LINKER_3_2 + WL[(i * 5) % 96] + fu.LINKER_2_1 + WL[(i * 11) % 96] + "ACGT" * 10
+        q2 = "@" + "F" * (len(s2) - 1)
+        recs2.append("@M.%d\n%s\n+\n%s\n" % (i, s2, q2))
+        recs1.append("@M.%d\n%s\n+\n%s\n" % (i, "+" + "ACGT" * 20, "@" + "E" * 80))
+    r1, r2 = "".join(recs1).encode(), "".join(recs2).encode()
+    ref = orc.demultiplex(r1, r2, WL, 1, 1)
+    dm, merged, passing, stats = run_both(ssd, r1, r2, 1, 1)
+    assert merged == ref.merged1 and passing == ref.passing and stats["n_matched"] == ref.n_matched
