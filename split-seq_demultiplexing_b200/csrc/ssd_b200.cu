@@ -218,6 +218,47 @@ int radix_sort64(ssd_ctx* c, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* v
     return SSD_OK;
 }
 
+// LSD radix sort of 64-bit keys over bits [0, bits), one kernel per 8-bit digit (ssd_onesweep.cuh).  from_ann: the keys are
+// the regular (cell, UMI) keys of the batch's annotation words (n_keys of them), a and b are only buffers; otherwise a holds
+// the keys.  *sorted is whichever of a / b the result ended up in.
+int os_sort64(ssd_ctx* c, bool from_ann, uint64_t* a, uint64_t* b, uint64_t n_keys, int bits, uint64_t** sorted)
+{
+    *sorted = a;
+    if (n_keys == 0) return SSD_OK;
+    const int passes = std::max(1, (bits + kOsBits - 1) / kOsBits);
+    if (passes > kOsMaxPasses || n_keys > (uint64_t)kOsValue) return fail(c, SSD_ERANGE, "key space too large for the radix sort");
+    const uint64_t n_first = from_ann ? c->n_rec_r2 : n_keys;
+    const uint64_t tiles_first = (n_first + kOsTile - 1) / kOsTile, tiles_next = (n_keys + kOsTile - 1) / kOsTile;
+    const size_t head_words = (size_t)kOsMaxPasses * kOsRadix + 64;  // histograms, then one ticket per pass
+    const size_t status_words = (size_t)(tiles_first + (uint64_t)(passes - 1) * tiles_next) * kOsRadix;
+    OKR(ensure(c, c->b_os, (head_words + status_words) * sizeof(uint32_t)));
+    uint32_t* ghist = (uint32_t*)c->b_os.p;
+    uint32_t* ticket = ghist + (size_t)kOsMaxPasses * kOsRadix;
+    uint32_t* status = ghist + head_words;
+    CU(c, cudaMemsetAsync(c->b_os.p, 0, (head_words + status_words) * sizeof(uint32_t), c->stream));
+    const uint32_t hist_blocks = (uint32_t)std::min<uint64_t>(blocks_for(n_first, kThreads), 148 * 8);
+    uint64_t *src = a, *dst = b;
+    if (from_ann) {
+        const KeysFromAnn ka{(const uint64_t*)c->b_ann.p, c->dcfg.umi_bits};
+        k_os_hist<KeysFromAnn><<<hist_blocks, kThreads, 0, c->stream>>>(ka, n_first, passes, ghist);
+        k_os_pass<KeysFromAnn><<<(uint32_t)tiles_first, kThreads, 0, c->stream>>>(ka, n_first, 0, a, ghist, status, ticket);
+    } else {
+        k_os_hist<KeysArray><<<hist_blocks, kThreads, 0, c->stream>>>(KeysArray{a}, n_first, passes, ghist);
+        k_os_pass<KeysArray><<<(uint32_t)tiles_first, kThreads, 0, c->stream>>>(KeysArray{a}, n_first, 0, b, ghist, status, ticket);
+        std::swap(src, dst);
+    }
+    status += tiles_first * kOsRadix;
+    for (int p = 1; p < passes; p++) {
+        k_os_pass<KeysArray><<<(uint32_t)tiles_next, kThreads, 0, c->stream>>>(KeysArray{src}, n_keys, p * kOsBits, dst, ghist + (size_t)p * kOsRadix, status, ticket + p);
+        status += tiles_next * kOsRadix;
+        std::swap(src, dst);
+    }
+    c->n_launches += 1 + passes;
+    CU(c, cudaGetLastError());
+    *sorted = src;
+    return SSD_OK;
+}
+
 // sort + unique of regular keys.  `keys` holds n keys (or, when from_ann, the keys are taken from the
 // annotation words of the batch and `keys` only is the buffer they are compacted into by the first pass);
 // result: *uniq (a context buffer or `keys`), *n_uniq
@@ -230,19 +271,7 @@ int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint3
     OKR(ensure(c, c->b_keys_alt, n * sizeof(uint64_t)));
     uint64_t* sorted = nullptr;
     const int bits = c->dcfg.umi_bits + c->dcfg.cell_bits;
-    if (from_ann) {
-        // pass 1 reads the annotations of all records, drops what is not a regular key, lands n keys in b_keys_alt
-        OKR((radix_pass<KeysFromAnn, false>(c, KeysFromAnn{(const uint64_t*)c->b_ann.p, c->dcfg.umi_bits}, c->n_rec_r2, 0,
-                                            (uint64_t*)c->b_keys_alt.p, nullptr, nullptr)));
-        uint64_t *a = (uint64_t*)c->b_keys_alt.p, *b = keys;
-        for (int bit = kRadixBits; bit < bits; bit += kRadixBits) {
-            OKR((radix_pass<KeysArray, false>(c, KeysArray{a}, n, bit, b, nullptr, nullptr)));
-            std::swap(a, b);
-        }
-        sorted = a;
-    } else {
-        OKR(radix_sort64<false>(c, keys, (uint64_t*)c->b_keys_alt.p, nullptr, nullptr, n, bits, &sorted, nullptr));
-    }
+    OKR(os_sort64(c, from_ann, keys, (uint64_t*)c->b_keys_alt.p, n, bits, &sorted));
     uint64_t* other = sorted == keys ? (uint64_t*)c->b_keys_alt.p : keys;
     OKR(ensure(c, c->b_pos, (n + 1) * sizeof(uint32_t)));
     uint32_t* pos = (uint32_t*)c->b_pos.p;
@@ -372,31 +401,12 @@ int distinct_counts_local(ssd_ctx* c)
         if (side) CU(c, cudaEventRecord(c->ev_join, st));
     }
     if (n_keys) {
-        const int bits = c->dcfg.umi_bits + c->dcfg.cell_bits;
-        const int passes = (bits + kOsBits - 1) / kOsBits;
-        if (passes > kOsMaxPasses || n_keys > (uint64_t)kOsValue) return fail(c, SSD_ERANGE, "key space too large for the radix sort");
-        const uint64_t tiles_first = (n_rec + kOsTile - 1) / kOsTile, tiles_next = (n_keys + kOsTile - 1) / kOsTile;
-        const size_t head_words = (size_t)kOsMaxPasses * kOsRadix + 64;  // histograms, then one ticket per pass
-        const size_t status_words = (size_t)(tiles_first + (uint64_t)(passes - 1) * tiles_next) * kOsRadix;
-        OKR(ensure(c, c->b_os, (head_words + status_words) * sizeof(uint32_t)));
         OKR(ensure(c, c->b_keys, n_keys * sizeof(uint64_t)));
         OKR(ensure(c, c->b_keys_alt, n_keys * sizeof(uint64_t)));
-        uint32_t* ghist = (uint32_t*)c->b_os.p;
-        uint32_t* ticket = ghist + (size_t)kOsMaxPasses * kOsRadix;
-        uint32_t* status = ghist + head_words;
-        CU(c, cudaMemsetAsync(c->b_os.p, 0, (head_words + status_words) * sizeof(uint32_t), c->stream));
-        const KeysFromAnn from_ann{ann, c->dcfg.umi_bits};
-        k_os_hist<KeysFromAnn><<<(uint32_t)std::min<uint64_t>(blocks_for(n_rec, kThreads), 148 * 8), kThreads, 0, c->stream>>>(from_ann, n_rec, passes, ghist);
-        uint64_t *a = (uint64_t*)c->b_keys.p, *b = (uint64_t*)c->b_keys_alt.p;
-        k_os_pass<KeysFromAnn><<<(uint32_t)tiles_first, kThreads, 0, c->stream>>>(from_ann, n_rec, 0, a, ghist, status, ticket);
-        status += tiles_first * kOsRadix;
-        for (int p = 1; p < passes; p++) {
-            k_os_pass<KeysArray><<<(uint32_t)tiles_next, kThreads, 0, c->stream>>>(KeysArray{a}, n_keys, p * kOsBits, b, ghist + (size_t)p * kOsRadix, status, ticket + p);
-            status += tiles_next * kOsRadix;
-            std::swap(a, b);
-        }
-        k_count_sorted<<<blocks_for(n_keys, kThreads), kThreads, 0, c->stream>>>(a, n_keys, c->dcfg.umi_bits, c->d_distinct);
-        c->n_launches += 2 + passes;
+        uint64_t* sorted = nullptr;
+        OKR(os_sort64(c, true, (uint64_t*)c->b_keys.p, (uint64_t*)c->b_keys_alt.p, n_keys, c->dcfg.umi_bits + c->dcfg.cell_bits, &sorted));
+        k_count_sorted<<<blocks_for(n_keys, kThreads), kThreads, 0, c->stream>>>(sorted, n_keys, c->dcfg.umi_bits, c->d_distinct);
+        c->n_launches++;
     }
     if (side) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     CU(c, cudaGetLastError());

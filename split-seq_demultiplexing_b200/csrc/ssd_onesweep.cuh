@@ -13,6 +13,9 @@
 
 namespace ssd {
 
+#ifndef SSD_OS_MINBLOCKS
+#define SSD_OS_MINBLOCKS 4
+#endif
 constexpr int kOsBits = 8;
 constexpr int kOsRadix = 1 << kOsBits;
 constexpr int kOsItems = 16;
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(kThreads) k_os_hist(Src keys, uint64_t n, int 
 
 // one pass: stable scatter of the keys by the digit at `shift`
 template <class Src>
-__global__ void __launch_bounds__(kThreads) k_os_pass(Src keys_in, uint64_t n, int shift, uint64_t* keys_out, const uint32_t* ghist,
+__global__ void __launch_bounds__(kThreads, SSD_OS_MINBLOCKS) k_os_pass(Src keys_in, uint64_t n, int shift, uint64_t* keys_out, const uint32_t* ghist,
                                                       uint32_t* status, uint32_t* ticket)
 {
     __shared__ uint64_t s_keys[kOsTile];
