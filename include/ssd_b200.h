@@ -129,6 +129,15 @@ int ssd_local_unique_keys(ssd_ctx *ctx, uint64_t **d_keys, uint64_t *n_keys, voi
  * after an all-to-all by cell range); they are sorted in place. */
 int ssd_count_distinct(ssd_ctx *ctx, uint64_t *d_keys, uint64_t n_keys, void *d_irregular,
                        uint64_t n_irregular);
+/* Multi-GPU hosts, the cheaper exchange: this batch's (cell,UMI) keys WITH their duplicates, regular keys grouped by
+ * the rank that owns their cell (one partition pass instead of a sort): owner k's keys are
+ * (*d_keys)[offsets[k] .. offsets[k + 1]), offsets has world + 1 entries (host).  Irregular keys come back as an
+ * unordered list; the caller routes them with ssd_owner_layout.  The arrays stay owned by the context.
+ * Replaces the set-union of per-chunk UMI sets the reference gets for free from its single results file (V2:404-411). */
+int ssd_partition_keys(ssd_ctx *ctx, int world, uint64_t **d_keys, uint64_t *offsets, void **d_irregular,
+                       uint64_t *n_irregular);
+/* Owner rank of a cell in a world of W ranks: ((cell >> *shift) * W) / *n_buckets. */
+int ssd_owner_layout(const ssd_ctx *ctx, int *shift, int *n_buckets);
 /* Bit width of the 2-bit-packed UMI inside a regular key (cell id = key >> umi_bits). */
 int ssd_key_layout(const ssd_ctx *ctx, int *umi_bits, int *cell_bits);
 

@@ -240,10 +240,10 @@ int os_sort64(ssd_ctx* c, bool from_ann, uint64_t* a, uint64_t* b, uint64_t n_ke
     uint64_t *src = a, *dst = b;
     if (from_ann) {
         const KeysFromAnn ka{(const uint64_t*)c->b_ann.p, c->dcfg.umi_bits};
-        k_os_hist<KeysFromAnn><<<hist_blocks, kThreads, 0, c->stream>>>(ka, n_first, passes, ghist);
+        k_os_hist<KeysFromAnn><<<hist_blocks, kThreads, 0, c->stream>>>(ka, n_first, passes, ghist, 0);
         k_os_pass<KeysFromAnn><<<(uint32_t)tiles_first, kThreads, 0, c->stream>>>(ka, n_first, 0, a, ghist, status, ticket);
     } else {
-        k_os_hist<KeysArray><<<hist_blocks, kThreads, 0, c->stream>>>(KeysArray{a}, n_first, passes, ghist);
+        k_os_hist<KeysArray><<<hist_blocks, kThreads, 0, c->stream>>>(KeysArray{a}, n_first, passes, ghist, 0);
         k_os_pass<KeysArray><<<(uint32_t)tiles_first, kThreads, 0, c->stream>>>(KeysArray{a}, n_first, 0, b, ghist, status, ticket);
         std::swap(src, dst);
     }
@@ -378,26 +378,64 @@ int count_cells(ssd_ctx* c, const uint64_t* uniq, uint64_t n_uniq, const IrrKey*
 // Per-cell distinct-UMI counts of the batch straight from the annotation words (single GPU: no unique-key lists, no
 // host round trip).  Regular keys: one-kernel-per-pass radix sort + first-occurrence count; irregular keys: hash set
 // on the side stream.
-int distinct_counts_local(ssd_ctx* c)
+// hash set of irregular keys on `st`: from the batch's annotation words (keys == nullptr) or from an array of n keys
+int irr_hash_counts(ssd_ctx* c, const IrrKey* keys, uint64_t n, cudaStream_t st)
+{
+    if (n == 0) return SSD_OK;
+    uint64_t slots = 1024;
+    while (slots < 2 * n) slots <<= 1;
+    if (slots > (1ull << 32)) return fail(c, SSD_ERANGE, "too many irregular UMIs in one batch");
+    OKR(ensure(c, c->b_irr_table, slots * sizeof(ulonglong2)));
+    CU(c, cudaMemsetAsync(c->b_irr_table.p, 0, slots * sizeof(ulonglong2), st));
+    if (keys) k_irr_hash_keys<<<blocks_for(n, kThreads), kThreads, 0, st>>>(keys, n, (ulonglong2*)c->b_irr_table.p, (uint32_t)(slots - 1), c->d_distinct);
+    else k_irr_hash<<<blocks_for(c->n_rec_r2, kThreads), kThreads, 0, st>>>((const uint64_t*)c->b_ann.p, c->n_rec_r2, c->r2, (ulonglong2*)c->b_irr_table.p,
+                                                                              (uint32_t)(slots - 1), c->d_distinct);
+    c->n_launches++;
+    CU(c, cudaGetLastError());
+    return SSD_OK;
+}
+
+// Per-cell distinct counts of arbitrary key arrays (duplicates allowed; d_keys is reordered): what a rank does with the
+// keys its peers sent for the cells it owns.
+int distinct_counts_arrays(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys, const IrrKey* d_irr, uint64_t n_irr)
 {
     CU(c, cudaMemsetAsync(c->d_distinct, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
-    const uint64_t n_rec = c->n_rec_r2, n_keys = c->n_keys, n_irr = c->n_irr;
-    const uint64_t* ann = (const uint64_t*)c->b_ann.p;
     const bool side = n_irr != 0 && c->side_stream != nullptr;
     if (n_irr) {
-        uint64_t slots = 1024;
-        while (slots < 2 * n_irr) slots <<= 1;
-        if (slots > (1ull << 32)) return fail(c, SSD_ERANGE, "too many irregular UMIs in one batch");
-        OKR(ensure(c, c->b_irr_table, slots * sizeof(ulonglong2)));
         cudaStream_t st = c->stream;
         if (side) {
             CU(c, cudaEventRecord(c->ev_fork, c->stream));
             CU(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
             st = c->side_stream;
         }
-        CU(c, cudaMemsetAsync(c->b_irr_table.p, 0, slots * sizeof(ulonglong2), st));
-        k_irr_hash<<<blocks_for(n_rec, kThreads), kThreads, 0, st>>>(ann, n_rec, c->r2, (ulonglong2*)c->b_irr_table.p, (uint32_t)(slots - 1), c->d_distinct);
+        OKR(irr_hash_counts(c, d_irr, n_irr, st));
+        if (side) CU(c, cudaEventRecord(c->ev_join, st));
+    }
+    if (n_keys) {
+        OKR(ensure(c, c->b_keys_alt, n_keys * sizeof(uint64_t)));
+        uint64_t* sorted = nullptr;
+        OKR(os_sort64(c, false, d_keys, (uint64_t*)c->b_keys_alt.p, n_keys, c->dcfg.umi_bits + c->dcfg.cell_bits, &sorted));
+        k_count_sorted<<<blocks_for(n_keys, kThreads), kThreads, 0, c->stream>>>(sorted, n_keys, c->dcfg.umi_bits, c->d_distinct);
         c->n_launches++;
+    }
+    if (side) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    CU(c, cudaGetLastError());
+    return SSD_OK;
+}
+
+int distinct_counts_local(ssd_ctx* c)
+{
+    CU(c, cudaMemsetAsync(c->d_distinct, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
+    const uint64_t n_keys = c->n_keys, n_irr = c->n_irr;
+    const bool side = n_irr != 0 && c->side_stream != nullptr;
+    if (n_irr) {
+        cudaStream_t st = c->stream;
+        if (side) {
+            CU(c, cudaEventRecord(c->ev_fork, c->stream));
+            CU(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+            st = c->side_stream;
+        }
+        OKR(irr_hash_counts(c, nullptr, n_irr, st));
         if (side) CU(c, cudaEventRecord(c->ev_join, st));
     }
     if (n_keys) {
@@ -878,6 +916,77 @@ extern "C" int ssd_local_unique_keys(ssd_ctx* c, uint64_t** d_keys, uint64_t* n_
     return SSD_OK;
 }
 
+namespace {
+// buckets of the owner partition: cell >> shift, at most 256 of them
+void owner_layout(const ssd_ctx* c, int* shift, int* n_buckets)
+{
+    int s = 0;
+    while (((c->n_cells_total - 1) >> s) >= (uint64_t)kOsRadix) s++;
+    *shift = s;
+    *n_buckets = (int)((c->n_cells_total - 1) >> s) + 1;
+}
+}  // namespace
+
+extern "C" int ssd_owner_layout(const ssd_ctx* c, int* shift, int* n_buckets)
+{
+    if (!c) return SSD_EINVAL;
+    int s, nb;
+    owner_layout(c, &s, &nb);
+    if (shift) *shift = s;
+    if (n_buckets) *n_buckets = nb;
+    return SSD_OK;
+}
+
+extern "C" int ssd_partition_keys(ssd_ctx* c, int world, uint64_t** d_keys, uint64_t* offsets, void** d_irregular, uint64_t* n_irregular)
+{
+    if (!c || world < 1 || !offsets) return SSD_EINVAL;
+    if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_partition_keys before ssd_demux_device");
+    CU(c, cudaSetDevice(c->device));
+    StageTimer t(c, 2);
+    c->unique_done = false;
+    int shift, nb;
+    owner_layout(c, &shift, &nb);
+    const uint64_t n_keys = c->n_keys, n_rec = c->n_rec_r2;
+    uint32_t hist[kOsRadix] = {0};
+    if (n_keys) {
+        // one scatter pass on the bucket digit: keys come out grouped by bucket, hence by owner
+        const uint64_t tiles = (n_rec + kOsTile - 1) / kOsTile;
+        const size_t head_words = (size_t)kOsMaxPasses * kOsRadix + 64, status_words = (size_t)tiles * kOsRadix;
+        OKR(ensure(c, c->b_os, (head_words + status_words) * sizeof(uint32_t)));
+        OKR(ensure(c, c->b_keys, n_keys * sizeof(uint64_t)));
+        uint32_t* ghist = (uint32_t*)c->b_os.p;
+        CU(c, cudaMemsetAsync(c->b_os.p, 0, (head_words + status_words) * sizeof(uint32_t), c->stream));
+        const KeysFromAnn ka{(const uint64_t*)c->b_ann.p, c->dcfg.umi_bits};
+        const int sh = c->dcfg.umi_bits + shift;
+        k_os_hist<KeysFromAnn><<<(uint32_t)std::min<uint64_t>(blocks_for(n_rec, kThreads), 148 * 8), kThreads, 0, c->stream>>>(ka, n_rec, 1, ghist, sh);
+        k_os_pass<KeysFromAnn><<<(uint32_t)tiles, kThreads, 0, c->stream>>>(ka, n_rec, sh, (uint64_t*)c->b_keys.p, ghist, ghist + head_words,
+                                                                              ghist + (size_t)kOsMaxPasses * kOsRadix);
+        c->n_launches += 2;
+        CU(c, cudaMemcpyAsync(hist, ghist, sizeof hist, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (c->n_irr) {
+        unsigned long long* cursor = (unsigned long long*)c->d_err_off;  // free after phase 1 (errors were read)
+        OKR(ensure(c, c->b_irr, c->n_irr * sizeof(IrrKey)));
+        CU(c, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), c->stream));
+        k_collect_irr<<<blocks_for(n_rec, kThreads), kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, n_rec, c->r2, (IrrKey*)c->b_irr.p, cursor);
+        c->n_launches++;
+    }
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(c->stream));
+    uint64_t run = 0;
+    int b = 0;
+    for (int k = 0; k < world; k++) {
+        offsets[k] = run;
+        for (; b < nb && (uint64_t)b * (uint64_t)world / (uint64_t)nb == (uint64_t)k; b++) run += hist[b];
+    }
+    offsets[world] = run;
+    if (run != n_keys) return fail(c, SSD_EINVAL, "key partition lost keys (internal)");
+    if (d_keys) *d_keys = (uint64_t*)c->b_keys.p;
+    if (d_irregular) *d_irregular = c->b_irr.p;
+    if (n_irregular) *n_irregular = c->n_irr;
+    return SSD_OK;
+}
+
 extern "C" int ssd_count_distinct(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys, void* d_irregular, uint64_t n_irregular)
 {
     if (!c) return SSD_EINVAL;
@@ -892,7 +1001,7 @@ extern "C" int ssd_count_distinct(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys,
         nui = c->n_uniq_irr;
     } else {
         c->unique_done = false;  // the context's buffers are reused as scratch below
-        OKR(sort_unique_both(c, d_keys, n_keys, (IrrKey*)d_irregular, n_irregular, false, &uk, &nuk, &ui, &nui));
+        return distinct_counts_arrays(c, d_keys, n_keys, (const IrrKey*)d_irregular, n_irregular);
     }
     return count_cells(c, uk, nuk, ui, nui);
 }

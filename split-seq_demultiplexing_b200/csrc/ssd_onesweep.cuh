@@ -26,7 +26,7 @@ static_assert(kThreads == kOsRadix, "one thread per digit");
 
 // digit histograms of all passes in one read of the keys
 template <class Src>
-__global__ void __launch_bounds__(kThreads) k_os_hist(Src keys, uint64_t n, int passes, uint32_t* ghist)
+__global__ void __launch_bounds__(kThreads) k_os_hist(Src keys, uint64_t n, int passes, uint32_t* ghist, int shift0)
 {
     __shared__ uint32_t s_h[kOsMaxPasses][kOsRadix];
     for (int j = threadIdx.x; j < kOsMaxPasses * kOsRadix; j += kThreads) (&s_h[0][0])[j] = 0;
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kThreads) k_os_hist(Src keys, uint64_t n, int 
         if (k != kNoKey) {
 #pragma unroll
             for (int p = 0; p < kOsMaxPasses; p++)
-                if (p < passes) atomicAdd(&s_h[p][(uint32_t)(k >> (kOsBits * p)) & (kOsRadix - 1)], 1u);
+                if (p < passes) atomicAdd(&s_h[p][(uint32_t)(k >> (shift0 + kOsBits * p)) & (kOsRadix - 1)], 1u);
         }
     }
     __syncthreads();
@@ -178,6 +178,29 @@ __device__ __forceinline__ void cas128(void* p, unsigned long long cmp_lo, unsig
         : "memory");
 }
 
+// insert one irregular key; true when it was not in the set yet
+__device__ __forceinline__ bool irr_insert(ulonglong2* table, uint32_t slot_mask, uint64_t hi, uint64_t lo)
+{
+    hi |= 1ull << 63;  // never all zero: zero means empty
+    unsigned long long h = (hi ^ (lo * 0x9E3779B97F4A7C15ull)) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 31;
+    for (uint32_t s = (uint32_t)h & slot_mask;; s = (s + 1u) & slot_mask) {
+        unsigned long long olo, ohi;
+        cas128(&table[s], 0ull, 0ull, lo, hi, olo, ohi);
+        if (olo == 0ull && ohi == 0ull) return true;
+        if (olo == lo && ohi == hi) return false;
+    }
+}
+
+// irregular keys given as an array (what peers sent): distinct[cell] += first occurrences
+__global__ void __launch_bounds__(kThreads) k_irr_hash_keys(const IrrKey* keys, uint64_t n, ulonglong2* table, uint32_t slot_mask, uint32_t* distinct)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const IrrKey k = keys[i];
+    if (irr_insert(table, slot_mask, k.hi, k.lo)) atomicAdd(&distinct[(uint32_t)(k.hi >> kIrrCellShift) & (uint32_t)kAnnCellMask], 1u);
+}
+
 // table: slots of {lo, hi | 1 << 63}, zero = empty; n_slots is a power of two >= 2 * (number of irregular records)
 __global__ void __launch_bounds__(kThreads) k_irr_hash(const uint64_t* ann, uint64_t n, const uint8_t* r2buf, ulonglong2* table, uint32_t slot_mask,
                                                        uint32_t* distinct)
@@ -196,18 +219,8 @@ __global__ void __launch_bounds__(kThreads) k_irr_hash(const uint64_t* ann, uint
         else lo |= c << (8 * (9 - j));
     }
     const uint32_t cell = ann_cell(a);
-    hi |= ((uint64_t)cell << kIrrCellShift) | ((uint64_t)ulen << 32) | (1ull << 63);
-    unsigned long long h = (hi ^ (lo * 0x9E3779B97F4A7C15ull)) * 0xFF51AFD7ED558CCDull;
-    h ^= h >> 31;
-    for (uint32_t s = (uint32_t)h & slot_mask;; s = (s + 1u) & slot_mask) {
-        unsigned long long olo, ohi;
-        cas128(&table[s], 0ull, 0ull, lo, hi, olo, ohi);
-        if (olo == 0ull && ohi == 0ull) {  // first time this (cell, UMI) is seen
-            atomicAdd(&distinct[cell], 1u);
-            return;
-        }
-        if (olo == lo && ohi == hi) return;
-    }
+    hi |= ((uint64_t)cell << kIrrCellShift) | ((uint64_t)ulen << 32);
+    if (irr_insert(table, slot_mask, hi, lo)) atomicAdd(&distinct[cell], 1u);  // first time this (cell, UMI) is seen
 }
 
 }  // namespace ssd

@@ -92,6 +92,9 @@ _SIGS = {
     "ssd_local_unique_keys": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "ssd_count_distinct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "ssd_key_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ssd_owner_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ssd_partition_keys": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_uint64)]),
     "ssd_build_filter": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "ssd_filter_single": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "ssd_emit_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -1,10 +1,12 @@
 """Multi-GPU orchestration: one process per GPU (torch.distributed), reads sharded by record range.
 
 The per-cell READ counts are additive, so they are all-reduced (NCCL over NVLink).  The reference's -m, however,
-counts DISTINCT UMIs per cell (V2:411), which is not additive across shards: every rank therefore sorts and
-deduplicates its own (cell, UMI) keys, the keys are exchanged all-to-all by CELL RANGE (rank k owns cells
-[k * ceil(C / W), (k + 1) * ceil(C / W))), every rank counts the distinct keys of the cells it owns, and those
-counts (zero elsewhere) are all-reduced so that all ranks hold the same, exact, global table.
+counts DISTINCT UMIs per cell (V2:411), which is not additive across shards: every rank groups its (cell, UMI) keys
+by the rank that OWNS their cell (one partition pass on the device, duplicates kept), the groups are exchanged
+all-to-all, every rank sorts what it received and counts the distinct keys of the cells it owns, and those counts
+(zero elsewhere) are all-reduced so that all ranks hold the same, exact, global table.  (exchange_keys, the first
+version, exchanges locally sorted + deduplicated keys by contiguous cell range; it is kept for hosts that want the
+unique lists.)
 
 The functions below only use torch ops + collectives on whatever device the tensors live on, so the exchange logic
 is exercised on CPU with the gloo backend in tests/test_distributed_gloo.py.
@@ -50,6 +52,37 @@ def exchange_keys(keys, irr, n_cells_total: int, world: int, umi_bits: int, grou
     return rk, ri
 
 
+def owner_of_cells(cells, shift: int, n_buckets: int, world: int):
+    """Owner rank of each cell id (int64 tensor): ((cell >> shift) * world) // n_buckets, as the library partitions."""
+    return ((cells >> shift) * world) // n_buckets
+
+
+def group_by_owner(rows, cells, shift: int, n_buckets: int, world: int):
+    """Reorder `rows` (first dimension) so that the rows of owner 0 come first, then owner 1, ...; returns the
+    reordered rows and the per-owner counts (int64[world])."""
+    import torch
+    owner = owner_of_cells(cells, shift, n_buckets, world)
+    order = torch.argsort(owner, stable=True)
+    counts = torch.bincount(owner, minlength=world)[:world] if owner.numel() else torch.zeros(world, dtype=torch.int64, device=rows.device)
+    return rows[order].contiguous(), counts
+
+
+def exchange_raw(keys, key_counts, irr, irr_counts, group=None):
+    """All-to-all of keys already grouped by owner rank.  keys: int64[n], key_counts: int64[world]; irr: int64[m, 2],
+    irr_counts: int64[world].  Returns what the peers sent this rank (regular, irregular)."""
+    import torch
+    import torch.distributed as dist
+    send = torch.stack([key_counts, irr_counts], dim=1).contiguous()  # [world, 2]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    send_l, recv_l = send.cpu().tolist(), recv.cpu().tolist()
+    rk = torch.empty(sum(r[0] for r in recv_l), dtype=torch.int64, device=keys.device)
+    dist.all_to_all_single(rk, keys.contiguous(), [r[0] for r in recv_l], [s[0] for s in send_l], group=group)
+    ri = torch.empty((sum(r[1] for r in recv_l), 2), dtype=torch.int64, device=keys.device)
+    dist.all_to_all_single(ri, irr.contiguous(), [r[1] for r in recv_l], [s[1] for s in send_l], group=group)
+    return rk, ri
+
+
 def global_filter(dm, world: int, group=None) -> dict:
     """After dm.demux_device(...) on every rank: make the -m decision global and exact, return dm's stats.
     Collectives: all-reduce of the read histogram, all-to-all of the unique keys, all-reduce of the distinct table."""
@@ -57,8 +90,12 @@ def global_filter(dm, world: int, group=None) -> dict:
     if world > 1:
         dist.all_reduce(dm.reads_histogram(), group=group)
         if dm.filter_mode == "distinct_umi":
-            keys, irr = dm.local_unique_keys()
-            rk, ri = exchange_keys(keys, irr, dm.n_cells_total, world, dm.umi_bits, group=group)
+            import torch
+            keys, offsets, irr = dm.partition_keys(world)
+            shift, n_buckets = dm.owner_layout()
+            key_counts = torch.tensor([offsets[k + 1] - offsets[k] for k in range(world)], dtype=torch.int64, device=keys.device)
+            irr, irr_counts = group_by_owner(irr, irr[:, 0] >> IRR_CELL_SHIFT, shift, n_buckets, world)
+            rk, ri = exchange_raw(keys, key_counts, irr, irr_counts, group=group)
             dm.count_distinct(rk, ri)
             dist.all_reduce(dm.distinct_histogram(), group=group)
         return dm.build_filter()

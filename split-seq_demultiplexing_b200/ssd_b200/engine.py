@@ -133,6 +133,26 @@ class Demultiplexer:
                if ni.value else torch.empty((0, 2), dtype=torch.int64, device="cuda"))
         return keys, irr
 
+    def owner_layout(self):
+        """(shift, n_buckets): the rank that owns a cell in a world of W ranks is ((cell >> shift) * W) // n_buckets."""
+        sh, nb = C.c_int(), C.c_int()
+        self._check(self.lib.ssd_owner_layout(self._ctx, C.byref(sh), C.byref(nb)))
+        return sh.value, nb.value
+
+    def partition_keys(self, world: int):
+        """This batch's (cell,UMI) keys with duplicates, as torch views: int64[n] grouped by owner rank, the world + 1
+        offsets of the groups (list), and the irregular keys int64[n_irr, 2] in no particular order."""
+        import torch
+        pk, pi, ni = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        offs = (C.c_uint64 * (world + 1))()
+        self._check(self.lib.ssd_partition_keys(self._ctx, world, C.byref(pk), offs, C.byref(pi), C.byref(ni)))
+        offsets = list(offs)
+        nk = offsets[-1]
+        keys = torch.as_tensor(_DevArray(pk.value, nk, "<i8", self), device="cuda") if nk else torch.empty(0, dtype=torch.int64, device="cuda")
+        irr = (torch.as_tensor(_DevArray(pi.value, 2 * ni.value, "<i8", self), device="cuda").view(-1, 2)
+               if ni.value else torch.empty((0, 2), dtype=torch.int64, device="cuda"))
+        return keys, offsets, irr
+
     def count_distinct(self, keys, irr):
         """Per-cell distinct counts from int64 key tensors (any order, duplicates allowed; reordered in place)."""
         self._check(self.lib.ssd_count_distinct(self._ctx, C.c_void_p(keys.data_ptr() if keys.numel() else 0), keys.numel(),

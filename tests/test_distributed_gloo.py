@@ -73,6 +73,49 @@ def test_exchange_by_cell_range(tmp_path, world):
     assert (tables[0] == want).all()
 
 
+def _worker_raw(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ssd_b200 import distributed as D
+    shift, n_buckets = 12, ((N_CELLS - 1) >> 12) + 1   # what ssd_owner_layout returns for 96^3 cells
+    rng = np.random.default_rng(500 + rank)
+    keys, irr = _make_keys(100 + rank)
+    keys = np.concatenate([keys, rng.choice(keys, size=5000)])   # raw keys: duplicates, no order
+    rng.shuffle(keys)
+    irr = np.concatenate([irr, irr[rng.integers(0, len(irr), size=200)]])
+    k, kc = D.group_by_owner(torch.from_numpy(keys), torch.from_numpy(keys) >> UMI_BITS, shift, n_buckets, world)
+    i, ic = D.group_by_owner(torch.from_numpy(irr), torch.from_numpy(irr)[:, 0] >> 36, shift, n_buckets, world)
+    rk, ri = D.exchange_raw(k, kc, i, ic)
+    assert bool((D.owner_of_cells(rk >> UMI_BITS, shift, n_buckets, world) == rank).all())
+    assert ri.numel() == 0 or bool((D.owner_of_cells(ri[:, 0] >> 36, shift, n_buckets, world) == rank).all())
+    distinct = torch.zeros(N_CELLS, dtype=torch.int32)
+    uk = torch.unique(rk)
+    distinct.index_add_(0, (uk >> UMI_BITS), torch.ones(uk.numel(), dtype=torch.int32))
+    if ri.numel():
+        ui = torch.unique(ri, dim=0)
+        distinct.index_add_(0, (ui[:, 0] >> 36), torch.ones(ui.shape[0], dtype=torch.int32))
+    dist.all_reduce(distinct)
+    np.save(os.path.join(out_dir, "distinct_%d.npy" % rank), distinct.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_raw_keys_by_owner(tmp_path, world):
+    """The exchange the GPU path uses: raw keys (duplicates kept) grouped by owner rank, owners interleaved by bucket."""
+    port = _free_port()
+    mp.spawn(_worker_raw, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    tables = [np.load(os.path.join(str(tmp_path), "distinct_%d.npy" % r)) for r in range(world)]
+    for t in tables[1:]:
+        assert (t == tables[0]).all()
+    all_keys = np.unique(np.concatenate([_make_keys(100 + r)[0] for r in range(world)]))
+    all_irr = np.unique(np.concatenate([_make_keys(100 + r)[1] for r in range(world)]), axis=0)
+    want = np.zeros(N_CELLS, dtype=np.int64)
+    np.add.at(want, all_keys >> UMI_BITS, 1)
+    np.add.at(want, all_irr[:, 0] >> 36, 1)
+    assert (tables[0] == want).all()
+
+
 def test_shard_record_ranges():
     from ssd_b200.distributed import shard_record_ranges
     assert shard_record_ranges(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
