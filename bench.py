@@ -50,6 +50,20 @@ def workload_config(n_gpus):
             "l2": "inputs (6.5 GB per GPU) are far larger than the 126 MB L2; no explicit flush"}
 
 
+def ncu_traffic(kernel_key, pairs_per_gpu):
+    """DRAM bytes (read + written) per launch of the kernel from the committed `ncu --set full` capture of this very
+    workload (profiles/r01_dram_traffic.json, made by profiles/extract_traffic.py); None for any other workload."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_dram_traffic.json")
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+        if t["workload"]["pairs_per_gpu"] != pairs_per_gpu or t["workload"]["read_len"] != READ_LEN:
+            return None
+        return t["kernels"][kernel_key]["traffic"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -302,9 +316,9 @@ def main():
     pipeline_gbs = pipeline_bytes * args.steps / (ms * 1e-3) / 1e9
     roofline = None
     if dom:
-        roofline = {"bound": "hbm", "kernel": {"scan_r1": "k_scan<R1>", "scan_r2": "k_scan<R2>", "emit": "k_emit"}[dom],
+        roofline = {"bound": "hbm", "kernel": {"scan_r1": "k_scan<R1>", "scan_r2": "k_scan<R2>", "emit": "k_emit_tiled"}[dom],
                     "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["gbs"] / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": ncu_traffic(dom, n), "peak_source": peak_src,
                     "per_kernel": per_kernel,
                     "stage_ms_per_step": {k: v[0] / max(1, args.steps) for k, v in stage.items()},
                     "pipeline": {"algorithmic_bytes_per_step": pipeline_bytes, "achieved": pipeline_gbs, "frac": pipeline_gbs / peak}}

@@ -58,6 +58,7 @@ struct ssd_ctx {
     bool wide = false;  // 64-bit record offsets
     uint64_t rec_cap = 0;
     uint64_t n_rec_r1 = 0, n_rec_r2 = 0, n_rec = 0, n_keys = 0, n_irr = 0;
+    uint32_t emit_grid = 148;
     uint64_t n_respec = 0;  // scans repeated without guessing (diagnostics)
     bool phase1_done = false, filter_done = false, unique_done = false;
     int planned = -1;  // which output b_out_off currently describes (-1 = none)
@@ -543,7 +544,9 @@ int launch_emit(ssd_ctx* c, int which, uint8_t* d_out, const uint32_t* order = n
     }
     const uint32_t nb = blocks_for(a.n_rec, a.rpb);
     StageTimer t(c, 5);
-    if (nb && tiled) k_emit_tiled<OffT><<<nb, kThreads, sizeof(TileSmem), c->stream>>>(a, c->dcfg);
+    if (nb && tiled && !getenv("SSD_EMIT_TILED_BLOCKS"))
+        k_emit_stream<OffT><<<std::min<uint32_t>(nb, c->emit_grid), kStreamThreads, sizeof(StreamSmem), c->stream>>>(a, c->dcfg, nb);
+    else if (nb && tiled) k_emit_tiled<OffT><<<nb, kThreads, sizeof(TileSmem), c->stream>>>(a, c->dcfg);
     else if (nb) k_emit<OffT><<<nb, kThreads, 0, c->stream>>>(a, c->dcfg);
     c->n_launches += nb ? 1 : 0;
     CU(c, cudaGetLastError());
@@ -706,7 +709,11 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
         CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
         CUB_(cudaFuncSetAttribute(k_emit_tiled<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
         CUB_(cudaFuncSetAttribute(k_emit_tiled<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+        CUB_(cudaFuncSetAttribute(k_emit_stream<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
+        CUB_(cudaFuncSetAttribute(k_emit_stream<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
         int per_sm = 0;
+        CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_stream<uint32_t>, kStreamThreads, sizeof(StreamSmem)));
+        c->emit_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
         CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<kScanR2, uint32_t, true>, kScanThreads, sizeof(ScanSmem)));
         c->scan_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
     }
