@@ -16,9 +16,15 @@
 
 namespace ssd {
 
-constexpr int kTR = 64;            // records per block, at most
-constexpr int kTIn = 24 * 1024;    // staged read-1 bytes per block
-constexpr int kTOut = 26 * 1024;   // staged output bytes per block
+#ifndef SSD_EMIT_TR
+#define SSD_EMIT_TR 64
+#endif
+#ifndef SSD_EMIT_MINBLOCKS
+#define SSD_EMIT_MINBLOCKS 2
+#endif
+constexpr int kTR = SSD_EMIT_TR;          // records per tile, at most (32 or 64)
+constexpr int kTIn = kTR * 384;           // staged read-1 bytes per tile
+constexpr int kTOut = kTR * 416;          // staged output bytes per tile
 constexpr int kTPad = 16;          // bytes in front of the staged input (16-byte loads may start before the first record)
 
 struct __align__(128) TileSmem {
@@ -323,7 +329,14 @@ __global__ void __launch_bounds__(kThreads) k_emit_tiled(const __grid_constant__
 // copy that overlaps the next tile's assembly (two output buffers).  No thread of the consumers ever waits for global
 // memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int kStreamStages = 2;
+#ifndef SSD_EMIT_STAGES
+#define SSD_EMIT_STAGES 2
+#endif
+constexpr int kStreamStages = SSD_EMIT_STAGES;
+#ifndef SSD_EMIT_OUTBUFS
+#define SSD_EMIT_OUTBUFS 2
+#endif
+constexpr int kStreamOutBufs = SSD_EMIT_OUTBUFS;  // 2: a slice leaves while the next is assembled; 1: the next tile waits for the slice to leave
 constexpr int kStreamConsumers = 8;                              // warps
 constexpr int kStreamThreads = (kStreamConsumers + 1) * 32;      // + the producer warp
 constexpr uint32_t kStreamGeneric = 1u, kStreamTwoSeg = 2u, kStreamEmpty = 4u;
@@ -340,14 +353,14 @@ struct __align__(128) StreamStage {
 
 struct __align__(128) StreamSmem {
     StreamStage st[kStreamStages];
-    uint8_t out[2][kTOut + 32];
+    uint8_t out[kStreamOutBufs][kTOut + 32];
     unsigned long long full[kStreamStages], empty[kStreamStages];
 };
 
 __device__ __forceinline__ void sync_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kStreamConsumers * 32) : "memory"); }
 
 template <typename OffT>
-__global__ void __launch_bounds__(kStreamThreads, 2) k_emit_stream(const __grid_constant__ EmitArgs<OffT> args, const __grid_constant__ DevCfg cfg,
+__global__ void __launch_bounds__(kStreamThreads, SSD_EMIT_MINBLOCKS) k_emit_stream(const __grid_constant__ EmitArgs<OffT> args, const __grid_constant__ DevCfg cfg,
                                                                     uint32_t n_tiles)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -363,6 +376,34 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_emit_stream(const __grid_
 
     if (warp == kStreamConsumers) {
         // ================================ producer warp ================================
+        // the per-record arrays of a tile are requested one tile ahead (registers), so that the round trip to global memory
+        // overlaps the wait for a free stage
+        uint64_t o0[2], o1[2], start[2];
+        uint4 mt[2];
+        unsigned long long an[2];
+        auto request = [&](uint64_t t) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                o0[h] = o1[h] = start[h] = 0;
+                mt[h] = make_uint4(0u, 0u, 0u, 0u);
+                an[h] = 0;
+            }
+            if (t >= n_tiles) return;
+            const uint64_t r0 = t * args.rpb;
+            const uint32_t nrec = (uint32_t)(r0 + args.rpb < args.n_rec ? args.rpb : args.n_rec - r0);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t k = (uint32_t)lane + 32u * h;
+                if (k < nrec) {
+                    o0[h] = args.out_off[r0 + k];
+                    o1[h] = args.out_off[r0 + k + 1];
+                    start[h] = (uint64_t)args.r1_start[r0 + k];
+                    mt[h] = args.r1_meta[r0 + k];
+                    an[h] = args.ann[r0 + k];
+                }
+            }
+        };
+        request(blockIdx.x);
         for (uint32_t it = 0;; it++) {
             const uint32_t s = it % kStreamStages;
             StreamStage& T = S.st[s];
@@ -378,24 +419,6 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_emit_stream(const __grid_
             }
             const uint64_t r0 = t * args.rpb;
             const uint32_t nrec = (uint32_t)(r0 + args.rpb < args.n_rec ? args.rpb : args.n_rec - r0);
-            // two records per lane, everything requested at once (one round trip)
-            uint64_t o0[2], o1[2], start[2];
-            uint4 mt[2];
-            unsigned long long an[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t k = (uint32_t)lane + 32u * h;
-                o0[h] = o1[h] = start[h] = 0;
-                mt[h] = make_uint4(0u, 0u, 0u, 0u);
-                an[h] = 0;
-                if (k < nrec) {
-                    o0[h] = args.out_off[r0 + k];
-                    o1[h] = args.out_off[r0 + k + 1];
-                    start[h] = (uint64_t)args.r1_start[r0 + k];
-                    mt[h] = args.r1_meta[r0 + k];
-                    an[h] = args.ann[r0 + k];
-                }
-            }
             const uint32_t last = nrec - 1u;
             const uint64_t out_lo = __shfl_sync(0xFFFFFFFFu, o0[0], 0);
             const uint64_t oh0 = __shfl_sync(0xFFFFFFFFu, o1[0], (int)(last & 31u)), oh1 = __shfl_sync(0xFFFFFFFFu, o1[1], (int)(last & 31u));
@@ -484,6 +507,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_emit_stream(const __grid_
                 if (!bulk) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&S.full[s])) : "memory");
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&S.full[s])) : "memory");
             }
+            request(t + gridDim.x);
         }
         return;
     }
@@ -492,12 +516,16 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_emit_stream(const __grid_
     for (uint32_t it = 0;; it++) {
         const uint32_t s = it % kStreamStages;
         const StreamStage& T = S.st[s];
-        uint8_t* s_out = S.out[it & 1u];
+        uint8_t* s_out = S.out[kStreamOutBufs == 2 ? (it & 1u) : 0u];
         mbar_wait(reinterpret_cast<uint64_t*>(&S.full[s]), (it / kStreamStages) & 1u);
         if (T.tile == 0xFFFFFFFFu) break;
         const uint32_t nrec = T.nrec, flags = T.flags;
         const uint64_t out_lo = T.out_lo, out_hi = T.out_hi;
         const bool staged = (flags & (kStreamGeneric | kStreamEmpty)) == 0u;
+        if (kStreamOutBufs == 1) {
+            if (tid == 0) bulk_wait_read();  // the previous slice has left the buffer
+            sync_consumers();
+        }
         if (flags & kStreamGeneric) {
             const uint64_t r0 = (uint64_t)T.tile * args.rpb;
             emit_block_generic(args, cfg, r0, r0 + nrec, kStreamConsumers);
@@ -593,7 +621,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_emit_stream(const __grid_
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
-        if (tid == 0) bulk_wait_read();  // the slice written two tiles ago has left the other buffer
+        if (kStreamOutBufs == 2 && tid == 0) bulk_wait_read();  // the slice written two tiles ago has left the other buffer
         sync_consumers();
         // ---- the finished slice leaves with one bulk copy; shared and global addresses agree modulo 16 ----
         if (staged) {
