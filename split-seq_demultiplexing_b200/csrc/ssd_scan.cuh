@@ -930,6 +930,9 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                             }
                         }
                     }
+                    // read 2 only needs the id token: stop as soon as every lane has seen its end (control bytes behind it do
+                    // not matter, a control byte before or at it has been flagged above)
+                    if (MODE == kScanR2 && __all_sync(0xFFFFFFFFu, found_tok || w + 1u >= nwords)) break;
                 }
             }
             fp = tok_hash_finish(h, tok_len);
