@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1183,6 +1184,13 @@ extern "C" int ssd_host_alloc(void** p, size_t bytes)
 
 extern "C" int ssd_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? SSD_OK : SSD_ECUDA; }
 
+namespace {
+// Contexts used from different host threads pipeline over PCIe: one batch uploads while another computes and a third
+// downloads.  Copies in the same direction share one DMA engine; letting two uploads interleave only delays both, so
+// each direction is handed to one context at a time.
+std::mutex g_h2d_turn, g_d2h_turn;
+}  // namespace
+
 extern "C" int ssd_emit_host(ssd_ctx* c, int which, void* out, size_t out_cap, size_t* written)
 {
     if (!c) return SSD_EINVAL;
@@ -1193,6 +1201,7 @@ extern "C" int ssd_emit_host(ssd_ctx* c, int which, void* out, size_t out_cap, s
     if (!need) return SSD_OK;
     OKR(ensure(c, c->b_out, need + 32));
     OKR(ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, nullptr));
+    std::lock_guard<std::mutex> turn(g_d2h_turn);
     CU(c, cudaMemcpyAsync(out, c->b_out.p, need, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return SSD_OK;
@@ -1207,10 +1216,14 @@ extern "C" int ssd_run_host(ssd_ctx* c, const void* r1, size_t r1_len, const voi
     OKR(ensure(c, c->b_in2, r2_len + 32));
     // chunked so that a pageable source does not stall the whole transfer behind one staging copy
     const size_t chunk = (size_t)64 << 20;
-    for (size_t o = 0; o < r1_len; o += chunk)
-        CU(c, cudaMemcpyAsync((uint8_t*)c->b_in1.p + o, (const uint8_t*)r1 + o, std::min(chunk, r1_len - o), cudaMemcpyHostToDevice, c->stream));
-    for (size_t o = 0; o < r2_len; o += chunk)
-        CU(c, cudaMemcpyAsync((uint8_t*)c->b_in2.p + o, (const uint8_t*)r2 + o, std::min(chunk, r2_len - o), cudaMemcpyHostToDevice, c->stream));
+    {
+        std::lock_guard<std::mutex> turn(g_h2d_turn);
+        for (size_t o = 0; o < r1_len; o += chunk)
+            CU(c, cudaMemcpyAsync((uint8_t*)c->b_in1.p + o, (const uint8_t*)r1 + o, std::min(chunk, r1_len - o), cudaMemcpyHostToDevice, c->stream));
+        for (size_t o = 0; o < r2_len; o += chunk)
+            CU(c, cudaMemcpyAsync((uint8_t*)c->b_in2.p + o, (const uint8_t*)r2 + o, std::min(chunk, r2_len - o), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
     OKR(ssd_demux_device(c, c->b_in1.p, r1_len, c->b_in2.p, r2_len));
     OKR(ssd_filter_single(c, stats));
     if (!out && !out_cap) {

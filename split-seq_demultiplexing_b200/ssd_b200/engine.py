@@ -267,6 +267,52 @@ class Demultiplexer:
         return {self.cell_string(int(c)): (int(hist[c]), int(dist[c])) for c in np.nonzero(hist)[0]}
 
 
+class HostPipeline:
+    """Several contexts on one GPU fed from host threads: while one batch uploads, the previous one computes and
+    downloads (PCIe is full duplex; the library hands each direction to one context at a time).  The reference runs
+    its chunks through joblib workers the same way (CLI3:56-64).  `map` keeps the order of the batches."""
+
+    def __init__(self, whitelist: Sequence[str], depth: int = 2, **config):
+        self.contexts = [Demultiplexer(whitelist, **config) for _ in range(max(1, depth))]
+
+    def map(self, batches, which: int = L.EMIT_PASSING, outs=None):
+        """batches: sequence of (read-1 bytes-like, read-2 bytes-like) host buffers (pinned for full PCIe speed).
+        outs: optional list of one reusable host output array per context.  Returns [(output array, stats), ...]."""
+        import threading
+        batches = list(batches)
+        results = [None] * len(batches)
+        errors = []
+        nxt = {"i": 0}
+        lock = threading.Lock()
+
+        def work(k):
+            dm = self.contexts[k]  # the library selects the context's device on every call
+            while True:
+                with lock:
+                    i = nxt["i"]
+                    if i >= len(batches) or errors:
+                        return
+                    nxt["i"] = i + 1
+                try:
+                    results[i] = dm.run_host(batches[i][0], batches[i][1], which, out=None if outs is None else outs[k])
+                except Exception as e:  # noqa: BLE001 - re-raised below, in the caller's thread
+                    errors.append(e)
+                    return
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(self.contexts))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results
+
+    def close(self):
+        for dm in self.contexts:
+            dm.close()
+
+
 def synth_spec(whitelist: Sequence[str], n_pairs: int, seed: int = 0x5EED0001, first_index: int = 1, read_len: int = 150,
                cell_pool: int = 100000, p_sub: float = 0.01, p_n: float = 0.002, p_junk: float = 0.10, p_dup_umi: float = 0.05,
                p_tie: float = 0.0, p_trunc: float = 0.0, p_atqual: float = 0.02):

@@ -124,3 +124,20 @@ def test_calc_demux_results_index_error():
     dm = ssd_b200.Demultiplexer(WL, errors=0, min_count=1)
     with pytest.raises(IndexError):
         dm.filter_annotated_host(b"@noannotation\nACGT\n+\nEEEE\n")
+
+
+def test_host_pipeline_keeps_order_and_results():
+    """HostPipeline: two contexts on two host threads; every batch gives what a single context gives, in order."""
+    import ssd_b200
+    from oracle import ssd_oracle_py as orc
+    wl = fu.load_whitelist()
+    batches = []
+    for k in range(5):
+        spec = ssd_b200.synth_spec(wl, 3000 + 500 * k, seed=900 + k, cell_pool=200)
+        batches.append(ssd_b200.synth_host(spec))
+    pipe = ssd_b200.HostPipeline(wl, depth=2, errors=1, min_count=2)
+    got = pipe.map(batches)
+    pipe.close()
+    for (r1, r2), (out, st) in zip(batches, got):
+        ref = orc.demultiplex(r1, r2, wl, 1, 2)
+        assert out.tobytes() == ref.passing and st["n_matched"] == ref.n_matched
