@@ -414,12 +414,18 @@ constexpr int kScanR2 = 1;
 constexpr int kScanAnn = 2;  // an already annotated FASTQ (MergedCells_1.fastq): V2.calc_demux_results
 
 
-constexpr int kComputeWarps = 8;
+#ifndef SSD_SCAN_AWARPS
+#define SSD_SCAN_AWARPS 8
+#endif
+#ifndef SSD_SCAN_BWARPS
+#define SSD_SCAN_BWARPS 4
+#endif
+constexpr int kAWarps = SSD_SCAN_AWARPS, kBWarps = SSD_SCAN_BWARPS;  // first the stage A warps (bitmap, count, list), then the stage B warps (records)
+constexpr int kComputeWarps = kAWarps + kBWarps;
 constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kAWarps = 4, kBWarps = kComputeWarps - kAWarps;  // warps 0-3: stage A (bitmap, count, list); warps 4-7: stage B (records)
 constexpr int kAThreads = kAWarps * 32, kBThreads = kBWarps * 32;
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
-constexpr int kScanThreads = kComputeThreads + 96;  // eight compute warps + the copy warp + the prefix warp (works in block 0) + the commit warp
+constexpr int kScanThreads = kComputeThreads + 96;  // the compute warps + the copy warp + the prefix warp (works in block 0) + the commit warp
 #ifndef SSD_SCAN_STAGE_SLOTS
 #define SSD_SCAN_STAGE_SLOTS 2
 #endif
@@ -427,9 +433,6 @@ constexpr int kStageSlots = SSD_SCAN_STAGE_SLOTS;  // tiles whose records wait (
 
 // Shared memory of one persistent scan block.
 constexpr int kWinChunks = kWin / 16;                    // 16-byte chunks of a window
-constexpr int kChunksPerWarp = kWinChunks / kComputeWarps;  // each compute warp owns a contiguous run of chunks
-constexpr int kRows = (kChunksPerWarp + 31) / 32;        // 32-chunk rows per warp
-static_assert(kWinChunks % kComputeWarps == 0, "window size");
 
 // What stage B found for the records of one tile, parked until the tile's first record number is known.
 struct StageSlot {
@@ -725,16 +728,15 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         PROF_T(t2);
         PROF_ADD(1, t1, t2);
         // newlines owned by this tile: mask words [0, kTileWords), WPT consecutive ones per thread; halo words: 1 per thread of warps 0-1
-        constexpr int WPT = kTileWords / kAThreads;  // 4, 6 or 8 mask words per thread (16 / 24 / 32 KiB tiles)
-        static_assert(WPT >= 2 && WPT <= 8 && WPT % 2 == 0 && WPT * kAThreads == kTileWords, "tile size");
-        static_assert(kHaloWords <= 64, "halo size");
-        unsigned long long q[WPT / 2];
+        constexpr int WPT = kTileWords / kAThreads;  // mask words (32 bytes each) per thread
+        static_assert(WPT >= 1 && WPT <= 8 && WPT * kAThreads == kTileWords, "tile size");
+        static_assert(kHaloWords <= 64 && kAThreads >= 64, "halo size");
+        uint32_t mw[WPT];
         uint32_t cnt = 0;
 #pragma unroll
-        for (int w = 0; w < WPT / 2; w++) {
-            const uint2 v = *reinterpret_cast<const uint2*>(&s_mask[WPT * tid + 2 * w]);
-            q[w] = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
-            cnt += (uint32_t)__popcll(q[w]);
+        for (int w = 0; w < WPT; w++) {
+            mw[w] = s_mask[WPT * tid + w];
+            cnt += (uint32_t)__popc(mw[w]);
         }
         const uint32_t hm = tid < kHaloWords ? s_mask[kTileWords + tid] : 0u;
         uint32_t incl = cnt, hincl = __popc(hm);
@@ -751,7 +753,11 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             S.warp_tile[warp] = incl;
             if (warp < 2) S.halo_sum[warp] = hincl;
         }
+        PROF_T(t2a);
         sync_a();
+        PROF_T(t2b);
+        PROF_ADD(10, t2, t2a);
+        PROF_ADD(11, t2a, t2b);
         uint32_t warp_base = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < kAWarps; w++) {
@@ -772,24 +778,25 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         // line-start list: s_lstart[1 + k] = byte after the k-th newline of the window (tile first, then halo);
         // one newline per iteration for every lane that still has one: warp-uniform trip count
         {
-            const uint32_t trip_nl = __reduce_max_sync(0xFFFFFFFFu, cnt);
-            uint32_t cur = 0;  // 64-bit word being drained
-            for (uint32_t k = 0; k < trip_nl; k++) {
-                if (k < cnt) {
+            // word by word (32 bytes each), without loops in the common case: a word holds at most two newlines unless lines
+            // are shorter than 16 bytes ("\n+\n" gives the two); its first is the lowest set bit, its second the highest
+            uint32_t idx = excl + 1u;
 #pragma unroll
-                    for (int w = 0; w < WPT / 2 - 1; w++)
-                        if (cur == (uint32_t)w && q[w] == 0ull) cur = w + 1;
-                    unsigned long long v = q[0];
-#pragma unroll
-                    for (int w = 1; w < WPT / 2; w++)
-                        if (cur == (uint32_t)w) v = q[w];
-                    const uint32_t b = 64u * cur + (uint32_t)__ffsll((long long)v) - 1u;
-                    v &= v - 1ull;
-#pragma unroll
-                    for (int w = 0; w < WPT / 2; w++)
-                        if (cur == (uint32_t)w) q[w] = v;
-                    const uint32_t idx = excl + k + 1u;
-                    if (idx < (uint32_t)kMaxLines) s_lstart[idx] = (uint16_t)(tid * (32 * WPT) + b + 1);
+            for (int w = 0; w < WPT; w++) {
+                uint32_t m = mw[w];
+                const uint32_t p = (uint32_t)__popc(m);
+                const uint32_t pos0 = (uint32_t)tid * (32 * WPT) + 32u * w + 1u;
+                if (p > 2u) {  // rare: every newline of the word, one by one
+                    while (m) {
+                        const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                        m &= m - 1u;
+                        if (idx < (uint32_t)kMaxLines) s_lstart[idx] = (uint16_t)(pos0 + b);
+                        idx++;
+                    }
+                } else {
+                    if (p >= 1u && idx < (uint32_t)kMaxLines) s_lstart[idx] = (uint16_t)(pos0 + (uint32_t)__ffs((int)m) - 1u);
+                    if (p == 2u && idx + 1u < (uint32_t)kMaxLines) s_lstart[idx + 1u] = (uint16_t)(pos0 + 31u - (uint32_t)__clz((int)m));
+                    idx += p;
                 }
             }
             uint32_t hrank = hexcl, mm = hm;
@@ -800,7 +807,11 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                 hrank++;
             }
         }
+        PROF_T(t2c);
+        PROF_ADD(12, t2b, t2c);
         sync_a();  // list complete; warp_tile / halo_sum / mask may be reused
+        PROF_T(t2d);
+        PROF_ADD(13, t2c, t2d);
         if (tid == 0) mbar_arrive(&S.list_full[ls]);  // hand the tile to stage B
         PROF_T(t3);
         PROF_ADD(2, t2, t3);
