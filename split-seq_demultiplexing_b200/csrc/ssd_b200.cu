@@ -1021,7 +1021,7 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
     CU(c, cudaSetDevice(c->device));
     DevCounters h{};
     StageTimer t(c, 3);
-    c->n_launches += 4 + (c->cfg.collapse_pairs > 0 ? 1 : 0);
+    c->n_launches += 2 + (c->cfg.collapse_pairs > 0 ? 1 : 0);
     CU(c, cudaMemsetAsync((char*)c->d_cnt + offsetof(DevCounters, n_matched), 0, 6 * sizeof(unsigned long long), c->stream));
     const uint32_t nbc = blocks_for(c->n_cells_total, kThreads);
     k_filter<<<nbc, kThreads, 0, c->stream>>>(c->d_hist, c->d_distinct, c->n_cells_total, (long long)c->cfg.min_count, c->cfg.filter_mode, c->d_pass,
@@ -1031,13 +1031,12 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
         // exclusive scan of the post-filter output lengths; its first kernel also counts the retained records
         // and sizes the pre-filter output
         const uint32_t nb = (uint32_t)(c->n_rec / kScanBlock + 1);
-        OKR(ensure(c, c->b_bsums, (size_t)nb * sizeof(unsigned long long)));
+        OKR(ensure(c, c->b_bsums, ((size_t)nb + 2) * sizeof(unsigned long long)));
         OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
-        unsigned long long* bs = (unsigned long long*)c->b_bsums.p;
+        unsigned long long* bs = (unsigned long long*)c->b_bsums.p;  // [0]: ticket, [1..]: tile status
         OutLen f = make_outlen(c, SSD_EMIT_PASSING);
-        k_plan_reduce<<<nb, kThreads, 0, c->stream>>>(f, c->n_rec, bs, c->d_cnt);
-        k_scan_block_sums<unsigned long long><<<1, kThreads, 0, c->stream>>>(bs, nb, &c->d_cnt->bytes_passing);
-        k_scan_apply<unsigned long long, OutLen><<<nb, kThreads, 0, c->stream>>>(f, c->n_rec, bs, (unsigned long long*)c->b_out_off.p);
+        CU(c, cudaMemsetAsync(bs, 0, ((size_t)nb + 2) * sizeof(unsigned long long), c->stream));
+        k_plan_onepass<<<nb, kThreads, 0, c->stream>>>(f, c->n_rec, (unsigned long long*)c->b_out_off.p, bs + 1, (uint32_t*)bs, c->d_cnt);
         c->planned = SSD_EMIT_PASSING;
     }
     CU(c, cudaGetLastError());

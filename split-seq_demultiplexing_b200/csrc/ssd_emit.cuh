@@ -28,10 +28,11 @@ __global__ void k_filter(const uint32_t* hist, const uint32_t* distinct, uint64_
         ok = present && v >= min_count;
         pass[c] = ok ? 1 : 0;
     }
-    uint32_t b1 = __ballot_sync(0xFFFFFFFFu, present), b2 = __ballot_sync(0xFFFFFFFFu, ok);
-    if ((threadIdx.x & 31) == 0) {
-        if (b1) atomicAdd(&cnt->n_cells, (unsigned long long)__popc(b1));
-        if (b2) atomicAdd(&cnt->n_passing_cells, (unsigned long long)__popc(b2));
+    // one pair of atomics per block
+    const int n1 = __syncthreads_count(present), n2 = __syncthreads_count(ok);
+    if (threadIdx.x == 0) {
+        if (n1) atomicAdd(&cnt->n_cells, (unsigned long long)n1);
+        if (n2) atomicAdd(&cnt->n_passing_cells, (unsigned long long)n2);
     }
 }
 
@@ -121,6 +122,67 @@ __global__ void __launch_bounds__(kThreads) k_plan_reduce(OutLen f, uint64_t n, 
         if (vm) atomicAdd(&cnt->bytes_matched, vm);
     }
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// The same in one pass: exclusive scan of the post-filter lengths with a decoupled look-back over per-tile sums
+// (tiles taken by ticket), retained-record count and pre-filter size on the side.  status: one u64 per tile, zeroed.
+constexpr unsigned long long kPlanAgg = 1ull << 62, kPlanPrefix = 2ull << 62, kPlanValue = (1ull << 62) - 1ull;
+__global__ void __launch_bounds__(kThreads) k_plan_onepass(OutLen f, uint64_t n, unsigned long long* out_off, unsigned long long* status,
+                                                           uint32_t* ticket, DevCounters* cnt)
+{
+    __shared__ unsigned long long s_tmp[kThreads / 32];
+    __shared__ unsigned long long s_prior;
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t base = (uint64_t)tile * kScanBlock + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t len[kScanItems];
+    unsigned long long v = 0, vm = 0;
+    uint32_t nz = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        uint32_t lm = 0, lp = 0;
+        if (base + k < n) f.both(base + k, lm, lp);
+        len[k] = lp;
+        v += lp;
+        vm += lm;
+        nz += lp ? 1u : 0u;
+    }
+    unsigned long long total;
+    unsigned long long run = block_exclusive_scan(v, s_tmp, total);
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = status;
+        if (tile != 0) st[tile] = kPlanAgg | total;
+        unsigned long long prior = 0;
+        for (uint32_t t = tile; t > 0;) {
+            const unsigned long long x = st[t - 1];
+            if ((x >> 62) == 0ull) continue;
+            prior += x & kPlanValue;
+            if ((x >> 62) == 2ull) break;
+            t--;
+        }
+        st[tile] = kPlanPrefix | (prior + total);
+        s_prior = prior;
+        if ((uint64_t)(tile + 1) * kScanBlock >= n) {  // the last tile closes the array
+            out_off[n] = prior + total;
+            cnt->bytes_passing = prior + total;
+        }
+    }
+    nz = __reduce_add_sync(0xFFFFFFFFu, nz);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) vm += __shfl_xor_sync(0xFFFFFFFFu, vm, d);
+    if ((threadIdx.x & 31) == 0) {
+        if (nz) atomicAdd(&cnt->n_retained, (unsigned long long)nz);
+        if (vm) atomicAdd(&cnt->bytes_matched, vm);
+    }
+    __syncthreads();
+    run += s_prior;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) out_off[base + k] = run;
+        run += len[k];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
