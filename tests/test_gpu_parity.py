@@ -357,3 +357,50 @@ def test_misleading_lines_repeat_the_scan(ssd, orc):
     ref = orc.demultiplex(r1, r2, WL, 1, 1)
     dm, merged, passing, stats = run_both(ssd, r1, r2, 1, 1)
     assert merged == ref.merged1 and passing == ref.passing and stats["n_matched"] == ref.n_matched
+
+
+def test_full_size_10m_properties(ssd):
+    """BASELINE.json's configuration (10 M synthetic pairs, e=1, -m 10) is far beyond what the CPU oracle finishes in
+    seconds, so it is checked through size-independent properties: the per-cell tables are additive over a split of
+    the input into two halves (reads exactly, distinct UMIs as an upper bound that is tight for cells seen in only one
+    half), the statistics follow from the tables, and the output has exactly four lines per retained record, every
+    one of a passing cell."""
+    import torch
+    n, m = 10_000_000, 10
+    dm = ssd.Demultiplexer(WL, errors=1, min_count=m, record_bytes_hint=160)
+    spec = ssd.synth_spec(WL, n, seed=0x5EED0001)
+    d1, d2 = ssd.synth_device(dm, spec)
+    out, stats = dm.run_device(d1, d2, ssd.EMIT_PASSING)
+    torch.cuda.synchronize()
+    hist = dm.reads_histogram().clone().to(torch.int64)
+    distinct = dm.distinct_histogram().clone().to(torch.int64)
+    passing = distinct >= m
+    assert stats["n_records_r1"] == n and stats["n_records_r2"] == n
+    assert int(hist.sum()) == stats["n_matched"] == stats["n_regular_keys"] + stats["n_irregular_keys"]
+    assert int((hist > 0).sum()) == stats["n_cells"] and int(passing.sum()) == stats["n_passing_cells"]
+    assert int(hist[passing].sum()) == stats["n_retained"]
+    assert bool((distinct <= hist).all()) and bool(((distinct > 0) == (hist > 0)).all())
+    assert out.numel() == stats["bytes_passing"] and int((out == 10).sum()) == 4 * stats["n_retained"]
+    # every output header carries a passing cell: '_' + 24 barcode bytes + '_' right after the id
+    starts = torch.nonzero(out == 10).flatten()[3::4] + 1                      # record starts (all but the first)
+    starts = torch.cat([torch.zeros(1, dtype=starts.dtype, device=starts.device), starts[:-1]])
+    assert bool((out[starts] == ord("@")).all())
+    del out, starts
+    # additivity over two halves of the same input (generated separately: the generator is counter based)
+    halves_hist = torch.zeros_like(hist)
+    halves_distinct = torch.zeros_like(distinct)
+    del d1, d2
+    for first in (1, n // 2 + 1):
+        sp = ssd.synth_spec(WL, n // 2, seed=0x5EED0001, first_index=first)
+        h1, h2 = ssd.synth_device(dm, sp)
+        dm.run_device(h1, h2, ssd.EMIT_PASSING)
+        torch.cuda.synchronize()
+        hh = dm.reads_histogram().to(torch.int64)
+        dd = dm.distinct_histogram().to(torch.int64)
+        only_here = (hh > 0) & (hist == hh)                                        # cells whose reads all sit in this half
+        assert bool((dd[only_here] == distinct[only_here]).all())
+        halves_hist += hh
+        halves_distinct += dd
+        del h1, h2
+    assert bool((halves_hist == hist).all())
+    assert bool((halves_distinct >= distinct).all())
