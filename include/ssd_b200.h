@@ -199,6 +199,8 @@ int ssd_set_timing(ssd_ctx *ctx, int enabled);
 int ssd_read_timings(ssd_ctx *ctx, double *ms_per_stage, uint32_t *spans_per_stage, int n_stages);
 /* Number of kernels this context has launched since it was created. */
 uint64_t ssd_launch_count(const ssd_ctx *ctx);
+/* Diagnostics: how many times a scan had to be repeated without guessing the record phase. */
+int ssd_scan_repeats(const ssd_ctx *ctx, uint64_t *n);
 
 /* ---- synthetic read pairs (bench / tests) ---------------------------------------- */
 typedef struct ssd_synth_spec {

@@ -59,6 +59,7 @@ struct ssd_ctx {
     bool wide = false;  // 64-bit record offsets
     uint64_t rec_cap = 0;
     uint64_t n_rec_r1 = 0, n_rec_r2 = 0, n_rec = 0, n_keys = 0, n_irr = 0;
+    bool defer1 = true, defer2 = true;  // scan variant per file: park-and-commit, or (after a failed guess) wait for the line index
     uint32_t emit_grid = 148;
     uint64_t n_respec = 0;  // scans repeated without guessing (diagnostics)
     bool phase1_done = false, filter_done = false, unique_done = false;
@@ -453,8 +454,8 @@ int distinct_counts_local(ssd_ctx* c)
     return SSD_OK;
 }
 
-template <typename OffT, bool DEFER>
-int launch_scans(ssd_ctx* c)
+template <typename OffT>
+int launch_scans(ssd_ctx* c, bool defer1, bool defer2)
 {
     ScanArgs<OffT> a{};
     a.cnt = c->d_cnt;
@@ -479,7 +480,8 @@ int launch_scans(ssd_ctx* c)
             a.status = (unsigned long long*)c->b_status1.p;
             a.n_tiles = nt1;
             StageTimer t(c, 0);
-            k_scan<kScanAnn, OffT, DEFER><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+            if (defer1) k_scan<kScanAnn, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+            else k_scan<kScanAnn, OffT, false><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
             c->n_launches++;
         }
         CU(c, cudaGetLastError());
@@ -491,7 +493,8 @@ int launch_scans(ssd_ctx* c)
         a.status = (unsigned long long*)c->b_status1.p;
         a.n_tiles = nt1;
         StageTimer t(c, 0);
-        k_scan<kScanR1, OffT, DEFER><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        if (defer1) k_scan<kScanR1, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        else k_scan<kScanR1, OffT, false><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         c->n_launches++;
     }
     if (nt2) {
@@ -500,7 +503,8 @@ int launch_scans(ssd_ctx* c)
         a.status = (unsigned long long*)c->b_status2.p;
         a.n_tiles = nt2;
         StageTimer t(c, 1);
-        k_scan<kScanR2, OffT, DEFER><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        if (defer2) k_scan<kScanR2, OffT, true><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        else k_scan<kScanR2, OffT, false><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         c->n_launches++;
     }
     CU(c, cudaGetLastError());
@@ -802,8 +806,10 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
     DevCounters h{};
     // the scans park their per-record results until the record numbers arrive and guess the record phase of each tile meanwhile;
     // a wrong guess (lines that look like record starts where none is) repeats the scan with the variant that waits instead
-    bool defer = getenv("SSD_SCAN_NODEFER") == nullptr;
-    for (int attempt = 0, overflows = 0; attempt < 4; attempt++) {
+    // (records so short that a tile holds more of them than stage B parks at once count as a wrong guess).  The choice is
+    // remembered per file for the next batches of this context.
+    if (getenv("SSD_SCAN_NODEFER")) c->defer1 = c->defer2 = false;
+    for (int attempt = 0, overflows = 0; attempt < 5; attempt++) {
         c->rec_cap = cap;
         OKR(ensure(c, c->b_status1, (size_t)(nt1 + 1) * 8));
         OKR(ensure(c, c->b_status2, (size_t)(nt2 + 1) * 8));
@@ -819,11 +825,11 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
         CU(c, cudaMemsetAsync(c->d_hist, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
         CU(c, cudaMemsetAsync(c->b_status1.p, 0, (size_t)(nt1 + 1) * 8, c->stream));
         CU(c, cudaMemsetAsync(c->b_status2.p, 0, (size_t)(nt2 + 1) * 8, c->stream));
-        if (defer) OKR(c->wide ? (launch_scans<uint64_t, true>(c)) : (launch_scans<uint32_t, true>(c)));
-        else OKR(c->wide ? (launch_scans<uint64_t, false>(c)) : (launch_scans<uint32_t, false>(c)));
+        OKR(c->wide ? launch_scans<uint64_t>(c, c->defer1, c->defer2) : launch_scans<uint32_t>(c, c->defer1, c->defer2));
         OKR(fetch_counters(c, &h));
-        if (h.err_flags & kErrRespec) {
-            defer = false;
+        if (h.err_flags & (kErrRespec | (kErrRespec << 1))) {
+            if (h.err_flags & kErrRespec) c->defer1 = false;
+            if (h.err_flags & (kErrRespec << 1)) c->defer2 = false;
             c->n_respec++;
             continue;
         }
@@ -831,7 +837,7 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
         if (++overflows == 2) return fail(c, SSD_EINVAL, "record tables overflowed twice (internal)");
         cap = std::max(h.n_records[0], h.n_records[1]) + 1;
     }
-    if (h.err_flags & (kErrRespec | kErrOverflow)) return fail(c, SSD_EINVAL, "scan did not settle (internal)");
+    if (h.err_flags & (kErrRespec | (kErrRespec << 1) | kErrOverflow)) return fail(c, SSD_EINVAL, "scan did not settle (internal)");
     if (h.err_flags & (kErrNoAt | kErrKey | kErrDense | kErrIndex | kErrForeign)) {
         unsigned long long off[2];
         CU(c, cudaMemcpy(off, c->d_err_off, sizeof off, cudaMemcpyDeviceToHost));
@@ -1433,6 +1439,13 @@ extern "C" int ssd_read_timings(ssd_ctx* c, double* ms_per_stage, uint32_t* laun
         cudaEventDestroy(sp.b);
     }
     c->spans.clear();
+    return SSD_OK;
+}
+
+extern "C" int ssd_scan_repeats(const ssd_ctx* c, uint64_t* n)
+{
+    if (!c || !n) return SSD_EINVAL;
+    *n = c->n_respec;
     return SSD_OK;
 }
 

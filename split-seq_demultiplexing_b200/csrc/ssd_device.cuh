@@ -66,7 +66,8 @@ constexpr uint32_t kErrDense = 8u;        // too many records in one tile (recor
 constexpr uint32_t kErrEmitLen = 16u;     // emitted record length differs from the planned one (internal)
 constexpr uint32_t kErrHeaderLong = 32u;  // header line longer than the supported maximum
 constexpr uint32_t kErrIndex = 64u;       // annotated header without two '_' (the reference's IndexError, V2:397-398)
-constexpr uint32_t kErrRespec = 256u;     // the scan guessed the record phase of a tile wrong: the host repeats it without guessing
+constexpr uint32_t kErrRespec = 256u;     // read-1 (<< 1: read-2) scan guessed the record phase of a tile wrong or met a tile with more
+                                          // records than it can park: the host repeats that scan with the variant that waits instead
 constexpr uint32_t kErrForeign = 128u;    // annotated header whose cell / UMI fields cannot come from this whitelist
 
 struct DevCounters {

@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             const uint32_t j_first = (uint32_t)(4ull * r_first - line_base);
             const bool good = guess != 0xFFFFFFFFu ? (n_rec == (guess >> 8) && (n_rec == 0u || j_first == (guess & 0xFFu))) : n_rec == 0u;
             if (!good) {
-                if (lane == 0) atomicOr(&args.cnt->err_flags, kErrRespec);  // the host repeats the scan without guessing
+                if (lane == 0) atomicOr(&args.cnt->err_flags, kErrRespec << (MODE == kScanR2 ? 1 : 0));  // the host repeats this scan without guessing
                 n_rec = 0;
             }
             const StageSlot& G = S.stage[ss];

@@ -212,6 +212,12 @@ class Demultiplexer:
         self._check(self.lib.ssd_read_timings(self._ctx, ms, cnt, len(self.STAGES)))
         return {s: (ms[i], cnt[i]) for i, s in enumerate(self.STAGES)}
 
+    def scan_repeats(self) -> int:
+        """How many times a scan was repeated without guessing the record phase (diagnostics)."""
+        n = C.c_uint64()
+        self._check(self.lib.ssd_scan_repeats(self._ctx, C.byref(n)))
+        return n.value
+
     def launch_count(self) -> int:
         return int(self.lib.ssd_launch_count(self._ctx))
 

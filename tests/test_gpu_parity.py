@@ -357,6 +357,27 @@ def test_misleading_lines_repeat_the_scan(ssd, orc):
     ref = orc.demultiplex(r1, r2, WL, 1, 1)
     dm, merged, passing, stats = run_both(ssd, r1, r2, 1, 1)
     assert merged == ref.merged1 and passing == ref.passing and stats["n_matched"] == ref.n_matched
+    assert dm.scan_repeats() >= 1
+
+
+def test_short_records_repeat_once_per_context(ssd, orc):
+    """Short reads (the bundled ones are 66 / 94 bp) put more records into a tile than stage B parks at once: the first
+    batch repeats the read-1 scan with the variant that waits, and the context remembers the choice for later batches."""
+    import random
+    rng = random.Random(5)
+    f, r = [], []
+    for i in range(30000):
+        s1 = "".join(rng.choice("ACGT") for _ in range(40))
+        s2 = "".join(rng.choice("ACGT") for _ in range(10)) + WL[i % 96] + fu.LINKER_3_2 + WL[(i * 7) % 96] + fu.LINKER_2_1 + WL[(i // 5) % 96]
+        f.append("@S.%d %d/1\n%s\n+\n%s\n" % (i, i, s1, "E" * 40))
+        r.append("@S.%d %d/2\n%s\n+\n%s\n" % (i, i, s2, "A" * len(s2)))
+    r1, r2 = "".join(f).encode(), "".join(r).encode()
+    ref = orc.demultiplex(r1, r2, WL, 1, 3)
+    dm, merged, passing, stats = run_both(ssd, r1, r2, 1, 3)
+    assert merged == ref.merged1 and passing == ref.passing and stats["n_matched"] == ref.n_matched == 30000
+    assert dm.scan_repeats() == 1
+    again, _ = dm.run_host(r1, r2, ssd.EMIT_PASSING)
+    assert again.tobytes() == ref.passing and dm.scan_repeats() == 1
 
 
 def test_full_size_10m_properties(ssd):
