@@ -136,6 +136,11 @@ int ssd_count_distinct(ssd_ctx *ctx, uint64_t *d_keys, uint64_t n_keys, void *d_
  * Replaces the set-union of per-chunk UMI sets the reference gets for free from its single results file (V2:404-411). */
 int ssd_partition_keys(ssd_ctx *ctx, int world, uint64_t **d_keys, uint64_t *offsets, void **d_irregular,
                        uint64_t *n_irregular);
+/* ssd_count_distinct for a rank of a multi-GPU job: regular keys are what the peers sent for this rank's cells;
+ * the irregular keys are everybody's (all-gathered, unordered), of which only those of cells this rank owns are
+ * counted; records with hi == ~0 are padding. */
+int ssd_count_distinct_owned(ssd_ctx *ctx, uint64_t *d_keys, uint64_t n_keys, void *d_irregular,
+                             uint64_t n_irregular, int rank, int world);
 /* Owner rank of a cell in a world of W ranks: ((cell >> *shift) * W) / *n_buckets. */
 int ssd_owner_layout(const ssd_ctx *ctx, int *shift, int *n_buckets);
 /* Bit width of the 2-bit-packed UMI inside a regular key (cell id = key >> umi_bits). */

@@ -382,7 +382,9 @@ int count_cells(ssd_ctx* c, const uint64_t* uniq, uint64_t n_uniq, const IrrKey*
 // host round trip).  Regular keys: one-kernel-per-pass radix sort + first-occurrence count; irregular keys: hash set
 // on the side stream.
 // hash set of irregular keys on `st`: from the batch's annotation words (keys == nullptr) or from an array of n keys
-int irr_hash_counts(ssd_ctx* c, const IrrKey* keys, uint64_t n, cudaStream_t st)
+void owner_layout(const ssd_ctx* c, int* shift, int* n_buckets);
+
+int irr_hash_counts(ssd_ctx* c, const IrrKey* keys, uint64_t n, cudaStream_t st, int rank = 0, int world = 0)
 {
     if (n == 0) return SSD_OK;
     uint64_t slots = 1024;
@@ -390,7 +392,10 @@ int irr_hash_counts(ssd_ctx* c, const IrrKey* keys, uint64_t n, cudaStream_t st)
     if (slots > (1ull << 32)) return fail(c, SSD_ERANGE, "too many irregular UMIs in one batch");
     OKR(ensure(c, c->b_irr_table, slots * sizeof(ulonglong2)));
     CU(c, cudaMemsetAsync(c->b_irr_table.p, 0, slots * sizeof(ulonglong2), st));
-    if (keys) k_irr_hash_keys<<<blocks_for(n, kThreads), kThreads, 0, st>>>(keys, n, (ulonglong2*)c->b_irr_table.p, (uint32_t)(slots - 1), c->d_distinct);
+    int shift = 0, nb = 1;
+    owner_layout(c, &shift, &nb);
+    if (keys) k_irr_hash_keys<<<blocks_for(n, kThreads), kThreads, 0, st>>>(keys, n, (ulonglong2*)c->b_irr_table.p, (uint32_t)(slots - 1), c->d_distinct, rank, world,
+                                                                          shift, nb);
     else k_irr_hash<<<blocks_for(c->n_rec_r2, kThreads), kThreads, 0, st>>>((const uint64_t*)c->b_ann.p, c->n_rec_r2, c->r2, (ulonglong2*)c->b_irr_table.p,
                                                                               (uint32_t)(slots - 1), c->d_distinct);
     c->n_launches++;
@@ -400,7 +405,7 @@ int irr_hash_counts(ssd_ctx* c, const IrrKey* keys, uint64_t n, cudaStream_t st)
 
 // Per-cell distinct counts of arbitrary key arrays (duplicates allowed; d_keys is reordered): what a rank does with the
 // keys its peers sent for the cells it owns.
-int distinct_counts_arrays(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys, const IrrKey* d_irr, uint64_t n_irr)
+int distinct_counts_arrays(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys, const IrrKey* d_irr, uint64_t n_irr, int rank = 0, int world = 0)
 {
     CU(c, cudaMemsetAsync(c->d_distinct, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
     const bool side = n_irr != 0 && c->side_stream != nullptr;
@@ -411,7 +416,7 @@ int distinct_counts_arrays(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys, const 
             CU(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
             st = c->side_stream;
         }
-        OKR(irr_hash_counts(c, d_irr, n_irr, st));
+        OKR(irr_hash_counts(c, d_irr, n_irr, st, rank, world));
         if (side) CU(c, cudaEventRecord(c->ev_join, st));
     }
     if (n_keys) {
@@ -961,6 +966,19 @@ extern "C" int ssd_partition_keys(ssd_ctx* c, int world, uint64_t** d_keys, uint
     int shift, nb;
     owner_layout(c, &shift, &nb);
     const uint64_t n_keys = c->n_keys, n_rec = c->n_rec_r2;
+    if (c->n_irr) {
+        // next to the partition pass, on the side stream
+        unsigned long long* cursor = (unsigned long long*)c->d_err_off;  // free after phase 1 (errors were read)
+        OKR(ensure(c, c->b_irr, c->n_irr * sizeof(IrrKey)));
+        cudaStream_t st = c->side_stream ? c->side_stream : c->stream;
+        if (c->side_stream) {
+            CU(c, cudaEventRecord(c->ev_fork, c->stream));
+            CU(c, cudaStreamWaitEvent(st, c->ev_fork, 0));
+        }
+        CU(c, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
+        k_collect_irr<<<blocks_for(n_rec, kThreads), kThreads, 0, st>>>((const uint64_t*)c->b_ann.p, n_rec, c->r2, (IrrKey*)c->b_irr.p, cursor);
+        c->n_launches++;
+    }
     uint32_t hist[kOsRadix] = {0};
     if (n_keys) {
         // one scatter pass on the bucket digit: keys come out grouped by bucket, hence by owner
@@ -978,12 +996,9 @@ extern "C" int ssd_partition_keys(ssd_ctx* c, int world, uint64_t** d_keys, uint
         c->n_launches += 2;
         CU(c, cudaMemcpyAsync(hist, ghist, sizeof hist, cudaMemcpyDeviceToHost, c->stream));
     }
-    if (c->n_irr) {
-        unsigned long long* cursor = (unsigned long long*)c->d_err_off;  // free after phase 1 (errors were read)
-        OKR(ensure(c, c->b_irr, c->n_irr * sizeof(IrrKey)));
-        CU(c, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), c->stream));
-        k_collect_irr<<<blocks_for(n_rec, kThreads), kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, n_rec, c->r2, (IrrKey*)c->b_irr.p, cursor);
-        c->n_launches++;
+    if (c->n_irr && c->side_stream) {
+        CU(c, cudaEventRecord(c->ev_join, c->side_stream));
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(c->stream));
@@ -1018,6 +1033,15 @@ extern "C" int ssd_count_distinct(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys,
         return distinct_counts_arrays(c, d_keys, n_keys, (const IrrKey*)d_irregular, n_irregular);
     }
     return count_cells(c, uk, nuk, ui, nui);
+}
+
+extern "C" int ssd_count_distinct_owned(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys, void* d_irregular, uint64_t n_irregular, int rank, int world)
+{
+    if (!c || world < 1 || rank < 0 || rank >= world) return SSD_EINVAL;
+    CU(c, cudaSetDevice(c->device));
+    StageTimer t(c, 2);
+    c->unique_done = false;  // the context's buffers are reused as scratch
+    return distinct_counts_arrays(c, d_keys, n_keys, (const IrrKey*)d_irregular, n_irregular, rank, world);
 }
 
 extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)

@@ -193,12 +193,18 @@ __device__ __forceinline__ bool irr_insert(ulonglong2* table, uint32_t slot_mask
 }
 
 // irregular keys given as an array (what peers sent): distinct[cell] += first occurrences
-__global__ void __launch_bounds__(kThreads) k_irr_hash_keys(const IrrKey* keys, uint64_t n, ulonglong2* table, uint32_t slot_mask, uint32_t* distinct)
+// world > 0: only keys whose cell this rank owns count (owner = ((cell >> shift) * world) / n_buckets); a key with hi == ~0
+// is padding
+__global__ void __launch_bounds__(kThreads) k_irr_hash_keys(const IrrKey* keys, uint64_t n, ulonglong2* table, uint32_t slot_mask, uint32_t* distinct,
+                                                            int rank, int world, int shift, int n_buckets)
 {
     const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     const IrrKey k = keys[i];
-    if (irr_insert(table, slot_mask, k.hi, k.lo)) atomicAdd(&distinct[(uint32_t)(k.hi >> kIrrCellShift) & (uint32_t)kAnnCellMask], 1u);
+    if (k.hi == ~0ull) return;
+    const uint32_t cell = (uint32_t)(k.hi >> kIrrCellShift) & (uint32_t)kAnnCellMask;
+    if (world > 0 && (int)(((uint64_t)(cell >> shift) * (uint64_t)world) / (uint64_t)n_buckets) != rank) return;
+    if (irr_insert(table, slot_mask, k.hi, k.lo)) atomicAdd(&distinct[cell], 1u);
 }
 
 // table: slots of {lo, hi | 1 << 63}, zero = empty; n_slots is a power of two >= 2 * (number of irregular records)

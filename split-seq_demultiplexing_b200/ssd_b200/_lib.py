@@ -91,6 +91,7 @@ _SIGS = {
     "ssd_distinct_histogram_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "ssd_local_unique_keys": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "ssd_count_distinct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "ssd_count_distinct_owned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
     "ssd_key_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ssd_scan_repeats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "ssd_owner_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

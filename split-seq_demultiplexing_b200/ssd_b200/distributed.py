@@ -83,21 +83,47 @@ def exchange_raw(keys, key_counts, irr, irr_counts, group=None):
     return rk, ri
 
 
+def exchange_owned(keys, key_counts, irr, group=None):
+    """The exchange of the GPU path: regular keys (grouped by owner rank, key_counts[k] of them for rank k; a list or a tensor) go
+    all-to-all; the few irregular keys go to everybody (all-gather, padded with -1 rows to the longest list), the
+    receiver keeps those of its own cells.  Returns (regular keys received, all irregular keys)."""
+    import torch
+    import torch.distributed as dist
+    send_keys = [int(x) for x in (key_counts.tolist() if hasattr(key_counts, "tolist") else key_counts)]  # host-side counts
+    world = len(send_keys)
+    send = torch.tensor([[k, irr.shape[0]] for k in send_keys], dtype=torch.int64, device=keys.device)  # [world, 2]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    recv_l = recv.cpu().tolist()
+    rk = torch.empty(sum(r[0] for r in recv_l), dtype=torch.int64, device=keys.device)
+    dist.all_to_all_single(rk, keys.contiguous(), [r[0] for r in recv_l], send_keys, group=group)
+    longest = max(r[1] for r in recv_l)
+    if longest == 0:
+        return rk, torch.empty((0, 2), dtype=torch.int64, device=keys.device)
+    pad = torch.full((longest, 2), -1, dtype=torch.int64, device=keys.device)
+    pad[: irr.shape[0]] = irr
+    everything = torch.empty((world * longest, 2), dtype=torch.int64, device=keys.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(everything, pad, group=group)
+    else:
+        dist.all_gather(list(everything.view(world, longest, 2).unbind(0)), pad, group=group)
+    return rk, everything
+
+
 def global_filter(dm, world: int, group=None) -> dict:
     """After dm.demux_device(...) on every rank: make the -m decision global and exact, return dm's stats.
     Collectives: all-reduce of the read histogram, all-to-all of the unique keys, all-reduce of the distinct table."""
     import torch.distributed as dist
     if world > 1:
-        dist.all_reduce(dm.reads_histogram(), group=group)
+        pending = dist.all_reduce(dm.reads_histogram(), group=group, async_op=True)  # overlaps the key exchange
         if dm.filter_mode == "distinct_umi":
             import torch
+            rank = dist.get_rank(group)
             keys, offsets, irr = dm.partition_keys(world)
-            shift, n_buckets = dm.owner_layout()
-            key_counts = torch.tensor([offsets[k + 1] - offsets[k] for k in range(world)], dtype=torch.int64, device=keys.device)
-            irr, irr_counts = group_by_owner(irr, irr[:, 0] >> IRR_CELL_SHIFT, shift, n_buckets, world)
-            rk, ri = exchange_raw(keys, key_counts, irr, irr_counts, group=group)
-            dm.count_distinct(rk, ri)
+            rk, ri = exchange_owned(keys, [offsets[k + 1] - offsets[k] for k in range(world)], irr, group=group)
+            dm.count_distinct_owned(rk, ri, rank, world)
             dist.all_reduce(dm.distinct_histogram(), group=group)
+        pending.wait()
         return dm.build_filter()
     return dm.filter_single()
 

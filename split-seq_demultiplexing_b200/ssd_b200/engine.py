@@ -158,6 +158,12 @@ class Demultiplexer:
         self._check(self.lib.ssd_count_distinct(self._ctx, C.c_void_p(keys.data_ptr() if keys.numel() else 0), keys.numel(),
                                                 C.c_void_p(irr.data_ptr() if irr.numel() else 0), irr.numel() // 2))
 
+    def count_distinct_owned(self, keys, irr, rank: int, world: int):
+        """count_distinct for rank `rank` of `world`: keys = what the peers sent for this rank's cells, irr = everybody's
+        irregular keys (all-gathered; rows of -1 are padding), of which only this rank's cells are counted."""
+        self._check(self.lib.ssd_count_distinct_owned(self._ctx, C.c_void_p(keys.data_ptr() if keys.numel() else 0), keys.numel(),
+                                                      C.c_void_p(irr.data_ptr() if irr.numel() else 0), irr.numel() // 2, rank, world))
+
     def build_filter(self) -> dict:
         st = L.Stats()
         self._check(self.lib.ssd_build_filter(self._ctx, C.byref(st)))

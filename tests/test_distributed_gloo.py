@@ -85,10 +85,11 @@ def _worker_raw(rank, world, port, out_dir):
     rng.shuffle(keys)
     irr = np.concatenate([irr, irr[rng.integers(0, len(irr), size=200)]])
     k, kc = D.group_by_owner(torch.from_numpy(keys), torch.from_numpy(keys) >> UMI_BITS, shift, n_buckets, world)
-    i, ic = D.group_by_owner(torch.from_numpy(irr), torch.from_numpy(irr)[:, 0] >> 36, shift, n_buckets, world)
-    rk, ri = D.exchange_raw(k, kc, i, ic)
+    # the exchange of the GPU path: irregular keys go to everybody, the receiver keeps its own cells
+    rk, everything = D.exchange_owned(k, kc, torch.from_numpy(irr))
+    everything = everything[everything[:, 0] != -1]                              # padding rows
+    ri = everything[D.owner_of_cells(everything[:, 0] >> 36, shift, n_buckets, world) == rank]
     assert bool((D.owner_of_cells(rk >> UMI_BITS, shift, n_buckets, world) == rank).all())
-    assert ri.numel() == 0 or bool((D.owner_of_cells(ri[:, 0] >> 36, shift, n_buckets, world) == rank).all())
     distinct = torch.zeros(N_CELLS, dtype=torch.int32)
     uk = torch.unique(rk)
     distinct.index_add_(0, (uk >> UMI_BITS), torch.ones(uk.numel(), dtype=torch.int32))
