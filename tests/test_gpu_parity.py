@@ -425,3 +425,24 @@ def test_full_size_10m_properties(ssd):
         del h1, h2
     assert bool((halves_hist == hist).all())
     assert bool((halves_distinct >= distinct).all())
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_against_oracle(ssd, orc, seed):
+    """Seeded random configurations of the adversarial generator (sizes, line endings, header forms, N / tie / junk /
+    truncation rates, e, m), CUDA path against the CPU oracle: both outputs byte for byte, per-record cells, counts."""
+    import random
+    rng = random.Random(1000 + seed)
+    n = rng.choice([1, 7, 300, 2500, 12000])
+    kw = dict(ncells=rng.choice([1, 5, 40, 400]), crlf=rng.random() < 0.3, r1_len=rng.choice([(1, 30), (20, 80), (150, 150), (400, 900)]),
+              weird_headers=rng.random() < 0.7, final_newline=rng.random() < 0.7, p_short=rng.choice([0.0, 0.05, 0.3]),
+              p_n=rng.choice([0.0, 0.02, 0.15]), p_junk=rng.choice([0.0, 0.1, 0.5]), p_tie=rng.choice([0.0, 0.03, 0.2]),
+              p_lower=rng.choice([0.0, 0.01]), p_atqual=rng.choice([0.0, 0.1, 0.6]), p_dup_umi=rng.choice([0.0, 0.2, 0.8]))
+    e, m = rng.choice([0, 1, 1, 2, 3]), rng.choice([1, 2, 5, 10])
+    r1, r2 = fu.make_pairs(5000 + seed, n, WL, **kw)
+    ref = orc.demultiplex(r1, r2, WL, e, m)
+    dm, merged, passing, stats = run_both(ssd, r1, r2, e, m)
+    assert merged == ref.merged1 and passing == ref.passing
+    assert (stats["n_matched"], stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]) == (
+        ref.n_matched, ref.n_cells, ref.n_passing_cells, ref.n_retained)
+    assert dm.record_cells().tolist() == ref.rec_cell
