@@ -417,6 +417,9 @@ constexpr int kScanAnn = 2;  // an already annotated FASTQ (MergedCells_1.fastq)
 #ifndef SSD_SCAN_AWARPS
 #define SSD_SCAN_AWARPS 8
 #endif
+#ifndef SSD_SCAN_R2_SPREAD
+#define SSD_SCAN_R2_SPREAD 0
+#endif
 #ifndef SSD_SCAN_BWARPS
 #define SSD_SCAN_BWARPS 4
 #endif
@@ -1131,9 +1134,9 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             }
         };
 
-        // read 2 (global-memory latency in the chain): record i of a batch goes to warp i % 4, lane i / 4, so every warp gets its
-        // share and the stage ends sooner; read 1 keeps records packed into as few warps as possible
-        const uint32_t my_i = MODE == kScanR2 ? (uint32_t)lane * kBWarps + (uint32_t)wb : (uint32_t)tb;
+        // records are packed into as few warps as possible (fewer warp instructions); SSD_SCAN_R2_SPREAD=1 deals read 2's records
+        // round robin to the warps instead, which ends the stage sooner but costs a third more instructions
+        const uint32_t my_i = (MODE == kScanR2 && SSD_SCAN_R2_SPREAD) ? (uint32_t)lane * kBWarps + (uint32_t)wb : (uint32_t)tb;
 
         // ---- the guess: a record starts at the first line (of the four candidates) that begins with '@' and whose second
         //      next line begins with '+'.  A wrong guess costs a second pass, never a wrong result. ----
