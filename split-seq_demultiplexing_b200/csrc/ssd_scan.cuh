@@ -742,16 +742,15 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             cnt += (uint32_t)__popc(mw[w]);
         }
         const uint32_t hm = tid < kHaloWords ? s_mask[kTileWords + tid] : 0u;
-        uint32_t incl = cnt, hincl = __popc(hm);
+        // both prefix sums in one: a warp's tile count (<= 32 x 32 WPT bits) in the low half, its halo count in the high half
+        static_assert(32 * 32 * WPT < 65536, "packed scan");
+        uint32_t both = cnt | ((uint32_t)__popc(hm) << 16);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            uint32_t hv = __shfl_up_sync(0xFFFFFFFFu, hincl, d);
-            if (lane >= d) {
-                incl += v;
-                hincl += hv;
-            }
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, both, d);
+            if (lane >= d) both += v;
         }
+        const uint32_t incl = both & 0xFFFFu, hincl = both >> 16;
         if (lane == 31) {
             S.warp_tile[warp] = incl;
             if (warp < 2) S.halo_sum[warp] = hincl;
