@@ -38,6 +38,7 @@ extern "C" {
 #define SSD_ESTATE (-6)     /* call sequence violated                                                 */
 #define SSD_ERANGE (-7)     /* output buffer too small                                                */
 #define SSD_EINDEX (-8)     /* annotated header without two '_' (V2:397-398)           -> IndexError        */
+#define SSD_EIO (-9)        /* a file could not be opened, read or written              -> OSError            */
 
 /* -m semantics.  V2:411 keeps a cell when len(set(UMIs)) >= m; the bash pipeline's step 1
  * (demultiplex_using_barcodes.py:409) counts reads instead. */
@@ -109,6 +110,16 @@ int ssd_demux_device(ssd_ctx *ctx, const void *d_r1, size_t r1_len, const void *
 int ssd_annotated_device(ssd_ctx *ctx, const void *d_text, size_t len);
 /* The same from a HOST buffer, through to the filtered text (out == NULL and out_cap == 0: stop after the filter). */
 int ssd_annotated_host(ssd_ctx *ctx, const void *text, size_t len, void *out, size_t out_cap, size_t *written,
+                       ssd_stats *stats);
+
+/* File to file.  ssd_run_files = what V2.demultiplex_fun does with one pair of (chunk) files (V2:32-381):
+ * the two FASTQ files are read with pread on two host threads into pinned rings and uploaded as they arrive, the batch
+ * is demultiplexed, and the selected output is downloaded in chunks and written to out_path while the next chunk is in
+ * flight.  append != 0 appends like the reference (V2:367, 415), else the file is truncated first.
+ * ssd_annotated_file = V2.calc_demux_results (V2:384-454) on an annotated file. */
+int ssd_run_files(ssd_ctx *ctx, const char *path_r1, const char *path_r2, int which, const char *out_path, int append,
+                  size_t *written, ssd_stats *stats);
+int ssd_annotated_file(ssd_ctx *ctx, const char *path_in, const char *out_path, int append, size_t *written,
                        ssd_stats *stats);
 
 /* ---- phase 2: the -m decision, V2.calc_demux_results pass 1 (V2:389-412) ---------------------- */

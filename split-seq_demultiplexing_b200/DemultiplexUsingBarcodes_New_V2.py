@@ -41,14 +41,11 @@ def demultiplex_fun(inputFastqF, inputFastqR, outputDir, numReadsBin, errorThres
             print(line)
         learned.pop("_found")
         positions = learned
-    r1 = _read_file(inputFastqF)
-    r2 = _read_file(inputFastqR)
     dm = ssd_b200.Demultiplexer(whitelist, errors=int(errorThreshold), min_count=1, positions=positions)
     try:
-        out, stats = dm.run_host(r1, r2, ssd_b200.EMIT_MATCHED)
+        # file to file inside the library: pread into pinned rings, overlapped uploads, chunked download + append (V2:367)
+        _, stats = dm.run_files(str(inputFastqF), str(inputFastqR), str(outputDir + "/MergedCells_1.fastq"), ssd_b200.EMIT_MATCHED, append=True)
         print("The linesInInputFastq value is set to " + str(4 * stats["n_records_r1"]))  # V2:88-90 (complete records)
-        with open(str(outputDir + "/MergedCells_1.fastq"), "ab") as fh:       # V2:367 (append mode)
-            fh.write(out.tobytes())
     finally:
         dm.close()
     sys.stdout.flush()
@@ -60,12 +57,10 @@ def calc_demux_results(outputDir, performanceMetrics, readsPerCellThreshold):
     if performanceMetrics is not True:  # V2:391: the whole body hangs off this flag
         return
     whitelist = hostlogic.load_whitelist(".")
-    text = _read_file(str(outputDir + "/MergedCells_1.fastq"))
     dm = ssd_b200.Demultiplexer(whitelist, errors=0, min_count=int(readsPerCellThreshold))
     try:
-        out, stats = dm.filter_annotated_host(text)
-        with open(str(outputDir + "/MergedCells_passing.fastq"), "ab") as fh:  # V2:415 (append mode)
-            fh.write(out.tobytes())
+        _, stats = dm.filter_annotated_file(str(outputDir + "/MergedCells_1.fastq"), str(outputDir + "/MergedCells_passing.fastq"),
+                                            append=True)                      # V2:415 (append mode)
     finally:
         dm.close()
     for line in hostlogic.summary_lines(stats["n_cells"], readsPerCellThreshold, stats["n_passing_cells"]):

@@ -9,9 +9,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -27,6 +32,39 @@ thread_local char g_create_error[512] = "";
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+};
+
+}  // namespace
+
+namespace {
+constexpr size_t kIoChunk = (size_t)32 << 20;  // bytes per pinned ring slot
+constexpr int kIoSlots = 3;
+
+struct IoRing {
+    uint8_t* slot[kIoSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t done[kIoSlots] = {nullptr, nullptr, nullptr};
+    cudaStream_t stream = nullptr;
+    int init()
+    {
+        if (stream) return SSD_OK;
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return SSD_ECUDA;
+        for (int k = 0; k < kIoSlots; k++) {
+            if (cudaHostAlloc((void**)&slot[k], kIoChunk, cudaHostAllocDefault) != cudaSuccess) return SSD_ENOMEM;
+            if (cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming) != cudaSuccess) return SSD_ECUDA;
+        }
+        return SSD_OK;
+    }
+    void destroy()
+    {
+        for (int k = 0; k < kIoSlots; k++) {
+            if (slot[k]) cudaFreeHost(slot[k]);
+            if (done[k]) cudaEventDestroy(done[k]);
+            slot[k] = nullptr;
+            done[k] = nullptr;
+        }
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
 };
 
 }  // namespace
@@ -76,6 +114,7 @@ struct ssd_ctx {
     DevBuf b_status1, b_status2, b_r1_start, b_r1_meta, b_r1_base, b_r1_tok, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
         b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
     DevBuf b_in1, b_in2, b_out;
+    IoRing io[2];  // pinned rings + streams of the file-to-file entry points (created on first use)
     DevBuf b_os, b_irr_table;  // one-kernel-per-pass sort: histograms, tickets, tile status; hash set of the irregular keys
     DevBuf b_sp_cells, b_sp_cells_alt, b_sp_recs, b_sp_recs_alt, b_sp_off, b_bk_cell, b_bk_off, b_bk_first;
     // the irregular-key path runs on its own stream with its own scratch, next to the regular sort
@@ -772,6 +811,8 @@ extern "C" void ssd_destroy(ssd_ctx* c)
     release(c->s_offsets);
     release(c->s_bsums);
     release(c->s_pos);
+    c->io[0].destroy();
+    c->io[1].destroy();
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -1260,6 +1301,170 @@ extern "C" int ssd_run_host(ssd_ctx* c, const void* r1, size_t r1_len, const voi
         return SSD_OK;
     }
     return ssd_emit_host(c, which, out, out_cap, written);
+}
+
+// ================================================================================================
+// file to file
+// ================================================================================================
+namespace {
+// one host thread: pread chunk after chunk into the ring, each chunk uploaded as soon as it is read
+void upload_file_worker(int device, int fd, size_t size, uint8_t* d_dst, IoRing* ring, int* rc, int* err_no)
+{
+    *rc = SSD_OK;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        *rc = SSD_ECUDA;
+        return;
+    }
+    size_t off = 0;
+    for (int k = 0; off < size; k++) {
+        const int s = k % kIoSlots;
+        if (k >= kIoSlots && cudaEventSynchronize(ring->done[s]) != cudaSuccess) {
+            *rc = SSD_ECUDA;
+            return;
+        }
+        const size_t want = std::min(kIoChunk, size - off);
+        size_t got = 0;
+        while (got < want) {
+            const ssize_t n = pread(fd, ring->slot[s] + got, want - got, (off_t)(off + got));
+            if (n < 0 && errno == EINTR) continue;
+            if (n <= 0) {
+                *rc = SSD_EIO;
+                *err_no = n < 0 ? errno : EIO;
+                return;
+            }
+            got += (size_t)n;
+        }
+        if (cudaMemcpyAsync(d_dst + off, ring->slot[s], want, cudaMemcpyHostToDevice, ring->stream) != cudaSuccess ||
+            cudaEventRecord(ring->done[s], ring->stream) != cudaSuccess) {
+            *rc = SSD_ECUDA;
+            return;
+        }
+        off += want;
+    }
+    if (cudaStreamSynchronize(ring->stream) != cudaSuccess) *rc = SSD_ECUDA;
+}
+
+int open_input(ssd_ctx* c, const char* path, int* fd, size_t* size)
+{
+    *fd = open(path, O_RDONLY);
+    struct stat st;
+    if (*fd < 0 || fstat(*fd, &st) != 0) {
+        const int e = errno;
+        if (*fd >= 0) close(*fd);
+        *fd = -1;
+        return fail(c, SSD_EIO, "%s: %s", path, strerror(e));
+    }
+    *size = (size_t)st.st_size;
+    return SSD_OK;
+}
+
+// emit `which` on the device, then download it chunk by chunk while the previous chunk is being written to the file
+int download_to_file(ssd_ctx* c, int which, const char* out_path, int append, size_t* written)
+{
+    const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
+    if (written) *written = (size_t)need;
+    const int fd = open(out_path, O_WRONLY | O_CREAT | (append ? O_APPEND : O_TRUNC), 0644);
+    if (fd < 0) return fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
+    int rc = SSD_OK;
+    if (need) {
+        rc = ensure(c, c->b_out, need + 32);
+        if (rc == SSD_OK) rc = ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, nullptr);
+        if (rc == SSD_OK) rc = c->io[0].init();
+        if (rc == SSD_OK) {
+            IoRing& ring = c->io[0];
+            std::lock_guard<std::mutex> turn(g_d2h_turn);
+            cudaError_t e = cudaStreamSynchronize(c->stream);  // the emit kernel ran on the context's stream
+            const size_t n_chunks = (need + kIoChunk - 1) / kIoChunk;
+            auto issue = [&](size_t k) {
+                const size_t off = k * kIoChunk;
+                e = cudaMemcpyAsync(ring.slot[k % 2], (const uint8_t*)c->b_out.p + off, std::min(kIoChunk, (size_t)need - off), cudaMemcpyDeviceToHost,
+                                    ring.stream);
+                if (e == cudaSuccess) e = cudaEventRecord(ring.done[k % 2], ring.stream);
+            };
+            if (e == cudaSuccess) issue(0);
+            for (size_t k = 0; k < n_chunks && e == cudaSuccess && rc == SSD_OK; k++) {
+                e = cudaEventSynchronize(ring.done[k % 2]);
+                if (e != cudaSuccess) break;
+                if (k + 1 < n_chunks) issue(k + 1);
+                const size_t off = k * kIoChunk, len = std::min(kIoChunk, (size_t)need - off);
+                size_t put = 0;
+                while (put < len) {
+                    const ssize_t n = write(fd, ring.slot[k % 2] + put, len - put);
+                    if (n < 0 && errno == EINTR) continue;
+                    if (n <= 0) {
+                        rc = fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
+                        break;
+                    }
+                    put += (size_t)n;
+                }
+            }
+            if (e != cudaSuccess) {
+                cudaStreamSynchronize(ring.stream);
+                rc = fail(c, SSD_ECUDA, "download: %s", cudaGetErrorString(e));
+            } else {
+                cudaStreamSynchronize(ring.stream);
+            }
+        }
+    }
+    if (close(fd) != 0 && rc == SSD_OK) rc = fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
+    return rc;
+}
+}  // namespace
+
+extern "C" int ssd_run_files(ssd_ctx* c, const char* path_r1, const char* path_r2, int which, const char* out_path, int append, size_t* written,
+                             ssd_stats* stats)
+{
+    if (!c || !path_r1 || !path_r2 || !out_path) return SSD_EINVAL;
+    if (which != SSD_EMIT_MATCHED && which != SSD_EMIT_PASSING) return fail(c, SSD_EINVAL, "unknown output selector");
+    CU(c, cudaSetDevice(c->device));
+    int fd[2] = {-1, -1};
+    size_t size[2] = {0, 0};
+    OKR(open_input(c, path_r1, &fd[0], &size[0]));
+    int rc = open_input(c, path_r2, &fd[1], &size[1]);
+    if (rc == SSD_OK) rc = ensure(c, c->b_in1, size[0] + 32);
+    if (rc == SSD_OK) rc = ensure(c, c->b_in2, size[1] + 32);
+    if (rc == SSD_OK) rc = c->io[0].init();
+    if (rc == SSD_OK) rc = c->io[1].init();
+    if (rc == SSD_OK) {
+        std::lock_guard<std::mutex> turn(g_h2d_turn);
+        int wrc[2] = {SSD_OK, SSD_OK}, werr[2] = {0, 0};
+        std::thread t1(upload_file_worker, c->device, fd[0], size[0], (uint8_t*)c->b_in1.p, &c->io[0], &wrc[0], &werr[0]);
+        upload_file_worker(c->device, fd[1], size[1], (uint8_t*)c->b_in2.p, &c->io[1], &wrc[1], &werr[1]);
+        t1.join();
+        for (int k = 0; k < 2 && rc == SSD_OK; k++) {
+            if (wrc[k] == SSD_EIO) rc = fail(c, SSD_EIO, "%s: %s", k ? path_r2 : path_r1, strerror(werr[k]));
+            else if (wrc[k] != SSD_OK) rc = fail(c, wrc[k], "upload of %s failed", k ? path_r2 : path_r1);
+        }
+    }
+    for (int k = 0; k < 2; k++)
+        if (fd[k] >= 0) close(fd[k]);
+    if (rc != SSD_OK) return rc;
+    OKR(ssd_demux_device(c, c->b_in1.p, size[0], c->b_in2.p, size[1]));
+    OKR(ssd_filter_single(c, stats));
+    return download_to_file(c, which, out_path, append, written);
+}
+
+extern "C" int ssd_annotated_file(ssd_ctx* c, const char* path_in, const char* out_path, int append, size_t* written, ssd_stats* stats)
+{
+    if (!c || !path_in || !out_path) return SSD_EINVAL;
+    CU(c, cudaSetDevice(c->device));
+    int fd = -1;
+    size_t size = 0;
+    OKR(open_input(c, path_in, &fd, &size));
+    int rc = ensure(c, c->b_in1, size + 32);
+    if (rc == SSD_OK) rc = c->io[0].init();
+    if (rc == SSD_OK) {
+        std::lock_guard<std::mutex> turn(g_h2d_turn);
+        int wrc = SSD_OK, werr = 0;
+        upload_file_worker(c->device, fd, size, (uint8_t*)c->b_in1.p, &c->io[0], &wrc, &werr);
+        if (wrc == SSD_EIO) rc = fail(c, SSD_EIO, "%s: %s", path_in, strerror(werr));
+        else if (wrc != SSD_OK) rc = fail(c, wrc, "upload of %s failed", path_in);
+    }
+    close(fd);
+    if (rc != SSD_OK) return rc;
+    OKR(ssd_annotated_device(c, c->b_in1.p, size));
+    OKR(ssd_filter_single(c, stats));
+    return download_to_file(c, SSD_EMIT_PASSING, out_path, append, written);
 }
 
 extern "C" int ssd_annotated_host(ssd_ctx* c, const void* text, size_t len, void* out, size_t out_cap, size_t* written, ssd_stats* stats)

@@ -19,7 +19,7 @@ HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "ssd_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
-OK, EINVAL, ECUDA, EKEY, EMALFORMED, ENOMEM, ESTATE, ERANGE, EINDEX = 0, -1, -2, -3, -4, -5, -6, -7, -8
+OK, EINVAL, ECUDA, EKEY, EMALFORMED, ENOMEM, ESTATE, ERANGE, EINDEX, EIO = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9
 FILTER_DISTINCT_UMI, FILTER_READS = 0, 1
 EMIT_MATCHED, EMIT_PASSING = 0, 1
 
@@ -92,6 +92,8 @@ _SIGS = {
     "ssd_local_unique_keys": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "ssd_count_distinct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "ssd_count_distinct_owned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
+    "ssd_run_files": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(Stats)]),
+    "ssd_annotated_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(Stats)]),
     "ssd_key_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ssd_scan_repeats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "ssd_owner_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -3,6 +3,7 @@ error codes onto the exception types the reference raises."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 from . import _lib as L
@@ -25,6 +26,8 @@ def _raise(code: int, msg: str):
         raise ValueError(msg)
     if code == L.ENOMEM:
         raise MemoryError(msg)
+    if code == L.EIO:
+        raise (FileNotFoundError if "No such file" in msg else OSError)(msg)
     raise RuntimeError("libssd_b200 error %d: %s" % (code, msg))
 
 
@@ -257,6 +260,23 @@ class Demultiplexer:
         if n.value:
             self._check(self.lib.ssd_emit_host(self._ctx, which, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)))
         return out[: n.value], st.as_dict()
+
+    def run_files(self, path_r1: str, path_r2: str, out_path: str, which: int = L.EMIT_PASSING, append: bool = True):
+        """File to file (what V2.demultiplex_fun does with one pair of chunk files): reads, uploads, demultiplexes and
+        appends (or writes) the selected output to out_path, all inside the library with pinned rings and overlapped
+        copies.  Returns (bytes written, stats)."""
+        st = L.Stats()
+        n = C.c_size_t()
+        self._check(self.lib.ssd_run_files(self._ctx, os.fsencode(path_r1), os.fsencode(path_r2), which, os.fsencode(out_path), 1 if append else 0,
+                                           C.byref(n), C.byref(st)))
+        return n.value, st.as_dict()
+
+    def filter_annotated_file(self, path_in: str, out_path: str, append: bool = True):
+        """V2.calc_demux_results file to file: returns (bytes written, stats)."""
+        st = L.Stats()
+        n = C.c_size_t()
+        self._check(self.lib.ssd_annotated_file(self._ctx, os.fsencode(path_in), os.fsencode(out_path), 1 if append else 0, C.byref(n), C.byref(st)))
+        return n.value, st.as_dict()
 
     def filter_annotated_host(self, text):
         """V2.calc_demux_results on the text of MergedCells_1.fastq (any buffer-protocol object): returns

@@ -141,3 +141,36 @@ def test_host_pipeline_keeps_order_and_results():
     for (r1, r2), (out, st) in zip(batches, got):
         ref = orc.demultiplex(r1, r2, wl, 1, 2)
         assert out.tobytes() == ref.passing and st["n_matched"] == ref.n_matched
+
+
+def test_run_files_matches_run_host(tmp_path):
+    """ssd_run_files / ssd_annotated_file: file to file, same bytes as the buffer path and the oracle; append semantics
+    (V2:367, 415); a missing input raises FileNotFoundError."""
+    import ssd_b200
+    from oracle import ssd_oracle_py as orc
+    wl = fu.load_whitelist()
+    spec = ssd_b200.synth_spec(wl, 150_000, seed=31, cell_pool=2000)      # ~49 MB per file: several ring chunks
+    r1, r2 = ssd_b200.synth_host(spec)
+    p1, p2 = tmp_path / "f.fastq", tmp_path / "r.fastq"
+    p1.write_bytes(r1)
+    p2.write_bytes(r2)
+    ref = orc.demultiplex(r1, r2, wl, 1, 10)
+    dm = ssd_b200.Demultiplexer(wl, errors=1, min_count=10)
+    merged = tmp_path / "MergedCells_1.fastq"
+    n, st = dm.run_files(str(p1), str(p2), str(merged), ssd_b200.EMIT_MATCHED, append=True)
+    assert n == len(ref.merged1) and merged.read_bytes() == ref.merged1 and st["n_matched"] == ref.n_matched
+    n, _ = dm.run_files(str(p1), str(p2), str(merged), ssd_b200.EMIT_MATCHED, append=True)       # appends like the reference
+    assert merged.read_bytes() == ref.merged1 * 2
+    n, _ = dm.run_files(str(p1), str(p2), str(merged), ssd_b200.EMIT_MATCHED, append=False)      # truncates on request
+    assert merged.read_bytes() == ref.merged1
+    passing = tmp_path / "MergedCells_passing.fastq"
+    dm2 = ssd_b200.Demultiplexer(wl, errors=0, min_count=10)
+    n, st2 = dm2.filter_annotated_file(str(merged), str(passing), append=True)
+    assert passing.read_bytes() == ref.passing and st2["n_passing_cells"] == ref.n_passing_cells
+    with pytest.raises(FileNotFoundError):
+        dm.run_files(str(tmp_path / "missing.fastq"), str(p2), str(merged))
+    empty = tmp_path / "empty.fastq"
+    empty.write_bytes(b"")
+    out = tmp_path / "out.fastq"
+    n, st3 = dm.run_files(str(empty), str(empty), str(out), ssd_b200.EMIT_PASSING, append=False)
+    assert n == 0 and out.read_bytes() == b"" and st3["n_records_r1"] == 0
