@@ -189,6 +189,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=None, help="steps of the host-buffer loop (default min(steps, 5))")
+    ap.add_argument("--e2e-files", action="store_true",
+                    help="also time the file-to-file entry point (ssd_run_files) on files written to --files-dir (default /dev/shm)")
+    ap.add_argument("--files-dir", default="/dev/shm")
     ap.add_argument("--no-e2e-pipeline", action="store_true", help="measure the end-to-end leg one batch at a time only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -266,7 +269,7 @@ def main():
     h2.copy_(d2)
     hout = torch.empty(int(last["bytes_passing"]) + 4096, dtype=torch.uint8, pin_memory=True)
     a1, a2, aout = h1.numpy(), h2.numpy(), hout.numpy()
-    e2e_value, e2e_serial, d2h, e2e_note = None, None, 0, None
+    e2e_value, e2e_serial, d2h, e2e_note, files_value = None, None, 0, None, None
     if e2e_steps <= 0:
         pass
     elif world == 1:
@@ -303,6 +306,25 @@ def main():
                 e2e_value = piped
                 e2e_note = ("two contexts in flight on two host threads (each step: H2D of its inputs, kernels, D2H of its result); "
                             "one batch at a time gives serial_value")
+        if args.e2e_files:
+            # (c) file to file: the two FASTQ files in args.files_dir (RAM-backed by default, so that this measures the
+            #     library's ingest/egress path and not a disk), output written next to them
+            import tempfile
+            tmp = tempfile.mkdtemp(prefix="ssd_bench_", dir=args.files_dir)
+            try:
+                f1, f2, fo = os.path.join(tmp, "r1.fastq"), os.path.join(tmp, "r2.fastq"), os.path.join(tmp, "out.fastq")
+                a1.tofile(f1)
+                a2.tofile(f2)
+                dm.run_files(f1, f2, fo, ssd_b200.EMIT_PASSING, append=False)
+                t0 = time.perf_counter()
+                reps = max(1, min(3, e2e_steps))
+                for _ in range(reps):
+                    wrote, _ = dm.run_files(f1, f2, fo, ssd_b200.EMIT_PASSING, append=False)
+                files_value = n * reps / (time.perf_counter() - t0)
+                assert wrote == d2h
+            finally:
+                import shutil
+                shutil.rmtree(tmp, ignore_errors=True)
     else:
         # every rank moves its own shard host->device, runs the distributed step, and reads its output back
         def e2e_step():
@@ -361,7 +383,7 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in1 + in2) * world, "d2h_bytes_per_step": d2h * world,
-                        "steps": e2e_steps, "serial_value": e2e_serial, "note": e2e_note},
+                        "steps": e2e_steps, "serial_value": e2e_serial, "files_value": files_value, "note": e2e_note},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "result": {k: int(v) for k, v in last.items()}}
         print(json.dumps(line))

@@ -37,12 +37,13 @@ struct DevBuf {
 }  // namespace
 
 namespace {
-constexpr size_t kIoChunk = (size_t)32 << 20;  // bytes per pinned ring slot
-constexpr int kIoSlots = 3;
+constexpr size_t kIoChunk = (size_t)16 << 20;  // bytes per pinned slot
+constexpr int kIoLanes = 8;                    // host threads moving file data (4 per input file; 4 for the output)
+constexpr int kIoSlots = 2;                    // pinned slots per lane: one being filled / written, one in flight
 
-struct IoRing {
-    uint8_t* slot[kIoSlots] = {nullptr, nullptr, nullptr};
-    cudaEvent_t done[kIoSlots] = {nullptr, nullptr, nullptr};
+struct IoLane {  // what one I/O thread owns
+    uint8_t* slot[kIoSlots] = {nullptr, nullptr};
+    cudaEvent_t done[kIoSlots] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
     int init()
     {
@@ -66,7 +67,6 @@ struct IoRing {
         stream = nullptr;
     }
 };
-
 }  // namespace
 
 struct ssd_ctx {
@@ -114,7 +114,7 @@ struct ssd_ctx {
     DevBuf b_status1, b_status2, b_r1_start, b_r1_meta, b_r1_base, b_r1_tok, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
         b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
     DevBuf b_in1, b_in2, b_out;
-    IoRing io[2];  // pinned rings + streams of the file-to-file entry points (created on first use)
+    IoLane io[kIoLanes];  // pinned slots + streams of the file-to-file entry points (created on first use)
     DevBuf b_os, b_irr_table;  // one-kernel-per-pass sort: histograms, tickets, tile status; hash set of the irregular keys
     DevBuf b_sp_cells, b_sp_cells_alt, b_sp_recs, b_sp_recs_alt, b_sp_off, b_bk_cell, b_bk_off, b_bk_first;
     // the irregular-key path runs on its own stream with its own scratch, next to the regular sort
@@ -811,8 +811,7 @@ extern "C" void ssd_destroy(ssd_ctx* c)
     release(c->s_offsets);
     release(c->s_bsums);
     release(c->s_pos);
-    c->io[0].destroy();
-    c->io[1].destroy();
+    for (int k = 0; k < kIoLanes; k++) c->io[k].destroy();
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -1307,41 +1306,104 @@ extern "C" int ssd_run_host(ssd_ctx* c, const void* r1, size_t r1_len, const voi
 // file to file
 // ================================================================================================
 namespace {
-// one host thread: pread chunk after chunk into the ring, each chunk uploaded as soon as it is read
-void upload_file_worker(int device, int fd, size_t size, uint8_t* d_dst, IoRing* ring, int* rc, int* err_no)
+// one host thread of `stride`: pread chunks first, first + stride, ... into its pinned slots, each uploaded as soon as it is read
+void upload_file_worker(int device, int fd, size_t size, uint8_t* d_dst, IoLane* lane, int first, int stride, int* rc, int* err_no)
 {
     *rc = SSD_OK;
     if (cudaSetDevice(device) != cudaSuccess) {
         *rc = SSD_ECUDA;
         return;
     }
-    size_t off = 0;
-    for (int k = 0; off < size; k++) {
-        const int s = k % kIoSlots;
-        if (k >= kIoSlots && cudaEventSynchronize(ring->done[s]) != cudaSuccess) {
+    int n = 0;
+    for (size_t k = (size_t)first; k * kIoChunk < size; k += (size_t)stride, n++) {
+        const int s = n % kIoSlots;
+        if (n >= kIoSlots && cudaEventSynchronize(lane->done[s]) != cudaSuccess) {
             *rc = SSD_ECUDA;
             return;
         }
-        const size_t want = std::min(kIoChunk, size - off);
+        const size_t off = k * kIoChunk, want = std::min(kIoChunk, size - off);
         size_t got = 0;
         while (got < want) {
-            const ssize_t n = pread(fd, ring->slot[s] + got, want - got, (off_t)(off + got));
-            if (n < 0 && errno == EINTR) continue;
-            if (n <= 0) {
+            const ssize_t r = pread(fd, lane->slot[s] + got, want - got, (off_t)(off + got));
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) {
                 *rc = SSD_EIO;
-                *err_no = n < 0 ? errno : EIO;
+                *err_no = r < 0 ? errno : EIO;
                 return;
             }
-            got += (size_t)n;
+            got += (size_t)r;
         }
-        if (cudaMemcpyAsync(d_dst + off, ring->slot[s], want, cudaMemcpyHostToDevice, ring->stream) != cudaSuccess ||
-            cudaEventRecord(ring->done[s], ring->stream) != cudaSuccess) {
+        if (cudaMemcpyAsync(d_dst + off, lane->slot[s], want, cudaMemcpyHostToDevice, lane->stream) != cudaSuccess ||
+            cudaEventRecord(lane->done[s], lane->stream) != cudaSuccess) {
             *rc = SSD_ECUDA;
             return;
         }
-        off += want;
     }
-    if (cudaStreamSynchronize(ring->stream) != cudaSuccess) *rc = SSD_ECUDA;
+    if (cudaStreamSynchronize(lane->stream) != cudaSuccess) *rc = SSD_ECUDA;
+}
+
+// one host thread of `stride`: download chunks first, first + stride, ... and pwrite them at base + offset
+void download_file_worker(int device, int fd, size_t base, size_t size, const uint8_t* d_src, IoLane* lane, int first, int stride, int* rc, int* err_no)
+{
+    *rc = SSD_OK;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        *rc = SSD_ECUDA;
+        return;
+    }
+    auto issue = [&](size_t k, int s) {
+        const size_t off = k * kIoChunk;
+        return cudaMemcpyAsync(lane->slot[s], d_src + off, std::min(kIoChunk, size - off), cudaMemcpyDeviceToHost, lane->stream) == cudaSuccess &&
+               cudaEventRecord(lane->done[s], lane->stream) == cudaSuccess;
+    };
+    size_t k = (size_t)first;
+    if (k * kIoChunk < size && !issue(k, 0)) {
+        *rc = SSD_ECUDA;
+        return;
+    }
+    for (int n = 0; k * kIoChunk < size; k += (size_t)stride, n++) {
+        const int s = n % kIoSlots;
+        const size_t next = k + (size_t)stride;
+        if (next * kIoChunk < size && !issue(next, (n + 1) % kIoSlots)) {  // the other slot was written out in the previous round
+            *rc = SSD_ECUDA;
+            return;
+        }
+        if (cudaEventSynchronize(lane->done[s]) != cudaSuccess) {
+            *rc = SSD_ECUDA;
+            return;
+        }
+        const size_t off = k * kIoChunk, len = std::min(kIoChunk, size - off);
+        size_t put = 0;
+        while (put < len) {
+            const ssize_t w = pwrite(fd, lane->slot[s] + put, len - put, (off_t)(base + off + put));
+            if (w < 0 && errno == EINTR) continue;
+            if (w <= 0) {
+                *rc = SSD_EIO;
+                *err_no = w < 0 ? errno : EIO;
+                return;
+            }
+            put += (size_t)w;
+        }
+    }
+    if (cudaStreamSynchronize(lane->stream) != cudaSuccess) *rc = SSD_ECUDA;
+}
+
+// all lanes in [lane0, lane0 + n) work on one file; returns the first failure
+template <class Worker, class... A>
+int run_lanes(ssd_ctx* c, const char* path, int lane0, int n, Worker worker, A... a)
+{
+    int rc[kIoLanes], err[kIoLanes];
+    std::thread th[kIoLanes];
+    for (int t = 0; t < n; t++) {
+        rc[t] = SSD_OK;
+        err[t] = 0;
+        th[t] = std::thread(worker, a..., &c->io[lane0 + t], t, n, &rc[t], &err[t]);
+    }
+    for (int t = 0; t < n; t++) th[t].join();
+    for (int t = 0; t < n; t++) {
+        if (rc[t] == SSD_EIO) return fail(c, SSD_EIO, "%s: %s", path, strerror(err[t]));
+        if (rc[t] != SSD_OK) return fail(c, rc[t], "moving %s failed", path);
+    }
+    return SSD_OK;
 }
 
 int open_input(ssd_ctx* c, const char* path, int* fd, size_t* size)
@@ -1358,52 +1420,23 @@ int open_input(ssd_ctx* c, const char* path, int* fd, size_t* size)
     return SSD_OK;
 }
 
-// emit `which` on the device, then download it chunk by chunk while the previous chunk is being written to the file
+// emit `which` on the device, then download it with four threads, each overlapping its copies with its pwrites
 int download_to_file(ssd_ctx* c, int which, const char* out_path, int append, size_t* written)
 {
     const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
     if (written) *written = (size_t)need;
-    const int fd = open(out_path, O_WRONLY | O_CREAT | (append ? O_APPEND : O_TRUNC), 0644);
+    const int fd = open(out_path, O_WRONLY | O_CREAT | (append ? 0 : O_TRUNC), 0644);
     if (fd < 0) return fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
-    int rc = SSD_OK;
-    if (need) {
+    const off_t base = append ? lseek(fd, 0, SEEK_END) : 0;  // V2:367, 415 open in append mode
+    int rc = base < 0 ? fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno)) : SSD_OK;
+    if (need && rc == SSD_OK) {
         rc = ensure(c, c->b_out, need + 32);
         if (rc == SSD_OK) rc = ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, nullptr);
-        if (rc == SSD_OK) rc = c->io[0].init();
+        for (int k = 0; k < 4 && rc == SSD_OK; k++) rc = c->io[k].init();
+        if (rc == SSD_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, SSD_ECUDA, "emit failed");  // the emit kernel ran on the context's stream
         if (rc == SSD_OK) {
-            IoRing& ring = c->io[0];
             std::lock_guard<std::mutex> turn(g_d2h_turn);
-            cudaError_t e = cudaStreamSynchronize(c->stream);  // the emit kernel ran on the context's stream
-            const size_t n_chunks = (need + kIoChunk - 1) / kIoChunk;
-            auto issue = [&](size_t k) {
-                const size_t off = k * kIoChunk;
-                e = cudaMemcpyAsync(ring.slot[k % 2], (const uint8_t*)c->b_out.p + off, std::min(kIoChunk, (size_t)need - off), cudaMemcpyDeviceToHost,
-                                    ring.stream);
-                if (e == cudaSuccess) e = cudaEventRecord(ring.done[k % 2], ring.stream);
-            };
-            if (e == cudaSuccess) issue(0);
-            for (size_t k = 0; k < n_chunks && e == cudaSuccess && rc == SSD_OK; k++) {
-                e = cudaEventSynchronize(ring.done[k % 2]);
-                if (e != cudaSuccess) break;
-                if (k + 1 < n_chunks) issue(k + 1);
-                const size_t off = k * kIoChunk, len = std::min(kIoChunk, (size_t)need - off);
-                size_t put = 0;
-                while (put < len) {
-                    const ssize_t n = write(fd, ring.slot[k % 2] + put, len - put);
-                    if (n < 0 && errno == EINTR) continue;
-                    if (n <= 0) {
-                        rc = fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
-                        break;
-                    }
-                    put += (size_t)n;
-                }
-            }
-            if (e != cudaSuccess) {
-                cudaStreamSynchronize(ring.stream);
-                rc = fail(c, SSD_ECUDA, "download: %s", cudaGetErrorString(e));
-            } else {
-                cudaStreamSynchronize(ring.stream);
-            }
+            rc = run_lanes(c, out_path, 0, 4, download_file_worker, c->device, fd, (size_t)base, (size_t)need, (const uint8_t*)c->b_out.p);
         }
     }
     if (close(fd) != 0 && rc == SSD_OK) rc = fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
@@ -1423,18 +1456,14 @@ extern "C" int ssd_run_files(ssd_ctx* c, const char* path_r1, const char* path_r
     int rc = open_input(c, path_r2, &fd[1], &size[1]);
     if (rc == SSD_OK) rc = ensure(c, c->b_in1, size[0] + 32);
     if (rc == SSD_OK) rc = ensure(c, c->b_in2, size[1] + 32);
-    if (rc == SSD_OK) rc = c->io[0].init();
-    if (rc == SSD_OK) rc = c->io[1].init();
+    for (int k = 0; k < kIoLanes && rc == SSD_OK; k++) rc = c->io[k].init();
     if (rc == SSD_OK) {
         std::lock_guard<std::mutex> turn(g_h2d_turn);
-        int wrc[2] = {SSD_OK, SSD_OK}, werr[2] = {0, 0};
-        std::thread t1(upload_file_worker, c->device, fd[0], size[0], (uint8_t*)c->b_in1.p, &c->io[0], &wrc[0], &werr[0]);
-        upload_file_worker(c->device, fd[1], size[1], (uint8_t*)c->b_in2.p, &c->io[1], &wrc[1], &werr[1]);
-        t1.join();
-        for (int k = 0; k < 2 && rc == SSD_OK; k++) {
-            if (wrc[k] == SSD_EIO) rc = fail(c, SSD_EIO, "%s: %s", k ? path_r2 : path_r1, strerror(werr[k]));
-            else if (wrc[k] != SSD_OK) rc = fail(c, wrc[k], "upload of %s failed", k ? path_r2 : path_r1);
-        }
+        int rc2 = SSD_OK;
+        std::thread other([&] { rc2 = run_lanes(c, path_r2, 4, 4, upload_file_worker, c->device, fd[1], size[1], (uint8_t*)c->b_in2.p); });
+        rc = run_lanes(c, path_r1, 0, 4, upload_file_worker, c->device, fd[0], size[0], (uint8_t*)c->b_in1.p);
+        other.join();
+        if (rc == SSD_OK) rc = rc2;
     }
     for (int k = 0; k < 2; k++)
         if (fd[k] >= 0) close(fd[k]);
@@ -1452,13 +1481,10 @@ extern "C" int ssd_annotated_file(ssd_ctx* c, const char* path_in, const char* o
     size_t size = 0;
     OKR(open_input(c, path_in, &fd, &size));
     int rc = ensure(c, c->b_in1, size + 32);
-    if (rc == SSD_OK) rc = c->io[0].init();
+    for (int k = 0; k < kIoLanes && rc == SSD_OK; k++) rc = c->io[k].init();
     if (rc == SSD_OK) {
         std::lock_guard<std::mutex> turn(g_h2d_turn);
-        int wrc = SSD_OK, werr = 0;
-        upload_file_worker(c->device, fd, size, (uint8_t*)c->b_in1.p, &c->io[0], &wrc, &werr);
-        if (wrc == SSD_EIO) rc = fail(c, SSD_EIO, "%s: %s", path_in, strerror(werr));
-        else if (wrc != SSD_OK) rc = fail(c, wrc, "upload of %s failed", path_in);
+        rc = run_lanes(c, path_in, 0, kIoLanes, upload_file_worker, c->device, fd, size, (uint8_t*)c->b_in1.p);
     }
     close(fd);
     if (rc != SSD_OK) return rc;
