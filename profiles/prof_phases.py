@@ -12,7 +12,7 @@ dm.lib.ssd_debug_scan_profile.argtypes=[C.c_void_p, C.c_int]
 dm.lib.ssd_debug_scan_profile(buf, 1)
 dm.demux_device(d1.data_ptr(), d1.numel(), d2.data_ptr(), d2.numel())
 dm.lib.ssd_debug_scan_profile(buf, 0)
-names={0:'A.wait_full',1:'A.mask',2:'A.count+list',9:'A.wait_list_empty',5:'B.wait_list',6:'B.compute',3:'B.poll+sync',8:'B.poll_only',4:'B.commit',10:'A.popc+scan',11:'A.sync1',12:'A.bases+emit',13:'A.sync2'}
+names={0:'A.wait_full',1:'A.mask',2:'A.count+list',9:'A.wait_list_empty',5:'B.wait_list',6:'B.compute',3:'B.poll+sync',8:'B.poll_only',4:'B.commit',10:'A.popc+scan',11:'A.sync1',12:'A.bases+emit',13:'A.sync2',14:'B.header',15:'B.windows+umi'}
 for m in (0,1):
     n=buf[m*16+7]
     print('R%d tiles=%d'%(m+1,n), {v: round(buf[m*16+k]/max(n,1)) for k,v in names.items()})
