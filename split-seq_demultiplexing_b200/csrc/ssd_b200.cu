@@ -116,6 +116,7 @@ struct ssd_ctx {
     DevBuf b_in1, b_in2, b_out;
     IoLane io[kIoLanes];  // pinned slots + streams of the file-to-file entry points (created on first use)
     DevBuf b_os, b_irr_table;  // one-kernel-per-pass sort: histograms, tickets, tile status; hash set of the irregular keys
+    DevBuf b_seg;              // per-cell hash sets of the regular keys: key counts (when not the read histogram) and segment offsets
     DevBuf b_sp_cells, b_sp_cells_alt, b_sp_recs, b_sp_recs_alt, b_sp_off, b_bk_cell, b_bk_off, b_bk_first;
     // the irregular-key path runs on its own stream with its own scratch, next to the regular sort
     cudaStream_t side_stream = nullptr;
@@ -442,6 +443,37 @@ int irr_hash_counts(ssd_ctx* c, const IrrKey* keys, uint64_t n, cudaStream_t st,
     return SSD_OK;
 }
 
+// Regular keys into per-cell hash sets (k_umi_sets): distinct[cell] += first occurrences.  `counts` = per-cell number of
+// keys (an upper bound will do) or nullptr to count the keys here; `table` is scratch for 2 x n_keys_bound 32-bit slots.
+inline bool use_sort_for_distinct(uint64_t n_keys_bound)
+{
+    static const bool v = getenv("SSD_DISTINCT_SORT") != nullptr;
+    return v || n_keys_bound >= (1ull << 31);  // segment offsets are 32-bit
+}
+
+template <class Src>
+int umi_set_counts(ssd_ctx* c, Src src, uint64_t n_src, uint64_t n_keys_bound, const uint32_t* counts, DevBuf* table)
+{
+    const uint64_t nc = c->n_cells_total;
+    OKR(ensure(c, c->b_seg, (2 * nc + 2) * sizeof(uint32_t)));
+    uint32_t* seg = (uint32_t*)c->b_seg.p;
+    if (!counts) {
+        uint32_t* own = seg + nc + 1;
+        CU(c, cudaMemsetAsync(own, 0, nc * sizeof(uint32_t), c->stream));
+        k_cell_key_counts<Src><<<blocks_for(n_src, kThreads), kThreads, 0, c->stream>>>(src, n_src, c->dcfg.umi_bits, own);
+        c->n_launches++;
+        counts = own;
+    }
+    const uint32_t bitmap_words = c->dcfg.umi_bits >= 5 ? 1u << (c->dcfg.umi_bits - 5) : 1u;
+    OKR(exclusive_scan<uint32_t>(c, UmiSetWords{counts, bitmap_words}, nc, seg));
+    OKR(ensure(c, *table, 2 * n_keys_bound * sizeof(uint32_t)));
+    CU(c, cudaMemsetAsync(table->p, 0, 2 * n_keys_bound * sizeof(uint32_t), c->stream));
+    k_umi_sets<Src><<<(uint32_t)std::min<uint64_t>(blocks_for(n_src, kThreads), 148 * 8), kThreads, 0, c->stream>>>(src, n_src, c->dcfg.umi_bits, counts, seg, (uint32_t*)table->p, c->d_distinct);
+    c->n_launches++;
+    CU(c, cudaGetLastError());
+    return SSD_OK;
+}
+
 // Per-cell distinct counts of arbitrary key arrays (duplicates allowed; d_keys is reordered): what a rank does with the
 // keys its peers sent for the cells it owns.
 int distinct_counts_arrays(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys, const IrrKey* d_irr, uint64_t n_irr, int rank = 0, int world = 0)
@@ -458,12 +490,17 @@ int distinct_counts_arrays(ssd_ctx* c, uint64_t* d_keys, uint64_t n_keys, const 
         OKR(irr_hash_counts(c, d_irr, n_irr, st, rank, world));
         if (side) CU(c, cudaEventRecord(c->ev_join, st));
     }
-    if (n_keys) {
+    if (n_keys && use_sort_for_distinct(n_keys)) {
         OKR(ensure(c, c->b_keys_alt, n_keys * sizeof(uint64_t)));
         uint64_t* sorted = nullptr;
         OKR(os_sort64(c, false, d_keys, (uint64_t*)c->b_keys_alt.p, n_keys, c->dcfg.umi_bits + c->dcfg.cell_bits, &sorted));
         k_count_sorted<<<blocks_for(n_keys, kThreads), kThreads, 0, c->stream>>>(sorted, n_keys, c->dcfg.umi_bits, c->d_distinct);
         c->n_launches++;
+    } else if (n_keys) {
+        // scratch for the sets: whichever key buffer of the context the caller's keys do not live in
+        const char* kp = (const char*)d_keys;
+        const bool in_alt = c->b_keys_alt.p && kp >= (const char*)c->b_keys_alt.p && kp < (const char*)c->b_keys_alt.p + c->b_keys_alt.cap;
+        OKR(umi_set_counts(c, KeysArray{d_keys}, n_keys, n_keys, nullptr, in_alt ? &c->b_keys : &c->b_keys_alt));
     }
     if (side) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     CU(c, cudaGetLastError());
@@ -485,7 +522,10 @@ int distinct_counts_local(ssd_ctx* c)
         OKR(irr_hash_counts(c, nullptr, n_irr, st));
         if (side) CU(c, cudaEventRecord(c->ev_join, st));
     }
-    if (n_keys) {
+    if (n_keys && !use_sort_for_distinct(n_keys + n_irr)) {
+        // the read histogram of the batch is the per-cell key count (irregular keys included: those sets are a little larger)
+        OKR(umi_set_counts(c, KeysFromAnnStream{(const uint64_t*)c->b_ann.p, c->dcfg.umi_bits}, c->n_rec_r2, n_keys + n_irr, c->d_hist, &c->b_keys));
+    } else if (n_keys) {
         OKR(ensure(c, c->b_keys, n_keys * sizeof(uint64_t)));
         OKR(ensure(c, c->b_keys_alt, n_keys * sizeof(uint64_t)));
         uint64_t* sorted = nullptr;
@@ -796,7 +836,7 @@ extern "C" void ssd_destroy(ssd_ctx* c)
     DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_r1_start, &c->b_r1_meta, &c->b_r1_base, &c->b_r1_tok, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
                       &c->b_irr_alt, &c->b_perm, &c->b_perm_alt, &c->b_tmp64a, &c->b_tmp64b, &c->b_counts, &c->b_offsets, &c->b_bsums,
                       &c->b_pos, &c->b_out_off, &c->b_cells, &c->b_in1, &c->b_in2, &c->b_out, &c->b_sp_cells, &c->b_sp_cells_alt, &c->b_sp_recs,
-                      &c->b_sp_recs_alt, &c->b_sp_off, &c->b_bk_cell, &c->b_bk_off, &c->b_bk_first, &c->b_os, &c->b_irr_table};
+                      &c->b_sp_recs_alt, &c->b_sp_off, &c->b_bk_cell, &c->b_bk_off, &c->b_bk_first, &c->b_os, &c->b_irr_table, &c->b_seg};
     for (DevBuf* b : bufs) release(*b);
     cudaFree(c->d_cnt);
     cudaFree(c->d_err_off);

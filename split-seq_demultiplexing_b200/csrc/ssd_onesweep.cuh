@@ -6,6 +6,9 @@
 // decoupled look-back over per-tile digit counts, reorders the tile in shared memory and writes digit runs
 // contiguously.  The first pass reads the annotation words directly (compaction for free).  A last kernel counts the
 // first occurrences per cell in the sorted keys, one atomic per (warp, cell).
+// On one GPU (and for the keys a rank receives for its cells) the sort is not needed at all: k_umi_sets below inserts
+// the keys into per-cell hash sets sized from the per-cell key counts; the sort remains for hosts that want the
+// sorted unique lists (ssd_local_unique_keys) and behind SSD_DISTINCT_SORT=1.
 // Irregular keys (UMI with non-ACGT bytes or short; raw bytes, 128 bits) are few: an open-addressing hash set with
 // 128-bit compare-and-swap, exact, one kernel, on the side stream.
 #pragma once
@@ -163,6 +166,115 @@ __global__ void __launch_bounds__(kThreads) k_count_sorted(const uint64_t* keys,
         const uint32_t c = (uint32_t)__popc(heads & peers);
         if (c) atomicAdd(&distinct[cell], c);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// regular keys, without sorting: one exact open-addressing set PER CELL
+// ---------------------------------------------------------------------------------------------
+// A cell with h keys (its entry of the read histogram, or of a count of the keys at hand) owns the 2 h consecutive
+// 32-bit slots starting at seg[cell] (seg = exclusive scan of the per-cell set sizes), so every set is at most half
+// full and a slot only has to hold the UMI (<= 20 bits, stored + 1; zero = empty).  A cell with so many keys that one
+// bit per possible UMI is smaller than that (2 h > 4^umi_len / 32 words) gets the bitmap instead.  The first insertion
+// of a (cell, UMI) adds one to distinct[cell]; that is the len(set(...)) of V2:411 with one read of the keys and no
+// ordering at all.
+struct UmiSetWords {
+    const uint32_t* counts;
+    uint32_t bitmap_words;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const
+    {
+        const uint64_t w = 2ull * counts[i];
+        return w > bitmap_words ? bitmap_words : (uint32_t)w;
+    }
+};
+template <class Src>
+__global__ void __launch_bounds__(kThreads) k_cell_key_counts(Src keys, uint64_t n, int umi_bits, uint32_t* counts)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = keys(i);
+    if (k != kNoKey) atomicAdd(&counts[(uint32_t)(k >> umi_bits)], 1u);
+}
+
+// Cells with many keys would serialise their `distinct` updates on one address (the largest cell of the bench workload
+// holds 8 % of the reads): a block collects the first occurrences of such cells in a small direct-mapped table in
+// shared memory and adds them once at the end; a conflict in that table falls back to the global atomic.
+constexpr uint32_t kHotCellKeys = 512;  // a cell with at least this many keys goes through the block's table
+constexpr int kHotSlots = 256;
+// The work per key is a chain of dependent long-latency accesses (key -> per-cell count and offset -> compare-and-swap), so
+// the loop is software-pipelined: while key i is inserted, the count and offset of key i + 1 and key i + 2 itself are on
+// their way.
+template <class Src>
+__global__ void __launch_bounds__(kThreads) k_umi_sets(Src keys, uint64_t n, int umi_bits, const uint32_t* __restrict__ counts,
+                                                       const uint32_t* __restrict__ seg, uint32_t* table, uint32_t* distinct)
+{
+    const uint32_t bitmap_words = umi_bits >= 5 ? 1u << (umi_bits - 5) : 1u;
+    __shared__ uint32_t s_cell[kHotSlots], s_cnt[kHotSlots];
+    for (int j = threadIdx.x; j < kHotSlots; j += kThreads) {
+        s_cell[j] = 0xFFFFFFFFu;
+        s_cnt[j] = 0;
+    }
+    __syncthreads();
+    const uint64_t G = (uint64_t)gridDim.x * kThreads;
+    uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    uint64_t k1 = i < n ? keys(i) : kNoKey;          // key i
+    uint64_t k2 = i + G < n ? keys(i + G) : kNoKey;  // key i + 1 (in units of the grid stride)
+    uint32_t cnt1 = 0, sg1 = 0;
+    if (k1 != kNoKey) {
+        cnt1 = __ldg(counts + (uint32_t)(k1 >> umi_bits));
+        sg1 = __ldg(seg + (uint32_t)(k1 >> umi_bits));
+    }
+    for (; i < n; i += G) {
+        const uint64_t k = k1;
+        const uint32_t cnt = cnt1, sg = sg1;
+        // next stage of the two keys behind this one
+        k1 = k2;
+        cnt1 = sg1 = 0;
+        if (k1 != kNoKey) {
+            cnt1 = __ldg(counts + (uint32_t)(k1 >> umi_bits));
+            sg1 = __ldg(seg + (uint32_t)(k1 >> umi_bits));
+        }
+        k2 = i + 2 * G < n ? keys(i + 2 * G) : kNoKey;
+        if (k == kNoKey || cnt == 0u) continue;  // cnt == 0 cannot happen: the key itself was counted
+        const uint32_t cell = (uint32_t)(k >> umi_bits), umi = (uint32_t)k & ((1u << umi_bits) - 1u);
+        const uint64_t slots = 2ull * cnt;
+        uint32_t* set = table + sg;
+        if (slots > (uint64_t)bitmap_words) {
+            // a large cell: one bit per possible UMI is smaller than its hash set (and stays in the cache)
+            const uint32_t bit = 1u << (umi & 31u);
+            const uint32_t old = atomicOr(set + (umi >> 5), bit);
+            if (!(old & bit)) {
+                const uint32_t e = (cell * 0x9E3779B1u) >> 24;
+                const uint32_t prev = atomicCAS(&s_cell[e], 0xFFFFFFFFu, cell);
+                if (prev == 0xFFFFFFFFu || prev == cell) atomicAdd(&s_cnt[e], 1u);
+                else atomicAdd(&distinct[cell], 1u);
+            }
+            continue;
+        }
+        uint32_t h = umi * 0x9E3779B1u;
+        h = (h ^ (h >> 15)) * 0x85EBCA77u;
+        uint64_t s = ((uint64_t)h * slots) >> 32;
+        const uint32_t val = umi + 1u;
+        for (;;) {
+            const uint32_t old = atomicCAS(set + s, 0u, val);
+            if (old == val) break;  // seen before
+            if (old == 0u) {        // first occurrence of this (cell, UMI)
+                bool local = false;
+                if (cnt >= kHotCellKeys) {
+                    const uint32_t e = (cell * 0x9E3779B1u) >> 24;
+                    static_assert(kHotSlots == 256, "8-bit slot index");
+                    const uint32_t prev = atomicCAS(&s_cell[e], 0xFFFFFFFFu, cell);
+                    local = prev == 0xFFFFFFFFu || prev == cell;
+                    if (local) atomicAdd(&s_cnt[e], 1u);
+                }
+                if (!local) atomicAdd(&distinct[cell], 1u);
+                break;
+            }
+            if (++s == slots) s = 0;
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < kHotSlots; j += kThreads)
+        if (s_cnt[j]) atomicAdd(&distinct[s_cell[j]], s_cnt[j]);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -189,6 +189,21 @@ struct KeysFromAnn {
     }
 };
 
+// the same, read with the streaming hint: the words are used once and should not push other data out of the L2
+struct KeysFromAnnStream {
+    const uint64_t* ann;
+    int umi_bits;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const
+    {
+#ifdef SSD_UMI_NOSTREAM
+        const uint64_t a = ann[i];
+#else
+        const uint64_t a = __ldcs(reinterpret_cast<const unsigned long long*>(ann) + i);
+#endif
+        return ann_state(a) == 1 ? (((uint64_t)ann_cell(a) << umi_bits) | ann_payload(a)) : kNoKey;
+    }
+};
+
 template <class Src>
 __global__ void __launch_bounds__(kThreads) k_sort_hist(Src keys, uint64_t n, int bit, uint32_t* counts, uint32_t n_blocks)
 {
