@@ -160,6 +160,19 @@ def test_device_resident_path_1m(ssd, orc):
     assert dm.record_cells().tolist() == ref.rec_cell
 
 
+@pytest.mark.parametrize("cell_pool,p_dup", [(3, 0.5), (40, 0.05)])
+def test_large_cells_use_umi_bitmaps(ssd, orc, cell_pool, p_dup):
+    """Cells with more than 4^10 / 64 keys count their distinct UMIs in a bitmap, smaller ones in a hash set (k_umi_sets);
+    both next to each other, with many duplicates, against the oracle's len(set(...))."""
+    spec = ssd.synth_spec(WL, 150000, seed=0xB17, cell_pool=cell_pool, p_dup_umi=p_dup, p_junk=0.02)
+    r1, r2 = ssd.synth_host(spec)
+    ref = orc.demultiplex(r1, r2, WL, 1, 10)
+    dm, merged, passing, stats = run_both(ssd, r1, r2, 1, 10)
+    assert max(v[0] for v in ref.cells.values()) > 20000  # at least one cell is past the bitmap threshold
+    assert dm.cell_table() == {c.decode(): (v[0], v[1]) for c, v in ref.cells.items()}
+    assert passing == ref.passing
+
+
 def test_reads_filter_mode(ssd, orc):
     # SSD_FILTER_READS keeps cells with >= m READS (the north_star histogram filter); V2 counts distinct UMIs
     spec = ssd.synth_spec(WL, 20000, seed=5, cell_pool=300, p_dup_umi=0.6)
@@ -380,17 +393,35 @@ def test_short_records_repeat_once_per_context(ssd, orc):
     assert again.tobytes() == ref.passing and dm.scan_repeats() == 1
 
 
-def test_full_size_10m_properties(ssd):
-    """BASELINE.json's configuration (10 M synthetic pairs, e=1, -m 10) is far beyond what the CPU oracle finishes in
-    seconds, so it is checked through size-independent properties: the per-cell tables are additive over a split of
-    the input into two halves (reads exactly, distinct UMIs as an upper bound that is tight for cells seen in only one
-    half), the statistics follow from the tables, and the output has exactly four lines per retained record, every
-    one of a passing cell."""
+FULL_SIZE = [
+    # BASELINE.json configs[1]: 10 M pairs, e=1, merged output
+    pytest.param(10_000_000, 1, 10, dict(seed=0x5EED0001), dict(), False, id="config2-10M-e1"),
+    # configs[2]: 100 M pairs, e=2, N bases, planted 2/2 ties, truncated read 2, RanHex/OligoDT collapse on
+    pytest.param(100_000_000, 2, 10, dict(seed=0x5EED0002, cell_pool=1_000_000, p_n=0.01, p_tie=0.01, p_trunc=0.005),
+                 dict(collapse_pairs=48), False, id="config3-100M-e2-collapse"),
+    # configs[4]: split-mode bucketing of 100 M pairs over the 96^3 cells
+    pytest.param(100_000_000, 1, 10, dict(seed=0x5EED0004, cell_pool=1_000_000), dict(), True, id="config5-100M-split"),
+]
+
+
+@pytest.mark.parametrize("n,e,m,spec_kw,dm_kw,split", FULL_SIZE)
+def test_full_size_properties(ssd, n, e, m, spec_kw, dm_kw, split):
+    """BASELINE.json's full-size configurations are far beyond what the CPU oracle finishes in seconds, so they are checked
+    through size-independent properties: the per-cell tables are additive over a split of the input into two halves (reads
+    exactly, distinct UMIs as an upper bound that is tight for cells seen in only one half), the statistics follow from the
+    tables, the output has exactly four lines per retained record and every record starts with '@'; in split mode the
+    buckets partition the merged output (same bytes in total, one passing cell per bucket, sizes = the cells' bytes).
+    Inputs of 100 M pairs are 32.7 GB per file: they also exercise the 64-bit record offsets for real."""
+    import gc
     import torch
-    n, m = 10_000_000, 10
-    dm = ssd.Demultiplexer(WL, errors=1, min_count=m, record_bytes_hint=160)
-    spec = ssd.synth_spec(WL, n, seed=0x5EED0001)
-    d1, d2 = ssd.synth_device(dm, spec)
+    gc.collect()
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    need = (1_480 if split else 1_150) * n  # both files, the output (twice in split mode), per-record tables, slack
+    if free < need:
+        pytest.skip("needs %d GB of free device memory, %d GB are free" % (need >> 30, free >> 30))
+    dm = ssd.Demultiplexer(WL, errors=e, min_count=m, record_bytes_hint=160, **dm_kw)
+    d1, d2 = ssd.synth_device(dm, ssd.synth_spec(WL, n, **spec_kw))
     out, stats = dm.run_device(d1, d2, ssd.EMIT_PASSING)
     torch.cuda.synchronize()
     hist = dm.reads_histogram().clone().to(torch.int64)
@@ -401,19 +432,47 @@ def test_full_size_10m_properties(ssd):
     assert int((hist > 0).sum()) == stats["n_cells"] and int(passing.sum()) == stats["n_passing_cells"]
     assert int(hist[passing].sum()) == stats["n_retained"]
     assert bool((distinct <= hist).all()) and bool(((distinct > 0) == (hist > 0)).all())
-    assert out.numel() == stats["bytes_passing"] and int((out == 10).sum()) == 4 * stats["n_retained"]
-    # every output header carries a passing cell: '_' + 24 barcode bytes + '_' right after the id
-    starts = torch.nonzero(out == 10).flatten()[3::4] + 1                      # record starts (all but the first)
-    starts = torch.cat([torch.zeros(1, dtype=starts.dtype, device=starts.device), starts[:-1]])
-    assert bool((out[starts] == ord("@")).all())
-    del out, starts
+    assert out.numel() == stats["bytes_passing"]
+    # four lines per retained record, each record starting with '@' (counted in slices: the masks are as large as the output)
+    n_nl, chunk = 0, 1 << 30
+    for lo in range(0, out.numel(), chunk):
+        nl = torch.nonzero(out[lo:lo + chunk] == 10).flatten() + lo
+        first_idx = n_nl                                   # global index of this slice's first newline
+        n_nl += nl.numel()
+        k0 = (3 - first_idx) % 4                           # newlines number 3, 7, 11, ... end a record
+        ends = nl[k0::4]
+        ends = ends[ends + 1 < out.numel()]
+        assert bool((out[ends + 1] == ord("@")).all())
+        del nl, ends
+    assert n_nl == 4 * stats["n_retained"] and (out.numel() == 0 or int(out[0]) == ord("@"))
+    if split:
+        sp_out = torch.empty(stats["bytes_passing"] + 16, dtype=torch.uint8, device="cuda")
+        nbytes, table, _ = dm.emit_split_device(sp_out.data_ptr(), sp_out.numel())
+        assert nbytes == stats["bytes_passing"] and len(table) == stats["n_passing_cells"]
+        cells = [t[0] for t in table]
+        assert len(set(cells)) == len(cells)
+        offs = [t[1] for t in table]
+        assert offs == sorted(offs) and offs[0] == 0 and offs[-1] + table[-1][3] == nbytes
+        assert all(offs[k] + table[k][3] == offs[k + 1] for k in range(len(table) - 1))
+        # the same multiset of bytes as the merged output, and a sample of buckets holds only its own cell
+        hm, hs = torch.zeros(256, dtype=torch.int64, device="cuda"), torch.zeros(256, dtype=torch.int64, device="cuda")
+        for lo in range(0, nbytes, chunk):
+            hm += torch.bincount(out[lo:lo + chunk].to(torch.int32), minlength=256)
+            hs += torch.bincount(sp_out[lo:min(lo + chunk, nbytes)].to(torch.int32), minlength=256)
+        assert bool((hm == hs).all())
+        step = max(1, len(table) // 50)
+        for cell, off, _, nb in table[::step]:
+            recs = fu.records(sp_out[off:off + nb].cpu().numpy().tobytes())
+            assert recs and all(r.split(b"\n", 1)[0].split(b"_")[1] == cell.encode() for r in recs)
+        del sp_out
+    del out
     # additivity over two halves of the same input (generated separately: the generator is counter based)
     halves_hist = torch.zeros_like(hist)
     halves_distinct = torch.zeros_like(distinct)
     del d1, d2
+    torch.cuda.empty_cache()
     for first in (1, n // 2 + 1):
-        sp = ssd.synth_spec(WL, n // 2, seed=0x5EED0001, first_index=first)
-        h1, h2 = ssd.synth_device(dm, sp)
+        h1, h2 = ssd.synth_device(dm, ssd.synth_spec(WL, n // 2, first_index=first, **spec_kw))
         dm.run_device(h1, h2, ssd.EMIT_PASSING)
         torch.cuda.synchronize()
         hh = dm.reads_histogram().to(torch.int64)
@@ -425,6 +484,8 @@ def test_full_size_10m_properties(ssd):
         del h1, h2
     assert bool((halves_hist == hist).all())
     assert bool((halves_distinct >= distinct).all())
+    dm.close()
+    torch.cuda.empty_cache()
 
 
 @pytest.mark.parametrize("seed", range(24))
