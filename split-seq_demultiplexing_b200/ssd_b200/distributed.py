@@ -128,6 +128,73 @@ def global_filter(dm, world: int, group=None) -> dict:
     return dm.filter_single()
 
 
+def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, sink=None) -> dict:
+    """Inputs too large for one call (BASELINE config 4: 10^9 read pairs; 64 GiB per file is the per-call limit, the HBM of one
+    GPU the practical one): the -m decision needs every batch's per-cell read counts and (cell, UMI) keys before the first
+    record can be written, so the batches are gone through twice, the way the reference goes through its chunk files
+    (CLI3:56-64) and then through MergedCells_1.fastq (V2:389-454).
+
+      pass 1  every batch: scan + match (dm.demux_device); its read histogram is added up, its (cell, UMI) keys are kept
+              (one GPU: the batch's sorted unique list; N GPUs: grouped by owner rank and sent there right away).
+              Then one exact distinct count over everything kept, and the all-reduces of the two tables when N > 1.
+      pass 2  every batch again: scan + match, the GLOBAL tables put in place of the batch's own, filter, write.
+
+    `batches` is a callable returning an iterator of (r1, r2) uint8 CUDA tensors (called twice; every rank passes its own
+    shard's batches).  sink(out_tensor, stats) receives each batch's output in order (the tensor is only valid during the
+    call); without a sink the outputs are dropped.  Returns the statistics summed over the batches (cell counts are global)."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib as L
+    which = L.EMIT_PASSING if which is None else which
+    distinct_mode = dm.filter_mode == "distinct_umi"
+    rank = dist.get_rank(group) if world > 1 else 0
+    hist, kept_k, kept_i = None, [], []
+    for r1, r2 in batches():
+        dm.demux_device(r1.data_ptr(), r1.numel(), r2.data_ptr(), r2.numel(), keep=(r1, r2))
+        h = dm.reads_histogram()
+        hist = h.clone() if hist is None else hist.add_(h)
+        if distinct_mode:
+            if world > 1:
+                keys, offsets, irr = dm.partition_keys(world)
+                k, i = exchange_owned(keys, [offsets[j + 1] - offsets[j] for j in range(world)], irr, group=group)
+            else:
+                k, i = dm.local_unique_keys()
+            kept_k.append(k.clone())
+            kept_i.append(i.clone())
+    if hist is None:
+        return {}
+    distinct = None
+    if distinct_mode:
+        all_k = torch.cat(kept_k) if kept_k else torch.empty(0, dtype=torch.int64, device="cuda")
+        all_i = torch.cat(kept_i) if kept_i else torch.empty((0, 2), dtype=torch.int64, device="cuda")
+        del kept_k, kept_i
+        if world > 1:
+            dm.count_distinct_owned(all_k, all_i, rank, world)
+            dist.all_reduce(dm.distinct_histogram(), group=group)
+        else:
+            dm.count_distinct(all_k, all_i)
+        distinct = dm.distinct_histogram().clone()
+        del all_k, all_i
+    if world > 1:
+        dist.all_reduce(hist, group=group)
+    total = {}
+    for r1, r2 in batches():
+        dm.demux_device(r1.data_ptr(), r1.numel(), r2.data_ptr(), r2.numel(), keep=(r1, r2))
+        dm.reads_histogram().copy_(hist)
+        if distinct is not None:
+            dm.distinct_histogram().copy_(distinct)
+        st = dm.build_filter()
+        need = st["bytes_matched"] if which == L.EMIT_MATCHED else st["bytes_passing"]
+        out = torch.empty(need + 16, dtype=torch.uint8, device=r1.device)
+        n = dm.emit_device(which, out.data_ptr(), out.numel())
+        if sink is not None:
+            sink(out[:n], st)
+        for key, v in st.items():
+            total[key] = v if key in ("n_cells", "n_passing_cells") else total.get(key, 0) + v
+        del out
+    return total
+
+
 def shard_record_ranges(n_records: int, world: int) -> List[Tuple[int, int]]:
     """Contiguous record ranges per rank (the reference cuts line-aligned chunks the same way, LIB:6-97)."""
     per = (n_records + world - 1) // world

@@ -71,3 +71,58 @@ def test_two_ranks_equal_one(tmp_path, filter_mode):
     if filter_mode == "distinct_umi":
         from oracle import ssd_oracle_py as orc
         assert out.tobytes() == orc.demultiplex(r1, r2, WL, 1, 10).passing
+
+
+N_BATCH = 25000
+BATCHES_PER_RANK = 3
+
+
+def _batch_worker(rank, world, port, out_dir):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import ssd_b200
+    from ssd_b200.distributed import demux_batches
+    dm = ssd_b200.Demultiplexer(WL, errors=1, min_count=10, device=rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    dm.set_stream(stream.cuda_stream)
+
+    def batches():
+        for b in range(BATCHES_PER_RANK):
+            first = 1 + (rank * BATCHES_PER_RANK + b) * N_BATCH
+            yield ssd_b200.synth_device(dm, ssd_b200.synth_spec(WL, N_BATCH, seed=78, first_index=first, cell_pool=2000, p_n=0.01, p_dup_umi=0.3))
+
+    parts = []
+    total = demux_batches(dm, batches, world=world, sink=lambda out, st: parts.append(out.cpu().numpy().tobytes()))
+    torch.cuda.synchronize()
+    np.save(os.path.join(out_dir, "bout_%d.npy" % rank), np.frombuffer(b"".join(parts), dtype=np.uint8))
+    np.save(os.path.join(out_dir, "bstats_%d.npy" % rank), np.array([total["n_cells"], total["n_passing_cells"], total["n_retained"]]))
+    dist.destroy_process_group()
+
+
+def test_two_ranks_three_batches_each_equal_one_call(tmp_path):
+    """BASELINE config 4 in small: the input sharded over two ranks and cut into three batches per rank (two passes over the
+    batches, keys sent to the owner rank batch by batch) gives the bytes of one call on the whole input."""
+    import numpy as np
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import ssd_b200
+    world = 2
+    mp.spawn(_batch_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(os.path.join(str(tmp_path), "bout_%d.npy" % r)).tobytes() for r in range(world)]
+    st = [np.load(os.path.join(str(tmp_path), "bstats_%d.npy" % r)) for r in range(world)]
+    n = world * BATCHES_PER_RANK * N_BATCH
+    r1, r2 = ssd_b200.synth_host(ssd_b200.synth_spec(WL, n, seed=78, cell_pool=2000, p_n=0.01, p_dup_umi=0.3))
+    dm = ssd_b200.Demultiplexer(WL, errors=1, min_count=10)
+    out, stats = dm.run_host(r1, r2, ssd_b200.EMIT_PASSING)
+    assert b"".join(parts) == out.tobytes()
+    assert int(st[0][0]) == int(st[1][0]) == stats["n_cells"]
+    assert int(st[0][1]) == int(st[1][1]) == stats["n_passing_cells"]
+    assert int(st[0][2]) + int(st[1][2]) == stats["n_retained"]

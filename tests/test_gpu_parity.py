@@ -488,6 +488,31 @@ def test_full_size_properties(ssd, n, e, m, spec_kw, dm_kw, split):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("filter_mode", ["distinct_umi", "reads"])
+def test_batches_equal_one_call(ssd, orc, filter_mode):
+    """Inputs cut into batches (two passes: global tables first, then the writer) give the bytes of one call on the whole
+    input, which in turn are the oracle's."""
+    from ssd_b200.distributed import demux_batches
+    sizes = [20000, 1, 35000, 4999]
+    kw = dict(seed=0xBA7C, cell_pool=1500, p_n=0.01, p_dup_umi=0.4)
+    dm = ssd.Demultiplexer(WL, errors=1, min_count=10, filter_mode=filter_mode)
+
+    def batches():
+        first = 1
+        for n in sizes:
+            yield ssd.synth_device(dm, ssd.synth_spec(WL, n, first_index=first, **kw))
+            first += n
+
+    parts = []
+    total = demux_batches(dm, batches, sink=lambda out, st: parts.append(out.cpu().numpy().tobytes()))
+    r1, r2 = ssd.synth_host(ssd.synth_spec(WL, sum(sizes), **kw))
+    whole, stats = ssd.Demultiplexer(WL, errors=1, min_count=10, filter_mode=filter_mode).run_host(r1, r2, ssd.EMIT_PASSING)
+    assert b"".join(parts) == whole.tobytes()
+    assert [total[k] for k in ("n_cells", "n_passing_cells", "n_retained", "n_matched")] == [stats[k] for k in ("n_cells", "n_passing_cells", "n_retained", "n_matched")]
+    if filter_mode == "distinct_umi":
+        assert whole.tobytes() == orc.demultiplex(r1, r2, WL, 1, 10).passing
+
+
 @pytest.mark.parametrize("seed", range(24))
 def test_fuzz_against_oracle(ssd, orc, seed):
     """Seeded random configurations of the adversarial generator (sizes, line endings, header forms, N / tie / junk /
