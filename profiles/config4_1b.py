@@ -3,7 +3,7 @@
 (all-reduce of the read histogram, exact distinct-UMI exchange by owner rank), every rank writing its own records.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        profiles/config4_1b.py [--pairs 1000000000] [--batch 125000000]
+        profiles/config4_1b.py [--pairs 1000000000] [--batch 100000000]
 
 A rank's shard (pairs / N) is generated on the device batch by batch (S1B seed 0x5EED0003) and goes through
 ssd_b200.distributed.demux_batches: two passes over the batches.  Prints one JSON line (rank 0): wall time of the two
@@ -24,7 +24,7 @@ for p in (ROOT, os.path.join(ROOT, "split-seq_demultiplexing_b200")):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=1_000_000_000)
-    ap.add_argument("--batch", type=int, default=125_000_000)
+    ap.add_argument("--batch", type=int, default=100_000_000)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist

@@ -161,6 +161,9 @@ def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, si
                 k, i = dm.local_unique_keys()
             kept_k.append(k.clone())
             kept_i.append(i.clone())
+        torch.cuda.synchronize()
+        dm._keep = []  # the batch may go before the next one is produced (two of them need not fit)
+        del r1, r2
     if hist is None:
         return {}
     distinct = None
@@ -168,6 +171,7 @@ def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, si
         all_k = torch.cat(kept_k) if kept_k else torch.empty(0, dtype=torch.int64, device="cuda")
         all_i = torch.cat(kept_i) if kept_i else torch.empty((0, 2), dtype=torch.int64, device="cuda")
         del kept_k, kept_i
+        torch.cuda.empty_cache()  # the library allocates with cudaMalloc: blocks torch has cached are out of its reach
         if world > 1:
             dm.count_distinct_owned(all_k, all_i, rank, world)
             dist.all_reduce(dm.distinct_histogram(), group=group)
@@ -191,7 +195,10 @@ def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, si
             sink(out[:n], st)
         for key, v in st.items():
             total[key] = v if key in ("n_cells", "n_passing_cells") else total.get(key, 0) + v
-        del out
+        torch.cuda.synchronize()
+        dm._keep = []
+        del out, r1, r2
+        torch.cuda.empty_cache()  # batches of tens of GB: do not let the caching allocator fragment what is left
     return total
 
 
