@@ -128,7 +128,7 @@ def global_filter(dm, world: int, group=None) -> dict:
     return dm.filter_single()
 
 
-def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, sink=None) -> dict:
+def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, sink=None, timing: dict = None) -> dict:
     """Inputs too large for one call (BASELINE config 4: 10^9 read pairs; 64 GiB per file is the per-call limit, the HBM of one
     GPU the practical one): the -m decision needs every batch's per-cell read counts and (cell, UMI) keys before the first
     record can be written, so the batches are gone through twice, the way the reference goes through its chunk files
@@ -141,7 +141,9 @@ def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, si
 
     `batches` is a callable returning an iterator of (r1, r2) uint8 CUDA tensors (called twice; every rank passes its own
     shard's batches).  sink(out_tensor, stats) receives each batch's output in order (the tensor is only valid during the
-    call); without a sink the outputs are dropped.  Returns the statistics summed over the batches (cell counts are global)."""
+    call); without a sink the outputs are dropped.  Returns the statistics summed over the batches (cell counts are global).
+    `timing`, when given, receives the wall-clock seconds of pass 1, of the global count and of pass 2 (device synchronised)."""
+    import time
     import torch
     import torch.distributed as dist
     from . import _lib as L
@@ -149,6 +151,7 @@ def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, si
     distinct_mode = dm.filter_mode == "distinct_umi"
     rank = dist.get_rank(group) if world > 1 else 0
     hist, kept_k, kept_i = None, [], []
+    t_start = time.perf_counter()
     for r1, r2 in batches():
         dm.demux_device(r1.data_ptr(), r1.numel(), r2.data_ptr(), r2.numel(), keep=(r1, r2))
         h = dm.reads_histogram()
@@ -166,6 +169,7 @@ def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, si
         del r1, r2
     if hist is None:
         return {}
+    t_pass1 = time.perf_counter()
     distinct = None
     if distinct_mode:
         all_k = torch.cat(kept_k) if kept_k else torch.empty(0, dtype=torch.int64, device="cuda")
@@ -181,6 +185,8 @@ def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, si
         del all_k, all_i
     if world > 1:
         dist.all_reduce(hist, group=group)
+    torch.cuda.synchronize()
+    t_count = time.perf_counter()
     total = {}
     for r1, r2 in batches():
         dm.demux_device(r1.data_ptr(), r1.numel(), r2.data_ptr(), r2.numel(), keep=(r1, r2))
@@ -199,6 +205,8 @@ def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, si
         dm._keep = []
         del out, r1, r2
         torch.cuda.empty_cache()  # batches of tens of GB: do not let the caching allocator fragment what is left
+    if timing is not None:
+        timing.update(pass1_s=t_pass1 - t_start, count_s=t_count - t_pass1, pass2_s=time.perf_counter() - t_count)
     return total
 
 
