@@ -122,6 +122,30 @@ int ssd_run_files(ssd_ctx *ctx, const char *path_r1, const char *path_r2, int wh
 int ssd_annotated_file(ssd_ctx *ctx, const char *path_in, const char *out_path, int append, size_t *written,
                        ssd_stats *stats);
 
+/* The file path in pieces, for inputs that do not fit one call (more than 64 GiB per file, or more than the GPU holds): the
+ * host cuts the files into batches of whole records and drives the batches itself -- one pass when no filter is involved
+ * (V2.demultiplex_fun writes every matched pair, V2:367), two passes when -m is (V2.calc_demux_results, V2:389-454: per-cell
+ * tables over all batches first, see ssd_b200/filebatch.py).
+ *   ssd_load_file_range   bytes [offset, offset + length) of a file (clamped to the file) into the context's input buffer
+ *                         `slot` (0: read 1 or the annotated text, 1: read 2), read with pread on eight host threads into
+ *                         pinned rings and uploaded as they arrive
+ *   ssd_demux_loaded      ssd_demux_device on the two loaded ranges; ssd_annotated_loaded: ssd_annotated_device on slot 0
+ *   ssd_emit_file         after the filter (ssd_filter_single / ssd_build_filter): the selected output into out_path,
+ *                         appended (V2:367, 415) or truncating
+ *   ssd_fastq_record_cuts host only, no context: where a FASTQ file can be cut between records ('\n' ends a line, four
+ *                         lines make a record).  records_in == NULL: entry 0 is (record 0, byte 0), after a cut at byte b
+ *                         the next cut is the first record start at or after b + target_bytes, the last entry is (number
+ *                         of complete records, file size).  records_in != NULL (ascending): the offsets at which those
+ *                         records start (the file size for records past the end) -- the mate file cut at the same records.
+ *                         SSD_ERANGE when `capacity` entries do not suffice. */
+int ssd_load_file_range(ssd_ctx *ctx, int slot, const char *path, uint64_t offset, uint64_t length);
+int ssd_demux_loaded(ssd_ctx *ctx);
+int ssd_annotated_loaded(ssd_ctx *ctx);
+int ssd_emit_file(ssd_ctx *ctx, int which, const char *out_path, int append, size_t *written);
+int ssd_fastq_record_cuts(const char *path, uint64_t target_bytes, const uint64_t *records_in, uint64_t n_in,
+                          uint64_t *records_out, uint64_t *offsets_out, uint64_t capacity, uint64_t *n_out,
+                          uint64_t *n_records_total);
+
 /* ---- phase 2: the -m decision, V2.calc_demux_results pass 1 (V2:389-412) ---------------------- */
 /* Device pointers to the n^3 uint32 per-cell read counts / distinct-UMI counts of this context.
  * A multi-GPU host all-reduces (sums) them in place between the calls below. */

@@ -114,6 +114,7 @@ struct ssd_ctx {
     DevBuf b_status1, b_status2, b_r1_start, b_r1_meta, b_r1_base, b_r1_tok, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
         b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
     DevBuf b_in1, b_in2, b_out;
+    size_t loaded[2] = {0, 0};  // bytes ssd_load_file_range put into b_in1 / b_in2
     IoLane io[kIoLanes];  // pinned slots + streams of the file-to-file entry points (created on first use)
     DevBuf b_os, b_irr_table;  // one-kernel-per-pass sort: histograms, tickets, tile status; hash set of the irregular keys
     DevBuf b_seg;              // per-cell hash sets of the regular keys: key counts (when not the read histogram) and segment offsets
@@ -1347,7 +1348,7 @@ extern "C" int ssd_run_host(ssd_ctx* c, const void* r1, size_t r1_len, const voi
 // ================================================================================================
 namespace {
 // one host thread of `stride`: pread chunks first, first + stride, ... into its pinned slots, each uploaded as soon as it is read
-void upload_file_worker(int device, int fd, size_t size, uint8_t* d_dst, IoLane* lane, int first, int stride, int* rc, int* err_no)
+void upload_file_worker(int device, int fd, size_t base, size_t size, uint8_t* d_dst, IoLane* lane, int first, int stride, int* rc, int* err_no)
 {
     *rc = SSD_OK;
     if (cudaSetDevice(device) != cudaSuccess) {
@@ -1364,7 +1365,7 @@ void upload_file_worker(int device, int fd, size_t size, uint8_t* d_dst, IoLane*
         const size_t off = k * kIoChunk, want = std::min(kIoChunk, size - off);
         size_t got = 0;
         while (got < want) {
-            const ssize_t r = pread(fd, lane->slot[s] + got, want - got, (off_t)(off + got));
+            const ssize_t r = pread(fd, lane->slot[s] + got, want - got, (off_t)(base + off + got));
             if (r < 0 && errno == EINTR) continue;
             if (r <= 0) {
                 *rc = SSD_EIO;
@@ -1500,8 +1501,8 @@ extern "C" int ssd_run_files(ssd_ctx* c, const char* path_r1, const char* path_r
     if (rc == SSD_OK) {
         std::lock_guard<std::mutex> turn(g_h2d_turn);
         int rc2 = SSD_OK;
-        std::thread other([&] { rc2 = run_lanes(c, path_r2, 4, 4, upload_file_worker, c->device, fd[1], size[1], (uint8_t*)c->b_in2.p); });
-        rc = run_lanes(c, path_r1, 0, 4, upload_file_worker, c->device, fd[0], size[0], (uint8_t*)c->b_in1.p);
+        std::thread other([&] { rc2 = run_lanes(c, path_r2, 4, 4, upload_file_worker, c->device, fd[1], (size_t)0, size[1], (uint8_t*)c->b_in2.p); });
+        rc = run_lanes(c, path_r1, 0, 4, upload_file_worker, c->device, fd[0], (size_t)0, size[0], (uint8_t*)c->b_in1.p);
         other.join();
         if (rc == SSD_OK) rc = rc2;
     }
@@ -1524,13 +1525,173 @@ extern "C" int ssd_annotated_file(ssd_ctx* c, const char* path_in, const char* o
     for (int k = 0; k < kIoLanes && rc == SSD_OK; k++) rc = c->io[k].init();
     if (rc == SSD_OK) {
         std::lock_guard<std::mutex> turn(g_h2d_turn);
-        rc = run_lanes(c, path_in, 0, kIoLanes, upload_file_worker, c->device, fd, size, (uint8_t*)c->b_in1.p);
+        rc = run_lanes(c, path_in, 0, kIoLanes, upload_file_worker, c->device, fd, (size_t)0, size, (uint8_t*)c->b_in1.p);
     }
     close(fd);
     if (rc != SSD_OK) return rc;
     OKR(ssd_annotated_device(c, c->b_in1.p, size));
     OKR(ssd_filter_single(c, stats));
     return download_to_file(c, SSD_EMIT_PASSING, out_path, append, written);
+}
+
+// ---- the same in pieces, for inputs that have to go through the GPU in batches (ssd_b200.filebatch) ----
+extern "C" int ssd_load_file_range(ssd_ctx* c, int slot, const char* path, uint64_t offset, uint64_t length)
+{
+    if (!c || !path || slot < 0 || slot > 1) return SSD_EINVAL;
+    CU(c, cudaSetDevice(c->device));
+    int fd = -1;
+    size_t size = 0;
+    OKR(open_input(c, path, &fd, &size));
+    const size_t off = std::min<uint64_t>(offset, size), len = (size_t)std::min<uint64_t>(length, size - off);
+    DevBuf& buf = slot == 0 ? c->b_in1 : c->b_in2;
+    int rc = ensure(c, buf, len + 32);
+    for (int k = 0; k < kIoLanes && rc == SSD_OK; k++) rc = c->io[k].init();
+    if (rc == SSD_OK) {
+        std::lock_guard<std::mutex> turn(g_h2d_turn);
+        rc = run_lanes(c, path, 0, kIoLanes, upload_file_worker, c->device, fd, off, len, (uint8_t*)buf.p);
+    }
+    close(fd);
+    if (rc == SSD_OK) c->loaded[slot] = len;
+    return rc;
+}
+
+extern "C" int ssd_demux_loaded(ssd_ctx* c)
+{
+    if (!c) return SSD_EINVAL;
+    return ssd_demux_device(c, c->b_in1.p, c->loaded[0], c->b_in2.p, c->loaded[1]);
+}
+
+extern "C" int ssd_annotated_loaded(ssd_ctx* c)
+{
+    if (!c) return SSD_EINVAL;
+    return ssd_annotated_device(c, c->b_in1.p, c->loaded[0]);
+}
+
+extern "C" int ssd_emit_file(ssd_ctx* c, int which, const char* out_path, int append, size_t* written)
+{
+    if (!c || !out_path) return SSD_EINVAL;
+    if (which != SSD_EMIT_MATCHED && which != SSD_EMIT_PASSING) return fail(c, SSD_EINVAL, "unknown output selector");
+    if (!c->filter_done) return fail(c, SSD_ESTATE, "ssd_emit_file before the filter was built");
+    CU(c, cudaSetDevice(c->device));
+    return download_to_file(c, which, out_path, append, written);
+}
+
+// Where a FASTQ file can be cut into batches of whole records (host only; a line ends at '\n', a record is four lines).
+//   records_in == NULL: cuts by size.  Entry 0 is (record 0, byte 0); after a cut at byte b the next one is the first record
+//                       start at or after b + target_bytes; the last entry is (number of complete records, file size).
+//   records_in != NULL: the byte offsets at which the given records (ascending indices) start; an index past the end of
+//                       the file gives the file size.  This is how the mate file is cut at the same records.
+// n_out receives the number of entries written (at most cap; SSD_ERANGE when cap is too small).
+extern "C" int ssd_fastq_record_cuts(const char* path, uint64_t target_bytes, const uint64_t* records_in, uint64_t n_in, uint64_t* records_out,
+                                     uint64_t* offsets_out, uint64_t cap, uint64_t* n_out, uint64_t* n_records_total)
+{
+    if (!path || !records_out || !offsets_out || !n_out || (!records_in && target_bytes == 0)) return SSD_EINVAL;
+    const int fd = open(path, O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) {
+        if (fd >= 0) close(fd);
+        return SSD_EIO;
+    }
+    const uint64_t size = (uint64_t)st.st_size;
+    constexpr size_t kBuf = (size_t)8 << 20, kSub = (size_t)64 << 10;
+    std::vector<uint8_t> buf(kBuf);
+    auto count_nl = [](const uint8_t* p, size_t n) {
+        uint64_t k = 0;
+        for (size_t i = 0; i < n; i++) k += p[i] == '\n';
+        return k;
+    };
+    uint64_t n = 0, lines = 0, pos = 0, last_cut = 0, next_in = 0;
+    int rc = SSD_OK;
+    uint8_t last_byte = '\n';
+    auto put = [&](uint64_t rec, uint64_t off) {
+        if (n >= cap) {
+            rc = SSD_ERANGE;
+            return;
+        }
+        records_out[n] = rec;
+        offsets_out[n] = off;
+        n++;
+    };
+    if (!records_in) put(0, 0);
+    while (records_in && next_in < n_in && records_in[next_in] == 0) {
+        put(0, 0);
+        next_in++;
+    }
+    while (pos < size && rc == SSD_OK) {
+        const size_t want = (size_t)std::min<uint64_t>(kBuf, size - pos);
+        size_t got = 0;
+        while (got < want) {
+            const ssize_t r = pread(fd, buf.data() + got, want - got, (off_t)(pos + got));
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) {
+                close(fd);
+                return SSD_EIO;
+            }
+            got += (size_t)r;
+        }
+        last_byte = buf[want - 1];
+        for (size_t s0 = 0; s0 < want && rc == SSD_OK; s0 += kSub) {
+            const size_t sn = std::min(kSub, want - s0);
+            const uint8_t* b = buf.data() + s0;
+            const uint64_t sub_pos = pos + s0;
+            size_t i = 0;
+            while (i < sn && rc == SSD_OK) {
+                if (!records_in) {
+                    const uint64_t limit = last_cut + target_bytes;
+                    if (sub_pos + sn <= limit) {  // the whole rest of this piece lies before the next cut
+                        lines += count_nl(b + i, sn - i);
+                        break;
+                    }
+                    if (sub_pos + i < limit) {
+                        const size_t k = (size_t)(limit - sub_pos - i);
+                        lines += count_nl(b + i, k);
+                        i += k;
+                    }
+                    const uint8_t* q = (const uint8_t*)memchr(b + i, '\n', sn - i);
+                    if (!q) break;
+                    i = (size_t)(q - b) + 1;
+                    lines++;
+                    if ((lines & 3u) == 0 && sub_pos + i < size) {
+                        put(lines >> 2, sub_pos + i);
+                        last_cut = sub_pos + i;
+                    }
+                } else {
+                    if (next_in >= n_in) {
+                        lines += count_nl(b + i, sn - i);
+                        break;
+                    }
+                    const uint64_t goal = 4 * records_in[next_in];  // the record starts after newline number `goal`
+                    const uint64_t here = count_nl(b + i, sn - i);
+                    if (lines + here < goal) {
+                        lines += here;
+                        break;
+                    }
+                    while (lines < goal) {
+                        const uint8_t* q = (const uint8_t*)memchr(b + i, '\n', sn - i);
+                        i = (size_t)(q - b) + 1;
+                        lines++;
+                    }
+                    put(records_in[next_in], sub_pos + i);
+                    next_in++;
+                    while (next_in < n_in && rc == SSD_OK && records_in[next_in] == records_in[next_in - 1]) {
+                        put(records_in[next_in], sub_pos + i);
+                        next_in++;
+                    }
+                }
+            }
+        }
+        pos += want;
+    }
+    close(fd);
+    const uint64_t n_lines = lines + (size && last_byte != '\n' ? 1 : 0);
+    if (!records_in) {
+        if (rc == SSD_OK) put(n_lines >> 2, size);
+    } else {
+        while (next_in < n_in && rc == SSD_OK) put(records_in[next_in++], size);
+    }
+    *n_out = n;
+    if (n_records_total) *n_records_total = n_lines >> 2;
+    return rc;
 }
 
 extern "C" int ssd_annotated_host(ssd_ctx* c, const void* text, size_t len, void* out, size_t out_cap, size_t* written, ssd_stats* stats)

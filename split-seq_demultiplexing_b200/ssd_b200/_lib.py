@@ -94,6 +94,12 @@ _SIGS = {
     "ssd_count_distinct_owned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
     "ssd_run_files": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(Stats)]),
     "ssd_annotated_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(Stats)]),
+    "ssd_load_file_range": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_uint64]),
+    "ssd_demux_loaded": (C.c_int, [C.c_void_p]),
+    "ssd_annotated_loaded": (C.c_int, [C.c_void_p]),
+    "ssd_emit_file": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_size_t)]),
+    "ssd_fastq_record_cuts": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                        C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ssd_key_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ssd_scan_repeats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "ssd_owner_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -128,32 +128,21 @@ def global_filter(dm, world: int, group=None) -> dict:
     return dm.filter_single()
 
 
-def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, sink=None, timing: dict = None) -> dict:
-    """Inputs too large for one call (BASELINE config 4: 10^9 read pairs; 64 GiB per file is the per-call limit, the HBM of one
-    GPU the practical one): the -m decision needs every batch's per-cell read counts and (cell, UMI) keys before the first
-    record can be written, so the batches are gone through twice, the way the reference goes through its chunk files
-    (CLI3:56-64) and then through MergedCells_1.fastq (V2:389-454).
-
-      pass 1  every batch: scan + match (dm.demux_device); its read histogram is added up, its (cell, UMI) keys are kept
-              (one GPU: the batch's sorted unique list; N GPUs: grouped by owner rank and sent there right away).
-              Then one exact distinct count over everything kept, and the all-reduces of the two tables when N > 1.
-      pass 2  every batch again: scan + match, the GLOBAL tables put in place of the batch's own, filter, write.
-
-    `batches` is a callable returning an iterator of (r1, r2) uint8 CUDA tensors (called twice; every rank passes its own
-    shard's batches).  sink(out_tensor, stats) receives each batch's output in order (the tensor is only valid during the
-    call); without a sink the outputs are dropped.  Returns the statistics summed over the batches (cell counts are global).
-    `timing`, when given, receives the wall-clock seconds of pass 1, of the global count and of pass 2 (device synchronised)."""
+def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None) -> dict:
+    """The two passes over batches that a global -m decision needs (see demux_batches).  `phase1` is a callable returning an
+    iterator; every step of the iterator has run phase 1 of the next batch on dm (ssd_demux_device, ssd_demux_loaded,
+    ssd_annotated_loaded ...) and yields whatever `emit` needs to know about the batch.  It is gone through twice.
+    emit(batch, stats) is called in pass 2 once the filter of the batch is built from the GLOBAL tables; it writes the
+    batch's output (ssd_emit_device, ssd_emit_file ...).  Returns the statistics summed over the batches (cell counts are
+    global)."""
     import time
     import torch
     import torch.distributed as dist
-    from . import _lib as L
-    which = L.EMIT_PASSING if which is None else which
     distinct_mode = dm.filter_mode == "distinct_umi"
     rank = dist.get_rank(group) if world > 1 else 0
     hist, kept_k, kept_i = None, [], []
     t_start = time.perf_counter()
-    for r1, r2 in batches():
-        dm.demux_device(r1.data_ptr(), r1.numel(), r2.data_ptr(), r2.numel(), keep=(r1, r2))
+    for batch in phase1():
         h = dm.reads_histogram()
         hist = h.clone() if hist is None else hist.add_(h)
         if distinct_mode:
@@ -166,7 +155,7 @@ def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, si
             kept_i.append(i.clone())
         torch.cuda.synchronize()
         dm._keep = []  # the batch may go before the next one is produced (two of them need not fit)
-        del r1, r2
+        del batch
     if hist is None:
         return {}
     t_pass1 = time.perf_counter()
@@ -188,26 +177,58 @@ def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, si
     torch.cuda.synchronize()
     t_count = time.perf_counter()
     total = {}
-    for r1, r2 in batches():
-        dm.demux_device(r1.data_ptr(), r1.numel(), r2.data_ptr(), r2.numel(), keep=(r1, r2))
+    for batch in phase1():
         dm.reads_histogram().copy_(hist)
         if distinct is not None:
             dm.distinct_histogram().copy_(distinct)
         st = dm.build_filter()
-        need = st["bytes_matched"] if which == L.EMIT_MATCHED else st["bytes_passing"]
-        out = torch.empty(need + 16, dtype=torch.uint8, device=r1.device)
-        n = dm.emit_device(which, out.data_ptr(), out.numel())
-        if sink is not None:
-            sink(out[:n], st)
+        emit(batch, st)
         for key, v in st.items():
             total[key] = v if key in ("n_cells", "n_passing_cells") else total.get(key, 0) + v
         torch.cuda.synchronize()
         dm._keep = []
-        del out, r1, r2
+        del batch
         torch.cuda.empty_cache()  # batches of tens of GB: do not let the caching allocator fragment what is left
     if timing is not None:
         timing.update(pass1_s=t_pass1 - t_start, count_s=t_count - t_pass1, pass2_s=time.perf_counter() - t_count)
     return total
+
+
+def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, sink=None, timing: dict = None) -> dict:
+    """Inputs too large for one call (BASELINE config 4: 10^9 read pairs; 64 GiB per file is the per-call limit, the HBM of one
+    GPU the practical one): the -m decision needs every batch's per-cell read counts and (cell, UMI) keys before the first
+    record can be written, so the batches are gone through twice, the way the reference goes through its chunk files
+    (CLI3:56-64) and then through MergedCells_1.fastq (V2:389-454).
+
+      pass 1  every batch: scan + match (dm.demux_device); its read histogram is added up, its (cell, UMI) keys are kept
+              (one GPU: the batch's sorted unique list; N GPUs: grouped by owner rank and sent there right away).
+              Then one exact distinct count over everything kept, and the all-reduces of the two tables when N > 1.
+      pass 2  every batch again: scan + match, the GLOBAL tables put in place of the batch's own, filter, write.
+
+    `batches` is a callable returning an iterator of (r1, r2) uint8 CUDA tensors (called twice; every rank passes its own
+    shard's batches).  sink(out_tensor, stats) receives each batch's output in order (the tensor is only valid during the
+    call); without a sink the outputs are dropped.  Returns the statistics summed over the batches (cell counts are global).
+    `timing`, when given, receives the wall-clock seconds of pass 1, of the global count and of pass 2 (device synchronised)."""
+    import torch
+    from . import _lib as L
+    which = L.EMIT_PASSING if which is None else which
+
+    def phase1():
+        for r1, r2 in batches():
+            dm.demux_device(r1.data_ptr(), r1.numel(), r2.data_ptr(), r2.numel(), keep=(r1, r2))
+            dev = r1.device
+            del r1, r2
+            yield dev
+
+    def emit(dev, st):
+        need = st["bytes_matched"] if which == L.EMIT_MATCHED else st["bytes_passing"]
+        out = torch.empty(need + 16, dtype=torch.uint8, device=dev)
+        n = dm.emit_device(which, out.data_ptr(), out.numel())
+        if sink is not None:
+            sink(out[:n], st)
+        del out
+
+    return two_pass(dm, phase1, emit, world=world, group=group, timing=timing)
 
 
 def shard_record_ranges(n_records: int, world: int) -> List[Tuple[int, int]]:

@@ -264,7 +264,11 @@ class Demultiplexer:
     def run_files(self, path_r1: str, path_r2: str, out_path: str, which: int = L.EMIT_PASSING, append: bool = True):
         """File to file (what V2.demultiplex_fun does with one pair of chunk files): reads, uploads, demultiplexes and
         appends (or writes) the selected output to out_path, all inside the library with pinned rings and overlapped
-        copies.  Returns (bytes written, stats)."""
+        copies.  Returns (bytes written, stats).  Files above SSD_BATCH_BYTES (16 GiB) go through the GPU in batches of whole
+        records (ssd_b200.filebatch) with the same bytes as result."""
+        from . import filebatch
+        if filebatch.needs_batches(path_r1, path_r2):
+            return filebatch.run_files_batched(self, path_r1, path_r2, out_path, which, append)
         st = L.Stats()
         n = C.c_size_t()
         self._check(self.lib.ssd_run_files(self._ctx, os.fsencode(path_r1), os.fsencode(path_r2), which, os.fsencode(out_path), 1 if append else 0,
@@ -272,7 +276,11 @@ class Demultiplexer:
         return n.value, st.as_dict()
 
     def filter_annotated_file(self, path_in: str, out_path: str, append: bool = True):
-        """V2.calc_demux_results file to file: returns (bytes written, stats)."""
+        """V2.calc_demux_results file to file: returns (bytes written, stats).  Files above SSD_BATCH_BYTES: two passes over
+        batches (ssd_b200.filebatch)."""
+        from . import filebatch
+        if filebatch.needs_batches(path_in):
+            return filebatch.filter_annotated_file_batched(self, path_in, out_path, append)
         st = L.Stats()
         n = C.c_size_t()
         self._check(self.lib.ssd_annotated_file(self._ctx, os.fsencode(path_in), os.fsencode(out_path), 1 if append else 0, C.byref(n), C.byref(st)))

@@ -1,0 +1,133 @@
+"""Files that do not fit one call: cut into batches of whole records and driven batch by batch.
+
+ssd_run_files / ssd_annotated_file hold a whole file (pair) on the GPU; that stops at 64 GiB per file and, before that,
+at what the GPU's memory holds next to the output.  The reference has the same problem in RAM and solves it with line
+bins (numReadsBin, V2:80-81, 207-262) and chunk files (LIB:6-97).  Here the host finds record-aligned cut points
+(ssd_fastq_record_cuts: newline counting, no '@' heuristics), the mate file is cut at the same RECORDS, and every batch
+goes through ssd_load_file_range -> ssd_demux_loaded / ssd_annotated_loaded -> filter -> ssd_emit_file (append).
+
+  * V2.demultiplex_fun writes every matched pair (V2:367): batches are independent, one pass.
+  * V2.calc_demux_results decides per cell over the WHOLE file (V2:389-412) before it copies a record (V2:415-454): two
+    passes (ssd_b200.distributed.two_pass): per-cell tables over all batches first, then filter + write per batch.
+
+SSD_BATCH_BYTES (default 16 GiB per file and batch) is the cut target; the drop-in modules switch to this path for files
+above it.  The output is byte-identical to the single call's (tests/test_gpu_dropin.py forces tiny batches on the bundled
+files and checks the reference's golden digests)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+from . import _lib as L
+
+DEFAULT_BATCH_BYTES = 16 << 30
+
+
+def batch_bytes() -> int:
+    return max(1, int(os.environ.get("SSD_BATCH_BYTES", DEFAULT_BATCH_BYTES)))
+
+
+def needs_batches(*paths: str) -> bool:
+    limit = batch_bytes()
+    return any(os.path.exists(p) and os.path.getsize(p) > limit for p in paths)
+
+
+def record_cuts(path: str, target_bytes: Optional[int] = None, records: Optional[Sequence[int]] = None) -> Tuple[List[int], List[int], int]:
+    """(record indices, byte offsets, complete records in the file).  By size (target_bytes) or at given records."""
+    lib = L.load()
+    size = os.path.getsize(path)  # FileNotFoundError like the reference's open()
+    if records is None:
+        cap = size // max(1, int(target_bytes)) + 3
+        rin, n_in = None, 0
+    else:
+        cap = len(records) + 1
+        rin, n_in = (C.c_uint64 * len(records))(*records), len(records)
+    while True:
+        rec, off = (C.c_uint64 * cap)(), (C.c_uint64 * cap)()
+        n, total = C.c_uint64(), C.c_uint64()
+        rc = lib.ssd_fastq_record_cuts(os.fsencode(path), int(target_bytes or 0), rin, n_in, rec, off, cap, C.byref(n), C.byref(total))
+        if rc == L.ERANGE:
+            cap *= 2
+            continue
+        if rc != L.OK:
+            raise OSError("cannot read %s" % path)
+        return list(rec[: n.value]), list(off[: n.value]), total.value
+
+
+def pair_batches(path_r1: str, path_r2: str, target_bytes: Optional[int] = None):
+    """[(offset 1, length 1, offset 2, length 2)]: the same record range of both files per batch; read 1 is cut by size, read
+    2 at the same records (the last batch takes whatever is left of both files, so surplus records still meet the mate
+    check of V2:349-350)."""
+    target = batch_bytes() if target_bytes is None else int(target_bytes)
+    rec, off1, _ = record_cuts(path_r1, target_bytes=target)
+    _, off2, _ = record_cuts(path_r2, records=rec)
+    off1[-1], off2[-1] = os.path.getsize(path_r1), os.path.getsize(path_r2)
+    return [(off1[k], off1[k + 1] - off1[k], off2[k], off2[k + 1] - off2[k]) for k in range(len(rec) - 1)] or [(0, off1[-1], 0, off2[-1])]
+
+
+def _truncate(path: str, append: bool):
+    if not append:
+        open(path, "wb").close()
+
+
+def _emit_file(dm, which: int, out_path: str) -> int:
+    n = C.c_size_t()
+    dm._check(dm.lib.ssd_emit_file(dm._ctx, which, os.fsencode(out_path), 1, C.byref(n)))
+    return n.value
+
+
+def run_files_batched(dm, path_r1: str, path_r2: str, out_path: str, which: int = L.EMIT_PASSING, append: bool = True,
+                      target_bytes: Optional[int] = None):
+    """Demultiplexer.run_files for files of any size.  Returns (bytes written, stats summed over the batches)."""
+    from .distributed import two_pass
+    batches = pair_batches(path_r1, path_r2, target_bytes)
+    p1, p2 = os.fsencode(path_r1), os.fsencode(path_r2)
+    _truncate(out_path, append)
+    written = [0]
+
+    def phase1():
+        for o1, n1, o2, n2 in batches:
+            dm._check(dm.lib.ssd_load_file_range(dm._ctx, 0, p1, o1, n1))
+            dm._check(dm.lib.ssd_load_file_range(dm._ctx, 1, p2, o2, n2))
+            dm._check(dm.lib.ssd_demux_loaded(dm._ctx))
+            yield None
+
+    if which == L.EMIT_MATCHED:  # no decision across batches: one pass
+        total = {}
+        for _ in phase1():
+            st = dm.filter_single()
+            written[0] += _emit_file(dm, which, out_path)
+            for key, v in st.items():
+                total[key] = total.get(key, 0) + v
+        return written[0], total
+
+    def emit(_, st):
+        written[0] += _emit_file(dm, which, out_path)
+
+    total = two_pass(dm, phase1, emit)
+    return written[0], total
+
+
+def filter_annotated_file_batched(dm, path_in: str, out_path: str, append: bool = True, target_bytes: Optional[int] = None):
+    """Demultiplexer.filter_annotated_file (V2.calc_demux_results) for a MergedCells_1.fastq of any size."""
+    from .distributed import two_pass
+    target = batch_bytes() if target_bytes is None else int(target_bytes)
+    _, off, _ = record_cuts(path_in, target_bytes=target)
+    off[-1] = os.path.getsize(path_in)
+    ranges = [(off[k], off[k + 1] - off[k]) for k in range(len(off) - 1)] or [(0, off[-1])]
+    p = os.fsencode(path_in)
+    _truncate(out_path, append)
+    written = [0]
+
+    def phase1():
+        for o, n in ranges:
+            dm._check(dm.lib.ssd_load_file_range(dm._ctx, 0, p, o, n))
+            dm._check(dm.lib.ssd_annotated_loaded(dm._ctx))
+            yield None
+
+    def emit(_, st):
+        written[0] += _emit_file(dm, L.EMIT_PASSING, out_path)
+
+    total = two_pass(dm, phase1, emit)
+    return written[0], total

@@ -174,3 +174,73 @@ def test_run_files_matches_run_host(tmp_path):
     out = tmp_path / "out.fastq"
     n, st3 = dm.run_files(str(empty), str(empty), str(out), ssd_b200.EMIT_PASSING, append=False)
     assert n == 0 and out.read_bytes() == b"" and st3["n_records_r1"] == 0
+
+
+@pytest.mark.parametrize("batch_bytes", [40000, 300000])
+@pytest.mark.parametrize("e,m", [(1, 10), (2, 10)])
+def test_reference_function_surface_in_batches(workdir, digests, monkeypatch, e, m, batch_bytes):
+    """Files above SSD_BATCH_BYTES go through the GPU in batches of whole records (ssd_b200.filebatch: one pass for
+    demultiplex_fun, two passes for calc_demux_results).  Forced here with tiny batches on the bundled files: the
+    reference's golden digests and printed summary must come out unchanged, and so must the bytes of the single call."""
+    V2 = importlib.import_module("DemultiplexUsingBarcodes_New_V2")
+    with contextlib.redirect_stdout(io.StringIO()):
+        V2.demultiplex_fun("F.fastq", "R.fastq", "out", 100000, e, True, 10, False, True)
+        V2.calc_demux_results("out", True, str(m))
+    whole = [open("out/MergedCells_1.fastq", "rb").read(), open("out/MergedCells_passing.fastq", "rb").read()]
+    os.remove("out/MergedCells_1.fastq")
+    os.remove("out/MergedCells_passing.fastq")
+    monkeypatch.setenv("SSD_BATCH_BYTES", str(batch_bytes))
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        V2.demultiplex_fun("F.fastq", "R.fastq", "out", 100000, e, True, 10, False, True)
+        V2.calc_demux_results("out", True, str(m))
+    gold = digests["e%d_m%d" % (e, m)]
+    got = [open("out/MergedCells_1.fastq", "rb").read(), open("out/MergedCells_passing.fastq", "rb").read()]
+    assert fu.canonical_sha(got[0]) == gold["merged1_sha"] and fu.canonical_sha(got[1]) == gold["passing_sha"]
+    assert got == whole
+    assert buf.getvalue().strip().split("\n")[-2:] == gold["stdout_tail"]
+    assert "The linesInInputFastq value is set to 20000" in buf.getvalue()
+
+
+def test_run_files_in_batches_matches_the_oracle(tmp_path, monkeypatch):
+    """run_files / filter_annotated_file with SSD_BATCH_BYTES far below the file sizes, -m decided over all batches (both
+    filter modes), a surplus read-2 record in the last batch, append semantics."""
+    import ssd_b200
+    from oracle import ssd_oracle_py as orc
+    wl = fu.load_whitelist()
+    r1, r2 = ssd_b200.synth_host(ssd_b200.synth_spec(wl, 60_000, seed=32, cell_pool=800, p_dup_umi=0.4, p_n=0.01))
+    p1, p2 = tmp_path / "f.fastq", tmp_path / "r.fastq"
+    p1.write_bytes(r1)
+    p2.write_bytes(r2)
+    ref = orc.demultiplex(r1, r2, wl, 1, 10)
+    monkeypatch.setenv("SSD_BATCH_BYTES", str(3_000_000))                 # 7 batches
+    dm = ssd_b200.Demultiplexer(wl, errors=1, min_count=10)
+    passing = tmp_path / "passing.fastq"
+    n, st = dm.run_files(str(p1), str(p2), str(passing), ssd_b200.EMIT_PASSING, append=False)
+    assert passing.read_bytes() == ref.passing and n == len(ref.passing)
+    assert (st["n_matched"], st["n_cells"], st["n_passing_cells"], st["n_retained"], st["n_records_r1"]) == (
+        ref.n_matched, ref.n_cells, ref.n_passing_cells, ref.n_retained, 60_000)
+    n, _ = dm.run_files(str(p1), str(p2), str(passing), ssd_b200.EMIT_PASSING, append=True)
+    assert passing.read_bytes() == ref.passing * 2
+    merged = tmp_path / "merged.fastq"
+    n, st = dm.run_files(str(p1), str(p2), str(merged), ssd_b200.EMIT_MATCHED, append=False)
+    assert merged.read_bytes() == ref.merged1 and st["n_matched"] == ref.n_matched
+    dm2 = ssd_b200.Demultiplexer(wl, errors=0, min_count=10)
+    out2 = tmp_path / "passing2.fastq"
+    n, st2 = dm2.filter_annotated_file(str(merged), str(out2), append=True)
+    assert out2.read_bytes() == ref.passing and (st2["n_cells"], st2["n_passing_cells"]) == (ref.n_cells, ref.n_passing_cells)
+    # reads mode over batches
+    dm3 = ssd_b200.Demultiplexer(wl, errors=1, min_count=10, filter_mode="reads")
+    out3 = tmp_path / "passing3.fastq"
+    dm3.run_files(str(p1), str(p2), str(out3), ssd_b200.EMIT_PASSING, append=False)
+    monkeypatch.delenv("SSD_BATCH_BYTES")
+    whole3 = tmp_path / "whole3.fastq"
+    dm3.run_files(str(p1), str(p2), str(whole3), ssd_b200.EMIT_PASSING, append=False)
+    assert out3.read_bytes() == whole3.read_bytes()
+    # a mate missing in the middle of the files is still the reference's KeyError, from whichever batch it falls in
+    monkeypatch.setenv("SSD_BATCH_BYTES", str(3_000_000))
+    bad = tmp_path / "bad.fastq"
+    assert r2.count(b"@SYN.30001 ") == 1
+    bad.write_bytes(r2.replace(b"@SYN.30001 ", b"@SYX.30001 ", 1))
+    with pytest.raises(KeyError):
+        dm.run_files(str(p1), str(bad), str(tmp_path / "x.fastq"), ssd_b200.EMIT_MATCHED, append=False)

@@ -131,3 +131,79 @@ def test_oracle_on_synthetic_is_sane(ssd):
     res = orc.demultiplex(r1, r2, WL, 1, 10)
     assert res.n_records == 20000 and 0.8 * 20000 < res.n_matched < 20000
     assert 0 < res.n_passing_cells <= res.n_cells <= 500 + 2000
+
+
+# ---- record-aligned cut points of FASTQ files (ssd_fastq_record_cuts; host only) ------------------------------------
+def _record_starts(data: bytes):
+    """Byte offsets at which records start: 0 and the byte after every 4th newline."""
+    import numpy as np
+    nl = np.flatnonzero(np.frombuffer(data, dtype=np.uint8) == 10)
+    starts = np.concatenate([[0], nl[3::4] + 1])
+    n_lines = len(nl) + (1 if data and data[-1] != 10 else 0)
+    return starts, n_lines // 4
+
+
+def _check_cuts(ssd, tmp_path, data: bytes, target: int):
+    import numpy as np
+    from ssd_b200 import filebatch
+    p = tmp_path / "x.fastq"
+    p.write_bytes(data)
+    starts, n_records = _record_starts(data)
+    rec, off, total = filebatch.record_cuts(str(p), target_bytes=target)
+    assert total == n_records
+    assert (rec[0], off[0]) == (0, 0) and (rec[-1], off[-1]) == (n_records, len(data))
+    # expected: after a cut at byte b, the next cut is the first record start at or after b + target (and before the end)
+    want, prev = [], 0
+    while True:
+        k = int(np.searchsorted(starts, prev + target))
+        if k >= len(starts) or int(starts[k]) >= len(data):
+            break
+        want.append((k, int(starts[k])))
+        prev = int(starts[k])
+    inner = list(zip(rec[1:-1], off[1:-1]))
+    assert inner == want
+    # the same records located again by index (how the mate file is cut), plus indices past the end
+    asked = [r for r, _ in inner][:2000] + [n_records + 5]
+    rec2, off2, total2 = filebatch.record_cuts(str(p), records=asked)
+    assert rec2 == asked and total2 == n_records
+    assert off2[:-1] == [o for _, o in inner][:2000] and off2[-1] == len(data)
+
+
+@pytest.mark.parametrize("target", [1, 100, 333, 4096, 70000, 10**9])
+def test_record_cuts_on_the_bundled_file(ssd, tmp_path, target):
+    r1, _ = fu.load_bundled()
+    _check_cuts(ssd, tmp_path, r1[:200000], target)
+
+
+@pytest.mark.parametrize("data", [
+    b"", b"\n", b"@a\nAC\n+\nEE", b"@a\nAC\n+\nEE\n", b"@a\nAC\n+\nEE\n@b\nGG\n+\n!!", b"@a\r\nAC\r\n+\r\nEE\r\n@b\r\nGG\r\n+\r\n!!\r\n",
+    b"\n\n\n\n\n\n\n\n\n", b"@a\nAC\n+\nEE\n" * 50000 + b"@tail\nA"],
+    ids=["empty", "newline", "one-open", "one", "two-open", "crlf", "blank-lines", "many"])
+@pytest.mark.parametrize("target", [1, 7, 64, 65536, 70001])
+def test_record_cuts_edge_cases(ssd, tmp_path, data, target):
+    _check_cuts(ssd, tmp_path, data, target)
+
+
+def test_record_cuts_across_read_buffers(ssd, tmp_path):
+    """22 MB: the cutter reads 8 MiB at a time and counts 64 KiB pieces; cuts and record lookups across those edges."""
+    data = b"@a\nAC\n+\nEE\n" * 1_000_000 + b"@r 1\n" + b"A" * 70000 + b"\n+\n" + b"E" * 70000 + b"\n" + b"@a\nAC\n+\nEE\n" * 1_000_000
+    for target in (65536, (8 << 20) - 3, 5_000_000):
+        _check_cuts(ssd, tmp_path, data, target)
+
+
+def test_pair_batches_cover_both_files_with_the_same_records(ssd, tmp_path):
+    from ssd_b200 import filebatch
+    r1, r2 = fu.load_bundled()
+    p1, p2 = tmp_path / "a.fastq", tmp_path / "b.fastq"
+    p1.write_bytes(r1)
+    p2.write_bytes(r2 + b"@extra 1/2\nACGT\n+\nEEEE\n")                 # a surplus record ends up in the last batch
+    batches = filebatch.pair_batches(str(p1), str(p2), target_bytes=50000)
+    assert len(batches) > 10
+    assert batches[0][0] == 0 and batches[0][2] == 0
+    for (o1, n1, o2, n2), nxt in zip(batches, batches[1:]):
+        assert o1 + n1 == nxt[0] and o2 + n2 == nxt[2]
+        assert r1[o1:o1 + n1].count(b"\n") == r2[o2:o2 + n2].count(b"\n") and r1[o1:o1 + n1].count(b"\n") % 4 == 0
+    o1, n1, o2, n2 = batches[-1]
+    assert o1 + n1 == len(r1) and o2 + n2 == os.path.getsize(str(p2))
+    with pytest.raises(FileNotFoundError):
+        filebatch.pair_batches(str(tmp_path / "missing.fastq"), str(p2))
