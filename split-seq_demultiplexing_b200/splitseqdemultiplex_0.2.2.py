@@ -1,90 +1,8 @@
 #!/usr/bin/env python
-"""Drop-in for the reference's python_only_tool/splitseqdemultiplex_0.2.2.py and 0.2.3.py (CLI3; 0.2.2 is a stale copy that crashes upstream): same options, same outputs
-(<outputDir>/MergedCells_passing.fastq, the two summary lines), the demultiplexing done on B200 GPUs.
-
-CLI3 splits the FASTQs into -n chunk files, runs demultiplex_fun per chunk in worker processes, filters the
-concatenation, then deletes the intermediates (CLI3:52-81).  Here the whole pair of files goes through one fused
-device pipeline (scan, match, filter, write); -n is accepted for compatibility and ignored (one process drives one
-GPU; launch under torchrun for several).  The bash wrappers' extra flags (-v fast, -c, -t, -g) are accepted too.
-"""
-import argparse
+"""Drop-in for the reference's python_only_tool/splitseqdemultiplex_0.2.2.py: upstream it is a stale copy of 0.2.3 (CLI3)
+that crashes; here it is the same command line, served by splitseqdemultiplex_0.2.3.py next to it."""
 import os
-import sys
-
-import numpy as np
-
-_HERE = os.path.dirname(os.path.abspath(__file__))
-if _HERE not in sys.path:
-    sys.path.insert(0, _HERE)
-
-import ssd_b200  # noqa: E402
-from ssd_b200 import hostlogic  # noqa: E402
-
-
-def build_parser():
-    p = argparse.ArgumentParser()
-    # CLI3:22-38
-    p.add_argument('-n', '--numCores', required=True, help='accepted for compatibility (the reference: number of CPUs)')
-    p.add_argument('-e', '--errors', required=True, help='The max number of errors permissible per barcode "-e = 1" is recommended.')
-    p.add_argument('-m', '--minReads', required=True, help='The minimum number of distinct UMIs per cell for a cell to be retained.')
-    p.add_argument('-1', '--round1Barcodes', required=True, help='parsed and ignored like the reference (V2 opens Round1_barcodes_new5.txt in the CWD)')
-    p.add_argument('-2', '--round2Barcodes', required=True, help='parsed and ignored like the reference')
-    p.add_argument('-3', '--round3Barcodes', required=True, help='parsed and ignored like the reference')
-    p.add_argument('-f', '--fastqF', required=True, help='filepath to the forward .fastq file')
-    p.add_argument('-r', '--fastqR', required=True, help='filepath to the reverse .fastq file')
-    p.add_argument('-o', '--outputDir', required=True, help='name of the output directory')
-    p.add_argument('-a', '--align', required=True, help='any non-empty value asks for alignment, which is out of scope here: pass ""')
-    p.add_argument('-x', '--starGenome', required=False)
-    p.add_argument('-s', '--geneAnnotation', required=False)
-    p.add_argument('-i', '--indexType', required=False)
-    p.add_argument('-b', '--numReadsBin', required=True, help='accepted for compatibility (the reference: reads per flush)')
-    p.add_argument('-p', '--performanceMetrics', required=True, help='any non-empty string is True, like the reference (CLI3:61)')
-    p.add_argument('-l', '--lengthFastq', required=True, help='accepted for compatibility (the reference: lines of the input)')
-    p.add_argument('-k', '--positionDetection', required=False, dest='positionDetection', action='store_false',
-                   help='give -k to turn automated barcode position detection OFF (store_false, CLI3:38)')
-    # bash wrapper vocabulary (splitseqdemultiplex_0.2.2.sh:83-193)
-    p.add_argument('-v', '--version', required=False, default='fast', help='only "fast" exists here')
-    p.add_argument('-c', '--collapseRandomHexamers', required=False, default='false',
-                   help='"true": fold RanHex Round1 barcodes into their OligoDT partners (Collapse_RanHex_Odt.py); the reference\'s fast path ignores it')
-    p.add_argument('-t', '--targetMemory', required=False)
-    p.add_argument('-g', '--granularity', required=False)
-    return p
-
-
-def main(argv=None):
-    args = build_parser().parse_args(argv)
-    if str(args.version) != 'fast':
-        sys.exit('only --version fast is implemented')
-    print("Starting Step1: demultiplexing on the GPU.")
-    if not os.path.exists(args.outputDir):
-        os.makedirs(args.outputDir)                                            # CLI3:48-49
-    whitelist = hostlogic.load_whitelist(".")
-    positions = dict(hostlogic.DEFAULT_POSITIONS)
-    if args.positionDetection:                                                  # default True (CLI3:38, 63)
-        print("Learning barcode positions to replace defaults...")
-        learned = hostlogic.learn_positions(hostlogic.learner_sample(args.fastqR))
-        for line in hostlogic.positions_report(learned):
-            print(line)
-        learned.pop("_found")
-        positions = learned
-    collapse = 48 if str(args.collapseRandomHexamers).lower() == 'true' else 0
-    dm = ssd_b200.Demultiplexer(whitelist, errors=int(args.errors), min_count=int(args.minReads), positions=positions,
-                                collapse_pairs=collapse)
-    r1 = np.fromfile(args.fastqF, dtype=np.uint8)
-    r2 = np.fromfile(args.fastqR, dtype=np.uint8)
-    out, stats = dm.run_host(r1, r2, ssd_b200.EMIT_PASSING)
-    dm.close()
-    if bool(args.performanceMetrics):                                           # CLI3:70 + V2:391
-        with open(os.path.join(args.outputDir, "MergedCells_passing.fastq"), "ab") as fh:  # V2:415 (append mode)
-            fh.write(out.tobytes())
-        for line in hostlogic.summary_lines(stats["n_cells"], args.minReads, stats["n_passing_cells"]):
-            print(line)
-    if bool(args.align):                                                        # CLI3:88
-        sys.exit("Alignment setting = True, but alignment is outside the scope of this tool: rerun with -a \"\" and "
-                 "feed MergedCells_passing.fastq to STAR yourself")
-    print("Alignment setting = False, exiting run")
-    return 0
-
+import runpy
 
 if __name__ == '__main__':
-    main()
+    runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "splitseqdemultiplex_0.2.3.py"), run_name="__main__")

@@ -4,14 +4,13 @@
 
 CLI3 splits the FASTQs into -n chunk files, runs demultiplex_fun per chunk in worker processes, filters the
 concatenation, then deletes the intermediates (CLI3:52-81).  Here the whole pair of files goes through one fused
-device pipeline (scan, match, filter, write); -n is accepted for compatibility and ignored (one process drives one
-GPU; launch under torchrun for several).  The bash wrappers' extra flags (-v fast, -c, -t, -g) are accepted too.
+device pipeline (scan, match, filter, write); -n is accepted for compatibility and ignored: one process drives one
+GPU, and `torchrun --nproc-per-node N splitseqdemultiplex_0.2.3.py ...` shares the pair of files between N GPUs
+(ssd_b200.filebatch.run_files_sharded: contiguous runs of record-aligned batches per rank, -m decided globally).  The bash wrappers' extra flags (-v fast, -c, -t, -g) are accepted too.
 """
 import argparse
 import os
 import sys
-
-import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 if _HERE not in sys.path:
@@ -55,34 +54,54 @@ def main(argv=None):
     args = build_parser().parse_args(argv)
     if str(args.version) != 'fast':
         sys.exit('only --version fast is implemented')
-    print("Starting Step1: demultiplexing on the GPU.")
-    if not os.path.exists(args.outputDir):
+    # Under torchrun (one process per GPU) the ranks share the pair of files: the reference's fan-out over chunk files
+    # (CLI3:52-64) with GPUs in place of worker processes; rank 0 does the talking.
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    say = print if rank == 0 else (lambda *a, **k: None)
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    say("Starting Step1: demultiplexing on the GPU.")
+    if rank == 0 and not os.path.exists(args.outputDir):
         os.makedirs(args.outputDir)                                            # CLI3:48-49
     whitelist = hostlogic.load_whitelist(".")
     positions = dict(hostlogic.DEFAULT_POSITIONS)
     if args.positionDetection:                                                  # default True (CLI3:38, 63)
-        print("Learning barcode positions to replace defaults...")
+        say("Learning barcode positions to replace defaults...")
         learned = hostlogic.learn_positions(hostlogic.learner_sample(args.fastqR))
         for line in hostlogic.positions_report(learned):
-            print(line)
+            say(line)
         learned.pop("_found")
         positions = learned
     collapse = 48 if str(args.collapseRandomHexamers).lower() == 'true' else 0
     dm = ssd_b200.Demultiplexer(whitelist, errors=int(args.errors), min_count=int(args.minReads), positions=positions,
-                                collapse_pairs=collapse)
-    r1 = np.fromfile(args.fastqF, dtype=np.uint8)
-    r2 = np.fromfile(args.fastqR, dtype=np.uint8)
-    out, stats = dm.run_host(r1, r2, ssd_b200.EMIT_PASSING)
-    dm.close()
-    if bool(args.performanceMetrics):                                           # CLI3:70 + V2:391
-        with open(os.path.join(args.outputDir, "MergedCells_passing.fastq"), "ab") as fh:  # V2:415 (append mode)
-            fh.write(out.tobytes())
+                                collapse_pairs=collapse, device=local if world > 1 else None)
+    # file to file inside the library (pinned rings, overlapped copies; batches of whole records above SSD_BATCH_BYTES).
+    # Without -p the reference still demultiplexes (and raises on a missing mate) but never writes the passing file.
+    wanted = bool(args.performanceMetrics)                                      # CLI3:70 + V2:391
+    out_path = os.path.join(args.outputDir, "MergedCells_passing.fastq") if wanted else os.devnull
+    try:
+        if world > 1:
+            from ssd_b200 import filebatch
+            if not wanted:
+                out_path = os.path.join(args.outputDir, ".MergedCells_passing.discard")  # the ranks' parts need a real directory
+            _, stats = filebatch.run_files_sharded(dm, args.fastqF, args.fastqR, out_path, ssd_b200.EMIT_PASSING, append=True, world=world)
+            if not wanted and rank == 0:
+                os.remove(out_path)
+        else:
+            _, stats = dm.run_files(args.fastqF, args.fastqR, out_path, ssd_b200.EMIT_PASSING, append=True)  # V2:415 (append mode)
+    finally:
+        dm.close()
+    if wanted:
         for line in hostlogic.summary_lines(stats["n_cells"], args.minReads, stats["n_passing_cells"]):
-            print(line)
+            say(line)
     if bool(args.align):                                                        # CLI3:88
         sys.exit("Alignment setting = True, but alignment is outside the scope of this tool: rerun with -a \"\" and "
                  "feed MergedCells_passing.fastq to STAR yourself")
-    print("Alignment setting = False, exiting run")
+    say("Alignment setting = False, exiting run")
     return 0
 
 

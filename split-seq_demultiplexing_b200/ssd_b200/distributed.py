@@ -128,13 +128,14 @@ def global_filter(dm, world: int, group=None) -> dict:
     return dm.filter_single()
 
 
-def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None) -> dict:
+def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None, rounds: int = None) -> dict:
     """The two passes over batches that a global -m decision needs (see demux_batches).  `phase1` is a callable returning an
     iterator; every step of the iterator has run phase 1 of the next batch on dm (ssd_demux_device, ssd_demux_loaded,
     ssd_annotated_loaded ...) and yields whatever `emit` needs to know about the batch.  It is gone through twice.
     emit(batch, stats) is called in pass 2 once the filter of the batch is built from the GLOBAL tables; it writes the
     batch's output (ssd_emit_device, ssd_emit_file ...).  Returns the statistics summed over the batches (cell counts are
-    global)."""
+    global).  With N > 1 every batch of pass 1 is one round of collectives, so all ranks must go through the same number
+    of rounds: `rounds` = the largest batch count of any rank (ranks with fewer batches, or none, send empty messages)."""
     import time
     import torch
     import torch.distributed as dist
@@ -156,8 +157,16 @@ def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None) 
         torch.cuda.synchronize()
         dm._keep = []  # the batch may go before the next one is produced (two of them need not fit)
         del batch
+    if distinct_mode and world > 1:
+        for _ in range(len(kept_k), rounds or 0):  # this rank has fewer batches than another: empty rounds
+            k, i = exchange_owned(torch.empty(0, dtype=torch.int64, device="cuda"), [0] * world,
+                                  torch.empty((0, 2), dtype=torch.int64, device="cuda"), group=group)
+            kept_k.append(k.clone())
+            kept_i.append(i.clone())
     if hist is None:
-        return {}
+        if world == 1:
+            return {}
+        hist = torch.zeros_like(dm.reads_histogram())
     t_pass1 = time.perf_counter()
     distinct = None
     if distinct_mode:
@@ -165,11 +174,15 @@ def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None) 
         all_i = torch.cat(kept_i) if kept_i else torch.empty((0, 2), dtype=torch.int64, device="cuda")
         del kept_k, kept_i
         torch.cuda.empty_cache()  # the library allocates with cudaMalloc: blocks torch has cached are out of its reach
+        # the library may run on a stream of its own (no set_stream): hand tensors over only when both sides are done
+        torch.cuda.synchronize()
         if world > 1:
             dm.count_distinct_owned(all_k, all_i, rank, world)
+            torch.cuda.synchronize()
             dist.all_reduce(dm.distinct_histogram(), group=group)
         else:
             dm.count_distinct(all_k, all_i)
+        torch.cuda.synchronize()
         distinct = dm.distinct_histogram().clone()
         del all_k, all_i
     if world > 1:
@@ -181,6 +194,7 @@ def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None) 
         dm.reads_histogram().copy_(hist)
         if distinct is not None:
             dm.distinct_histogram().copy_(distinct)
+        torch.cuda.synchronize()
         st = dm.build_filter()
         emit(batch, st)
         for key, v in st.items():

@@ -131,3 +131,78 @@ def filter_annotated_file_batched(dm, path_in: str, out_path: str, append: bool 
 
     total = two_pass(dm, phase1, emit)
     return written[0], total
+
+
+def run_files_sharded(dm, path_r1: str, path_r2: str, out_path: str, which: int = L.EMIT_PASSING, append: bool = True,
+                      world: int = 1, group=None, target_bytes: Optional[int] = None):
+    """One pair of files, N ranks (one process per GPU, torch.distributed initialised): the reference's fan-out over chunk
+    files (CLI3:52-64) with GPUs in place of worker processes.  Rank 0 cuts the files into batches of whole records (at
+    most SSD_BATCH_BYTES, at least N of them when the files allow), every rank takes a contiguous run of batches through
+    the two passes of ssd_b200.distributed.two_pass (read histogram all-reduced, (cell, UMI) keys sent to the owner rank
+    batch by batch, so -m is decided globally and exactly), writes its records to <out_path>.part<rank>, and rank 0 strings
+    the parts together in rank order -- the bytes of the single-GPU call.  Returns (bytes written by all ranks, stats with
+    the per-rank sums added up); call it on every rank."""
+    import torch
+    import torch.distributed as dist
+    from .distributed import shard_record_ranges, two_pass
+    if world <= 1:
+        return run_files_batched(dm, path_r1, path_r2, out_path, which, append, target_bytes)
+    rank = dist.get_rank(group)
+    box = [None]
+    if rank == 0:
+        try:
+            target = target_bytes
+            if target is None:
+                target = max(1, min(batch_bytes(), -(-os.path.getsize(path_r1) // world)))
+            batches = pair_batches(path_r1, path_r2, target)
+            box[0] = [batches[lo:hi] for lo, hi in shard_record_ranges(len(batches), world)]
+            _truncate(out_path, append)
+        except OSError as e:  # every rank raises what rank 0 met
+            box[0] = e
+    dist.broadcast_object_list(box, src=0, group=group)
+    if isinstance(box[0], Exception):
+        raise box[0]
+    plan = box[0]
+    mine, rounds = plan[rank], max(len(p) for p in plan)
+    part = "%s.part%d" % (out_path, rank)
+    open(part, "wb").close()
+    p1, p2 = os.fsencode(path_r1), os.fsencode(path_r2)
+    written = [0]
+
+    def phase1():
+        for o1, n1, o2, n2 in mine:
+            dm._check(dm.lib.ssd_load_file_range(dm._ctx, 0, p1, o1, n1))
+            dm._check(dm.lib.ssd_load_file_range(dm._ctx, 1, p2, o2, n2))
+            dm._check(dm.lib.ssd_demux_loaded(dm._ctx))
+            yield None
+
+    def emit(_, st):
+        written[0] += _emit_file(dm, which, part)
+
+    total = two_pass(dm, phase1, emit, world=world, group=group, rounds=rounds)
+    keys = sorted(k for k in total if k not in ("n_cells", "n_passing_cells"))
+    if not total:  # a rank without batches: the cell counts come from the tables every rank holds
+        keys = []
+    names = [None]
+    if rank == 0:
+        names[0] = keys
+    dist.broadcast_object_list(names, src=0, group=group)
+    sums = torch.tensor([float(total.get(k, 0)) for k in names[0]] + [float(written[0])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(sums, group=group)
+    cells = torch.tensor([float(total.get("n_cells", 0)), float(total.get("n_passing_cells", 0))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(cells, op=dist.ReduceOp.MAX, group=group)
+    stats = {k: int(v) for k, v in zip(names[0], sums.tolist())}
+    stats["n_cells"], stats["n_passing_cells"] = int(cells[0]), int(cells[1])
+    dist.barrier(group=group)
+    if rank == 0:
+        with open(out_path, "ab") as out:
+            for r in range(world):
+                with open("%s.part%d" % (out_path, r), "rb") as fh:
+                    while True:
+                        buf = fh.read(64 << 20)
+                        if not buf:
+                            break
+                        out.write(buf)
+                os.remove("%s.part%d" % (out_path, r))
+    dist.barrier(group=group)
+    return int(sums[-1]), stats

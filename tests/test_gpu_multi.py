@@ -126,3 +126,53 @@ def test_two_ranks_three_batches_each_equal_one_call(tmp_path):
     assert int(st[0][0]) == int(st[1][0]) == stats["n_cells"]
     assert int(st[0][1]) == int(st[1][1]) == stats["n_passing_cells"]
     assert int(st[0][2]) + int(st[1][2]) == stats["n_retained"]
+
+
+def _cli_worker(rank, world, port, workdir, batch_bytes):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                      SSD_BATCH_BYTES=str(batch_bytes))
+    os.chdir(workdir)
+    import contextlib
+    import io
+    import runpy
+    import sys
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "split-seq_demultiplexing_b200")
+    sys.path.insert(0, pkg)
+    sys.argv = ["splitseqdemultiplex_0.2.3.py", "-n", "2", "-e", "1", "-m", "10", "-1", "a", "-2", "b", "-3", "c", "-f", "F.fastq", "-r", "R.fastq",
+                "-o", "results", "-a", "", "-b", "100000", "-p", "True", "-l", "20000"]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        runpy.run_path(os.path.join(pkg, "splitseqdemultiplex_0.2.3.py"), run_name="__main__")
+    open("stdout_%d.txt" % rank, "w").write(buf.getvalue())
+    import torch.distributed as dist
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch_bytes", [100000, 10**9])
+def test_cli_under_two_ranks_matches_the_reference_digest(tmp_path, batch_bytes):
+    """The drop-in CLI launched with one process per GPU: the two ranks share the bundled pair of files (8 batches of whole
+    records, or one batch and a rank without work), -m is decided globally, rank 0 strings the parts together; the result
+    is the reference's golden digest and its printed summary."""
+    import json
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    fu.write_whitelist_files(str(tmp_path))
+    r1, r2 = fu.load_bundled()
+    (tmp_path / "F.fastq").write_bytes(r1)
+    (tmp_path / "R.fastq").write_bytes(r2)
+    mp.spawn(_cli_worker, args=(2, _free_port(), str(tmp_path), batch_bytes), nprocs=2, join=True)
+    gold = json.load(open(os.path.join(fu.GOLDEN_DIR, "bundled_digests.json")))["e1_m10"]
+    out = (tmp_path / "results" / "MergedCells_passing.fastq").read_bytes()
+    assert fu.canonical_sha(out) == gold["passing_sha"]
+    assert not [f for f in os.listdir(str(tmp_path / "results")) if ".part" in f]
+    said = (tmp_path / "stdout_0.txt").read_text()
+    assert gold["stdout_tail"][0] in said and gold["stdout_tail"][1] in said
+    assert (tmp_path / "stdout_1.txt").read_text() == ""
+    # and the bytes of the single-GPU call on the same files
+    import ssd_b200
+    dm = ssd_b200.Demultiplexer(WL, errors=1, min_count=10)
+    single = tmp_path / "single.fastq"
+    dm.run_files(str(tmp_path / "F.fastq"), str(tmp_path / "R.fastq"), str(single), ssd_b200.EMIT_PASSING, append=False)
+    assert out == single.read_bytes()
