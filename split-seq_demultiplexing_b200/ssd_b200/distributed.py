@@ -141,6 +141,9 @@ def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None, 
     import torch.distributed as dist
     distinct_mode = dm.filter_mode == "distinct_umi"
     rank = dist.get_rank(group) if world > 1 else 0
+    dev = dm.reads_histogram().device  # "cuda" with the library; the gloo tests drive this function with a CPU stand-in
+    sync = torch.cuda.synchronize if dev.type == "cuda" else (lambda: None)
+    trim = torch.cuda.empty_cache if dev.type == "cuda" else (lambda: None)
     hist, kept_k, kept_i = None, [], []
     t_start = time.perf_counter()
     for batch in phase1():
@@ -154,13 +157,13 @@ def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None, 
                 k, i = dm.local_unique_keys()
             kept_k.append(k.clone())
             kept_i.append(i.clone())
-        torch.cuda.synchronize()
+        sync()
         dm._keep = []  # the batch may go before the next one is produced (two of them need not fit)
         del batch
     if distinct_mode and world > 1:
         for _ in range(len(kept_k), rounds or 0):  # this rank has fewer batches than another: empty rounds
-            k, i = exchange_owned(torch.empty(0, dtype=torch.int64, device="cuda"), [0] * world,
-                                  torch.empty((0, 2), dtype=torch.int64, device="cuda"), group=group)
+            k, i = exchange_owned(torch.empty(0, dtype=torch.int64, device=dev), [0] * world,
+                                  torch.empty((0, 2), dtype=torch.int64, device=dev), group=group)
             kept_k.append(k.clone())
             kept_i.append(i.clone())
     if hist is None:
@@ -170,39 +173,39 @@ def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None, 
     t_pass1 = time.perf_counter()
     distinct = None
     if distinct_mode:
-        all_k = torch.cat(kept_k) if kept_k else torch.empty(0, dtype=torch.int64, device="cuda")
-        all_i = torch.cat(kept_i) if kept_i else torch.empty((0, 2), dtype=torch.int64, device="cuda")
+        all_k = torch.cat(kept_k) if kept_k else torch.empty(0, dtype=torch.int64, device=dev)
+        all_i = torch.cat(kept_i) if kept_i else torch.empty((0, 2), dtype=torch.int64, device=dev)
         del kept_k, kept_i
-        torch.cuda.empty_cache()  # the library allocates with cudaMalloc: blocks torch has cached are out of its reach
+        trim()  # the library allocates with cudaMalloc: blocks torch has cached are out of its reach
         # the library may run on a stream of its own (no set_stream): hand tensors over only when both sides are done
-        torch.cuda.synchronize()
+        sync()
         if world > 1:
             dm.count_distinct_owned(all_k, all_i, rank, world)
-            torch.cuda.synchronize()
+            sync()
             dist.all_reduce(dm.distinct_histogram(), group=group)
         else:
             dm.count_distinct(all_k, all_i)
-        torch.cuda.synchronize()
+        sync()
         distinct = dm.distinct_histogram().clone()
         del all_k, all_i
     if world > 1:
         dist.all_reduce(hist, group=group)
-    torch.cuda.synchronize()
+    sync()
     t_count = time.perf_counter()
     total = {}
     for batch in phase1():
         dm.reads_histogram().copy_(hist)
         if distinct is not None:
             dm.distinct_histogram().copy_(distinct)
-        torch.cuda.synchronize()
+        sync()
         st = dm.build_filter()
         emit(batch, st)
         for key, v in st.items():
             total[key] = v if key in ("n_cells", "n_passing_cells") else total.get(key, 0) + v
-        torch.cuda.synchronize()
+        sync()
         dm._keep = []
         del batch
-        torch.cuda.empty_cache()  # batches of tens of GB: do not let the caching allocator fragment what is left
+        trim()  # batches of tens of GB: do not let the caching allocator fragment what is left
     if timing is not None:
         timing.update(pass1_s=t_pass1 - t_start, count_s=t_count - t_pass1, pass2_s=time.perf_counter() - t_count)
     return total

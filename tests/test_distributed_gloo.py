@@ -123,3 +123,114 @@ def test_shard_record_ranges():
     assert shard_record_ranges(3, 8)[3:] == [(3, 3)] * 5
     r = shard_record_ranges(1_000_000_007, 8)
     assert r[0][0] == 0 and r[-1][1] == 1_000_000_007 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+# ---- two_pass (batches over time and over ranks) with a CPU stand-in for the library -------------------------------
+class _StandIn:
+    """What two_pass needs from a Demultiplexer, on CPU tensors: per-batch read histogram and (cell, UMI) keys, ownership
+    like the library's (interleaved bucket ranges), exact distinct counts of arbitrary key arrays."""
+    SHIFT, NB = 12, (N_CELLS + (1 << 12) - 1) >> 12
+
+    def __init__(self, m):
+        self.filter_mode, self.m, self._keep = "distinct_umi", m, []
+        self.hist = torch.zeros(N_CELLS, dtype=torch.int32)
+        self.distinct = torch.zeros(N_CELLS, dtype=torch.int32)
+        self.batch_cells = torch.empty(0, dtype=torch.int64)
+        self.keys = torch.empty(0, dtype=torch.int64)
+
+    def load(self, cells, umis):  # "phase 1" of a batch
+        self.batch_cells = cells
+        self.keys = (cells << UMI_BITS) | umis
+        self.hist.zero_()
+        self.hist.index_add_(0, cells, torch.ones(cells.numel(), dtype=torch.int32))
+
+    def reads_histogram(self):
+        return self.hist
+
+    def distinct_histogram(self):
+        return self.distinct
+
+    def local_unique_keys(self):
+        return torch.unique(self.keys), torch.empty((0, 2), dtype=torch.int64)
+
+    def partition_keys(self, world):
+        from ssd_b200 import distributed as D
+        rows, counts = D.group_by_owner(self.keys, self.keys >> UMI_BITS, self.SHIFT, self.NB, world)
+        offs = [0]
+        for c in counts.tolist():
+            offs.append(offs[-1] + c)
+        return rows, offs, torch.empty((0, 2), dtype=torch.int64)
+
+    def _count(self, keys):
+        self.distinct.zero_()
+        uk = torch.unique(keys)
+        self.distinct.index_add_(0, uk >> UMI_BITS, torch.ones(uk.numel(), dtype=torch.int32))
+
+    def count_distinct(self, keys, irr):
+        self._count(keys)
+
+    def count_distinct_owned(self, keys, irr, rank, world):
+        from ssd_b200 import distributed as D
+        assert bool((D.owner_of_cells(keys >> UMI_BITS, self.SHIFT, self.NB, world) == rank).all())  # only this rank's cells arrived
+        self._count(keys)
+
+    def build_filter(self):
+        passing = self.distinct >= self.m
+        return {"n_cells": int((self.hist > 0).sum()), "n_passing_cells": int(passing.sum()),
+                "n_retained": int(passing[self.batch_cells].sum()), "n_matched": int(self.batch_cells.numel())}
+
+
+def _batches_of(rank, counts):
+    rng = np.random.default_rng(7)
+    cells = rng.choice(N_CELLS, size=400, replace=False)
+    out = []
+    for r, n_batches in enumerate(counts):
+        mine = []
+        for b in range(n_batches):
+            n = int(rng.integers(1, 4000))
+            mine.append((torch.from_numpy(rng.choice(cells, size=n)).to(torch.int64), torch.from_numpy(rng.integers(0, 40, size=n)).to(torch.int64)))
+        out.append(mine)
+    return out
+
+
+def _two_pass_worker(rank, world, port, out_dir, counts):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ssd_b200 import distributed as D
+    dm = _StandIn(m=5)
+    mine = _batches_of(rank, counts)[rank]
+
+    def phase1():
+        for cells, umis in mine:
+            dm.load(cells, umis)
+            yield cells
+
+    kept = []
+    total = D.two_pass(dm, phase1, lambda cells, st: kept.append(st["n_retained"]), world=world, rounds=max(counts))
+    np.save(os.path.join(out_dir, "tp_%d.npy" % rank), np.array([total.get("n_cells", -1), total.get("n_passing_cells", -1), sum(kept), len(kept)]))
+    np.save(os.path.join(out_dir, "tp_distinct_%d.npy" % rank), dm.distinct_histogram().numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts", [(3, 1), (2, 2), (1, 0), (0, 2, 4)])
+def test_two_pass_over_ranks_with_unequal_batch_counts(tmp_path, counts):
+    """Every rank goes through the same number of collective rounds whatever its number of batches (even none); the global
+    tables every rank ends up with are those of one process that sees all keys."""
+    world = len(counts)
+    mp.spawn(_two_pass_worker, args=(world, _free_port(), str(tmp_path), counts), nprocs=world, join=True)
+    everything = [b for per_rank in _batches_of(0, counts) for b in per_rank]
+    cells = torch.cat([c for c, _ in everything])
+    keys = torch.unique(torch.cat([(c << UMI_BITS) | u for c, u in everything]))
+    distinct = torch.zeros(N_CELLS, dtype=torch.int32)
+    distinct.index_add_(0, keys >> UMI_BITS, torch.ones(keys.numel(), dtype=torch.int32))
+    passing = distinct >= 5
+    retained = 0
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), "tp_%d.npy" % r))
+        assert (np.load(os.path.join(str(tmp_path), "tp_distinct_%d.npy" % r)) == distinct.numpy()).all()
+        assert got[3] == counts[r]
+        if counts[r]:
+            assert got[0] == len(torch.unique(cells)) and got[1] == int(passing.sum())
+        retained += got[2]
+    assert retained == int(passing[cells].sum())
