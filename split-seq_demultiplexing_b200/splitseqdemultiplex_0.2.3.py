@@ -42,7 +42,8 @@ def build_parser():
     p.add_argument('-k', '--positionDetection', required=False, dest='positionDetection', action='store_false',
                    help='give -k to turn automated barcode position detection OFF (store_false, CLI3:38)')
     # bash wrapper vocabulary (splitseqdemultiplex_0.2.2.sh:83-193)
-    p.add_argument('-v', '--version', required=False, default='fast', help='only "fast" exists here')
+    p.add_argument('-v', '--version', required=False, default='fast',
+                   help='"fast" (merged output) or "split" (the same records as one file per cell, legacy naming)')
     p.add_argument('-c', '--collapseRandomHexamers', required=False, default='false',
                    help='"true": fold RanHex Round1 barcodes into their OligoDT partners (Collapse_RanHex_Odt.py); the reference\'s fast path ignores it')
     p.add_argument('-t', '--targetMemory', required=False)
@@ -52,8 +53,8 @@ def build_parser():
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    if str(args.version) != 'fast':
-        sys.exit('only --version fast is implemented')
+    if str(args.version) not in ('fast', 'split'):
+        sys.exit('only --version fast (and its per-cell variant, split) is implemented')
     # Under torchrun (one process per GPU) the ranks share the pair of files: the reference's fan-out over chunk files
     # (CLI3:52-64) with GPUs in place of worker processes; rank 0 does the talking.
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -84,7 +85,17 @@ def main(argv=None):
     wanted = bool(args.performanceMetrics)                                      # CLI3:70 + V2:391
     out_path = os.path.join(args.outputDir, "MergedCells_passing.fastq") if wanted else os.devnull
     try:
-        if world > 1:
+        if str(args.version) == 'split':
+            # per-cell files instead of the merged one: the fast path's annotated records bucketed by cell, named like the
+            # legacy pipeline's results (round1-round2-round3.fastq, demultiplex_using_barcodes.py:364); one GPU, one call
+            import numpy as np
+            if world > 1:
+                sys.exit('--version split runs on one GPU')
+            _, stats = dm.run_host(np.fromfile(args.fastqF, dtype=np.uint8), np.fromfile(args.fastqR, dtype=np.uint8), ssd_b200.EMIT_PASSING)
+            if wanted:
+                files = dm.write_split_files(args.outputDir, hostlogic.load_round_names("."), stats)
+                say("# of results files [{}]".format(len(files)))               # demultiplex_using_barcodes.py:408
+        elif world > 1:
             from ssd_b200 import filebatch
             if not wanted:
                 out_path = os.path.join(args.outputDir, ".MergedCells_passing.discard")  # the ranks' parts need a real directory

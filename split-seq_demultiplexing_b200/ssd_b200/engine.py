@@ -195,10 +195,36 @@ class Demultiplexer:
             self._check(self.lib.ssd_split_index(self._ctx, cells.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
                                                  first.ctypes.data_as(C.c_void_p), nb.value))
         table = []
+        self._split_ids = [int(c) for c in cells]  # cell ids of the buckets, in table order
         for b in range(nb.value):
             end_off = int(offs[b + 1]) if b + 1 < nb.value else n.value
             table.append((self.cell_string(int(cells[b])), int(offs[b]), None, end_off - int(offs[b])))
         return n.value, table, first
+
+    def write_split_files(self, out_dir: str, round_names=None, stats: Optional[dict] = None) -> List[Tuple[str, int]]:
+        """Split mode on disk: after a run, one FASTQ file per passing cell holding that cell's annotated
+        records in input order, named like the legacy pipeline's per-cell files, round1-round2-round3.fastq with the
+        full-length barcodes of the three Round files (demultiplex_using_barcodes.py:364; round_names =
+        hostlogic.load_round_names(dir)), or with the 8-mers when no names are given.  Files are opened in append mode like
+        splitseq_utilities.flushBuffers (utilities:15-21).  `stats` = what the run returned (else the filter is rebuilt).
+        Returns [(file name, bytes)] in cell order."""
+        import torch
+        from . import hostlogic
+        stats = stats or self.build_filter()
+        out = torch.empty(int(stats["bytes_passing"]) + 16, dtype=torch.uint8, device="cuda")
+        n, table, _ = self.emit_split_device(out.data_ptr(), out.numel())
+        host = out[:n].cpu().numpy()
+        del out
+        os.makedirs(out_dir, exist_ok=True)
+        nw, written = len(self.whitelist), []
+        for (_, off, _, nbytes), cid in zip(table, self._split_ids):
+            i1, i2, i3 = cid // (nw * nw), (cid // nw) % nw, cid % nw
+            name = (hostlogic.split_file_name(round_names, i1, i2, i3) if round_names is not None
+                    else "%s-%s-%s.fastq" % (self.whitelist[i1], self.whitelist[i2], self.whitelist[i3]))
+            with open(os.path.join(out_dir, name), "ab") as fh:
+                fh.write(host[off:off + nbytes].tobytes())
+            written.append((name, nbytes))
+        return written
 
     def record_cells(self):
         import numpy as np

@@ -28,6 +28,22 @@ def load_whitelist(directory: str = ".") -> List[str]:
     return wl
 
 
+def load_round_names(directory: str = ".") -> Tuple[List[str], List[str], List[str]]:
+    """The full-length barcodes of the three rounds (16-, 13- and 14-mers in the bundled files), line i of every file being
+    entry i of the whitelist (Round 1 carries its 8-mer at [8:16], Rounds 2 and 3 at [0:8]).  The legacy pipeline names
+    its per-cell files after them: round1 + "-" + round2 + "-" + round3 + ".fastq" (demultiplex_using_barcodes.py:364)."""
+    out = []
+    for name in (ROUND1_FILE, ROUND2_FILE, ROUND3_FILE):
+        with open(os.path.join(directory, name), "r") as fh:
+            out.append([line.rstrip() for line in fh])
+    return out[0], out[1], out[2]
+
+
+def split_file_name(names: Tuple[List[str], List[str], List[str]], i1: int, i2: int, i3: int) -> str:
+    """demultiplex_using_barcodes.py:364: bufferKey = round1 + HYPHEN + round2 + HYPHEN + round3 + FASTQ_EXTENSION."""
+    return names[0][i1] + "-" + names[1][i2] + "-" + names[2][i3] + ".fastq"
+
+
 def learner_sample(fastq_r: str, n_lines: int = 1001) -> List[str]:
     """LIB:99-110: the first 1001 lines of read 2, each strip()ped."""
     with open(fastq_r, "r") as fh:

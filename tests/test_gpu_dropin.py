@@ -244,3 +244,37 @@ def test_run_files_in_batches_matches_the_oracle(tmp_path, monkeypatch):
     bad.write_bytes(r2.replace(b"@SYN.30001 ", b"@SYX.30001 ", 1))
     with pytest.raises(KeyError):
         dm.run_files(str(p1), str(bad), str(tmp_path / "x.fastq"), ssd_b200.EMIT_MATCHED, append=False)
+
+
+def test_cli_split_version_writes_one_file_per_cell(workdir, digests):
+    """-v split: the fast path's passing records as one file per cell, named like the legacy pipeline's results
+    (round1-round2-round3.fastq with the full-length barcodes, demultiplex_using_barcodes.py:364), appended to like
+    flushBuffers does.  The union of the files is the merged output of -v fast (the reference's golden digest)."""
+    from ssd_b200 import hostlogic
+    argv = ["-n", "4", "-e", "1", "-m", "10", "-1", "a", "-2", "b", "-3", "c", "-f", "F.fastq", "-r", "R.fastq", "-o", "cells",
+            "-a", "", "-b", "100000", "-p", "True", "-l", "20000", "-v", "split"]
+    old = sys.argv
+    sys.argv = ["splitseqdemultiplex_0.2.3.py"] + argv
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            runpy.run_path(os.path.join(PKG, "splitseqdemultiplex_0.2.3.py"), run_name="__main__")
+    finally:
+        sys.argv = old
+    gold = digests["e1_m10"]
+    files = sorted(os.listdir("cells"))
+    assert len(files) == gold["passing_cells"]
+    assert "# of results files [%d]" % len(files) in buf.getvalue()
+    names = hostlogic.load_round_names(".")
+    r1 = {n[8:16]: n for n in names[0]}
+    r2 = {n[0:8]: n for n in names[1]}
+    r3 = {n[0:8]: n for n in names[2]}
+    everything = []
+    for f in files:
+        recs = fu.records(open(os.path.join("cells", f), "rb").read())
+        cells = {r.split(b"\n", 1)[0].split(b"_")[1].decode() for r in recs}
+        assert len(cells) == 1                                             # one cell per file
+        c = cells.pop()
+        assert f == r1[c[0:8]] + "-" + r2[c[8:16]] + "-" + r3[c[16:24]] + ".fastq"
+        everything.append(open(os.path.join("cells", f), "rb").read())
+    assert fu.canonical_sha(b"".join(everything)) == gold["passing_sha"]

@@ -207,3 +207,15 @@ def test_pair_batches_cover_both_files_with_the_same_records(ssd, tmp_path):
     assert o1 + n1 == len(r1) and o2 + n2 == os.path.getsize(str(p2))
     with pytest.raises(FileNotFoundError):
         filebatch.pair_batches(str(tmp_path / "missing.fastq"), str(p2))
+
+
+def test_round_names_and_legacy_split_file_name(ssd, tmp_path):
+    from ssd_b200 import hostlogic
+    fu.write_whitelist_files(str(tmp_path))
+    names = hostlogic.load_round_names(str(tmp_path))
+    wl = hostlogic.load_whitelist(str(tmp_path))
+    assert [len(n) for n in names] == [len(wl)] * 3
+    assert all(a[8:16] == w and b[0:8] == w and c[0:8] == w for a, b, c, w in zip(*names, wl))   # line i of every file is entry i
+    # demultiplex_using_barcodes.py:364: round1 + "-" + round2 + "-" + round3 + ".fastq"
+    assert hostlogic.split_file_name(names, 0, 1, 2) == names[0][0] + "-" + names[1][1] + "-" + names[2][2] + ".fastq"
+    assert (len(names[0][0]), len(names[1][0]), len(names[2][0])) == (16, 13, 14)
