@@ -470,7 +470,8 @@ int umi_set_counts(ssd_ctx* c, Src src, uint64_t n_src, uint64_t n_keys_bound, c
     OKR(ensure(c, *table, 2 * n_keys_bound * sizeof(uint32_t)));
     CU(c, cudaMemsetAsync(table->p, 0, 2 * n_keys_bound * sizeof(uint32_t), c->stream));
     k_umi_sets<Src><<<(uint32_t)std::min<uint64_t>(blocks_for(n_src, kThreads), 148 * 8), kThreads, 0, c->stream>>>(src, n_src, c->dcfg.umi_bits, counts, seg, (uint32_t*)table->p, c->d_distinct);
-    c->n_launches++;
+    k_umi_bitmap_counts<<<148 * 4, kThreads, 0, c->stream>>>(counts, seg, (const uint32_t*)table->p, (uint32_t)nc, c->dcfg.umi_bits, c->d_distinct);
+    c->n_launches += 2;
     CU(c, cudaGetLastError());
     return SSD_OK;
 }

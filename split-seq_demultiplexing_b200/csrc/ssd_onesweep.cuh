@@ -239,15 +239,9 @@ __global__ void __launch_bounds__(kThreads) k_umi_sets(Src keys, uint64_t n, int
         const uint64_t slots = 2ull * cnt;
         uint32_t* set = table + sg;
         if (slots > (uint64_t)bitmap_words) {
-            // a large cell: one bit per possible UMI is smaller than its hash set (and stays in the cache)
-            const uint32_t bit = 1u << (umi & 31u);
-            const uint32_t old = atomicOr(set + (umi >> 5), bit);
-            if (!(old & bit)) {
-                const uint32_t e = (cell * 0x9E3779B1u) >> 24;
-                const uint32_t prev = atomicCAS(&s_cell[e], 0xFFFFFFFFu, cell);
-                if (prev == 0xFFFFFFFFu || prev == cell) atomicAdd(&s_cnt[e], 1u);
-                else atomicAdd(&distinct[cell], 1u);
-            }
+            // a large cell: one bit per possible UMI is smaller than its hash set (and stays in the cache).  The bit is set
+            // without waiting for the old value (RED); k_umi_bitmap_counts counts the bits of these cells afterwards.
+            atomicOr(set + (umi >> 5), 1u << (umi & 31u));
             continue;
         }
         uint32_t h = umi * 0x9E3779B1u;
@@ -275,6 +269,36 @@ __global__ void __launch_bounds__(kThreads) k_umi_sets(Src keys, uint64_t n, int
     __syncthreads();
     for (int j = threadIdx.x; j < kHotSlots; j += kThreads)
         if (s_cnt[j]) atomicAdd(&distinct[s_cell[j]], s_cnt[j]);
+}
+
+// distinct[cell] += set bits of the bitmap of every cell that has one (the cells k_umi_sets did not count itself)
+__global__ void __launch_bounds__(kThreads) k_umi_bitmap_counts(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ seg,
+                                                                const uint32_t* __restrict__ table, uint32_t n_cells, int umi_bits, uint32_t* distinct)
+{
+    const uint32_t bitmap_words = umi_bits >= 5 ? 1u << (umi_bits - 5) : 1u;
+    __shared__ uint32_t s_list[kThreads], s_n, s_sum;
+    for (uint32_t base = blockIdx.x * kThreads; base < n_cells; base += gridDim.x * kThreads) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const uint32_t cell = base + threadIdx.x;
+        if (cell < n_cells && 2ull * counts[cell] > (uint64_t)bitmap_words) s_list[atomicAdd(&s_n, 1u)] = cell;
+        __syncthreads();
+        const uint32_t n = s_n;
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t c = s_list[k];
+            const uint32_t* bm = table + seg[c];
+            uint32_t sum = 0;
+            for (uint32_t w = threadIdx.x; w < bitmap_words; w += kThreads) sum += (uint32_t)__popc(bm[w]);
+            sum = __reduce_add_sync(0xFFFFFFFFu, sum);
+            if (threadIdx.x == 0) s_sum = 0;
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&s_sum, sum);
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(&distinct[c], s_sum);
+            __syncthreads();
+        }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
