@@ -9,7 +9,7 @@ python bench.py > $o/bench_$tag.json 2> $o/bench_$tag.err || { echo "bench faile
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 0"
 $B > $o/plain_$tag.log 2>&1 || { echo "plain bench failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/launches_$tag.csv $B > $o/ncu_l_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"^(k_scan|k_emit_stream|k_umi_sets)$" -s 8 -c 4 -f -o $o/top4_$tag $B > $o/ncu_f_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"^(k_scan|k_emit_stream|k_umi_sets|k_umi_bitmap_counts)$" -s 10 -c 5 -f -o $o/top4_$tag $B > $o/ncu_f_$tag.log 2>&1
 ncu -i $o/top4_$tag.ncu-rep --page raw --csv > $o/top4_${tag}_raw.csv 2>/dev/null
 ncu -i $o/top4_$tag.ncu-rep --page source --print-source cuda,sass --csv > $o/top4_${tag}_src.csv 2>/dev/null
 ls -la $o/*$tag* | awk '{print $5, $9}'
