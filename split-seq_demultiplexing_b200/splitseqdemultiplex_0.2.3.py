@@ -46,6 +46,8 @@ def build_parser():
                    help='"fast" (merged output) or "split" (the same records as one file per cell, legacy naming)')
     p.add_argument('-c', '--collapseRandomHexamers', required=False, default='false',
                    help='"true": fold RanHex Round1 barcodes into their OligoDT partners (Collapse_RanHex_Odt.py); the reference\'s fast path ignores it')
+    p.add_argument('--useBarcodeFiles', action='store_true',
+                   help='extension: read the whitelist from the -1/-2/-3 files instead of Round*_barcodes_new*.txt in the CWD')
     p.add_argument('-t', '--targetMemory', required=False)
     p.add_argument('-g', '--granularity', required=False)
     return p
@@ -68,7 +70,8 @@ def main(argv=None):
     say("Starting Step1: demultiplexing on the GPU.")
     if rank == 0 and not os.path.exists(args.outputDir):
         os.makedirs(args.outputDir)                                            # CLI3:48-49
-    whitelist = hostlogic.load_whitelist(".")
+    whitelist = (hostlogic.load_whitelist_from(args.round1Barcodes, args.round2Barcodes, args.round3Barcodes) if args.useBarcodeFiles
+                 else hostlogic.load_whitelist("."))
     positions = dict(hostlogic.DEFAULT_POSITIONS)
     if args.positionDetection:                                                  # default True (CLI3:38, 63)
         say("Learning barcode positions to replace defaults...")

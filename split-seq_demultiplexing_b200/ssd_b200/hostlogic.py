@@ -28,6 +28,20 @@ def load_whitelist(directory: str = ".") -> List[str]:
     return wl
 
 
+def load_whitelist_from(round1: str, round2: str, round3: str) -> List[str]:
+    """Opt-in extension: take the whitelist from the files given with -1/-2/-3 instead of the fixed names in
+    the CWD.  Round 1 carries its 8-mer at [8:16] (V2:58), Rounds 2 and 3 at [0:8]; the fast path matches all three rounds
+    against ONE list (V2:302-304), so the three files must spell the same 8-mers in the same order, as the bundled ones do."""
+    with open(round1, "r") as fh:
+        wl = [line.rstrip()[8:16] for line in fh if line.strip()]
+    for path in (round2, round3):
+        with open(path, "r") as fh:
+            other = [line.rstrip()[0:8] for line in fh if line.strip()]
+        if other != wl:
+            raise ValueError("%s does not carry the 8-mers of %s: per-round whitelists are not supported by the fast path" % (path, round1))
+    return wl
+
+
 def load_round_names(directory: str = ".") -> Tuple[List[str], List[str], List[str]]:
     """The full-length barcodes of the three rounds (16-, 13- and 14-mers in the bundled files), line i of every file being
     entry i of the whitelist (Round 1 carries its 8-mer at [8:16], Rounds 2 and 3 at [0:8]).  The legacy pipeline names

@@ -219,3 +219,14 @@ def test_round_names_and_legacy_split_file_name(ssd, tmp_path):
     # demultiplex_using_barcodes.py:364: round1 + "-" + round2 + "-" + round3 + ".fastq"
     assert hostlogic.split_file_name(names, 0, 1, 2) == names[0][0] + "-" + names[1][1] + "-" + names[2][2] + ".fastq"
     assert (len(names[0][0]), len(names[1][0]), len(names[2][0])) == (16, 13, 14)
+
+
+def test_whitelist_from_the_given_files(ssd, tmp_path):
+    from ssd_b200 import hostlogic
+    fu.write_whitelist_files(str(tmp_path))
+    paths = [str(tmp_path / n) for n in (hostlogic.ROUND1_FILE, hostlogic.ROUND2_FILE, hostlogic.ROUND3_FILE)]
+    assert hostlogic.load_whitelist_from(*paths) == hostlogic.load_whitelist(str(tmp_path)) == WL
+    other = tmp_path / "r3_other.txt"
+    other.write_text("".join("ACGTACGTGTGGCC\n" for _ in WL))
+    with pytest.raises(ValueError, match="per-round"):
+        hostlogic.load_whitelist_from(paths[0], paths[1], str(other))
