@@ -461,7 +461,7 @@ int umi_set_counts(ssd_ctx* c, Src src, uint64_t n_src, uint64_t n_keys_bound, c
     if (!counts) {
         uint32_t* own = seg + nc + 1;
         CU(c, cudaMemsetAsync(own, 0, nc * sizeof(uint32_t), c->stream));
-        k_cell_key_counts<Src><<<blocks_for(n_src, kThreads), kThreads, 0, c->stream>>>(src, n_src, c->dcfg.umi_bits, own);
+        k_cell_key_counts<Src><<<(uint32_t)std::min<uint64_t>(blocks_for(n_src, kThreads), 148 * 8), kThreads, 0, c->stream>>>(src, n_src, c->dcfg.umi_bits, own);
         c->n_launches++;
         counts = own;
     }
