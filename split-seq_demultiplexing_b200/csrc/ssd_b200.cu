@@ -1559,12 +1559,14 @@ extern "C" int ssd_load_file_range(ssd_ctx* c, int slot, const char* path, uint6
 extern "C" int ssd_demux_loaded(ssd_ctx* c)
 {
     if (!c) return SSD_EINVAL;
+    if (!c->b_in1.p || !c->b_in2.p) return fail(c, SSD_ESTATE, "ssd_demux_loaded before ssd_load_file_range of both slots");
     return ssd_demux_device(c, c->b_in1.p, c->loaded[0], c->b_in2.p, c->loaded[1]);
 }
 
 extern "C" int ssd_annotated_loaded(ssd_ctx* c)
 {
     if (!c) return SSD_EINVAL;
+    if (!c->b_in1.p) return fail(c, SSD_ESTATE, "ssd_annotated_loaded before ssd_load_file_range of slot 0");
     return ssd_annotated_device(c, c->b_in1.p, c->loaded[0]);
 }
 
