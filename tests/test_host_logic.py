@@ -230,3 +230,20 @@ def test_whitelist_from_the_given_files(ssd, tmp_path):
     other.write_text("".join("ACGTACGTGTGGCC\n" for _ in WL))
     with pytest.raises(ValueError, match="per-round"):
         hostlogic.load_whitelist_from(paths[0], paths[1], str(other))
+
+
+def test_record_cuts_error_codes(ssd, tmp_path):
+    import ctypes as C
+    from ssd_b200 import _lib as L
+    lib = L.load()
+    p = tmp_path / "x.fastq"
+    p.write_bytes(b"@a\nAC\n+\nEE\n" * 1000)
+    rec, off = (C.c_uint64 * 4)(), (C.c_uint64 * 4)()
+    n, total = C.c_uint64(), C.c_uint64()
+    # more cuts than the arrays hold: SSD_ERANGE (the Python wrapper then retries with larger arrays)
+    assert lib.ssd_fastq_record_cuts(str(p).encode(), 100, None, 0, rec, off, 4, C.byref(n), C.byref(total)) == L.ERANGE
+    assert lib.ssd_fastq_record_cuts(str(tmp_path / "missing").encode(), 100, None, 0, rec, off, 4, C.byref(n), C.byref(total)) == L.EIO
+    assert lib.ssd_fastq_record_cuts(str(p).encode(), 0, None, 0, rec, off, 4, C.byref(n), C.byref(total)) == L.EINVAL
+    from ssd_b200 import filebatch
+    r, o, t = filebatch.record_cuts(str(p), target_bytes=100)          # grows its arrays until they fit
+    assert t == 1000 and len(r) > 4 and o[-1] == 11000
