@@ -1585,27 +1585,147 @@ extern "C" int ssd_emit_file(ssd_ctx* c, int which, const char* out_path, int ap
 //   records_in != NULL: the byte offsets at which the given records (ascending indices) start; an index past the end of
 //                       the file gives the file size.  This is how the mate file is cut at the same records.
 // n_out receives the number of entries written (at most cap; SSD_ERANGE when cap is too small).
+// The newlines of every 4 MiB block are counted once, on up to 16 host threads (pread + SWAR count); a cut is then located
+// through the prefix sums of the block counts and a walk inside one block.
+namespace {
+constexpr size_t kCutBlock = (size_t)4 << 20;
+
+inline uint64_t count_newlines(const uint8_t* p, size_t n)
+{
+    uint64_t k = 0;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t x;
+        memcpy(&x, p + i, 8);
+        x ^= 0x0A0A0A0A0A0A0A0Aull;
+        const uint64_t z = ~(((x & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | x | 0x7F7F7F7F7F7F7F7Full);  // 0x80 where the byte was '\n'
+        k += ((z >> 7) * 0x0101010101010101ull) >> 56;  // the eight 0/1 bytes summed into the top byte (no popcount instruction assumed)
+    }
+    for (; i < n; i++) k += p[i] == '\n';
+    return k;
+}
+
+bool pread_all(int fd, uint8_t* dst, size_t want, uint64_t off)
+{
+    size_t got = 0;
+    while (got < want) {
+        const ssize_t r = pread(fd, dst + got, want - got, (off_t)(off + got));
+        if (r < 0 && errno == EINTR) continue;
+        if (r <= 0) return false;
+        got += (size_t)r;
+    }
+    return true;
+}
+
+struct CutFile {
+    int fd = -1;
+    uint64_t size = 0, total = 0;       // bytes, newlines
+    std::vector<uint64_t> before;       // newlines before block b (n_blocks + 1 entries)
+    std::vector<uint8_t> blk;           // the block looked at last
+    uint64_t blk_index = ~0ull;
+    size_t blk_len = 0;
+    bool ok = true;
+
+    const uint8_t* block(uint64_t b)
+    {
+        if (b != blk_index) {
+            blk_len = (size_t)std::min<uint64_t>(kCutBlock, size - b * kCutBlock);
+            if (!pread_all(fd, blk.data(), blk_len, b * kCutBlock)) ok = false;
+            blk_index = b;
+        }
+        return blk.data();
+    }
+    // a cursor inside the current block, so that a run of cuts in one block costs one pass over it: cur_lines = newlines in [0, cur_off)
+    uint64_t cur_off = 0, cur_lines = 0;
+
+    // newlines in [0, off) and whether byte off - 1 is one (0 < off <= size)
+    uint64_t lines_before(uint64_t off, bool* ends_line)
+    {
+        const uint64_t b = (off - 1) / kCutBlock, lo = b * kCutBlock;
+        const uint8_t* p = block(b);
+        if (cur_off < lo || cur_off > off) {
+            cur_off = lo;
+            cur_lines = before[b];
+        }
+        cur_lines += count_newlines(p + (cur_off - lo), (size_t)(off - cur_off));
+        cur_off = off;
+        *ends_line = p[off - lo - 1] == '\n';
+        return cur_lines;
+    }
+    // the byte offset right after newline number g (1 <= g <= total)
+    uint64_t after_newline(uint64_t g)
+    {
+        const uint64_t b = (uint64_t)(std::lower_bound(before.begin(), before.end(), g) - before.begin()) - 1;  // before[b] < g <= before[b + 1]
+        const uint64_t lo = b * kCutBlock;
+        const uint8_t* p = block(b);
+        if (cur_off < lo || cur_off > lo + blk_len || cur_lines >= g) {
+            cur_off = lo;
+            cur_lines = before[b];
+        }
+        size_t i = (size_t)(cur_off - lo);
+        while (cur_lines < g) {
+            const uint8_t* q = (const uint8_t*)memchr(p + i, '\n', blk_len - i);
+            if (!q) {  // cannot happen: the block holds before[b + 1] - before[b] newlines
+                ok = false;
+                return size;
+            }
+            i = (size_t)(q - p) + 1;
+            cur_lines++;
+        }
+        cur_off = lo + i;
+        return cur_off;
+    }
+};
+}  // namespace
+
 extern "C" int ssd_fastq_record_cuts(const char* path, uint64_t target_bytes, const uint64_t* records_in, uint64_t n_in, uint64_t* records_out,
                                      uint64_t* offsets_out, uint64_t cap, uint64_t* n_out, uint64_t* n_records_total)
 {
     if (!path || !records_out || !offsets_out || !n_out || (!records_in && target_bytes == 0)) return SSD_EINVAL;
-    const int fd = open(path, O_RDONLY);
+    CutFile f;
+    f.fd = open(path, O_RDONLY);
     struct stat st;
-    if (fd < 0 || fstat(fd, &st) != 0) {
-        if (fd >= 0) close(fd);
+    if (f.fd < 0 || fstat(f.fd, &st) != 0) {
+        if (f.fd >= 0) close(f.fd);
         return SSD_EIO;
     }
-    const uint64_t size = (uint64_t)st.st_size;
-    constexpr size_t kBuf = (size_t)8 << 20, kSub = (size_t)64 << 10;
-    std::vector<uint8_t> buf(kBuf);
-    auto count_nl = [](const uint8_t* p, size_t n) {
-        uint64_t k = 0;
-        for (size_t i = 0; i < n; i++) k += p[i] == '\n';
-        return k;
-    };
-    uint64_t n = 0, lines = 0, pos = 0, last_cut = 0, next_in = 0;
+    f.size = (uint64_t)st.st_size;
+    const uint64_t n_blocks = (f.size + kCutBlock - 1) / kCutBlock;
+    f.before.assign(n_blocks + 1, 0);
+    f.blk.resize(kCutBlock);
+    // newlines per block, in parallel
+    {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const int n_threads = (int)std::min<uint64_t>(std::min<unsigned>(hw, 16u), std::max<uint64_t>(n_blocks, 1));
+        std::vector<std::thread> th;
+        std::vector<int> bad(n_threads, 0);
+        for (int t = 0; t < n_threads; t++)
+            th.emplace_back([&, t] {
+                std::vector<uint8_t> buf(kCutBlock);
+                for (uint64_t b = (uint64_t)t; b < n_blocks; b += (uint64_t)n_threads) {
+                    const size_t len = (size_t)std::min<uint64_t>(kCutBlock, f.size - b * kCutBlock);
+                    if (!pread_all(f.fd, buf.data(), len, b * kCutBlock)) {
+                        bad[t] = 1;
+                        return;
+                    }
+                    f.before[b + 1] = count_newlines(buf.data(), len);
+                }
+            });
+        for (auto& x : th) x.join();
+        for (int t = 0; t < n_threads; t++)
+            if (bad[t]) {
+                close(f.fd);
+                return SSD_EIO;
+            }
+    }
+    for (uint64_t b = 0; b < n_blocks; b++) f.before[b + 1] += f.before[b];
+    f.total = f.before[n_blocks];
+    bool last_is_newline = true;
+    if (f.size) f.lines_before(f.size, &last_is_newline);
+    const uint64_t n_lines = f.total + (f.size && !last_is_newline ? 1 : 0);
+
+    uint64_t n = 0;
     int rc = SSD_OK;
-    uint8_t last_byte = '\n';
     auto put = [&](uint64_t rec, uint64_t off) {
         if (n >= cap) {
             rc = SSD_ERANGE;
@@ -1615,86 +1735,38 @@ extern "C" int ssd_fastq_record_cuts(const char* path, uint64_t target_bytes, co
         offsets_out[n] = off;
         n++;
     };
-    if (!records_in) put(0, 0);
-    while (records_in && next_in < n_in && records_in[next_in] == 0) {
-        put(0, 0);
-        next_in++;
-    }
-    while (pos < size && rc == SSD_OK) {
-        const size_t want = (size_t)std::min<uint64_t>(kBuf, size - pos);
-        size_t got = 0;
-        while (got < want) {
-            const ssize_t r = pread(fd, buf.data() + got, want - got, (off_t)(pos + got));
-            if (r < 0 && errno == EINTR) continue;
-            if (r <= 0) {
-                close(fd);
-                return SSD_EIO;
-            }
-            got += (size_t)r;
-        }
-        last_byte = buf[want - 1];
-        for (size_t s0 = 0; s0 < want && rc == SSD_OK; s0 += kSub) {
-            const size_t sn = std::min(kSub, want - s0);
-            const uint8_t* b = buf.data() + s0;
-            const uint64_t sub_pos = pos + s0;
-            size_t i = 0;
-            while (i < sn && rc == SSD_OK) {
-                if (!records_in) {
-                    const uint64_t limit = last_cut + target_bytes;
-                    if (sub_pos + sn <= limit) {  // the whole rest of this piece lies before the next cut
-                        lines += count_nl(b + i, sn - i);
-                        break;
-                    }
-                    if (sub_pos + i < limit) {
-                        const size_t k = (size_t)(limit - sub_pos - i);
-                        lines += count_nl(b + i, k);
-                        i += k;
-                    }
-                    const uint8_t* q = (const uint8_t*)memchr(b + i, '\n', sn - i);
-                    if (!q) break;
-                    i = (size_t)(q - b) + 1;
-                    lines++;
-                    if ((lines & 3u) == 0 && sub_pos + i < size) {
-                        put(lines >> 2, sub_pos + i);
-                        last_cut = sub_pos + i;
-                    }
-                } else {
-                    if (next_in >= n_in) {
-                        lines += count_nl(b + i, sn - i);
-                        break;
-                    }
-                    const uint64_t goal = 4 * records_in[next_in];  // the record starts after newline number `goal`
-                    const uint64_t here = count_nl(b + i, sn - i);
-                    if (lines + here < goal) {
-                        lines += here;
-                        break;
-                    }
-                    while (lines < goal) {
-                        const uint8_t* q = (const uint8_t*)memchr(b + i, '\n', sn - i);
-                        i = (size_t)(q - b) + 1;
-                        lines++;
-                    }
-                    put(records_in[next_in], sub_pos + i);
-                    next_in++;
-                    while (next_in < n_in && rc == SSD_OK && records_in[next_in] == records_in[next_in - 1]) {
-                        put(records_in[next_in], sub_pos + i);
-                        next_in++;
-                    }
-                }
-            }
-        }
-        pos += want;
-    }
-    close(fd);
-    const uint64_t n_lines = lines + (size && last_byte != '\n' ? 1 : 0);
     if (!records_in) {
-        if (rc == SSD_OK) put(n_lines >> 2, size);
+        put(0, 0);
+        uint64_t last_cut = 0;
+        while (rc == SSD_OK && f.ok) {
+            const uint64_t limit = last_cut + target_bytes;
+            if (limit >= f.size || limit < last_cut) break;
+            bool at_line_end = false;
+            const uint64_t before = f.lines_before(limit, &at_line_end);
+            uint64_t cut, g;
+            if (before && (before & 3u) == 0 && at_line_end) {  // a record starts exactly at the limit
+                g = before;
+                cut = limit;
+            } else {
+                g = (before / 4 + 1) * 4;
+                if (g > f.total) break;
+                cut = f.after_newline(g);
+            }
+            if (cut >= f.size) break;
+            put(g >> 2, cut);
+            last_cut = cut;
+        }
+        if (rc == SSD_OK) put(n_lines >> 2, f.size);
     } else {
-        while (next_in < n_in && rc == SSD_OK) put(records_in[next_in++], size);
+        for (uint64_t k = 0; k < n_in && rc == SSD_OK && f.ok; k++) {
+            const uint64_t r = records_in[k];
+            put(r, r == 0 ? 0 : (r > f.total / 4 ? f.size : f.after_newline(4 * r)));
+        }
     }
+    close(f.fd);
     *n_out = n;
     if (n_records_total) *n_records_total = n_lines >> 2;
-    return rc;
+    return f.ok ? rc : SSD_EIO;
 }
 
 extern "C" int ssd_annotated_host(ssd_ctx* c, const void* text, size_t len, void* out, size_t out_cap, size_t* written, ssd_stats* stats)
