@@ -726,22 +726,52 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         const uint8_t* s_win = S.win[ws];
         uint32_t* s_mask = S.mask;
         uint16_t* s_lstart = S.lstart[ls];
-        build_nl_mask<kAThreads, (kWinWords * 2 + kAThreads - 1) / kAThreads>(s_win, win_bytes, reinterpret_cast<uint16_t*>(s_mask), kWinWords * 2);
-        sync_a();
-        PROF_T(t2);
-        PROF_ADD(1, t1, t2);
         // newlines owned by this tile: mask words [0, kTileWords), WPT consecutive ones per thread; halo words: 1 per thread of warps 0-1
         constexpr int WPT = kTileWords / kAThreads;  // mask words (32 bytes each) per thread
         static_assert(WPT >= 1 && WPT <= 8 && WPT * kAThreads == kTileWords, "tile size");
         static_assert(kHaloWords <= 64 && kAThreads >= 64, "halo size");
         uint32_t mw[WPT];
         uint32_t cnt = 0;
+#ifdef SSD_SCAN_REGMASK
+        // experiment (unmeasured): every thread builds its own mask words from the two 16-byte chunks each
+        // covers, so the bitmap never goes through shared memory (no 16-bit stores, no re-read, one barrier less); the price is
+        // a 2-way bank conflict of the 96-byte-strided 16-byte loads
+        const uint4* w4 = reinterpret_cast<const uint4*>(s_win);
+        const uint32_t nfull = win_bytes >> 4;
+        auto chunk_mask = [&](uint32_t c) -> uint32_t {
+            if (c > nfull || (c == nfull && !(win_bytes & 15u))) return 0u;
+            const uint4 v = w4[c];
+            const uint32_t lo = __dp4a(nl_flags(v.x), 0x08040201u, __dp4a(nl_flags(v.y), 0x80402010u, 0u));
+            const uint32_t hi = __dp4a(nl_flags(v.z), 0x08040201u, __dp4a(nl_flags(v.w), 0x80402010u, 0u));
+            const uint32_t m = (lo >> 7) | ((hi >> 7) << 8);
+            return c == nfull ? m & ((1u << (win_bytes & 15u)) - 1u) : m;  // the chunk the data ends in
+        };
+#pragma unroll
+        for (int w = 0; w < WPT; w++) {
+            const uint32_t c0 = 2u * (uint32_t)(WPT * tid + w);
+            mw[w] = chunk_mask(c0) | (chunk_mask(c0 + 1u) << 16);
+            cnt += (uint32_t)__popc(mw[w]);
+        }
+        uint32_t hm = 0;
+        if (tid < kHaloWords) {
+            const uint32_t c0 = 2u * (uint32_t)(kTileWords + tid);
+            hm = chunk_mask(c0) | (chunk_mask(c0 + 1u) << 16);
+        }
+        (void)s_mask;
+        PROF_T(t2);
+        PROF_ADD(1, t1, t2);
+#else
+        build_nl_mask<kAThreads, (kWinWords * 2 + kAThreads - 1) / kAThreads>(s_win, win_bytes, reinterpret_cast<uint16_t*>(s_mask), kWinWords * 2);
+        sync_a();
+        PROF_T(t2);
+        PROF_ADD(1, t1, t2);
 #pragma unroll
         for (int w = 0; w < WPT; w++) {
             mw[w] = s_mask[WPT * tid + w];
             cnt += (uint32_t)__popc(mw[w]);
         }
         const uint32_t hm = tid < kHaloWords ? s_mask[kTileWords + tid] : 0u;
+#endif
         // both prefix sums in one: a warp's tile count (<= 32 x 32 WPT bits) in the low half, its halo count in the high half
         static_assert(32 * 32 * WPT < 65536, "packed scan");
         uint32_t both = cnt | ((uint32_t)__popc(hm) << 16);
