@@ -142,6 +142,10 @@ int ssd_load_file_range(ssd_ctx *ctx, int slot, const char *path, uint64_t offse
 int ssd_demux_loaded(ssd_ctx *ctx);
 int ssd_annotated_loaded(ssd_ctx *ctx);
 int ssd_emit_file(ssd_ctx *ctx, int which, const char *out_path, int append, size_t *written);
+/* Host only: *plain = 1 when every line of the file already equals Python's line.strip() + "\n" (ASCII, no '\r', no blank
+ * next to a newline or at the start, final newline present), i.e. when the reference's splitter (LIB:36, 83) would copy the
+ * file's bytes unchanged; *n_lines = its number of lines. */
+int ssd_fastq_lines_are_stripped(const char *path, int *plain, uint64_t *n_lines);
 int ssd_fastq_record_cuts(const char *path, uint64_t target_bytes, const uint64_t *records_in, uint64_t n_in,
                           uint64_t *records_out, uint64_t *offsets_out, uint64_t capacity, uint64_t *n_out,
                           uint64_t *n_records_total);

@@ -1769,6 +1769,86 @@ extern "C" int ssd_fastq_record_cuts(const char* path, uint64_t target_bytes, co
     return f.ok ? rc : SSD_EIO;
 }
 
+// Host only: is every line of the file already what Python's line.strip() + "\n" would make of it?  That is the case when
+// the file is ASCII, has no '\r' (text mode would translate it), no blank (str.isspace) next to a '\n' or at the very
+// start, and ends with '\n' (or is empty).  The reference's splitter copies line.strip() + "\n" (LIB:36, 83); for such a
+// file that is a plain copy of byte ranges.  *plain = 1 / 0; *n_lines = number of lines.
+extern "C" int ssd_fastq_lines_are_stripped(const char* path, int* plain, uint64_t* n_lines)
+{
+    if (!path || !plain) return SSD_EINVAL;
+    const int fd = open(path, O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) {
+        if (fd >= 0) close(fd);
+        return SSD_EIO;
+    }
+    const uint64_t size = (uint64_t)st.st_size;
+    const uint64_t n_blocks = (size + kCutBlock - 1) / kCutBlock;
+    uint8_t blank[256];
+    for (int b = 0; b < 256; b++) blank[b] = (b == ' ' || (b >= 9 && b <= 13 && b != '\n') || (b >= 0x1c && b <= 0x1f)) ? 1 : 0;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int n_threads = (int)std::min<uint64_t>(std::min<unsigned>(hw, 16u), std::max<uint64_t>(n_blocks, 1));
+    std::vector<int> verdict(n_threads, 1);  // 1 plain so far, 0 not plain, -1 read error
+    std::vector<uint64_t> lines(n_threads, 0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++)
+        th.emplace_back([&, t] {
+            std::vector<uint8_t> buf(kCutBlock + 2);
+            for (uint64_t b = (uint64_t)t; b < n_blocks && verdict[t] == 1; b += (uint64_t)n_threads) {
+                // the block with one byte of context on either side (0 stands for "outside the file")
+                const uint64_t lo = b * kCutBlock, len = std::min<uint64_t>(kCutBlock, size - lo);
+                const uint64_t from = lo ? lo - 1 : 0, to = std::min<uint64_t>(size, lo + len + 1);
+                uint8_t* p = buf.data() + (lo ? 0 : 1);
+                buf[0] = 0;
+                if (!pread_all(fd, p, (size_t)(to - from), from)) {
+                    verdict[t] = -1;
+                    return;
+                }
+                uint8_t* q = buf.data() + 1;  // q[i] = byte lo + i, q[-1] / q[len] = the neighbours
+                if (to == lo + len) q[len] = 0;
+                bool ok = true;
+                uint64_t nl = 0, i = 0;
+                auto one = [&](uint64_t k) {
+                    const uint8_t c = q[k];
+                    if (c >= 0x80 || c == '\r') ok = false;
+                    if (c == '\n') {
+                        nl++;
+                        if (blank[q[k - 1]] || blank[q[k + 1]]) ok = false;
+                    }
+                };
+                for (; i + 8 <= len; i += 8) {  // eight bytes at a time; only words that hold a newline are looked at bytewise
+                    uint64_t x;
+                    memcpy(&x, q + i, 8);
+                    const uint64_t cr = x ^ 0x0D0D0D0D0D0D0D0Dull, lf = x ^ 0x0A0A0A0A0A0A0A0Aull;
+                    if ((x & 0x8080808080808080ull) || ((cr - 0x0101010101010101ull) & ~cr & 0x8080808080808080ull)) ok = false;
+                    if ((lf - 0x0101010101010101ull) & ~lf & 0x8080808080808080ull)
+                        for (uint64_t k = i; k < i + 8; k++) one(k);
+                }
+                for (; i < len; i++) one(i);
+                lines[t] += nl;
+                if (!ok) verdict[t] = 0;
+            }
+        });
+    for (auto& x : th) x.join();
+    int v = 1;
+    uint64_t total = 0;
+    for (int t = 0; t < n_threads; t++) {
+        if (verdict[t] < 0) v = -1;
+        else if (verdict[t] == 0 && v == 1) v = 0;
+        total += lines[t];
+    }
+    if (v == 1 && size) {
+        uint8_t first = 0, last = 0;
+        if (!pread_all(fd, &first, 1, 0) || !pread_all(fd, &last, 1, size - 1)) v = -1;
+        else if (blank[first] || last != '\n') v = 0;
+    }
+    close(fd);
+    if (v < 0) return SSD_EIO;
+    *plain = v;
+    if (n_lines) *n_lines = total;  // exact when plain (every line ends with its newline)
+    return SSD_OK;
+}
+
 extern "C" int ssd_annotated_host(ssd_ctx* c, const void* text, size_t len, void* out, size_t out_cap, size_t* written, ssd_stats* stats)
 {
     if (!c) return SSD_EINVAL;

@@ -98,6 +98,7 @@ _SIGS = {
     "ssd_demux_loaded": (C.c_int, [C.c_void_p]),
     "ssd_annotated_loaded": (C.c_int, [C.c_void_p]),
     "ssd_emit_file": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_size_t)]),
+    "ssd_fastq_lines_are_stripped": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "ssd_fastq_record_cuts": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                         C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ssd_key_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

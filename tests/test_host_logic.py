@@ -247,3 +247,65 @@ def test_record_cuts_error_codes(ssd, tmp_path):
     from ssd_b200 import filebatch
     r, o, t = filebatch.record_cuts(str(p), target_bytes=100)          # grows its arrays until they fit
     assert t == 1000 and len(r) > 4 and o[-1] == 11000
+
+
+def _split_both_ways(lib, monkeypatch, tmp_path, data: bytes, n: int, length: int):
+    """split_fastqF_fun through the byte-range path (when it applies) and line by line: (chunk files, took the fast path)."""
+    import glob
+    out = []
+    for slow in (False, True):
+        d = tmp_path / ("slow" if slow else "fast")
+        d.mkdir(exist_ok=True)
+        monkeypatch.chdir(d)
+        for f in glob.glob("split_fastq_F_*"):
+            os.remove(f)
+        open("in.fastq", "wb").write(data)
+        if slow:
+            monkeypatch.setenv("SSD_SPLIT_LINE_BY_LINE", "1")
+        else:
+            monkeypatch.delenv("SSD_SPLIT_LINE_BY_LINE", raising=False)
+        lib.split_fastqF_fun(n, "in.fastq", length)
+        out.append({f: open(f, "rb").read() for f in sorted(glob.glob("split_fastq_F_*"))})
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 3, 8])
+def test_split_by_byte_ranges_equals_line_by_line(ssd, tmp_path, monkeypatch, n):
+    import ctypes as C
+    import importlib
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    lib = importlib.import_module("Splitseq_fun_lib")
+    L = importlib.import_module("ssd_b200._lib")
+    from ssd_b200 import hostlogic
+    r1, _ = fu.load_bundled()
+    rec = b"@a 1/1\nACGT\n+\nEEEE\n"
+    cases = {
+        "bundled": (r1, 20000, 1),
+        "tiny (fewer chunks than asked for)": (rec * 10, 40, 1),
+        "partial last record": (rec * 9 + b"@b\nAC\n", 38, 1),
+        "crlf": (rec.replace(b"\n", b"\r\n") * 12, 48, 0),
+        "trailing blank": (rec * 5 + b"@c 1/1 \nACGT\n+\nEEEE\n" + rec * 6, 48, 0),
+        "leading tab": (rec * 5 + b"@c\n\tACGT\n+\nEEEE\n" + rec * 6, 48, 0),
+        "no final newline": (rec * 12 + b"@d\nAC\n+\nEE", 52, 0),
+        "non-ascii": (rec * 6 + "@é\nAC\n+\nEE\n".encode() + rec * 5, 48, 0),
+        "blank lines": (rec * 3 + b"\n\n\n\n" + rec * 8, 48, 1),
+        "empty": (b"", 0, 1),
+    }
+    for name, (data, length, plain) in cases.items():
+        p = tmp_path / "probe.fastq"
+        p.write_bytes(data)
+        got, nl = C.c_int(-1), C.c_uint64(0)
+        assert L.load().ssd_fastq_lines_are_stripped(str(p).encode(), C.byref(got), C.byref(nl)) == 0
+        assert got.value == plain, name
+        if plain:
+            assert nl.value == data.count(b"\n"), name
+        if length:
+            took = []
+            real = lib._split_by_ranges
+            monkeypatch.setattr(lib, "_split_by_ranges", lambda *a: took.append(real(*a)) or took[-1])
+            fast, slow = _split_both_ways(lib, monkeypatch, tmp_path, data, n, length)
+            monkeypatch.setattr(lib, "_split_by_ranges", real)
+            assert fast == slow, name
+            assert took == [bool(plain)], name                             # the byte-range path ran exactly when the file allows it
+            assert len(slow) == min(n, -(-data.count(b"\n") // hostlogic.tuned_split_size(length, n))) or not plain, name
