@@ -13,6 +13,7 @@ Outputs (all committed):
   rule_cases.json.gz       SURVEY.md Appendix B: small hand-built inputs with the reference's outputs / exception
   adversarial.json.gz      seeded adversarial sets (tests/fastq_util.make_pairs) with the reference's canonical outputs
   learner_cases.json       position-learner known answers (V2:164-199)
+  splitter_cases.json      chunk files of the reference's splitter (LIB:6-110): names, sizes, SHA-256
 """
 import contextlib
 import gzip
@@ -276,6 +277,54 @@ def make_learner_cases(wl):
     print("learner:", cases)
 
 
+def splitter_inputs():
+    """Inputs of the splitter cases: (name, bytes, lengthFastq).  Shared with the tests."""
+    r1, _ = fu.load_bundled()
+    rec = b"@a 1/1\nACGT\n+\nEEEE\n"
+    return [
+        ("bundled", r1, 20000),
+        ("tiny", rec * 10, 40),
+        ("partial_last_record", rec * 9 + b"@b\nAC\n", 38),
+        ("crlf", rec.replace(b"\n", b"\r\n") * 12, 48),
+        ("trailing_blank", rec * 5 + b"@c 1/1 \nACGT\n+\nEEEE\n" + rec * 6, 48),
+        ("leading_tab", rec * 5 + b"@c\n\tACGT\n+\nEEEE\n" + rec * 6, 48),
+        ("no_final_newline", rec * 12 + b"@d\nAC\n+\nEE", 52),
+        ("blank_lines", rec * 3 + b"\n\n\n\n" + rec * 8, 48),
+    ]
+
+
+def make_splitter_cases():
+    """The reference's Splitseq_fun_lib.split_fastqF_fun / split_fastqR_fun (LIB:6-110), run unmodified: names, sizes and
+    SHA-256 of the chunk files (and of the position-learner sample) for several inputs and core counts."""
+    if REF_TOOL not in sys.path:
+        sys.path.insert(0, REF_TOOL)
+    lib = importlib.import_module("Splitseq_fun_lib")
+    cases = []
+    cwd = os.getcwd()
+    for name, data, length in splitter_inputs():
+        for n in (1, 3, 4, 8):
+            for fn, prefix in (("split_fastqF_fun", "split_fastq_F"), ("split_fastqR_fun", "split_fastq_R")):
+                tmp = tempfile.mkdtemp(prefix="ssdgold_")
+                try:
+                    os.chdir(tmp)
+                    with open("in.fastq", "wb") as fh:
+                        fh.write(data)
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        getattr(lib, fn)(n, "in.fastq", length)
+                    files = sorted(f for f in os.listdir(".") if f.startswith(prefix))
+                    rec = {"input": name, "n": n, "fn": fn, "length": length,
+                           "files": {f: [os.path.getsize(f), hashlib.sha256(open(f, "rb").read()).hexdigest()] for f in files}}
+                    if os.path.exists("position_learner_fastqr.fastq"):
+                        rec["learner_sha"] = hashlib.sha256(open("position_learner_fastqr.fastq", "rb").read()).hexdigest()
+                    cases.append(rec)
+                finally:
+                    os.chdir(cwd)
+                    shutil.rmtree(tmp, ignore_errors=True)
+    with open(os.path.join(HERE, "splitter_cases.json"), "w") as fh:
+        json.dump(cases, fh, indent=1, sort_keys=True)
+    print("splitter cases:", len(cases))
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF_TOOL):
         sys.exit("the reference is not mounted; golden vectors can only be regenerated in the authoring container")
@@ -284,3 +333,4 @@ if __name__ == "__main__":
     make_rule_cases(wl)
     make_adversarial(wl)
     make_learner_cases(wl)
+    make_splitter_cases()

@@ -309,3 +309,44 @@ def test_split_by_byte_ranges_equals_line_by_line(ssd, tmp_path, monkeypatch, n)
             assert fast == slow, name
             assert took == [bool(plain)], name                             # the byte-range path ran exactly when the file allows it
             assert len(slow) == min(n, -(-data.count(b"\n") // hostlogic.tuned_split_size(length, n))) or not plain, name
+
+
+def _splitter_cases():
+    with open(os.path.join(fu.GOLDEN_DIR, "splitter_cases.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("line_by_line", [False, True], ids=["byte-ranges-when-possible", "line-by-line"])
+def test_splitter_matches_the_reference_golden(ssd, tmp_path, monkeypatch, line_by_line):
+    """The chunk files (names, sizes, SHA-256) and the learner sample of the UNMODIFIED reference's splitter (LIB:6-110,
+    tests/golden/make_golden.py::make_splitter_cases) for 8 inputs x 4 core counts x both functions, through the drop-in
+    module with and without its byte-range path."""
+    import contextlib
+    import hashlib
+    import importlib
+    import io
+    sys.path.insert(0, os.path.join(fu.GOLDEN_DIR))
+    inputs = {name: (data, length) for name, data, length in importlib.import_module("make_golden").splitter_inputs()}
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    lib = importlib.import_module("Splitseq_fun_lib")
+    if line_by_line:
+        monkeypatch.setenv("SSD_SPLIT_LINE_BY_LINE", "1")
+    else:
+        monkeypatch.delenv("SSD_SPLIT_LINE_BY_LINE", raising=False)
+    cases = _splitter_cases()
+    assert len(cases) == 64
+    for k, case in enumerate(cases):
+        d = tmp_path / ("c%d" % k)
+        d.mkdir()
+        monkeypatch.chdir(d)
+        data, length = inputs[case["input"]]
+        assert length == case["length"]
+        open("in.fastq", "wb").write(data)
+        with contextlib.redirect_stdout(io.StringIO()):
+            getattr(lib, case["fn"])(case["n"], "in.fastq", length)
+        prefix = "split_fastq_F" if case["fn"] == "split_fastqF_fun" else "split_fastq_R"
+        got = {f: [os.path.getsize(f), hashlib.sha256(open(f, "rb").read()).hexdigest()] for f in sorted(os.listdir(".")) if f.startswith(prefix)}
+        assert got == case["files"], (case["input"], case["n"], case["fn"])
+        if "learner_sha" in case:
+            assert hashlib.sha256(open("position_learner_fastqr.fastq", "rb").read()).hexdigest() == case["learner_sha"]
