@@ -13,6 +13,7 @@ Outputs (all committed):
   rule_cases.json.gz       SURVEY.md Appendix B: small hand-built inputs with the reference's outputs / exception
   adversarial.json.gz      seeded adversarial sets (tests/fastq_util.make_pairs) with the reference's canonical outputs
   learner_cases.json       position-learner known answers (V2:164-199)
+  collapse_cases.json      which per-cell files Collapse_RanHex_Odt.py folds into which, for seeded random cell sets
   splitter_cases.json      chunk files of the reference's splitter (LIB:6-110): names, sizes, SHA-256
 """
 import contextlib
@@ -325,6 +326,54 @@ def make_splitter_cases():
     print("splitter cases:", len(cases))
 
 
+def make_collapse_cases():
+    """Collapse_RanHex_Odt.py (the reference's script, run unmodified in a scratch directory next to copies of its RanHex.txt /
+    OligoDT.txt): per-cell files named round1-round2-round3.fastq (demultiplex_using_barcodes.py:364) for seeded random
+    cell sets, each file holding its own name; afterwards the surviving files and their contents say which RanHex cell was
+    folded into which OligoDT cell.  Cells are stored as index triples into the Round files (line i = whitelist entry i)."""
+    import random
+    import subprocess
+    rounds = []
+    for name in ("Round1_barcodes_new5.txt", "Round2_barcodes_new4.txt", "Round3_barcodes_new4.txt"):
+        with open(os.path.join(REF, name)) as fh:
+            rounds.append([l.strip() for l in fh if l.strip()])
+    index = [{b: i for i, b in enumerate(r)} for r in rounds]
+    cases = []
+    for seed, n_cells, p_pair in ((1, 40, 0.5), (2, 400, 0.3), (3, 1500, 0.1), (4, 5, 1.0), (5, 300, 0.0)):
+        rng = random.Random(seed)
+        cells = set()
+        while len(cells) < n_cells:
+            i1, i2, i3 = rng.randrange(96), rng.randrange(96), rng.randrange(96)
+            cells.add((i1, i2, i3))
+            if rng.random() < p_pair:                       # plant the partner well: RanHex k + 48 <-> OligoDT k
+                cells.add(((i1 + 48) % 96, i2, i3))
+        tmp = tempfile.mkdtemp(prefix="ssdgold_")
+        try:
+            os.makedirs(os.path.join(tmp, "results"))
+            for f in ("RanHex.txt", "OligoDT.txt"):
+                shutil.copy(os.path.join(REF, f), os.path.join(tmp, f))
+            for i1, i2, i3 in cells:
+                name = rounds[0][i1] + "-" + rounds[1][i2] + "-" + rounds[2][i3] + ".fastq"
+                with open(os.path.join(tmp, "results", name), "w") as fh:
+                    fh.write(name + "\n")
+            subprocess.run([sys.executable, os.path.join(REF, "Collapse_RanHex_Odt.py")], cwd=tmp, check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            merges = []
+            survivors = sorted(os.listdir(os.path.join(tmp, "results")))
+            for f in survivors:
+                lines = open(os.path.join(tmp, "results", f)).read().split()
+                assert lines[0] == f
+                for other in lines[1:]:
+                    a, b = other[:-6].split("-"), f[:-6].split("-")
+                    merges.append([[index[k][a[k]] for k in range(3)], [index[k][b[k]] for k in range(3)]])
+            cases.append({"seed": seed, "cells": sorted(list(c) for c in cells), "merges": sorted(merges), "n_files_after": len(survivors)})
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    with open(os.path.join(HERE, "collapse_cases.json"), "w") as fh:
+        json.dump(cases, fh, sort_keys=True)
+    print("collapse cases:", [(c["seed"], len(c["cells"]), len(c["merges"])) for c in cases])
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF_TOOL):
         sys.exit("the reference is not mounted; golden vectors can only be regenerated in the authoring container")
@@ -334,3 +383,4 @@ if __name__ == "__main__":
     make_adversarial(wl)
     make_learner_cases(wl)
     make_splitter_cases()
+    make_collapse_cases()

@@ -150,3 +150,24 @@ def test_collapse_rule():
     assert remap[cid(49, 5, 6)] == cid(49, 5, 6)
     assert remap[cid(0, 5, 6)] == cid(0, 5, 6)
     assert sum(1 for i, r in enumerate(remap) if r != i) == 1
+
+
+def test_collapse_rule_matches_the_reference_script():
+    """Collapse_RanHex_Odt.py run unmodified on per-cell files of seeded random cell sets (tests/golden/make_golden.py::
+    make_collapse_cases): the oracle's remap table folds exactly the cells the script folded, into the same partners."""
+    import json
+    import os
+    with open(os.path.join(fu.GOLDEN_DIR, "collapse_cases.json")) as fh:
+        cases = json.load(fh)
+    n, pairs = 96, 48
+    cid = lambda t: (t[0] * n + t[1]) * n + t[2]  # noqa: E731
+    assert sum(len(c["merges"]) for c in cases) > 200
+    for c in cases:
+        present = bytearray(n * n * n)
+        for cell in c["cells"]:
+            present[cid(cell)] = 1
+        remap = orc.collapse_map(bytes(present), n, pairs)
+        want = {cid(src): cid(dst) for src, dst in c["merges"]}
+        got = {i: int(r) for i, r in enumerate(remap) if r != i and present[i]}
+        assert got == want, c["seed"]
+        assert c["n_files_after"] == len(c["cells"]) - len(want)
