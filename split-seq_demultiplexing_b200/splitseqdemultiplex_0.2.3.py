@@ -48,6 +48,8 @@ def build_parser():
                    help='"true": fold RanHex Round1 barcodes into their OligoDT partners (Collapse_RanHex_Odt.py); the reference\'s fast path ignores it')
     p.add_argument('--useBarcodeFiles', action='store_true',
                    help='extension: read the whitelist from the -1/-2/-3 files instead of Round*_barcodes_new*.txt in the CWD')
+    p.add_argument('--cellTable', required=False,
+                   help='extension: also write cell / reads / distinct UMIs / passing as tab-separated text to this path (one GPU)')
     p.add_argument('-t', '--targetMemory', required=False)
     p.add_argument('-g', '--granularity', required=False)
     return p
@@ -107,6 +109,8 @@ def main(argv=None):
                 os.remove(out_path)
         else:
             _, stats = dm.run_files(args.fastqF, args.fastqR, out_path, ssd_b200.EMIT_PASSING, append=True)  # V2:415 (append mode)
+        if args.cellTable and world == 1:
+            dm.write_cell_table(args.cellTable)  # the global tables are still in place after the (last) batch
     finally:
         dm.close()
     if wanted:

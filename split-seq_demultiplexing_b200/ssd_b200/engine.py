@@ -72,6 +72,7 @@ class Demultiplexer:
         cfg.collapse_pairs = int(collapse_pairs)
         cfg.record_bytes_hint = int(record_bytes_hint)
         self.filter_mode = filter_mode
+        self.min_count = int(min_count)
         self._ctx = C.c_void_p()
         rc = self.lib.ssd_create(C.byref(cfg), C.byref(self._ctx))
         if rc != L.OK:
@@ -324,6 +325,15 @@ class Demultiplexer:
         if n.value:
             self._check(self.lib.ssd_emit_host(self._ctx, L.EMIT_PASSING, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)))
         return out[: n.value], st.as_dict()
+
+    def write_cell_table(self, path: str) -> int:
+        """The per-cell (reads, distinct UMIs) table of the last run as tab-separated text (hostlogic.format_cell_table);
+        returns the number of cells."""
+        from . import hostlogic
+        table = self.cell_table()
+        with open(path, "w") as fh:
+            fh.write(hostlogic.format_cell_table(table, self.min_count))
+        return len(table)
 
     def cell_table(self) -> Dict[str, Tuple[int, int]]:
         """{cell string: (reads, distinct UMIs)} for every detected cell (small outputs / tests)."""

@@ -113,3 +113,14 @@ def summary_lines(n_cells: int, threshold, n_passing: int) -> List[str]:
     """V2:458-459, verbatim."""
     return ["The total number of unique barcodes detected was " + str(n_cells),
             "The number of barcodes passing the minimum UMI threshold of " + str(threshold) + " was " + str(n_passing)]
+
+
+def format_cell_table(table: Dict[str, Tuple[int, int]], threshold: int) -> str:
+    """Per-cell summary as tab-separated text (the counts without a FASTQ round trip): one line per detected
+    cell, in whitelist-independent (lexicographic) order of the 24-base cell id -- cell, reads, distinct UMIs, and whether
+    the cell passes the -m threshold on distinct UMIs (V2:411)."""
+    lines = ["cell\treads\tdistinct_umis\tpassing\n"]
+    for cell in sorted(table):
+        reads, distinct = table[cell]
+        lines.append("%s\t%d\t%d\t%d\n" % (cell, reads, distinct, 1 if distinct >= int(threshold) else 0))
+    return "".join(lines)

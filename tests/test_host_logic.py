@@ -350,3 +350,12 @@ def test_splitter_matches_the_reference_golden(ssd, tmp_path, monkeypatch, line_
         assert got == case["files"], (case["input"], case["n"], case["fn"])
         if "learner_sha" in case:
             assert hashlib.sha256(open("position_learner_fastqr.fastq", "rb").read()).hexdigest() == case["learner_sha"]
+
+
+def test_format_cell_table(ssd):
+    from ssd_b200 import hostlogic
+    a, b = WL[1] + WL[2] + WL[3], WL[0] + WL[0] + WL[95]
+    text = hostlogic.format_cell_table({a: (12, 10), b: (9, 9)}, "10")
+    rows = text.split("\n")
+    assert rows[0] == "cell\treads\tdistinct_umis\tpassing" and rows[-1] == ""
+    assert rows[1:3] == sorted(["%s\t12\t10\t1" % a, "%s\t9\t9\t0" % b])
