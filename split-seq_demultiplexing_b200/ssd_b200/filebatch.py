@@ -133,6 +133,18 @@ def filter_annotated_file_batched(dm, path_in: str, out_path: str, append: bool 
     return written[0], total
 
 
+def plan_shards(path_r1: str, path_r2: str, world: int, target_bytes: Optional[int] = None):
+    """What rank 0 decides for run_files_sharded: the pair of files cut into batches of whole records (at most SSD_BATCH_BYTES
+    of read 1 each, and small enough that there are about `world` of them when the files allow), dealt to the ranks as
+    contiguous runs in file order.  Returns one list of (offset 1, length 1, offset 2, length 2) per rank (possibly empty)."""
+    from .distributed import shard_record_ranges
+    target = target_bytes
+    if target is None:
+        target = max(1, min(batch_bytes(), -(-os.path.getsize(path_r1) // world)))
+    batches = pair_batches(path_r1, path_r2, target)
+    return [batches[lo:hi] for lo, hi in shard_record_ranges(len(batches), world)]
+
+
 def run_files_sharded(dm, path_r1: str, path_r2: str, out_path: str, which: int = L.EMIT_PASSING, append: bool = True,
                       world: int = 1, group=None, target_bytes: Optional[int] = None):
     """One pair of files, N ranks (one process per GPU, torch.distributed initialised): the reference's fan-out over chunk
@@ -144,18 +156,14 @@ def run_files_sharded(dm, path_r1: str, path_r2: str, out_path: str, which: int 
     the per-rank sums added up); call it on every rank."""
     import torch
     import torch.distributed as dist
-    from .distributed import shard_record_ranges, two_pass
+    from .distributed import two_pass
     if world <= 1:
         return run_files_batched(dm, path_r1, path_r2, out_path, which, append, target_bytes)
     rank = dist.get_rank(group)
     box = [None]
     if rank == 0:
         try:
-            target = target_bytes
-            if target is None:
-                target = max(1, min(batch_bytes(), -(-os.path.getsize(path_r1) // world)))
-            batches = pair_batches(path_r1, path_r2, target)
-            box[0] = [batches[lo:hi] for lo, hi in shard_record_ranges(len(batches), world)]
+            box[0] = plan_shards(path_r1, path_r2, world, target_bytes)
             _truncate(out_path, append)
         except OSError as e:  # every rank raises what rank 0 met
             box[0] = e

@@ -359,3 +359,28 @@ def test_format_cell_table(ssd):
     rows = text.split("\n")
     assert rows[0] == "cell\treads\tdistinct_umis\tpassing" and rows[-1] == ""
     assert rows[1:3] == sorted(["%s\t12\t10\t1" % a, "%s\t9\t9\t0" % b])
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_plan_shards_deals_contiguous_runs_of_whole_records(ssd, tmp_path, monkeypatch, world):
+    from ssd_b200 import filebatch
+    r1, r2 = fu.load_bundled()
+    p1, p2 = tmp_path / "a.fastq", tmp_path / "b.fastq"
+    p1.write_bytes(r1)
+    p2.write_bytes(r2)
+    for batch_bytes in (10**9, 60000):
+        monkeypatch.setenv("SSD_BATCH_BYTES", str(batch_bytes))
+        plan = filebatch.plan_shards(str(p1), str(p2), world)
+        assert len(plan) == world
+        flat = [b for per_rank in plan for b in per_rank]
+        assert flat[0][0] == 0 and flat[0][2] == 0
+        assert all(a[0] + a[1] == b[0] and a[2] + a[3] == b[2] for a, b in zip(flat, flat[1:]))      # file order, no gaps
+        assert flat[-1][0] + flat[-1][1] == len(r1) and flat[-1][2] + flat[-1][3] == len(r2)
+        assert all(n1 <= max(batch_bytes, 400) + 400 for _, n1, _, _ in flat)                         # the cut target holds (+ one record)
+        for o1, n1, o2, n2 in flat:
+            assert r1[o1:o1 + n1].count(b"\n") == r2[o2:o2 + n2].count(b"\n") and r1[o1:o1 + n1].count(b"\n") % 4 == 0
+        sizes = [len(per_rank) for per_rank in plan]
+        assert max(sizes) - min(s for s in sizes if s or world > len(flat)) <= max(sizes)              # runs, not a deal of single batches
+        assert sizes == sorted(sizes, reverse=True) and (len(flat) < world or min(sizes) >= 1 or sum(sizes) == len(flat))
+        if batch_bytes == 10**9 and world > 1:
+            assert len(flat) >= min(world, 2)                                                          # cut into about one batch per rank
