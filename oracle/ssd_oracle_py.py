@@ -35,8 +35,15 @@ class _Out(C.Structure):
                 ("error", C.c_int), ("error_msg", C.c_char * 256)]
 
 
+class _SynthSpec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("first_index", C.c_uint64), ("n_pairs", C.c_uint64), ("read_len", C.c_int32),
+                ("n_whitelist", C.c_int32), ("whitelist", C.c_char_p), ("cell_pool", C.c_uint32), ("p_sub_ppm", C.c_uint32),
+                ("p_n_ppm", C.c_uint32), ("p_junk_ppm", C.c_uint32), ("p_dup_umi_ppm", C.c_uint32), ("p_tie_ppm", C.c_uint32),
+                ("p_trunc_ppm", C.c_uint32), ("p_atqual_ppm", C.c_uint32)]
+
+
 def build(force: bool = False) -> str:
-    src = [os.path.join(HERE, "ssd_oracle.c"), os.path.join(HERE, "ssd_oracle.h")]
+    src = [os.path.join(HERE, "ssd_oracle.c"), os.path.join(HERE, "ssd_oracle.h"), os.path.join(HERE, "ssd_synth_ref.c")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
         subprocess.check_call(["make", "-C", HERE, "-B", "libssd_oracle.so"], stdout=subprocess.DEVNULL)
     return LIB_PATH
@@ -58,6 +65,8 @@ def lib():
         _lib.ssd_oracle_collapse_map.restype = None
         _lib.ssd_oracle_free.argtypes = [C.POINTER(_Out)]
         _lib.ssd_oracle_free.restype = None
+        _lib.ssd_oracle_synth_sizes.argtypes = [C.POINTER(_SynthSpec), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        _lib.ssd_oracle_synth_generate.argtypes = [C.POINTER(_SynthSpec), C.c_void_p, C.c_void_p, C.c_int]
     return _lib
 
 
@@ -154,3 +163,23 @@ def collapse_map(present: bytes, n: int, n_pairs: int) -> List[int]:
     remap = (C.c_uint32 * (n * n * n))()
     lib().ssd_oracle_collapse_map(present, n, n_pairs, remap)
     return list(remap)
+
+
+def synth_pairs(whitelist: List[str], n_pairs: int, seed: int = 0x5EED0001, first_index: int = 1, read_len: int = 150,
+                cell_pool: int = 100000, p_sub: float = 0.01, p_n: float = 0.002, p_junk: float = 0.10, p_dup_umi: float = 0.05,
+                p_tie: float = 0.0, p_trunc: float = 0.0, p_atqual: float = 0.02, n_threads: Optional[int] = None):
+    """The synthetic read pairs of SURVEY 8d (same arguments and same bytes as ssd_b200.synth_spec + synth_host / synth_device)
+    made by oracle/ssd_synth_ref.c, without the product library.  Returns two numpy uint8 arrays (read 1, read 2)."""
+    import numpy as np
+    raw = b"".join(w.encode()[:8] for w in whitelist)
+    ppm = lambda p: int(round(p * 1e6))  # noqa: E731
+    spec = _SynthSpec(seed, first_index, n_pairs, read_len, len(whitelist), raw, cell_pool, ppm(p_sub), ppm(p_n), ppm(p_junk),
+                      ppm(p_dup_umi), ppm(p_tie), ppm(p_trunc), ppm(p_atqual))
+    a, b = C.c_uint64(), C.c_uint64()
+    if lib().ssd_oracle_synth_sizes(C.byref(spec), C.byref(a), C.byref(b)) != 0:
+        raise ValueError("bad synthetic spec")
+    r1, r2 = np.empty(a.value, dtype=np.uint8), np.empty(b.value, dtype=np.uint8)
+    if lib().ssd_oracle_synth_generate(C.byref(spec), r1.ctypes.data_as(C.c_void_p), r2.ctypes.data_as(C.c_void_p),
+                                       n_threads or os.cpu_count() or 1) != 0:
+        raise ValueError("bad synthetic spec")
+    return r1, r2

@@ -13,7 +13,12 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("SSD_B200_LIB") or os.path.join(CSRC, "libssd_b200.so")  # override: A/B builds while tuning
-SOURCES = ["ssd_b200.cu", "ssd_kernels.cuh", "ssd_device.cuh", "ssd_synth.cuh"]
+
+def sources():
+    """Everything the library is compiled from: every .cu / .cuh under csrc/ (ssd_kernels.cuh includes them all)."""
+    import glob
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")))
+
 HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "ssd_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -54,7 +59,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [HEADER]
+    deps = sources() + [HEADER]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 

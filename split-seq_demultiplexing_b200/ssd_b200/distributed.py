@@ -110,11 +110,25 @@ def exchange_owned(keys, key_counts, irr, group=None):
     return rk, everything
 
 
+def _adopt_torch_stream(dm):
+    """Point the library context at torch's current CUDA stream (no-op for the CPU stand-ins of the gloo tests), so that the
+    library's kernels and torch's collectives are ordered against each other.  Torch reports the legacy default stream as
+    handle 0, which ssd_set_stream reads as "the context's own stream"; CUDA's explicit handle for it is cudaStreamLegacy (1)."""
+    import torch
+    if not hasattr(dm, "set_stream") or not torch.cuda.is_available():
+        return
+    handle = torch.cuda.current_stream().cuda_stream
+    dm.set_stream(handle if handle != 0 else 1)
+
+
 def global_filter(dm, world: int, group=None) -> dict:
     """After dm.demux_device(...) on every rank: make the -m decision global and exact, return dm's stats.
     Collectives: all-reduce of the read histogram, all-to-all of the unique keys, all-reduce of the distinct table."""
     import torch.distributed as dist
     if world > 1:
+        # torch's collectives are ordered on torch's current stream only: the library must enqueue on that very stream, or it
+        # reads what NCCL has not delivered yet (and NCCL sends tables the kernels have not finished).  Idempotent.
+        _adopt_torch_stream(dm)
         pending = dist.all_reduce(dm.reads_histogram(), group=group, async_op=True)  # overlaps the key exchange
         if dm.filter_mode == "distinct_umi":
             import torch
@@ -145,6 +159,8 @@ def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None, 
     sync = torch.cuda.synchronize if dev.type == "cuda" else (lambda: None)
     trim = torch.cuda.empty_cache if dev.type == "cuda" else (lambda: None)
     hist, kept_k, kept_i = None, [], []
+    if world > 1 and dev.type == "cuda":
+        _adopt_torch_stream(dm)
     t_start = time.perf_counter()
     for batch in phase1():
         h = dm.reads_histogram()
@@ -161,7 +177,11 @@ def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None, 
         dm._keep = []  # the batch may go before the next one is produced (two of them need not fit)
         del batch
     if distinct_mode and world > 1:
-        for _ in range(len(kept_k), rounds or 0):  # this rank has fewer batches than another: empty rounds
+        if rounds is None:  # every rank goes through as many exchange rounds as the rank with the most batches
+            r = torch.tensor([len(kept_k)], dtype=torch.int64, device=dev)
+            dist.all_reduce(r, op=dist.ReduceOp.MAX, group=group)
+            rounds = int(r.item())
+        for _ in range(len(kept_k), rounds):  # this rank has fewer batches than another: empty rounds
             k, i = exchange_owned(torch.empty(0, dtype=torch.int64, device=dev), [0] * world,
                                   torch.empty((0, 2), dtype=torch.int64, device=dev), group=group)
             kept_k.append(k.clone())
@@ -252,3 +272,15 @@ def shard_record_ranges(n_records: int, world: int) -> List[Tuple[int, int]]:
     """Contiguous record ranges per rank (the reference cuts line-aligned chunks the same way, LIB:6-97)."""
     per = (n_records + world - 1) // world
     return [(min(k * per, n_records), min((k + 1) * per, n_records)) for k in range(world)]
+
+
+def deal_evenly(n_items: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous runs of n_items over `world` ranks whose lengths differ by at most one (the first n % world ranks get the
+    extra item): no rank idles while another holds two more batches than it."""
+    base, extra = divmod(n_items, world)
+    out, lo = [], 0
+    for k in range(world):
+        hi = lo + base + (1 if k < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out

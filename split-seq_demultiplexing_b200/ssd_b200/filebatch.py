@@ -94,12 +94,15 @@ def run_files_batched(dm, path_r1: str, path_r2: str, out_path: str, which: int 
             yield None
 
     if which == L.EMIT_MATCHED:  # no decision across batches: one pass
+        # (V2.demultiplex_fun never looks at -m: only the output sizes are needed, so the per-batch filter is built from the
+        # read histogram alone and the per-cell counts, which are per batch here, are not reported)
         total = {}
         for _ in phase1():
-            st = dm.filter_single()
+            st = dm.build_filter()
             written[0] += _emit_file(dm, which, out_path)
             for key, v in st.items():
-                total[key] = total.get(key, 0) + v
+                if key not in ("n_cells", "n_passing_cells", "n_retained", "bytes_passing"):
+                    total[key] = total.get(key, 0) + v
         return written[0], total
 
     def emit(_, st):
@@ -137,12 +140,15 @@ def plan_shards(path_r1: str, path_r2: str, world: int, target_bytes: Optional[i
     """What rank 0 decides for run_files_sharded: the pair of files cut into batches of whole records (at most SSD_BATCH_BYTES
     of read 1 each, and small enough that there are about `world` of them when the files allow), dealt to the ranks as
     contiguous runs in file order.  Returns one list of (offset 1, length 1, offset 2, length 2) per rank (possibly empty)."""
-    from .distributed import shard_record_ranges
+    from .distributed import deal_evenly
     target = target_bytes
     if target is None:
-        target = max(1, min(batch_bytes(), -(-os.path.getsize(path_r1) // world)))
+        # as many batches as a multiple of `world` allows under the per-batch limit, all about the same size
+        size = max(1, os.path.getsize(path_r1))
+        per_rank = -(-size // (world * batch_bytes()))  # batches every rank gets
+        target = max(1, -(-size // (world * per_rank)))
     batches = pair_batches(path_r1, path_r2, target)
-    return [batches[lo:hi] for lo, hi in shard_record_ranges(len(batches), world)]
+    return [batches[lo:hi] for lo, hi in deal_evenly(len(batches), world)]
 
 
 def run_files_sharded(dm, path_r1: str, path_r2: str, out_path: str, which: int = L.EMIT_PASSING, append: bool = True,

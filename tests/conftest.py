@@ -9,3 +9,23 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "split-seq_demul
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _cuda_devices():
+    try:
+        import torch
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests are skipped (not failed) on a host without a usable CUDA device, so a plain `pytest tests` gives a
+    meaningful signal everywhere; the product itself still fails loudly there (ssd_create has no CPU fallback)."""
+    import pytest
+    if _cuda_devices() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

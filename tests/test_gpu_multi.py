@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir, filter_mode):
+def _worker(rank, world, port, out_dir, filter_mode, own_stream=True):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -30,9 +30,11 @@ def _worker(rank, world, port, out_dir, filter_mode):
     import ssd_b200
     from ssd_b200.distributed import global_filter
     dm = ssd_b200.Demultiplexer(WL, errors=1, min_count=10, device=rank, filter_mode=filter_mode)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    dm.set_stream(stream.cuda_stream)
+    if own_stream:
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        dm.set_stream(stream.cuda_stream)
+    # else: a default user -- torch on its default stream, the context on its own; global_filter has to order the two itself
     spec = ssd_b200.synth_spec(WL, N_PER_RANK, seed=77, first_index=1 + rank * N_PER_RANK, cell_pool=3000, p_n=0.01, p_dup_umi=0.3)
     d1, d2 = ssd_b200.synth_device(dm, spec)
     dm.demux_device(d1.data_ptr(), d1.numel(), d2.data_ptr(), d2.numel(), keep=(d1, d2))
@@ -45,8 +47,8 @@ def _worker(rank, world, port, out_dir, filter_mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("filter_mode", ["distinct_umi", "reads"])
-def test_two_ranks_equal_one(tmp_path, filter_mode):
+@pytest.mark.parametrize("filter_mode,own_stream", [("distinct_umi", True), ("reads", True), ("distinct_umi", False)])
+def test_two_ranks_equal_one(tmp_path, filter_mode, own_stream):
     import numpy as np
     import torch
     import torch.multiprocessing as mp
@@ -54,7 +56,7 @@ def test_two_ranks_equal_one(tmp_path, filter_mode):
         pytest.skip("needs two GPUs")
     import ssd_b200
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), filter_mode), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), filter_mode, own_stream), nprocs=world, join=True)
     parts = [np.load(os.path.join(str(tmp_path), "out_%d.npy" % r)).tobytes() for r in range(world)]
     st = [np.load(os.path.join(str(tmp_path), "stats_%d.npy" % r)) for r in range(world)]
     # single GPU on the concatenated input

@@ -488,6 +488,57 @@ def test_full_size_properties(ssd, n, e, m, spec_kw, dm_kw, split):
     torch.cuda.empty_cache()
 
 
+FULL_SIZE_ORACLE = [
+    # BASELINE.json configs[1], the bench workload itself: 10 M pairs, seed 0x5EED0001, e=1, -m 10
+    pytest.param(10_000_000, 1, 1, 10, dict(seed=0x5EED0001), id="config2-10M-e1"),
+    # configs[2]'s shape (e=2, N bases, planted 2/2 ties, truncated read 2): a 10 M slice from the middle of the 100 M set
+    pytest.param(10_000_000, 45_000_001, 2, 10, dict(seed=0x5EED0002, cell_pool=1_000_000, p_n=0.01, p_tie=0.01, p_trunc=0.005),
+                 id="config3-slice-10M-e2"),
+]
+
+
+@pytest.mark.parametrize("n,first,e,m,spec_kw", FULL_SIZE_ORACLE)
+def test_full_size_against_oracle(ssd, orc, n, first, e, m, spec_kw):
+    """SURVEY 8c "full at 10 M": the bench workload (and a 10 M slice of config 3) bit for bit against the oracle -- CLI3's
+    structure (split, one demultiplex_fun per chunk on every host core, calc_demux_results) on the bytes the device
+    generated: both outputs, the statistics and the whole per-cell (reads, distinct UMIs) table."""
+    import gc
+    import torch
+    gc.collect()
+    torch.cuda.empty_cache()
+    dm = ssd.Demultiplexer(WL, errors=e, min_count=m, record_bytes_hint=160)
+    d1, d2 = ssd.synth_device(dm, ssd.synth_spec(WL, n, first_index=first, **spec_kw))
+    out, stats = dm.run_device(d1, d2, ssd.EMIT_PASSING)
+    torch.cuda.synchronize()
+    r1, r2 = d1.cpu().numpy(), d2.cpu().numpy()
+    g1, g2 = orc.synth_pairs(WL, n, first_index=first, **spec_kw)  # the oracle-side generator makes the same bytes
+    assert r1.size == g1.size and r2.size == g2.size and bool((r1 == g1).all()) and bool((r2 == g2).all())
+    del g1, g2
+    ref = orc.run_cli(r1.tobytes(), r2.tobytes(), WL, e, m, n_workers=os.cpu_count() or 1, length_fastq=4 * n)
+    assert (stats["n_records_r1"], stats["n_matched"], stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]) == (
+        n, ref.n_matched, ref.n_cells, ref.n_passing_cells, ref.n_retained)
+    got = out.cpu().numpy().tobytes()
+    assert len(got) == len(ref.passing) == stats["bytes_passing"]
+    assert hashlib.sha256(got).hexdigest() == hashlib.sha256(ref.passing).hexdigest()
+    del got
+    merged = torch.empty(stats["bytes_matched"] + 16, dtype=torch.uint8, device="cuda")
+    k = dm.emit_device(ssd.EMIT_MATCHED, merged.data_ptr(), merged.numel())
+    assert k == len(ref.merged1)
+    assert hashlib.sha256(merged[:k].cpu().numpy().tobytes()).hexdigest() == hashlib.sha256(ref.merged1).hexdigest()
+    hist, distinct = dm.reads_histogram().cpu().numpy(), dm.distinct_histogram().cpu().numpy()
+    idx = {w: i for i, w in enumerate(WL)}
+    nw = len(WL)
+    want_h, want_d = np.zeros_like(hist), np.zeros_like(distinct)
+    for c, v in ref.cells.items():
+        s = c.decode()
+        cid = (idx[s[0:8]] * nw + idx[s[8:16]]) * nw + idx[s[16:24]]
+        want_h[cid], want_d[cid] = v[0], v[1]
+    assert bool((hist == want_h).all()) and bool((distinct == want_d).all())
+    dm.close()
+    del d1, d2, out, merged
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("filter_mode", ["distinct_umi", "reads"])
 def test_batches_equal_one_call(ssd, orc, filter_mode):
     """Inputs cut into batches (two passes: global tables first, then the writer) give the bytes of one call on the whole

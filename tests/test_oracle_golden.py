@@ -171,3 +171,21 @@ def test_collapse_rule_matches_the_reference_script():
         got = {i: int(r) for i, r in enumerate(remap) if r != i and present[i]}
         assert got == want, c["seed"]
         assert c["n_files_after"] == len(c["cells"]) - len(want)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(seed=0x5EED0001),
+    dict(seed=0x5EED0002, cell_pool=3000, p_n=0.01, p_tie=0.01, p_trunc=0.005, first_index=999_990),
+    dict(seed=3, read_len=94, p_atqual=0.5, p_dup_umi=0.5, p_junk=0.3),
+], ids=["config2", "config3-shape", "short-reads"])
+def test_oracle_generator_equals_the_products_host_twin(kw):
+    """oracle/ssd_synth_ref.c (what bench.py's reference arm generates its workload with, so that it never loads the product
+    library) against ssd_synth_generate_host: the same bytes for the same spec."""
+    import ssd_b200
+    from oracle import ssd_oracle_py as orc
+    wl = fu.load_whitelist()
+    h1, h2 = ssd_b200.synth_host(ssd_b200.synth_spec(wl, 6000, **kw))
+    a, b = orc.synth_pairs(wl, 6000, **kw)
+    assert a.tobytes() == h1 and b.tobytes() == h2
+    a1, b1 = orc.synth_pairs(wl, 6000, n_threads=1, **kw)
+    assert a1.tobytes() == h1 and b1.tobytes() == h2
