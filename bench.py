@@ -269,7 +269,7 @@ def main():
         h2 = torch.empty(d2.numel(), dtype=torch.uint8, pin_memory=True)
         h1.copy_(d1)
         h2.copy_(d2)
-        hout = torch.empty(int(last["bytes_passing"]) + 4096, dtype=torch.uint8, pin_memory=True)
+        hout = torch.empty(int(last["written"]) + 4096, dtype=torch.uint8, pin_memory=True)
         a1, a2, aout = h1.numpy(), h2.numpy(), hout.numpy()
     if e2e_steps <= 0:
         pass
@@ -349,7 +349,7 @@ def main():
 
     # ---- roofline of the dominant kernel (algorithmic bytes = bytes read once + bytes written once) ----
     peak, peak_src = measured_peak()
-    in1, in2, outb = d1.numel(), d2.numel(), int(last["bytes_passing"])
+    in1, in2, outb = d1.numel(), d2.numel(), int(last["written"])
     kept_frac = last["n_retained"] / max(1, last["n_records_r1"])
     algo = {"scan_r1": in1, "scan_r2": in2, "emit": int(kept_frac * in1) + outb}
     per_kernel = {}

@@ -95,12 +95,15 @@ struct ssd_ctx {
     const uint8_t* r2 = nullptr;
     size_t r1_len = 0, r2_len = 0;
     bool wide = false;  // 64-bit record offsets
-    uint64_t rec_cap = 0;
+    uint64_t rec_cap = 0, rec_cap_r1 = 0;  // capacity of the per-record arrays of phase 1 / of the read-1 tables
     uint64_t n_rec_r1 = 0, n_rec_r2 = 0, n_rec = 0, n_keys = 0, n_irr = 0;
     bool defer1 = true, defer2 = true;  // scan variant per file: park-and-commit, or (after a failed guess) wait for the line index
     uint32_t emit_grid = 148;
     uint64_t n_respec = 0;  // scans repeated without guessing (diagnostics)
     bool phase1_done = false, filter_done = false, unique_done = false;
+    bool r1_tables = false;  // the per-record tables of read 1 exist (split mode, table-driven writers, annotated input): made on demand
+    bool sized[2] = {false, false};  // stats.bytes_matched / bytes_passing are exact (else upper bounds): the text has been written once
+    uint32_t fused_grid = 148;
     int planned = -1;  // which output b_out_off currently describes (-1 = none)
     bool annotated = false;  // the batch is an already annotated FASTQ (V2.calc_demux_results)
     uint64_t n_buckets = 0;  // split mode: buckets of the last ssd_emit_split_device
@@ -111,7 +114,7 @@ struct ssd_ctx {
     uint64_t n_uniq_irr = 0;
     ssd_stats stats{};
 
-    DevBuf b_status1, b_status2, b_r1_start, b_r1_meta, b_r1_base, b_r1_tok, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
+    DevBuf b_status1, b_status2, b_status3, b_r1_start, b_r1_meta, b_r1_base, b_r2_tok, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
         b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
     DevBuf b_in1, b_in2, b_out;
     size_t loaded[2] = {0, 0};  // bytes ssd_load_file_range put into b_in1 / b_in2
@@ -541,7 +544,7 @@ int distinct_counts_local(ssd_ctx* c)
 }
 
 template <typename OffT>
-int launch_scans(ssd_ctx* c, bool defer1, bool defer2)
+ScanArgs<OffT> scan_args(ssd_ctx* c)
 {
     ScanArgs<OffT> a{};
     a.cnt = c->d_cnt;
@@ -550,47 +553,66 @@ int launch_scans(ssd_ctx* c, bool defer1, bool defer2)
     a.r1_start = (OffT*)c->b_r1_start.p;
     a.r1_meta = (uint4*)c->b_r1_meta.p;
     a.r1_base = (uint32_t*)c->b_r1_base.p;
-    a.r1_tok = (unsigned long long*)c->b_r1_tok.p;
+    a.r2_tok = (unsigned long long*)c->b_r2_tok.p;
     a.r1buf = c->r1;
     a.r1_len = c->r1_len;
     a.ann = (uint64_t*)c->b_ann.p;
     a.hist = c->d_hist;
     a.irr = (IrrKey*)c->b_irr.p;
     a.lut = c->d_lut;
+    return a;
+}
 
-    const uint32_t nt1 = blocks_for(c->r1_len, kTile), nt2 = c->annotated ? 0u : blocks_for(c->r2_len, kTile);
+// phase 1: the read-2 scan (or, for an annotated batch, the scan of the annotated text)
+template <typename OffT>
+int launch_scan_phase1(ssd_ctx* c, bool defer)
+{
+    ScanArgs<OffT> a = scan_args<OffT>(c);
     if (c->annotated) {
+        const uint32_t nt1 = blocks_for(c->r1_len, kTile);
         if (nt1) {
             a.buf = c->r1;
             a.len = c->r1_len;
             a.status = (unsigned long long*)c->b_status1.p;
             a.n_tiles = nt1;
             StageTimer t(c, 0);
-            if (defer1) k_scan<kScanAnn, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+            if (defer) k_scan<kScanAnn, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
             else k_scan<kScanAnn, OffT, false><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
             c->n_launches++;
         }
         CU(c, cudaGetLastError());
         return SSD_OK;
     }
-    if (nt1) {
-        a.buf = c->r1;
-        a.len = c->r1_len;
-        a.status = (unsigned long long*)c->b_status1.p;
-        a.n_tiles = nt1;
-        StageTimer t(c, 0);
-        if (defer1) k_scan<kScanR1, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
-        else k_scan<kScanR1, OffT, false><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
-        c->n_launches++;
-    }
+    const uint32_t nt2 = blocks_for(c->r2_len, kTile);
     if (nt2) {
         a.buf = c->r2;
         a.len = c->r2_len;
         a.status = (unsigned long long*)c->b_status2.p;
         a.n_tiles = nt2;
         StageTimer t(c, 1);
-        if (defer2) k_scan<kScanR2, OffT, true><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        if (defer) k_scan<kScanR2, OffT, true><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         else k_scan<kScanR2, OffT, false><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        c->n_launches++;
+    }
+    CU(c, cudaGetLastError());
+    return SSD_OK;
+}
+
+// the read-1 scan that leaves per-record tables (split mode, table-driven writers); read 2 has been scanned
+template <typename OffT>
+int launch_scan_r1(ssd_ctx* c, bool defer)
+{
+    ScanArgs<OffT> a = scan_args<OffT>(c);
+    a.rec_cap = c->rec_cap_r1;
+    const uint32_t nt1 = blocks_for(c->r1_len, kTile);
+    if (nt1) {
+        a.buf = c->r1;
+        a.len = c->r1_len;
+        a.status = (unsigned long long*)c->b_status1.p;
+        a.n_tiles = nt1;
+        StageTimer t(c, 0);
+        if (defer) k_scan<kScanR1, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        else k_scan<kScanR1, OffT, false><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         c->n_launches++;
     }
     CU(c, cudaGetLastError());
@@ -802,14 +824,17 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
         CUB_(cudaFuncSetAttribute(k_emit_tiled<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
         CUB_(cudaFuncSetAttribute(k_emit_stream<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
         CUB_(cudaFuncSetAttribute(k_emit_stream<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
+        CUB_(cudaFuncSetAttribute(k_fused_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
         int per_sm = 0;
+        CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_r1, kFThreads, sizeof(FusedSmem)));
+        c->fused_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
         CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_stream<uint32_t>, kStreamThreads, sizeof(StreamSmem)));
         c->emit_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
         CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<kScanR2, uint32_t, true>, kScanThreads, sizeof(ScanSmem)));
         c->scan_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
     }
     CUB_(cudaMalloc(&c->d_cnt, sizeof(DevCounters)));
-    CUB_(cudaMalloc(&c->d_err_off, 2 * sizeof(unsigned long long)));
+    CUB_(cudaMalloc(&c->d_err_off, 4 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_lut, (size_t)(d.e + 1) * 65536u));
     CUB_(cudaMalloc(&c->d_wl_len, kMaxWl));
     CUB_(cudaMalloc(&c->d_wl64, kMaxWl * 8));
@@ -835,7 +860,7 @@ extern "C" void ssd_destroy(ssd_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_r1_start, &c->b_r1_meta, &c->b_r1_base, &c->b_r1_tok, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
+    DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_status3, &c->b_r1_start, &c->b_r1_meta, &c->b_r1_base, &c->b_r2_tok, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
                       &c->b_irr_alt, &c->b_perm, &c->b_perm_alt, &c->b_tmp64a, &c->b_tmp64b, &c->b_counts, &c->b_offsets, &c->b_bsums,
                       &c->b_pos, &c->b_out_off, &c->b_cells, &c->b_in1, &c->b_in2, &c->b_out, &c->b_sp_cells, &c->b_sp_cells_alt, &c->b_sp_recs,
                       &c->b_sp_recs_alt, &c->b_sp_off, &c->b_bk_cell, &c->b_bk_off, &c->b_bk_first, &c->b_os, &c->b_irr_table, &c->b_seg};
@@ -873,6 +898,83 @@ extern "C" int ssd_set_stream(ssd_ctx* c, void* cuda_stream)
 // ================================================================================================
 namespace {
 
+// Read-2 id of record r (the KeyError argument of V2:350): the read-2 scan left the inclusive newline prefix of every
+// tile in b_status2, so the tile holding newline number 4r is found on the host and only that tile is fetched.
+std::string r2_token_of_record(ssd_ctx* c, uint64_t r)
+{
+    const uint32_t nt2 = blocks_for(c->r2_len, kTile);
+    if (!nt2 || !c->b_status2.p) return "?";
+    size_t start = 0;
+    if (r > 0) {
+        std::vector<unsigned long long> st(nt2);
+        if (cudaMemcpy(st.data(), c->b_status2.p, (size_t)nt2 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return "?";
+        const unsigned long long want = 4ull * r;  // the record starts right after this newline (1-based count)
+        uint32_t lo = 0, hi = nt2 - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) / 2;
+            if ((st[mid] & kStatusValue) >= want) hi = mid;
+            else lo = mid + 1;
+        }
+        const unsigned long long before = lo ? (st[lo - 1] & kStatusValue) : 0ull;
+        const size_t t_lo = (size_t)lo * kTile, t_len = std::min<size_t>(kTile, c->r2_len - t_lo);
+        std::vector<uint8_t> bytes(t_len);
+        if (cudaMemcpy(bytes.data(), c->r2 + t_lo, t_len, cudaMemcpyDeviceToHost) != cudaSuccess) return "?";
+        unsigned long long seen = before;
+        size_t i = 0;
+        for (; i < t_len && seen < want; i++)
+            if (bytes[i] == '\n') seen++;
+        if (seen < want) return "?";
+        start = t_lo + i;
+    }
+    return token_at(c, c->r2, c->r2_len, start);
+}
+
+// What the kernels flagged, as the error the reference raises for it (V2:350 KeyError, V2:397-398 IndexError, ...).
+int report_errors(ssd_ctx* c, uint32_t flags)
+{
+    if (!(flags & (kErrNoAt | kErrKey | kErrDense | kErrIndex | kErrForeign))) return SSD_OK;
+    unsigned long long off[4];
+    CU(c, cudaMemcpy(off, c->d_err_off, sizeof off, cudaMemcpyDeviceToHost));
+    if (flags & kErrDense) return fail(c, SSD_EMALFORMED, "FASTQ records shorter than 32 bytes on average are not supported");
+    if (flags & kErrIndex) return fail(c, SSD_EINDEX, "list index out of range");
+    if (flags & kErrForeign)
+        return fail(c, SSD_EINVAL, "record at byte %llu: the cell/UMI fields of its header are not made of this whitelist's barcodes", off[0]);
+    if (flags & kErrNoAt) {
+        int f = off[0] != ~0ull ? 0 : 1;
+        return fail(c, SSD_EMALFORMED, "read %d: record at byte %llu does not start with '@'", f + 1, off[f]);
+    }
+    std::string tok = r2_token_of_record(c, off[2]);
+    return fail(c, SSD_EKEY, "%s", tok.c_str());
+}
+
+// Read 1 ended after n_rec_r1 records: a matched read-2 record beyond that has no mate (V2:349-350).
+int check_unmated_tail(ssd_ctx* c)
+{
+    if (c->annotated || c->n_rec_r2 <= c->n_rec_r1) return SSD_OK;
+    CU(c, cudaMemsetAsync(c->d_err_off, 0xFF, 4 * sizeof(unsigned long long), c->stream));
+    k_first_matched_from<<<148, kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, c->n_rec_r1, c->n_rec_r2, c->d_err_off + 2);
+    c->n_launches++;
+    unsigned long long first = ~0ull;
+    CU(c, cudaMemcpyAsync(&first, c->d_err_off + 2, sizeof first, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (first == ~0ull) return SSD_OK;
+    std::string tok = r2_token_of_record(c, first);
+    return fail(c, SSD_EKEY, "%s", tok.c_str());
+}
+
+// Resets what a pass over read 1 reports: its line / record counts, the error state, its tile ticket, the emitted sizes.
+__global__ void k_reset_r1_pass(DevCounters* cnt, unsigned long long* err_off)
+{
+    cnt->n_lines[0] = 0;
+    cnt->n_records[0] = 0;
+    cnt->err_flags = 0;
+    cnt->ticket[0] = 0;
+    cnt->ticket_fused = 0;
+    cnt->emit_bytes = 0;
+    cnt->emit_records = 0;
+    for (int k = 0; k < 4; k++) err_off[k] = ~0ull;
+}
+
 int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, size_t r2_len, bool annotated)
 {
     if ((r1_len && !d_r1) || (r2_len && !d_r2)) return fail(c, SSD_EINVAL, "null input pointer");
@@ -884,39 +986,47 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
     c->r2_len = r2_len;
     c->annotated = annotated;
     c->wide = std::max(r1_len, r2_len) >= (1ull << 32) || getenv("SSD_FORCE_WIDE") != nullptr;
-    c->phase1_done = c->filter_done = c->unique_done = false;
+    c->phase1_done = c->filter_done = c->unique_done = c->r1_tables = false;
+    c->sized[0] = c->sized[1] = false;
     c->planned = -1;
     if (std::max(r1_len, r2_len) >= (1ull << 36)) return fail(c, SSD_EINVAL, "a batch is limited to 64 GiB per file");
 
-    const uint32_t nt1 = blocks_for(r1_len, kTile), nt2 = blocks_for(r2_len, kTile);
-    uint64_t cap = std::max(r1_len, r2_len) / (uint64_t)c->record_hint + 1024;
+    // Phase 1 is the scan of READ 2 alone (barcodes, UMIs, histogram, id fingerprints): read 1 is not touched before the
+    // writer's single pass over it (ssd_fused.cuh) or, for split mode, the table-building scan (ensure_r1_tables).
+    // An annotated batch is one file: its scan leaves the per-record tables its writer needs.
+    const size_t scan_len = annotated ? r1_len : r2_len;
+    const uint32_t nt = blocks_for(scan_len, kTile);
+    DevBuf& status = annotated ? c->b_status1 : c->b_status2;
+    uint64_t cap = scan_len / (uint64_t)c->record_hint + 1024;
     DevCounters h{};
-    // the scans park their per-record results until the record numbers arrive and guess the record phase of each tile meanwhile;
+    // the scan parks its per-record results until the record numbers arrive and guesses the record phase of each tile meanwhile;
     // a wrong guess (lines that look like record starts where none is) repeats the scan with the variant that waits instead
     // (records so short that a tile holds more of them than stage B parks at once count as a wrong guess).  The choice is
     // remembered per file for the next batches of this context.
     if (getenv("SSD_SCAN_NODEFER")) c->defer1 = c->defer2 = false;
+    bool& defer = annotated ? c->defer1 : c->defer2;
     for (int attempt = 0, overflows = 0; attempt < 5; attempt++) {
         c->rec_cap = cap;
-        OKR(ensure(c, c->b_status1, (size_t)(nt1 + 1) * 8));
-        OKR(ensure(c, c->b_status2, (size_t)(nt2 + 1) * 8));
-        OKR(ensure(c, c->b_r1_start, (cap + 1) * (c->wide ? 8 : 4)));
-        OKR(ensure(c, c->b_r1_meta, cap * 16));
-        OKR(ensure(c, c->b_r1_base, cap * 4));
-        OKR(ensure(c, c->b_r1_tok, cap * 8));
+        OKR(ensure(c, status, (size_t)(nt + 1) * 8));
         OKR(ensure(c, c->b_ann, cap * 8));
+        if (annotated) {
+            c->rec_cap_r1 = cap;
+            OKR(ensure(c, c->b_r1_start, (cap + 1) * (c->wide ? 8 : 4)));
+            OKR(ensure(c, c->b_r1_meta, cap * 16));
+            OKR(ensure(c, c->b_r1_base, cap * 4));
+        } else {
+            OKR(ensure(c, c->b_r2_tok, cap * 8));
+        }
         OKR(ensure(c, c->b_keys, cap * 8));
         OKR(ensure(c, c->b_irr, cap * sizeof(IrrKey)));
         CU(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(DevCounters), c->stream));
-        CU(c, cudaMemsetAsync(c->d_err_off, 0xFF, 2 * sizeof(unsigned long long), c->stream));
+        CU(c, cudaMemsetAsync(c->d_err_off, 0xFF, 4 * sizeof(unsigned long long), c->stream));
         CU(c, cudaMemsetAsync(c->d_hist, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
-        CU(c, cudaMemsetAsync(c->b_status1.p, 0, (size_t)(nt1 + 1) * 8, c->stream));
-        CU(c, cudaMemsetAsync(c->b_status2.p, 0, (size_t)(nt2 + 1) * 8, c->stream));
-        OKR(c->wide ? launch_scans<uint64_t>(c, c->defer1, c->defer2) : launch_scans<uint32_t>(c, c->defer1, c->defer2));
+        CU(c, cudaMemsetAsync(status.p, 0, (size_t)(nt + 1) * 8, c->stream));
+        OKR(c->wide ? launch_scan_phase1<uint64_t>(c, defer) : launch_scan_phase1<uint32_t>(c, defer));
         OKR(fetch_counters(c, &h));
         if (h.err_flags & (kErrRespec | (kErrRespec << 1))) {
-            if (h.err_flags & kErrRespec) c->defer1 = false;
-            if (h.err_flags & (kErrRespec << 1)) c->defer2 = false;
+            defer = false;
             c->n_respec++;
             continue;
         }
@@ -925,23 +1035,11 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
         cap = std::max(h.n_records[0], h.n_records[1]) + 1;
     }
     if (h.err_flags & (kErrRespec | (kErrRespec << 1) | kErrOverflow)) return fail(c, SSD_EINVAL, "scan did not settle (internal)");
-    if (h.err_flags & (kErrNoAt | kErrKey | kErrDense | kErrIndex | kErrForeign)) {
-        unsigned long long off[2];
-        CU(c, cudaMemcpy(off, c->d_err_off, sizeof off, cudaMemcpyDeviceToHost));
-        if (h.err_flags & kErrDense) return fail(c, SSD_EMALFORMED, "FASTQ records shorter than 32 bytes on average are not supported");
-        if (h.err_flags & kErrIndex) return fail(c, SSD_EINDEX, "list index out of range");
-        if (h.err_flags & kErrForeign)
-            return fail(c, SSD_EINVAL, "record at byte %llu: the cell/UMI fields of its header are not made of this whitelist's barcodes", off[0]);
-        if (h.err_flags & kErrNoAt) {
-            int f = off[0] != ~0ull ? 0 : 1;
-            return fail(c, SSD_EMALFORMED, "read %d: record at byte %llu does not start with '@'", f + 1, off[f]);
-        }
-        std::string tok = token_at(c, c->r2, c->r2_len, off[1]);
-        return fail(c, SSD_EKEY, "%s", tok.c_str());
-    }
-    c->n_rec_r1 = h.n_records[0];
+    OKR(report_errors(c, h.err_flags));
     c->n_rec_r2 = annotated ? h.n_records[0] : h.n_records[1];
-    c->n_rec = std::min(c->n_rec_r1, c->n_rec_r2);
+    c->n_rec_r1 = annotated ? h.n_records[0] : 0;  // read 1 has not been looked at yet
+    c->n_rec = c->n_rec_r2;
+    c->r1_tables = annotated;
     c->n_keys = h.n_keys;
     c->n_irr = h.n_irr;
     c->phase1_done = true;
@@ -950,6 +1048,45 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
     c->stats.n_records_r2 = c->n_rec_r2;
     c->stats.n_regular_keys = c->n_keys;
     c->stats.n_irregular_keys = c->n_irr;
+    return SSD_OK;
+}
+
+// The per-record tables of read 1 (record starts, 16-byte descriptors, output-length contributions), made on demand by the
+// table-building scan: split mode and the table-driven writers need them, the fused pass does not.  Checks the mates' ids
+// against read 2's fingerprints on the way (V2:349-350).
+int ensure_r1_tables(ssd_ctx* c)
+{
+    if (c->r1_tables) return SSD_OK;
+    const uint32_t nt1 = blocks_for(c->r1_len, kTile);
+    uint64_t cap = std::max<uint64_t>(c->n_rec_r2 + 1024, c->r1_len / (uint64_t)c->record_hint + 1024);
+    DevCounters h{};
+    for (int attempt = 0, overflows = 0; attempt < 5; attempt++) {
+        c->rec_cap_r1 = cap;
+        OKR(ensure(c, c->b_status1, (size_t)(nt1 + 1) * 8));
+        OKR(ensure(c, c->b_r1_start, (cap + 1) * (c->wide ? 8 : 4)));
+        OKR(ensure(c, c->b_r1_meta, cap * 16));
+        OKR(ensure(c, c->b_r1_base, cap * 4));
+        k_reset_r1_pass<<<1, 1, 0, c->stream>>>(c->d_cnt, c->d_err_off);
+        CU(c, cudaMemsetAsync(c->b_status1.p, 0, (size_t)(nt1 + 1) * 8, c->stream));
+        OKR(c->wide ? launch_scan_r1<uint64_t>(c, c->defer1) : launch_scan_r1<uint32_t>(c, c->defer1));
+        c->n_launches++;
+        OKR(fetch_counters(c, &h));
+        if (h.err_flags & kErrRespec) {
+            c->defer1 = false;
+            c->n_respec++;
+            continue;
+        }
+        if (!(h.err_flags & kErrOverflow)) break;
+        if (++overflows == 2) return fail(c, SSD_EINVAL, "record tables overflowed twice (internal)");
+        cap = h.n_records[0] + 1;
+    }
+    if (h.err_flags & (kErrRespec | kErrOverflow)) return fail(c, SSD_EINVAL, "scan did not settle (internal)");
+    OKR(report_errors(c, h.err_flags));
+    c->n_rec_r1 = h.n_records[0];
+    c->n_rec = std::min(c->n_rec_r1, c->n_rec_r2);
+    c->stats.n_records_r1 = c->n_rec_r1;
+    OKR(check_unmated_tail(c));
+    c->r1_tables = true;
     return SSD_OK;
 }
 
@@ -1126,6 +1263,17 @@ extern "C" int ssd_count_distinct_owned(ssd_ctx* c, uint64_t* d_keys, uint64_t n
     return distinct_counts_arrays(c, d_keys, n_keys, (const IrrKey*)d_irregular, n_irregular, rank, world);
 }
 
+namespace {
+// Upper bound of an output's size before it has been written: an output record is at most 38 bytes longer than its read-1
+// record (the header only loses bytes, "_" + 24 barcode bytes + "_" + UMI (<= 10) + the "+" line's remainder).
+uint64_t output_bound(const ssd_ctx* c, int which)
+{
+    if (c->sized[which]) return which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
+    const uint64_t n = which == SSD_EMIT_MATCHED ? c->stats.n_matched : c->stats.n_retained;
+    return n ? (uint64_t)c->r1_len + 38ull * n + 64 : 0;
+}
+}  // namespace
+
 extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
 {
     if (!c) return SSD_EINVAL;
@@ -1139,9 +1287,11 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
     k_filter<<<nbc, kThreads, 0, c->stream>>>(c->d_hist, c->d_distinct, c->n_cells_total, (long long)c->cfg.min_count, c->cfg.filter_mode, c->d_pass,
                                               c->d_cnt);
     if (c->cfg.collapse_pairs > 0) k_collapse_map<<<nbc, kThreads, 0, c->stream>>>(c->d_pass, c->dcfg.n_wl, c->cfg.collapse_pairs, c->d_remap);
-    {
-        // exclusive scan of the post-filter output lengths; its first kernel also counts the retained records
-        // and sizes the pre-filter output
+    c->sized[SSD_EMIT_PASSING] = false;  // the set of passing cells may have changed
+    c->planned = -1;
+    if (c->r1_tables) {
+        // the per-record tables exist (annotated input, or split mode ran before): exclusive scan of the post-filter output
+        // lengths; its first kernel also counts the retained records and sizes the pre-filter output
         const uint32_t nb = (uint32_t)(c->n_rec / kScanBlock + 1);
         OKR(ensure(c, c->b_bsums, ((size_t)nb + 2) * sizeof(unsigned long long)));
         OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
@@ -1150,6 +1300,10 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
         CU(c, cudaMemsetAsync(bs, 0, ((size_t)nb + 2) * sizeof(unsigned long long), c->stream));
         k_plan_onepass<<<nb, kThreads, 0, c->stream>>>(f, c->n_rec, (unsigned long long*)c->b_out_off.p, bs + 1, (uint32_t*)bs, c->d_cnt);
         c->planned = SSD_EMIT_PASSING;
+    } else if (c->n_rec_r2) {
+        // read 1 has not been looked at: only the number of retained records is known (the sizes follow from the writer's pass)
+        k_count_retained<<<(uint32_t)std::min<uint64_t>(blocks_for(c->n_rec_r2, kThreads), 148 * 8), kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, c->n_rec_r2,
+                                                                                                                          c->d_pass, c->d_cnt);
     }
     CU(c, cudaGetLastError());
     OKR(fetch_counters(c, &h));
@@ -1157,10 +1311,23 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
     c->stats.n_cells = h.n_cells;
     c->stats.n_passing_cells = h.n_passing_cells;
     c->stats.n_retained = h.n_retained;
-    c->stats.bytes_matched = h.bytes_matched;
-    c->stats.bytes_passing = h.bytes_passing;
+    if (c->r1_tables) {
+        c->stats.bytes_matched = h.bytes_matched;
+        c->stats.bytes_passing = h.bytes_passing;
+        c->sized[0] = c->sized[1] = true;
+    } else {
+        c->stats.bytes_matched = output_bound(c, SSD_EMIT_MATCHED);
+        c->stats.bytes_passing = output_bound(c, SSD_EMIT_PASSING);
+    }
     c->filter_done = true;
     if (stats) *stats = c->stats;
+    return SSD_OK;
+}
+
+extern "C" int ssd_get_stats(const ssd_ctx* c, ssd_stats* stats)
+{
+    if (!c || !stats) return SSD_EINVAL;
+    *stats = c->stats;
     return SSD_OK;
 }
 
@@ -1186,23 +1353,96 @@ extern "C" int ssd_filter_single(ssd_ctx* c, ssd_stats* stats)
 // ================================================================================================
 // phase 3
 // ================================================================================================
+namespace {
+// The merged outputs in ONE pass over read 1 (ssd_fused.cuh): record boundaries, mate check, header rewrite and the
+// prefix-sum-compacted write, straight from the read-2 annotations and the per-cell pass table.
+int emit_fused(ssd_ctx* c, int which, uint8_t* d_out, size_t cap, size_t* written)
+{
+    const uint32_t nt = blocks_for(c->r1_len, kFTile);
+    DevCounters h{};
+    if (nt) {
+        OKR(ensure(c, c->b_status1, (size_t)(nt + 1) * 8));
+        OKR(ensure(c, c->b_status3, (size_t)(nt + 1) * 8));
+        k_reset_r1_pass<<<1, 1, 0, c->stream>>>(c->d_cnt, c->d_err_off);
+        CU(c, cudaMemsetAsync(c->b_status1.p, 0, (size_t)(nt + 1) * 8, c->stream));
+        CU(c, cudaMemsetAsync(c->b_status3.p, 0, (size_t)(nt + 1) * 8, c->stream));
+        FusedArgs a{};
+        a.buf = c->r1;
+        a.len = c->r1_len;
+        a.st1 = (unsigned long long*)c->b_status1.p;
+        a.st2 = (unsigned long long*)c->b_status3.p;
+        a.n_tiles = nt;
+        a.cnt = c->d_cnt;
+        a.err_off = c->d_err_off;
+        a.ann = (const uint64_t*)c->b_ann.p;
+        a.r2_tok = (const unsigned long long*)c->b_r2_tok.p;
+        a.n_rec_r2 = c->n_rec_r2;
+        a.pass = which == SSD_EMIT_PASSING ? c->d_pass : nullptr;
+        a.remap = (which == SSD_EMIT_PASSING && c->cfg.collapse_pairs > 0) ? c->d_remap : nullptr;
+        a.r2buf = c->r2;
+        a.wl64 = c->d_wl64;
+        a.out = d_out;
+        a.cap = cap;
+        {
+            StageTimer t(c, 5);
+            k_fused_r1<<<std::min<uint32_t>(nt, c->fused_grid), kFThreads, sizeof(FusedSmem), c->stream>>>(a, c->dcfg);
+        }
+        c->n_launches += 2;
+        CU(c, cudaGetLastError());
+        OKR(fetch_counters(c, &h));
+    }
+    if (h.err_flags & kErrEmitLen) return fail(c, SSD_ECUDA, "internal: emitted record length differs from the planned length");
+    OKR(report_errors(c, h.err_flags));
+    c->n_rec_r1 = h.n_records[0];
+    c->n_rec = std::min(c->n_rec_r1, c->n_rec_r2);
+    c->stats.n_records_r1 = c->n_rec_r1;
+    OKR(check_unmated_tail(c));
+    (which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing) = h.emit_bytes;
+    c->sized[which] = true;
+    if (written) *written = (size_t)h.emit_bytes;
+    if (h.err_flags & kErrRange) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)h.emit_bytes, cap);
+    const uint64_t want = which == SSD_EMIT_MATCHED ? c->stats.n_matched : c->stats.n_retained;
+    if (h.emit_records != want) return fail(c, SSD_ECUDA, "internal: %llu records written, %llu expected", (unsigned long long)h.emit_records, (unsigned long long)want);
+    return SSD_OK;
+}
+
+inline bool use_fused(const ssd_ctx* c)
+{
+    static const bool legacy = getenv("SSD_EMIT_TABLES") != nullptr;  // the table-driven writers (read-1 scan + plan + writer), for comparison
+    return !c->annotated && c->dcfg.bc8 && !legacy;
+}
+}  // namespace
+
 extern "C" int ssd_emit_device(ssd_ctx* c, int which, void* d_out, size_t cap, size_t* written)
 {
     if (!c) return SSD_EINVAL;
     if (!c->filter_done) return fail(c, SSD_ESTATE, "ssd_emit_device before ssd_build_filter");
     if (which != SSD_EMIT_MATCHED && which != SSD_EMIT_PASSING) return fail(c, SSD_EINVAL, "unknown output selector");
     CU(c, cudaSetDevice(c->device));
+    if (written) *written = 0;
+    if (use_fused(c)) {
+        if (!d_out && cap) return fail(c, SSD_EINVAL, "null output pointer");
+        return emit_fused(c, which, (uint8_t*)d_out, d_out ? cap : 0, written);
+    }
+    // table-driven: per-record tables of read 1, exclusive scan of the output lengths, writer
+    OKR(ensure_r1_tables(c));
+    if (c->planned != which || !c->sized[which]) {
+        StageTimer t(c, 4);
+        OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
+        OKR(exclusive_scan<unsigned long long>(c, make_outlen(c, which), c->n_rec, (unsigned long long*)c->b_out_off.p));
+        c->planned = which;
+        unsigned long long total = 0;
+        CU(c, cudaMemcpyAsync(&total, (unsigned long long*)c->b_out_off.p + c->n_rec, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        (which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing) = total;
+        c->sized[which] = true;
+    }
     const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
     if (written) *written = (size_t)need;
     if (need > cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, cap);
     if (need == 0) return SSD_OK;
     if (!d_out) return fail(c, SSD_EINVAL, "null output pointer");
-    if (c->planned != which) {
-        StageTimer t(c, 4);
-        OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
-        OKR(exclusive_scan<unsigned long long>(c, make_outlen(c, which), c->n_rec, (unsigned long long*)c->b_out_off.p));
-        c->planned = which;
-    }
+    CU(c, cudaMemsetAsync(&c->d_cnt->err_flags, 0, sizeof(unsigned int), c->stream));
     OKR(c->wide ? launch_emit<uint64_t>(c, which, (uint8_t*)d_out) : launch_emit<uint32_t>(c, which, (uint8_t*)d_out));
     DevCounters h{};
     OKR(fetch_counters(c, &h));
@@ -1216,14 +1456,13 @@ extern "C" int ssd_emit_split_device(ssd_ctx* c, void* d_out, size_t cap, size_t
     if (!c) return SSD_EINVAL;
     if (!c->filter_done) return fail(c, SSD_ESTATE, "ssd_emit_split_device before ssd_build_filter");
     CU(c, cudaSetDevice(c->device));
-    const uint64_t need = c->stats.bytes_passing, n = c->stats.n_retained;
-    if (written) *written = (size_t)need;
+    OKR(ensure_r1_tables(c));  // buckets are written through per-record tables of read 1
+    const uint64_t n = c->stats.n_retained;
+    if (written) *written = 0;
     if (n_buckets) *n_buckets = 0;
     c->n_buckets = 0;
-    c->split_bytes = need;
-    if (need > cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, cap);
+    c->split_bytes = 0;
     if (n == 0) return SSD_OK;
-    if (!d_out) return fail(c, SSD_EINVAL, "null output pointer");
     if (n >= (1ull << 32)) return fail(c, SSD_EINVAL, "split mode is limited to 2^32 records per batch");
     OutLen f = make_outlen(c, SSD_EMIT_PASSING);
     // 1. (cell, record) pairs of the written records, in input order
@@ -1244,6 +1483,15 @@ extern "C" int ssd_emit_split_device(ssd_ctx* c, void* d_out, size_t cap, size_t
     // 3. byte offsets in bucket order, 4. the writer through the permutation
     unsigned long long* off = (unsigned long long*)c->b_sp_off.p;
     OKR(exclusive_scan<unsigned long long>(c, SplitLen{f, order}, n, off));
+    unsigned long long need = 0;
+    CU(c, cudaMemcpyAsync(&need, off + n, sizeof need, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->stats.bytes_passing = need;  // the buckets hold the post-filter text, regrouped
+    c->sized[SSD_EMIT_PASSING] = true;
+    c->split_bytes = need;
+    if (written) *written = (size_t)need;
+    if (need > cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, cap);
+    if (!d_out) return fail(c, SSD_EINVAL, "null output pointer");
     OKR(c->wide ? launch_emit<uint64_t>(c, SSD_EMIT_PASSING, (uint8_t*)d_out, order, off, n)
                 : launch_emit<uint32_t>(c, SSD_EMIT_PASSING, (uint8_t*)d_out, order, off, n));
     // 5. bucket table
@@ -1306,12 +1554,16 @@ extern "C" int ssd_emit_host(ssd_ctx* c, int which, void* out, size_t out_cap, s
 {
     if (!c) return SSD_EINVAL;
     if (!c->filter_done) return fail(c, SSD_ESTATE, "ssd_emit_host before the filter was built");
-    const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
-    if (written) *written = (size_t)need;
+    if (which != SSD_EMIT_MATCHED && which != SSD_EMIT_PASSING) return fail(c, SSD_EINVAL, "unknown output selector");
+    const uint64_t bound = output_bound(c, which);  // exact once the text has been written before
+    if (written) *written = (size_t)bound;
+    if (!bound) return SSD_OK;
+    OKR(ensure(c, c->b_out, bound + 32));
+    size_t need = 0;
+    OKR(ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, &need));
+    if (written) *written = need;
     if (need > out_cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, out_cap);
     if (!need) return SSD_OK;
-    OKR(ensure(c, c->b_out, need + 32));
-    OKR(ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, nullptr));
     std::lock_guard<std::mutex> turn(g_d2h_turn);
     CU(c, cudaMemcpyAsync(out, c->b_out.p, need, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -1338,10 +1590,12 @@ extern "C" int ssd_run_host(ssd_ctx* c, const void* r1, size_t r1_len, const voi
     OKR(ssd_demux_device(c, c->b_in1.p, r1_len, c->b_in2.p, r2_len));
     OKR(ssd_filter_single(c, stats));
     if (!out && !out_cap) {
-        if (written) *written = (size_t)(which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing);
+        if (written) *written = (size_t)output_bound(c, which);  // an upper bound: ssd_emit_host reports the exact size
         return SSD_OK;
     }
-    return ssd_emit_host(c, which, out, out_cap, written);
+    const int rc = ssd_emit_host(c, which, out, out_cap, written);
+    if (stats) *stats = c->stats;  // now with the exact sizes and read 1's record count
+    return rc;
 }
 
 // ================================================================================================
@@ -1465,21 +1719,23 @@ int open_input(ssd_ctx* c, const char* path, int* fd, size_t* size)
 // emit `which` on the device, then download it with four threads, each overlapping its copies with its pwrites
 int download_to_file(ssd_ctx* c, int which, const char* out_path, int append, size_t* written)
 {
-    const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
-    if (written) *written = (size_t)need;
+    const uint64_t bound = output_bound(c, which);
+    if (written) *written = 0;
     const int fd = open(out_path, O_WRONLY | O_CREAT | (append ? 0 : O_TRUNC), 0644);
     if (fd < 0) return fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
     const off_t base = append ? lseek(fd, 0, SEEK_END) : 0;  // V2:367, 415 open in append mode
     int rc = base < 0 ? fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno)) : SSD_OK;
-    if (need && rc == SSD_OK) {
-        rc = ensure(c, c->b_out, need + 32);
-        if (rc == SSD_OK) rc = ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, nullptr);
+    if (bound && rc == SSD_OK) {
+        size_t need = 0;
+        rc = ensure(c, c->b_out, bound + 32);
+        if (rc == SSD_OK) rc = ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, &need);
         for (int k = 0; k < 4 && rc == SSD_OK; k++) rc = c->io[k].init();
         if (rc == SSD_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, SSD_ECUDA, "emit failed");  // the emit kernel ran on the context's stream
-        if (rc == SSD_OK) {
+        if (rc == SSD_OK && need) {
             std::lock_guard<std::mutex> turn(g_d2h_turn);
-            rc = run_lanes(c, out_path, 0, 4, download_file_worker, c->device, fd, (size_t)base, (size_t)need, (const uint8_t*)c->b_out.p);
+            rc = run_lanes(c, out_path, 0, 4, download_file_worker, c->device, fd, (size_t)base, need, (const uint8_t*)c->b_out.p);
         }
+        if (rc == SSD_OK && written) *written = need;
     }
     if (close(fd) != 0 && rc == SSD_OK) rc = fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
     return rc;
@@ -1512,7 +1768,9 @@ extern "C" int ssd_run_files(ssd_ctx* c, const char* path_r1, const char* path_r
     if (rc != SSD_OK) return rc;
     OKR(ssd_demux_device(c, c->b_in1.p, size[0], c->b_in2.p, size[1]));
     OKR(ssd_filter_single(c, stats));
-    return download_to_file(c, which, out_path, append, written);
+    rc = download_to_file(c, which, out_path, append, written);
+    if (stats) *stats = c->stats;  // now with the exact sizes and read 1's record count
+    return rc;
 }
 
 extern "C" int ssd_annotated_file(ssd_ctx* c, const char* path_in, const char* out_path, int append, size_t* written, ssd_stats* stats)
@@ -2061,6 +2319,19 @@ extern "C" int ssd_scan_repeats(const ssd_ctx* c, uint64_t* n)
 }
 
 extern "C" uint64_t ssd_launch_count(const ssd_ctx* c) { return c ? c->n_launches : 0; }
+
+#ifdef SSD_FUSED_PROFILE
+// debug builds only: clock totals of the fused pass per stage and wait reason (see ssd_fused.cuh)
+extern "C" int ssd_debug_fused_profile(unsigned long long* out16, int reset)
+{
+    if (out16 && cudaMemcpyFromSymbol(out16, ssd::g_fused_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return SSD_ECUDA;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(ssd::g_fused_prof, z, sizeof z) != cudaSuccess) return SSD_ECUDA;
+    }
+    return SSD_OK;
+}
+#endif
 
 #ifdef SSD_SCAN_PROFILE
 // debug builds only: per-phase clock totals of the scan kernels (phases 0..4, tiles in [7]) for read 1 / read 2

@@ -113,6 +113,7 @@ _SIGS = {
                                      C.POINTER(C.c_uint64)]),
     "ssd_build_filter": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "ssd_filter_single": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "ssd_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "ssd_emit_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ssd_emit_split_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
     "ssd_split_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),

@@ -41,12 +41,12 @@ def digests():
 def run_both(ssd, r1, r2, e, m, **kw):
     dm = ssd.Demultiplexer(WL, errors=e, min_count=m, **kw)
     passing, stats = dm.run_host(r1, r2, ssd.EMIT_PASSING)
-    merged = np.empty(stats["bytes_matched"], dtype=np.uint8)
+    merged = np.empty(stats["bytes_matched"], dtype=np.uint8)  # an upper bound until that text has been written
     import ctypes as C
     n = C.c_size_t()
     if merged.size:
         dm._check(dm.lib.ssd_emit_host(dm._ctx, ssd.EMIT_MATCHED, merged.ctypes.data_as(C.c_void_p), merged.size, C.byref(n)))
-    return dm, merged.tobytes(), passing.tobytes(), stats
+    return dm, merged[: n.value].tobytes(), passing.tobytes(), dm.stats()
 
 
 def table_bytes(dm):
