@@ -5,19 +5,22 @@
 // join), V2:134-141 + 367-370 / 415-454 (header rewrite, writers).  Read 2 has been scanned before (ssd_scan.cuh): its
 // annotation word and id fingerprint per record, and the -m decision per cell, are inputs here.
 //
-// Persistent, warp-specialised, one block per SM, tiles of 24 KiB taken by ticket:
+// Persistent, warp-specialised, one block per SM, tiles of 16 KiB taken by ticket:
 //   copy warp     keeps kFSlots tile windows (tile + 2 KiB halo) arriving with bulk copies (TMA, mbarrier complete_tx)
 //   stage A       (8 warps) newline bitmap from 16-byte shared loads, tile newline count PUBLISHED (chain 1), list of line starts
 //   prefix warp 1 (block 0) turns the published newline counts into inclusive prefixes, in tile order
-//   stage B       (2 groups of 4 warps, alternate tiles) waits for the tile's line index, then one thread per record:
-//                 header walk (id fingerprint, name.split("/")[0].replace(" ","").strip()), read / quality bounds, the
-//                 record's annotation + read 2's fingerprint (mate check, V2:350), pass decision, output length;
-//                 exclusive scan of the lengths inside the tile, tile output bytes PUBLISHED (chain 2)
+//   stage B       (3 groups of 3 warps, tiles dealt round robin: the stage is latency bound) waits for the tile's line
+//                 index, then one thread per record: header walk (id fingerprint, name.split("/")[0].replace(" ","")
+//                 .strip(), squeezed IN PLACE in the window), read / quality bounds, the record's annotation + read 2's
+//                 fingerprint (mate check, V2:350), pass decision, output length; exclusive scan of the lengths inside
+//                 the tile, tile output bytes PUBLISHED (chain 2); descriptors into a ring of kFDesc slots
 //   prefix warp 2 (block 0) the same look-back over the tiles' output bytes: where each tile's slice of the output starts
-//   stage C       (8 warps) assembles the tile's output slice shared -> shared (header squeeze, "_cell_umi", 16-byte
-//                 chunks of read + quality funnel-shifted into place) and sends it off with a bulk store (two buffers)
-// Two dependent look-back chains (record numbers, then output offsets) cost latency, not bandwidth: the windows in
-// flight cover it.  Nothing is guessed: a tile is only processed with its exact record numbers.
+//   poll warp     waits for a described tile's output offset, so that stage C never does
+//   stage C       (8 warps) assembles the tile's output slice shared -> shared ("_cell_umi" literal, word-wise copies of the
+//                 short pieces, 16-byte chunks of read + quality funnel-shifted into place) and sends it off with a bulk
+//                 store (two buffers)
+// Two dependent look-back chains (record numbers, then output offsets) cost latency, not bandwidth: the windows and
+// descriptor slots in flight cover it.  Nothing is guessed: a tile is only processed with its exact record numbers.
 // Records outside the fast path's preconditions (control bytes in the header, more than two trailing blanks, records
 // that outgrow the window, tiles with more than kFMaxRec records) make their tile take an exact path from global memory.
 #pragma once
@@ -26,27 +29,27 @@
 namespace ssd {
 
 #ifndef SSD_FUSED_SLOTS
-#define SSD_FUSED_SLOTS 5
+#define SSD_FUSED_SLOTS 7
 #endif
-constexpr int kFTile = 24576;
+constexpr int kFTile = 16384;
 constexpr int kFHalo = 2048;
 constexpr int kFWin = kFTile + kFHalo;
 constexpr int kFWinWords = kFWin / 32, kFTileWords = kFTile / 32, kFHaloWords = kFHalo / 32;
-constexpr int kFSlots = SSD_FUSED_SLOTS;           // tile windows per block: being filled / in A / waiting / in B / in C
+constexpr int kFSlots = SSD_FUSED_SLOTS;           // tile windows per block: being filled / in A / in B (3) / described, waiting / in C
 constexpr int kFMaxRecTile = kFTile / 32;          // records starting in one tile (>= 32 bytes each on average)
 constexpr int kFMaxLines = 4 * kFMaxRecTile + 72;  // line-start list entries (tile + halo)
-constexpr int kFMaxRec = 256;                      // records of a tile that stage B describes for stage C
-constexpr int kFBatchRec = 128;                    // records per assembly batch
-constexpr int kFOut = 28672;                       // staged output bytes per assembly batch (< 32768: offsets share words with flags)
-constexpr int kFAWarps = 8, kFBWarps = 4, kFBGroups = 2, kFCWarps = 8;
+constexpr int kFMaxRec = 128;                      // records of a tile that stage B describes for stage C
+constexpr int kFOut = 20480;                       // staged output bytes per assembly batch (< 32768: offsets share words with flags)
+constexpr int kFDesc = 4;                          // descriptor slots between stage B and stage C
+constexpr int kFAWarps = 8, kFBWarps = 3, kFBGroups = 3, kFCWarps = 8;
 constexpr int kFAThreads = kFAWarps * 32, kFBThreads = kFBWarps * 32, kFCThreads = kFCWarps * 32;
 constexpr int kFWarpB0 = kFAWarps, kFWarpC0 = kFWarpB0 + kFBGroups * kFBWarps, kFWarpCopy = kFWarpC0 + kFCWarps;
-constexpr int kFWarpPrefix1 = kFWarpCopy + 1, kFWarpPrefix2 = kFWarpCopy + 2;
-constexpr int kFThreads = (kFWarpPrefix2 + 1) * 32;
+constexpr int kFWarpPrefix1 = kFWarpCopy + 1, kFWarpPrefix2 = kFWarpCopy + 2, kFWarpPoll = kFWarpCopy + 3;
+constexpr int kFThreads = (kFWarpPoll + 1) * 32;
 constexpr uint32_t kFGeneric = 1u, kFSequential = 2u;  // tile flags: exact path per record / one warp walks the tile
-static_assert(kFBGroups == 2, "stage B groups alternate tiles; list and descriptor slots are indexed by it & 1");
 static_assert(kFTileWords % kFAThreads == 0 && kFHaloWords <= 64, "tile shape");
 static_assert(kFWin + 48 < kFOut, "one record of the fast path always fits an assembly batch");
+static_assert(kFThreads <= 1024, "block size");
 
 struct FusedArgs {
     const uint8_t* buf;  // read 1
@@ -72,30 +75,31 @@ struct FDesc {
     unsigned long long ann[kFMaxRec];  // annotation of the record, 0 = not written
     uint4 info[kFMaxRec];              // x = start in the window | cut << 16, y = kept | tail << 16, z = seq_rel | seq_len << 16, w = qual_rel | qual_len << 16
     uint32_t rel[kFMaxRec + 4];        // exclusive scan of the output lengths (n_rec + 1 entries)
-    unsigned long long r_first;
+    unsigned long long r_first, out_hi;  // first record number; inclusive prefix of the output bytes (set by the poll warp)
     uint32_t tile, n_rec, total, n_kept, flags, first_s0, cps, cps_magic;
 };
 
 struct __align__(128) FusedSmem {
     uint8_t win[kFSlots][kFWin + 128];  // tile windows (bulk-copy destinations)
     uint8_t out[2][kFOut + 32];         // assembled output slices (bulk-store sources)
-    FDesc desc[kFBGroups];
-    uint2 c_head[kFBatchRec];           // stage C, per record of the batch: {dst | src << 16, cut | literal dst << 16 | two segments << 31}
-    uint2 c_seg[2][kFBatchRec];         // long segments {dst | src << 16, length}
-    uint2 c_chk[2][kFBatchRec];         // their whole 16-byte chunks
-    uint16_t lstart[2][kFMaxLines];     // line-start lists between stage A and stage B
+    FDesc desc[kFDesc];
+    uint2 c_seg[3][kFMaxRec];           // stage C, per record of the batch: {dst | src << 16, length} of header', read (+ "+" + quality when adjacent), quality
+    uint2 c_chk[2][kFMaxRec];           // whole 16-byte chunks of the two long segments
+    uint32_t c_lit[kFMaxRec];           // where the literal goes | two long segments << 31
+    uint16_t lstart[kFBGroups][kFMaxLines];  // line-start lists between stage A and stage B
     alignas(16) uint32_t mask[kFWinWords];
     unsigned long long wl64[kMaxWl];
-    unsigned long long full[kFSlots], empty[kFSlots];  // mbarriers: bytes landed / stage C is done with the window
-    unsigned long long list_full[2], list_empty[2];    // stage A -> stage B
-    unsigned long long desc_full[2], desc_empty[2];    // stage B -> stage C
-    unsigned long long line_base[kFBGroups], c_out_hi;
+    unsigned long long full[kFSlots], empty[kFSlots];              // mbarriers: bytes landed / stage C is done with the window
+    unsigned long long list_full[kFBGroups], list_empty[kFBGroups];  // stage A -> stage B
+    unsigned long long desc_full[kFDesc], desc_ready[kFDesc], desc_empty[kFDesc];  // stage B -> poll warp -> stage C -> stage B
+    unsigned long long line_base[kFBGroups];
     uint32_t tile[kFSlots];
-    uint32_t total[2], n_listed[2], list_tile[2];
+    uint32_t total[kFBGroups], n_listed[kFBGroups], list_tile[kFBGroups];
     uint32_t warp_tile[kFAWarps], halo_sum[2];
     uint32_t b_warp[kFBGroups][kFBWarps], b_flags[kFBGroups], b_kept[kFBGroups];
     uint32_t c_flags[2];  // per assembly batch (alternating): 1 = some record has two long segments
 };
+static_assert(sizeof(FusedSmem) <= 232448, "the block's shared memory must fit the 227 KiB an sm_100 block may ask for");
 
 // In-order inclusive prefix over published per-tile values (decoupled look-back done by ONE warp for everybody): every
 // lane takes 8 consecutive entries, 256 tiles per round trip to L2.  Entries: flag << 62 | value, flag 1 = published.
@@ -187,10 +191,12 @@ __device__ __noinline__ void r1_measure_generic(const Acc& a, size_t len, size_t
     m.fp = tok_hash_generic(a, L.s[0], tok_e);
 }
 
+
 #ifdef SSD_FUSED_PROFILE
 // debug builds only: clock totals per stage and wait reason, summed over the blocks (one thread per stage group counts)
 //   0 A wait list slot  1 A wait data  2 A work   3 B wait list  4 B wait desc slot  5 B poll chain 1  6 B work
-//   7 C wait desc  8 C poll chain 2  9 C work  10 tiles  11 copy wait window  12 C describe  13 C tasks + chunks (thread 0)  14 C fence + bulk wait + sync  15 C store
+//   7 C wait ready  8 poll warp: chain 2  9 C work  10 tiles  11 copy wait window  12 C describe  13 C assemble (thread 0)
+//   14 C fence + bulk wait + sync  15 C store
 __device__ unsigned long long g_fused_prof[16];
 #define FP_T(var) const long long var = clock64()
 #define FP_ADD(slot, a, b) fprof[slot] += (unsigned long long)((b) - (a))
@@ -208,7 +214,42 @@ __device__ unsigned long long g_fused_prof[16];
 
 __device__ __forceinline__ void sync_fa() { asm volatile("bar.sync 1, %0;" ::"n"(kFAThreads) : "memory"); }
 __device__ __forceinline__ void sync_fb(int g) { asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(kFBThreads) : "memory"); }
-__device__ __forceinline__ void sync_fc() { asm volatile("bar.sync 4, %0;" ::"n"(kFCThreads) : "memory"); }
+__device__ __forceinline__ void sync_fc() { asm volatile("bar.sync 5, %0;" ::"n"(kFCThreads) : "memory"); }
+
+// n bytes shared -> shared at any alignment: dst-aligned 32-bit words (two source words funnel-shifted), at most three
+// bytes on either side bytewise.  Reads up to 3 bytes past src + n (inside the window's padding).
+__device__ __forceinline__ void copy_words(uint8_t* s_out, uint32_t dst, const uint8_t* s_in, uint32_t src, uint32_t n)
+{
+    uint32_t h = (4u - (dst & 3u)) & 3u;
+    h = h < n ? h : n;
+    for (uint32_t i = 0; i < h; i++) s_out[dst + i] = s_in[src + i];
+    dst += h;
+    src += h;
+    n -= h;
+    const uint32_t nw = n >> 2, sh = (src & 3u) * 8u;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(s_in + (src & ~3u));
+    uint32_t* o = reinterpret_cast<uint32_t*>(s_out + dst);
+    uint32_t prev = nw ? w[0] : 0u;
+    for (uint32_t i = 0; i < nw; i++) {
+        const uint32_t nxt = w[i + 1];
+        o[i] = __funnelshift_r(prev, nxt, sh);
+        prev = nxt;
+    }
+    for (uint32_t i = nw << 2; i < n; i++) s_out[dst + i] = s_in[src + i];
+}
+
+// the bytes of a long segment that do not fill a 16-byte output chunk (up to 15 in front, up to 15 behind), word-wise
+__device__ __forceinline__ void edges_words(const uint8_t* s_in, uint8_t* s_out, uint2 sg)
+{
+    const uint32_t dst = sg.x & 0xFFFFu, src = sg.x >> 16, len = sg.y;
+    uint32_t nh = (16u - (dst & 15u)) & 15u;
+    nh = nh < len ? nh : len;
+    copy_words(s_out, dst, s_in, src, nh);
+    const uint32_t e = dst + len;
+    uint32_t t0 = e & ~15u;
+    t0 = t0 > dst + nh ? t0 : dst + nh;
+    copy_words(s_out, t0, s_in, src + (t0 - dst), e - t0);
+}
 
 __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant__ FusedArgs args, const __grid_constant__ DevCfg cfg)
 {
@@ -220,10 +261,13 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
             mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), 1);
             mbar_init(reinterpret_cast<uint64_t*>(&S.empty[s]), 1);
         }
-        for (int s = 0; s < 2; s++) {
+        for (int s = 0; s < kFBGroups; s++) {
             mbar_init(reinterpret_cast<uint64_t*>(&S.list_full[s]), 1);
             mbar_init(reinterpret_cast<uint64_t*>(&S.list_empty[s]), 1);
+        }
+        for (int s = 0; s < kFDesc; s++) {
             mbar_init(reinterpret_cast<uint64_t*>(&S.desc_full[s]), 1);
+            mbar_init(reinterpret_cast<uint64_t*>(&S.desc_ready[s]), 1);
             mbar_init(reinterpret_cast<uint64_t*>(&S.desc_empty[s]), 1);
         }
     }
@@ -238,6 +282,29 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
     }
     if (warp == kFWarpPrefix2) {
         if (blockIdx.x == 0) prefix_chain(st2, args.n_tiles, lane);
+        return;
+    }
+    if (warp == kFWarpPoll) {
+        // ================================ poll warp: where a described tile's slice of the output ends ================================
+        if (lane != 0) return;
+        FP_DECL;
+        for (uint32_t it = 0;; it++) {
+            const uint32_t ds = it % kFDesc;
+            FDesc& D = S.desc[ds];
+            mbar_wait(reinterpret_cast<uint64_t*>(&S.desc_full[ds]), (it / kFDesc) & 1u);
+            const uint32_t tile = D.tile;
+            if (tile != kNoTile) {
+                FP_T(p0);
+                const unsigned long long incl = poll_prefix(st2, tile);  // inclusive prefix of the output bytes, written by prefix warp 2
+                FP_T(p1);
+                FP_ADD(8, p0, p1);
+                D.out_hi = incl;
+                if (tile == args.n_tiles - 1) args.cnt->emit_bytes = incl;
+            }
+            mbar_arrive(&S.desc_ready[ds]);
+            if (tile == kNoTile) break;
+        }
+        FP_FLUSH(true);
         return;
     }
     if (warp == kFWarpCopy) {
@@ -283,9 +350,9 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
         // ================================ stage A: newline bitmap, count, line-start list ================================
         FP_DECL;
         for (uint32_t it = 0;; it++) {
-            const uint32_t ws = it % kFSlots, ls = it & 1u;
+            const uint32_t ws = it % kFSlots, ls = it % kFBGroups;
             FP_T(p0);
-            if (it >= 2u) mbar_wait(reinterpret_cast<uint64_t*>(&S.list_empty[ls]), ((it >> 1) - 1u) & 1u);
+            if (it >= (uint32_t)kFBGroups) mbar_wait(reinterpret_cast<uint64_t*>(&S.list_empty[ls]), ((it / kFBGroups) - 1u) & 1u);
             FP_T(p1);
             mbar_wait(reinterpret_cast<uint64_t*>(&S.full[ws]), (it / kFSlots) & 1u);
             FP_T(p2);
@@ -293,16 +360,14 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
             FP_ADD(1, p1, p2);
             const uint32_t tile = S.tile[ws];
             if (tile == kNoTile) {
-                // the end reaches both stage-B groups: this iteration's and the next one's
-                if (tid == 0) {
-                    S.list_tile[ls] = kNoTile;
-                    mbar_arrive(&S.list_full[ls]);
-                }
-                const uint32_t it2 = it + 1u, ls2 = it2 & 1u;
-                if (it2 >= 2u) mbar_wait(reinterpret_cast<uint64_t*>(&S.list_empty[ls2]), ((it2 >> 1) - 1u) & 1u);
-                if (tid == 0) {
-                    S.list_tile[ls2] = kNoTile;
-                    mbar_arrive(&S.list_full[ls2]);
+                // the end reaches every stage-B group: this iteration's and the following ones'
+                for (uint32_t j = 0; j < (uint32_t)kFBGroups; j++) {
+                    const uint32_t it2 = it + j, ls2 = it2 % kFBGroups;
+                    if (j != 0u && it2 >= (uint32_t)kFBGroups) mbar_wait(reinterpret_cast<uint64_t*>(&S.list_empty[ls2]), ((it2 / kFBGroups) - 1u) & 1u);
+                    if (tid == 0) {
+                        S.list_tile[ls2] = kNoTile;
+                        mbar_arrive(&S.list_full[ls2]);
+                    }
                 }
                 break;
             }
@@ -393,17 +458,17 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
 
     if (warp < kFWarpC0) {
         // ================================ stage B: the records that start in the tile ================================
-        const int g = (warp - kFWarpB0) / kFBWarps;                  // group: takes the block's tiles it = g, g + 2, ...
+        const int g = (warp - kFWarpB0) / kFBWarps;                         // group: takes the block's tiles it = g, g + 3, ...
         const int tb = tid - (kFWarpB0 + g * kFBWarps) * 32, wb = tb >> 5;  // thread / warp inside the group
-        FDesc& D = S.desc[g];
         GlobAcc ga{args.buf, args.len};
         FP_DECL;
-        for (uint32_t it = (uint32_t)g;; it += 2u) {
-            const uint32_t ws = it % kFSlots, ls = (uint32_t)g;
+        for (uint32_t it = (uint32_t)g;; it += (uint32_t)kFBGroups) {
+            const uint32_t ws = it % kFSlots, ls = (uint32_t)g, ds = it % kFDesc;
+            FDesc& D = S.desc[ds];
             FP_T(p0);
-            mbar_wait(reinterpret_cast<uint64_t*>(&S.list_full[ls]), (it >> 1) & 1u);
+            mbar_wait(reinterpret_cast<uint64_t*>(&S.list_full[ls]), (it / kFBGroups) & 1u);
             FP_T(p1);
-            if (it >= 2u) mbar_wait(reinterpret_cast<uint64_t*>(&S.desc_empty[g]), ((it >> 1) - 1u) & 1u);  // stage C is done with the previous tile of this group
+            if (it >= (uint32_t)kFDesc) mbar_wait(reinterpret_cast<uint64_t*>(&S.desc_empty[ds]), ((it / kFDesc) - 1u) & 1u);  // stage C is done with the slot
             FP_T(p2);
             FP_ADD(3, p0, p1);
             FP_ADD(4, p1, p2);
@@ -411,13 +476,13 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
             if (tile == kNoTile) {
                 if (tb == 0) {
                     D.tile = kNoTile;
-                    mbar_arrive(&S.desc_full[g]);
+                    mbar_arrive(&S.desc_full[ds]);
                 }
                 break;
             }
             const size_t tile_lo = (size_t)tile * kFTile;
             const uint32_t win_bytes = (uint32_t)(args.len - tile_lo < (size_t)kFWin ? args.len - tile_lo : (size_t)kFWin);
-            const uint8_t* s_win = S.win[ws];
+            uint8_t* s_win = S.win[ws];
             const uint16_t* s_lstart = S.lstart[ls];
             const uint32_t total = S.total[ls], n_listed = S.n_listed[ls];
             const uint32_t* words = reinterpret_cast<const uint32_t*>(s_win);
@@ -480,7 +545,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
                 const uint32_t trip = __reduce_max_sync(0xFFFFFFFFu, nwords);
                 // one pass over the header, four bytes at a time from its first byte: id fingerprint and the pieces of
                 // name.split("/")[0].replace(" ", "").strip() (V2:135-138)
-                uint32_t cut = hdr_len, spaces = 0, bad = 0, tok_len = hdr_len;
+                uint32_t cut = hdr_len, spaces = 0, bad = 0, tok_len = hdr_len, first_sp = 0xFFFFFFFFu;
                 bool found_slash = false, found_tok = false;
                 unsigned long long h = kTokSeed;
                 {
@@ -507,15 +572,16 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
                                 if (4u * w < tok_len) h = tok_hash_step(h, tw);
                             }
                             if (!found_slash) {
-                                const uint32_t zs = zero_flags(x ^ 0x2F2F2F2Fu) & V, zp = zero_flags(x ^ 0x20202020u) & V;
+                                const uint32_t zs = zero_flags(x ^ 0x2F2F2F2Fu) & V;
+                                uint32_t zp = zero_flags(x ^ 0x20202020u) & V;
                                 if (zs) {
                                     const uint32_t bit = (uint32_t)__ffs((int)zs) - 1u;
                                     cut = 4u * w + (bit >> 3);
-                                    spaces += (uint32_t)__popc(zp & ((1u << bit) - 1u));
+                                    zp &= (1u << bit) - 1u;
                                     found_slash = true;
-                                } else {
-                                    spaces += (uint32_t)__popc(zp);
                                 }
+                                if (zp && first_sp == 0xFFFFFFFFu) first_sp = 4u * w + (((uint32_t)__ffs((int)zp) - 1u) >> 3);
+                                spaces += (uint32_t)__popc(zp);
                             }
                         }
                     }
@@ -529,7 +595,6 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
                 if (ok) {
                     noat = s_win[s0] != '@';
                     tail = (seq_e == s2 - 1u && s3 - s2 == 2u && s_win[s2] == '+' && qual_e == s4 - 1u) ? 1u : 0u;
-                    if (cut > 0xFFFFu) ok = false;
                 }
                 __syncwarp();
                 if (have && !ok) {
@@ -556,6 +621,15 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
                     }
                     if (keep) out_len = kept + 27u + ann_umi_len(an, cfg.umi_len) + seq_len + qual_len + 4u;
                 }
+                if (keep && ok && spaces) {
+                    // name.replace(" ", ""): squeezed in place, so that the writer copies header' like any other piece
+                    uint8_t* hw = s_win + s0;
+                    uint32_t o = first_sp;
+                    for (uint32_t k = first_sp + 1u; k < cut; k++) {
+                        const uint8_t ch = hw[k];
+                        if (ch != ' ') hw[o++] = ch;
+                    }
+                }
                 // exclusive scan of the output lengths over the group (and over the rounds)
                 uint32_t incl = out_len;
 #pragma unroll
@@ -581,7 +655,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
                     D.rel[i] = rel;
                 }
                 run += round_total;
-                sync_fb(g);  // b_warp may be reused
+                sync_fb(g);  // b_warp may be reused; the descriptors and the squeezed headers are in place
             }
             if (tb == 0) {
                 const uint32_t n_kept = S.b_kept[g];
@@ -596,12 +670,12 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
                 D.r_first = r_first;
                 D.first_s0 = n_rec ? (tile == 0 ? 0u : (uint32_t)s_lstart[j_first]) : 0u;
                 const uint32_t avg = n_kept ? run / n_kept : 0u;
-                uint32_t cps = (avg > 40u ? avg - 40u : 0u) / 16u;
+                uint32_t cps = (avg > 64u ? avg - 64u : 0u) / 16u;
                 cps = cps < 1u ? 1u : (cps > 64u ? 64u : cps);
                 D.cps = cps;
                 D.cps_magic = ((1u << 20) + cps - 1u) / cps;
                 st2[tile] = kFlagAgg | (unsigned long long)run;  // published: prefix warp 2 takes it from here
-                mbar_arrive(&S.desc_full[g]);   // over to stage C (which also releases the window)
+                mbar_arrive(&S.desc_full[ds]);   // over to the poll warp and stage C (which also releases the window)
                 mbar_arrive(&S.list_empty[ls]);  // the list slot may be refilled
                 FP_T(p4);
                 FP_ADD(6, p2, p4);
@@ -619,26 +693,17 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
         uint32_t nbuf = 0;
         FP_DECL;
         for (uint32_t it = 0;; it++) {
-            const uint32_t g = it & 1u, ws = it % kFSlots;
-            const FDesc& D = S.desc[g];
+            const uint32_t ds = it % kFDesc, ws = it % kFSlots;
+            const FDesc& D = S.desc[ds];
             FP_T(p0);
-            mbar_wait(reinterpret_cast<uint64_t*>(&S.desc_full[g]), (it >> 1) & 1u);
+            mbar_wait(reinterpret_cast<uint64_t*>(&S.desc_ready[ds]), (it / kFDesc) & 1u);
             FP_T(p1);
             FP_ADD(7, p0, p1);
             const uint32_t tile = D.tile;
             if (tile == kNoTile) break;
             const uint32_t total = D.total, n_rec = D.n_rec, flags = D.flags;
-            if (tc == 0) {
-                // where this tile's slice ends: inclusive prefix of the output bytes, written by prefix warp 2
-                const unsigned long long incl = poll_prefix(st2, tile);
-                FP_T(p2);
-                FP_ADD(8, p1, p2);
-                S.c_out_hi = incl;
-                if (tile == args.n_tiles - 1) args.cnt->emit_bytes = incl;
-                my_records += D.n_kept;
-            }
-            sync_fc();
-            const unsigned long long out_hi = S.c_out_hi, out_lo = out_hi - total;
+            const unsigned long long out_hi = D.out_hi, out_lo = out_hi - total;
+            if (tc == 0) my_records += D.n_kept;
             const size_t tile_lo = (size_t)tile * kFTile;
             const uint8_t* s_win = S.win[ws];
             if (total != 0u && out_hi > args.cap) {
@@ -672,11 +737,11 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
             } else if (total != 0u) {
                 const uint32_t cps = D.cps, cps_magic = D.cps_magic;
                 for (uint32_t k_lo = 0; k_lo < n_rec;) {
-                    // the next batch: at most kFBatchRec records whose output fits one staging buffer
+                    // the next batch: the records whose output fits one staging buffer (all of the tile's, as a rule)
                     const uint32_t base = D.rel[k_lo];
                     const unsigned long long q_lo = out_lo + base;
                     const uint32_t skew = (uint32_t)(((uintptr_t)args.out + q_lo) & 15u);
-                    uint32_t k_hi = n_rec < k_lo + (uint32_t)kFBatchRec ? n_rec : k_lo + (uint32_t)kFBatchRec;
+                    uint32_t k_hi = n_rec;
                     if (D.rel[k_hi] - base + skew > (uint32_t)kFOut) {
                         uint32_t lo = k_lo + 1u, hi = k_hi;  // rel[lo] fits (one record always does), rel[hi] does not
                         while (hi - lo > 1u) {
@@ -696,51 +761,42 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
                         if ((uint32_t)tc < nq) {
                             const uint32_t k = k_lo + (uint32_t)tc;
                             const unsigned long long an = D.ann[k];
-                            uint2 sa = make_uint2(0u, 0u), sb = make_uint2(0u, 0u), hd = make_uint2(0u, 0u);
+                            uint2 sh = make_uint2(0u, 0u), sa = make_uint2(0u, 0u), sb = make_uint2(0u, 0u);
+                            uint32_t lit_at = 0;
                             if (an != 0ull) {
                                 const uint4 nf = D.info[k];
-                                const uint32_t src0 = nf.x & 0xFFFFu, cut = nf.x >> 16, kept = nf.y & 0xFFFFu, seq_rel = nf.z & 0xFFFFu, seq_len = nf.z >> 16,
+                                const uint32_t src0 = nf.x & 0xFFFFu, kept = nf.y & 0xFFFFu, seq_rel = nf.z & 0xFFFFu, seq_len = nf.z >> 16,
                                                qual_rel = nf.w & 0xFFFFu, qual_len = nf.w >> 16;
                                 const uint32_t lit = 27u + ann_umi_len(an, cfg.umi_len);
                                 const uint32_t d = skew + (D.rel[k] - base), dA = d + kept + lit;
-                                hd = make_uint2(d | (src0 << 16), cut | ((d + kept) << 16));
+                                sh = make_uint2(d | (src0 << 16), kept);  // header', squeezed in place by stage B
+                                lit_at = d + kept;
                                 if (nf.y >> 16) {  // the source already reads  read "\n+\n" quality "\n"
                                     sa = make_uint2(dA | ((src0 + seq_rel) << 16), qual_rel + qual_len + 1u - seq_rel);
                                 } else {
                                     sa = make_uint2(dA | ((src0 + seq_rel) << 16), seq_len);
                                     sb = make_uint2((dA + seq_len + 3u) | ((src0 + qual_rel) << 16), qual_len);
-                                    hd.y |= 0x80000000u;
+                                    lit_at |= 0x80000000u;
                                 }
                             }
-                            S.c_seg[0][tc] = sa;
-                            S.c_seg[1][tc] = sb;
+                            S.c_seg[0][tc] = sh;
+                            S.c_seg[1][tc] = sa;
+                            S.c_seg[2][tc] = sb;
                             S.c_chk[0][tc] = tile_chunk_desc(sa);
                             S.c_chk[1][tc] = tile_chunk_desc(sb);
-                            S.c_head[tc] = hd;
+                            S.c_lit[tc] = lit_at;
                         }
                         sync_fc();
                         FP_T(c1);
                         FP_ADD(12, c0, c1);
-                        if ((uint32_t)tc < nq && (S.c_head[tc].y & 0x80000000u)) atomicOr(c_flags, 1u);
-                        if (tc < 64) {
-                            // ---- header without its blanks ----
-                            for (uint32_t t = (uint32_t)tc; t < nq; t += 64u) {
-                                if (D.ann[k_lo + t] == 0ull) continue;
-                                const uint2 hd = S.c_head[t];
-                                const uint32_t cut = hd.y & 0xFFFFu;
-                                const uint8_t* sp = s_win + (hd.x >> 16);
-                                uint8_t* dp = s_out + (hd.x & 0xFFFFu);
-                                for (uint32_t i = 0; i < cut; i++) {
-                                    const uint8_t ch = sp[i];
-                                    if (ch != ' ') *dp++ = ch;
-                                }
-                            }
-                        } else if (tc < 128) {
+                        if (tc < 128) {
                             // ---- '_' + barcode1 + barcode2 + barcode3 + '_' + umi + '\n' ----
-                            for (uint32_t t = (uint32_t)tc - 64u; t < nq; t += 64u) {
-                                const unsigned long long an = D.ann[k_lo + t];
-                                if (an == 0ull) continue;
-                                uint8_t* q = s_out + ((S.c_head[t].y >> 16) & 0x7FFFu);
+                            const uint32_t t = (uint32_t)tc;
+                            const unsigned long long an = t < nq ? D.ann[k_lo + t] : 0ull;
+                            if (an != 0ull) {
+                                const uint32_t la = S.c_lit[t];
+                                if (la & 0x80000000u) atomicOr(c_flags, 1u);
+                                uint8_t* q = s_out + (la & 0x7FFFu);
                                 uint32_t cell = ann_cell(an);
                                 if (args.remap) cell = args.remap[cell];
                                 uint32_t i1, i2, i3;
@@ -774,15 +830,16 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
                                 }
                                 q[26u + ulen] = '\n';
                             }
-                        } else if (tc < 192) {
-                            // ---- the ragged ends of the long segments, the separators of records whose lines are not adjacent ----
-                            for (uint32_t t = (uint32_t)tc - 128u; t < nq; t += 64u) {
-                                if (D.ann[k_lo + t] == 0ull) continue;
-                                const uint2 sa = S.c_seg[0][t];
-                                tile_edges(s_win, s_out, sa);
-                                if (S.c_head[t].y & 0x80000000u) {
-                                    const uint2 sb = S.c_seg[1][t];
-                                    tile_edges(s_win, s_out, sb);
+                        } else {
+                            // ---- header' and the ragged ends of the long segments (word-wise), the separators of records whose lines are not adjacent ----
+                            const uint32_t t = (uint32_t)tc - 128u;
+                            if (t < nq && D.ann[k_lo + t] != 0ull) {
+                                const uint2 sh = S.c_seg[0][t], sa = S.c_seg[1][t];
+                                copy_words(s_out, sh.x & 0xFFFFu, s_win, sh.x >> 16, sh.y);
+                                edges_words(s_win, s_out, sa);
+                                if (S.c_lit[t] & 0x80000000u) {
+                                    const uint2 sb = S.c_seg[2][t];
+                                    edges_words(s_win, s_out, sb);
                                     uint8_t* q = s_out + (sa.x & 0xFFFFu) + sa.y;
                                     q[0] = '\n';
                                     q[1] = '+';
@@ -840,7 +897,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_r1(const __grid_constant
             }
             sync_fc();  // every thread is done with the window and the descriptors
             if (tc == 0) {
-                mbar_arrive(&S.desc_empty[g]);
+                mbar_arrive(&S.desc_empty[ds]);
                 mbar_arrive(&S.empty[ws]);  // the window may be refilled
                 FP_T(p3);
                 FP_ADD(9, p1, p3);

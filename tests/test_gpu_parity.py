@@ -359,10 +359,11 @@ def test_scan_without_guessing_matches(ssd, orc, monkeypatch):
 
 def test_misleading_lines_repeat_the_scan(ssd, orc):
     """Quality lines that start with '@' followed two lines later by a read that starts with '+' cannot be told from a
-    record start inside one tile: the guess fails, the library repeats the scan without guessing, results stay exact."""
+    record start inside one tile: the read-2 scan's guess fails, the library repeats that scan without guessing, results
+    stay exact (the '+' is part of the UMI, which is copied verbatim: V2:295).  The pass over read 1 never guesses."""
     recs1, recs2 = [], []
     for i in range(6000):
-        s2 = "ACGTACGTAC" + WL[i % 96] + fu.LINKER_3_2 + WL[(i * 5) % 96] + fu.LINKER_2_1 + WL[(i * 11) % 96] + "ACGT" * 10
+        s2 = "+CGTACGTAC" + WL[i % 96] + fu.LINKER_3_2 + WL[(i * 5) % 96] + fu.LINKER_2_1 + WL[(i * 11) % 96] + "ACGT" * 10
         q2 = "@" + "F" * (len(s2) - 1)
         recs2.append("@M.%d\n%s\n+\n%s\n" % (i, s2, q2))
         recs1.append("@M.%d\n%s\n+\n%s\n" % (i, "+" + "ACGT" * 20, "@" + "E" * 80))
