@@ -76,14 +76,13 @@ typedef struct ssd_config {
 } ssd_config;
 
 typedef struct ssd_stats {
-    uint64_t n_records_r1, n_records_r2; /* complete 4-line records found (read 1: once an output was written) */
+    uint64_t n_records_r1, n_records_r2; /* complete 4-line records found                             */
     uint64_t n_matched;        /* records whose three barcodes matched (MergedCells_1 records)         */
     uint64_t n_cells;          /* "total number of unique barcodes detected" (V2:458)                  */
     uint64_t n_passing_cells;  /* "barcodes passing the minimum UMI threshold" (V2:459)                */
     uint64_t n_retained;       /* records of passing cells                                             */
-    uint64_t bytes_matched;    /* size of the SSD_EMIT_MATCHED text: an UPPER BOUND until that text has been written once  */
-    uint64_t bytes_passing;    /* size of the SSD_EMIT_PASSING text: likewise (the writer's pass over read 1 is the first   */
-                               /* look at read 1: ssd_emit_* report the exact size, ssd_get_stats has it afterwards)       */
+    uint64_t bytes_matched;    /* size of the SSD_EMIT_MATCHED text                                    */
+    uint64_t bytes_passing;    /* size of the SSD_EMIT_PASSING text                                    */
     uint64_t n_regular_keys, n_irregular_keys; /* (cell,UMI) keys: ACGT-only full-length UMIs / others */
 } ssd_stats;
 
@@ -95,12 +94,10 @@ const char *ssd_last_error(const ssd_ctx *ctx); /* ctx may be NULL: error of the
 /* cudaStream_t to enqueue on (0/NULL = the context's own stream). */
 int ssd_set_stream(ssd_ctx *ctx, void *cuda_stream);
 
-/* ---- phase 1: V2.demultiplex_fun's read-2 side (V2:270-337) ----------------------------------- */
-/* FASTQ record-boundary scan of READ 2, UMI/barcode extraction at the configured offsets, Hamming<=e first-hit
- * matching, per-cell read histogram, (cell,UMI) key capture, read-id fingerprints.  Read 1 is only registered here:
- * it is read ONCE, by the writer (phase 3), which finds its records, checks that every matched read-2 record meets a
- * read-1 record with the same id (V2:349-350: SSD_EKEY comes from ssd_emit_*, like SSD_EMALFORMED for read 1) and
- * writes the annotated text in the same pass.
+/* ---- phase 1: V2.demultiplex_fun minus the file writing (V2:207-358) ------------------------- */
+/* FASTQ record-boundary scan of both mates (read 2 first: UMI/barcode extraction at the configured offsets,
+ * Hamming<=e first-hit matching, per-cell read histogram, (cell,UMI) key capture, read-id fingerprints; then read 1:
+ * per-record tables for the writers and the mate-id check of V2:349-350 against read 2's fingerprints).
  * d_r1/d_r2 are DEVICE pointers, 16-byte aligned, to the whole text of the two files (or of the same
  * record range of both); they must stay valid and unchanged until the last ssd_emit of this batch.
  * Starts a new batch: previous per-batch results are discarded. */
@@ -190,11 +187,10 @@ int ssd_owner_layout(const ssd_ctx *ctx, int *shift, int *n_buckets);
 int ssd_key_layout(const ssd_ctx *ctx, int *umi_bits, int *cell_bits);
 
 /* Decide which cells pass from the (possibly all-reduced) histograms, apply the optional
- * RanHex->OligoDT collapse, count this batch's retained records.  Fills `stats` (may be NULL).  n_cells and
- * n_passing_cells count over the whole (all-reduced) histogram; the record counts are this batch's; bytes_* are upper
- * bounds (see ssd_stats) unless the batch is an annotated one. */
+ * RanHex->OligoDT collapse, size both outputs.  Fills `stats` (may be NULL).  n_cells and
+ * n_passing_cells count over the whole (all-reduced) histogram; the record counts are this batch's. */
 int ssd_build_filter(ssd_ctx *ctx, ssd_stats *stats);
-/* The statistics of the current batch as they stand now (after an ssd_emit_*: exact sizes, read 1's record count). */
+/* The statistics of the current batch as the last ssd_build_filter left them. */
 int ssd_get_stats(const ssd_ctx *ctx, ssd_stats *stats);
 
 /* Single-GPU convenience: ssd_local_unique_keys + ssd_count_distinct (distinct mode only) +
@@ -203,8 +199,7 @@ int ssd_filter_single(ssd_ctx *ctx, ssd_stats *stats);
 
 /* ---- phase 3: the writers, V2:134-141 + V2:367-370 and V2:415-454 ----------------------------- */
 /* Write the annotated FASTQ text of this batch, records in input order, into the DEVICE buffer d_out
- * (capacity `cap` bytes, any alignment).  *written receives the exact size of the text; SSD_ERANGE when it is larger
- * than `cap` (nothing is written past the end; cap >= stats.bytes_* of ssd_build_filter always suffices). */
+ * (capacity `cap` bytes, any alignment).  *written receives stats.bytes_matched / bytes_passing. */
 int ssd_emit_device(ssd_ctx *ctx, int which, void *d_out, size_t cap, size_t *written);
 
 /* Split mode (BASELINE config 5; bucket model of demultiplex_using_barcodes.py:350-372, one buffer per cell): the
@@ -217,8 +212,7 @@ int ssd_split_index(ssd_ctx *ctx, uint32_t *cells_host, uint64_t *offsets_host, 
 
 /* ---- host-buffer convenience (the end-to-end path) -------------------------------------------- */
 /* Whole pipeline on HOST buffers: chunked H2D into context-owned device staging, phases 1-3, D2H of
- * the selected output into `out` (capacity out_cap).  Pinned host memory makes the copies async.
- * out == NULL and out_cap == 0: stop after the filter; *written is then an upper bound of the output's size. */
+ * the selected output into `out` (capacity out_cap).  Pinned host memory makes the copies async. */
 int ssd_run_host(ssd_ctx *ctx, const void *r1, size_t r1_len, const void *r2, size_t r2_len, int which,
                  void *out, size_t out_cap, size_t *written, ssd_stats *stats);
 /* After ssd_run_host (or the phase calls): emit the selected output of the current batch into a HOST
@@ -238,12 +232,12 @@ int ssd_record_cells(ssd_ctx *ctx, int32_t *cells_host, uint64_t capacity, uint6
 
 /* ---- instrumentation -------------------------------------------------------------------------- */
 /* Pipeline stages for ssd_read_timings. */
-#define SSD_STAGE_SCAN_R1 0   /* table-building scan of read 1 (split mode, annotated input, table-driven writers) */
+#define SSD_STAGE_SCAN_R1 0   /* record-boundary scan of read 1: per-record tables for the writers, mate-id check */
 #define SSD_STAGE_SCAN_R2 1   /* scan of read 2 fused with extraction, matching, histogram, key capture */
 #define SSD_STAGE_DISTINCT 2  /* radix sort + unique + per-cell distinct-UMI count                       */
 #define SSD_STAGE_FILTER 3    /* pass decision, collapse map, output sizing                              */
 #define SSD_STAGE_PLAN 4      /* exclusive scan of output lengths                                        */
-#define SSD_STAGE_EMIT 5      /* the writer: the fused pass over read 1 (record scan + mate check + write)  */
+#define SSD_STAGE_EMIT 5      /* the writer                                                              */
 #define SSD_N_STAGES 6
 /* When enabled, every stage is bracketed by a CUDA-event pair on the context's stream. */
 int ssd_set_timing(ssd_ctx *ctx, int enabled);

@@ -101,9 +101,7 @@ struct ssd_ctx {
     uint32_t emit_grid = 148;
     uint64_t n_respec = 0;  // scans repeated without guessing (diagnostics)
     bool phase1_done = false, filter_done = false, unique_done = false;
-    bool r1_tables = false;  // the per-record tables of read 1 exist (split mode, table-driven writers, annotated input): made on demand
-    bool sized[2] = {false, false};  // stats.bytes_matched / bytes_passing are exact (else upper bounds): the text has been written once
-    uint32_t fused_grid = 148;
+    bool r1_tables = false;  // the per-record tables of read 1 (or of the annotated text) are in place
     int planned = -1;  // which output b_out_off currently describes (-1 = none)
     bool annotated = false;  // the batch is an already annotated FASTQ (V2.calc_demux_results)
     uint64_t n_buckets = 0;  // split mode: buckets of the last ssd_emit_split_device
@@ -824,10 +822,7 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
         CUB_(cudaFuncSetAttribute(k_emit_tiled<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
         CUB_(cudaFuncSetAttribute(k_emit_stream<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
         CUB_(cudaFuncSetAttribute(k_emit_stream<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
-        CUB_(cudaFuncSetAttribute(k_fused_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
         int per_sm = 0;
-        CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_r1, kFThreads, sizeof(FusedSmem)));
-        c->fused_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
         CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_stream<uint32_t>, kStreamThreads, sizeof(StreamSmem)));
         c->emit_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
         CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<kScanR2, uint32_t, true>, kScanThreads, sizeof(ScanSmem)));
@@ -962,18 +957,17 @@ int check_unmated_tail(ssd_ctx* c)
     return fail(c, SSD_EKEY, "%s", tok.c_str());
 }
 
-// Resets what a pass over read 1 reports: its line / record counts, the error state, its tile ticket, the emitted sizes.
+// Resets what the scan of read 1 reports: its line / record counts, the error state, its tile ticket.
 __global__ void k_reset_r1_pass(DevCounters* cnt, unsigned long long* err_off)
 {
     cnt->n_lines[0] = 0;
     cnt->n_records[0] = 0;
     cnt->err_flags = 0;
     cnt->ticket[0] = 0;
-    cnt->ticket_fused = 0;
-    cnt->emit_bytes = 0;
-    cnt->emit_records = 0;
     for (int k = 0; k < 4; k++) err_off[k] = ~0ull;
 }
+
+int ensure_r1_tables(ssd_ctx* c);
 
 int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, size_t r2_len, bool annotated)
 {
@@ -987,12 +981,11 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
     c->annotated = annotated;
     c->wide = std::max(r1_len, r2_len) >= (1ull << 32) || getenv("SSD_FORCE_WIDE") != nullptr;
     c->phase1_done = c->filter_done = c->unique_done = c->r1_tables = false;
-    c->sized[0] = c->sized[1] = false;
     c->planned = -1;
     if (std::max(r1_len, r2_len) >= (1ull << 36)) return fail(c, SSD_EINVAL, "a batch is limited to 64 GiB per file");
 
-    // Phase 1 is the scan of READ 2 alone (barcodes, UMIs, histogram, id fingerprints): read 1 is not touched before the
-    // writer's single pass over it (ssd_fused.cuh) or, for split mode, the table-building scan (ensure_r1_tables).
+    // Read 2 goes first (barcodes, UMIs, histogram, id fingerprints: it needs nothing from read 1), then the scan of read 1
+    // that leaves the per-record tables the writers work from and checks the mates' ids (ensure_r1_tables).
     // An annotated batch is one file: its scan leaves the per-record tables its writer needs.
     const size_t scan_len = annotated ? r1_len : r2_len;
     const uint32_t nt = blocks_for(scan_len, kTile);
@@ -1048,12 +1041,11 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
     c->stats.n_records_r2 = c->n_rec_r2;
     c->stats.n_regular_keys = c->n_keys;
     c->stats.n_irregular_keys = c->n_irr;
-    return SSD_OK;
+    return annotated ? SSD_OK : ensure_r1_tables(c);
 }
 
-// The per-record tables of read 1 (record starts, 16-byte descriptors, output-length contributions), made on demand by the
-// table-building scan: split mode and the table-driven writers need them, the fused pass does not.  Checks the mates' ids
-// against read 2's fingerprints on the way (V2:349-350).
+// The per-record tables of read 1 (record starts, 16-byte descriptors, output-length contributions) from its scan, which
+// checks the mates' ids against read 2's fingerprints on the way (V2:349-350).
 int ensure_r1_tables(ssd_ctx* c)
 {
     if (c->r1_tables) return SSD_OK;
@@ -1263,17 +1255,6 @@ extern "C" int ssd_count_distinct_owned(ssd_ctx* c, uint64_t* d_keys, uint64_t n
     return distinct_counts_arrays(c, d_keys, n_keys, (const IrrKey*)d_irregular, n_irregular, rank, world);
 }
 
-namespace {
-// Upper bound of an output's size before it has been written: an output record is at most 38 bytes longer than its read-1
-// record (the header only loses bytes, "_" + 24 barcode bytes + "_" + UMI (<= 10) + the "+" line's remainder).
-uint64_t output_bound(const ssd_ctx* c, int which)
-{
-    if (c->sized[which]) return which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
-    const uint64_t n = which == SSD_EMIT_MATCHED ? c->stats.n_matched : c->stats.n_retained;
-    return n ? (uint64_t)c->r1_len + 38ull * n + 64 : 0;
-}
-}  // namespace
-
 extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
 {
     if (!c) return SSD_EINVAL;
@@ -1287,11 +1268,9 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
     k_filter<<<nbc, kThreads, 0, c->stream>>>(c->d_hist, c->d_distinct, c->n_cells_total, (long long)c->cfg.min_count, c->cfg.filter_mode, c->d_pass,
                                               c->d_cnt);
     if (c->cfg.collapse_pairs > 0) k_collapse_map<<<nbc, kThreads, 0, c->stream>>>(c->d_pass, c->dcfg.n_wl, c->cfg.collapse_pairs, c->d_remap);
-    c->sized[SSD_EMIT_PASSING] = false;  // the set of passing cells may have changed
-    c->planned = -1;
-    if (c->r1_tables) {
-        // the per-record tables exist (annotated input, or split mode ran before): exclusive scan of the post-filter output
-        // lengths; its first kernel also counts the retained records and sizes the pre-filter output
+    {
+        // exclusive scan of the post-filter output lengths; its first kernel also counts the retained records
+        // and sizes the pre-filter output
         const uint32_t nb = (uint32_t)(c->n_rec / kScanBlock + 1);
         OKR(ensure(c, c->b_bsums, ((size_t)nb + 2) * sizeof(unsigned long long)));
         OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
@@ -1300,10 +1279,6 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
         CU(c, cudaMemsetAsync(bs, 0, ((size_t)nb + 2) * sizeof(unsigned long long), c->stream));
         k_plan_onepass<<<nb, kThreads, 0, c->stream>>>(f, c->n_rec, (unsigned long long*)c->b_out_off.p, bs + 1, (uint32_t*)bs, c->d_cnt);
         c->planned = SSD_EMIT_PASSING;
-    } else if (c->n_rec_r2) {
-        // read 1 has not been looked at: only the number of retained records is known (the sizes follow from the writer's pass)
-        k_count_retained<<<(uint32_t)std::min<uint64_t>(blocks_for(c->n_rec_r2, kThreads), 148 * 8), kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, c->n_rec_r2,
-                                                                                                                          c->d_pass, c->d_cnt);
     }
     CU(c, cudaGetLastError());
     OKR(fetch_counters(c, &h));
@@ -1311,14 +1286,8 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
     c->stats.n_cells = h.n_cells;
     c->stats.n_passing_cells = h.n_passing_cells;
     c->stats.n_retained = h.n_retained;
-    if (c->r1_tables) {
-        c->stats.bytes_matched = h.bytes_matched;
-        c->stats.bytes_passing = h.bytes_passing;
-        c->sized[0] = c->sized[1] = true;
-    } else {
-        c->stats.bytes_matched = output_bound(c, SSD_EMIT_MATCHED);
-        c->stats.bytes_passing = output_bound(c, SSD_EMIT_PASSING);
-    }
+    c->stats.bytes_matched = h.bytes_matched;
+    c->stats.bytes_passing = h.bytes_passing;
     c->filter_done = true;
     if (stats) *stats = c->stats;
     return SSD_OK;
@@ -1353,96 +1322,23 @@ extern "C" int ssd_filter_single(ssd_ctx* c, ssd_stats* stats)
 // ================================================================================================
 // phase 3
 // ================================================================================================
-namespace {
-// The merged outputs in ONE pass over read 1 (ssd_fused.cuh): record boundaries, mate check, header rewrite and the
-// prefix-sum-compacted write, straight from the read-2 annotations and the per-cell pass table.
-int emit_fused(ssd_ctx* c, int which, uint8_t* d_out, size_t cap, size_t* written)
-{
-    const uint32_t nt = blocks_for(c->r1_len, kFTile);
-    DevCounters h{};
-    if (nt) {
-        OKR(ensure(c, c->b_status1, (size_t)(nt + 1) * 8));
-        OKR(ensure(c, c->b_status3, (size_t)(nt + 1) * 8));
-        k_reset_r1_pass<<<1, 1, 0, c->stream>>>(c->d_cnt, c->d_err_off);
-        CU(c, cudaMemsetAsync(c->b_status1.p, 0, (size_t)(nt + 1) * 8, c->stream));
-        CU(c, cudaMemsetAsync(c->b_status3.p, 0, (size_t)(nt + 1) * 8, c->stream));
-        FusedArgs a{};
-        a.buf = c->r1;
-        a.len = c->r1_len;
-        a.st1 = (unsigned long long*)c->b_status1.p;
-        a.st2 = (unsigned long long*)c->b_status3.p;
-        a.n_tiles = nt;
-        a.cnt = c->d_cnt;
-        a.err_off = c->d_err_off;
-        a.ann = (const uint64_t*)c->b_ann.p;
-        a.r2_tok = (const unsigned long long*)c->b_r2_tok.p;
-        a.n_rec_r2 = c->n_rec_r2;
-        a.pass = which == SSD_EMIT_PASSING ? c->d_pass : nullptr;
-        a.remap = (which == SSD_EMIT_PASSING && c->cfg.collapse_pairs > 0) ? c->d_remap : nullptr;
-        a.r2buf = c->r2;
-        a.wl64 = c->d_wl64;
-        a.out = d_out;
-        a.cap = cap;
-        {
-            StageTimer t(c, 5);
-            k_fused_r1<<<std::min<uint32_t>(nt, c->fused_grid), kFThreads, sizeof(FusedSmem), c->stream>>>(a, c->dcfg);
-        }
-        c->n_launches += 2;
-        CU(c, cudaGetLastError());
-        OKR(fetch_counters(c, &h));
-    }
-    if (h.err_flags & kErrEmitLen) return fail(c, SSD_ECUDA, "internal: emitted record length differs from the planned length");
-    OKR(report_errors(c, h.err_flags));
-    c->n_rec_r1 = h.n_records[0];
-    c->n_rec = std::min(c->n_rec_r1, c->n_rec_r2);
-    c->stats.n_records_r1 = c->n_rec_r1;
-    OKR(check_unmated_tail(c));
-    (which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing) = h.emit_bytes;
-    c->sized[which] = true;
-    if (written) *written = (size_t)h.emit_bytes;
-    if (h.err_flags & kErrRange) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)h.emit_bytes, cap);
-    const uint64_t want = which == SSD_EMIT_MATCHED ? c->stats.n_matched : c->stats.n_retained;
-    if (h.emit_records != want) return fail(c, SSD_ECUDA, "internal: %llu records written, %llu expected", (unsigned long long)h.emit_records, (unsigned long long)want);
-    return SSD_OK;
-}
-
-inline bool use_fused(const ssd_ctx* c)
-{
-    static const bool legacy = getenv("SSD_EMIT_TABLES") != nullptr;  // the table-driven writers (read-1 scan + plan + writer), for comparison
-    return !c->annotated && c->dcfg.bc8 && !legacy;
-}
-}  // namespace
-
 extern "C" int ssd_emit_device(ssd_ctx* c, int which, void* d_out, size_t cap, size_t* written)
 {
     if (!c) return SSD_EINVAL;
     if (!c->filter_done) return fail(c, SSD_ESTATE, "ssd_emit_device before ssd_build_filter");
     if (which != SSD_EMIT_MATCHED && which != SSD_EMIT_PASSING) return fail(c, SSD_EINVAL, "unknown output selector");
     CU(c, cudaSetDevice(c->device));
-    if (written) *written = 0;
-    if (use_fused(c)) {
-        if (!d_out && cap) return fail(c, SSD_EINVAL, "null output pointer");
-        return emit_fused(c, which, (uint8_t*)d_out, d_out ? cap : 0, written);
-    }
-    // table-driven: per-record tables of read 1, exclusive scan of the output lengths, writer
-    OKR(ensure_r1_tables(c));
-    if (c->planned != which || !c->sized[which]) {
-        StageTimer t(c, 4);
-        OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
-        OKR(exclusive_scan<unsigned long long>(c, make_outlen(c, which), c->n_rec, (unsigned long long*)c->b_out_off.p));
-        c->planned = which;
-        unsigned long long total = 0;
-        CU(c, cudaMemcpyAsync(&total, (unsigned long long*)c->b_out_off.p + c->n_rec, sizeof total, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-        (which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing) = total;
-        c->sized[which] = true;
-    }
     const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
     if (written) *written = (size_t)need;
     if (need > cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, cap);
     if (need == 0) return SSD_OK;
     if (!d_out) return fail(c, SSD_EINVAL, "null output pointer");
-    CU(c, cudaMemsetAsync(&c->d_cnt->err_flags, 0, sizeof(unsigned int), c->stream));
+    if (c->planned != which) {
+        StageTimer t(c, 4);
+        OKR(ensure(c, c->b_out_off, (c->n_rec + 1) * sizeof(uint64_t)));
+        OKR(exclusive_scan<unsigned long long>(c, make_outlen(c, which), c->n_rec, (unsigned long long*)c->b_out_off.p));
+        c->planned = which;
+    }
     OKR(c->wide ? launch_emit<uint64_t>(c, which, (uint8_t*)d_out) : launch_emit<uint32_t>(c, which, (uint8_t*)d_out));
     DevCounters h{};
     OKR(fetch_counters(c, &h));
@@ -1456,13 +1352,14 @@ extern "C" int ssd_emit_split_device(ssd_ctx* c, void* d_out, size_t cap, size_t
     if (!c) return SSD_EINVAL;
     if (!c->filter_done) return fail(c, SSD_ESTATE, "ssd_emit_split_device before ssd_build_filter");
     CU(c, cudaSetDevice(c->device));
-    OKR(ensure_r1_tables(c));  // buckets are written through per-record tables of read 1
-    const uint64_t n = c->stats.n_retained;
-    if (written) *written = 0;
+    const uint64_t need = c->stats.bytes_passing, n = c->stats.n_retained;
+    if (written) *written = (size_t)need;
     if (n_buckets) *n_buckets = 0;
     c->n_buckets = 0;
-    c->split_bytes = 0;
+    c->split_bytes = need;
+    if (need > cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, cap);
     if (n == 0) return SSD_OK;
+    if (!d_out) return fail(c, SSD_EINVAL, "null output pointer");
     if (n >= (1ull << 32)) return fail(c, SSD_EINVAL, "split mode is limited to 2^32 records per batch");
     OutLen f = make_outlen(c, SSD_EMIT_PASSING);
     // 1. (cell, record) pairs of the written records, in input order
@@ -1483,15 +1380,6 @@ extern "C" int ssd_emit_split_device(ssd_ctx* c, void* d_out, size_t cap, size_t
     // 3. byte offsets in bucket order, 4. the writer through the permutation
     unsigned long long* off = (unsigned long long*)c->b_sp_off.p;
     OKR(exclusive_scan<unsigned long long>(c, SplitLen{f, order}, n, off));
-    unsigned long long need = 0;
-    CU(c, cudaMemcpyAsync(&need, off + n, sizeof need, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    c->stats.bytes_passing = need;  // the buckets hold the post-filter text, regrouped
-    c->sized[SSD_EMIT_PASSING] = true;
-    c->split_bytes = need;
-    if (written) *written = (size_t)need;
-    if (need > cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, cap);
-    if (!d_out) return fail(c, SSD_EINVAL, "null output pointer");
     OKR(c->wide ? launch_emit<uint64_t>(c, SSD_EMIT_PASSING, (uint8_t*)d_out, order, off, n)
                 : launch_emit<uint32_t>(c, SSD_EMIT_PASSING, (uint8_t*)d_out, order, off, n));
     // 5. bucket table
@@ -1555,15 +1443,12 @@ extern "C" int ssd_emit_host(ssd_ctx* c, int which, void* out, size_t out_cap, s
     if (!c) return SSD_EINVAL;
     if (!c->filter_done) return fail(c, SSD_ESTATE, "ssd_emit_host before the filter was built");
     if (which != SSD_EMIT_MATCHED && which != SSD_EMIT_PASSING) return fail(c, SSD_EINVAL, "unknown output selector");
-    const uint64_t bound = output_bound(c, which);  // exact once the text has been written before
-    if (written) *written = (size_t)bound;
-    if (!bound) return SSD_OK;
-    OKR(ensure(c, c->b_out, bound + 32));
-    size_t need = 0;
-    OKR(ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, &need));
-    if (written) *written = need;
+    const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
+    if (written) *written = (size_t)need;
     if (need > out_cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, out_cap);
     if (!need) return SSD_OK;
+    OKR(ensure(c, c->b_out, need + 32));
+    OKR(ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, nullptr));
     std::lock_guard<std::mutex> turn(g_d2h_turn);
     CU(c, cudaMemcpyAsync(out, c->b_out.p, need, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -1590,12 +1475,10 @@ extern "C" int ssd_run_host(ssd_ctx* c, const void* r1, size_t r1_len, const voi
     OKR(ssd_demux_device(c, c->b_in1.p, r1_len, c->b_in2.p, r2_len));
     OKR(ssd_filter_single(c, stats));
     if (!out && !out_cap) {
-        if (written) *written = (size_t)output_bound(c, which);  // an upper bound: ssd_emit_host reports the exact size
+        if (written) *written = (size_t)(which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing);
         return SSD_OK;
     }
-    const int rc = ssd_emit_host(c, which, out, out_cap, written);
-    if (stats) *stats = c->stats;  // now with the exact sizes and read 1's record count
-    return rc;
+    return ssd_emit_host(c, which, out, out_cap, written);
 }
 
 // ================================================================================================
@@ -1719,23 +1602,21 @@ int open_input(ssd_ctx* c, const char* path, int* fd, size_t* size)
 // emit `which` on the device, then download it with four threads, each overlapping its copies with its pwrites
 int download_to_file(ssd_ctx* c, int which, const char* out_path, int append, size_t* written)
 {
-    const uint64_t bound = output_bound(c, which);
-    if (written) *written = 0;
+    const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
+    if (written) *written = (size_t)need;
     const int fd = open(out_path, O_WRONLY | O_CREAT | (append ? 0 : O_TRUNC), 0644);
     if (fd < 0) return fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
     const off_t base = append ? lseek(fd, 0, SEEK_END) : 0;  // V2:367, 415 open in append mode
     int rc = base < 0 ? fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno)) : SSD_OK;
-    if (bound && rc == SSD_OK) {
-        size_t need = 0;
-        rc = ensure(c, c->b_out, bound + 32);
-        if (rc == SSD_OK) rc = ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, &need);
+    if (need && rc == SSD_OK) {
+        rc = ensure(c, c->b_out, need + 32);
+        if (rc == SSD_OK) rc = ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, nullptr);
         for (int k = 0; k < 4 && rc == SSD_OK; k++) rc = c->io[k].init();
         if (rc == SSD_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, SSD_ECUDA, "emit failed");  // the emit kernel ran on the context's stream
-        if (rc == SSD_OK && need) {
+        if (rc == SSD_OK) {
             std::lock_guard<std::mutex> turn(g_d2h_turn);
-            rc = run_lanes(c, out_path, 0, 4, download_file_worker, c->device, fd, (size_t)base, need, (const uint8_t*)c->b_out.p);
+            rc = run_lanes(c, out_path, 0, 4, download_file_worker, c->device, fd, (size_t)base, (size_t)need, (const uint8_t*)c->b_out.p);
         }
-        if (rc == SSD_OK && written) *written = need;
     }
     if (close(fd) != 0 && rc == SSD_OK) rc = fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
     return rc;
@@ -1768,9 +1649,7 @@ extern "C" int ssd_run_files(ssd_ctx* c, const char* path_r1, const char* path_r
     if (rc != SSD_OK) return rc;
     OKR(ssd_demux_device(c, c->b_in1.p, size[0], c->b_in2.p, size[1]));
     OKR(ssd_filter_single(c, stats));
-    rc = download_to_file(c, which, out_path, append, written);
-    if (stats) *stats = c->stats;  // now with the exact sizes and read 1's record count
-    return rc;
+    return download_to_file(c, which, out_path, append, written);
 }
 
 extern "C" int ssd_annotated_file(ssd_ctx* c, const char* path_in, const char* out_path, int append, size_t* written, ssd_stats* stats)
@@ -2319,19 +2198,6 @@ extern "C" int ssd_scan_repeats(const ssd_ctx* c, uint64_t* n)
 }
 
 extern "C" uint64_t ssd_launch_count(const ssd_ctx* c) { return c ? c->n_launches : 0; }
-
-#ifdef SSD_FUSED_PROFILE
-// debug builds only: clock totals of the fused pass per stage and wait reason (see ssd_fused.cuh)
-extern "C" int ssd_debug_fused_profile(unsigned long long* out16, int reset)
-{
-    if (out16 && cudaMemcpyFromSymbol(out16, ssd::g_fused_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return SSD_ECUDA;
-    if (reset) {
-        unsigned long long z[16] = {0};
-        if (cudaMemcpyToSymbol(ssd::g_fused_prof, z, sizeof z) != cudaSuccess) return SSD_ECUDA;
-    }
-    return SSD_OK;
-}
-#endif
 
 #ifdef SSD_SCAN_PROFILE
 // debug builds only: per-phase clock totals of the scan kernels (phases 0..4, tiles in [7]) for read 1 / read 2

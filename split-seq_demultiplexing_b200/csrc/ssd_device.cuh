@@ -69,7 +69,6 @@ constexpr uint32_t kErrIndex = 64u;       // annotated header without two '_' (t
 constexpr uint32_t kErrRespec = 256u;     // read-1 (<< 1: read-2) scan guessed the record phase of a tile wrong or met a tile with more
                                           // records than it can park: the host repeats that scan with the variant that waits instead
 constexpr uint32_t kErrForeign = 128u;    // annotated header whose cell / UMI fields cannot come from this whitelist
-constexpr uint32_t kErrRange = 1024u;     // the output buffer is smaller than the text (nothing is written past its end)
 
 struct DevCounters {
     unsigned long long n_lines[2];     // total lines of read 1 / read 2
@@ -78,11 +77,9 @@ struct DevCounters {
     unsigned long long n_irr;          // irregular keys appended
     unsigned int err_flags;
     unsigned int ticket[2];            // dynamic tile tickets of the two scans
-    unsigned int ticket_fused;         // ... and of the fused read-1 pass
+    unsigned int pad;
     // produced by ssd_build_filter; zeroed as one block starting at n_matched
     unsigned long long n_matched, bytes_matched, bytes_passing, n_retained, n_cells, n_passing_cells;
-    // produced by the fused read-1 pass (zeroed before every launch): size of the text it wrote, records in it
-    unsigned long long emit_bytes, emit_records;
 };
 
 // ---------------------------------------------------------------------------------------------

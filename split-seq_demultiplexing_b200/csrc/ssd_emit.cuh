@@ -587,6 +587,13 @@ __global__ void k_bucket_table(const uint64_t* cells, const uint32_t* bpos, cons
     }
 }
 
+// Error path of the mate check (V2:349-350): the first matched read-2 record at or after record `from` (read 1 ended there).
+__global__ void k_first_matched_from(const uint64_t* ann, uint64_t from, uint64_t n, unsigned long long* err_rec)
+{
+    for (uint64_t r = from + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
+        if (ann_state(ann[r]) != 0u) atomicMin(err_rec, (unsigned long long)r);
+}
+
 __global__ void k_record_cells(const uint64_t* ann, uint64_t n, int32_t* cells)
 {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -6,4 +6,3 @@
 #include "ssd_scan.cuh"
 #include "ssd_emit.cuh"
 #include "ssd_emit_tiled.cuh"
-#include "ssd_fused.cuh"

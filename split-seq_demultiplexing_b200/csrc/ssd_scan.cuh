@@ -6,11 +6,10 @@
 // indices: decoupled look-back) and lists the line starts; stage B processes every record that starts in the tile,
 // one thread per record, from shared memory:
 //   read 2: UMI / barcode extraction (V2:293-301), first-hit Hamming matching (V2:302-304, 327-329), per-cell
-//           histogram, (cell, UMI) keys, and the read-id fingerprint the read-1 pass checks (V2:349-350).
+//           histogram, (cell, UMI) keys, and the read-id fingerprint the read-1 scan checks (V2:349-350).
 //           Read 2 is scanned FIRST: it needs nothing from read 1.
-//   read 1: (only for split mode and the table-driven writers; the merged outputs are written by the fused pass of
-//           ssd_fused.cuh, which scans read 1 itself) record offset + a 16-byte descriptor the writer needs
-//           (V2:134-141, 246, 249), mate-id check against read 2's fingerprints
+//   read 1: record offset + a 16-byte descriptor the writer needs (V2:134-141, 246, 249), mate-id check against read 2's
+//           fingerprints (V2:350)
 //   annotated input (MergedCells_1.fastq, V2:389-404): cell / UMI parsed back from the header
 // The per-record code is written to stay convergent: line boundaries come from a per-tile list of line
 // starts (no searching), headers and barcode windows are handled four bytes at a time with

@@ -22,7 +22,7 @@ def sources():
 HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "ssd_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "186"]  # 186: comparisons that are constant in some template instances
 
 OK, EINVAL, ECUDA, EKEY, EMALFORMED, ENOMEM, ESTATE, ERANGE, EINDEX, EIO = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9
 FILTER_DISTINCT_UMI, FILTER_READS = 0, 1

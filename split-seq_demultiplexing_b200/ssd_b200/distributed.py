@@ -220,8 +220,6 @@ def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None, 
         sync()
         st = dm.build_filter()
         emit(batch, st)
-        if hasattr(dm, "stats"):
-            st = dm.stats()  # the writer's pass has sized the output exactly and counted read 1's records
         for key, v in st.items():
             total[key] = v if key in ("n_cells", "n_passing_cells") else total.get(key, 0) + v
         sync()

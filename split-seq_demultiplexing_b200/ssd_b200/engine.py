@@ -179,15 +179,12 @@ class Demultiplexer:
         return st.as_dict()
 
     def stats(self) -> dict:
-        """The statistics of the current batch as they stand now.  bytes_matched / bytes_passing are upper bounds until the
-        text in question has been written once: read 1 is first looked at by the writer's pass (include/ssd_b200.h)."""
+        """The statistics of the current batch as the last filter left them."""
         st = L.Stats()
         self._check(self.lib.ssd_get_stats(self._ctx, C.byref(st)))
         return st.as_dict()
 
     def emit_device(self, which: int, out_ptr: int, cap: int) -> int:
-        """Phase 3: one pass over read 1 (record scan, mate check V2:349-350, header rewrite, compacted write).  Returns the
-        exact size of the text; cap >= the bytes_* figure of the filter's statistics always suffices."""
         n = C.c_size_t()
         self._check(self.lib.ssd_emit_device(self._ctx, which, C.c_void_p(out_ptr), cap, C.byref(n)))
         return n.value
@@ -221,7 +218,7 @@ class Demultiplexer:
         import torch
         from . import hostlogic
         stats = stats or self.build_filter()
-        out = torch.empty(int(stats["bytes_passing"]) + 16, dtype=torch.uint8, device="cuda")  # an upper bound before the first write
+        out = torch.empty(int(stats["bytes_passing"]) + 16, dtype=torch.uint8, device="cuda")
         n, table, _ = self.emit_split_device(out.data_ptr(), out.numel())
         host = out[:n].cpu().numpy()
         del out
@@ -276,7 +273,7 @@ class Demultiplexer:
         self.set_stream(handle)
         self.demux_device(r1.data_ptr(), r1.numel(), r2.data_ptr(), r2.numel(), keep=(r1, r2))
         stats = self.filter_single()
-        need = stats["bytes_matched"] if which == L.EMIT_MATCHED else stats["bytes_passing"]  # an upper bound
+        need = stats["bytes_matched"] if which == L.EMIT_MATCHED else stats["bytes_passing"]
         out = torch.empty(need + 16, dtype=torch.uint8, device=r1.device)
         n = self.emit_device(which, out.data_ptr(), out.numel())
         return out[:n], self.stats()
@@ -291,13 +288,13 @@ class Demultiplexer:
         n = C.c_size_t()
         args = (self._ctx, a1.ctypes.data_as(C.c_void_p), a1.size, a2.ctypes.data_as(C.c_void_p), a2.size, which)
         if out is not None and out.size:
-            # the caller's buffer (pinned, reused): everything in one call; too small -> the exact size is known afterwards
+            # the caller's buffer (pinned, reused): everything in one call
             rc = self.lib.ssd_run_host(*args, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n), C.byref(st))
             if rc != L.ERANGE:
                 self._check(rc)
                 return out[: n.value], self.stats()
         else:
-            self._check(self.lib.ssd_run_host(*args, None, 0, C.byref(n), C.byref(st)))  # n: an upper bound of the output's size
+            self._check(self.lib.ssd_run_host(*args, None, 0, C.byref(n), C.byref(st)))
         out = np.empty(n.value, dtype=np.uint8)
         if n.value:
             self._check(self.lib.ssd_emit_host(self._ctx, which, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)))

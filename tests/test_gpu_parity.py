@@ -41,7 +41,7 @@ def digests():
 def run_both(ssd, r1, r2, e, m, **kw):
     dm = ssd.Demultiplexer(WL, errors=e, min_count=m, **kw)
     passing, stats = dm.run_host(r1, r2, ssd.EMIT_PASSING)
-    merged = np.empty(stats["bytes_matched"], dtype=np.uint8)  # an upper bound until that text has been written
+    merged = np.empty(stats["bytes_matched"], dtype=np.uint8)
     import ctypes as C
     n = C.c_size_t()
     if merged.size:
@@ -360,7 +360,7 @@ def test_scan_without_guessing_matches(ssd, orc, monkeypatch):
 def test_misleading_lines_repeat_the_scan(ssd, orc):
     """Quality lines that start with '@' followed two lines later by a read that starts with '+' cannot be told from a
     record start inside one tile: the read-2 scan's guess fails, the library repeats that scan without guessing, results
-    stay exact (the '+' is part of the UMI, which is copied verbatim: V2:295).  The pass over read 1 never guesses."""
+    stay exact (the '+' is part of the UMI, which is copied verbatim: V2:295)."""
     recs1, recs2 = [], []
     for i in range(6000):
         s2 = "+CGTACGTAC" + WL[i % 96] + fu.LINKER_3_2 + WL[(i * 5) % 96] + fu.LINKER_2_1 + WL[(i * 11) % 96] + "ACGT" * 10
