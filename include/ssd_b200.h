@@ -95,9 +95,8 @@ const char *ssd_last_error(const ssd_ctx *ctx); /* ctx may be NULL: error of the
 int ssd_set_stream(ssd_ctx *ctx, void *cuda_stream);
 
 /* ---- phase 1: V2.demultiplex_fun minus the file writing (V2:207-358) ------------------------- */
-/* FASTQ record-boundary scan of both mates (read 2 first: UMI/barcode extraction at the configured offsets,
- * Hamming<=e first-hit matching, per-cell read histogram, (cell,UMI) key capture, read-id fingerprints; then read 1:
- * per-record tables for the writers and the mate-id check of V2:349-350 against read 2's fingerprints).
+/* FASTQ record-boundary scan of both mates, UMI/barcode extraction at the configured offsets,
+ * Hamming<=e first-hit matching, mate-id check, per-cell read histogram, (cell,UMI) key capture.
  * d_r1/d_r2 are DEVICE pointers, 16-byte aligned, to the whole text of the two files (or of the same
  * record range of both); they must stay valid and unchanged until the last ssd_emit of this batch.
  * Starts a new batch: previous per-batch results are discarded. */
@@ -199,7 +198,7 @@ int ssd_filter_single(ssd_ctx *ctx, ssd_stats *stats);
 
 /* ---- phase 3: the writers, V2:134-141 + V2:367-370 and V2:415-454 ----------------------------- */
 /* Write the annotated FASTQ text of this batch, records in input order, into the DEVICE buffer d_out
- * (capacity `cap` bytes, any alignment).  *written receives stats.bytes_matched / bytes_passing. */
+ * (capacity `cap` bytes, 16-byte aligned).  *written receives stats.bytes_matched / bytes_passing. */
 int ssd_emit_device(ssd_ctx *ctx, int which, void *d_out, size_t cap, size_t *written);
 
 /* Split mode (BASELINE config 5; bucket model of demultiplex_using_barcodes.py:350-372, one buffer per cell): the
@@ -232,7 +231,7 @@ int ssd_record_cells(ssd_ctx *ctx, int32_t *cells_host, uint64_t capacity, uint6
 
 /* ---- instrumentation -------------------------------------------------------------------------- */
 /* Pipeline stages for ssd_read_timings. */
-#define SSD_STAGE_SCAN_R1 0   /* record-boundary scan of read 1: per-record tables for the writers, mate-id check */
+#define SSD_STAGE_SCAN_R1 0   /* record-boundary scan of read 1 + output-length planning              */
 #define SSD_STAGE_SCAN_R2 1   /* scan of read 2 fused with extraction, matching, histogram, key capture */
 #define SSD_STAGE_DISTINCT 2  /* radix sort + unique + per-cell distinct-UMI count                       */
 #define SSD_STAGE_FILTER 3    /* pass decision, collapse map, output sizing                              */

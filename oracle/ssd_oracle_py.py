@@ -105,10 +105,17 @@ def _cfg(whitelist: List[str], e: int, bin_reads: int, positions: Optional[dict]
     return cfg
 
 
+def _bytes_at(ptr, n: int) -> bytes:
+    """n bytes at a C pointer (ctypes.string_at stops at 2 GiB; the full-size comparisons are larger)."""
+    if not n:
+        return b""
+    return bytes((C.c_char * n).from_address(C.cast(ptr, C.c_void_p).value))
+
+
 def _collect(out: _Out, want_rec_cell: bool) -> OracleResult:
     res = OracleResult()
-    res.merged1 = C.string_at(out.merged1, out.merged1_len) if out.merged1_len else b""
-    res.passing = C.string_at(out.passing, out.passing_len) if out.passing_len else b""
+    res.merged1 = _bytes_at(out.merged1, out.merged1_len)
+    res.passing = _bytes_at(out.passing, out.passing_len)
     res.n_records, res.n_matched, res.n_retained = out.n_records, out.n_matched, out.n_retained
     res.n_cells, res.n_passing_cells = out.n_cells, out.n_passing_cells
     if want_rec_cell and out.n_records:

@@ -7,7 +7,6 @@
 #   bash profiles/ab_variants.sh clean
 VARIANTS=(
   "base||0"
-  "regmask|-DSSD_SCAN_REGMASK|1"
 )
 root=$(cd "$(dirname "$0")/.." && pwd)
 src=$root/split-seq_demultiplexing_b200/csrc

@@ -95,13 +95,12 @@ struct ssd_ctx {
     const uint8_t* r2 = nullptr;
     size_t r1_len = 0, r2_len = 0;
     bool wide = false;  // 64-bit record offsets
-    uint64_t rec_cap = 0, rec_cap_r1 = 0;  // capacity of the per-record arrays of phase 1 / of the read-1 tables
+    uint64_t rec_cap = 0;
     uint64_t n_rec_r1 = 0, n_rec_r2 = 0, n_rec = 0, n_keys = 0, n_irr = 0;
     bool defer1 = true, defer2 = true;  // scan variant per file: park-and-commit, or (after a failed guess) wait for the line index
     uint32_t emit_grid = 148;
     uint64_t n_respec = 0;  // scans repeated without guessing (diagnostics)
     bool phase1_done = false, filter_done = false, unique_done = false;
-    bool r1_tables = false;  // the per-record tables of read 1 (or of the annotated text) are in place
     int planned = -1;  // which output b_out_off currently describes (-1 = none)
     bool annotated = false;  // the batch is an already annotated FASTQ (V2.calc_demux_results)
     uint64_t n_buckets = 0;  // split mode: buckets of the last ssd_emit_split_device
@@ -112,7 +111,7 @@ struct ssd_ctx {
     uint64_t n_uniq_irr = 0;
     ssd_stats stats{};
 
-    DevBuf b_status1, b_status2, b_status3, b_r1_start, b_r1_meta, b_r1_base, b_r2_tok, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
+    DevBuf b_status1, b_status2, b_r1_start, b_r1_meta, b_r1_base, b_r1_tok, b_ann, b_keys, b_keys_alt, b_irr, b_irr_alt, b_perm, b_perm_alt, b_tmp64a,
         b_tmp64b, b_counts, b_offsets, b_bsums, b_pos, b_out_off, b_cells;
     DevBuf b_in1, b_in2, b_out;
     size_t loaded[2] = {0, 0};  // bytes ssd_load_file_range put into b_in1 / b_in2
@@ -542,7 +541,7 @@ int distinct_counts_local(ssd_ctx* c)
 }
 
 template <typename OffT>
-ScanArgs<OffT> scan_args(ssd_ctx* c)
+int launch_scans(ssd_ctx* c, bool defer1, bool defer2)
 {
     ScanArgs<OffT> a{};
     a.cnt = c->d_cnt;
@@ -551,66 +550,47 @@ ScanArgs<OffT> scan_args(ssd_ctx* c)
     a.r1_start = (OffT*)c->b_r1_start.p;
     a.r1_meta = (uint4*)c->b_r1_meta.p;
     a.r1_base = (uint32_t*)c->b_r1_base.p;
-    a.r2_tok = (unsigned long long*)c->b_r2_tok.p;
+    a.r1_tok = (unsigned long long*)c->b_r1_tok.p;
     a.r1buf = c->r1;
     a.r1_len = c->r1_len;
     a.ann = (uint64_t*)c->b_ann.p;
     a.hist = c->d_hist;
     a.irr = (IrrKey*)c->b_irr.p;
     a.lut = c->d_lut;
-    return a;
-}
 
-// phase 1: the read-2 scan (or, for an annotated batch, the scan of the annotated text)
-template <typename OffT>
-int launch_scan_phase1(ssd_ctx* c, bool defer)
-{
-    ScanArgs<OffT> a = scan_args<OffT>(c);
+    const uint32_t nt1 = blocks_for(c->r1_len, kTile), nt2 = c->annotated ? 0u : blocks_for(c->r2_len, kTile);
     if (c->annotated) {
-        const uint32_t nt1 = blocks_for(c->r1_len, kTile);
         if (nt1) {
             a.buf = c->r1;
             a.len = c->r1_len;
             a.status = (unsigned long long*)c->b_status1.p;
             a.n_tiles = nt1;
             StageTimer t(c, 0);
-            if (defer) k_scan<kScanAnn, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+            if (defer1) k_scan<kScanAnn, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
             else k_scan<kScanAnn, OffT, false><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
             c->n_launches++;
         }
         CU(c, cudaGetLastError());
         return SSD_OK;
     }
-    const uint32_t nt2 = blocks_for(c->r2_len, kTile);
-    if (nt2) {
-        a.buf = c->r2;
-        a.len = c->r2_len;
-        a.status = (unsigned long long*)c->b_status2.p;
-        a.n_tiles = nt2;
-        StageTimer t(c, 1);
-        if (defer) k_scan<kScanR2, OffT, true><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
-        else k_scan<kScanR2, OffT, false><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
-        c->n_launches++;
-    }
-    CU(c, cudaGetLastError());
-    return SSD_OK;
-}
-
-// the read-1 scan that leaves per-record tables (split mode, table-driven writers); read 2 has been scanned
-template <typename OffT>
-int launch_scan_r1(ssd_ctx* c, bool defer)
-{
-    ScanArgs<OffT> a = scan_args<OffT>(c);
-    a.rec_cap = c->rec_cap_r1;
-    const uint32_t nt1 = blocks_for(c->r1_len, kTile);
     if (nt1) {
         a.buf = c->r1;
         a.len = c->r1_len;
         a.status = (unsigned long long*)c->b_status1.p;
         a.n_tiles = nt1;
         StageTimer t(c, 0);
-        if (defer) k_scan<kScanR1, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        if (defer1) k_scan<kScanR1, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         else k_scan<kScanR1, OffT, false><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        c->n_launches++;
+    }
+    if (nt2) {
+        a.buf = c->r2;
+        a.len = c->r2_len;
+        a.status = (unsigned long long*)c->b_status2.p;
+        a.n_tiles = nt2;
+        StageTimer t(c, 1);
+        if (defer2) k_scan<kScanR2, OffT, true><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        else k_scan<kScanR2, OffT, false><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         c->n_launches++;
     }
     CU(c, cudaGetLastError());
@@ -829,7 +809,7 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
         c->scan_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
     }
     CUB_(cudaMalloc(&c->d_cnt, sizeof(DevCounters)));
-    CUB_(cudaMalloc(&c->d_err_off, 4 * sizeof(unsigned long long)));
+    CUB_(cudaMalloc(&c->d_err_off, 2 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_lut, (size_t)(d.e + 1) * 65536u));
     CUB_(cudaMalloc(&c->d_wl_len, kMaxWl));
     CUB_(cudaMalloc(&c->d_wl64, kMaxWl * 8));
@@ -855,7 +835,7 @@ extern "C" void ssd_destroy(ssd_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_status3, &c->b_r1_start, &c->b_r1_meta, &c->b_r1_base, &c->b_r2_tok, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
+    DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_r1_start, &c->b_r1_meta, &c->b_r1_base, &c->b_r1_tok, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
                       &c->b_irr_alt, &c->b_perm, &c->b_perm_alt, &c->b_tmp64a, &c->b_tmp64b, &c->b_counts, &c->b_offsets, &c->b_bsums,
                       &c->b_pos, &c->b_out_off, &c->b_cells, &c->b_in1, &c->b_in2, &c->b_out, &c->b_sp_cells, &c->b_sp_cells_alt, &c->b_sp_recs,
                       &c->b_sp_recs_alt, &c->b_sp_off, &c->b_bk_cell, &c->b_bk_off, &c->b_bk_first, &c->b_os, &c->b_irr_table, &c->b_seg};
@@ -893,82 +873,6 @@ extern "C" int ssd_set_stream(ssd_ctx* c, void* cuda_stream)
 // ================================================================================================
 namespace {
 
-// Read-2 id of record r (the KeyError argument of V2:350): the read-2 scan left the inclusive newline prefix of every
-// tile in b_status2, so the tile holding newline number 4r is found on the host and only that tile is fetched.
-std::string r2_token_of_record(ssd_ctx* c, uint64_t r)
-{
-    const uint32_t nt2 = blocks_for(c->r2_len, kTile);
-    if (!nt2 || !c->b_status2.p) return "?";
-    size_t start = 0;
-    if (r > 0) {
-        std::vector<unsigned long long> st(nt2);
-        if (cudaMemcpy(st.data(), c->b_status2.p, (size_t)nt2 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return "?";
-        const unsigned long long want = 4ull * r;  // the record starts right after this newline (1-based count)
-        uint32_t lo = 0, hi = nt2 - 1;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) / 2;
-            if ((st[mid] & kStatusValue) >= want) hi = mid;
-            else lo = mid + 1;
-        }
-        const unsigned long long before = lo ? (st[lo - 1] & kStatusValue) : 0ull;
-        const size_t t_lo = (size_t)lo * kTile, t_len = std::min<size_t>(kTile, c->r2_len - t_lo);
-        std::vector<uint8_t> bytes(t_len);
-        if (cudaMemcpy(bytes.data(), c->r2 + t_lo, t_len, cudaMemcpyDeviceToHost) != cudaSuccess) return "?";
-        unsigned long long seen = before;
-        size_t i = 0;
-        for (; i < t_len && seen < want; i++)
-            if (bytes[i] == '\n') seen++;
-        if (seen < want) return "?";
-        start = t_lo + i;
-    }
-    return token_at(c, c->r2, c->r2_len, start);
-}
-
-// What the kernels flagged, as the error the reference raises for it (V2:350 KeyError, V2:397-398 IndexError, ...).
-int report_errors(ssd_ctx* c, uint32_t flags)
-{
-    if (!(flags & (kErrNoAt | kErrKey | kErrDense | kErrIndex | kErrForeign))) return SSD_OK;
-    unsigned long long off[4];
-    CU(c, cudaMemcpy(off, c->d_err_off, sizeof off, cudaMemcpyDeviceToHost));
-    if (flags & kErrDense) return fail(c, SSD_EMALFORMED, "FASTQ records shorter than 32 bytes on average are not supported");
-    if (flags & kErrIndex) return fail(c, SSD_EINDEX, "list index out of range");
-    if (flags & kErrForeign)
-        return fail(c, SSD_EINVAL, "record at byte %llu: the cell/UMI fields of its header are not made of this whitelist's barcodes", off[0]);
-    if (flags & kErrNoAt) {
-        int f = off[0] != ~0ull ? 0 : 1;
-        return fail(c, SSD_EMALFORMED, "read %d: record at byte %llu does not start with '@'", f + 1, off[f]);
-    }
-    std::string tok = r2_token_of_record(c, off[2]);
-    return fail(c, SSD_EKEY, "%s", tok.c_str());
-}
-
-// Read 1 ended after n_rec_r1 records: a matched read-2 record beyond that has no mate (V2:349-350).
-int check_unmated_tail(ssd_ctx* c)
-{
-    if (c->annotated || c->n_rec_r2 <= c->n_rec_r1) return SSD_OK;
-    CU(c, cudaMemsetAsync(c->d_err_off, 0xFF, 4 * sizeof(unsigned long long), c->stream));
-    k_first_matched_from<<<148, kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, c->n_rec_r1, c->n_rec_r2, c->d_err_off + 2);
-    c->n_launches++;
-    unsigned long long first = ~0ull;
-    CU(c, cudaMemcpyAsync(&first, c->d_err_off + 2, sizeof first, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    if (first == ~0ull) return SSD_OK;
-    std::string tok = r2_token_of_record(c, first);
-    return fail(c, SSD_EKEY, "%s", tok.c_str());
-}
-
-// Resets what the scan of read 1 reports: its line / record counts, the error state, its tile ticket.
-__global__ void k_reset_r1_pass(DevCounters* cnt, unsigned long long* err_off)
-{
-    cnt->n_lines[0] = 0;
-    cnt->n_records[0] = 0;
-    cnt->err_flags = 0;
-    cnt->ticket[0] = 0;
-    for (int k = 0; k < 4; k++) err_off[k] = ~0ull;
-}
-
-int ensure_r1_tables(ssd_ctx* c);
-
 int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, size_t r2_len, bool annotated)
 {
     if ((r1_len && !d_r1) || (r2_len && !d_r2)) return fail(c, SSD_EINVAL, "null input pointer");
@@ -980,46 +884,39 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
     c->r2_len = r2_len;
     c->annotated = annotated;
     c->wide = std::max(r1_len, r2_len) >= (1ull << 32) || getenv("SSD_FORCE_WIDE") != nullptr;
-    c->phase1_done = c->filter_done = c->unique_done = c->r1_tables = false;
+    c->phase1_done = c->filter_done = c->unique_done = false;
     c->planned = -1;
     if (std::max(r1_len, r2_len) >= (1ull << 36)) return fail(c, SSD_EINVAL, "a batch is limited to 64 GiB per file");
 
-    // Read 2 goes first (barcodes, UMIs, histogram, id fingerprints: it needs nothing from read 1), then the scan of read 1
-    // that leaves the per-record tables the writers work from and checks the mates' ids (ensure_r1_tables).
-    // An annotated batch is one file: its scan leaves the per-record tables its writer needs.
-    const size_t scan_len = annotated ? r1_len : r2_len;
-    const uint32_t nt = blocks_for(scan_len, kTile);
-    DevBuf& status = annotated ? c->b_status1 : c->b_status2;
-    uint64_t cap = scan_len / (uint64_t)c->record_hint + 1024;
+    const uint32_t nt1 = blocks_for(r1_len, kTile), nt2 = blocks_for(r2_len, kTile);
+    uint64_t cap = std::max(r1_len, r2_len) / (uint64_t)c->record_hint + 1024;
     DevCounters h{};
-    // the scan parks its per-record results until the record numbers arrive and guesses the record phase of each tile meanwhile;
+    // the scans park their per-record results until the record numbers arrive and guess the record phase of each tile meanwhile;
     // a wrong guess (lines that look like record starts where none is) repeats the scan with the variant that waits instead
     // (records so short that a tile holds more of them than stage B parks at once count as a wrong guess).  The choice is
     // remembered per file for the next batches of this context.
     if (getenv("SSD_SCAN_NODEFER")) c->defer1 = c->defer2 = false;
-    bool& defer = annotated ? c->defer1 : c->defer2;
     for (int attempt = 0, overflows = 0; attempt < 5; attempt++) {
         c->rec_cap = cap;
-        OKR(ensure(c, status, (size_t)(nt + 1) * 8));
+        OKR(ensure(c, c->b_status1, (size_t)(nt1 + 1) * 8));
+        OKR(ensure(c, c->b_status2, (size_t)(nt2 + 1) * 8));
+        OKR(ensure(c, c->b_r1_start, (cap + 1) * (c->wide ? 8 : 4)));
+        OKR(ensure(c, c->b_r1_meta, cap * 16));
+        OKR(ensure(c, c->b_r1_base, cap * 4));
+        OKR(ensure(c, c->b_r1_tok, cap * 8));
         OKR(ensure(c, c->b_ann, cap * 8));
-        if (annotated) {
-            c->rec_cap_r1 = cap;
-            OKR(ensure(c, c->b_r1_start, (cap + 1) * (c->wide ? 8 : 4)));
-            OKR(ensure(c, c->b_r1_meta, cap * 16));
-            OKR(ensure(c, c->b_r1_base, cap * 4));
-        } else {
-            OKR(ensure(c, c->b_r2_tok, cap * 8));
-        }
         OKR(ensure(c, c->b_keys, cap * 8));
         OKR(ensure(c, c->b_irr, cap * sizeof(IrrKey)));
         CU(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(DevCounters), c->stream));
-        CU(c, cudaMemsetAsync(c->d_err_off, 0xFF, 4 * sizeof(unsigned long long), c->stream));
+        CU(c, cudaMemsetAsync(c->d_err_off, 0xFF, 2 * sizeof(unsigned long long), c->stream));
         CU(c, cudaMemsetAsync(c->d_hist, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
-        CU(c, cudaMemsetAsync(status.p, 0, (size_t)(nt + 1) * 8, c->stream));
-        OKR(c->wide ? launch_scan_phase1<uint64_t>(c, defer) : launch_scan_phase1<uint32_t>(c, defer));
+        CU(c, cudaMemsetAsync(c->b_status1.p, 0, (size_t)(nt1 + 1) * 8, c->stream));
+        CU(c, cudaMemsetAsync(c->b_status2.p, 0, (size_t)(nt2 + 1) * 8, c->stream));
+        OKR(c->wide ? launch_scans<uint64_t>(c, c->defer1, c->defer2) : launch_scans<uint32_t>(c, c->defer1, c->defer2));
         OKR(fetch_counters(c, &h));
         if (h.err_flags & (kErrRespec | (kErrRespec << 1))) {
-            defer = false;
+            if (h.err_flags & kErrRespec) c->defer1 = false;
+            if (h.err_flags & (kErrRespec << 1)) c->defer2 = false;
             c->n_respec++;
             continue;
         }
@@ -1028,11 +925,23 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
         cap = std::max(h.n_records[0], h.n_records[1]) + 1;
     }
     if (h.err_flags & (kErrRespec | (kErrRespec << 1) | kErrOverflow)) return fail(c, SSD_EINVAL, "scan did not settle (internal)");
-    OKR(report_errors(c, h.err_flags));
+    if (h.err_flags & (kErrNoAt | kErrKey | kErrDense | kErrIndex | kErrForeign)) {
+        unsigned long long off[2];
+        CU(c, cudaMemcpy(off, c->d_err_off, sizeof off, cudaMemcpyDeviceToHost));
+        if (h.err_flags & kErrDense) return fail(c, SSD_EMALFORMED, "FASTQ records shorter than 32 bytes on average are not supported");
+        if (h.err_flags & kErrIndex) return fail(c, SSD_EINDEX, "list index out of range");
+        if (h.err_flags & kErrForeign)
+            return fail(c, SSD_EINVAL, "record at byte %llu: the cell/UMI fields of its header are not made of this whitelist's barcodes", off[0]);
+        if (h.err_flags & kErrNoAt) {
+            int f = off[0] != ~0ull ? 0 : 1;
+            return fail(c, SSD_EMALFORMED, "read %d: record at byte %llu does not start with '@'", f + 1, off[f]);
+        }
+        std::string tok = token_at(c, c->r2, c->r2_len, off[1]);
+        return fail(c, SSD_EKEY, "%s", tok.c_str());
+    }
+    c->n_rec_r1 = h.n_records[0];
     c->n_rec_r2 = annotated ? h.n_records[0] : h.n_records[1];
-    c->n_rec_r1 = annotated ? h.n_records[0] : 0;  // read 1 has not been looked at yet
-    c->n_rec = c->n_rec_r2;
-    c->r1_tables = annotated;
+    c->n_rec = std::min(c->n_rec_r1, c->n_rec_r2);
     c->n_keys = h.n_keys;
     c->n_irr = h.n_irr;
     c->phase1_done = true;
@@ -1041,44 +950,6 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
     c->stats.n_records_r2 = c->n_rec_r2;
     c->stats.n_regular_keys = c->n_keys;
     c->stats.n_irregular_keys = c->n_irr;
-    return annotated ? SSD_OK : ensure_r1_tables(c);
-}
-
-// The per-record tables of read 1 (record starts, 16-byte descriptors, output-length contributions) from its scan, which
-// checks the mates' ids against read 2's fingerprints on the way (V2:349-350).
-int ensure_r1_tables(ssd_ctx* c)
-{
-    if (c->r1_tables) return SSD_OK;
-    const uint32_t nt1 = blocks_for(c->r1_len, kTile);
-    uint64_t cap = std::max<uint64_t>(c->n_rec_r2 + 1024, c->r1_len / (uint64_t)c->record_hint + 1024);
-    DevCounters h{};
-    for (int attempt = 0, overflows = 0; attempt < 5; attempt++) {
-        c->rec_cap_r1 = cap;
-        OKR(ensure(c, c->b_status1, (size_t)(nt1 + 1) * 8));
-        OKR(ensure(c, c->b_r1_start, (cap + 1) * (c->wide ? 8 : 4)));
-        OKR(ensure(c, c->b_r1_meta, cap * 16));
-        OKR(ensure(c, c->b_r1_base, cap * 4));
-        k_reset_r1_pass<<<1, 1, 0, c->stream>>>(c->d_cnt, c->d_err_off);
-        CU(c, cudaMemsetAsync(c->b_status1.p, 0, (size_t)(nt1 + 1) * 8, c->stream));
-        OKR(c->wide ? launch_scan_r1<uint64_t>(c, c->defer1) : launch_scan_r1<uint32_t>(c, c->defer1));
-        c->n_launches++;
-        OKR(fetch_counters(c, &h));
-        if (h.err_flags & kErrRespec) {
-            c->defer1 = false;
-            c->n_respec++;
-            continue;
-        }
-        if (!(h.err_flags & kErrOverflow)) break;
-        if (++overflows == 2) return fail(c, SSD_EINVAL, "record tables overflowed twice (internal)");
-        cap = h.n_records[0] + 1;
-    }
-    if (h.err_flags & (kErrRespec | kErrOverflow)) return fail(c, SSD_EINVAL, "scan did not settle (internal)");
-    OKR(report_errors(c, h.err_flags));
-    c->n_rec_r1 = h.n_records[0];
-    c->n_rec = std::min(c->n_rec_r1, c->n_rec_r2);
-    c->stats.n_records_r1 = c->n_rec_r1;
-    OKR(check_unmated_tail(c));
-    c->r1_tables = true;
     return SSD_OK;
 }
 
@@ -1442,7 +1313,6 @@ extern "C" int ssd_emit_host(ssd_ctx* c, int which, void* out, size_t out_cap, s
 {
     if (!c) return SSD_EINVAL;
     if (!c->filter_done) return fail(c, SSD_ESTATE, "ssd_emit_host before the filter was built");
-    if (which != SSD_EMIT_MATCHED && which != SSD_EMIT_PASSING) return fail(c, SSD_EINVAL, "unknown output selector");
     const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
     if (written) *written = (size_t)need;
     if (need > out_cap) return fail(c, SSD_ERANGE, "output needs %llu bytes, buffer has %zu", (unsigned long long)need, out_cap);

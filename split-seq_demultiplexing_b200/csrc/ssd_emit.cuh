@@ -212,17 +212,28 @@ struct EmitArgs {
     uint32_t cps, cps_magic;         // tiled writer: 16-byte chunk slots per record, ceil(2^20 / cps)
 };
 
-// One warp writes one output record (V2:134-141) from the read-1 record that starts at byte `start`, annotated with `an`.
-// `dst` is a generic pointer (shared staging buffer or global memory) to the first byte of the record's output; returns
-// the number of bytes written.  Exact for any record (any header, any number of trailing blanks, any length).
-template <class Acc>
-__device__ __forceinline__ uint32_t emit_record_plain(const Acc& a, size_t r1_len, size_t start, uint64_t an, const uint32_t* remap, const uint8_t* r2buf,
-                                                      const DevCfg& cfg, uint8_t* dst)
+// One warp writes one output record (V2:134-141).  `dst` is a generic pointer (shared staging buffer or
+// global memory) to the first byte of the record's output; returns the number of bytes written.
+template <class Acc, typename OffT>
+__device__ __forceinline__ uint32_t emit_record_generic(const Acc& a, const EmitArgs<OffT>& args, const DevCfg& cfg, uint64_t r, uint8_t* dst)
 {
     const int lane = threadIdx.x & 31;
+    const size_t start = (size_t)args.r1_start[r];
     Lines L;
-    find_lines(a, start, r1_len, true, L);
+    find_lines(a, start, args.r1_len, true, L);
     uint32_t o = 0;
+    if (args.copy_mode) {  // the four lines, strip()ped
+        for (int k = 0; k < 4; k++) {
+            size_t le = rstrip_end(a, L.s[k], L.e[k]), ls = L.s[k];
+            while (ls < le && py_space(a.byte(ls))) ls++;
+            for (size_t i = lane; i < le - ls; i += 32) dst[o + i] = (uint8_t)a.byte(ls + i);
+            o += (uint32_t)(le - ls);
+            if (lane == 0) dst[o] = '\n';
+            o += 1;
+        }
+        return o;
+    }
+
     // header: bytes before the first '/', blanks removed, then strip()
     size_t cut = L.e[0];
     for (size_t p = L.s[0]; p < L.e[0]; p += 32) {
@@ -252,8 +263,9 @@ __device__ __forceinline__ uint32_t emit_record_plain(const Acc& a, size_t r1_le
     }
 
     // '_' + barcode1 + barcode2 + barcode3 + '_' + umi + '\n'
+    const uint64_t an = args.ann[r];
     uint32_t cell = ann_cell(an);
-    if (remap) cell = remap[cell];
+    if (args.remap) cell = args.remap[cell];
     uint32_t ci1, ci2, ci3;
     cell_indices(cfg, cell, ci1, ci2, ci3);
     const uint32_t idx[3] = {ci1, ci2, ci3};
@@ -272,7 +284,7 @@ __device__ __forceinline__ uint32_t emit_record_plain(const Acc& a, size_t r1_le
         if ((uint32_t)lane < ulen) dst[o + lane] = (uint8_t)base2_char((uint32_t)(ann_payload(an) >> (2 * lane)));
     } else {
         const size_t uoff = (size_t)(ann_payload(an) >> 5);
-        if ((uint32_t)lane < ulen) dst[o + lane] = r2buf[uoff + lane];
+        if ((uint32_t)lane < ulen) dst[o + lane] = args.r2buf[uoff + lane];
     }
     o += ulen;
     if (lane == 0) dst[o] = '\n';
@@ -291,27 +303,6 @@ __device__ __forceinline__ uint32_t emit_record_plain(const Acc& a, size_t r1_le
     o += qual_len;
     if (lane == 0) dst[o] = '\n';
     o += 1;
-    return o;
-}
-
-// The same driven by the per-record tables of the read-1 scan (split mode, annotated input, the table-driven writers).
-template <class Acc, typename OffT>
-__device__ __forceinline__ uint32_t emit_record_generic(const Acc& a, const EmitArgs<OffT>& args, const DevCfg& cfg, uint64_t r, uint8_t* dst)
-{
-    const int lane = threadIdx.x & 31;
-    const size_t start = (size_t)args.r1_start[r];
-    if (!args.copy_mode) return emit_record_plain(a, args.r1_len, start, args.ann[r], args.remap, args.r2buf, cfg, dst);
-    Lines L;
-    find_lines(a, start, args.r1_len, true, L);
-    uint32_t o = 0;
-    for (int k = 0; k < 4; k++) {  // the four lines, strip()ped
-        size_t le = rstrip_end(a, L.s[k], L.e[k]), ls = L.s[k];
-        while (ls < le && py_space(a.byte(ls))) ls++;
-        for (size_t i = lane; i < le - ls; i += 32) dst[o + i] = (uint8_t)a.byte(ls + i);
-        o += (uint32_t)(le - ls);
-        if (lane == 0) dst[o] = '\n';
-        o += 1;
-    }
     return o;
 }
 
@@ -585,13 +576,6 @@ __global__ void k_bucket_table(const uint64_t* cells, const uint32_t* bpos, cons
         b_off[b] = out_off[k];
         b_first[b] = k;
     }
-}
-
-// Error path of the mate check (V2:349-350): the first matched read-2 record at or after record `from` (read 1 ended there).
-__global__ void k_first_matched_from(const uint64_t* ann, uint64_t from, uint64_t n, unsigned long long* err_rec)
-{
-    for (uint64_t r = from + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
-        if (ann_state(ann[r]) != 0u) atomicMin(err_rec, (unsigned long long)r);
 }
 
 __global__ void k_record_cells(const uint64_t* ann, uint64_t n, int32_t* cells)

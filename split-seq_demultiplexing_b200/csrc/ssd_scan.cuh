@@ -1,15 +1,14 @@
 // ssd_scan.cuh — single-pass FASTQ record-boundary scan fused with the per-record work (sm_100a).
 //
-// Persistent, warp-specialised blocks (one wave) take 24 KiB tiles of the file by ticket.  A copy warp keeps the
-// tiles (plus a 2 KiB halo) arriving in shared memory with bulk copies (TMA); stage A turns newlines into a bitmap
+// Persistent, warp-specialised blocks (one wave, two per SM) take 24 KiB tiles of the file by ticket.  A copy warp keeps
+// the tiles (plus a 2 KiB halo) arriving in shared memory with bulk copies (TMA); stage A turns newlines into a bitmap
 // through 16-byte vector loads, publishes the tile's newline count (a prefix warp chains the counts into global line
-// indices: decoupled look-back) and lists the line starts; stage B processes every record that starts in the tile,
-// one thread per record, from shared memory:
-//   read 2: UMI / barcode extraction (V2:293-301), first-hit Hamming matching (V2:302-304, 327-329), per-cell
-//           histogram, (cell, UMI) keys, and the read-id fingerprint the read-1 scan checks (V2:349-350).
-//           Read 2 is scanned FIRST: it needs nothing from read 1.
-//   read 1: record offset + a 16-byte descriptor the writer needs (V2:134-141, 246, 249), mate-id check against read 2's
-//           fingerprints (V2:350)
+// indices: decoupled look-back) and lists the line starts; stage B processes every record that starts in the tile, one
+// thread per record, from shared memory, guessing the record phase so that it never waits for the line index; a commit
+// warp writes the parked results out under their record numbers once the index has arrived:
+//   read 1: record offset + a 16-byte descriptor the writer needs (V2:134-141, 246, 249), read-id fingerprint
+//   read 2: UMI / barcode extraction (V2:293-301), first-hit Hamming matching (V2:302-304, 327-329),
+//           mate-id check (V2:350), per-cell histogram, (cell, UMI) keys
 //   annotated input (MergedCells_1.fastq, V2:389-404): cell / UMI parsed back from the header
 // The per-record code is written to stay convergent: line boundaries come from a per-tile list of line
 // starts (no searching), headers and barcode windows are handled four bytes at a time with
@@ -68,14 +67,13 @@ struct ScanArgs {
     unsigned long long* status;  // one word per tile: flag << 62 | newline count (aggregate or inclusive prefix)
     uint32_t n_tiles;
     DevCounters* cnt;
-    unsigned long long* err_off;  // [0], [1]: smallest offending byte offset per file; [2]: smallest record number whose mates' ids differ
+    unsigned long long* err_off;  // [2] smallest offending byte offset per file
     uint64_t rec_cap;
     // read 1 outputs
     OffT* r1_start;
     uint4* r1_meta;
     uint32_t* r1_base;
-    unsigned long long* r2_tok;  // read-2 id fingerprint per matched record: 64-bit hash of the first header token, low 16 bits = its length
-                                 // (written by the read-2 scan, compared by whoever walks read 1)
+    unsigned long long* r1_tok;  // read id fingerprint: 64-bit hash of the first header token, low 16 bits = its length
     // read 2 inputs / outputs
     const uint8_t* r1buf;
     size_t r1_len;
@@ -89,12 +87,6 @@ __device__ __forceinline__ void raise(DevCounters* cnt, unsigned long long* err_
 {
     atomicOr(&cnt->err_flags, flag);
     atomicMin(&err_off[file], (unsigned long long)off);
-}
-// V2:349-350: the matched read-2 record number r has no read-1 mate of the same id (KeyError(id))
-__device__ __forceinline__ void raise_key(DevCounters* cnt, unsigned long long* err_off, uint64_t r)
-{
-    atomicOr(&cnt->err_flags, kErrKey);
-    atomicMin(&err_off[2], (unsigned long long)r);
 }
 
 // ---- SIMD-in-register byte tests (flags land in bit 7 of each byte) ----------------------------------
@@ -145,10 +137,10 @@ __device__ __forceinline__ uint32_t ldg_word_safe(const uint8_t* buf, size_t off
 }
 
 // ---- read-id fingerprint -------------------------------------------------------------------------------
-// The mate join of the reference is by read id (V2:349-350).  Read 2's scan leaves, per matched record, a 64-bit
+// The mate join of the reference is by read id (V2:349-350).  Read 1's scan leaves, per record, a 64-bit
 // fingerprint of the id (first whitespace-delimited header token): a hash over the token taken as little-endian
-// 32-bit words from its first byte (last word zero-padded), with the token length in the low 16 bits.  The pass over
-// read 1 compares fingerprints instead of chasing read 2's bytes through global memory.
+// 32-bit words from its first byte (last word zero-padded), with the token length in the low 16 bits.  Read 2's
+// scan compares fingerprints instead of chasing read 1's bytes through global memory.
 __device__ __forceinline__ unsigned long long tok_hash_step(unsigned long long h, uint32_t word)
 {
     h = (h ^ (unsigned long long)word) * 0xFF51AFD7ED558CCDull;
@@ -179,7 +171,7 @@ __device__ __forceinline__ unsigned long long tok_hash_generic(const Acc& a, siz
 // exact generic path (any accessor)
 // ======================================================================================================
 template <class Acc, typename OffT>
-__device__ __noinline__ bool r1_record_generic(const Acc& a, const ScanArgs<OffT>& args, uint64_t r, size_t start, uint64_t n_rec_r2)
+__device__ __noinline__ bool r1_record_generic(const Acc& a, const ScanArgs<OffT>& args, uint64_t r, size_t start)
 {
     Lines L;
     if (!find_lines(a, start, args.len, true, L)) return false;
@@ -220,7 +212,7 @@ __device__ __noinline__ bool r1_record_generic(const Acc& a, const ScanArgs<OffT
     args.r1_start[r] = (OffT)start;
     args.r1_meta[r] = m;
     args.r1_base[r] = kept_at_last_nonspace + (uint32_t)seq_len + (uint32_t)qual_len + 7u;
-    if (r < n_rec_r2 && ann_state(args.ann[r]) != 0u && args.r2_tok[r] != tok_hash_generic(a, L.s[0], tok_e)) raise_key(args.cnt, args.err_off, r);
+    args.r1_tok[r] = tok_hash_generic(a, L.s[0], tok_e);
     return true;
 }
 
@@ -229,9 +221,17 @@ struct R2Out {
     IrrKey irr;
 };
 
+// Mate join by read id (V2:349-350): read-2 token [tok_s, tok_e) against the fingerprint read 1 left for record r.
+template <class Acc, typename OffT>
+__device__ __forceinline__ bool mate_ok_generic(const Acc& a, const ScanArgs<OffT>& args, uint64_t r, size_t tok_s, size_t tok_e, uint64_t n_rec_r1)
+{
+    if (r >= n_rec_r1) return false;
+    return args.r1_tok[r] == tok_hash_generic(a, tok_s, tok_e);
+}
+
 template <class Acc, typename OffT>
 __device__ __noinline__ bool r2_record_generic(const Acc& a, const ScanArgs<OffT>& args, const DevCfg& cfg, uint64_t r, size_t start,
-                                               R2Out& out, bool& complete)
+                                               R2Out& out, bool& complete, uint64_t n_rec_r1)
 {
     Lines L;
     out.ann = 0;
@@ -263,7 +263,10 @@ __device__ __noinline__ bool r2_record_generic(const Acc& a, const ScanArgs<OffT
 
     size_t tok_e = L.s[0];
     while (tok_e < L.e[0] && !py_space(a.byte(tok_e))) tok_e++;
-    args.r2_tok[r] = tok_hash_generic(a, L.s[0], tok_e);  // V2:349-350: the pass over read 1 compares
+    if (!mate_ok_generic(a, args, r, L.s[0], tok_e, n_rec_r1)) {
+        raise(args.cnt, args.err_off, 1, kErrKey, start);
+        return true;
+    }
 
     // UMI = lineRead[umi_start:umi_end] verbatim (V2:295); regular = full length and ACGT only
     size_t ulo = (size_t)cfg.us < seq_len ? (size_t)cfg.us : seq_len;
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         // block ever waits for the line index.
         if (!DEFER) return;
         GlobAcc ga{args.buf, args.len};
-        const uint64_t n_rec_r2 = MODE == kScanR1 ? args.cnt->n_records[1] : 0;  // read 2 was scanned by an earlier launch
+        const uint64_t n_rec_r1 = MODE == kScanR2 ? args.cnt->n_records[0] : 0;
         for (uint32_t it = 0;; it++) {
             const uint32_t ss = it % kStageSlots;
             mbar_wait(reinterpret_cast<uint64_t*>(&S.stage_full[ss]), (it / kStageSlots) & 1u);
@@ -567,10 +570,9 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                         args.r1_start[r] = (OffT)(tile_lo + s0);
                         args.r1_meta[r] = G.mt[i];
                         args.r1_base[r] = G.base[i];
-                        // V2:349-350: a matched read-2 record must meet a read-1 record of the same id (fingerprint compare)
-                        if (r < n_rec_r2 && ann_state(args.ann[r]) != 0u && args.r2_tok[r] != G.fp[i]) raise_key(args.cnt, args.err_off, r);
+                        args.r1_tok[r] = G.fp[i];
                     } else if (have) {
-                        r1_record_generic(ga, args, r, tile_lo + s0, n_rec_r2);
+                        r1_record_generic(ga, args, r, tile_lo + s0);
                     }
                 } else if (MODE == kScanAnn) {
                     if (ok2) {
@@ -589,12 +591,13 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                 } else {
                     if (ok2) {
                         if (fl & kStNoAt) raise(args.cnt, args.err_off, 1, kErrNoAt, tile_lo + s0);
-                        if (fl & kStMatched) args.r2_tok[r] = G.fp[i];  // V2:349-350: compared by the pass over read 1
+                        // V2:349-350: the read-1 mate must carry the same id (fingerprint compare)
+                        if ((fl & kStMatched) && !(r + 1u <= n_rec_r1 && args.r1_tok[r] == G.fp[i])) raise(args.cnt, args.err_off, 1, kErrKey, tile_lo + s0);
                         if (fl & kStComplete) args.ann[r] = G.ann[i];
                     } else if (have) {
                         R2Out o;
                         bool complete = false;
-                        r2_record_generic(ga, args, cfg, r, tile_lo + s0, o, complete);
+                        r2_record_generic(ga, args, cfg, r, tile_lo + s0, o, complete, n_rec_r1);
                         if (complete) args.ann[r] = o.ann;
                         const uint32_t st8 = ann_state(o.ann);
                         if (st8) atomicAdd(&args.hist[ann_cell(o.ann)], 1u);
@@ -700,7 +703,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
 #ifdef SSD_SCAN_PROFILE
     unsigned long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
-    const uint64_t n_rec_r2 = MODE == kScanR1 ? args.cnt->n_records[1] : 0;  // read 2 was scanned by an earlier launch
+    const uint64_t n_rec_r1 = MODE == kScanR2 ? args.cnt->n_records[0] : 0;  // read 1 was scanned by the previous launch
 
     // stage A (warps 0-3): newline bitmap, count, line-start list of the block's it-th tile; false when the tiles are exhausted
     auto stage_a = [&](uint32_t it) -> bool {
@@ -731,35 +734,6 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         static_assert(kHaloWords <= 64 && kAThreads >= 64, "halo size");
         uint32_t mw[WPT];
         uint32_t cnt = 0;
-#ifdef SSD_SCAN_REGMASK
-        // experiment (unmeasured): every thread builds its own mask words from the two 16-byte chunks each
-        // covers, so the bitmap never goes through shared memory (no 16-bit stores, no re-read, one barrier less); the price is
-        // a 2-way bank conflict of the 96-byte-strided 16-byte loads
-        const uint4* w4 = reinterpret_cast<const uint4*>(s_win);
-        const uint32_t nfull = win_bytes >> 4;
-        auto chunk_mask = [&](uint32_t c) -> uint32_t {
-            if (c > nfull || (c == nfull && !(win_bytes & 15u))) return 0u;
-            const uint4 v = w4[c];
-            const uint32_t lo = __dp4a(nl_flags(v.x), 0x08040201u, __dp4a(nl_flags(v.y), 0x80402010u, 0u));
-            const uint32_t hi = __dp4a(nl_flags(v.z), 0x08040201u, __dp4a(nl_flags(v.w), 0x80402010u, 0u));
-            const uint32_t m = (lo >> 7) | ((hi >> 7) << 8);
-            return c == nfull ? m & ((1u << (win_bytes & 15u)) - 1u) : m;  // the chunk the data ends in
-        };
-#pragma unroll
-        for (int w = 0; w < WPT; w++) {
-            const uint32_t c0 = 2u * (uint32_t)(WPT * tid + w);
-            mw[w] = chunk_mask(c0) | (chunk_mask(c0 + 1u) << 16);
-            cnt += (uint32_t)__popc(mw[w]);
-        }
-        uint32_t hm = 0;
-        if (tid < kHaloWords) {
-            const uint32_t c0 = 2u * (uint32_t)(kTileWords + tid);
-            hm = chunk_mask(c0) | (chunk_mask(c0 + 1u) << 16);
-        }
-        (void)s_mask;
-        PROF_T(t2);
-        PROF_ADD(1, t1, t2);
-#else
         build_nl_mask<kAThreads, (kWinWords * 2 + kAThreads - 1) / kAThreads>(s_win, win_bytes, reinterpret_cast<uint16_t*>(s_mask), kWinWords * 2);
         sync_a();
         PROF_T(t2);
@@ -770,7 +744,6 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             cnt += (uint32_t)__popc(mw[w]);
         }
         const uint32_t hm = tid < kHaloWords ? s_mask[kTileWords + tid] : 0u;
-#endif
         // both prefix sums in one: a warp's tile count (<= 32 x 32 WPT bits) in the low half, its halo count in the high half
         static_assert(32 * 32 * WPT < 65536, "packed scan");
         uint32_t both = cnt | ((uint32_t)__popc(hm) << 16);
@@ -851,6 +824,14 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
 
     // stage B: the records that start in the block's it-th tile
     const int tb = tid - kAThreads, wb = warp - kAWarps;  // thread / warp index inside the stage-B group
+    // read 2: the mate check still in flight (fingerprint of read 1 requested, not yet compared)
+    bool pend = false;
+    unsigned long long pend_fp1 = 0, pend_fp = 0;
+    size_t pend_off = 0;
+    auto settle = [&]() {
+        if (pend && pend_fp1 != pend_fp) raise(args.cnt, args.err_off, 1, kErrKey, pend_off);
+        pend = false;
+    };
     auto stage_b = [&](uint32_t it) -> bool {
         const uint32_t ws = it % kWinSlots, ls = it % kListSlots;
         PROF_T(t7);
@@ -1091,17 +1072,17 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
 
         auto commit = [&](uint64_t r) {
             const bool ok2 = ok && r < args.rec_cap;  // beyond the capacity: the exact path raises the overflow flag
+            if (MODE == kScanR2) settle();
             if (MODE == kScanR1) {
                 if (ok2) {
                     if (noat) raise(args.cnt, args.err_off, 0, kErrNoAt, tile_lo + s0);
                     args.r1_start[r] = (OffT)(tile_lo + s0);
                     args.r1_meta[r] = mt;
                     args.r1_base[r] = base_len;
-                    // V2:349-350: a matched read-2 record must meet a read-1 record of the same id (fingerprint compare)
-                    if (r < n_rec_r2 && ann_state(args.ann[r]) != 0u && args.r2_tok[r] != fp) raise_key(args.cnt, args.err_off, r);
+                    args.r1_tok[r] = fp;
                 }
                 __syncwarp();
-                if (have && !ok2) r1_record_generic(ga, args, r, tile_lo + s0, n_rec_r2);
+                if (have && !ok2) r1_record_generic(ga, args, r, tile_lo + s0);
                 __syncwarp();
             } else if (MODE == kScanAnn) {
                 if (ok2) {
@@ -1124,13 +1105,24 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             } else {
                 if (ok2) {
                     if (noat) raise(args.cnt, args.err_off, 1, kErrNoAt, tile_lo + s0);
-                    if (matched) args.r2_tok[r] = fp;  // V2:349-350: compared by the pass over read 1
+                    if (matched) {
+                        // V2:349-350: the read-1 mate must carry the same id (fingerprint compare).  A mismatch fails the whole
+                        // call, so nothing below waits for the fingerprint: it is requested here and compared one tile later.
+                        if (r + 1u <= n_rec_r1) {
+                            pend_fp1 = args.r1_tok[r];
+                            pend_fp = fp;
+                            pend_off = tile_lo + s0;
+                            pend = true;
+                        } else {
+                            raise(args.cnt, args.err_off, 1, kErrKey, tile_lo + s0);
+                        }
+                    }
                 } else {
                     o.ann = 0;
                     complete = false;
                 }
                 __syncwarp();
-                if (have && !ok2) r2_record_generic(ga, args, cfg, r, tile_lo + s0, o, complete);
+                if (have && !ok2) r2_record_generic(ga, args, cfg, r, tile_lo + s0, o, complete, n_rec_r1);
                 __syncwarp();
                 // ---- results: annotation, histogram, key counts; the regular (cell, UMI) key is the annotation itself
                 //      (the sort reads it from there), irregular keys are collected afterwards by k_collect_irr ----
@@ -1274,6 +1266,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         while (stage_a(n_a)) n_a++;
     } else {
         while (stage_b(n_a)) n_a++;
+        if (MODE == kScanR2) settle();
     }
 #ifdef SSD_SCAN_PROFILE
     if (tid == 0 || tb == 0) {
