@@ -291,6 +291,7 @@ def measure_resident(env, cid, cfg, args):
     dm.set_timing(False)
     value = env.world * n * args.steps / (ms / 1e3)
 
+    in1, in2 = d1.numel(), d2.numel()
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region ----
     e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "steps": 0}
     e2e_steps = args.e2e_steps if args.e2e_steps is not None else min(args.steps, 6)
@@ -303,6 +304,12 @@ def measure_resident(env, cid, cfg, args):
             h1.copy_(d1)
             h2.copy_(d2)
         else:
+            # the resident batch has done its job: its memory goes to the contexts of this leg
+            del d1, d2, out
+            dm.close()
+            torch.cuda.empty_cache()
+            dm = make_dm(env, cfg)
+            out = torch.empty(int(ne * 400) + 4096, dtype=torch.uint8, device="cuda")
             s1, s2 = ssd_b200.synth_device(dm, ssd_b200.synth_spec(env.wl, ne, seed=cfg["seed"], first_index=env.rank * n + 1, read_len=READ_LEN, **cfg["spec"]))
             h1 = torch.empty(s1.numel(), dtype=torch.uint8, pin_memory=True)
             h2 = torch.empty(s2.numel(), dtype=torch.uint8, pin_memory=True)
@@ -402,7 +409,7 @@ def measure_resident(env, cid, cfg, args):
 
     # ---- roofline (algorithmic bytes = every input byte read once + every output byte written once) ----
     peak, peak_src = measured_peak()
-    in1, in2, outb = d1.numel(), d2.numel(), int(last["written"])
+    outb = int(last["written"])
     algo = {"scan_r1": in1, "scan_r2": in2, "emit": outb}  # the writer's re-read of read 1 is not credited
     kname = {"scan_r1": "k_scan<R1>", "scan_r2": "k_scan<R2>", "emit": "k_emit (split)" if split else "k_emit_stream"}
     per_kernel = {}
@@ -422,7 +429,7 @@ def measure_resident(env, cid, cfg, args):
                     "stage_ms_per_step": {k: v[0] / max(1, args.steps) for k, v in stage.items()},
                     "pipeline": {"algorithmic_bytes_per_step": pipeline_bytes, "achieved": pipeline_gbs, "frac": pipeline_gbs / peak}}
     dm.close()
-    del d1, d2, out
+    d1 = d2 = out = None
     torch.cuda.empty_cache()
     return dict(value=value, ms_per_step=ms / args.steps, e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline,
                 result={k: int(v) for k, v in last.items()})

@@ -180,6 +180,18 @@ int ssd_partition_keys(ssd_ctx *ctx, int world, uint64_t **d_keys, uint64_t *off
  * counted; records with hi == ~0 are padding. */
 int ssd_count_distinct_owned(ssd_ctx *ctx, uint64_t *d_keys, uint64_t n_keys, void *d_irregular,
                              uint64_t n_irregular, int rank, int world);
+/* Multi-GPU hosts, the -m decision without shipping every key (what ssd_b200.distributed.global_filter does):
+ *   ssd_distinct_local   per-cell distinct-UMI counts of THIS batch into the distinct table (the read histogram must still be the
+ *                        batch's own).  A cell passes when any rank alone counts >= m (all-reduce MAX of these tables) and fails
+ *                        when all ranks together hold < m reads of it (all-reduce SUM of the read histograms).
+ *   ssd_undecided_keys   this batch's (cell,UMI) keys, duplicates kept, of the cells in between (d_distinct_max[cell] < m <=
+ *                        d_reads_global[cell]; both device arrays of n^3 uint32): *d_keys / *d_irregular in the formats above,
+ *                        *d_counts -> two uint64 on the device (regular, irregular) valid once the stream has run.  Every rank
+ *                        holds fewer than m distinct keys per such cell, so all-gathering them and counting with
+ *                        ssd_count_distinct decides those cells exactly. */
+int ssd_distinct_local(ssd_ctx *ctx);
+int ssd_undecided_keys(ssd_ctx *ctx, const uint32_t *d_reads_global, const uint32_t *d_distinct_max, uint64_t **d_keys,
+                       void **d_irregular, uint64_t **d_counts);
 /* Owner rank of a cell in a world of W ranks: ((cell >> *shift) * W) / *n_buckets. */
 int ssd_owner_layout(const ssd_ctx *ctx, int *shift, int *n_buckets);
 /* Bit width of the 2-bit-packed UMI inside a regular key (cell id = key >> umi_bits). */

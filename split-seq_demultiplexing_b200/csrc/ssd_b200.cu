@@ -11,7 +11,9 @@
 #include <string.h>
 #include <errno.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/vfs.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -38,7 +40,8 @@ struct DevBuf {
 
 namespace {
 constexpr size_t kIoChunk = (size_t)16 << 20;  // bytes per pinned slot
-constexpr int kIoLanes = 8;                    // host threads moving file data (4 per input file; 4 for the output)
+constexpr int kIoLanes = 16;                   // host threads moving file data (8 per input file; 8 for the output)
+constexpr int kIoHalf = kIoLanes / 2;
 constexpr int kIoSlots = 2;                    // pinned slots per lane: one being filled / written, one in flight
 
 struct IoLane {  // what one I/O thread owns
@@ -82,6 +85,7 @@ struct ssd_ctx {
 
     DevCounters* d_cnt = nullptr;
     unsigned long long* d_err_off = nullptr;
+    unsigned long long* d_ucnt = nullptr;  // [2] cursors of ssd_undecided_keys
     uint8_t* d_lut = nullptr;
     uint8_t* d_wl_len = nullptr;
     unsigned long long* d_wl64 = nullptr;  // whitelist entries as 8-byte words (tiled writer)
@@ -810,6 +814,7 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
     }
     CUB_(cudaMalloc(&c->d_cnt, sizeof(DevCounters)));
     CUB_(cudaMalloc(&c->d_err_off, 2 * sizeof(unsigned long long)));
+    CUB_(cudaMalloc(&c->d_ucnt, 2 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_lut, (size_t)(d.e + 1) * 65536u));
     CUB_(cudaMalloc(&c->d_wl_len, kMaxWl));
     CUB_(cudaMalloc(&c->d_wl64, kMaxWl * 8));
@@ -842,6 +847,7 @@ extern "C" void ssd_destroy(ssd_ctx* c)
     for (DevBuf* b : bufs) release(*b);
     cudaFree(c->d_cnt);
     cudaFree(c->d_err_off);
+    cudaFree(c->d_ucnt);
     cudaFree(c->d_lut);
     cudaFree(c->d_wl_len);
     cudaFree(c->d_wl64);
@@ -1164,6 +1170,41 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
     return SSD_OK;
 }
 
+extern "C" int ssd_distinct_local(ssd_ctx* c)
+{
+    if (!c) return SSD_EINVAL;
+    if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_distinct_local before ssd_demux_device");
+    CU(c, cudaSetDevice(c->device));
+    c->unique_done = false;
+    StageTimer t(c, 2);
+    return distinct_counts_local(c);
+}
+
+extern "C" int ssd_undecided_keys(ssd_ctx* c, const uint32_t* d_reads_global, const uint32_t* d_distinct_max, uint64_t** d_keys, void** d_irregular,
+                                  uint64_t** d_counts)
+{
+    if (!c || !d_reads_global || !d_distinct_max || !d_keys || !d_irregular || !d_counts) return SSD_EINVAL;
+    if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_undecided_keys before ssd_demux_device");
+    CU(c, cudaSetDevice(c->device));
+    StageTimer t(c, 2);
+    c->unique_done = false;  // the key buffers are reused
+    const uint64_t n = c->n_rec_r2;
+    OKR(ensure(c, c->b_keys, std::max<uint64_t>(c->n_keys, 1) * sizeof(uint64_t)));
+    OKR(ensure(c, c->b_irr, std::max<uint64_t>(c->n_irr, 1) * sizeof(IrrKey)));
+    CU(c, cudaMemsetAsync(c->d_ucnt, 0, 2 * sizeof(unsigned long long), c->stream));
+    const uint32_t m = (uint32_t)std::min<long long>(std::max<long long>(c->cfg.min_count, 0), 0xFFFFFFFFll);
+    if (n) {
+        k_undecided_keys<<<(uint32_t)std::min<uint64_t>(blocks_for(n, 256), 148 * 8), 256, 0, c->stream>>>(
+            (const uint64_t*)c->b_ann.p, n, c->r2, d_reads_global, d_distinct_max, m, c->dcfg.umi_bits, (uint64_t*)c->b_keys.p, (IrrKey*)c->b_irr.p, c->d_ucnt);
+        c->n_launches++;
+    }
+    CU(c, cudaGetLastError());
+    *d_keys = (uint64_t*)c->b_keys.p;
+    *d_irregular = c->b_irr.p;
+    *d_counts = (uint64_t*)c->d_ucnt;
+    return SSD_OK;
+}
+
 extern "C" int ssd_get_stats(const ssd_ctx* c, ssd_stats* stats)
 {
     if (!c || !stats) return SSD_EINVAL;
@@ -1355,8 +1396,44 @@ extern "C" int ssd_run_host(ssd_ctx* c, const void* r1, size_t r1_len, const voi
 // file to file
 // ================================================================================================
 namespace {
-// one host thread of `stride`: pread chunks first, first + stride, ... into its pinned slots, each uploaded as soon as it is read
-void upload_file_worker(int device, int fd, size_t base, size_t size, uint8_t* d_dst, IoLane* lane, int first, int stride, int* rc, int* err_no)
+// A byte range of a file mapped into memory: the I/O threads then move file data with plain memcpy between the page cache and
+// their pinned slots, which is several times faster per thread than pread / pwrite (one kernel crossing per page run instead
+// of per call, no extra locking); profiles/r02_host_io.md has the numbers.  Input ranges are always mapped; the output range
+// only on a RAM-backed file system (on a disk the dirty pages of a mapping are written back at the kernel's leisure, pwrite
+// is the better citizen there).  SSD_IO_NOMMAP=1 forces pread / pwrite.
+struct RangeMap {
+    void* p = MAP_FAILED;
+    size_t len = 0;
+    uint8_t* data = nullptr;  // first byte of the range
+    bool open_range(int fd, size_t base, size_t size, bool writable)
+    {
+        static const bool off = getenv("SSD_IO_NOMMAP") != nullptr;
+        if (off || size == 0) return false;
+        if (writable) {
+            struct statfs fs;
+            if (fstatfs(fd, &fs) != 0 || (unsigned long)fs.f_type != 0x01021994ul) return false;  // TMPFS_MAGIC
+            if (ftruncate(fd, (off_t)(base + size)) != 0) return false;
+        }
+        const size_t page = (size_t)sysconf(_SC_PAGESIZE), lo = base & ~(page - 1);
+        len = size + (base - lo);
+        p = mmap(nullptr, len, writable ? PROT_READ | PROT_WRITE : PROT_READ, MAP_SHARED, fd, (off_t)lo);
+        if (p == MAP_FAILED) return false;
+        madvise(p, len, MADV_SEQUENTIAL);
+        data = (uint8_t*)p + (base - lo);
+        return true;
+    }
+    void close_range()
+    {
+        if (p != MAP_FAILED) munmap(p, len);
+        p = MAP_FAILED;
+        data = nullptr;
+    }
+};
+
+// one host thread of `stride`: chunks first, first + stride, ... of the range into its pinned slots (memcpy from the mapping, or
+// pread), each uploaded as soon as it is there
+void upload_file_worker(int device, int fd, const uint8_t* map, size_t base, size_t size, uint8_t* d_dst, IoLane* lane, int first, int stride, int* rc,
+                        int* err_no)
 {
     *rc = SSD_OK;
     if (cudaSetDevice(device) != cudaSuccess) {
@@ -1372,6 +1449,10 @@ void upload_file_worker(int device, int fd, size_t base, size_t size, uint8_t* d
         }
         const size_t off = k * kIoChunk, want = std::min(kIoChunk, size - off);
         size_t got = 0;
+        if (map) {
+            memcpy(lane->slot[s], map + off, want);
+            got = want;
+        }
         while (got < want) {
             const ssize_t r = pread(fd, lane->slot[s] + got, want - got, (off_t)(base + off + got));
             if (r < 0 && errno == EINTR) continue;
@@ -1391,8 +1472,9 @@ void upload_file_worker(int device, int fd, size_t base, size_t size, uint8_t* d
     if (cudaStreamSynchronize(lane->stream) != cudaSuccess) *rc = SSD_ECUDA;
 }
 
-// one host thread of `stride`: download chunks first, first + stride, ... and pwrite them at base + offset
-void download_file_worker(int device, int fd, size_t base, size_t size, const uint8_t* d_src, IoLane* lane, int first, int stride, int* rc, int* err_no)
+// one host thread of `stride`: download chunks first, first + stride, ... and put them at base + offset (memcpy into the mapping, or pwrite)
+void download_file_worker(int device, int fd, uint8_t* map, size_t base, size_t size, const uint8_t* d_src, IoLane* lane, int first, int stride, int* rc,
+                          int* err_no)
 {
     *rc = SSD_OK;
     if (cudaSetDevice(device) != cudaSuccess) {
@@ -1422,6 +1504,10 @@ void download_file_worker(int device, int fd, size_t base, size_t size, const ui
         }
         const size_t off = k * kIoChunk, len = std::min(kIoChunk, size - off);
         size_t put = 0;
+        if (map) {
+            memcpy(map + off, lane->slot[s], len);
+            put = len;
+        }
         while (put < len) {
             const ssize_t w = pwrite(fd, lane->slot[s] + put, len - put, (off_t)(base + off + put));
             if (w < 0 && errno == EINTR) continue;
@@ -1481,11 +1567,16 @@ int download_to_file(ssd_ctx* c, int which, const char* out_path, int append, si
     if (need && rc == SSD_OK) {
         rc = ensure(c, c->b_out, need + 32);
         if (rc == SSD_OK) rc = ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, nullptr);
-        for (int k = 0; k < 4 && rc == SSD_OK; k++) rc = c->io[k].init();
+        for (int k = 0; k < kIoHalf && rc == SSD_OK; k++) rc = c->io[k].init();
         if (rc == SSD_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, SSD_ECUDA, "emit failed");  // the emit kernel ran on the context's stream
         if (rc == SSD_OK) {
-            std::lock_guard<std::mutex> turn(g_d2h_turn);
-            rc = run_lanes(c, out_path, 0, 4, download_file_worker, c->device, fd, (size_t)base, (size_t)need, (const uint8_t*)c->b_out.p);
+            RangeMap m;
+            m.open_range(fd, (size_t)base, (size_t)need, true);
+            {
+                std::lock_guard<std::mutex> turn(g_d2h_turn);
+                rc = run_lanes(c, out_path, 0, kIoHalf, download_file_worker, c->device, fd, m.data, (size_t)base, (size_t)need, (const uint8_t*)c->b_out.p);
+            }
+            m.close_range();
         }
     }
     if (close(fd) != 0 && rc == SSD_OK) rc = fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
@@ -1509,9 +1600,16 @@ extern "C" int ssd_run_files(ssd_ctx* c, const char* path_r1, const char* path_r
     if (rc == SSD_OK) {
         std::lock_guard<std::mutex> turn(g_h2d_turn);
         int rc2 = SSD_OK;
-        std::thread other([&] { rc2 = run_lanes(c, path_r2, 4, 4, upload_file_worker, c->device, fd[1], (size_t)0, size[1], (uint8_t*)c->b_in2.p); });
-        rc = run_lanes(c, path_r1, 0, 4, upload_file_worker, c->device, fd[0], (size_t)0, size[0], (uint8_t*)c->b_in1.p);
+        RangeMap m1, m2;
+        m1.open_range(fd[0], 0, size[0], false);
+        m2.open_range(fd[1], 0, size[1], false);
+        std::thread other([&] {
+            rc2 = run_lanes(c, path_r2, kIoHalf, kIoHalf, upload_file_worker, c->device, fd[1], (const uint8_t*)m2.data, (size_t)0, size[1], (uint8_t*)c->b_in2.p);
+        });
+        rc = run_lanes(c, path_r1, 0, kIoHalf, upload_file_worker, c->device, fd[0], (const uint8_t*)m1.data, (size_t)0, size[0], (uint8_t*)c->b_in1.p);
         other.join();
+        m1.close_range();
+        m2.close_range();
         if (rc == SSD_OK) rc = rc2;
     }
     for (int k = 0; k < 2; k++)
@@ -1533,7 +1631,10 @@ extern "C" int ssd_annotated_file(ssd_ctx* c, const char* path_in, const char* o
     for (int k = 0; k < kIoLanes && rc == SSD_OK; k++) rc = c->io[k].init();
     if (rc == SSD_OK) {
         std::lock_guard<std::mutex> turn(g_h2d_turn);
-        rc = run_lanes(c, path_in, 0, kIoLanes, upload_file_worker, c->device, fd, (size_t)0, size, (uint8_t*)c->b_in1.p);
+        RangeMap m;
+        m.open_range(fd, 0, size, false);
+        rc = run_lanes(c, path_in, 0, kIoLanes, upload_file_worker, c->device, fd, (const uint8_t*)m.data, (size_t)0, size, (uint8_t*)c->b_in1.p);
+        m.close_range();
     }
     close(fd);
     if (rc != SSD_OK) return rc;
@@ -1556,7 +1657,10 @@ extern "C" int ssd_load_file_range(ssd_ctx* c, int slot, const char* path, uint6
     for (int k = 0; k < kIoLanes && rc == SSD_OK; k++) rc = c->io[k].init();
     if (rc == SSD_OK) {
         std::lock_guard<std::mutex> turn(g_h2d_turn);
-        rc = run_lanes(c, path, 0, kIoLanes, upload_file_worker, c->device, fd, off, len, (uint8_t*)buf.p);
+        RangeMap m;
+        m.open_range(fd, off, len, false);
+        rc = run_lanes(c, path, 0, kIoLanes, upload_file_worker, c->device, fd, (const uint8_t*)m.data, off, len, (uint8_t*)buf.p);
+        m.close_range();
     }
     close(fd);
     if (rc == SSD_OK) c->loaded[slot] = len;

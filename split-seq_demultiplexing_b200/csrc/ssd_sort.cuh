@@ -365,6 +365,51 @@ __global__ void k_collect_irr(const uint64_t* ann, uint64_t n, const uint8_t* r2
     out[atomicAdd(cursor, 1ull)] = k;
 }
 
+// Multi-GPU -m decision: a cell is UNDECIDED when no rank alone holds >= m distinct UMIs of it (dmax[cell] < m, the all-reduced
+// MAX of the ranks' local counts) although all ranks together hold >= m reads of it (reads[cell], the all-reduced SUM).  Only
+// the (cell, UMI) keys of such cells have to be exchanged: every rank holds fewer than m distinct ones per cell.  This gathers
+// this batch's keys of the undecided cells (duplicates kept): regular keys and irregular keys, one warp-aggregated cursor each.
+__global__ void __launch_bounds__(256) k_undecided_keys(const uint64_t* __restrict__ ann, uint64_t n, const uint8_t* r2buf, const uint32_t* __restrict__ reads,
+                                                        const uint32_t* __restrict__ dmax, uint32_t m, int umi_bits, uint64_t* keys_out, IrrKey* irr_out,
+                                                        unsigned long long* cursors)
+{
+    const int lane = threadIdx.x & 31;
+    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = base + lane;
+        uint64_t a = r < n ? ann[r] : 0ull;
+        uint32_t st = ann_state(a);
+        if (st) {
+            const uint32_t cell = ann_cell(a);
+            if (!(__ldg(dmax + cell) < m && __ldg(reads + cell) >= m)) st = 0;
+        }
+        const uint32_t reg = __ballot_sync(0xFFFFFFFFu, st == 1u), irr = __ballot_sync(0xFFFFFFFFu, st == 2u);
+        unsigned long long b0 = 0, b1 = 0;
+        if (lane == 0) {
+            if (reg) b0 = atomicAdd(&cursors[0], (unsigned long long)__popc(reg));
+            if (irr) b1 = atomicAdd(&cursors[1], (unsigned long long)__popc(irr));
+        }
+        b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
+        b1 = __shfl_sync(0xFFFFFFFFu, b1, 0);
+        const uint32_t below = (1u << lane) - 1u;
+        if (st == 1u) keys_out[b0 + (uint32_t)__popc(reg & below)] = ((uint64_t)ann_cell(a) << umi_bits) | ann_payload(a);
+        if (st == 2u) {
+            const uint64_t payload = ann_payload(a);
+            const uint32_t ulen = (uint32_t)(payload & 31u);
+            const uint8_t* p = r2buf + (size_t)(payload >> 5);
+            uint64_t hi = 0, lo = 0;
+            for (uint32_t j = 0; j < ulen; j++) {
+                const uint64_t c = p[j];
+                if (j < 4) hi |= c << (8 * (3 - j));
+                else lo |= c << (8 * (9 - j));
+            }
+            IrrKey k;
+            k.hi = ((uint64_t)ann_cell(a) << kIrrCellShift) | ((uint64_t)ulen << 32) | hi;
+            k.lo = lo;
+            irr_out[b1 + (uint32_t)__popc(irr & below)] = k;
+        }
+    }
+}
+
 __global__ void k_iota(uint32_t* p, uint64_t n)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

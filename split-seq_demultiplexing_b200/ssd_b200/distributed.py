@@ -121,25 +121,85 @@ def _adopt_torch_stream(dm):
     dm.set_stream(handle if handle != 0 else 1)
 
 
-def global_filter(dm, world: int, group=None) -> dict:
-    """After dm.demux_device(...) on every rank: make the -m decision global and exact, return dm's stats.
-    Collectives: all-reduce of the read histogram, all-to-all of the unique keys, all-reduce of the distinct table."""
+def _gather_rows(rows, counts_per_rank: List[int], group=None):
+    """Everybody's first counts_per_rank[k] rows of `rows` (same trailing shape on every rank), concatenated in rank order:
+    an all-gather padded to the longest list, the padding dropped afterwards."""
+    import torch
     import torch.distributed as dist
-    if world > 1:
-        # torch's collectives are ordered on torch's current stream only: the library must enqueue on that very stream, or it
-        # reads what NCCL has not delivered yet (and NCCL sends tables the kernels have not finished).  Idempotent.
-        _adopt_torch_stream(dm)
-        pending = dist.all_reduce(dm.reads_histogram(), group=group, async_op=True)  # overlaps the key exchange
-        if dm.filter_mode == "distinct_umi":
-            import torch
-            rank = dist.get_rank(group)
-            keys, offsets, irr = dm.partition_keys(world)
-            rk, ri = exchange_owned(keys, [offsets[k + 1] - offsets[k] for k in range(world)], irr, group=group)
-            dm.count_distinct_owned(rk, ri, rank, world)
-            dist.all_reduce(dm.distinct_histogram(), group=group)
-        pending.wait()
+    world, longest = len(counts_per_rank), max(counts_per_rank)
+    if longest == 0:
+        return rows[:0]
+    rank = dist.get_rank(group)
+    pad = torch.zeros((longest,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    pad[: counts_per_rank[rank]] = rows[: counts_per_rank[rank]]
+    everything = torch.empty((world * longest,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(everything, pad, group=group)
+    else:
+        dist.all_gather(list(everything.view((world, longest) + tuple(rows.shape[1:])).unbind(0)), pad, group=group)
+    return torch.cat([everything[k * longest: k * longest + counts_per_rank[k]] for k in range(world)])
+
+
+def global_filter(dm, world: int, group=None, exact_table: bool = False) -> dict:
+    """After dm.demux_device(...) on every rank: make the -m decision global and exact, return dm's stats.
+
+    reads mode: one all-reduce of the read histogram.  distinct-UMI mode (V2:411), without shipping every key: every rank counts
+    the distinct UMIs of ITS OWN records per cell; a cell passes as soon as one rank alone counts >= m (all-reduce MAX of those
+    tables) and fails when all ranks together hold < m reads of it (all-reduce SUM of the read histograms, distinct <= reads).
+    Only the cells in between are undecided, and every rank holds fewer than m distinct UMIs of each of them: their keys are
+    all-gathered (a few hundred thousand instead of every rank's millions), counted exactly by everybody, done.  One host round
+    trip (the sizes of the gather), no owner partition.  Afterwards the distinct table holds, per cell, the exact global count
+    for the undecided cells and the largest local count elsewhere: a lower bound that decides -m like the exact table.
+    exact_table=True runs the exchange by owner rank instead and leaves the exact global distinct count of every cell (what a
+    per-cell table wants)."""
+    if world <= 1:
+        return dm.filter_single()
+    import torch
+    import torch.distributed as dist
+    # torch's collectives are ordered on torch's current stream only: the library must enqueue on that very stream, or it
+    # reads what NCCL has not delivered yet (and NCCL sends tables the kernels have not finished).  Idempotent.
+    _adopt_torch_stream(dm)
+    if dm.filter_mode != "distinct_umi":
+        dist.all_reduce(dm.reads_histogram(), group=group)
         return dm.build_filter()
-    return dm.filter_single()
+    if exact_table:
+        return _global_filter_by_owner(dm, world, group)
+    rank = dist.get_rank(group)
+    hist = dm.reads_histogram()
+    reads = hist.clone()
+    pending = dist.all_reduce(reads, group=group, async_op=True)  # overlaps the local distinct count (which needs the LOCAL histogram)
+    dm.distinct_local()
+    dmax = dm.distinct_histogram().clone()
+    dist.all_reduce(dmax, op=dist.ReduceOp.MAX, group=group)
+    pending.wait()
+    keys, irr, counts = dm.undecided_keys(reads, dmax)
+    all_counts = torch.empty((world, 2), dtype=torch.int64, device=counts.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(all_counts, counts.view(1, 2), group=group)
+    else:
+        dist.all_gather(list(all_counts.unbind(0)), counts.clone(), group=group)
+    sizes = all_counts.cpu().tolist()  # the one host round trip of the step
+    all_k = _gather_rows(keys, [c[0] for c in sizes], group=group)
+    all_i = _gather_rows(irr, [c[1] for c in sizes], group=group)
+    dm.count_distinct(all_k, all_i)  # exact global counts of the undecided cells (zero elsewhere)
+    exact = dm.distinct_histogram()
+    torch.maximum(exact, dmax, out=exact)
+    hist.copy_(reads)
+    return dm.build_filter()
+
+
+def _global_filter_by_owner(dm, world: int, group=None) -> dict:
+    """The -m decision with the exact global distinct count of EVERY cell: all (cell, UMI) keys go to the rank that owns their cell
+    (all-to-all, duplicates kept; irregular keys to everybody), every rank counts the cells it owns, the table is all-reduced."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    pending = dist.all_reduce(dm.reads_histogram(), group=group, async_op=True)  # overlaps the key exchange
+    keys, offsets, irr = dm.partition_keys(world)
+    rk, ri = exchange_owned(keys, [offsets[k + 1] - offsets[k] for k in range(world)], irr, group=group)
+    dm.count_distinct_owned(rk, ri, rank, world)
+    dist.all_reduce(dm.distinct_histogram(), group=group)
+    pending.wait()
+    return dm.build_filter()
 
 
 def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None, rounds: int = None) -> dict:
@@ -170,7 +230,9 @@ def two_pass(dm, phase1, emit, world: int = 1, group=None, timing: dict = None, 
                 keys, offsets, irr = dm.partition_keys(world)
                 k, i = exchange_owned(keys, [offsets[j + 1] - offsets[j] for j in range(world)], irr, group=group)
             else:
-                k, i = dm.local_unique_keys()
+                # one GPU: the batch's keys as they are (one compaction pass over the annotation words, duplicates kept);
+                # the per-cell sets at the end do not need them sorted or unique
+                k, _, i = dm.partition_keys(1)
             kept_k.append(k.clone())
             kept_i.append(i.clone())
         sync()

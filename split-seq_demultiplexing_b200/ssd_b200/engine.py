@@ -168,6 +168,26 @@ class Demultiplexer:
         self._check(self.lib.ssd_count_distinct_owned(self._ctx, C.c_void_p(keys.data_ptr() if keys.numel() else 0), keys.numel(),
                                                       C.c_void_p(irr.data_ptr() if irr.numel() else 0), irr.numel() // 2, rank, world))
 
+    def distinct_local(self):
+        """Per-cell distinct-UMI counts of THIS batch into the distinct table (the read histogram must still be the batch's own)."""
+        self._check(self.lib.ssd_distinct_local(self._ctx))
+
+    def undecided_keys(self, reads_global, distinct_max):
+        """This batch's (cell, UMI) keys (duplicates kept) of the cells no rank decides alone: distinct_max[cell] < m <= reads_global[cell]
+        (int32 CUDA tensors over the cell space).  Returns (int64[n_regular_keys] buffer, int64[n_irregular_keys, 2] buffer,
+        int64[2] counts on the device): only the first counts[0] / counts[1] entries of the buffers are keys, once the stream ran."""
+        import torch
+        pk, pi, pc = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.lib.ssd_undecided_keys(self._ctx, C.c_void_p(reads_global.data_ptr()), C.c_void_p(distinct_max.data_ptr()),
+                                                C.byref(pk), C.byref(pi), C.byref(pc)))
+        st = self.stats()
+        nk, ni = st["n_regular_keys"], st["n_irregular_keys"]
+        keys = torch.as_tensor(_DevArray(pk.value, nk, "<i8", self), device="cuda") if nk else torch.empty(0, dtype=torch.int64, device="cuda")
+        irr = (torch.as_tensor(_DevArray(pi.value, 2 * ni, "<i8", self), device="cuda").view(-1, 2)
+               if ni else torch.empty((0, 2), dtype=torch.int64, device="cuda"))
+        counts = torch.as_tensor(_DevArray(pc.value, 2, "<i8", self), device="cuda")
+        return keys, irr, counts
+
     def build_filter(self) -> dict:
         st = L.Stats()
         self._check(self.lib.ssd_build_filter(self._ctx, C.byref(st)))

@@ -153,6 +153,18 @@ class _StandIn:
     def local_unique_keys(self):
         return torch.unique(self.keys), torch.empty((0, 2), dtype=torch.int64)
 
+    def distinct_local(self):
+        self._count(self.keys)
+
+    def undecided_keys(self, reads_global, distinct_max):
+        cells = self.keys >> UMI_BITS
+        und = (distinct_max[cells] < self.m) & (reads_global[cells] >= self.m)
+        k = self.keys[und]
+        pad = torch.full((self.keys.numel(),), -7, dtype=torch.int64)  # a buffer of full capacity, like the library's
+        pad[: k.numel()] = k
+        self.n_undecided_sent = int(k.numel())
+        return pad, torch.empty((0, 2), dtype=torch.int64), torch.tensor([k.numel(), 0], dtype=torch.int64)
+
     def partition_keys(self, world):
         from ssd_b200 import distributed as D
         rows, counts = D.group_by_owner(self.keys, self.keys >> UMI_BITS, self.SHIFT, self.NB, world)
@@ -234,3 +246,61 @@ def test_two_pass_over_ranks_with_unequal_batch_counts(tmp_path, counts):
             assert got[0] == len(torch.unique(cells)) and got[1] == int(passing.sum())
         retained += got[2]
     assert retained == int(passing[cells].sum())
+
+
+def _global_filter_worker(rank, world, port, out_dir, exact):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ssd_b200 import distributed as D
+    dm = _StandIn(m=5)
+    cells, umis = _global_filter_input(rank)
+    dm.load(cells, umis)
+    st = D.global_filter(dm, world, exact_table=exact)
+    np.save(os.path.join(out_dir, "gf_%d.npy" % rank), np.array([st["n_cells"], st["n_passing_cells"], st["n_retained"], getattr(dm, "n_undecided_sent", -1),
+                                                                 int(cells.numel())]))
+    np.save(os.path.join(out_dir, "gf_distinct_%d.npy" % rank), dm.distinct_histogram().numpy())
+    np.save(os.path.join(out_dir, "gf_hist_%d.npy" % rank), dm.reads_histogram().numpy())
+    dist.destroy_process_group()
+
+
+def _global_filter_input(rank):
+    """Cells of every kind for m = 5: decided by one rank alone, failing on the read count, and undecided ones (fewer than 5
+    distinct UMIs on every rank, 5 or more reads in total -- some of which pass only once the ranks' UMIs are united, some of
+    which still fail because the ranks hold the SAME UMIs)."""
+    rng = np.random.default_rng(4242)
+    pool = rng.choice(N_CELLS, size=600, replace=False)
+    rng = np.random.default_rng(900 + rank)
+    big = rng.choice(pool[:200], size=6000)                       # plenty of reads per cell: decided locally
+    small = rng.choice(pool[200:500], size=700)                   # 2-3 reads per cell and rank: undecided or failing
+    same = np.repeat(pool[500:600], 3)                            # the same three UMIs on every rank: 3 distinct globally, >= 5 reads
+    cells = np.concatenate([big, small, same])
+    umis = np.concatenate([rng.integers(0, 50, size=big.size), rng.integers(0, 1 << 16, size=small.size), np.tile(np.arange(3), 100)])
+    return torch.from_numpy(cells).to(torch.int64), torch.from_numpy(umis).to(torch.int64)
+
+
+@pytest.mark.parametrize("world,exact", [(2, False), (3, False), (2, True)])
+def test_global_filter_decides_like_one_process(tmp_path, world, exact):
+    """global_filter's exchange of the UNDECIDED cells' keys only (and the exchange by owner rank behind exact_table=True): the
+    same passing cells as one process that sees every key; only a fraction of the keys travels."""
+    mp.spawn(_global_filter_worker, args=(world, _free_port(), str(tmp_path), exact), nprocs=world, join=True)
+    parts = [_global_filter_input(r) for r in range(world)]
+    cells = torch.cat([c for c, _ in parts])
+    keys = torch.unique(torch.cat([(c << UMI_BITS) | u for c, u in parts]))
+    distinct = torch.zeros(N_CELLS, dtype=torch.int32)
+    distinct.index_add_(0, keys >> UMI_BITS, torch.ones(keys.numel(), dtype=torch.int32))
+    passing = distinct >= 5
+    assert 0 < int(passing.sum()) < len(torch.unique(cells))
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), "gf_%d.npy" % r))
+        table = torch.from_numpy(np.load(os.path.join(str(tmp_path), "gf_distinct_%d.npy" % r)))
+        hist = torch.from_numpy(np.load(os.path.join(str(tmp_path), "gf_hist_%d.npy" % r)))
+        assert got[0] == len(torch.unique(cells)) and got[1] == int(passing.sum())
+        assert got[2] == int(passing[parts[r][0]].sum())
+        assert bool(((table >= 5) == passing).all())               # the table decides like the exact one ...
+        assert bool((table <= distinct).all())                     # ... and never overstates a count
+        assert int(hist.sum()) == cells.numel()                    # the read histogram ends up global
+        if exact:
+            assert bool((table == distinct).all())
+        else:
+            assert 0 < got[3] < got[4] // 4                        # only the undecided cells' keys were sent
