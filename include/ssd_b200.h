@@ -163,6 +163,11 @@ int ssd_distinct_histogram_device(ssd_ctx *ctx, uint32_t **d_distinct);
  * unique; the arrays stay owned by the context. */
 int ssd_local_unique_keys(ssd_ctx *ctx, uint64_t **d_keys, uint64_t *n_keys, void **d_irregular,
                           uint64_t *n_irregular);
+/* Per-cell x UMI table of the last batch (extension, SURVEY 8f.4: the table a downstream counter wants, without a FASTQ round
+ * trip): the sorted unique (cell,UMI) keys as above, and next to them the number of READS each key was seen in (uint32).  The
+ * arrays live on the device and belong to the context. */
+int ssd_cell_umi_table(ssd_ctx *ctx, uint64_t **d_keys, uint32_t **d_reads, uint64_t *n_keys, void **d_irregular,
+                       uint32_t **d_irregular_reads, uint64_t *n_irregular);
 /* Count distinct keys per cell into the distinct histogram (overwrites it).  Inputs are device arrays
  * in the formats above, not necessarily unique or sorted (e.g. the concatenation of what peers sent
  * after an all-to-all by cell range); they are sorted in place. */
@@ -182,16 +187,26 @@ int ssd_count_distinct_owned(ssd_ctx *ctx, uint64_t *d_keys, uint64_t n_keys, vo
                              uint64_t n_irregular, int rank, int world);
 /* Multi-GPU hosts, the -m decision without shipping every key (what ssd_b200.distributed.global_filter does):
  *   ssd_distinct_local   per-cell distinct-UMI counts of THIS batch into the distinct table (the read histogram must still be the
- *                        batch's own).  A cell passes when any rank alone counts >= m (all-reduce MAX of these tables) and fails
- *                        when all ranks together hold < m reads of it (all-reduce SUM of the read histograms).
- *   ssd_undecided_keys   this batch's (cell,UMI) keys, duplicates kept, of the cells in between (d_distinct_max[cell] < m <=
- *                        d_reads_global[cell]; both device arrays of n^3 uint32): *d_keys / *d_irregular in the formats above,
- *                        *d_counts -> two uint64 on the device (regular, irregular) valid once the stream has run.  Every rank
- *                        holds fewer than m distinct keys per such cell, so all-gathering them and counting with
- *                        ssd_count_distinct decides those cells exactly. */
+ *                        batch's own).
+ *   ssd_pack_decision    *d_packed -> n^3 uint64 on the device, one word per cell: bits 0..39 = reads of the cell in this batch,
+ *                        bit 40 = this batch alone counts >= m distinct UMIs.  The caller all-reduces (SUM) the array over the
+ *                        ranks in place: bits 0..39 = global reads, bits 40.. = number of ranks that decide "pass" alone.  A
+ *                        cell passes when that number is not zero and fails when the global reads are < m (distinct <= reads).
+ *   ssd_undecided_keys   this batch's (cell,UMI) keys, duplicates kept, of the cells in between (given the all-reduced words) as
+ *                        ONE packed list of capacity + 1 records in the irregular-key format above (regular UMIs spelled out as
+ *                        bytes): *d_records -> record 0 is the header {hi = ~0, lo = number of keys this batch had}, records
+ *                        1 .. capacity are keys, unused ones all ones (padding).  lo > capacity means the list is incomplete.
+ *                        Nothing comes back to the host: the lists of all ranks are all-gathered as they are (fixed size), and
+ *                        ssd_count_distinct(ctx, NULL, 0, gathered, world * (capacity + 1)) counts them (padding and headers
+ *                        are skipped).  Every rank holds fewer than m distinct keys per such cell, so this decides those cells
+ *                        exactly.
+ *   ssd_adopt_decision   after that count: read histogram := global reads, distinct[cell] := max(distinct[cell], m) for the cells
+ *                        some rank decided alone.  The distinct table is then a lower bound of the exact global one that decides
+ *                        -m exactly like it, identical on all ranks; ssd_build_filter follows. */
 int ssd_distinct_local(ssd_ctx *ctx);
-int ssd_undecided_keys(ssd_ctx *ctx, const uint32_t *d_reads_global, const uint32_t *d_distinct_max, uint64_t **d_keys,
-                       void **d_irregular, uint64_t **d_counts);
+int ssd_pack_decision(ssd_ctx *ctx, uint64_t **d_packed);
+int ssd_undecided_keys(ssd_ctx *ctx, const uint64_t *d_packed_global, uint64_t capacity, void **d_records);
+int ssd_adopt_decision(ssd_ctx *ctx, const uint64_t *d_packed_global);
 /* Owner rank of a cell in a world of W ranks: ((cell >> *shift) * W) / *n_buckets. */
 int ssd_owner_layout(const ssd_ctx *ctx, int *shift, int *n_buckets);
 /* Bit width of the 2-bit-packed UMI inside a regular key (cell id = key >> umi_bits). */

@@ -7,6 +7,9 @@
 #   bash profiles/ab_variants.sh clean
 VARIANTS=(
   "base||0"
+  "g2t16|-DSSD_SCAN_TILE=16384 -DSSD_SCAN_SLOTS=4 -DSSD_SCAN_BGROUPS=2|1"
+  "g3t16a4|-DSSD_SCAN_TILE=16384 -DSSD_SCAN_SLOTS=5 -DSSD_SCAN_BGROUPS=3 -DSSD_SCAN_BWARPS=6 -DSSD_SCAN_AWARPS=4|0"
+  "g2t16s5|-DSSD_SCAN_TILE=16384 -DSSD_SCAN_SLOTS=5 -DSSD_SCAN_BGROUPS=2|0"
 )
 root=$(cd "$(dirname "$0")/.." && pwd)
 src=$root/split-seq_demultiplexing_b200/csrc
@@ -21,7 +24,7 @@ run)
   cd "$root"
   for v in "${VARIANTS[@]}"; do
     IFS='|' read -r name flags t <<< "$v"
-    SSD_B200_LIB=$root/profiles/v_$name.so python bench.py --steps 30 --warmup 3 --no-cpu-baseline --e2e-steps 0 2>&1 | python -c "
+    SSD_B200_LIB=$root/profiles/v_$name.so python bench.py --steps 30 --warmup 3 --no-cpu-baseline --e2e-steps 0 --no-other-configs --no-e2e-files --no-parity-check 2>&1 | python -c "
 import sys, json
 l = json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('$name', round(l['ms_per_step'], 3), {k: round(v, 3) for k, v in l['roofline']['stage_ms_per_step'].items()})"

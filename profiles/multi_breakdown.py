@@ -1,7 +1,8 @@
-"""Where a multi-GPU step spends its time: run under torchrun, prints per-phase milliseconds on rank 0."""
+"""Where a multi-GPU step spends its time: run under torchrun, prints per-phase milliseconds on rank 0.
+CUDA events on the step's stream between the phases of ssd_b200.distributed.global_filter (no synchronisation inside the step,
+so the phases overlap with the host exactly as in bench.py); the sum of the phases is the step."""
 import os
 import sys
-import time
 
 import torch
 import torch.distributed as dist
@@ -14,7 +15,7 @@ from ssd_b200 import distributed as D  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
-dist.init_process_group("nccl")
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 wl = fu.load_whitelist()
 n = 10_000_000
 dm = ssd_b200.Demultiplexer(wl, errors=1, min_count=10, device=local, record_bytes_hint=160)
@@ -22,40 +23,46 @@ spec = ssd_b200.synth_spec(wl, n, seed=0x5EED0001, first_index=rank * n + 1)
 d1, d2 = ssd_b200.synth_device(dm, spec)
 stream = torch.cuda.Stream()
 out = torch.empty(int(n * 330), dtype=torch.uint8, device="cuda")
-acc = {}
-
-
-def tick(name, t0):
-    torch.cuda.synchronize()
-    acc[name] = acc.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
-    return time.perf_counter()
-
-
+cap = D.UNDECIDED_CAPACITY
+names = ["demux", "distinct_local", "pack + all-reduce(sum, 7 MB)", "undecided_keys", "all-gather", "count_distinct + adopt", "build_filter (sync)", "emit"]
+acc = [0.0] * len(names)
+und = 0
+STEPS, WARM = 13, 3
 with torch.cuda.stream(stream):
     dm.set_stream(stream.cuda_stream)
-    for it in range(8):
-        if it == 3:
-            acc.clear()
+    for it in range(STEPS):
         torch.cuda.synchronize()
         dist.barrier()
-        t = time.perf_counter()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        k = 0
+        ev[k].record(); k += 1
         dm.demux_device(d1.data_ptr(), d1.numel(), d2.data_ptr(), d2.numel())
-        t = tick("demux", t)
-        dist.all_reduce(dm.reads_histogram())
-        t = tick("allreduce hist", t)
-        keys, offsets, irr = dm.partition_keys(world)
-        t = tick("partition", t)
-        kc = torch.tensor([offsets[k + 1] - offsets[k] for k in range(world)], dtype=torch.int64, device=keys.device)
-        rk, ri = D.exchange_owned(keys, kc, irr)
-        t = tick("exchange", t)
-        dm.count_distinct_owned(rk, ri, rank, world)
-        t = tick("count distinct", t)
-        dist.all_reduce(dm.distinct_histogram())
-        t = tick("allreduce distinct", t)
+        ev[k].record(); k += 1
+        dm.distinct_local()
+        ev[k].record(); k += 1
+        packed = dm.pack_decision()
+        dist.all_reduce(packed)
+        ev[k].record(); k += 1
+        mine = dm.undecided_keys(packed, cap)
+        ev[k].record(); k += 1
+        everything = torch.empty((world * (cap + 1), 2), dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(everything, mine)
+        ev[k].record(); k += 1
+        dm.count_distinct(everything[:0, 0], everything)
+        dm.adopt_decision(packed)
+        ev[k].record(); k += 1
         st = dm.build_filter()
-        t = tick("filter", t)
+        ev[k].record(); k += 1
         dm.emit_device(ssd_b200.EMIT_PASSING, out.data_ptr(), out.numel())
-        t = tick("emit", t)
+        ev[k].record(); k += 1
+        torch.cuda.synchronize()
+        if it >= WARM:
+            for j in range(len(names)):
+                acc[j] += ev[j].elapsed_time(ev[j + 1])
+            und = int(everything.view(world, cap + 1, 2)[:, 0, 1].max())
+res = torch.tensor(acc, device="cuda") / (STEPS - WARM)
+dist.all_reduce(res, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print({k: round(v / 5, 3) for k, v in acc.items()}, "sum", round(sum(acc.values()) / 5, 3))
+    print({"n_gpus": world, "phases_ms_max_over_ranks": {a: round(float(b), 3) for a, b in zip(names, res.tolist())}, "sum_ms": round(float(res.sum()), 3),
+           "undecided_keys_max_per_rank": und, "capacity": cap})
 dist.destroy_process_group()

@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -85,7 +86,7 @@ struct ssd_ctx {
 
     DevCounters* d_cnt = nullptr;
     unsigned long long* d_err_off = nullptr;
-    unsigned long long* d_ucnt = nullptr;  // [2] cursors of ssd_undecided_keys
+    unsigned long long* d_ucnt = nullptr;  // [2] cursor of ssd_undecided_keys
     uint8_t* d_lut = nullptr;
     uint8_t* d_wl_len = nullptr;
     unsigned long long* d_wl64 = nullptr;  // whitelist entries as 8-byte words (tiled writer)
@@ -120,6 +121,8 @@ struct ssd_ctx {
     DevBuf b_in1, b_in2, b_out;
     size_t loaded[2] = {0, 0};  // bytes ssd_load_file_range put into b_in1 / b_in2
     IoLane io[kIoLanes];  // pinned slots + streams of the file-to-file entry points (created on first use)
+    DevBuf b_first, b_runs;  // ssd_cell_umi_table: where each unique key's run starts, run lengths
+    DevBuf b_und, b_und_bits, b_pack;  // multi-GPU -m decision: packed key list, undecided-cell bitmap, packed per-cell words
     DevBuf b_os, b_irr_table;  // one-kernel-per-pass sort: histograms, tickets, tile status; hash set of the irregular keys
     DevBuf b_seg;              // per-cell hash sets of the regular keys: key counts (when not the read histogram) and segment offsets
     DevBuf b_sp_cells, b_sp_cells_alt, b_sp_recs, b_sp_recs_alt, b_sp_off, b_bk_cell, b_bk_off, b_bk_first;
@@ -310,7 +313,7 @@ int os_sort64(ssd_ctx* c, bool from_ann, uint64_t* a, uint64_t* b, uint64_t n_ke
 // sort + unique of regular keys.  `keys` holds n keys (or, when from_ann, the keys are taken from the
 // annotation words of the batch and `keys` only is the buffer they are compacted into by the first pass);
 // result: *uniq (a context buffer or `keys`), *n_uniq
-int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint32_t* total_host, bool from_ann = false)
+int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint32_t* total_host, bool from_ann = false, uint32_t* first = nullptr)
 {
     // enqueues only: *total_host (pinned or pageable) is valid after the caller synchronised c->stream
     *uniq = keys;
@@ -324,7 +327,7 @@ int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint3
     OKR(ensure(c, c->b_pos, (n + 1) * sizeof(uint32_t)));
     uint32_t* pos = (uint32_t*)c->b_pos.p;
     OKR(exclusive_scan<uint32_t>(c, HeadFlag64{sorted}, n, pos));
-    k_compact64<<<blocks_for(n, kThreads), kThreads, 0, c->stream>>>(sorted, pos, n, other);
+    k_compact64<<<blocks_for(n, kThreads), kThreads, 0, c->stream>>>(sorted, pos, n, other, first);
     c->n_launches += 1;
     CU(c, cudaMemcpyAsync(total_host, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     *uniq = other;
@@ -332,7 +335,7 @@ int sort_unique64(ssd_ctx* c, uint64_t* keys, uint64_t n, uint64_t** uniq, uint3
 }
 
 // sort + unique of irregular keys through an index permutation (128-bit LSD: low word, then high word)
-int sort_unique_irr(ssd_ctx* c, IrrKey* keys, uint64_t n, IrrKey** uniq, uint32_t* total_host)
+int sort_unique_irr(ssd_ctx* c, IrrKey* keys, uint64_t n, IrrKey** uniq, uint32_t* total_host, uint32_t* first = nullptr)
 {
     // enqueues only, like sort_unique64
     *uniq = keys;
@@ -362,7 +365,7 @@ int sort_unique_irr(ssd_ctx* c, IrrKey* keys, uint64_t n, IrrKey** uniq, uint32_
     uint32_t* pos = (uint32_t*)c->b_pos.p;
     OKR(exclusive_scan<uint32_t>(c, HeadFlagIrr{keys, perm}, n, pos));
     IrrKey* out = (IrrKey*)c->b_irr_alt.p;
-    k_compact_irr<<<nb, kThreads, 0, c->stream>>>(keys, perm, pos, n, out);
+    k_compact_irr<<<nb, kThreads, 0, c->stream>>>(keys, perm, pos, n, out, first);
     CU(c, cudaMemcpyAsync(total_host, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     *uniq = out;
     return SSD_OK;
@@ -371,7 +374,7 @@ int sort_unique_irr(ssd_ctx* c, IrrKey* keys, uint64_t n, IrrKey** uniq, uint32_
 // Regular keys on the context's stream, irregular keys (few, launch-latency bound) next to them on the side
 // stream with their own scratch; joined before returning.  from_ann: keys come from the batch's annotations.
 int sort_unique_both(ssd_ctx* c, uint64_t* keys, uint64_t n_keys, IrrKey* irr, uint64_t n_irr, bool from_ann, uint64_t** uk, uint64_t* nuk,
-                     IrrKey** ui, uint64_t* nui)
+                     IrrKey** ui, uint64_t* nui, uint32_t* first_k = nullptr, uint32_t* first_i = nullptr)
 {
     uint32_t tot_k = 0, tot_i = 0;
     const bool side = n_irr != 0 && c->side_stream != nullptr;
@@ -392,7 +395,7 @@ int sort_unique_both(ssd_ctx* c, uint64_t* keys, uint64_t n_keys, IrrKey* irr, u
             k_collect_irr<<<blocks_for(c->n_rec_r2, kThreads), kThreads, 0, c->stream>>>((const uint64_t*)c->b_ann.p, c->n_rec_r2, c->r2, irr, cursor);
             c->n_launches++;
         }
-        rc = sort_unique_irr(c, irr, n_irr, ui, &tot_i);
+        rc = sort_unique_irr(c, irr, n_irr, ui, &tot_i, first_i);
     } else {
         *ui = irr;
     }
@@ -404,7 +407,7 @@ int sort_unique_both(ssd_ctx* c, uint64_t* keys, uint64_t n_keys, IrrKey* irr, u
         std::swap(c->b_bsums, c->s_bsums);
         std::swap(c->b_pos, c->s_pos);
     }
-    if (rc == SSD_OK) rc = sort_unique64(c, keys, n_keys, uk, &tot_k, from_ann);
+    if (rc == SSD_OK) rc = sort_unique64(c, keys, n_keys, uk, &tot_k, from_ann, first_k);
     if (side) cudaStreamWaitEvent(c->stream, c->ev_join, 0);
     if (rc != SSD_OK) return rc;
     CU(c, cudaStreamSynchronize(c->stream));
@@ -843,7 +846,7 @@ extern "C" void ssd_destroy(ssd_ctx* c)
     DevBuf* bufs[] = {&c->b_status1, &c->b_status2, &c->b_r1_start, &c->b_r1_meta, &c->b_r1_base, &c->b_r1_tok, &c->b_ann, &c->b_keys, &c->b_keys_alt, &c->b_irr,
                       &c->b_irr_alt, &c->b_perm, &c->b_perm_alt, &c->b_tmp64a, &c->b_tmp64b, &c->b_counts, &c->b_offsets, &c->b_bsums,
                       &c->b_pos, &c->b_out_off, &c->b_cells, &c->b_in1, &c->b_in2, &c->b_out, &c->b_sp_cells, &c->b_sp_cells_alt, &c->b_sp_recs,
-                      &c->b_sp_recs_alt, &c->b_sp_off, &c->b_bk_cell, &c->b_bk_off, &c->b_bk_first, &c->b_os, &c->b_irr_table, &c->b_seg};
+                      &c->b_sp_recs_alt, &c->b_sp_off, &c->b_bk_cell, &c->b_bk_off, &c->b_bk_first, &c->b_os, &c->b_irr_table, &c->b_seg, &c->b_und, &c->b_und_bits, &c->b_pack, &c->b_first, &c->b_runs};
     for (DevBuf* b : bufs) release(*b);
     cudaFree(c->d_cnt);
     cudaFree(c->d_err_off);
@@ -1023,6 +1026,35 @@ extern "C" int ssd_local_unique_keys(ssd_ctx* c, uint64_t** d_keys, uint64_t* n_
     return SSD_OK;
 }
 
+extern "C" int ssd_cell_umi_table(ssd_ctx* c, uint64_t** d_keys, uint32_t** d_reads, uint64_t* n_keys, void** d_irregular, uint32_t** d_irregular_reads,
+                                  uint64_t* n_irregular)
+{
+    if (!c) return SSD_EINVAL;
+    if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_cell_umi_table before ssd_demux_device");
+    CU(c, cudaSetDevice(c->device));
+    StageTimer t(c, 2);
+    OKR(ensure(c, c->b_keys, std::max<uint64_t>(c->n_keys, 1) * sizeof(uint64_t)));
+    OKR(ensure(c, c->b_irr, std::max<uint64_t>(c->n_irr, 1) * sizeof(IrrKey)));
+    OKR(ensure(c, c->b_first, (c->n_keys + c->n_irr + 2) * sizeof(uint32_t)));
+    uint32_t *first_k = (uint32_t*)c->b_first.p, *first_i = first_k + c->n_keys + 1;
+    OKR(sort_unique_both(c, (uint64_t*)c->b_keys.p, c->n_keys, (IrrKey*)c->b_irr.p, c->n_irr, true, &c->uniq_keys, &c->n_uniq, &c->uniq_irr,
+                         &c->n_uniq_irr, first_k, first_i));
+    c->unique_done = true;
+    OKR(ensure(c, c->b_runs, (c->n_uniq + c->n_uniq_irr + 2) * sizeof(uint32_t)));
+    uint32_t *runs_k = (uint32_t*)c->b_runs.p, *runs_i = runs_k + c->n_uniq + 1;
+    if (c->n_uniq) k_run_lengths<<<blocks_for(c->n_uniq, kThreads), kThreads, 0, c->stream>>>(first_k, c->n_uniq, c->n_keys, runs_k);
+    if (c->n_uniq_irr) k_run_lengths<<<blocks_for(c->n_uniq_irr, kThreads), kThreads, 0, c->stream>>>(first_i, c->n_uniq_irr, c->n_irr, runs_i);
+    c->n_launches += (c->n_uniq ? 1 : 0) + (c->n_uniq_irr ? 1 : 0);
+    CU(c, cudaGetLastError());
+    if (d_keys) *d_keys = c->uniq_keys;
+    if (d_reads) *d_reads = runs_k;
+    if (n_keys) *n_keys = c->n_uniq;
+    if (d_irregular) *d_irregular = c->uniq_irr;
+    if (d_irregular_reads) *d_irregular_reads = runs_i;
+    if (n_irregular) *n_irregular = c->n_uniq_irr;
+    return SSD_OK;
+}
+
 namespace {
 // buckets of the owner partition: cell >> shift, at most 256 of them
 void owner_layout(const ssd_ctx* c, int* shift, int* n_buckets)
@@ -1180,28 +1212,71 @@ extern "C" int ssd_distinct_local(ssd_ctx* c)
     return distinct_counts_local(c);
 }
 
-extern "C" int ssd_undecided_keys(ssd_ctx* c, const uint32_t* d_reads_global, const uint32_t* d_distinct_max, uint64_t** d_keys, void** d_irregular,
-                                  uint64_t** d_counts)
+namespace {
+// -m as the kernels of the exchange compare it (distinct counts are 32-bit): never = no count can reach it
+inline uint32_t min_count_u32(const ssd_ctx* c, bool* never)
 {
-    if (!c || !d_reads_global || !d_distinct_max || !d_keys || !d_irregular || !d_counts) return SSD_EINVAL;
+    *never = c->cfg.min_count > 0xFFFFFFFFll;
+    return (uint32_t)std::min<long long>(std::max<long long>(c->cfg.min_count, 0), 0xFFFFFFFFll);
+}
+}  // namespace
+
+extern "C" int ssd_pack_decision(ssd_ctx* c, uint64_t** d_packed)
+{
+    if (!c || !d_packed) return SSD_EINVAL;
+    if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_pack_decision before ssd_demux_device");
+    CU(c, cudaSetDevice(c->device));
+    StageTimer t(c, 2);
+    const uint64_t nc = c->n_cells_total;
+    OKR(ensure(c, c->b_pack, nc * sizeof(uint64_t)));
+    bool never;
+    const uint32_t m = min_count_u32(c, &never);
+    k_pack_decision<<<blocks_for(nc, kThreads), kThreads, 0, c->stream>>>(c->d_hist, c->d_distinct, nc, m, never, (unsigned long long*)c->b_pack.p);
+    c->n_launches++;
+    CU(c, cudaGetLastError());
+    *d_packed = (uint64_t*)c->b_pack.p;
+    return SSD_OK;
+}
+
+extern "C" int ssd_undecided_keys(ssd_ctx* c, const uint64_t* d_packed_global, uint64_t capacity, void** d_records)
+{
+    if (!c || !d_packed_global || !d_records || capacity == 0) return SSD_EINVAL;
     if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_undecided_keys before ssd_demux_device");
     CU(c, cudaSetDevice(c->device));
     StageTimer t(c, 2);
-    c->unique_done = false;  // the key buffers are reused
-    const uint64_t n = c->n_rec_r2;
-    OKR(ensure(c, c->b_keys, std::max<uint64_t>(c->n_keys, 1) * sizeof(uint64_t)));
-    OKR(ensure(c, c->b_irr, std::max<uint64_t>(c->n_irr, 1) * sizeof(IrrKey)));
-    CU(c, cudaMemsetAsync(c->d_ucnt, 0, 2 * sizeof(unsigned long long), c->stream));
-    const uint32_t m = (uint32_t)std::min<long long>(std::max<long long>(c->cfg.min_count, 0), 0xFFFFFFFFll);
+    const uint64_t n = c->n_rec_r2, nc = c->n_cells_total, words = (nc + 31) / 32;
+    OKR(ensure(c, c->b_und, (capacity + 1) * sizeof(IrrKey)));
+    OKR(ensure(c, c->b_und_bits, words * sizeof(uint32_t)));
+    CU(c, cudaMemsetAsync(c->b_und.p, 0xFF, (capacity + 1) * sizeof(IrrKey), c->stream));  // unused records are padding
+    CU(c, cudaMemsetAsync(c->d_ucnt, 0, sizeof(unsigned long long), c->stream));
+    bool never;
+    const uint32_t m = min_count_u32(c, &never);
+    k_mark_undecided<<<blocks_for(nc, kThreads), kThreads, 0, c->stream>>>((const unsigned long long*)d_packed_global, nc, m, (uint32_t*)c->b_und_bits.p);
+    c->n_launches++;
     if (n) {
-        k_undecided_keys<<<(uint32_t)std::min<uint64_t>(blocks_for(n, 256), 148 * 8), 256, 0, c->stream>>>(
-            (const uint64_t*)c->b_ann.p, n, c->r2, d_reads_global, d_distinct_max, m, c->dcfg.umi_bits, (uint64_t*)c->b_keys.p, (IrrKey*)c->b_irr.p, c->d_ucnt);
+        k_undecided_packed<<<(uint32_t)std::min<uint64_t>(blocks_for(n, 1024), 148 * 8), 256, 0, c->stream>>>(
+            (const uint64_t*)c->b_ann.p, n, c->r2, (const uint32_t*)c->b_und_bits.p, c->dcfg.umi_len, (IrrKey*)c->b_und.p, capacity, c->d_ucnt);
         c->n_launches++;
     }
+    k_undecided_header<<<1, 1, 0, c->stream>>>((IrrKey*)c->b_und.p, c->d_ucnt);
+    c->n_launches++;
     CU(c, cudaGetLastError());
-    *d_keys = (uint64_t*)c->b_keys.p;
-    *d_irregular = c->b_irr.p;
-    *d_counts = (uint64_t*)c->d_ucnt;
+    *d_records = c->b_und.p;
+    return SSD_OK;
+}
+
+extern "C" int ssd_adopt_decision(ssd_ctx* c, const uint64_t* d_packed_global)
+{
+    if (!c || !d_packed_global) return SSD_EINVAL;
+    if (!c->phase1_done) return fail(c, SSD_ESTATE, "ssd_adopt_decision before ssd_demux_device");
+    CU(c, cudaSetDevice(c->device));
+    StageTimer t(c, 2);
+    bool never;
+    const uint32_t m = min_count_u32(c, &never);
+    k_adopt_decision<<<blocks_for(c->n_cells_total, kThreads), kThreads, 0, c->stream>>>((const unsigned long long*)d_packed_global, c->n_cells_total, m, c->d_hist,
+                                                                                        c->d_distinct);
+    c->n_launches++;
+    CU(c, cudaGetLastError());
     return SSD_OK;
 }
 
@@ -1396,19 +1471,21 @@ extern "C" int ssd_run_host(ssd_ctx* c, const void* r1, size_t r1_len, const voi
 // file to file
 // ================================================================================================
 namespace {
-// A byte range of a file mapped into memory: the I/O threads then move file data with plain memcpy between the page cache and
-// their pinned slots, which is several times faster per thread than pread / pwrite (one kernel crossing per page run instead
-// of per call, no extra locking); profiles/r02_host_io.md has the numbers.  Input ranges are always mapped; the output range
-// only on a RAM-backed file system (on a disk the dirty pages of a mapping are written back at the kernel's leisure, pwrite
-// is the better citizen there).  SSD_IO_NOMMAP=1 forces pread / pwrite.
+// A byte range of a file mapped into memory.  Measured on the GPU box (profiles/r02_host_io.md, 16 host threads, RAM-backed
+// files): READING is fastest with plain pread into the pinned slots (42 GB/s; through a mapping 34 GB/s, and tearing down the
+// page tables of the mapping afterwards costs another 50 ms per 6 GB), WRITING is fastest through a shared mapping (memcpy
+// from the pinned slots: 15-19 GB/s over pages the file already has, 6.6-8 GB/s when every page is new, against 5.7 / 3.5
+// GB/s with pwrite).  So inputs are read with pread (SSD_IO_MMAP_INPUT=1 maps them instead) and the output range is mapped
+// when the file system is RAM-backed (on a disk the dirty pages of a mapping are written back at the kernel's leisure,
+// pwrite is the better citizen there).  SSD_IO_NOMMAP=1 forces pread / pwrite everywhere.
 struct RangeMap {
     void* p = MAP_FAILED;
     size_t len = 0;
     uint8_t* data = nullptr;  // first byte of the range
     bool open_range(int fd, size_t base, size_t size, bool writable)
     {
-        static const bool off = getenv("SSD_IO_NOMMAP") != nullptr;
-        if (off || size == 0) return false;
+        static const bool off = getenv("SSD_IO_NOMMAP") != nullptr, map_input = getenv("SSD_IO_MMAP_INPUT") != nullptr;
+        if (off || size == 0 || (!writable && !map_input)) return false;
         if (writable) {
             struct statfs fs;
             if (fstatfs(fd, &fs) != 0 || (unsigned long)fs.f_type != 0x01021994ul) return false;  // TMPFS_MAGIC
@@ -1425,6 +1502,17 @@ struct RangeMap {
     void close_range()
     {
         if (p != MAP_FAILED) munmap(p, len);
+        p = MAP_FAILED;
+        data = nullptr;
+    }
+    // tearing down the page tables of a multi-gigabyte mapping takes tens of milliseconds: off the caller's critical path
+    void close_range_later()
+    {
+        if (p != MAP_FAILED) {
+            void* q = p;
+            const size_t n = len;
+            std::thread([q, n] { munmap(q, n); }).detach();
+        }
         p = MAP_FAILED;
         data = nullptr;
     }
@@ -1522,6 +1610,26 @@ void download_file_worker(int device, int fd, uint8_t* map, size_t base, size_t 
     if (cudaStreamSynchronize(lane->stream) != cudaSuccess) *rc = SSD_ECUDA;
 }
 
+// SSD_IO_TRACE=1: wall-clock milliseconds of the phases of the file-to-file calls on stderr (profiles/files_probe.py reads them)
+struct IoTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    IoTrace() : t(std::chrono::steady_clock::now())
+    {
+        static const bool v = getenv("SSD_IO_TRACE") != nullptr;
+        on = v;
+    }
+    void lap(const char* what, size_t bytes = 0)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        const double ms = std::chrono::duration<double, std::milli>(now - t).count();
+        if (bytes) fprintf(stderr, "[ssd io] %-18s %9.2f ms  %7.2f GB/s\n", what, ms, (double)bytes / ms / 1e6);
+        else fprintf(stderr, "[ssd io] %-18s %9.2f ms\n", what, ms);
+        t = now;
+    }
+};
+
 // all lanes in [lane0, lane0 + n) work on one file; returns the first failure
 template <class Worker, class... A>
 int run_lanes(ssd_ctx* c, const char* path, int lane0, int n, Worker worker, A... a)
@@ -1555,31 +1663,41 @@ int open_input(ssd_ctx* c, const char* path, int* fd, size_t* size)
     return SSD_OK;
 }
 
-// emit `which` on the device, then download it with four threads, each overlapping its copies with its pwrites
+// emit `which` on the device, then download it with all I/O lanes, each overlapping its copies with its writes into the file
 int download_to_file(ssd_ctx* c, int which, const char* out_path, int append, size_t* written)
 {
     const uint64_t need = which == SSD_EMIT_MATCHED ? c->stats.bytes_matched : c->stats.bytes_passing;
     if (written) *written = (size_t)need;
-    const int fd = open(out_path, O_WRONLY | O_CREAT | (append ? 0 : O_TRUNC), 0644);
+    IoTrace tr;
+    // O_RDWR: a shared writable mapping needs it.  Not O_TRUNC: a file that is being replaced keeps the pages it has (cutting
+    // it to the new length below frees only the excess), so that writing over it costs a copy, not a page allocation per 4 KiB
+    const int fd = open(out_path, O_RDWR | O_CREAT, 0644);
     if (fd < 0) return fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
     const off_t base = append ? lseek(fd, 0, SEEK_END) : 0;  // V2:367, 415 open in append mode
     int rc = base < 0 ? fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno)) : SSD_OK;
+    if (rc == SSD_OK && !append && ftruncate(fd, (off_t)need) != 0) rc = fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
+    tr.lap("open output");
     if (need && rc == SSD_OK) {
         rc = ensure(c, c->b_out, need + 32);
         if (rc == SSD_OK) rc = ssd_emit_device(c, which, c->b_out.p, c->b_out.cap, nullptr);
-        for (int k = 0; k < kIoHalf && rc == SSD_OK; k++) rc = c->io[k].init();
+        for (int k = 0; k < kIoLanes && rc == SSD_OK; k++) rc = c->io[k].init();
         if (rc == SSD_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, SSD_ECUDA, "emit failed");  // the emit kernel ran on the context's stream
+        tr.lap("emit kernel");
         if (rc == SSD_OK) {
             RangeMap m;
             m.open_range(fd, (size_t)base, (size_t)need, true);
+            tr.lap("map output");
             {
                 std::lock_guard<std::mutex> turn(g_d2h_turn);
-                rc = run_lanes(c, out_path, 0, kIoHalf, download_file_worker, c->device, fd, m.data, (size_t)base, (size_t)need, (const uint8_t*)c->b_out.p);
+                rc = run_lanes(c, out_path, 0, kIoLanes, download_file_worker, c->device, fd, m.data, (size_t)base, (size_t)need, (const uint8_t*)c->b_out.p);
             }
-            m.close_range();
+            tr.lap("download + write", (size_t)need);
+            m.close_range_later();
+            tr.lap("unmap output");
         }
     }
     if (close(fd) != 0 && rc == SSD_OK) rc = fail(c, SSD_EIO, "%s: %s", out_path, strerror(errno));
+    tr.lap("close output");
     return rc;
 }
 }  // namespace
@@ -1592,11 +1710,13 @@ extern "C" int ssd_run_files(ssd_ctx* c, const char* path_r1, const char* path_r
     CU(c, cudaSetDevice(c->device));
     int fd[2] = {-1, -1};
     size_t size[2] = {0, 0};
+    IoTrace tr;
     OKR(open_input(c, path_r1, &fd[0], &size[0]));
     int rc = open_input(c, path_r2, &fd[1], &size[1]);
     if (rc == SSD_OK) rc = ensure(c, c->b_in1, size[0] + 32);
     if (rc == SSD_OK) rc = ensure(c, c->b_in2, size[1] + 32);
     for (int k = 0; k < kIoLanes && rc == SSD_OK; k++) rc = c->io[k].init();
+    tr.lap("open + buffers");
     if (rc == SSD_OK) {
         std::lock_guard<std::mutex> turn(g_h2d_turn);
         int rc2 = SSD_OK;
@@ -1608,15 +1728,18 @@ extern "C" int ssd_run_files(ssd_ctx* c, const char* path_r1, const char* path_r
         });
         rc = run_lanes(c, path_r1, 0, kIoHalf, upload_file_worker, c->device, fd[0], (const uint8_t*)m1.data, (size_t)0, size[0], (uint8_t*)c->b_in1.p);
         other.join();
-        m1.close_range();
-        m2.close_range();
+        tr.lap("read + upload", size[0] + size[1]);
+        m1.close_range_later();
+        m2.close_range_later();
         if (rc == SSD_OK) rc = rc2;
     }
     for (int k = 0; k < 2; k++)
         if (fd[k] >= 0) close(fd[k]);
+    tr.lap("unmap + close");
     if (rc != SSD_OK) return rc;
     OKR(ssd_demux_device(c, c->b_in1.p, size[0], c->b_in2.p, size[1]));
     OKR(ssd_filter_single(c, stats));
+    tr.lap("kernels");
     return download_to_file(c, which, out_path, append, written);
 }
 
@@ -1634,7 +1757,7 @@ extern "C" int ssd_annotated_file(ssd_ctx* c, const char* path_in, const char* o
         RangeMap m;
         m.open_range(fd, 0, size, false);
         rc = run_lanes(c, path_in, 0, kIoLanes, upload_file_worker, c->device, fd, (const uint8_t*)m.data, (size_t)0, size, (uint8_t*)c->b_in1.p);
-        m.close_range();
+        m.close_range_later();
     }
     close(fd);
     if (rc != SSD_OK) return rc;
@@ -1660,7 +1783,7 @@ extern "C" int ssd_load_file_range(ssd_ctx* c, int slot, const char* path, uint6
         RangeMap m;
         m.open_range(fd, off, len, false);
         rc = run_lanes(c, path, 0, kIoLanes, upload_file_worker, c->device, fd, (const uint8_t*)m.data, off, len, (uint8_t*)buf.p);
-        m.close_range();
+        m.close_range_later();
     }
     close(fd);
     if (rc == SSD_OK) c->loaded[slot] = len;

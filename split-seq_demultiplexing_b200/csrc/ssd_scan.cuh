@@ -425,16 +425,26 @@ constexpr int kScanAnn = 2;  // an already annotated FASTQ (MergedCells_1.fastq)
 #ifndef SSD_SCAN_BWARPS
 #define SSD_SCAN_BWARPS 4
 #endif
+#ifndef SSD_SCAN_BGROUPS
+#define SSD_SCAN_BGROUPS 1
+#endif
 constexpr int kAWarps = SSD_SCAN_AWARPS, kBWarps = SSD_SCAN_BWARPS;  // first the stage A warps (bitmap, count, list), then the stage B warps (records)
+// Stage B is a chain of dependent shared-memory reads and integer operations per record (one thread per record), so the time it
+// takes per tile hardly depends on how many records the tile holds.  kBGroups groups of stage-B warps therefore take the tiles
+// in turn (group g: the block's tiles g, g + kBGroups, ...): kBGroups tiles are in stage B at any time.
+constexpr int kBGroups = SSD_SCAN_BGROUPS;
+static_assert(kBWarps % kBGroups == 0, "stage-B warps per group");
+constexpr int kBGWarps = kBWarps / kBGroups;
 constexpr int kComputeWarps = kAWarps + kBWarps;
 constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kAThreads = kAWarps * 32, kBThreads = kBWarps * 32;
+constexpr int kAThreads = kAWarps * 32, kBThreads = kBGWarps * 32;  // kBThreads: threads of ONE stage-B group
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 constexpr int kScanThreads = kComputeThreads + 96;  // the compute warps + the copy warp + the prefix warp (works in block 0) + the commit warp
 #ifndef SSD_SCAN_STAGE_SLOTS
-#define SSD_SCAN_STAGE_SLOTS 2
+#define SSD_SCAN_STAGE_SLOTS (SSD_SCAN_BGROUPS > 1 ? SSD_SCAN_BGROUPS : 2)
 #endif
 constexpr int kStageSlots = SSD_SCAN_STAGE_SLOTS;  // tiles whose records wait (in shared memory) for their record numbers
+static_assert(kStageSlots % kBGroups == 0, "a stage slot belongs to one stage-B group");
 
 // Shared memory of one persistent scan block.
 constexpr int kWinChunks = kWin / 16;                    // 16-byte chunks of a window
@@ -457,7 +467,7 @@ struct __align__(128) ScanSmem {
     uint16_t lstart[kListSlots][kMaxLines];   // line-start lists of the tiles between stage A and stage B
     unsigned long long full[kWinSlots], empty[kWinSlots];  // mbarriers: bytes landed / window may be refilled
     unsigned long long list_full[kListSlots], list_empty[kListSlots];  // mbarriers: stage A done with a tile / stage B done with it
-    unsigned long long line_base;
+    unsigned long long line_base[kBGroups];
     uint32_t tile[kWinSlots];
     uint32_t total[kListSlots], n_listed[kListSlots], list_tile[kListSlots];
     uint32_t warp_tile[kAWarps], halo_sum[2];
@@ -479,7 +489,7 @@ __device__ unsigned long long g_scan_prof[2][16];
 #endif
 
 __device__ __forceinline__ void sync_a() { asm volatile("bar.sync 1, %0;" ::"n"(kAThreads) : "memory"); }
-__device__ __forceinline__ void sync_b() { asm volatile("bar.sync 2, %0;" ::"n"(kBThreads) : "memory"); }
+__device__ __forceinline__ void sync_b(int group) { asm volatile("bar.sync %0, %1;" ::"r"(2 + group), "n"(kBThreads) : "memory"); }
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {
@@ -717,9 +727,14 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         PROF_ADD(0, t0, t1);
         const uint32_t tile = S.tile[ws];
         if (tile == kNoTile) {
-            if (tid == 0) {
-                S.list_tile[ls] = kNoTile;
-                mbar_arrive(&S.list_full[ls]);
+            // the end, told to every stage-B group: the next kBGroups list slots in turn
+            for (uint32_t k = 0; k < (uint32_t)kBGroups; k++) {
+                const uint32_t itk = it + k, lk = itk % kListSlots;
+                if (k && itk >= (uint32_t)kListSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.list_empty[lk]), ((itk / kListSlots) - 1u) & 1u);
+                if (tid == 0) {
+                    S.list_tile[lk] = kNoTile;
+                    mbar_arrive(&S.list_full[lk]);
+                }
             }
             return false;
         }
@@ -823,7 +838,8 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
     };
 
     // stage B: the records that start in the block's it-th tile
-    const int tb = tid - kAThreads, wb = warp - kAWarps;  // thread / warp index inside the stage-B group
+    const int bgroup = warp >= kAWarps ? (warp - kAWarps) / kBGWarps : 0;
+    const int tb = tid - kAThreads - bgroup * kBThreads, wb = warp - kAWarps - bgroup * kBGWarps;  // thread / warp index inside its stage-B group
     // read 2: the mate check still in flight (fingerprint of read 1 requested, not yet compared)
     bool pend = false;
     unsigned long long pend_fp1 = 0, pend_fp = 0;
@@ -843,9 +859,10 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         if (tile == kNoTile) {
             if (DEFER && it >= (uint32_t)kStageSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.stage_empty[ss]), ((it / kStageSlots) - 1u) & 1u);
             if (DEFER && tb == 0) {
-                S.stage_tile[ss] = kNoTile;  // the commit warp stops here too
+                S.stage_tile[ss] = kNoTile;  // the commit warp stops at the first of these
                 mbar_arrive(&S.stage_full[ss]);
             }
+            if (tb == 0) mbar_arrive(&S.list_empty[ls]);  // stage A may be waiting for this slot to tell the next group
             return false;
         }
         const size_t tile_lo = (size_t)tile * kTile;
@@ -1137,7 +1154,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
 
         // records are packed into as few warps as possible (fewer warp instructions); SSD_SCAN_R2_SPREAD=1 deals read 2's records
         // round robin to the warps instead, which ends the stage sooner but costs a third more instructions
-        const uint32_t my_i = (MODE == kScanR2 && SSD_SCAN_R2_SPREAD) ? (uint32_t)lane * kBWarps + (uint32_t)wb : (uint32_t)tb;
+        const uint32_t my_i = (MODE == kScanR2 && SSD_SCAN_R2_SPREAD) ? (uint32_t)lane * kBGWarps + (uint32_t)wb : (uint32_t)tb;
 
         // ---- the guess: a record starts at the first line (of the four candidates) that begins with '@' and whose second
         //      next line begins with '+'.  A wrong guess costs a second pass, never a wrong result. ----
@@ -1194,7 +1211,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                 S.stage_flags[ss] = (n_listed + 1u > (uint32_t)kMaxLines ? 1u : 0u) |
                                     ((tile == args.n_tiles - 1 && args.len && s_win[win_bytes - 1] != '\n') ? 2u : 0u);
             }
-            sync_b();
+            sync_b(bgroup);
             PROF_T(t6d);
             PROF_ADD(4, t8, t6d);
             if (tb == 0) {
@@ -1220,17 +1237,17 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             PROF_T(t10);
             PROF_ADD(8, t4, t10);
             const unsigned long long excl_lines = (v & kStatusValue) - total;
-            S.line_base = excl_lines;
+            S.line_base[bgroup] = excl_lines;
             if (tile == args.n_tiles - 1) {
                 unsigned long long n_lines = excl_lines + total + ((args.len && s_win[win_bytes - 1] != '\n') ? 1ull : 0ull);
                 args.cnt->n_lines[MODE == kScanR2 ? 1 : 0] = n_lines;
                 args.cnt->n_records[MODE == kScanR2 ? 1 : 0] = n_lines >> 2;
             }
         }
-        sync_b();
+        sync_b(bgroup);
         PROF_T(t5);
         PROF_ADD(3, t4, t5);
-        const unsigned long long line_base = S.line_base;
+        const unsigned long long line_base = S.line_base[bgroup];
 
         // records that start in this tile: the line after a newline whose next-line index is 0 mod 4
         const unsigned long long r_first = tile == 0 ? 0ull : (line_base + 4) >> 2;
@@ -1251,7 +1268,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                 commit(r_first + base + my_i);
             }
         }
-        sync_b();
+        sync_b(bgroup);
         PROF_T(t6);
         PROF_ADD(4, t5, t6);
         if (tb == 0) {
@@ -1265,7 +1282,8 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
     if (warp < kAWarps) {
         while (stage_a(n_a)) n_a++;
     } else {
-        while (stage_b(n_a)) n_a++;
+        n_a = (uint32_t)bgroup;
+        while (stage_b(n_a)) n_a += (uint32_t)kBGroups;
         if (MODE == kScanR2) settle();
     }
 #ifdef SSD_SCAN_PROFILE

@@ -303,14 +303,26 @@ struct HeadFlagIrr {  // irregular keys are sorted through an index permutation
     }
 };
 
-__global__ void k_compact64(const uint64_t* in, const uint32_t* pos, uint64_t n, uint64_t* out)
+// first (optional): first[u] = position of unique key u in the sorted list (the run lengths follow from it: k_run_lengths)
+__global__ void k_compact64(const uint64_t* in, const uint32_t* pos, uint64_t n, uint64_t* out, uint32_t* first = nullptr)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (i == 0 || in[i] != in[i - 1]) out[pos[i]] = in[i];
+    if (i == 0 || in[i] != in[i - 1]) {
+        out[pos[i]] = in[i];
+        if (first) first[pos[i]] = (uint32_t)i;
+    }
 }
 
-__global__ void k_compact_irr(const IrrKey* in, const uint32_t* perm, const uint32_t* pos, uint64_t n, IrrKey* out)
+// reads[u] = length of the run of unique key u in a sorted list of n keys (n_uniq runs, first[u] = where run u starts)
+__global__ void k_run_lengths(const uint32_t* first, uint64_t n_uniq, uint64_t n, uint32_t* reads)
+{
+    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_uniq) return;
+    reads[u] = (u + 1 < n_uniq ? first[u + 1] : (uint32_t)n) - first[u];
+}
+
+__global__ void k_compact_irr(const IrrKey* in, const uint32_t* perm, const uint32_t* pos, uint64_t n, IrrKey* out, uint32_t* first = nullptr)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -320,7 +332,10 @@ __global__ void k_compact_irr(const IrrKey* in, const uint32_t* perm, const uint
         IrrKey b = in[perm[i - 1]];
         head = a.hi != b.hi || a.lo != b.lo;
     }
-    if (head) out[pos[i]] = a;
+    if (head) {
+        out[pos[i]] = a;
+        if (first) first[pos[i]] = (uint32_t)i;
+    }
 }
 
 // distinct[cell] += (index of the cell's last unique key) + 1 - (index of its first): two atomics per cell run
@@ -365,49 +380,129 @@ __global__ void k_collect_irr(const uint64_t* ann, uint64_t n, const uint8_t* r2
     out[atomicAdd(cursor, 1ull)] = k;
 }
 
-// Multi-GPU -m decision: a cell is UNDECIDED when no rank alone holds >= m distinct UMIs of it (dmax[cell] < m, the all-reduced
-// MAX of the ranks' local counts) although all ranks together hold >= m reads of it (reads[cell], the all-reduced SUM).  Only
-// the (cell, UMI) keys of such cells have to be exchanged: every rank holds fewer than m distinct ones per cell.  This gathers
-// this batch's keys of the undecided cells (duplicates kept): regular keys and irregular keys, one warp-aggregated cursor each.
-__global__ void __launch_bounds__(256) k_undecided_keys(const uint64_t* __restrict__ ann, uint64_t n, const uint8_t* r2buf, const uint32_t* __restrict__ reads,
-                                                        const uint32_t* __restrict__ dmax, uint32_t m, int umi_bits, uint64_t* keys_out, IrrKey* irr_out,
-                                                        unsigned long long* cursors)
+// Multi-GPU -m decision without shipping every key.  Per cell one 64-bit word travels through ONE all-reduce(SUM):
+//   bits 0..39  reads of the cell in this batch            -> global reads
+//   bits 40..63 1 when this rank alone counts >= m distinct -> number of ranks that decide "pass" by themselves
+// A cell is UNDECIDED when no rank decides alone although all ranks together hold >= m reads of it; only the (cell, UMI)
+// keys of such cells have to be exchanged, and every rank holds fewer than m distinct ones per cell.
+constexpr int kPackPassShift = 40;
+constexpr unsigned long long kPackReadsMask = (1ull << kPackPassShift) - 1ull;
+
+__global__ void k_pack_decision(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ distinct, uint64_t n_cells, uint32_t m, bool never,
+                                unsigned long long* __restrict__ packed)
 {
-    const int lane = threadIdx.x & 31;
-    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t r = base + lane;
-        uint64_t a = r < n ? ann[r] : 0ull;
-        uint32_t st = ann_state(a);
-        if (st) {
-            const uint32_t cell = ann_cell(a);
-            if (!(__ldg(dmax + cell) < m && __ldg(reads + cell) >= m)) st = 0;
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    packed[c] = (unsigned long long)hist[c] | ((!never && distinct[c] >= m) ? 1ull << kPackPassShift : 0ull);
+}
+
+// one bit per cell: undecided
+__global__ void k_mark_undecided(const unsigned long long* __restrict__ packed, uint64_t n_cells, uint32_t m, uint32_t* __restrict__ bits)
+{
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool u = false;
+    if (c < n_cells) {
+        const unsigned long long p = packed[c];
+        u = (p >> kPackPassShift) == 0ull && (p & kPackReadsMask) >= (unsigned long long)m;
+    }
+    const uint32_t w = __ballot_sync(0xFFFFFFFFu, u);
+    if ((threadIdx.x & 31) == 0 && c < n_cells) bits[c >> 5] = w;
+}
+
+// the tables after the exchange: global reads; distinct = exact count for the undecided cells (already there), m for the cells
+// some rank decided alone, untouched (zero) for the cells that fail on reads -- a lower bound that decides -m like the exact table
+__global__ void k_adopt_decision(const unsigned long long* __restrict__ packed, uint64_t n_cells, uint32_t m, uint32_t* __restrict__ hist,
+                                 uint32_t* __restrict__ distinct)
+{
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const unsigned long long p = packed[c], reads = p & kPackReadsMask;
+    hist[c] = reads > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)reads;
+    if (p >> kPackPassShift) distinct[c] = max(distinct[c], m);
+}
+
+// This batch's keys of the undecided cells (duplicates kept) as ONE list of 128-bit records in the irregular-key format
+// (cell, length, UMI bytes) -- a regular UMI is spelled out from its 2-bit code, so equal UMIs are equal records whichever
+// way a rank happened to hold them.  A block takes 1024 consecutive records per round (four per thread: their annotation words
+// and bitmap lookups are in flight together) and claims room for all its keys with ONE atomic on the cursor.  out[0] is the
+// header (k_undecided_header), keys go to out[1 ..= cap]; the cursor keeps counting past cap so that the receivers see the
+// overflow.
+__global__ void __launch_bounds__(256) k_undecided_packed(const uint64_t* __restrict__ ann, uint64_t n, const uint8_t* r2buf, const uint32_t* __restrict__ und_bits,
+                                                          int umi_len, IrrKey* out, unsigned long long cap, unsigned long long* cursor)
+{
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t chunk = blockIdx.x; chunk * 1024 < n; chunk += gridDim.x) {
+        uint64_t a[4];
+        uint32_t st[4], any[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t r = chunk * 1024 + (uint64_t)u * 256 + threadIdx.x;
+            a[u] = r < n ? __ldcs(reinterpret_cast<const unsigned long long*>(ann) + r) : 0ull;
         }
-        const uint32_t reg = __ballot_sync(0xFFFFFFFFu, st == 1u), irr = __ballot_sync(0xFFFFFFFFu, st == 2u);
-        unsigned long long b0 = 0, b1 = 0;
-        if (lane == 0) {
-            if (reg) b0 = atomicAdd(&cursors[0], (unsigned long long)__popc(reg));
-            if (irr) b1 = atomicAdd(&cursors[1], (unsigned long long)__popc(irr));
+        uint32_t mine = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            st[u] = ann_state(a[u]);
+            if (st[u]) {
+                const uint32_t cell = ann_cell(a[u]);
+                if (!((__ldg(und_bits + (cell >> 5)) >> (cell & 31u)) & 1u)) st[u] = 0;
+            }
+            any[u] = __ballot_sync(0xFFFFFFFFu, st[u] != 0u);
+            mine += (uint32_t)__popc(any[u]);
         }
-        b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
-        b1 = __shfl_sync(0xFFFFFFFFu, b1, 0);
-        const uint32_t below = (1u << lane) - 1u;
-        if (st == 1u) keys_out[b0 + (uint32_t)__popc(reg & below)] = ((uint64_t)ann_cell(a) << umi_bits) | ann_payload(a);
-        if (st == 2u) {
-            const uint64_t payload = ann_payload(a);
-            const uint32_t ulen = (uint32_t)(payload & 31u);
-            const uint8_t* p = r2buf + (size_t)(payload >> 5);
+        if (lane == 0) s_warp[warp] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) total += s_warp[w];
+            s_base = total ? atomicAdd(cursor, (unsigned long long)total) : 0ull;
+        }
+        __syncthreads();
+        unsigned long long b0 = s_base;
+        for (int w = 0; w < warp; w++) b0 += s_warp[w];
+        __syncthreads();  // s_warp / s_base are rewritten in the next round
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned long long slot = b0 + (unsigned long long)__popc(any[u] & ((1u << lane) - 1u));
+            b0 += (unsigned long long)__popc(any[u]);
+            if (!st[u] || slot >= cap) continue;
             uint64_t hi = 0, lo = 0;
-            for (uint32_t j = 0; j < ulen; j++) {
-                const uint64_t c = p[j];
-                if (j < 4) hi |= c << (8 * (3 - j));
-                else lo |= c << (8 * (9 - j));
+            uint32_t ulen;
+            if (st[u] == 1u) {
+                const uint64_t code = ann_payload(a[u]);
+                ulen = (uint32_t)umi_len;
+                for (uint32_t j = 0; j < ulen; j++) {
+                    const uint64_t c = (0x47544341u >> (8u * (uint32_t)((code >> (2u * j)) & 3u))) & 0xFFu;  // A C T G by code (pack4)
+                    if (j < 4) hi |= c << (8 * (3 - j));
+                    else lo |= c << (8 * (9 - j));
+                }
+            } else {
+                const uint64_t payload = ann_payload(a[u]);
+                ulen = (uint32_t)(payload & 31u);
+                const uint8_t* p = r2buf + (size_t)(payload >> 5);
+                for (uint32_t j = 0; j < ulen; j++) {
+                    const uint64_t c = p[j];
+                    if (j < 4) hi |= c << (8 * (3 - j));
+                    else lo |= c << (8 * (9 - j));
+                }
             }
             IrrKey k;
-            k.hi = ((uint64_t)ann_cell(a) << kIrrCellShift) | ((uint64_t)ulen << 32) | hi;
+            k.hi = ((uint64_t)ann_cell(a[u]) << kIrrCellShift) | ((uint64_t)ulen << 32) | hi;
             k.lo = lo;
-            irr_out[b1 + (uint32_t)__popc(irr & below)] = k;
+            out[1 + slot] = k;
         }
     }
+}
+
+// header of the packed list: hi = all ones (the counting kernels skip such records as padding), lo = number of keys the
+// rank had (more than the capacity = the list is incomplete)
+__global__ void k_undecided_header(IrrKey* out, const unsigned long long* cursor)
+{
+    out[0].hi = ~0ull;
+    out[0].lo = *cursor;
 }
 
 __global__ void k_iota(uint32_t* p, uint64_t n)

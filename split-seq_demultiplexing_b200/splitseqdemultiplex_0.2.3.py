@@ -50,6 +50,9 @@ def build_parser():
                    help='extension: read the whitelist from the -1/-2/-3 files instead of Round*_barcodes_new*.txt in the CWD')
     p.add_argument('--cellTable', required=False,
                    help='extension: also write cell / reads / distinct UMIs / passing as tab-separated text to this path (one GPU)')
+    p.add_argument('--cellUmiTable', required=False,
+                   help='extension: also write cell / UMI / reads (one row per distinct pair of the passing cells) as tab-separated '
+                        'text to this path (one GPU, input within one batch)')
     p.add_argument('-t', '--targetMemory', required=False)
     p.add_argument('-g', '--granularity', required=False)
     return p
@@ -111,6 +114,11 @@ def main(argv=None):
             _, stats = dm.run_files(args.fastqF, args.fastqR, out_path, ssd_b200.EMIT_PASSING, append=True)  # V2:415 (append mode)
         if args.cellTable and world == 1:
             dm.write_cell_table(args.cellTable)  # the global tables are still in place after the (last) batch
+        if args.cellUmiTable and world == 1:
+            from ssd_b200 import filebatch
+            if max(os.path.getsize(args.fastqF), os.path.getsize(args.fastqR)) > filebatch.batch_bytes():
+                sys.exit('--cellUmiTable needs the input within one batch (SSD_BATCH_BYTES)')
+            dm.write_cell_umi_table(args.cellUmiTable)
     finally:
         dm.close()
     if wanted:

@@ -115,7 +115,11 @@ _SIGS = {
     "ssd_filter_single": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "ssd_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "ssd_distinct_local": (C.c_int, [C.c_void_p]),
-    "ssd_undecided_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "ssd_cell_umi_table": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "ssd_pack_decision": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ssd_undecided_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "ssd_adopt_decision": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ssd_emit_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ssd_emit_split_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
     "ssd_split_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),

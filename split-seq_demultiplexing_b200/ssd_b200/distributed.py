@@ -13,6 +13,7 @@ is exercised on CPU with the gloo backend in tests/test_distributed_gloo.py.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Tuple
 
 IRR_CELL_SHIFT = 36  # irregular key: hi = cell << 36 | len << 32 | bytes[0..4)  (include/ssd_b200.h)
@@ -121,37 +122,25 @@ def _adopt_torch_stream(dm):
     dm.set_stream(handle if handle != 0 else 1)
 
 
-def _gather_rows(rows, counts_per_rank: List[int], group=None):
-    """Everybody's first counts_per_rank[k] rows of `rows` (same trailing shape on every rank), concatenated in rank order:
-    an all-gather padded to the longest list, the padding dropped afterwards."""
-    import torch
-    import torch.distributed as dist
-    world, longest = len(counts_per_rank), max(counts_per_rank)
-    if longest == 0:
-        return rows[:0]
-    rank = dist.get_rank(group)
-    pad = torch.zeros((longest,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
-    pad[: counts_per_rank[rank]] = rows[: counts_per_rank[rank]]
-    everything = torch.empty((world * longest,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
-    if dist.get_backend(group) == "nccl":
-        dist.all_gather_into_tensor(everything, pad, group=group)
-    else:
-        dist.all_gather(list(everything.view((world, longest) + tuple(rows.shape[1:])).unbind(0)), pad, group=group)
-    return torch.cat([everything[k * longest: k * longest + counts_per_rank[k]] for k in range(world)])
+UNDECIDED_CAPACITY = int(os.environ.get("SSD_UNDECIDED_CAPACITY", 1 << 18))  # first guess: keys per rank and step in global_filter's exchange (4 MiB)
 
 
-def global_filter(dm, world: int, group=None, exact_table: bool = False) -> dict:
+def global_filter(dm, world: int, group=None, exact_table: bool = False, capacity: int = None) -> dict:
     """After dm.demux_device(...) on every rank: make the -m decision global and exact, return dm's stats.
 
     reads mode: one all-reduce of the read histogram.  distinct-UMI mode (V2:411), without shipping every key: every rank counts
-    the distinct UMIs of ITS OWN records per cell; a cell passes as soon as one rank alone counts >= m (all-reduce MAX of those
-    tables) and fails when all ranks together hold < m reads of it (all-reduce SUM of the read histograms, distinct <= reads).
-    Only the cells in between are undecided, and every rank holds fewer than m distinct UMIs of each of them: their keys are
-    all-gathered (a few hundred thousand instead of every rank's millions), counted exactly by everybody, done.  One host round
-    trip (the sizes of the gather), no owner partition.  Afterwards the distinct table holds, per cell, the exact global count
-    for the undecided cells and the largest local count elsewhere: a lower bound that decides -m like the exact table.
-    exact_table=True runs the exchange by owner rank instead and leaves the exact global distinct count of every cell (what a
-    per-cell table wants)."""
+    the distinct UMIs of ITS OWN records per cell; one all-reduce(SUM) of a 64-bit word per cell carries both the reads of the
+    cell and how many ranks count >= m by themselves.  A cell passes as soon as one rank does, and fails when all ranks together
+    hold < m reads of it (distinct <= reads).  Only the cells in between are undecided, and every rank holds fewer than m
+    distinct UMIs of each of them: their keys travel as one fixed-size packed list per rank (all-gather; a few hundred thousand
+    keys instead of every rank's millions), everybody counts them exactly, done.  Two collectives, no owner partition and NO
+    host round trip: the sizes never come back to the host before the step's own synchronisation (build_filter).  The list
+    size follows what the previous steps needed (the headers of the gathered lists, identical on all ranks); should a rank
+    hold more undecided keys than the list takes, the step is repeated with the exchange by owner rank, which has no such
+    limit.  Afterwards the distinct table holds the exact global count for the undecided cells, m for the cells some rank
+    decided alone and 0 elsewhere: a lower bound that decides -m like the exact table, identical on all ranks.
+    exact_table=True runs the exchange by owner rank in the first place and leaves the exact global distinct count of every
+    cell (what a per-cell table wants)."""
     if world <= 1:
         return dm.filter_single()
     import torch
@@ -164,41 +153,40 @@ def global_filter(dm, world: int, group=None, exact_table: bool = False) -> dict
         return dm.build_filter()
     if exact_table:
         return _global_filter_by_owner(dm, world, group)
-    rank = dist.get_rank(group)
-    hist = dm.reads_histogram()
-    reads = hist.clone()
-    pending = dist.all_reduce(reads, group=group, async_op=True)  # overlaps the local distinct count (which needs the LOCAL histogram)
+    cap = int(capacity or getattr(dm, "_undecided_capacity", None) or UNDECIDED_CAPACITY)
     dm.distinct_local()
-    dmax = dm.distinct_histogram().clone()
-    dist.all_reduce(dmax, op=dist.ReduceOp.MAX, group=group)
-    pending.wait()
-    keys, irr, counts = dm.undecided_keys(reads, dmax)
-    all_counts = torch.empty((world, 2), dtype=torch.int64, device=counts.device)
+    packed = dm.pack_decision()
+    dist.all_reduce(packed, group=group)
+    mine = dm.undecided_keys(packed, cap)
+    everything = torch.empty((world * (cap + 1), 2), dtype=torch.int64, device=mine.device)
     if dist.get_backend(group) == "nccl":
-        dist.all_gather_into_tensor(all_counts, counts.view(1, 2), group=group)
+        dist.all_gather_into_tensor(everything, mine, group=group)
     else:
-        dist.all_gather(list(all_counts.unbind(0)), counts.clone(), group=group)
-    sizes = all_counts.cpu().tolist()  # the one host round trip of the step
-    all_k = _gather_rows(keys, [c[0] for c in sizes], group=group)
-    all_i = _gather_rows(irr, [c[1] for c in sizes], group=group)
-    dm.count_distinct(all_k, all_i)  # exact global counts of the undecided cells (zero elsewhere)
-    exact = dm.distinct_histogram()
-    torch.maximum(exact, dmax, out=exact)
-    hist.copy_(reads)
-    return dm.build_filter()
+        dist.all_gather(list(everything.view(world, cap + 1, 2).unbind(0)), mine.clone(), group=group)
+    most = everything.view(world, cap + 1, 2)[:, 0, 1].max()  # the largest list any rank wanted to send
+    dm.count_distinct(everything[:0, 0], everything)  # exact global counts of the undecided cells (zero elsewhere)
+    dm.adopt_decision(packed)
+    st = dm.build_filter()  # synchronises: reading `most` now costs no extra wait
+    most = int(most.item())
+    if capacity is None:  # next time: room for half as much again, in steps of 64 Ki keys (the same number on every rank)
+        dm._undecided_capacity = max(1 << 16, -(-(most + most // 2) // 65536) * 65536)
+    if most > cap:
+        return _global_filter_by_owner(dm, world, group, reads_are_global=True)
+    return st
 
 
-def _global_filter_by_owner(dm, world: int, group=None) -> dict:
+def _global_filter_by_owner(dm, world: int, group=None, reads_are_global: bool = False) -> dict:
     """The -m decision with the exact global distinct count of EVERY cell: all (cell, UMI) keys go to the rank that owns their cell
     (all-to-all, duplicates kept; irregular keys to everybody), every rank counts the cells it owns, the table is all-reduced."""
     import torch.distributed as dist
     rank = dist.get_rank(group)
-    pending = dist.all_reduce(dm.reads_histogram(), group=group, async_op=True)  # overlaps the key exchange
+    pending = None if reads_are_global else dist.all_reduce(dm.reads_histogram(), group=group, async_op=True)  # overlaps the key exchange
     keys, offsets, irr = dm.partition_keys(world)
     rk, ri = exchange_owned(keys, [offsets[k + 1] - offsets[k] for k in range(world)], irr, group=group)
     dm.count_distinct_owned(rk, ri, rank, world)
     dist.all_reduce(dm.distinct_histogram(), group=group)
-    pending.wait()
+    if pending is not None:
+        pending.wait()
     return dm.build_filter()
 
 

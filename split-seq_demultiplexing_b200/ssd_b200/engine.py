@@ -172,21 +172,27 @@ class Demultiplexer:
         """Per-cell distinct-UMI counts of THIS batch into the distinct table (the read histogram must still be the batch's own)."""
         self._check(self.lib.ssd_distinct_local(self._ctx))
 
-    def undecided_keys(self, reads_global, distinct_max):
-        """This batch's (cell, UMI) keys (duplicates kept) of the cells no rank decides alone: distinct_max[cell] < m <= reads_global[cell]
-        (int32 CUDA tensors over the cell space).  Returns (int64[n_regular_keys] buffer, int64[n_irregular_keys, 2] buffer,
-        int64[2] counts on the device): only the first counts[0] / counts[1] entries of the buffers are keys, once the stream ran."""
+    def pack_decision(self):
+        """One int64 per cell (CUDA tensor over the cell space, owned by the context): bits 0..39 = reads of the cell in this batch,
+        bit 40 = this batch alone counts >= m distinct UMIs (needs distinct_local first).  All-reduce it (SUM) in place."""
         import torch
-        pk, pi, pc = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        self._check(self.lib.ssd_undecided_keys(self._ctx, C.c_void_p(reads_global.data_ptr()), C.c_void_p(distinct_max.data_ptr()),
-                                                C.byref(pk), C.byref(pi), C.byref(pc)))
-        st = self.stats()
-        nk, ni = st["n_regular_keys"], st["n_irregular_keys"]
-        keys = torch.as_tensor(_DevArray(pk.value, nk, "<i8", self), device="cuda") if nk else torch.empty(0, dtype=torch.int64, device="cuda")
-        irr = (torch.as_tensor(_DevArray(pi.value, 2 * ni, "<i8", self), device="cuda").view(-1, 2)
-               if ni else torch.empty((0, 2), dtype=torch.int64, device="cuda"))
-        counts = torch.as_tensor(_DevArray(pc.value, 2, "<i8", self), device="cuda")
-        return keys, irr, counts
+        p = C.c_void_p()
+        self._check(self.lib.ssd_pack_decision(self._ctx, C.byref(p)))
+        return torch.as_tensor(_DevArray(p.value, self.n_cells_total, "<i8", self), device="cuda")
+
+    def undecided_keys(self, packed_global, capacity: int):
+        """This batch's (cell, UMI) keys (duplicates kept) of the cells no rank decides alone (all-reduced pack_decision words: no
+        rank passes it, global reads >= m), as one packed list: int64[capacity + 1, 2] on the device, row 0 = (-1, number of keys
+        the batch had), then the keys in the irregular-key format, unused rows all ones.  Nothing is read back."""
+        import torch
+        p = C.c_void_p()
+        self._check(self.lib.ssd_undecided_keys(self._ctx, C.c_void_p(packed_global.data_ptr()), int(capacity), C.byref(p)))
+        return torch.as_tensor(_DevArray(p.value, 2 * (int(capacity) + 1), "<i8", self), device="cuda").view(-1, 2)
+
+    def adopt_decision(self, packed_global):
+        """After count_distinct on the gathered lists: read histogram := global reads, distinct := max(distinct, m) where some rank
+        decided "pass" alone."""
+        self._check(self.lib.ssd_adopt_decision(self._ctx, C.c_void_p(packed_global.data_ptr())))
 
     def build_filter(self) -> dict:
         st = L.Stats()
@@ -366,6 +372,55 @@ class Demultiplexer:
         with open(path, "w") as fh:
             fh.write(hostlogic.format_cell_table(table, self.min_count))
         return len(table)
+
+    def cell_umi_table(self):
+        """Per-cell x UMI table of the last batch: numpy arrays (cells uint32[n], umis bytes-array S10[n], reads
+        uint32[n]) with one row per distinct (cell, UMI) pair and the number of reads it was seen in, sorted by cell id and,
+        inside a cell, regular UMIs (by 2-bit code) before irregular ones.  Sort + run-length count on the device
+        (ssd_cell_umi_table); only the unique rows come back."""
+        import numpy as np
+        import torch
+        pk, pr, pi, pir = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nk, ni = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.ssd_cell_umi_table(self._ctx, C.byref(pk), C.byref(pr), C.byref(nk), C.byref(pi), C.byref(pir), C.byref(ni)))
+        nk, ni = nk.value, ni.value
+
+        def host(ptr, n, typestr):
+            return torch.as_tensor(_DevArray(ptr, n, typestr, self), device="cuda").cpu().numpy() if n else np.zeros(0, dtype=np.dtype(typestr))
+
+        keys, kreads = host(pk.value, nk, "<i8").astype(np.uint64), host(pr.value, nk, "<i4").astype(np.uint32)
+        irr, ireads = host(pi.value, 2 * ni, "<i8").astype(np.uint64).reshape(-1, 2), host(pir.value, ni, "<i4").astype(np.uint32)
+        ulen = self.umi_bits // 2
+        cells_k = (keys >> np.uint64(self.umi_bits)).astype(np.uint32)
+        umis_k = np.zeros((nk, 10), dtype=np.uint8)
+        lut = np.frombuffer(b"ACTG", dtype=np.uint8)  # 2-bit code -> base (csrc/ssd_scan.cuh pack4)
+        for j in range(ulen):
+            umis_k[:, j] = lut[((keys >> np.uint64(2 * j)) & np.uint64(3)).astype(np.int64)]
+        cells_i = ((irr[:, 0] >> np.uint64(36)) & np.uint64((1 << 21) - 1)).astype(np.uint32)
+        umis_i = np.zeros((ni, 10), dtype=np.uint8)
+        for j in range(10):  # bytes 0..3 in hi (bits 24, 16, 8, 0), bytes 4..9 in lo (bits 40 .. 0); unused bytes are zero
+            word, shift = (irr[:, 0], 8 * (3 - j)) if j < 4 else (irr[:, 1], 8 * (9 - j))
+            umis_i[:, j] = ((word >> np.uint64(shift)) & np.uint64(0xFF)).astype(np.uint8)
+        cells = np.concatenate([cells_k, cells_i])
+        umis = np.concatenate([umis_k, umis_i]).view("S10").reshape(-1)
+        reads = np.concatenate([kreads, ireads])
+        order = np.argsort(cells, kind="stable")  # both halves are sorted by cell already: regular rows stay ahead of irregular ones
+        return cells[order], umis[order], reads[order]
+
+    def write_cell_umi_table(self, path: str, passing_only: bool = True) -> int:
+        """cell <tab> UMI <tab> reads, one line per distinct (cell, UMI) pair of the last batch (of the passing cells only by
+        default: what a per-cell UMI counter downstream consumes); returns the number of rows."""
+        import numpy as np
+        from . import hostlogic
+        cells, umis, reads = self.cell_umi_table()
+        if passing_only:
+            thr = self.min_count
+            ok = (self.reads_histogram() if self.filter_mode == "reads" else self.distinct_histogram()).cpu().numpy() >= thr
+            keep = ok[cells]
+            cells, umis, reads = cells[keep], umis[keep], reads[keep]
+        with open(path, "wb") as fh:
+            fh.write(hostlogic.format_cell_umi_table(self.whitelist, cells, umis, reads))
+        return int(cells.size)
 
     def cell_table(self) -> Dict[str, Tuple[int, int]]:
         """{cell string: (reads, distinct UMIs)} for every detected cell (small outputs / tests)."""

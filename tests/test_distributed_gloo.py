@@ -156,14 +156,26 @@ class _StandIn:
     def distinct_local(self):
         self._count(self.keys)
 
-    def undecided_keys(self, reads_global, distinct_max):
+    def pack_decision(self):
+        self._packed = self.hist.to(torch.int64) | ((self.distinct >= self.m).to(torch.int64) << 40)
+        return self._packed
+
+    def undecided_keys(self, packed, capacity):
+        # the library's packed list: row 0 = (-1, number of keys), then (cell << 36 | UMI, 0) rows, unused rows all ones
         cells = self.keys >> UMI_BITS
-        und = (distinct_max[cells] < self.m) & (reads_global[cells] >= self.m)
-        k = self.keys[und]
-        pad = torch.full((self.keys.numel(),), -7, dtype=torch.int64)  # a buffer of full capacity, like the library's
-        pad[: k.numel()] = k
+        und = ((packed >> 40) == 0) & ((packed & ((1 << 40) - 1)) >= self.m)
+        k = self.keys[und[cells]]
+        rows = torch.full((capacity + 1, 2), -1, dtype=torch.int64)
+        rows[0, 1] = k.numel()
+        n = min(int(k.numel()), capacity)
+        rows[1: 1 + n, 0] = ((k[:n] >> UMI_BITS) << 36) | (k[:n] & ((1 << UMI_BITS) - 1))
+        rows[1: 1 + n, 1] = 0
         self.n_undecided_sent = int(k.numel())
-        return pad, torch.empty((0, 2), dtype=torch.int64), torch.tensor([k.numel(), 0], dtype=torch.int64)
+        return rows
+
+    def adopt_decision(self, packed):
+        self.hist.copy_((packed & ((1 << 40) - 1)).to(torch.int32))
+        self.distinct.copy_(torch.where((packed >> 40) != 0, torch.clamp(self.distinct, min=self.m), self.distinct))
 
     def partition_keys(self, world):
         from ssd_b200 import distributed as D
@@ -179,6 +191,9 @@ class _StandIn:
         self.distinct.index_add_(0, uk >> UMI_BITS, torch.ones(uk.numel(), dtype=torch.int32))
 
     def count_distinct(self, keys, irr):
+        if irr is not None and irr.numel():  # packed records (padding and headers have hi == -1)
+            hi = irr[irr[:, 0] != -1][:, 0]
+            keys = torch.cat([keys, ((hi >> 36) << UMI_BITS) | (hi & ((1 << UMI_BITS) - 1))])
         self._count(keys)
 
     def count_distinct_owned(self, keys, irr, rank, world):
@@ -256,7 +271,7 @@ def _global_filter_worker(rank, world, port, out_dir, exact):
     dm = _StandIn(m=5)
     cells, umis = _global_filter_input(rank)
     dm.load(cells, umis)
-    st = D.global_filter(dm, world, exact_table=exact)
+    st = D.global_filter(dm, world, exact_table=exact == 1, capacity=64 if exact == 2 else 4096)
     np.save(os.path.join(out_dir, "gf_%d.npy" % rank), np.array([st["n_cells"], st["n_passing_cells"], st["n_retained"], getattr(dm, "n_undecided_sent", -1),
                                                                  int(cells.numel())]))
     np.save(os.path.join(out_dir, "gf_distinct_%d.npy" % rank), dm.distinct_histogram().numpy())
@@ -279,7 +294,7 @@ def _global_filter_input(rank):
     return torch.from_numpy(cells).to(torch.int64), torch.from_numpy(umis).to(torch.int64)
 
 
-@pytest.mark.parametrize("world,exact", [(2, False), (3, False), (2, True)])
+@pytest.mark.parametrize("world,exact", [(2, 0), (3, 0), (2, 1), (2, 2)])
 def test_global_filter_decides_like_one_process(tmp_path, world, exact):
     """global_filter's exchange of the UNDECIDED cells' keys only (and the exchange by owner rank behind exact_table=True): the
     same passing cells as one process that sees every key; only a fraction of the keys travels."""
@@ -300,7 +315,8 @@ def test_global_filter_decides_like_one_process(tmp_path, world, exact):
         assert bool(((table >= 5) == passing).all())               # the table decides like the exact one ...
         assert bool((table <= distinct).all())                     # ... and never overstates a count
         assert int(hist.sum()) == cells.numel()                    # the read histogram ends up global
-        if exact:
+        if exact:                                                  # 1: by owner rank; 2: the packed list overflowed -> by owner rank
             assert bool((table == distinct).all())
-        else:
+        if exact != 1:
             assert 0 < got[3] < got[4] // 4                        # only the undecided cells' keys were sent
+            assert (got[3] > 64) == (exact == 2) or exact == 0

@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir, filter_mode, own_stream=True):
+def _worker(rank, world, port, out_dir, filter_mode, own_stream=True, capacity=None):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -38,7 +38,7 @@ def _worker(rank, world, port, out_dir, filter_mode, own_stream=True):
     spec = ssd_b200.synth_spec(WL, N_PER_RANK, seed=77, first_index=1 + rank * N_PER_RANK, cell_pool=3000, p_n=0.01, p_dup_umi=0.3)
     d1, d2 = ssd_b200.synth_device(dm, spec)
     dm.demux_device(d1.data_ptr(), d1.numel(), d2.data_ptr(), d2.numel(), keep=(d1, d2))
-    stats = global_filter(dm, world)
+    stats = global_filter(dm, world, capacity=capacity)
     out = torch.empty(stats["bytes_passing"] + 16, dtype=torch.uint8, device="cuda")
     n = dm.emit_device(ssd_b200.EMIT_PASSING, out.data_ptr(), out.numel())
     torch.cuda.synchronize()
@@ -47,8 +47,10 @@ def _worker(rank, world, port, out_dir, filter_mode, own_stream=True):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("filter_mode,own_stream", [("distinct_umi", True), ("reads", True), ("distinct_umi", False)])
-def test_two_ranks_equal_one(tmp_path, filter_mode, own_stream):
+@pytest.mark.parametrize("filter_mode,own_stream,capacity", [("distinct_umi", True, None), ("reads", True, None), ("distinct_umi", False, None),
+                                                             ("distinct_umi", True, 8)])
+def test_two_ranks_equal_one(tmp_path, filter_mode, own_stream, capacity):
+    """capacity=8: the packed list of undecided keys overflows, global_filter repeats the decision with the exchange by owner."""
     import numpy as np
     import torch
     import torch.multiprocessing as mp
@@ -56,7 +58,7 @@ def test_two_ranks_equal_one(tmp_path, filter_mode, own_stream):
         pytest.skip("needs two GPUs")
     import ssd_b200
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), filter_mode, own_stream), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), filter_mode, own_stream, capacity), nprocs=world, join=True)
     parts = [np.load(os.path.join(str(tmp_path), "out_%d.npy" % r)).tobytes() for r in range(world)]
     st = [np.load(os.path.join(str(tmp_path), "stats_%d.npy" % r)) for r in range(world)]
     # single GPU on the concatenated input

@@ -133,6 +133,43 @@ def test_synthetic_vs_oracle(ssd, orc, e, m, kw):
     assert dm.cell_table() == want
 
 
+def _cell_umi_rows_from_text(merged: bytes, passing_cells=None):
+    """(cell, UMI) -> reads, from the headers `@id_CELL_UMI` of an annotated FASTQ text (what V2:395-398 parses back)."""
+    from collections import Counter
+    rows = Counter()
+    for h in merged.split(b"\n")[0::4]:
+        if not h:
+            continue
+        parts = h.split(b"_")
+        if passing_cells is None or parts[1] in passing_cells:
+            rows[(parts[1], parts[2])] += 1
+    return rows
+
+
+@pytest.mark.parametrize("e,m,kw", [(1, 3, {"p_n": 0.02, "p_dup_umi": 0.3}), (2, 5, {"p_trunc": 0.02, "p_n": 0.01})])
+def test_cell_umi_table_vs_oracle(ssd, orc, tmp_path, e, m, kw):
+    """the per-cell x UMI read counts straight from the device (sort + run lengths) equal what the oracle's
+    MergedCells_1 text says header by header -- regular UMIs, UMIs with N and truncated ones alike."""
+    r1, r2 = ssd.synth_host(ssd.synth_spec(WL, 40000, seed=0xC0DE + e, cell_pool=1500, **kw))
+    dm = ssd.Demultiplexer(WL, errors=e, min_count=m)
+    dm.run_host(r1, r2, ssd.EMIT_PASSING)
+    ref = orc.demultiplex(r1, r2, WL, e, m)
+    cells, umis, reads = dm.cell_umi_table()
+    got = {(dm.cell_string(int(c)).encode(), u): int(n) for c, u, n in zip(cells.tolist(), umis.tolist(), reads.tolist())}
+    assert len(got) == cells.size                      # one row per pair
+    assert got == dict(_cell_umi_rows_from_text(ref.merged1))
+    assert int(reads.sum()) == ref.n_matched
+    assert (np.diff(cells.astype(np.int64)) >= 0).all()  # sorted by cell
+    # the file: passing cells only, same rows
+    path = str(tmp_path / "cell_umi.tsv")
+    n_rows = dm.write_cell_umi_table(path)
+    lines = open(path, "rb").read().split(b"\n")
+    assert lines[0] == b"cell\tumi\treads" and lines[-1] == b"" and len(lines) == n_rows + 2
+    passing = {c for c, v in ref.cells.items() if v[1] >= m}
+    want = _cell_umi_rows_from_text(ref.merged1, passing)
+    assert {tuple(ln.split(b"\t")[:2]): int(ln.split(b"\t")[2]) for ln in lines[1:-1]} == dict(want)
+
+
 def test_device_generator_matches_host_twin(ssd):
     import torch
     spec = ssd.synth_spec(WL, 5000, seed=77, first_index=999990, p_tie=0.02, p_trunc=0.02)

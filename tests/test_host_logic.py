@@ -384,3 +384,18 @@ def test_plan_shards_deals_contiguous_runs_of_whole_records(ssd, tmp_path, monke
         assert sizes == sorted(sizes, reverse=True) and (len(flat) < world or min(sizes) >= 1 or sum(sizes) == len(flat))
         if batch_bytes == 10**9 and world > 1:
             assert len(flat) >= min(world, 2)                                                          # cut into about one batch per rank
+
+
+def test_format_cell_umi_table():
+    import numpy as np
+    from ssd_b200 import hostlogic
+    wl = ["AAAAAAAA", "CCCCCCCC", "GGGGGGGG"]
+    cells = np.array([0, 5, 26], dtype=np.uint32)            # (0,0,0), (0,1,2), (2,2,2)
+    umis = np.array([b"ACGTACGTAC", b"ANNTACGTAC", b"ACGTA"], dtype="S10")
+    reads = np.array([1, 12, 1234567], dtype=np.uint32)
+    text = hostlogic.format_cell_umi_table(wl, cells, umis, reads)
+    assert text == (b"cell\tumi\treads\n"
+                    b"AAAAAAAAAAAAAAAAAAAAAAAA\tACGTACGTAC\t1\n"
+                    b"AAAAAAAACCCCCCCCGGGGGGGG\tANNTACGTAC\t12\n"
+                    b"GGGGGGGGGGGGGGGGGGGGGGGG\tACGTA\t1234567\n")
+    assert hostlogic.format_cell_umi_table(wl, cells[:0], umis[:0], reads[:0]) == b"cell\tumi\treads\n"
