@@ -59,7 +59,8 @@ typedef struct ssd_ctx ssd_ctx;
 typedef struct ssd_config {
     uint32_t struct_size;     /* = sizeof(ssd_config), for ABI growth                                 */
     int32_t device;           /* CUDA ordinal; -1 = current device                                    */
-    int32_t n_whitelist;      /* 1..SSD_MAX_WHITELIST; one list serves all three rounds (V2:302-304)  */
+    int32_t n_whitelist;      /* 1..SSD_MAX_WHITELIST; one list serves all three rounds (V2:302-304)
+                                 unless whitelist2 / whitelist3 below say otherwise                   */
     const char *whitelist;    /* n_whitelist x 8 bytes (file order = match priority)                  */
     const uint8_t *whitelist_len; /* per-entry length 0..8, NULL = all 8                              */
     int32_t umi_start, umi_end;   /* Python slice bounds into the read-2 sequence, 0 <= start <= end  */
@@ -73,6 +74,16 @@ typedef struct ssd_config {
                                  for i < k when both cells survive the filter (Collapse_RanHex_Odt.py:44-71) */
     int32_t record_bytes_hint;/* lower bound on bytes per FASTQ record used to size tables; 0 = 24     */
     int32_t reserved;
+    /* Per-round whitelists (extension beyond the reference's fast path; the bash pipeline reads one file per
+     * round, demultiplex_using_barcodes.py:350-372).  `whitelist` is matched against the Round1 window (bc1), whitelist2
+     * against the Round2 window (bc2), whitelist3 against the Round3 window (bc3); NULL = `whitelist` serves that round
+     * too.  Cell id = (i1 * n2 + i2) * n3 + i3, written bc1 bc2 bc3 (V2:139).  collapse_pairs refers to the round-1 list.
+     * A caller compiled against the first layout (struct_size up to `reserved`) gets one list. */
+    int32_t n_whitelist2, n_whitelist3;
+    const char *whitelist2;
+    const uint8_t *whitelist2_len;
+    const char *whitelist3;
+    const uint8_t *whitelist3_len;
 } ssd_config;
 
 typedef struct ssd_stats {
@@ -93,6 +104,15 @@ void ssd_destroy(ssd_ctx *ctx);
 const char *ssd_last_error(const ssd_ctx *ctx); /* ctx may be NULL: error of the last failed ssd_create */
 /* cudaStream_t to enqueue on (0/NULL = the context's own stream). */
 int ssd_set_stream(ssd_ctx *ctx, void *cuda_stream);
+
+/* ---- the position learner on the device (V2:164-199, sample of LIB:99-110) ---------------------- */
+/* Over the first n_lines (<= 4096; the reference takes 1001) lines of the read-2 text at d_text (DEVICE pointer, current
+ * device): for every sequence line (line index % 4 == 1), the str.find() position of each of the three static sequences
+ * (NUL-terminated, <= 16 bytes) in the strip()ped line, -1 when absent.  found[k * capacity + t] = anchor k in sequence
+ * line t (host array of 3 * capacity), *n_sequence_lines = how many sequence lines the sample holds.  The caller keeps
+ * the positions >= 17 and takes their mode (ssd_b200/hostlogic.py: positions_from_found, V2:175-183). */
+int ssd_anchor_positions(const void *d_text, size_t len, uint32_t n_lines, const char *const anchors[3], int32_t *found,
+                         uint32_t capacity, uint32_t *n_sequence_lines);
 
 /* ---- phase 1: V2.demultiplex_fun minus the file writing (V2:207-358) ------------------------- */
 /* FASTQ record-boundary scan of both mates, UMI/barcode extraction at the configured offsets,
@@ -129,6 +149,11 @@ int ssd_annotated_file(ssd_ctx *ctx, const char *path_in, const char *out_path, 
  *   ssd_load_file_range   bytes [offset, offset + length) of a file (clamped to the file) into the context's input buffer
  *                         `slot` (0: read 1 or the annotated text, 1: read 2), read with pread on eight host threads into
  *                         pinned rings and uploaded as they arrive
+ *   ssd_loaded_newlines   the shard phase of several GPUs on one pair of files (what LIB:6-97 does with line counts):
+ *                         '\n' bytes per tile of 2^tile_log2 bytes of the range loaded into `slot`, counted on the device,
+ *                         copied into tile_counts[capacity]; *n_tiles = how many.  Every rank loads ITS byte range of the
+ *                         file and counts; the counts of all ranks (all-gather) give the line index of every tile, hence
+ *                         which tile holds the start of record r = line 4 r (ssd_b200/filebatch.py: plan_shards_device).
  *   ssd_demux_loaded      ssd_demux_device on the two loaded ranges; ssd_annotated_loaded: ssd_annotated_device on slot 0
  *   ssd_emit_file         after the filter (ssd_filter_single / ssd_build_filter): the selected output into out_path,
  *                         appended (V2:367, 415) or truncating
@@ -139,6 +164,7 @@ int ssd_annotated_file(ssd_ctx *ctx, const char *path_in, const char *out_path, 
  *                         records start (the file size for records past the end) -- the mate file cut at the same records.
  *                         SSD_ERANGE when `capacity` entries do not suffice. */
 int ssd_load_file_range(ssd_ctx *ctx, int slot, const char *path, uint64_t offset, uint64_t length);
+int ssd_loaded_newlines(ssd_ctx *ctx, int slot, int tile_log2, uint32_t *tile_counts, uint64_t capacity, uint64_t *n_tiles);
 int ssd_demux_loaded(ssd_ctx *ctx);
 int ssd_annotated_loaded(ssd_ctx *ctx);
 int ssd_emit_file(ssd_ctx *ctx, int which, const char *out_path, int append, size_t *written);

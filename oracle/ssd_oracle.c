@@ -131,12 +131,21 @@ static int hamming(const char *a, size_t la, const char *b, size_t lb)
 
 /* V2:302-304 + 327-329: [s for s in Eight_BP_barcode if hamming(s, window) <= e] then [0]:
  * the FIRST whitelist entry in file order within distance e, or -1 when the list is empty. */
-static int first_hit(const ssd_oracle_cfg *cfg, sv window)
+/* the list of round k (0: bc1, 1: bc2, 2: bc3): the one list of V2:60 unless the extension fields name another */
+static void round_list(const ssd_oracle_cfg *cfg, int k, const char **wl, const uint8_t **len, int *n)
 {
-    int i;
-    for (i = 0; i < cfg->n_whitelist; i++) {
-        size_t wl = cfg->wl_len ? cfg->wl_len[i] : 8;
-        if (hamming(cfg->whitelist + 8 * (size_t)i, wl, window.p, window.n) <= cfg->errors) return i;
+    *wl = cfg->whitelist; *len = cfg->wl_len; *n = cfg->n_whitelist;
+    if (k == 1 && cfg->whitelist2) { *wl = cfg->whitelist2; *len = cfg->wl_len2; *n = cfg->n_whitelist2; }
+    if (k == 2 && cfg->whitelist3) { *wl = cfg->whitelist3; *len = cfg->wl_len3; *n = cfg->n_whitelist3; }
+}
+
+static int first_hit(const ssd_oracle_cfg *cfg, int round, sv window)
+{
+    const char *list; const uint8_t *len; int n, i;
+    round_list(cfg, round, &list, &len, &n);
+    for (i = 0; i < n; i++) {
+        size_t wl = len ? len[i] : 8;
+        if (hamming(list + 8 * (size_t)i, wl, window.p, window.n) <= cfg->errors) return i;
     }
     return -1;
 }
@@ -206,7 +215,7 @@ int ssd_oracle_demultiplex(const ssd_oracle_cfg *cfg, const char *r1, size_t r1_
     uint64_t rec_n = out->n_records, rec_cap = out->n_records;
     parse_state pf, pr;
     int rc = SSD_ORACLE_OK;
-    const int n = cfg->n_whitelist;
+    const int n2 = cfg->whitelist2 ? cfg->n_whitelist2 : cfg->n_whitelist, n3 = cfg->whitelist3 ? cfg->n_whitelist3 : cfg->n_whitelist;
     uint64_t i;
     sv none = {NULL, 0};
 
@@ -303,9 +312,9 @@ int ssd_oracle_demultiplex(const ssd_oracle_cfg *cfg, const char *r1, size_t r1_
                 pr.read = sv_rstrip(line);
                 pr.have_read = 1;
                 umi = sv_slice(pr.read, cfg->umi_start, cfg->umi_end);
-                f1 = first_hit(cfg, sv_slice(pr.read, cfg->bc1_start, cfg->bc1_end));
-                f2 = first_hit(cfg, sv_slice(pr.read, cfg->bc2_start, cfg->bc2_end));
-                f3 = first_hit(cfg, sv_slice(pr.read, cfg->bc3_start, cfg->bc3_end));
+                f1 = first_hit(cfg, 0, sv_slice(pr.read, cfg->bc1_start, cfg->bc1_end));
+                f2 = first_hit(cfg, 1, sv_slice(pr.read, cfg->bc2_start, cfg->bc2_end));
+                f3 = first_hit(cfg, 2, sv_slice(pr.read, cfg->bc3_start, cfg->bc3_end));
                 complete++;
             }
             if (line_ct % 4 == 3) {                             /* V2:306-308 */
@@ -333,7 +342,7 @@ int ssd_oracle_demultiplex(const ssd_oracle_cfg *cfg, const char *r1, size_t r1_
                     rc = fail(out, SSD_ORACLE_EMALFORMED, "read 2: record completed without an id", none);
                     goto bin_done;
                 }
-                rec_cell[rec_n++] = (int32_t)((f1 * n + f2) * n + f3);
+                rec_cell[rec_n++] = (int32_t)((f1 * n2 + f2) * n3 + f3);
                 if (nr == rcap) {
                     rcap = rcap ? rcap * 2 : 1024;
                     rr = (rrec *)realloc(rr, rcap * sizeof *rr);
@@ -400,9 +409,15 @@ int ssd_oracle_demultiplex(const ssd_oracle_cfg *cfg, const char *r1, size_t r1_
                 if (buf_put(&merged, t.p, t.n)) { rc = SSD_ORACLE_ENOMEM; goto bin_done; }
             }
             buf_put(&merged, "_", 1);
-            w = cfg->whitelist + 8 * (size_t)rr[k].b1; wl = cfg->wl_len ? cfg->wl_len[rr[k].b1] : 8; buf_put(&merged, w, wl);
-            w = cfg->whitelist + 8 * (size_t)rr[k].b2; wl = cfg->wl_len ? cfg->wl_len[rr[k].b2] : 8; buf_put(&merged, w, wl);
-            w = cfg->whitelist + 8 * (size_t)rr[k].b3; wl = cfg->wl_len ? cfg->wl_len[rr[k].b3] : 8; buf_put(&merged, w, wl);
+            {
+                const int idx[3] = {rr[k].b1, rr[k].b2, rr[k].b3};
+                int rq;
+                for (rq = 0; rq < 3; rq++) {
+                    const char *list; const uint8_t *len; int nq;
+                    round_list(cfg, rq, &list, &len, &nq);
+                    w = list + 8 * (size_t)idx[rq]; wl = len ? len[idx[rq]] : 8; buf_put(&merged, w, wl);
+                }
+            }
             buf_put(&merged, "_", 1);
             buf_put(&merged, rr[k].umi.p, rr[k].umi.n);
             buf_put(&merged, "\n", 1);

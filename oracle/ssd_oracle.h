@@ -43,6 +43,15 @@ typedef struct ssd_oracle_cfg {
     int bc3_start, bc3_end;
     int errors;              /* -e : max Hamming distance per barcode                             */
     long bin_reads;          /* -b : reads per bin (V2:80)                                        */
+    /* Per-round lists (extension beyond the reference's fast path, which matches all three windows against the one list above,
+     * V2:60, 302-304): whitelist2 / whitelist3 != NULL give the Round2 (bc2) / Round3 (bc3) window its own list, matched by
+     * the same first-hit rule.  Parity of this extension is pinned on the restated rule only (the reference cannot run it). */
+    const char *whitelist2;
+    const uint8_t *wl_len2;
+    int n_whitelist2;
+    const char *whitelist3;
+    const uint8_t *wl_len3;
+    int n_whitelist3;
 } ssd_oracle_cfg;
 
 typedef struct ssd_oracle_cell {

@@ -19,7 +19,9 @@ class _Cfg(C.Structure):
     _fields_ = [("whitelist", C.c_char_p), ("wl_len", C.POINTER(C.c_uint8)), ("n_whitelist", C.c_int),
                 ("umi_start", C.c_int), ("umi_end", C.c_int), ("bc1_start", C.c_int), ("bc1_end", C.c_int),
                 ("bc2_start", C.c_int), ("bc2_end", C.c_int), ("bc3_start", C.c_int), ("bc3_end", C.c_int),
-                ("errors", C.c_int), ("bin_reads", C.c_long)]
+                ("errors", C.c_int), ("bin_reads", C.c_long),
+                ("whitelist2", C.c_char_p), ("wl_len2", C.POINTER(C.c_uint8)), ("n_whitelist2", C.c_int),
+                ("whitelist3", C.c_char_p), ("wl_len3", C.POINTER(C.c_uint8)), ("n_whitelist3", C.c_int)]
 
 
 class _Cell(C.Structure):
@@ -93,15 +95,25 @@ class OracleResult:
 DEFAULT_POSITIONS = dict(umi=(0, 10), bc3=(10, 18), bc2=(48, 56), bc1=(86, 94))  # V2:155-162
 
 
-def _cfg(whitelist: List[str], e: int, bin_reads: int, positions: Optional[dict]):
+def _cfg(whitelist: List[str], e: int, bin_reads: int, positions: Optional[dict], whitelist2=None, whitelist3=None):
     pos = dict(DEFAULT_POSITIONS)
     if positions:
         pos.update(positions)
-    raw = b"".join(w.encode().ljust(8, b"\0")[:8] for w in whitelist)
-    lens = (C.c_uint8 * len(whitelist))(*[min(len(w), 8) for w in whitelist])
+
+    def pack(ws):
+        return b"".join(w.encode().ljust(8, b"\0")[:8] for w in ws), (C.c_uint8 * len(ws))(*[min(len(w), 8) for w in ws])
+    raw, lens = pack(whitelist)
     cfg = _Cfg(raw, lens, len(whitelist), pos["umi"][0], pos["umi"][1], pos["bc1"][0], pos["bc1"][1],
                pos["bc2"][0], pos["bc2"][1], pos["bc3"][0], pos["bc3"][1], e, bin_reads)
-    cfg._keep = (raw, lens)
+    cfg._keep = [raw, lens]
+    if whitelist2 is not None:  # extension: the Round2 / Round3 windows against their own lists
+        raw2, lens2 = pack(whitelist2)
+        cfg.whitelist2, cfg.wl_len2, cfg.n_whitelist2 = raw2, lens2, len(whitelist2)
+        cfg._keep += [raw2, lens2]
+    if whitelist3 is not None:
+        raw3, lens3 = pack(whitelist3)
+        cfg.whitelist3, cfg.wl_len3, cfg.n_whitelist3 = raw3, lens3, len(whitelist3)
+        cfg._keep += [raw3, lens3]
     return cfg
 
 
@@ -127,10 +139,10 @@ def _collect(out: _Out, want_rec_cell: bool) -> OracleResult:
 
 
 def demultiplex(r1: bytes, r2: bytes, whitelist: List[str], e: int, m: int, *, bin_reads: int = 100000,
-                positions: Optional[dict] = None, want_rec_cell: bool = True) -> OracleResult:
-    """demultiplex_fun followed by calc_demux_results (V2:32-462)."""
+                positions: Optional[dict] = None, want_rec_cell: bool = True, whitelist2=None, whitelist3=None) -> OracleResult:
+    """demultiplex_fun followed by calc_demux_results (V2:32-462).  whitelist2 / whitelist3: the per-round extension."""
     L = lib()
-    cfg = _cfg(whitelist, e, bin_reads, positions)
+    cfg = _cfg(whitelist, e, bin_reads, positions, whitelist2, whitelist3)
     out = _Out()
     try:
         rc = L.ssd_oracle_demultiplex(C.byref(cfg), r1, len(r1), r2, len(r2), C.byref(out))

@@ -80,7 +80,8 @@ struct ssd_ctx {
     DevCfg dcfg{};
     uint64_t n_cells_total = 0;
     int record_hint = 48;
-    int bc_const = 0;  // 3 * whitelist entry length when all entries have the same length
+    int bc_const = 0;  // bytes of the three barcodes of a cell when every entry of a round has the same length
+    int n_lut_sets = 0;  // distinct whitelists among the three rounds
     uint32_t scan_grid = 296;  // persistent scan blocks: SM count x resident blocks per SM
     char err[512] = "";
 
@@ -659,7 +660,8 @@ OutLen make_outlen(ssd_ctx* c, int which)
     f.pass = which == SSD_EMIT_PASSING ? c->d_pass : nullptr;
     f.remap = (which == SSD_EMIT_PASSING && c->cfg.collapse_pairs > 0) ? c->d_remap : nullptr;
     f.wl_len = c->d_wl_len;
-    f.n = c->dcfg.n_wl;
+    f.n2 = c->dcfg.n_wl[1];
+    f.n3 = c->dcfg.n_wl[2];
     f.umi_len = c->dcfg.umi_len;
     f.bc_const = c->bc_const;
     f.copy_mode = c->annotated ? 1 : 0;
@@ -697,9 +699,19 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
 {
     if (!cfg || !out) return fail(nullptr, SSD_EINVAL, "ssd_create: null argument");
     *out = nullptr;
-    if (cfg->struct_size != sizeof(ssd_config)) return fail(nullptr, SSD_EINVAL, "ssd_config.struct_size %u != %zu", cfg->struct_size, sizeof(ssd_config));
+    // the structure grew by the per-round lists: a caller compiled against the first layout passes the shorter size and gets one list
+    const size_t v1_size = offsetof(ssd_config, n_whitelist2);
+    if (cfg->struct_size != sizeof(ssd_config) && cfg->struct_size != v1_size)
+        return fail(nullptr, SSD_EINVAL, "ssd_config.struct_size %u is neither %zu nor %zu", cfg->struct_size, sizeof(ssd_config), v1_size);
+    ssd_config full;
+    memset(&full, 0, sizeof full);
+    memcpy(&full, cfg, cfg->struct_size);
+    cfg = &full;
     if (cfg->n_whitelist < 1 || cfg->n_whitelist > SSD_MAX_WHITELIST || !cfg->whitelist)
         return fail(nullptr, SSD_EINVAL, "whitelist must hold 1..%d entries", SSD_MAX_WHITELIST);
+    if ((cfg->whitelist2 && (cfg->n_whitelist2 < 1 || cfg->n_whitelist2 > SSD_MAX_WHITELIST)) ||
+        (cfg->whitelist3 && (cfg->n_whitelist3 < 1 || cfg->n_whitelist3 > SSD_MAX_WHITELIST)))
+        return fail(nullptr, SSD_EINVAL, "the round 2 / round 3 whitelists must hold 1..%d entries", SSD_MAX_WHITELIST);
     const int32_t bounds[8] = {cfg->umi_start, cfg->umi_end, cfg->bc1_start, cfg->bc1_end, cfg->bc2_start, cfg->bc2_end, cfg->bc3_start, cfg->bc3_end};
     for (int i = 0; i < 8; i += 2)
         if (bounds[i] < 0 || bounds[i + 1] < bounds[i])
@@ -709,7 +721,7 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
         if (bounds[i + 1] - bounds[i] > 8) return fail(nullptr, SSD_EINVAL, "barcode windows longer than 8 bases are not supported");
     if (cfg->errors < 0 || cfg->errors > 8) return fail(nullptr, SSD_EINVAL, "errors must be in 0..8");
     if (cfg->filter_mode != SSD_FILTER_DISTINCT_UMI && cfg->filter_mode != SSD_FILTER_READS) return fail(nullptr, SSD_EINVAL, "unknown filter_mode");
-    if (cfg->collapse_pairs < 0 || 2 * cfg->collapse_pairs > cfg->n_whitelist) return fail(nullptr, SSD_EINVAL, "collapse_pairs out of range");
+    if (cfg->collapse_pairs < 0 || 2 * cfg->collapse_pairs > cfg->n_whitelist) return fail(nullptr, SSD_EINVAL, "collapse_pairs out of range");  // round-1 list
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -718,8 +730,9 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
 
     ssd_ctx* c = new ssd_ctx();
     c->cfg = *cfg;
-    c->cfg.whitelist = nullptr;
-    c->cfg.whitelist_len = nullptr;
+    c->cfg.struct_size = sizeof(ssd_config);
+    c->cfg.whitelist = c->cfg.whitelist2 = c->cfg.whitelist3 = nullptr;
+    c->cfg.whitelist_len = c->cfg.whitelist2_len = c->cfg.whitelist3_len = nullptr;
     if (cfg->device >= 0) {
         c->device = cfg->device;
     } else if (cudaGetDevice(&c->device) != cudaSuccess) {
@@ -747,7 +760,6 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
 
     DevCfg& d = c->dcfg;
     memset(&d, 0, sizeof d);
-    d.n_wl = cfg->n_whitelist;
     d.e = cfg->errors;
     d.us = cfg->umi_start;
     d.ue = cfg->umi_end;
@@ -759,34 +771,48 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
     d.b3e = cfg->bc3_end;
     d.umi_len = d.ue - d.us;
     d.umi_bits = 2 * d.umi_len;
-    c->n_cells_total = (uint64_t)d.n_wl * d.n_wl * d.n_wl;
+    // round k: its own list when given, else the first one (V2:60: one list for all rounds)
+    const char* lists[3] = {cfg->whitelist, cfg->whitelist2 ? cfg->whitelist2 : cfg->whitelist, cfg->whitelist3 ? cfg->whitelist3 : cfg->whitelist};
+    const uint8_t* lens[3] = {cfg->whitelist_len, cfg->whitelist2 ? cfg->whitelist2_len : cfg->whitelist_len,
+                              cfg->whitelist3 ? cfg->whitelist3_len : cfg->whitelist_len};
+    const int counts[3] = {cfg->n_whitelist, cfg->whitelist2 ? cfg->n_whitelist2 : cfg->n_whitelist, cfg->whitelist3 ? cfg->n_whitelist3 : cfg->n_whitelist};
+    d.fast_wl = 1;
+    d.bc8 = 1;
+    c->bc_const = 0;
+    bool same_len = true;
+    for (int k = 0; k < 3; k++) {
+        d.n_wl[k] = counts[k];
+        for (int i = 0; i < d.n_wl[k]; i++) {
+            int len = lens[k] ? std::min<int>(lens[k][i], 8) : 8;
+            d.wl_len[k][i] = (uint8_t)len;
+            uint32_t code = 0;
+            for (int j = 0; j < 8; j++) {
+                unsigned char ch = j < len ? (unsigned char)lists[k][i * 8 + j] : 0;
+                d.wl[k][i * 8 + j] = ch;
+                bool acgt = ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T';
+                if (!acgt) d.fast_wl = 0;
+                code |= ((uint32_t)(ch >> 1) & 3u) << (2 * j);
+            }
+            if (len != 8) d.fast_wl = d.bc8 = 0;
+            if (len != d.wl_len[k][0]) same_len = false;
+            d.wl_code[k][i] = (uint16_t)code;
+        }
+        // rounds with the same list share their lookup tables (sets are numbered densely in order of first use)
+        d.lut_set[k] = -1;
+        for (int j = 0; j < k && d.lut_set[k] < 0; j++)
+            if (d.n_wl[j] == d.n_wl[k] && memcmp(d.wl[j], d.wl[k], sizeof d.wl[k]) == 0 && memcmp(d.wl_len[j], d.wl_len[k], sizeof d.wl_len[k]) == 0)
+                d.lut_set[k] = d.lut_set[j];
+        if (d.lut_set[k] < 0) d.lut_set[k] = c->n_lut_sets++;
+    }
+    c->n_cells_total = (uint64_t)d.n_wl[0] * d.n_wl[1] * d.n_wl[2];
     d.cell_bits = 1;
     while ((1ull << d.cell_bits) < c->n_cells_total) d.cell_bits++;
-    d.fast_wl = 1;
-    for (int i = 0; i < d.n_wl; i++) {
-        int len = cfg->whitelist_len ? std::min<int>(cfg->whitelist_len[i], 8) : 8;
-        d.wl_len[i] = (uint8_t)len;
-        uint32_t code = 0;
-        for (int j = 0; j < 8; j++) {
-            unsigned char ch = j < len ? (unsigned char)cfg->whitelist[i * 8 + j] : 0;
-            d.wl[i * 8 + j] = ch;
-            bool acgt = ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T';
-            if (!acgt) d.fast_wl = 0;
-            code |= ((uint32_t)(ch >> 1) & 3u) << (2 * j);
-        }
-        if (len != 8) d.fast_wl = 0;
-        d.wl_code[i] = (uint16_t)code;
-    }
     d.fast_geom = (d.b1e - d.b1s == 8 && d.b2e - d.b2s == 8 && d.b3e - d.b3s == 8) ? 1 : 0;
     d.need_len = std::max(std::max(d.ue, d.b1e), std::max(d.b2e, d.b3e));
-    d.magic_n = ((1ull << 43) + (unsigned long long)d.n_wl - 1) / (unsigned long long)d.n_wl;
-    d.magic_nn = ((1ull << 43) + (unsigned long long)d.n_wl * d.n_wl - 1) / ((unsigned long long)d.n_wl * d.n_wl);
-    d.bc8 = 1;
-    for (int i = 0; i < d.n_wl; i++)
-        if (d.wl_len[i] != 8) d.bc8 = 0;
-    c->bc_const = 3 * d.wl_len[0];
-    for (int i = 1; i < d.n_wl; i++)
-        if (d.wl_len[i] != d.wl_len[0]) c->bc_const = 0;
+    const unsigned long long n3 = (unsigned long long)d.n_wl[2], n23 = (unsigned long long)d.n_wl[1] * n3;
+    d.magic_n = ((1ull << 43) + n3 - 1) / n3;
+    d.magic_nn = ((1ull << 43) + n23 - 1) / n23;
+    if (same_len) c->bc_const = d.wl_len[0][0] + d.wl_len[1][0] + d.wl_len[2][0];
     c->record_hint = cfg->record_bytes_hint > 0 ? cfg->record_bytes_hint : 48;
 
     {
@@ -818,20 +844,25 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
     CUB_(cudaMalloc(&c->d_cnt, sizeof(DevCounters)));
     CUB_(cudaMalloc(&c->d_err_off, 2 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_ucnt, 2 * sizeof(unsigned long long)));
-    CUB_(cudaMalloc(&c->d_lut, (size_t)(d.e + 1) * 65536u));
-    CUB_(cudaMalloc(&c->d_wl_len, kMaxWl));
-    CUB_(cudaMalloc(&c->d_wl64, kMaxWl * 8));
+    CUB_(cudaMalloc(&c->d_lut, (size_t)c->n_lut_sets * (size_t)(d.e + 1) * 65536u));
+    CUB_(cudaMalloc(&c->d_wl_len, 3 * kMaxWl));
+    CUB_(cudaMalloc(&c->d_wl64, 3 * kMaxWl * 8));
     CUB_(cudaMalloc(&c->d_hist, c->n_cells_total * sizeof(uint32_t)));
     CUB_(cudaMalloc(&c->d_distinct, c->n_cells_total * sizeof(uint32_t)));
     CUB_(cudaMalloc(&c->d_remap, c->n_cells_total * sizeof(uint32_t)));
     CUB_(cudaMalloc(&c->d_pass, c->n_cells_total));
-    CUB_(cudaMemcpyAsync(c->d_wl_len, d.wl_len, kMaxWl, cudaMemcpyHostToDevice, c->stream));
-    CUB_(cudaMemcpyAsync(c->d_wl64, d.wl, kMaxWl * 8, cudaMemcpyHostToDevice, c->stream));
+    CUB_(cudaMemcpyAsync(c->d_wl_len, d.wl_len, 3 * kMaxWl, cudaMemcpyHostToDevice, c->stream));
+    CUB_(cudaMemcpyAsync(c->d_wl64, d.wl, 3 * kMaxWl * 8, cudaMemcpyHostToDevice, c->stream));
     CUB_(cudaMemsetAsync(c->d_hist, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
     CUB_(cudaMemsetAsync(c->d_distinct, 0, c->n_cells_total * sizeof(uint32_t), c->stream));
     CUB_(cudaMemsetAsync(c->d_pass, 0, c->n_cells_total, c->stream));
     CUB_(cudaMemsetAsync(c->d_cnt, 0, sizeof(DevCounters), c->stream));
-    if (d.fast_wl) k_build_lut<<<256, 256, 0, c->stream>>>(d, c->d_lut, d.e + 1);
+    if (d.fast_wl)
+        for (int k = 0, built = 0; k < 3; k++)
+            if (d.lut_set[k] == built) {  // the first round of every set builds it
+                k_build_lut<<<256, 256, 0, c->stream>>>(d, k, c->d_lut + (size_t)built * (size_t)(d.e + 1) * 65536u, d.e + 1);
+                built++;
+            }
     CUB_(cudaGetLastError());
     CUB_(cudaStreamSynchronize(c->stream));
 #undef CUB_
@@ -1176,7 +1207,7 @@ extern "C" int ssd_build_filter(ssd_ctx* c, ssd_stats* stats)
     const uint32_t nbc = blocks_for(c->n_cells_total, kThreads);
     k_filter<<<nbc, kThreads, 0, c->stream>>>(c->d_hist, c->d_distinct, c->n_cells_total, (long long)c->cfg.min_count, c->cfg.filter_mode, c->d_pass,
                                               c->d_cnt);
-    if (c->cfg.collapse_pairs > 0) k_collapse_map<<<nbc, kThreads, 0, c->stream>>>(c->d_pass, c->dcfg.n_wl, c->cfg.collapse_pairs, c->d_remap);
+    if (c->cfg.collapse_pairs > 0) k_collapse_map<<<nbc, kThreads, 0, c->stream>>>(c->d_pass, c->dcfg.n_wl[0], c->dcfg.n_wl[1] * c->dcfg.n_wl[2], c->cfg.collapse_pairs, c->d_remap);
     {
         // exclusive scan of the post-filter output lengths; its first kernel also counts the retained records
         // and sizes the pre-filter output
@@ -1788,6 +1819,59 @@ extern "C" int ssd_load_file_range(ssd_ctx* c, int slot, const char* path, uint6
     close(fd);
     if (rc == SSD_OK) c->loaded[slot] = len;
     return rc;
+}
+
+extern "C" int ssd_anchor_positions(const void* d_text, size_t len, uint32_t n_lines, const char* const anchors[3], int32_t* found, uint32_t capacity,
+                                    uint32_t* n_sequence_lines)
+{
+    if (!anchors || !found || !n_sequence_lines || n_lines == 0 || n_lines > (uint32_t)kLearnMaxLines || (len && !d_text)) return SSD_EINVAL;
+    uint8_t h_anchor[48];
+    int h_len[3];
+    memset(h_anchor, 0, sizeof h_anchor);
+    for (int k = 0; k < 3; k++) {
+        if (!anchors[k] || strlen(anchors[k]) > 16) return SSD_EINVAL;
+        h_len[k] = (int)strlen(anchors[k]);
+        memcpy(h_anchor + 16 * k, anchors[k], (size_t)h_len[k]);
+    }
+    uint8_t* d_anchor = nullptr;
+    int32_t* d_found = nullptr;
+    const size_t found_bytes = (size_t)3 * capacity * sizeof(int32_t);
+    if (cudaMalloc(&d_anchor, 64 + 16 + 16) != cudaSuccess) return SSD_ECUDA;
+    if (cudaMalloc(&d_found, std::max<size_t>(found_bytes, 16)) != cudaSuccess) {
+        cudaFree(d_anchor);
+        return SSD_ECUDA;
+    }
+    int* d_len = (int*)(d_anchor + 64);
+    uint32_t* d_nseq = (uint32_t*)(d_anchor + 80);
+    bool ok = cudaMemcpy(d_anchor, h_anchor, sizeof h_anchor, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(d_len, h_len, sizeof h_len, cudaMemcpyHostToDevice) == cudaSuccess && cudaMemset(d_found, 0xFF, std::max<size_t>(found_bytes, 16)) == cudaSuccess;
+    if (ok) {
+        k_anchor_positions<<<1, 256>>>((const uint8_t*)d_text, (unsigned long long)len, n_lines, d_anchor, d_len, d_found, capacity, d_nseq);
+        ok = cudaGetLastError() == cudaSuccess && cudaMemcpy(found, d_found, found_bytes, cudaMemcpyDeviceToHost) == cudaSuccess &&
+             cudaMemcpy(n_sequence_lines, d_nseq, sizeof(uint32_t), cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    cudaFree(d_anchor);
+    cudaFree(d_found);
+    return ok ? SSD_OK : SSD_ECUDA;
+}
+
+extern "C" int ssd_loaded_newlines(ssd_ctx* c, int slot, int tile_log2, uint32_t* tile_counts, uint64_t capacity, uint64_t* n_tiles)
+{
+    if (!c || slot < 0 || slot > 1 || tile_log2 < 12 || tile_log2 > 30 || !n_tiles) return SSD_EINVAL;
+    CU(c, cudaSetDevice(c->device));
+    const uint64_t len = c->loaded[slot], tiles = (len + (1ull << tile_log2) - 1) >> tile_log2;
+    *n_tiles = tiles;
+    if (tiles == 0) return SSD_OK;
+    if (!tile_counts || capacity < tiles) return fail(c, SSD_ERANGE, "ssd_loaded_newlines: %llu tiles, room for %llu", (unsigned long long)tiles,
+                                                      (unsigned long long)capacity);
+    OKR(ensure(c, c->b_first, tiles * sizeof(uint32_t)));
+    const DevBuf& buf = slot == 0 ? c->b_in1 : c->b_in2;
+    k_count_newlines<<<(uint32_t)tiles, 256, 0, c->stream>>>((const uint8_t*)buf.p, len, tile_log2, (uint32_t*)c->b_first.p);
+    c->n_launches++;
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(tile_counts, c->b_first.p, tiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SSD_OK;
 }
 
 extern "C" int ssd_demux_loaded(ssd_ctx* c)

@@ -14,25 +14,36 @@ constexpr int kThreads = 256;
 // configuration passed to kernels by value (__grid_constant__)
 // ---------------------------------------------------------------------------------------------
 struct DevCfg {
-    int n_wl, e;
+    // Round k (0: the BC1 window, 1: BC2, 2: BC3) is matched against its own list.  The reference's fast path uses ONE list for
+    // all three (V2:60, 302-304: the 8-mers of Round1_barcodes_new5.txt), which is three equal lists here; rounds with equal
+    // lists share their lookup tables (lut_set).
+    int n_wl[3], lut_set[3], e;
     int us, ue, b1s, b1e, b2s, b2e, b3s, b3e;  // Python slice bounds into the read-2 sequence (V2:155-162)
     int umi_len;      // ue - us (<= 10)
     int umi_bits;     // 2 * umi_len
-    int cell_bits;    // ceil(log2(n_wl^3))
-    int fast_wl;      // every whitelist entry is 8 x ACGT -> 2-bit path + LUT
+    int cell_bits;    // ceil(log2(n1 n2 n3))
+    int fast_wl;      // every whitelist entry (of every round) is 8 x ACGT -> 2-bit path + LUT
     int fast_geom;    // all three barcode windows are exactly 8 wide
     int need_len;     // largest slice end: shorter read-2 sequences take the exact generic path
     int bc8;          // every whitelist entry is exactly 8 bytes long
-    unsigned long long magic_n, magic_nn;  // ceil(2^43 / n), ceil(2^43 / n^2): exact division of cell ids < 2^21
-    uint16_t wl_code[kMaxWl];
-    uint8_t wl_len[kMaxWl];
-    uint8_t wl[kMaxWl * 8];
+    unsigned long long magic_n, magic_nn;  // ceil(2^43 / n3), ceil(2^43 / (n2 n3)): exact division of cell ids < 2^21
+    uint16_t wl_code[3][kMaxWl];
+    uint8_t wl_len[3][kMaxWl];
+    uint8_t wl[3][kMaxWl * 8];
 };
+
+// cell id of the three list indices: (i1 * n2 + i2) * n3 + i3
+__device__ __forceinline__ uint32_t cell_of(const DevCfg& c, int i1, int i2, int i3) { return (uint32_t)((i1 * c.n_wl[1] + i2) * c.n_wl[2] + i3); }
+// the (e + 1) x 65536 first-hit tables of a round; level `lvl` of them
+__device__ __forceinline__ const uint8_t* lut_of(const DevCfg& c, const uint8_t* lut, int round, int lvl)
+{
+    return lut + ((size_t)c.lut_set[round] * (size_t)(c.e + 1) + (size_t)lvl) * 65536u;
+}
 
 // ---------------------------------------------------------------------------------------------
 // per-record annotation word (one uint64 per read pair, written by the read-2 scan)
 //   [63:62] state   0 = rejected, 1 = matched with a regular UMI, 2 = matched with an irregular UMI
-//   [61:41] cell    (i1 * n + i2) * n + i3
+//   [61:41] cell    (i1 * n2 + i2) * n3 + i3
 //   [40:0]  payload regular:   2-bit packed UMI (umi_bits wide)
 //                   irregular: (global offset of the UMI's first byte in read 2) << 5 | UMI length
 // ---------------------------------------------------------------------------------------------
@@ -204,7 +215,8 @@ __device__ __forceinline__ Packed pack_window(const Acc& a, size_t seq_s, size_t
 // V2:302-304 + 327-329: index of the FIRST whitelist entry (file order) whose Hamming distance to the
 // window over the overlapping prefix (zip() truncation, V2:72-73) is <= e; -1 when there is none.
 // lut[code] holds that index for full-length all-ACGT windows (0xFF = none).
-__device__ __forceinline__ int match_window(const DevCfg& c, const Packed& p, const uint8_t* raw, const uint8_t* __restrict__ lut)
+// `lut` = the round's level-e table (lut_of(c, base, round, c.e)).
+__device__ __forceinline__ int match_window(const DevCfg& c, int round, const Packed& p, const uint8_t* raw, const uint8_t* __restrict__ lut)
 {
     if (c.fast_wl) {
         if (p.n == 8 && p.valid == 0x5555u) {
@@ -214,17 +226,17 @@ __device__ __forceinline__ int match_window(const DevCfg& c, const Packed& p, co
         const uint32_t lenmask = p.n >= 8 ? 0x5555u : ((1u << (2 * p.n)) - 1u) & 0x5555u;
         const int base_d = __popc(lenmask & ~p.valid);  // non-ACGT bytes never equal a whitelist base
         if (base_d > c.e) return -1;
-        for (int i = 0; i < c.n_wl; i++) {
-            uint32_t x = p.code ^ c.wl_code[i];
+        for (int i = 0; i < c.n_wl[round]; i++) {
+            uint32_t x = p.code ^ c.wl_code[round][i];
             int d = base_d + __popc((x | (x >> 1)) & p.valid);
             if (d <= c.e) return i;
         }
         return -1;
     }
-    for (int i = 0; i < c.n_wl; i++) {
-        int n = p.n < (int)c.wl_len[i] ? p.n : (int)c.wl_len[i];
+    for (int i = 0; i < c.n_wl[round]; i++) {
+        int n = p.n < (int)c.wl_len[round][i] ? p.n : (int)c.wl_len[round][i];
         int d = 0;
-        for (int j = 0; j < n; j++) d += raw[j] != c.wl[i * 8 + j];
+        for (int j = 0; j < n; j++) d += raw[j] != c.wl[round][i * 8 + j];
         if (d <= c.e) return i;
     }
     return -1;
@@ -321,11 +333,11 @@ __device__ __forceinline__ uint32_t div_magic(uint32_t x, unsigned long long mag
 
 __device__ __forceinline__ void cell_indices(const DevCfg& c, uint32_t cell, uint32_t& i1, uint32_t& i2, uint32_t& i3)
 {
-    const uint32_t n = (uint32_t)c.n_wl;
+    const uint32_t n2 = (uint32_t)c.n_wl[1], n3 = (uint32_t)c.n_wl[2];
     i1 = div_magic(cell, c.magic_nn);
-    const uint32_t rem = cell - i1 * n * n;
+    const uint32_t rem = cell - i1 * n2 * n3;
     i2 = div_magic(rem, c.magic_n);
-    i3 = rem - i2 * n;
+    i3 = rem - i2 * n3;
 }
 
 }  // namespace ssd

@@ -36,15 +36,16 @@ __global__ void k_filter(const uint32_t* hist, const uint32_t* distinct, uint64_
     }
 }
 
-__global__ void k_collapse_map(const uint8_t* pass, int n, int pairs, uint32_t* remap)
+// n1, n23: size of the round-1 list, product of the sizes of the round-2 and round-3 lists
+__global__ void k_collapse_map(const uint8_t* pass, int n1, int n23, int pairs, uint32_t* remap)
 {
     uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t total = (uint64_t)n * n * n;
+    uint64_t total = (uint64_t)n1 * n23;
     if (c >= total) return;
-    uint32_t i1 = (uint32_t)(c / ((uint64_t)n * n));
+    uint32_t i1 = (uint32_t)(c / (uint64_t)n23);
     uint32_t out = (uint32_t)c;
     if (i1 >= (uint32_t)pairs && i1 < 2u * (uint32_t)pairs && pass[c]) {
-        uint64_t odt = c - (uint64_t)pairs * n * n;
+        uint64_t odt = c - (uint64_t)pairs * n23;
         if (pass[odt]) out = (uint32_t)odt;
     }
     remap[c] = out;
@@ -58,15 +59,15 @@ struct OutLen {
     const uint32_t* r1_base;  // header' + seq + qual + 7 fixed bytes, from the read-1 scan
     const uint8_t* pass;      // NULL = every matched record (MergedCells_1)
     const uint32_t* remap;    // NULL = no collapse
-    const uint8_t* wl_len;    // device copy of the per-entry whitelist lengths
-    int n, umi_len, bc_const;  // bc_const > 0: all entries have that length, 3 * length is added without lookups
+    const uint8_t* wl_len;    // device copy of the per-entry whitelist lengths: kMaxWl per round
+    int n2, n3, umi_len, bc_const;  // bc_const > 0: the three entries of every cell have that many bytes together, added without lookups
     int copy_mode;            // annotated input: records are copied as they are, r1_base already is the length
     __device__ __forceinline__ uint32_t bc_len(uint32_t cell, bool collapse) const
     {
         if (bc_const) return (uint32_t)bc_const;
         if (collapse && remap) cell = remap[cell];
-        const uint32_t i3 = cell % (uint32_t)n, i2 = (cell / (uint32_t)n) % (uint32_t)n, i1 = cell / ((uint32_t)n * (uint32_t)n);
-        return wl_len[i1] + wl_len[i2] + wl_len[i3];
+        const uint32_t i3 = cell % (uint32_t)n3, i2 = (cell / (uint32_t)n3) % (uint32_t)n2, i1 = cell / ((uint32_t)n2 * (uint32_t)n3);
+        return wl_len[i1] + wl_len[kMaxWl + i2] + wl_len[2 * kMaxWl + i3];
     }
     __device__ __forceinline__ uint32_t operator()(uint64_t r) const
     {
@@ -208,7 +209,7 @@ struct EmitArgs {
     const uint32_t* order;    // split mode: position k of the output holds record order[k] (NULL = input order)
     int copy_mode;            // annotated input: header, read, third line and quality are copied strip()ped (V2:435-447)
     DevCounters* cnt;
-    const unsigned long long* wl64;  // tiled writer: the whitelist entries as 8-byte words
+    const unsigned long long* wl64;  // tiled writer: the whitelist entries as 8-byte words, kMaxWl per round
     uint32_t cps, cps_magic;         // tiled writer: 16-byte chunk slots per record, ceil(2^20 / cps)
 };
 
@@ -273,8 +274,8 @@ __device__ __forceinline__ uint32_t emit_record_generic(const Acc& a, const Emit
     o += 1;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        uint32_t wl = cfg.wl_len[idx[k]];
-        if ((uint32_t)lane < wl) dst[o + lane] = cfg.wl[idx[k] * 8 + lane];
+        uint32_t wl = cfg.wl_len[k][idx[k]];
+        if ((uint32_t)lane < wl) dst[o + lane] = cfg.wl[k][idx[k] * 8 + lane];
         o += wl;
     }
     if (lane == 0) dst[o] = '_';
@@ -432,13 +433,13 @@ __device__ __forceinline__ uint32_t emit_group(const EmitArgs<OffT>& args, const
             uint32_t ch = '_';
             if (k) {
                 const uint32_t which = (k - 1u) >> 3, idx = which == 0u ? i1 : (which == 1u ? i2 : i3);
-                ch = cfg.wl[idx * 8u + ((k - 1u) & 7u)];
+                ch = cfg.wl[which][idx * 8u + ((k - 1u) & 7u)];
             }
             q[k] = (uint8_t)ch;
         }
         {
             const uint32_t k = 24u + (uint32_t)gl;  // 24: last barcode byte, 25: '_', 26..31: UMI 0..5
-            uint32_t ch = gl == 0 ? (uint32_t)cfg.wl[i3 * 8u + 7u] : (uint32_t)'_';
+            uint32_t ch = gl == 0 ? (uint32_t)cfg.wl[2][i3 * 8u + 7u] : (uint32_t)'_';
             if (gl >= 2) ch = __byte_perm(0x47544341u, 0u, (uint32_t)(payload >> (2u * (uint32_t)(gl - 2))) & 3u) & 0xFFu;
             q[k] = (uint8_t)ch;
         }
@@ -449,15 +450,15 @@ __device__ __forceinline__ uint32_t emit_group(const EmitArgs<OffT>& args, const
         }
         o += 37u;
     } else {
-        const uint32_t l1 = cfg.wl_len[i1], l2 = cfg.wl_len[i2], l3 = cfg.wl_len[i3];
+        const uint32_t l1 = cfg.wl_len[0][i1], l2 = cfg.wl_len[1][i2], l3 = cfg.wl_len[2][i3];
         const uint32_t ulen = ann_umi_len(an, cfg.umi_len);
         const uint32_t c1 = 1u, c2 = c1 + l1, c3 = c2 + l2, c4 = c3 + l3, c5 = c4 + 1u, c6 = c5 + ulen, lit = c6 + 1u;
         for (uint32_t k = gl; k < lit; k += kGroup) {
             uint32_t ch;
             if (k == 0u || k == c4) ch = '_';
-            else if (k < c2) ch = cfg.wl[i1 * 8u + (k - c1)];
-            else if (k < c3) ch = cfg.wl[i2 * 8u + (k - c2)];
-            else if (k < c4) ch = cfg.wl[i3 * 8u + (k - c3)];
+            else if (k < c2) ch = cfg.wl[0][i1 * 8u + (k - c1)];
+            else if (k < c3) ch = cfg.wl[1][i2 * 8u + (k - c2)];
+            else if (k < c4) ch = cfg.wl[2][i3 * 8u + (k - c3)];
             else if (k < c6) ch = regular ? (uint32_t)base2_char((uint32_t)(payload >> (2u * (k - c5)))) : (uint32_t)args.r2buf[(size_t)(payload >> 5) + (k - c5)];
             else ch = '\n';
             s_out[d + o + k] = (uint8_t)ch;

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kThreads) k_emit_tiled(const __grid_constant__
             if (args.remap) cell = args.remap[cell];
             uint32_t i1, i2, i3;
             cell_indices(cfg, cell, i1, i2, i3);
-            const unsigned long long b1 = __ldg(args.wl64 + i1), b2 = __ldg(args.wl64 + i2), b3 = __ldg(args.wl64 + i3);
+            const unsigned long long b1 = __ldg(args.wl64 + i1), b2 = __ldg(args.wl64 + kMaxWl + i2), b3 = __ldg(args.wl64 + 2 * kMaxWl + i3);
             const uint32_t b1l = (uint32_t)b1, b1h = (uint32_t)(b1 >> 32), b2l = (uint32_t)b2, b2h = (uint32_t)(b2 >> 32), b3l = (uint32_t)b3,
                            b3h = (uint32_t)(b3 >> 32);
             q[0] = '_';
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kStreamThreads, SSD_EMIT_MINBLOCKS) k_emit_str
                     if (args.remap) cell = args.remap[cell];
                     uint32_t i1, i2, i3;
                     cell_indices(cfg, cell, i1, i2, i3);
-                    const unsigned long long b1 = __ldg(args.wl64 + i1), b2 = __ldg(args.wl64 + i2), b3 = __ldg(args.wl64 + i3);
+                    const unsigned long long b1 = __ldg(args.wl64 + i1), b2 = __ldg(args.wl64 + kMaxWl + i2), b3 = __ldg(args.wl64 + 2 * kMaxWl + i3);
                     const uint32_t b1l = (uint32_t)b1, b1h = (uint32_t)(b1 >> 32), b2l = (uint32_t)b2, b2h = (uint32_t)(b2 >> 32), b3l = (uint32_t)b3,
                                    b3h = (uint32_t)(b3 >> 32);
                     q[0] = '_';

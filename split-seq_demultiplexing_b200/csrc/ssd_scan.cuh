@@ -80,7 +80,7 @@ struct ScanArgs {
     uint64_t* ann;
     uint32_t* hist;
     IrrKey* irr;
-    const uint8_t* lut;  // (e + 1) levels of 65536 bytes
+    const uint8_t* lut;  // per distinct list: (e + 1) levels of 65536 bytes (lut_of)
 };
 
 __device__ __forceinline__ void raise(DevCounters* cnt, unsigned long long* err_off, int file, uint32_t flag, size_t off)
@@ -249,17 +249,16 @@ __device__ __noinline__ bool r2_record_generic(const Acc& a, const ScanArgs<OffT
     const size_t seq_len = rstrip_end(a, seq_s, L.e[1]) - seq_s;  // lineRead = line.rstrip()  (V2:293)
 
     uint8_t raw[8];
-    const uint8_t* lut = args.lut + (size_t)cfg.e * 65536u;
     Packed p1 = pack_window(a, seq_s, seq_len, cfg.b1s, cfg.b1e, raw);
-    int i1 = match_window(cfg, p1, raw, lut);
+    int i1 = match_window(cfg, 0, p1, raw, lut_of(cfg, args.lut, 0, cfg.e));
     if (i1 < 0) return true;  // V2:310-313
     Packed p2 = pack_window(a, seq_s, seq_len, cfg.b2s, cfg.b2e, raw);
-    int i2 = match_window(cfg, p2, raw, lut);
+    int i2 = match_window(cfg, 1, p2, raw, lut_of(cfg, args.lut, 1, cfg.e));
     if (i2 < 0) return true;  // V2:314-317
     Packed p3 = pack_window(a, seq_s, seq_len, cfg.b3s, cfg.b3e, raw);
-    int i3 = match_window(cfg, p3, raw, lut);
+    int i3 = match_window(cfg, 2, p3, raw, lut_of(cfg, args.lut, 2, cfg.e));
     if (i3 < 0) return true;  // V2:318-321
-    const uint32_t cell = (uint32_t)((i1 * cfg.n_wl + i2) * cfg.n_wl + i3);
+    const uint32_t cell = cell_of(cfg, i1, i2, i3);
 
     size_t tok_e = L.s[0];
     while (tok_e < L.e[0] && !py_space(a.byte(tok_e))) tok_e++;
@@ -319,25 +318,25 @@ __device__ __noinline__ uint64_t ann_record_generic(const Acc& a, const ScanArgs
         const size_t cell_s = us[0] + 1, cell_n = us[1] - us[0] - 1, umi_s = us[1] + 1, umi_e = nus == 3 ? us[2] : le[0];
         const size_t ulen = umi_e - umi_s;
         int idx[3] = {-1, -1, -1};
-        // the cell must be three whitelist entries back to back (lengths as configured), matched exactly
+        // the cell must be three whitelist entries (of rounds 1, 2, 3) back to back (lengths as configured), matched exactly
         size_t p = cell_s;
         bool shape = true;
         for (int k = 0; k < 3 && shape; k++) {
             idx[k] = -1;
-            for (int i = 0; i < cfg.n_wl && idx[k] < 0; i++) {
-                const size_t n = cfg.wl_len[i];
+            for (int i = 0; i < cfg.n_wl[k] && idx[k] < 0; i++) {
+                const size_t n = cfg.wl_len[k][i];
                 if (p + n > cell_s + cell_n) continue;
                 bool eq = true;
-                for (size_t j = 0; j < n && eq; j++) eq = a.byte(p + j) == cfg.wl[i * 8 + j];
+                for (size_t j = 0; j < n && eq; j++) eq = a.byte(p + j) == cfg.wl[k][i * 8 + j];
                 if (eq && (k < 2 || p + n == cell_s + cell_n)) idx[k] = i;
             }
             if (idx[k] < 0) shape = false;
-            else p += cfg.wl_len[idx[k]];
+            else p += cfg.wl_len[k][idx[k]];
         }
         if (!shape || ulen > 10) {
             raise(args.cnt, args.err_off, 0, kErrForeign, start);
         } else {
-            const uint32_t cell = (uint32_t)((idx[0] * cfg.n_wl + idx[1]) * cfg.n_wl + idx[2]);
+            const uint32_t cell = cell_of(cfg, idx[0], idx[1], idx[2]);
             uint64_t code = 0;
             bool regular = (int)ulen == cfg.umi_len;
             for (size_t j = 0; j < ulen; j++) {
@@ -373,10 +372,10 @@ __device__ __noinline__ uint64_t ann_record_generic(const Acc& a, const ScanArgs
 // ======================================================================================================
 
 // First-hit index of an 8-base window given its 2-bit code and the XOR-against-expected words (zero = all ACGT).
-__device__ __forceinline__ int match8(const DevCfg& cfg, const uint8_t* __restrict__ lut, uint32_t code, uint32_t d0, uint32_t d1)
+__device__ __forceinline__ int match8(const DevCfg& cfg, int round, const uint8_t* __restrict__ lut, uint32_t code, uint32_t d0, uint32_t d1)
 {
     if ((d0 | d1) == 0u) {
-        uint32_t v = __ldg(lut + (size_t)cfg.e * 65536u + code);
+        uint32_t v = __ldg(lut_of(cfg, lut, round, cfg.e) + code);
         return v == 0xFFu ? -1 : (int)v;
     }
     // some bytes are not A/C/G/T: they mismatch every whitelist base
@@ -387,7 +386,7 @@ __device__ __forceinline__ int match8(const DevCfg& cfg, const uint8_t* __restri
         // first i with dist over the 7 good positions <= e-1  ==  min over the 4 substitutions of LUT[e-1]
         const uint32_t bit = inv0 ? (uint32_t)__ffs((int)inv0) - 1u : 32u + (uint32_t)__ffs((int)inv1) - 1u;  // 7,15,...,63
         const uint32_t pos = bit >> 3;
-        const uint8_t* l = lut + (size_t)(cfg.e - 1) * 65536u;
+        const uint8_t* l = lut_of(cfg, lut, round, cfg.e - 1);
         const uint32_t base = code & ~(3u << (2u * pos));
         uint32_t best = 0xFFu;
 #pragma unroll
@@ -404,8 +403,8 @@ __device__ __forceinline__ int match8(const DevCfg& cfg, const uint8_t* __restri
         if (!((inv0 >> (8u * j + 7u)) & 1u)) valid |= 1u << (2u * j);
         if (!((inv1 >> (8u * j + 7u)) & 1u)) valid |= 1u << (2u * (j + 4u));
     }
-    for (int i = 0; i < cfg.n_wl; i++) {
-        uint32_t x = code ^ cfg.wl_code[i];
+    for (int i = 0; i < cfg.n_wl[round]; i++) {
+        uint32_t x = code ^ cfg.wl_code[round][i];
         if (k + __popc((x | (x >> 1)) & valid) <= cfg.e) return i;
     }
     return -1;
@@ -1002,7 +1001,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                                 load8(words, s0 + cell_s + 8u * k, x0, x1);
                                 const uint32_t code = pack4(x0, d0) | (pack4(x1, d1) << 8);
                                 if ((d0 | d1) == 0u) {
-                                    const uint32_t v = __ldg(args.lut + code);  // level 0: exact match
+                                    const uint32_t v = __ldg(lut_of(cfg, args.lut, k, 0) + code);  // level 0: exact match
                                     idx[k] = v == 0xFFu ? -1 : (int)v;
                                 }
                             }
@@ -1010,7 +1009,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                         if (idx[0] < 0 || idx[1] < 0 || idx[2] < 0 || ulen > 10u) {
                             err_code = kErrForeign;
                         } else {
-                            const uint32_t cell = (uint32_t)((idx[0] * cfg.n_wl + idx[1]) * cfg.n_wl + idx[2]);
+                            const uint32_t cell = cell_of(cfg, idx[0], idx[1], idx[2]);
                             const uint32_t up = s0 + umi_s;
                             const uint32_t i0 = up >> 2, sh = (up & 3u) * 8u;
                             const uint32_t w0 = words[i0], w1 = words[i0 + 1], w2 = words[i0 + 2], w3 = words[i0 + 3];
@@ -1051,17 +1050,17 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                     const uint32_t code2 = pack4(x0, db0) | (pack4(x1, db1) << 8);
                     load8(words, s1 + (uint32_t)cfg.b3s, x0, x1);
                     const uint32_t code3 = pack4(x0, dc0) | (pack4(x1, dc1) << 8);
-                    const uint8_t* lute = args.lut + (size_t)cfg.e * 65536u;
-                    const uint32_t v1 = __ldg(lute + code1), v2 = __ldg(lute + code2), v3 = __ldg(lute + code3);
+                    const uint32_t v1 = __ldg(lut_of(cfg, args.lut, 0, cfg.e) + code1), v2 = __ldg(lut_of(cfg, args.lut, 1, cfg.e) + code2),
+                                   v3 = __ldg(lut_of(cfg, args.lut, 2, cfg.e) + code3);
                     int i1 = v1 == 0xFFu ? -1 : (int)v1, i2 = v2 == 0xFFu ? -1 : (int)v2, i3 = v3 == 0xFFu ? -1 : (int)v3;
                     if ((da0 | da1 | db0 | db1 | dc0 | dc1) != 0u) {  // some window holds a byte that is not A/C/G/T
-                        if (da0 | da1) i1 = match8(cfg, args.lut, code1, da0, da1);
-                        if (db0 | db1) i2 = match8(cfg, args.lut, code2, db0, db1);
-                        if (dc0 | dc1) i3 = match8(cfg, args.lut, code3, dc0, dc1);
+                        if (da0 | da1) i1 = match8(cfg, 0, args.lut, code1, da0, da1);
+                        if (db0 | db1) i2 = match8(cfg, 1, args.lut, code2, db0, db1);
+                        if (dc0 | dc1) i3 = match8(cfg, 2, args.lut, code3, dc0, dc1);
                     }
                     matched = i1 >= 0 && i2 >= 0 && i3 >= 0;  // V2:310-321: all three lists non-empty (the mate check follows in commit())
                     if (matched) {
-                        const uint32_t cell = (uint32_t)((i1 * cfg.n_wl + i2) * cfg.n_wl + i3);
+                        const uint32_t cell = cell_of(cfg, i1, i2, i3);
                         // UMI = lineRead[umi_start:umi_end] verbatim (V2:295)
                         const uint32_t up = s1 + (uint32_t)cfg.us;
                         const uint32_t i0 = up >> 2, sh = (up & 3u) * 8u;

@@ -8,14 +8,15 @@ namespace ssd {
 // ---------------------------------------------------------------------------------------------
 // first-hit LUT: lut[e'][code] for e' = 0..e
 // ---------------------------------------------------------------------------------------------
-__global__ void k_build_lut(const __grid_constant__ DevCfg cfg, uint8_t* lut, int n_levels)
+// `round`: whose list; `lut`: that list's set of tables
+__global__ void k_build_lut(const __grid_constant__ DevCfg cfg, int round, uint8_t* lut, int n_levels)
 {
     uint32_t code = blockIdx.x * blockDim.x + threadIdx.x;
     if (code >= 65536u) return;
     for (int lev = 0; lev < n_levels; lev++) {
         uint32_t hit = 0xFFu;
-        for (int i = 0; i < cfg.n_wl; i++) {
-            uint32_t x = code ^ cfg.wl_code[i];
+        for (int i = 0; i < cfg.n_wl[round]; i++) {
+            uint32_t x = code ^ cfg.wl_code[round][i];
             if (__popc((x | (x >> 1)) & 0x5555u) <= lev) {
                 hit = (uint32_t)i;
                 break;
@@ -503,6 +504,82 @@ __global__ void k_undecided_header(IrrKey* out, const unsigned long long* cursor
 {
     out[0].hi = ~0ull;
     out[0].lo = *cursor;
+}
+
+// Shard phase of the multi-GPU file path: newlines per tile of 2^tile_log2 bytes of a loaded byte range.  One block
+// per tile, 16-byte loads (the range starts 16-byte aligned in its buffer), the last bytes one by one.
+__global__ void __launch_bounds__(256) k_count_newlines(const uint8_t* __restrict__ buf, uint64_t len, int tile_log2, uint32_t* __restrict__ counts)
+{
+    const uint64_t lo = (uint64_t)blockIdx.x << tile_log2;
+    const uint64_t hi = lo + (1ull << tile_log2) < len ? lo + (1ull << tile_log2) : len;
+    uint32_t n = 0;
+    const uint64_t full = (hi - lo) & ~15ull;
+    const uint4* v = reinterpret_cast<const uint4*>(buf + lo);
+    for (uint64_t i = threadIdx.x; i < full / 16; i += blockDim.x) {
+        const uint4 w = __ldcs(v + i);
+        const uint32_t x[4] = {w.x ^ 0x0A0A0A0Au, w.y ^ 0x0A0A0A0Au, w.z ^ 0x0A0A0A0Au, w.w ^ 0x0A0A0A0Au};
+#pragma unroll
+        for (int k = 0; k < 4; k++) n += (uint32_t)__popc(~(((x[k] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x[k] | 0x7F7F7F7Fu));  // exact zero-byte test
+    }
+    for (uint64_t i = lo + full + threadIdx.x; i < hi; i += blockDim.x) n += buf[i] == '\n';
+    n = __reduce_add_sync(0xFFFFFFFFu, n);
+    __shared__ uint32_t s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) counts[blockIdx.x] = s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7];
+}
+
+// Position learner on the device (V2:164-199): over the first n_lines lines of read 2, for every sequence line (line index
+// % 4 == 1) the position of the first occurrence of each of three static sequences in the strip()ped line (LIB:105 writes
+// the sample strip()ped; str.find), -1 when absent.  One block: warp 0 lists the line starts, then one thread per sequence
+// line searches.  found[k * cap + t]: anchor k in sequence line t; *n_seq = sequence lines seen.
+constexpr int kLearnMaxLines = 4096;
+__global__ void __launch_bounds__(256) k_anchor_positions(const uint8_t* __restrict__ text, unsigned long long len, uint32_t n_lines, const uint8_t* __restrict__ anchors,
+                                                          const int* __restrict__ anchor_len, int32_t* __restrict__ found, uint32_t cap, uint32_t* __restrict__ n_seq)
+{
+    __shared__ unsigned long long start[kLearnMaxLines + 1];  // start[i] = first byte of line i; start[n] = end of the last line + 1
+    __shared__ uint32_t s_lines;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        uint32_t n = 0;  // complete lines listed so far
+        if (lane == 0) start[0] = 0;
+        for (unsigned long long base = 0; base < len && n < n_lines; base += 32) {
+            const unsigned long long p = base + lane;
+            const uint32_t nl = __ballot_sync(0xFFFFFFFFu, p < len && text[p] == '\n');
+            if (lane == 0) {
+                uint32_t m = nl;
+                while (m && n < n_lines) {
+                    const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                    m &= m - 1u;
+                    start[++n] = base + b + 1;
+                }
+            }
+            n = __shfl_sync(0xFFFFFFFFu, n, 0);
+        }
+        if (lane == 0) {
+            if (n < n_lines && start[n] < len) start[++n] = len + 1;  // a last line without its newline still is a line
+            s_lines = n;
+        }
+    }
+    __syncthreads();
+    const uint32_t lines = s_lines, seq_lines = lines >= 2 ? (lines - 2) / 4 + 1 : 0;
+    if (threadIdx.x == 0) *n_seq = seq_lines;
+    for (uint32_t t = threadIdx.x; t < seq_lines && t < cap; t += blockDim.x) {
+        unsigned long long lo = start[4 * t + 1], hi = start[4 * t + 2] - 1;  // [lo, hi) without the newline
+        while (lo < hi && py_space(text[lo])) lo++;
+        while (hi > lo && py_space(text[hi - 1])) hi--;
+        for (int k = 0; k < 3; k++) {
+            const int al = anchor_len[k];
+            int32_t pos = -1;
+            for (unsigned long long p = lo; p + al <= hi && pos < 0; p++) {
+                bool eq = true;
+                for (int j = 0; j < al && eq; j++) eq = text[p + j] == anchors[k * 16 + j];
+                if (eq) pos = (int32_t)(p - lo);
+            }
+            if (al == 0) pos = 0;
+            found[(size_t)k * cap + t] = pos;
+        }
+    }
 }
 
 __global__ void k_iota(uint32_t* p, uint64_t n)

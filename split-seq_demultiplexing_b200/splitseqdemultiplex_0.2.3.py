@@ -75,19 +75,26 @@ def main(argv=None):
     say("Starting Step1: demultiplexing on the GPU.")
     if rank == 0 and not os.path.exists(args.outputDir):
         os.makedirs(args.outputDir)                                            # CLI3:48-49
-    whitelist = (hostlogic.load_whitelist_from(args.round1Barcodes, args.round2Barcodes, args.round3Barcodes) if args.useBarcodeFiles
-                 else hostlogic.load_whitelist("."))
+    whitelist2 = whitelist3 = None
+    if args.useBarcodeFiles:
+        # one list per round from the -1/-2/-3 files; rounds whose 8-mers equal Round 1's share its list (the bundled files)
+        whitelist, w2, w3 = hostlogic.load_whitelists_from(args.round1Barcodes, args.round2Barcodes, args.round3Barcodes)
+        whitelist2, whitelist3 = (None if w2 == whitelist else w2), (None if w3 == whitelist else w3)
+    else:
+        whitelist = hostlogic.load_whitelist(".")
     positions = dict(hostlogic.DEFAULT_POSITIONS)
     if args.positionDetection:                                                  # default True (CLI3:38, 63)
         say("Learning barcode positions to replace defaults...")
-        learned = hostlogic.learn_positions(hostlogic.learner_sample(args.fastqR))
+        # the three find()s per sequence line run on the GPU (ssd_anchor_positions); SSD_LEARNER=host: the host version
+        learned = (hostlogic.learn_positions(hostlogic.learner_sample(args.fastqR)) if os.environ.get("SSD_LEARNER") == "host"
+                   else hostlogic.learn_positions_device(args.fastqR, device=local if world > 1 else None))
         for line in hostlogic.positions_report(learned):
             say(line)
         learned.pop("_found")
         positions = learned
     collapse = 48 if str(args.collapseRandomHexamers).lower() == 'true' else 0
     dm = ssd_b200.Demultiplexer(whitelist, errors=int(args.errors), min_count=int(args.minReads), positions=positions,
-                                collapse_pairs=collapse, device=local if world > 1 else None)
+                                collapse_pairs=collapse, device=local if world > 1 else None, whitelist2=whitelist2, whitelist3=whitelist3)
     # file to file inside the library (pinned rings, overlapped copies; batches of whole records above SSD_BATCH_BYTES).
     # Without -p the reference still demultiplexes (and raises on a missing mate) but never writes the passing file.
     wanted = bool(args.performanceMetrics)                                      # CLI3:70 + V2:391

@@ -35,7 +35,10 @@ class Config(C.Structure):
                 ("umi_start", C.c_int32), ("umi_end", C.c_int32), ("bc1_start", C.c_int32), ("bc1_end", C.c_int32),
                 ("bc2_start", C.c_int32), ("bc2_end", C.c_int32), ("bc3_start", C.c_int32), ("bc3_end", C.c_int32),
                 ("errors", C.c_int32), ("min_count", C.c_int64), ("filter_mode", C.c_int32),
-                ("collapse_pairs", C.c_int32), ("record_bytes_hint", C.c_int32), ("reserved", C.c_int32)]
+                ("collapse_pairs", C.c_int32), ("record_bytes_hint", C.c_int32), ("reserved", C.c_int32),
+                ("n_whitelist2", C.c_int32), ("n_whitelist3", C.c_int32),
+                ("whitelist2", C.c_char_p), ("whitelist2_len", C.POINTER(C.c_uint8)),
+                ("whitelist3", C.c_char_p), ("whitelist3_len", C.POINTER(C.c_uint8))]
 
 
 class Stats(C.Structure):
@@ -117,6 +120,8 @@ _SIGS = {
     "ssd_distinct_local": (C.c_int, [C.c_void_p]),
     "ssd_cell_umi_table": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "ssd_anchor_positions": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "ssd_loaded_newlines": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "ssd_pack_decision": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "ssd_undecided_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "ssd_adopt_decision": (C.c_int, [C.c_void_p, C.c_void_p]),

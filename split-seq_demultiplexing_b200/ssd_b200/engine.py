@@ -44,7 +44,11 @@ class Demultiplexer:
 
     def __init__(self, whitelist: Sequence[str], errors: int = 1, min_count: int = 10,
                  positions: Optional[Dict[str, Tuple[int, int]]] = None, filter_mode: str = "distinct_umi",
-                 collapse_pairs: int = 0, device: Optional[int] = None, record_bytes_hint: int = 0):
+                 collapse_pairs: int = 0, device: Optional[int] = None, record_bytes_hint: int = 0,
+                 whitelist2: Optional[Sequence[str]] = None, whitelist3: Optional[Sequence[str]] = None):
+        """whitelist: matched against the Round1 window (bc1) -- and against the other two as well (V2:60, 302-304: the reference's
+        fast path has ONE list) unless whitelist2 / whitelist3 give the Round2 (bc2) / Round3 (bc3) windows their own lists
+        (extension)."""
         self.lib = L.load()
         pos = dict(DEFAULT_POSITIONS)
         if positions:
@@ -52,16 +56,29 @@ class Demultiplexer:
         for k, (a, b) in pos.items():
             if a < 0 or b < a:
                 raise ValueError("slice %s=%d:%d is outside the supported contract (0 <= start <= end)" % (k, a, b))
-        self.whitelist = [w if isinstance(w, str) else w.decode() for w in whitelist]
+        def as_list(ws):
+            return [w if isinstance(w, str) else w.decode() for w in ws]
+
+        def pack(ws):
+            return b"".join(w.encode().ljust(8, b"\0")[:8] for w in ws), (C.c_uint8 * len(ws))(*[min(len(w), 8) for w in ws])
+        self.whitelist = as_list(whitelist)
+        # the list of every round (rounds[k] is matched against window bc<k+1>); the same object when a round has no list of its own
+        self.rounds = [self.whitelist, as_list(whitelist2) if whitelist2 is not None else self.whitelist,
+                       as_list(whitelist3) if whitelist3 is not None else self.whitelist]
         self.positions = pos
-        raw = b"".join(w.encode().ljust(8, b"\0")[:8] for w in self.whitelist)
-        lens = (C.c_uint8 * len(self.whitelist))(*[min(len(w), 8) for w in self.whitelist])
+        raw, lens = pack(self.whitelist)
         cfg = L.Config()
         cfg.struct_size = C.sizeof(L.Config)
         cfg.device = -1 if device is None else int(device)
         cfg.n_whitelist = len(self.whitelist)
         cfg.whitelist = raw
         cfg.whitelist_len = lens
+        if whitelist2 is not None:
+            raw2, lens2 = pack(self.rounds[1])
+            cfg.n_whitelist2, cfg.whitelist2, cfg.whitelist2_len = len(self.rounds[1]), raw2, lens2
+        if whitelist3 is not None:
+            raw3, lens3 = pack(self.rounds[2])
+            cfg.n_whitelist3, cfg.whitelist3, cfg.whitelist3_len = len(self.rounds[2]), raw3, lens3
         cfg.umi_start, cfg.umi_end = pos["umi"]
         cfg.bc1_start, cfg.bc1_end = pos["bc1"]
         cfg.bc2_start, cfg.bc2_end = pos["bc2"]
@@ -105,9 +122,14 @@ class Demultiplexer:
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.ssd_set_stream(self._ctx, C.c_void_p(cuda_stream)))
 
+    def cell_indices(self, cell: int) -> Tuple[int, int, int]:
+        """(i1, i2, i3) of a cell id = (i1 * n2 + i2) * n3 + i3."""
+        n2, n3 = len(self.rounds[1]), len(self.rounds[2])
+        return cell // (n2 * n3), (cell // n3) % n2, cell % n3
+
     def cell_string(self, cell: int) -> str:
-        n = len(self.whitelist)
-        return self.whitelist[cell // (n * n)] + self.whitelist[(cell // n) % n] + self.whitelist[cell % n]
+        i1, i2, i3 = self.cell_indices(cell)
+        return self.rounds[0][i1] + self.rounds[1][i2] + self.rounds[2][i3]
 
     # -- phases on device-resident inputs ---------------------------------------------------------
     def demux_device(self, r1_ptr: int, r1_len: int, r2_ptr: int, r2_len: int, keep=()):
@@ -249,11 +271,11 @@ class Demultiplexer:
         host = out[:n].cpu().numpy()
         del out
         os.makedirs(out_dir, exist_ok=True)
-        nw, written = len(self.whitelist), []
+        written = []
         for (_, off, _, nbytes), cid in zip(table, self._split_ids):
-            i1, i2, i3 = cid // (nw * nw), (cid // nw) % nw, cid % nw
+            i1, i2, i3 = self.cell_indices(cid)
             name = (hostlogic.split_file_name(round_names, i1, i2, i3) if round_names is not None
-                    else "%s-%s-%s.fastq" % (self.whitelist[i1], self.whitelist[i2], self.whitelist[i3]))
+                    else "%s-%s-%s.fastq" % (self.rounds[0][i1], self.rounds[1][i2], self.rounds[2][i3]))
             with open(os.path.join(out_dir, name), "ab") as fh:
                 fh.write(host[off:off + nbytes].tobytes())
             written.append((name, nbytes))
@@ -419,7 +441,7 @@ class Demultiplexer:
             keep = ok[cells]
             cells, umis, reads = cells[keep], umis[keep], reads[keep]
         with open(path, "wb") as fh:
-            fh.write(hostlogic.format_cell_umi_table(self.whitelist, cells, umis, reads))
+            fh.write(hostlogic.format_cell_umi_table(self.rounds, cells, umis, reads))
         return int(cells.size)
 
     def cell_table(self) -> Dict[str, Tuple[int, int]]:

@@ -151,6 +151,86 @@ def plan_shards(path_r1: str, path_r2: str, world: int, target_bytes: Optional[i
     return [batches[lo:hi] for lo, hi in deal_evenly(len(batches), world)]
 
 
+TILE_LOG2 = 20  # the shard phase counts newlines per MiB
+
+
+def device_tile_counts(dm, slot: int):
+    """count(path, offset, length) -> uint32 numpy array: newlines per 2^TILE_LOG2-byte tile of that byte range, counted on the
+    device: the range is loaded into the context's input buffer `slot` (pinned rings, H2D) and ssd_loaded_newlines counts it."""
+    import numpy as np
+
+    def count(path: str, offset: int, length: int):
+        if length <= 0:
+            return np.zeros(0, dtype=np.uint32)
+        dm._check(dm.lib.ssd_load_file_range(dm._ctx, slot, os.fsencode(path), int(offset), int(length)))
+        tiles = (length + (1 << TILE_LOG2) - 1) >> TILE_LOG2
+        out = np.zeros(tiles, dtype=np.uint32)
+        n = C.c_uint64()
+        dm._check(dm.lib.ssd_loaded_newlines(dm._ctx, slot, TILE_LOG2, out.ctypes.data_as(C.c_void_p), tiles, C.byref(n)))
+        return out[: n.value]
+    return count
+
+
+def _nth_newline_end(path: str, offset: int, length: int, tile_counts, j: int) -> int:
+    """File offset just behind the j-th (1-based) newline of the byte range [offset, offset + length), given the range's
+    per-tile newline counts: the tile comes from their prefix sums, the position inside it from the tile's bytes."""
+    import numpy as np
+    pre = np.cumsum(tile_counts, dtype=np.int64)
+    t = int(np.searchsorted(pre, j, side="left"))
+    before = int(pre[t - 1]) if t else 0
+    lo = offset + (t << TILE_LOG2)
+    with open(path, "rb") as fh:
+        fh.seek(lo)
+        buf = np.frombuffer(fh.read(min(1 << TILE_LOG2, offset + length - lo)), dtype=np.uint8)
+    return lo + int(np.flatnonzero(buf == 10)[j - before - 1]) + 1
+
+
+def plan_shards_device(path_r1: str, path_r2: str, world: int, rank: int, count1, count2, allgather, target_bytes: Optional[int] = None):
+    """The batch plan of run_files_sharded WITHOUT anybody reading a whole file ("shard phase"; the reference
+    aligns its chunks by counting lines, LIB:6-97): both files are cut into world x k byte ranges of equal size, every rank
+    counts the newlines of ITS ranges (count1 / count2: device_tile_counts), the per-range totals of all ranks are gathered
+    (allgather: list of int64 per rank -> the lists of all ranks), and line indices follow by prefix sums.  The v-th batch starts
+    at the first record that begins behind read 1's v-th byte cut, record r being line 4 r of BOTH files; whoever holds the
+    range containing that line in a file reports the byte offset (all ranks learn all offsets in a second gather).  No '@'
+    heuristics, like ssd_fastq_record_cuts.  Returns the same structure as plan_shards: one list of (offset 1, length 1,
+    offset 2, length 2) per rank."""
+    import numpy as np
+    s1, s2 = os.path.getsize(path_r1), os.path.getsize(path_r2)
+    limit = batch_bytes() if target_bytes is None else max(1, int(target_bytes))
+    per_rank = max(1, -(-max(s1, s2, 1) // (world * limit)))
+    v_all = world * per_rank
+    cut1 = [v * s1 // v_all for v in range(v_all + 1)]
+    cut2 = [v * s2 // v_all for v in range(v_all + 1)]
+    mine = range(rank * per_rank, (rank + 1) * per_rank)
+    tiles1 = {v: count1(path_r1, cut1[v], cut1[v + 1] - cut1[v]) for v in mine}
+    tiles2 = {v: count2(path_r2, cut2[v], cut2[v + 1] - cut2[v]) for v in mine}
+    totals = allgather([int(tiles1[v].sum()) for v in mine] + [int(tiles2[v].sum()) for v in mine])
+    n1 = np.array([t for part in totals for t in part[:per_rank]], dtype=np.int64)
+    n2 = np.array([t for part in totals for t in part[per_rank:]], dtype=np.int64)
+    before1, before2 = np.concatenate([[0], np.cumsum(n1)]), np.concatenate([[0], np.cumsum(n2)])  # newlines before each byte cut
+    # batch v starts at record r_v = the first record whose first line begins behind byte cut v of read 1: line 4 r_v, which
+    # begins right behind newline number 4 r_v (counted from 1) of either file; past the last such newline: the end of the file
+    found = []
+    for v in range(1, v_all):
+        target = 4 * (int(before1[v]) // 4 + 1)
+        for which, (before, cut, tiles, path) in enumerate(((before1, cut1, tiles1, path_r1), (before2, cut2, tiles2, path_r2))):
+            u = int(np.searchsorted(before, target, side="left")) - 1  # the range holding newline number `target`
+            if 0 <= u < v_all and u in tiles:
+                found.append((v, which, _nth_newline_end(path, cut[u], cut[u + 1] - cut[u], tiles[u], target - int(before[u]))))
+    off = np.full((2, v_all + 1), -1, dtype=np.int64)
+    off[:, 0] = 0
+    for part in allgather([x for f in found for x in f]):
+        for k in range(0, len(part), 3):
+            off[part[k + 1], part[k]] = part[k + 2]
+    off[0, v_all], off[1, v_all] = s1, s2
+    for which, size in ((0, s1), (1, s2)):  # a record past the end of a file: nothing left of that file from there on
+        for v in range(1, v_all):
+            if off[which, v] < 0:
+                off[which, v] = size
+    batches = [(int(off[0, v]), int(off[0, v + 1] - off[0, v]), int(off[1, v]), int(off[1, v + 1] - off[1, v])) for v in range(v_all)]
+    return [batches[r * per_rank: (r + 1) * per_rank] for r in range(world)]
+
+
 def run_files_sharded(dm, path_r1: str, path_r2: str, out_path: str, which: int = L.EMIT_PASSING, append: bool = True,
                       world: int = 1, group=None, target_bytes: Optional[int] = None):
     """One pair of files, N ranks (one process per GPU, torch.distributed initialised): the reference's fan-out over chunk
@@ -169,14 +249,26 @@ def run_files_sharded(dm, path_r1: str, path_r2: str, out_path: str, which: int 
     box = [None]
     if rank == 0:
         try:
-            box[0] = plan_shards(path_r1, path_r2, world, target_bytes)
+            for p in (path_r1, path_r2):
+                os.path.getsize(p)  # FileNotFoundError like the reference's open()
             _truncate(out_path, append)
         except OSError as e:  # every rank raises what rank 0 met
             box[0] = e
     dist.broadcast_object_list(box, src=0, group=group)
     if isinstance(box[0], Exception):
         raise box[0]
-    plan = box[0]
+    if os.environ.get("SSD_SHARD_PLAN", "device") == "host":
+        # the first version: rank 0 reads both files through and cuts them (ssd_fastq_record_cuts)
+        if rank == 0:
+            box[0] = plan_shards(path_r1, path_r2, world, target_bytes)
+        dist.broadcast_object_list(box, src=0, group=group)
+        plan = box[0]
+    else:
+        def allgather(values):
+            parts = [None] * world
+            dist.all_gather_object(parts, [int(x) for x in values], group=group)
+            return parts
+        plan = plan_shards_device(path_r1, path_r2, world, rank, device_tile_counts(dm, 0), device_tile_counts(dm, 1), allgather, target_bytes)
     mine, rounds = plan[rank], max(len(p) for p in plan)
     part = "%s.part%d" % (out_path, rank)
     open(part, "wb").close()

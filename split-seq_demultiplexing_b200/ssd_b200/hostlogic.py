@@ -6,7 +6,7 @@ from __future__ import annotations
 import itertools
 import os
 from collections import Counter
-from typing import Dict, Iterable, List, Tuple
+from typing import Sequence, Optional, Dict, Iterable, List, Tuple
 
 ROUND1_FILE = "Round1_barcodes_new5.txt"   # V2:56  (opened relative to the CWD, like the reference)
 ROUND2_FILE = "Round2_barcodes_new4.txt"   # V2:62
@@ -28,17 +28,25 @@ def load_whitelist(directory: str = ".") -> List[str]:
     return wl
 
 
-def load_whitelist_from(round1: str, round2: str, round3: str) -> List[str]:
-    """Opt-in extension: take the whitelist from the files given with -1/-2/-3 instead of the fixed names in
-    the CWD.  Round 1 carries its 8-mer at [8:16] (V2:58), Rounds 2 and 3 at [0:8]; the fast path matches all three rounds
-    against ONE list (V2:302-304), so the three files must spell the same 8-mers in the same order, as the bundled ones do."""
-    with open(round1, "r") as fh:
-        wl = [line.rstrip()[8:16] for line in fh if line.strip()]
-    for path in (round2, round3):
+def load_whitelists_from(round1: str, round2: str, round3: str) -> Tuple[List[str], List[str], List[str]]:
+    """Opt-in extension: take the whitelists from the files given with -1/-2/-3 instead of the fixed names in
+    the CWD, one list per round.  Round 1 carries its 8-mer at [8:16] (V2:58), Rounds 2 and 3 at [0:8] (the bundled 13- and
+    14-mers start with it).  The reference's fast path matches all three rounds against the Round-1 list (V2:60, 302-304);
+    with the bundled files the three lists are equal, so this gives the reference's result -- and with files that differ,
+    every window is matched against the list of its own round (Demultiplexer(whitelist, whitelist2=, whitelist3=))."""
+    out = []
+    for path, lo, hi in ((round1, 8, 16), (round2, 0, 8), (round3, 0, 8)):
         with open(path, "r") as fh:
-            other = [line.rstrip()[0:8] for line in fh if line.strip()]
-        if other != wl:
-            raise ValueError("%s does not carry the 8-mers of %s: per-round whitelists are not supported by the fast path" % (path, round1))
+            out.append([line.rstrip()[lo:hi] for line in fh if line.strip()])
+    return out[0], out[1], out[2]
+
+
+def load_whitelist_from(round1: str, round2: str, round3: str) -> List[str]:
+    """The one list of the reference's fast path from the -1/-2/-3 files; ValueError when the files disagree (use
+    load_whitelists_from and per-round lists then)."""
+    wl, w2, w3 = load_whitelists_from(round1, round2, round3)
+    if w2 != wl or w3 != wl:
+        raise ValueError("the Round 2 / Round 3 files do not carry the 8-mers of %s" % round1)
     return wl
 
 
@@ -75,6 +83,12 @@ def learn_positions(lines: Iterable[str]) -> Dict[str, Tuple[int, int]]:
                 p = line.find(anchor)
                 if p >= 17:
                     found[k].append(p)
+    return positions_from_found(found)
+
+
+def positions_from_found(found: Sequence[Sequence[int]]) -> Dict[str, Tuple[int, int]]:
+    """The second half of V2:164-199: found[k] = the find() positions >= 17 of static sequence k, in line order; the mode of
+    each list (first maximum in set iteration order, exactly what max(set(l), key=l.count) returns) gives the four slices."""
     modes = []
     for lst in found:
         if not lst:
@@ -88,6 +102,35 @@ def learn_positions(lines: Iterable[str]) -> Dict[str, Tuple[int, int]]:
     p1, p2, p3 = modes
     return {"umi": (p3 - 18, p3 - 8), "bc3": (p3 - 8, p3), "bc2": (p2 - 8, p2), "bc1": (p1 + 6, p1 + 14),
             "_found": (p1, p2, p3)}
+
+
+def learn_positions_device(fastq_r: str, n_lines: int = 1001, device: Optional[int] = None) -> Dict[str, Tuple[int, int]]:
+    """learn_positions with the searching done on the GPU (ssd_anchor_positions): the head of the file goes to the device, one
+    thread per sequence line runs the three find()s, the host takes the modes.  Same result as learner_sample +
+    learn_positions on files whose lines end in "\\n" or "\\r\\n" (the library's input contract)."""
+    import ctypes as C
+    import torch
+    from . import _lib as L
+    lib = L.load()
+    size = os.path.getsize(fastq_r)
+    want = min(size, 1 << 20)
+    while True:  # enough of the file to hold n_lines lines
+        with open(fastq_r, "rb") as fh:
+            head = fh.read(want)
+        if head.count(b"\n") >= n_lines or want >= size:
+            break
+        want = min(size, want * 4)
+    if device is not None:
+        torch.cuda.set_device(device)
+    d = torch.frombuffer(bytearray(head), dtype=torch.uint8).cuda() if head else torch.empty(0, dtype=torch.uint8, device="cuda")
+    cap = n_lines // 4 + 1
+    found = (C.c_int32 * (3 * cap))()
+    n_seq = C.c_uint32()
+    anchors = (C.c_char_p * 3)(*[a.encode() for a in ANCHORS])
+    rc = lib.ssd_anchor_positions(C.c_void_p(d.data_ptr() if d.numel() else 0), d.numel(), n_lines, anchors, found, cap, C.byref(n_seq))
+    if rc != L.OK:
+        raise RuntimeError("ssd_anchor_positions failed (%d)" % rc)
+    return positions_from_found([[p for p in found[k * cap: k * cap + n_seq.value] if p >= 17] for k in range(3)])
 
 
 def positions_report(pos: Dict[str, Tuple[int, int]]) -> List[str]:
@@ -128,12 +171,13 @@ def format_cell_table(table: Dict[str, Tuple[int, int]], threshold: int) -> str:
 
 def format_cell_umi_table(whitelist, cells, umis, reads) -> bytes:
     """The per-cell x UMI table as tab-separated text: `cell <tab> UMI <tab> reads` with the 24-base cell id spelled from the
-    whitelist (cell = (i1 * n + i2) * n + i3, printed bc1 bc2 bc3 like V2:139).  numpy arrays in, bytes out; vectorised, so
-    that tens of millions of rows take seconds."""
+    whitelist (cell = (i1 * n2 + i2) * n3 + i3, printed bc1 bc2 bc3 like V2:139).  whitelist: one list of strings, or the
+    three lists of the rounds.  numpy arrays in, bytes out; vectorised, so that tens of millions of rows take seconds."""
     import numpy as np
-    n = len(whitelist)
-    wl = np.array([w.encode() for w in whitelist], dtype="S8")
+    rounds = [whitelist] * 3 if isinstance(whitelist[0], str) else list(whitelist)
+    wl = [np.array([w.encode() for w in r], dtype="S8") for r in rounds]
+    n2, n3 = len(rounds[1]), len(rounds[2])
     cells = np.asarray(cells, dtype=np.int64)
-    ids = np.char.add(np.char.add(wl[cells // (n * n)], wl[(cells // n) % n]), wl[cells % n])
+    ids = np.char.add(np.char.add(wl[0][cells // (n2 * n3)], wl[1][(cells // n3) % n2]), wl[2][cells % n3])
     rows = np.char.add(np.char.add(np.char.add(np.char.add(ids, b"\t"), np.asarray(umis)), b"\t"), np.asarray(reads).astype("S10"))
     return b"cell\tumi\treads\n" + b"".join(r + b"\n" for r in rows.tolist())

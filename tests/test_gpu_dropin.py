@@ -278,3 +278,42 @@ def test_cli_split_version_writes_one_file_per_cell(workdir, digests):
         assert f == r1[c[0:8]] + "-" + r2[c[8:16]] + "-" + r3[c[16:24]] + ".fastq"
         everything.append(open(os.path.join("cells", f), "rb").read())
     assert fu.canonical_sha(b"".join(everything)) == gold["passing_sha"]
+
+
+@pytest.mark.parametrize("variant", ["bundled", "shift3", "shift11", "crlf", "short", "no_final_newline", "leading_blanks"])
+def test_device_learner_equals_host_learner(tmp_path, variant):
+    """ssd_anchor_positions (find() of the three static sequences per sequence line, on the device) + the mode on the host
+    give what the reference's learner gives (V2:164-199, golden learner_cases.json go through the same host half)."""
+    from ssd_b200 import hostlogic
+    r2 = fu.load_bundled()[1]
+    if variant.startswith("shift"):
+        k = int(variant[5:])
+        seq = "T" * k + "ACGTACGTAC" + WL[3] + fu.LINKER_3_2 + WL[7] + fu.LINKER_2_1 + WL[50] + "ACGT" * 10
+        r2 = "".join("@l%d %d/2\n%s\n+\n%s\n" % (i, i, seq, "A" * len(seq)) for i in range(300)).encode()
+    if variant == "crlf":
+        r2 = r2.replace(b"\n", b"\r\n")
+    if variant == "short":
+        r2 = b"\n".join(r2.split(b"\n")[:4 * 30]) + b"\n"       # fewer lines than the sample asks for
+    if variant == "no_final_newline":
+        r2 = b"\n".join(r2.split(b"\n")[:4 * 7 + 2])            # ends inside a record, on a sequence line without newline
+    if variant == "leading_blanks":
+        lines = r2.split(b"\n")
+        lines[1::4] = [b"  " + x + b" " for x in lines[1::4]]     # strip() removes them before find()
+        r2 = b"\n".join(lines)
+    p = tmp_path / "r2.fastq"
+    p.write_bytes(r2)
+    want = hostlogic.learn_positions(hostlogic.learner_sample(str(p)))
+    assert hostlogic.learn_positions_device(str(p)) == want
+    if variant == "bundled":
+        assert want["_found"] == (80, 56, 18)
+
+
+def test_device_learner_empty_raises_value_error(tmp_path):
+    from ssd_b200 import hostlogic
+    p = tmp_path / "r2.fastq"
+    p.write_bytes(b"@a\nACGT\n+\nEEEE\n")
+    with pytest.raises(ValueError):
+        hostlogic.learn_positions_device(str(p))
+    p.write_bytes(b"")
+    with pytest.raises(ValueError):
+        hostlogic.learn_positions_device(str(p))

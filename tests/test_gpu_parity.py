@@ -133,6 +133,91 @@ def test_synthetic_vs_oracle(ssd, orc, e, m, kw):
     assert dm.cell_table() == want
 
 
+# ---- per-round whitelists (extension) -----------------------------------------------------------------------
+def _first_hit(window: bytes, entries, e: int) -> int:
+    """V2:72-73 + 302-304 restated in three lines (a second opinion next to the C oracle): zip-truncated Hamming distance,
+    first entry in list order within e."""
+    for i, w in enumerate(entries):
+        if sum(a != b for a, b in zip(w.encode(), window)) <= e:
+            return i
+    return -1
+
+
+PER_ROUND = (WL, WL[::-1][:50], WL[10:] + ["ACGTACGT", "TTTTTTTT"])  # three different lists of three different sizes
+
+
+@pytest.mark.parametrize("e", [0, 1, 2])
+def test_per_round_lists_vs_oracle(ssd, orc, e):
+    """Every window against the list of its own round: record-for-record cell ids, both outputs, per-cell table and the
+    cell x UMI table equal the oracle's; the cell ids also equal a three-line Python restatement of the first-hit rule."""
+    l1, l2, l3 = PER_ROUND
+    r1, r2 = ssd.synth_host(ssd.synth_spec(WL, 20000, seed=0x3117 + e, cell_pool=1500, p_n=0.01, p_trunc=0.01, p_sub=0.03))
+    dm = ssd.Demultiplexer(l1, errors=e, min_count=3, whitelist2=l2, whitelist3=l3)
+    assert dm.n_cells_total == len(l1) * len(l2) * len(l3)
+    passing, stats = dm.run_host(r1, r2, ssd.EMIT_PASSING)
+    ref = orc.demultiplex(r1, r2, l1, e, 3, whitelist2=l2, whitelist3=l3)
+    got_cells = dm.record_cells().tolist()
+    assert got_cells == ref.rec_cell
+    assert passing.tobytes() == ref.passing
+    assert (stats["n_matched"], stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]) == (
+        ref.n_matched, ref.n_cells, ref.n_passing_cells, ref.n_retained)
+    assert 0 < ref.n_matched < 20000 and ref.n_passing_cells > 0
+    assert dm.cell_table() == {c.decode(): (v[0], v[1]) for c, v in ref.cells.items()}
+    cells, umis, reads = dm.cell_umi_table()
+    got = {(dm.cell_string(int(c)).encode(), u): int(n) for c, u, n in zip(cells.tolist(), umis.tolist(), reads.tolist())}
+    assert got == dict(_cell_umi_rows_from_text(ref.merged1))
+    # second opinion on the first 3000 records
+    seqs = r2.split(b"\n")[1::4]
+    for k in range(3000):
+        s = seqs[k].rstrip()
+        i1, i2, i3 = _first_hit(s[86:94], l1, e), _first_hit(s[48:56], l2, e), _first_hit(s[10:18], l3, e)
+        want = -1 if min(i1, i2, i3) < 0 else (i1 * len(l2) + i2) * len(l3) + i3
+        assert got_cells[k] == want, k
+
+
+def test_three_equal_lists_are_the_one_list(ssd, bundled, digests):
+    """The reference's configuration spelled as three lists gives the reference's bytes (golden digest of V2 on the bundled
+    files), through the device tables shared between the rounds."""
+    dm = ssd.Demultiplexer(WL, errors=1, min_count=10, whitelist2=list(WL), whitelist3=list(WL))
+    passing, stats = dm.run_host(bundled[0], bundled[1], ssd.EMIT_PASSING)
+    assert fu.canonical_sha(passing.tobytes()) == digests["e1_m10"]["passing_sha"]
+    assert (stats["n_matched"], stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]) == (3541, 430, 83, 2780)
+
+
+def test_per_round_lists_annotated_split_and_collapse(ssd, orc):
+    """The other consumers of the cell id under per-round lists: the annotated-text filter (V2:389-454) parses cells back with
+    the list of each round, split mode buckets by cell, the collapse map folds Round-1 index 48 + k into k."""
+    l1, l2, l3 = PER_ROUND
+    r1, r2 = ssd.synth_host(ssd.synth_spec(WL, 15000, seed=0x3120, cell_pool=600, p_n=0.01))
+    ref = orc.demultiplex(r1, r2, l1, 1, 4, whitelist2=l2, whitelist3=l3)
+    dm = ssd.Demultiplexer(l1, errors=1, min_count=4, whitelist2=l2, whitelist3=l3)
+    out, st = dm.filter_annotated_host(ref.merged1)
+    assert out.tobytes() == ref.passing and st["n_passing_cells"] == ref.n_passing_cells
+    # split mode: the buckets partition the merged output, one cell each
+    import torch
+    dm.run_host(r1, r2, ssd.EMIT_PASSING)
+    buf = torch.empty(len(ref.passing) + 64, dtype=torch.uint8, device="cuda")
+    n, table, _ = dm.emit_split_device(buf.data_ptr(), buf.numel())
+    text = buf[:n].cpu().numpy().tobytes()
+    assert fu.canonical_sha(text) == fu.canonical_sha(ref.passing)
+    for (_, off, _, nbytes), cid in zip(table, dm._split_ids):
+        heads = text[off:off + nbytes].split(b"\n")[0::4]
+        assert all(h.split(b"_")[1] == dm.cell_string(cid).encode() for h in heads if h)
+    # collapse on: cells (48 + k, i2, i3) fold into (k, i2, i3) when both pass
+    dmc = ssd.Demultiplexer(l1, errors=1, min_count=4, whitelist2=l2, whitelist3=l3, collapse_pairs=48)
+    outc, stc = dmc.run_host(r1, r2, ssd.EMIT_PASSING)
+    passing = {c for c, v in ref.cells.items() if v[1] >= 4}
+    want = []
+    recs = ref.passing.split(b"\n")
+    for k in range(0, len(recs) - 1, 4):
+        idp, cell, umi = recs[k].split(b"_")
+        i1 = l1.index(cell[:8].decode())
+        if i1 >= 48 and (l1[i1 - 48].encode() + cell[8:]) in passing:
+            cell = l1[i1 - 48].encode() + cell[8:]
+        want += [idp + b"_" + cell + b"_" + umi] + recs[k + 1:k + 4]
+    assert outc.tobytes() == b"\n".join(want) + b"\n"
+
+
 def _cell_umi_rows_from_text(merged: bytes, passing_cells=None):
     """(cell, UMI) -> reads, from the headers `@id_CELL_UMI` of an annotated FASTQ text (what V2:395-398 parses back)."""
     from collections import Counter

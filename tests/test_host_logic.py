@@ -228,8 +228,10 @@ def test_whitelist_from_the_given_files(ssd, tmp_path):
     assert hostlogic.load_whitelist_from(*paths) == hostlogic.load_whitelist(str(tmp_path)) == WL
     other = tmp_path / "r3_other.txt"
     other.write_text("".join("ACGTACGTGTGGCC\n" for _ in WL))
-    with pytest.raises(ValueError, match="per-round"):
+    with pytest.raises(ValueError, match="do not carry"):
         hostlogic.load_whitelist_from(paths[0], paths[1], str(other))
+    w1, w2, w3 = hostlogic.load_whitelists_from(paths[0], paths[1], str(other))   # one list per round
+    assert w1 == w2 == WL and w3 == ["ACGTACGT"] * len(WL)
 
 
 def test_record_cuts_error_codes(ssd, tmp_path):
@@ -399,3 +401,82 @@ def test_format_cell_umi_table():
                     b"AAAAAAAACCCCCCCCGGGGGGGG\tANNTACGTAC\t12\n"
                     b"GGGGGGGGGGGGGGGGGGGGGGGG\tACGTA\t1234567\n")
     assert hostlogic.format_cell_umi_table(wl, cells[:0], umis[:0], reads[:0]) == b"cell\tumi\treads\n"
+
+
+def _numpy_tile_counts(path, offset, length):
+    """CPU stand-in for filebatch.device_tile_counts (the library counts on the GPU): newlines per tile of a byte range."""
+    import numpy as np
+    from ssd_b200 import filebatch
+    with open(path, "rb") as fh:
+        fh.seek(offset)
+        buf = np.frombuffer(fh.read(length), dtype=np.uint8)
+    t = 1 << filebatch.TILE_LOG2
+    return np.array([int((buf[k:k + t] == 10).sum()) for k in range(0, len(buf), t)], dtype=np.uint32)
+
+
+def _plan_on_threads(paths, world, target_bytes=None):
+    """plan_shards_device on `world` threads standing in for the ranks (the all-gather is a barrier over a shared list)."""
+    import threading
+    from ssd_b200 import filebatch
+    barrier, slots, plans, errors = threading.Barrier(world), [None] * world, [None] * world, []
+
+    def run(rank):
+        def allgather(values):
+            slots[rank] = list(values)
+            barrier.wait()
+            out = [list(x) for x in slots]
+            barrier.wait()
+            return out
+        try:
+            plans[rank] = filebatch.plan_shards_device(paths[0], paths[1], world, rank, _numpy_tile_counts, _numpy_tile_counts, allgather, target_bytes)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            barrier.abort()
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    assert all(p == plans[0] for p in plans)  # every rank derives the same plan
+    return plans[0]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("ending", ["lf", "crlf", "no_final_newline", "surplus_r2"])
+def test_plan_shards_device_cuts_both_files_at_the_same_records(tmp_path, monkeypatch, world, ending):
+    """The shard phase without a whole-file pass: every rank counts the newlines of its byte ranges, line indices follow from
+    the gathered totals, batches start at the same RECORD in both files (whose records differ in size)."""
+    from ssd_b200 import filebatch
+    monkeypatch.setattr(filebatch, "TILE_LOG2", 12)  # several tiles per range on these small files
+    r1, r2 = fu.load_bundled()
+    if ending == "crlf":
+        r1, r2 = r1.replace(b"\n", b"\r\n"), r2.replace(b"\n", b"\r\n")
+    if ending == "no_final_newline":
+        r1, r2 = r1[:-1], r2[:-1]
+    if ending == "surplus_r2":
+        r1 = b"\n".join(r1.split(b"\n")[:4 * 4000]) + b"\n"
+    p1, p2 = tmp_path / "a.fastq", tmp_path / "b.fastq"
+    p1.write_bytes(r1)
+    p2.write_bytes(r2)
+    starts1 = [0] + [i + 1 for i, c in enumerate(r1) if c == 10]
+    starts2 = [0] + [i + 1 for i, c in enumerate(r2) if c == 10]
+    for target in (None, 70000):
+        plan = _plan_on_threads((str(p1), str(p2)), world, target)
+        assert len(plan) == world and len({len(x) for x in plan}) == 1      # the same number of batches on every rank
+        flat = [b for per_rank in plan for b in per_rank]
+        assert flat[0][0] == 0 and flat[0][2] == 0
+        assert all(a[0] + a[1] == b[0] and a[2] + a[3] == b[2] for a, b in zip(flat, flat[1:]))
+        assert flat[-1][0] + flat[-1][1] == len(r1) and flat[-1][2] + flat[-1][3] == len(r2)
+        for o1, _, o2, _ in flat[1:]:
+            if o1 < len(r1):
+                k = starts1.index(o1)                                            # a line start ...
+                assert k % 4 == 0                                                # ... of a record ...
+                assert o2 == (starts2[k] if k < len(starts2) else len(r2))       # ... and the same record of the mate file
+            else:
+                assert o2 == len(r2) or ending == "surplus_r2"
+        if target:
+            assert len(flat) > world and all(n1 <= 2 * target for _, n1, _, _ in flat)
+        if world > 1 and ending == "lf" and target is None:
+            sizes = [n1 for _, n1, _, _ in flat]
+            assert max(sizes) - min(sizes) < 2000                                # equal byte ranges, moved by less than a record or two
