@@ -49,6 +49,18 @@ extern "C" {
 #define SSD_EMIT_MATCHED 0 /* MergedCells_1.fastq      (V2:367-370)  every barcode-matched pair  */
 #define SSD_EMIT_PASSING 1 /* MergedCells_passing.fastq (V2:415-454)  pairs of cells passing -m   */
 
+/* Header line of an output record (read 1's name annotated with cell and UMI):
+ *   SSD_HEADER_FAST     name.split("/")[0].replace(" ", "").strip() + "_" + cell + "_" + umi                 (V2:134-141)
+ *   SSD_HEADER_EXTRACT  name.split()[0] + "_" + cell + "_" + umi + " " + name.split()[1]     (Extract_BC_UMI.py:78-85, what
+ *                       users of the legacy `-v merged` pipeline feed to their aligner: the read id stays a token of its
+ *                       own and the rest of the name survives as the comment; a name of one token is an IndexError there
+ *                       and SSD_EINDEX here).  An extension of the fast path: every record then goes through the exact
+ *                       record-by-record code of the scan and the writer (several times slower than the default), and the
+ *                       text is for downstream tools, not for V2.calc_demux_results (ssd_annotated_*), whose split("_")
+ *                       would take the comment for a part of the UMI. */
+#define SSD_HEADER_FAST 0
+#define SSD_HEADER_EXTRACT 1
+
 #define SSD_MAX_WHITELIST 128
 #define SSD_BARCODE_LEN 8
 
@@ -73,12 +85,12 @@ typedef struct ssd_config {
     int32_t collapse_pairs;   /* 0 = off; k = whitelist[k+i] (RanHex) folds into whitelist[i] (OligoDT)
                                  for i < k when both cells survive the filter (Collapse_RanHex_Odt.py:44-71) */
     int32_t record_bytes_hint;/* lower bound on bytes per FASTQ record used to size tables; 0 = 24     */
-    int32_t reserved;
+    int32_t header_style;     /* SSD_HEADER_*; 0 = the fast path's header (this field was `reserved`)  */
     /* Per-round whitelists (extension beyond the reference's fast path; the bash pipeline reads one file per
      * round, demultiplex_using_barcodes.py:350-372).  `whitelist` is matched against the Round1 window (bc1), whitelist2
      * against the Round2 window (bc2), whitelist3 against the Round3 window (bc3); NULL = `whitelist` serves that round
      * too.  Cell id = (i1 * n2 + i2) * n3 + i3, written bc1 bc2 bc3 (V2:139).  collapse_pairs refers to the round-1 list.
-     * A caller compiled against the first layout (struct_size up to `reserved`) gets one list. */
+     * A caller compiled against the first layout (struct_size up to `header_style`) gets one list. */
     int32_t n_whitelist2, n_whitelist3;
     const char *whitelist2;
     const uint8_t *whitelist2_len;

@@ -632,7 +632,7 @@ int launch_emit(ssd_ctx* c, int which, uint8_t* d_out, const uint32_t* order = n
     if (!order && n_out) rpb = rpb * c->n_rec / n_out;  // input-order blocks also walk over the records that are not written
     a.rpb = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(rpb, 1), 256);
     // input order, plain records, 8-byte whitelist entries: the tiled writer (bulk copies in and out, shared-to-shared assembly)
-    const bool tiled = !order && !a.copy_mode && c->dcfg.bc8 && c->n_rec && !getenv("SSD_EMIT_GROUPS");
+    const bool tiled = !order && !a.copy_mode && c->dcfg.bc8 && c->dcfg.header_style == 0 && c->n_rec && !getenv("SSD_EMIT_GROUPS");
     if (tiled) {
         const uint64_t avg_in = c->r1_len / c->n_rec + 1, avg_out_in = bytes / c->n_rec + 1;  // per input record
         const uint64_t rin = (uint64_t)(kTIn * 7 / 8) / avg_in, rout = (uint64_t)(kTOut * 7 / 8) / avg_out_in;
@@ -722,6 +722,7 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
     if (cfg->errors < 0 || cfg->errors > 8) return fail(nullptr, SSD_EINVAL, "errors must be in 0..8");
     if (cfg->filter_mode != SSD_FILTER_DISTINCT_UMI && cfg->filter_mode != SSD_FILTER_READS) return fail(nullptr, SSD_EINVAL, "unknown filter_mode");
     if (cfg->collapse_pairs < 0 || 2 * cfg->collapse_pairs > cfg->n_whitelist) return fail(nullptr, SSD_EINVAL, "collapse_pairs out of range");  // round-1 list
+    if (cfg->header_style != SSD_HEADER_FAST && cfg->header_style != SSD_HEADER_EXTRACT) return fail(nullptr, SSD_EINVAL, "unknown header_style");
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -771,6 +772,7 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
     d.b3e = cfg->bc3_end;
     d.umi_len = d.ue - d.us;
     d.umi_bits = 2 * d.umi_len;
+    d.header_style = cfg->header_style;
     // round k: its own list when given, else the first one (V2:60: one list for all rounds)
     const char* lists[3] = {cfg->whitelist, cfg->whitelist2 ? cfg->whitelist2 : cfg->whitelist, cfg->whitelist3 ? cfg->whitelist3 : cfg->whitelist};
     const uint8_t* lens[3] = {cfg->whitelist_len, cfg->whitelist2 ? cfg->whitelist2_len : cfg->whitelist_len,

@@ -26,6 +26,7 @@ struct DevCfg {
     int fast_geom;    // all three barcode windows are exactly 8 wide
     int need_len;     // largest slice end: shorter read-2 sequences take the exact generic path
     int bc8;          // every whitelist entry is exactly 8 bytes long
+    int header_style; // 0: V2:134-141 (id up to the first '/', blanks removed, _cell_umi); 1: Extract_BC_UMI.py:78-85 (first token _cell_umi, blank, second token)
     unsigned long long magic_n, magic_nn;  // ceil(2^43 / n3), ceil(2^43 / (n2 n3)): exact division of cell ids < 2^21
     uint16_t wl_code[3][kMaxWl];
     uint8_t wl_len[3][kMaxWl];

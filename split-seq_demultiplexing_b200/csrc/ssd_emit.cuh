@@ -235,9 +235,24 @@ __device__ __forceinline__ uint32_t emit_record_generic(const Acc& a, const Emit
         return o;
     }
 
+    size_t tok1_s = 0, tok1_e = 0;  // header style 1: the second token follows the UMI
+    if (cfg.header_style == 1) {
+        // Extract_BC_UMI.py:78-85: ReadName.split()[0], then _cell_umi, a blank, ReadName.split()[1]
+        size_t p = L.s[0], t0s, t0e;
+        while (p < L.e[0] && py_space(a.byte(p))) p++;
+        t0s = p;
+        while (p < L.e[0] && !py_space(a.byte(p))) p++;
+        t0e = p;
+        while (p < L.e[0] && py_space(a.byte(p))) p++;
+        tok1_s = p;
+        while (p < L.e[0] && !py_space(a.byte(p))) p++;
+        tok1_e = p;
+        for (size_t i = lane; i < t0e - t0s; i += 32) dst[o + i] = (uint8_t)a.byte(t0s + i);
+        o += (uint32_t)(t0e - t0s);
+    }
     // header: bytes before the first '/', blanks removed, then strip()
-    size_t cut = L.e[0];
-    for (size_t p = L.s[0]; p < L.e[0]; p += 32) {
+    size_t cut = cfg.header_style == 1 ? L.s[0] : L.e[0];
+    for (size_t p = L.s[0]; p < cut; p += 32) {
         uint32_t c = p + lane < L.e[0] ? a.byte(p + lane) : 0u;
         uint32_t sl = __ballot_sync(0xFFFFFFFFu, c == '/');
         if (sl) {
@@ -288,6 +303,12 @@ __device__ __forceinline__ uint32_t emit_record_generic(const Acc& a, const Emit
         if ((uint32_t)lane < ulen) dst[o + lane] = args.r2buf[uoff + lane];
     }
     o += ulen;
+    if (cfg.header_style == 1) {
+        if (lane == 0) dst[o] = ' ';
+        o += 1;
+        for (size_t i = lane; i < tok1_e - tok1_s; i += 32) dst[o + i] = (uint8_t)a.byte(tok1_s + i);
+        o += (uint32_t)(tok1_e - tok1_s);
+    }
     if (lane == 0) dst[o] = '\n';
     o += 1;
 
@@ -495,7 +516,7 @@ __global__ void __launch_bounds__(kThreads) k_emit(const __grid_constant__ EmitA
     if (out_hi == out_lo) return;  // nothing of this block survives the filter: no loads at all
 
     const uint32_t out_skew = (uint32_t)(((uintptr_t)args.out + out_lo) & 15u);
-    const bool staged = out_hi - out_lo + out_skew <= (uint64_t)kEmitOut;
+    const bool staged = cfg.header_style == 0 && out_hi - out_lo + out_skew <= (uint64_t)kEmitOut;  // the other header style: warp per record
 
     if (!staged) {
         // records too long for the staging buffer: one warp per record, global memory to global memory

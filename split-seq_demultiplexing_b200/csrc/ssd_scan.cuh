@@ -171,7 +171,7 @@ __device__ __forceinline__ unsigned long long tok_hash_generic(const Acc& a, siz
 // exact generic path (any accessor)
 // ======================================================================================================
 template <class Acc, typename OffT>
-__device__ __noinline__ bool r1_record_generic(const Acc& a, const ScanArgs<OffT>& args, uint64_t r, size_t start)
+__device__ __noinline__ bool r1_record_generic(const Acc& a, const ScanArgs<OffT>& args, uint64_t r, size_t start, int header_style = 0)
 {
     Lines L;
     if (!find_lines(a, start, args.len, true, L)) return false;
@@ -181,31 +181,50 @@ __device__ __noinline__ bool r1_record_generic(const Acc& a, const ScanArgs<OffT
         return true;
     }
     if (a.byte(L.s[0]) != '@') raise(args.cnt, args.err_off, 0, kErrNoAt, start);
-    // name.split("/")[0].replace(" ", "").strip()  (V2:135-138)
-    uint32_t kept = 0, kept_at_last_nonspace = 0;
-    size_t end2 = L.s[0];
-    for (size_t p = L.s[0]; p < L.e[0]; p++) {
-        uint32_t c = a.byte(p);
-        if (c == '/') break;
-        if (c != ' ') kept++;
-        if (!py_space(c)) {
-            kept_at_last_nonspace = kept;
-            end2 = p + 1;
-        }
-    }
     const size_t seq_e = rstrip_end(a, L.s[1], L.e[1]);
     const size_t qual_e = rstrip_end(a, L.s[3], L.e[3]);
-    const size_t cut_len = end2 - L.s[0], seq_rel = L.s[1] - start, seq_len = seq_e - L.s[1], qual_rel = L.s[3] - start,
-                 qual_len = qual_e - L.s[3];
+    const size_t seq_rel = L.s[1] - start, seq_len = seq_e - L.s[1], qual_rel = L.s[3] - start, qual_len = qual_e - L.s[3];
+    uint32_t kept_at_last_nonspace = 0;
     uint4 m;
-    if (cut_len < 65536 && seq_rel < 65536 && seq_len < 65536 && qual_rel < 65536 && qual_len < 65536) {
-        m.x = (uint32_t)cut_len | (kept_at_last_nonspace << 16);
-        m.y = (uint32_t)seq_rel | ((uint32_t)seq_len << 16);
-        m.z = (uint32_t)qual_rel | ((uint32_t)qual_len << 16);
-        m.w = 0;
-    } else {
+    if (header_style == 1) {
+        // Extract_BC_UMI.py:78-85: ReadName.split()[0] + "_" + cell + "_" + umi + " " + ReadName.split()[1]; the writer takes the
+        // record from its bytes (kMetaLong), the scan only has to say how long the header gets
+        size_t p = L.s[0];
+        uint32_t tl[2] = {0, 0};
+        int nt = 0;
+        while (p < L.e[0] && nt < 2) {
+            while (p < L.e[0] && py_space(a.byte(p))) p++;
+            const size_t t0 = p;
+            while (p < L.e[0] && !py_space(a.byte(p))) p++;
+            if (p > t0) tl[nt++] = (uint32_t)(p - t0);
+        }
+        if (nt < 2) raise(args.cnt, args.err_off, 0, kErrIndex, start);  // ReadName_parts[1]: IndexError
+        kept_at_last_nonspace = tl[0] + 1u + tl[1];
         m.x = m.y = m.z = 0;
         m.w = kMetaLong;
+    } else {
+        // name.split("/")[0].replace(" ", "").strip()  (V2:135-138)
+        uint32_t kept = 0;
+        size_t end2 = L.s[0];
+        for (size_t p = L.s[0]; p < L.e[0]; p++) {
+            uint32_t c = a.byte(p);
+            if (c == '/') break;
+            if (c != ' ') kept++;
+            if (!py_space(c)) {
+                kept_at_last_nonspace = kept;
+                end2 = p + 1;
+            }
+        }
+        const size_t cut_len = end2 - L.s[0];
+        if (cut_len < 65536 && seq_rel < 65536 && seq_len < 65536 && qual_rel < 65536 && qual_len < 65536) {
+            m.x = (uint32_t)cut_len | (kept_at_last_nonspace << 16);
+            m.y = (uint32_t)seq_rel | ((uint32_t)seq_len << 16);
+            m.z = (uint32_t)qual_rel | ((uint32_t)qual_len << 16);
+            m.w = 0;
+        } else {
+            m.x = m.y = m.z = 0;
+            m.w = kMetaLong;
+        }
     }
     size_t tok_e = L.s[0];
     while (tok_e < L.e[0] && !py_space(a.byte(tok_e))) tok_e++;
@@ -581,7 +600,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                         args.r1_base[r] = G.base[i];
                         args.r1_tok[r] = G.fp[i];
                     } else if (have) {
-                        r1_record_generic(ga, args, r, tile_lo + s0);
+                        r1_record_generic(ga, args, r, tile_lo + s0, cfg.header_style);
                     }
                 } else if (MODE == kScanAnn) {
                     if (ok2) {
@@ -970,7 +989,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
 
             if (MODE == kScanR1) {
                 uint32_t seq_e = s2 - 1u, qual_e = s4 - 1u;
-                ok = fast && bad == 0u;
+                ok = fast && bad == 0u && cfg.header_style == 0;  // the other header style goes the exact way, record by record
                 if (ok) ok = rstrip2(s_win, s1, seq_e) && rstrip2(s_win, s3, qual_e);
                 if (ok) {
                     noat = s_win[s0] != '@';
@@ -1098,7 +1117,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                     args.r1_tok[r] = fp;
                 }
                 __syncwarp();
-                if (have && !ok2) r1_record_generic(ga, args, r, tile_lo + s0);
+                if (have && !ok2) r1_record_generic(ga, args, r, tile_lo + s0, cfg.header_style);
                 __syncwarp();
             } else if (MODE == kScanAnn) {
                 if (ok2) {

@@ -50,6 +50,9 @@ def build_parser():
                    help='extension: read the whitelist from the -1/-2/-3 files instead of Round*_barcodes_new*.txt in the CWD')
     p.add_argument('--cellTable', required=False,
                    help='extension: also write cell / reads / distinct UMIs / passing as tab-separated text to this path (one GPU)')
+    p.add_argument('--headerStyle', required=False, default='fast', choices=['fast', 'extract'],
+                   help='extension: "extract" writes the headers of Extract_BC_UMI.py (id_cell_umi, blank, rest of the name) instead of '
+                        'the fast path\'s id_cell_umi')
     p.add_argument('--cellUmiTable', required=False,
                    help='extension: also write cell / UMI / reads (one row per distinct pair of the passing cells) as tab-separated '
                         'text to this path (one GPU, input within one batch)')
@@ -94,7 +97,7 @@ def main(argv=None):
         positions = learned
     collapse = 48 if str(args.collapseRandomHexamers).lower() == 'true' else 0
     dm = ssd_b200.Demultiplexer(whitelist, errors=int(args.errors), min_count=int(args.minReads), positions=positions,
-                                collapse_pairs=collapse, device=local if world > 1 else None, whitelist2=whitelist2, whitelist3=whitelist3)
+                                collapse_pairs=collapse, device=local if world > 1 else None, whitelist2=whitelist2, whitelist3=whitelist3, header_style=args.headerStyle)
     # file to file inside the library (pinned rings, overlapped copies; batches of whole records above SSD_BATCH_BYTES).
     # Without -p the reference still demultiplexes (and raises on a missing mate) but never writes the passing file.
     wanted = bool(args.performanceMetrics)                                      # CLI3:70 + V2:391

@@ -35,7 +35,7 @@ class Config(C.Structure):
                 ("umi_start", C.c_int32), ("umi_end", C.c_int32), ("bc1_start", C.c_int32), ("bc1_end", C.c_int32),
                 ("bc2_start", C.c_int32), ("bc2_end", C.c_int32), ("bc3_start", C.c_int32), ("bc3_end", C.c_int32),
                 ("errors", C.c_int32), ("min_count", C.c_int64), ("filter_mode", C.c_int32),
-                ("collapse_pairs", C.c_int32), ("record_bytes_hint", C.c_int32), ("reserved", C.c_int32),
+                ("collapse_pairs", C.c_int32), ("record_bytes_hint", C.c_int32), ("header_style", C.c_int32),
                 ("n_whitelist2", C.c_int32), ("n_whitelist3", C.c_int32),
                 ("whitelist2", C.c_char_p), ("whitelist2_len", C.POINTER(C.c_uint8)),
                 ("whitelist3", C.c_char_p), ("whitelist3_len", C.POINTER(C.c_uint8))]

@@ -45,10 +45,11 @@ class Demultiplexer:
     def __init__(self, whitelist: Sequence[str], errors: int = 1, min_count: int = 10,
                  positions: Optional[Dict[str, Tuple[int, int]]] = None, filter_mode: str = "distinct_umi",
                  collapse_pairs: int = 0, device: Optional[int] = None, record_bytes_hint: int = 0,
-                 whitelist2: Optional[Sequence[str]] = None, whitelist3: Optional[Sequence[str]] = None):
+                 whitelist2: Optional[Sequence[str]] = None, whitelist3: Optional[Sequence[str]] = None, header_style: str = "fast"):
         """whitelist: matched against the Round1 window (bc1) -- and against the other two as well (V2:60, 302-304: the reference's
         fast path has ONE list) unless whitelist2 / whitelist3 give the Round2 (bc2) / Round3 (bc3) windows their own lists
-        (extension)."""
+        (extension).  header_style: "fast" = V2:134-141 (`id_cell_umi`, blanks of the name removed, cut at the first
+        "/"), "extract" = Extract_BC_UMI.py:78-85 (`id_cell_umi comment`; IndexError for names of one token; exact but slower path)."""
         self.lib = L.load()
         pos = dict(DEFAULT_POSITIONS)
         if positions:
@@ -88,6 +89,7 @@ class Demultiplexer:
         cfg.filter_mode = {"distinct_umi": L.FILTER_DISTINCT_UMI, "reads": L.FILTER_READS}[filter_mode]
         cfg.collapse_pairs = int(collapse_pairs)
         cfg.record_bytes_hint = int(record_bytes_hint)
+        cfg.header_style = {"fast": 0, "extract": 1}[header_style]
         self.filter_mode = filter_mode
         self.min_count = int(min_count)
         self._ctx = C.c_void_p()

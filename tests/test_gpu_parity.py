@@ -706,3 +706,47 @@ def test_fuzz_against_oracle(ssd, orc, seed):
     assert (stats["n_matched"], stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]) == (
         ref.n_matched, ref.n_cells, ref.n_passing_cells, ref.n_retained)
     assert dm.record_cells().tolist() == ref.rec_cell
+
+
+def test_extract_style_headers_equal_the_reference_script(ssd, orc):
+    """SSD_HEADER_EXTRACT against the UNMODIFIED Extract_BC_UMI.py (tests/golden/make_golden_extract.py ran it on these very
+    reads): `id_cell_umi rest-of-name`, then read, "+", quality.  The script names the cell after its input file and finds the
+    UMI by its own rule, so the golden record is compared with the cell field swapped for the fast path's cell, and the UMI
+    wherever the script's position finder lands on the default offset; the outputs, the filter and the tables otherwise equal
+    the default header style's."""
+    import gzip
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_extract", os.path.join(fu.GOLDEN_DIR, "make_golden_extract.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    with gzip.open(os.path.join(fu.GOLDEN_DIR, "extract_bc_umi_case.json.gz")) as fh:
+        case = json.loads(fh.read())
+    r1, r2 = gen.inputs()
+    gold = case["output"].encode().split(b"\n")
+    gold = {gold[k].split(b"_")[0]: gold[k:k + 4] for k in range(0, len(gold) - 1, 4)}
+    assert len(gold) == case["n"]
+    dm = ssd.Demultiplexer(WL, errors=1, min_count=1, header_style="extract")
+    out, stats = dm.run_host(r1, r2, ssd.EMIT_MATCHED)
+    ref = orc.demultiplex(r1, r2, WL, 1, 1)  # the default style: same records, same cells, same UMIs
+    lines, fast = out.tobytes().split(b"\n"), ref.merged1.split(b"\n")
+    assert stats["n_matched"] == ref.n_matched > 150 and len(lines) == len(fast)
+    same_umi = 0
+    for k in range(0, len(lines) - 1, 4):
+        head, rest = lines[k].split(b" ", 1)
+        ident, cell, umi = head.split(b"_")
+        g = gold[ident]
+        g_ident, g_cell, g_umi_rest = g[0].split(b"_")
+        g_umi, g_rest = g_umi_rest.split(b" ", 1)
+        assert g_cell == case["cell"].encode() and rest == g_rest and lines[k + 1:k + 4] == g[1:4]
+        assert (cell, umi) == tuple(fast[k].split(b"_")[1:3]) and lines[k + 1:k + 4] == fast[k + 1:k + 4]
+        same_umi += umi == g_umi
+    assert same_umi >= 0.9 * stats["n_matched"]
+    # the filter does not look at headers: -m decides as with the default style
+    dm10 = ssd.Demultiplexer(WL, errors=1, min_count=3, header_style="extract")
+    out10, st10 = dm10.run_host(r1, r2, ssd.EMIT_PASSING)
+    ref10 = orc.demultiplex(r1, r2, WL, 1, 3)
+    assert (st10["n_passing_cells"], st10["n_retained"]) == (ref10.n_passing_cells, ref10.n_retained)
+    assert out10.tobytes().split(b"\n")[1::4] == ref10.passing.split(b"\n")[1::4]  # the same records, in the same order
+    # a name of one token: ReadName_parts[1] is an IndexError in the script
+    with pytest.raises(IndexError):
+        ssd.Demultiplexer(WL, errors=1, min_count=1, header_style="extract").run_host(r1.replace(b"@SRR6750041.5 5/1", b"@SRR6750041.5"), r2, ssd.EMIT_MATCHED)
