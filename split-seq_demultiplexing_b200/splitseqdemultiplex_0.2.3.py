@@ -49,7 +49,7 @@ def build_parser():
     p.add_argument('--useBarcodeFiles', action='store_true',
                    help='extension: read the whitelist from the -1/-2/-3 files instead of Round*_barcodes_new*.txt in the CWD')
     p.add_argument('--cellTable', required=False,
-                   help='extension: also write cell / reads / distinct UMIs / passing as tab-separated text to this path (one GPU)')
+                   help='extension: also write cell / reads / distinct UMIs / passing as tab-separated text to this path')
     p.add_argument('--headerStyle', required=False, default='fast', choices=['fast', 'extract'],
                    help='extension: "extract" writes the headers of Extract_BC_UMI.py (id_cell_umi, blank, rest of the name) instead of '
                         'the fast path\'s id_cell_umi')
@@ -106,13 +106,19 @@ def main(argv=None):
         if str(args.version) == 'split':
             # per-cell files instead of the merged one: the fast path's annotated records bucketed by cell, named like the
             # legacy pipeline's results (round1-round2-round3.fastq, demultiplex_using_barcodes.py:364); one GPU, one call
-            import numpy as np
             if world > 1:
-                sys.exit('--version split runs on one GPU')
-            _, stats = dm.run_host(np.fromfile(args.fastqF, dtype=np.uint8), np.fromfile(args.fastqR, dtype=np.uint8), ssd_b200.EMIT_PASSING)
-            if wanted:
-                files = dm.write_split_files(args.outputDir, hostlogic.load_round_names("."), stats)
-                say("# of results files [{}]".format(len(files)))               # demultiplex_using_barcodes.py:408
+                # every rank buckets its record range; the ranks append to the per-cell files in rank order
+                from ssd_b200 import filebatch
+                if not wanted:
+                    sys.exit('--version split under torchrun needs -p (the per-cell files are its only output)')
+                n_mine, stats = filebatch.run_split_sharded(dm, args.fastqF, args.fastqR, args.outputDir, hostlogic.load_round_names("."), world=world)
+                say("# of results files [{}]".format(stats["n_passing_cells"]))   # demultiplex_using_barcodes.py:408
+            else:
+                import numpy as np
+                _, stats = dm.run_host(np.fromfile(args.fastqF, dtype=np.uint8), np.fromfile(args.fastqR, dtype=np.uint8), ssd_b200.EMIT_PASSING)
+                if wanted:
+                    files = dm.write_split_files(args.outputDir, hostlogic.load_round_names("."), stats)
+                    say("# of results files [{}]".format(len(files)))               # demultiplex_using_barcodes.py:408
         elif world > 1:
             from ssd_b200 import filebatch
             if not wanted:
@@ -122,8 +128,10 @@ def main(argv=None):
                 os.remove(out_path)
         else:
             _, stats = dm.run_files(args.fastqF, args.fastqR, out_path, ssd_b200.EMIT_PASSING, append=True)  # V2:415 (append mode)
-        if args.cellTable and world == 1:
-            dm.write_cell_table(args.cellTable)  # the global tables are still in place after the (last) batch
+        if args.cellTable and rank == 0 and (world == 1 or str(args.version) != 'split'):
+            # the global tables are still in place after the (last) batch; on several GPUs every rank holds them (two_pass
+            # leaves the exact distinct counts of the exchange by owner rank), rank 0 writes
+            dm.write_cell_table(args.cellTable)
         if args.cellUmiTable and world == 1:
             from ssd_b200 import filebatch
             if max(os.path.getsize(args.fastqF), os.path.getsize(args.fastqR)) > filebatch.batch_bytes():

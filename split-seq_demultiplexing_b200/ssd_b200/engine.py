@@ -273,15 +273,23 @@ class Demultiplexer:
         host = out[:n].cpu().numpy()
         del out
         os.makedirs(out_dir, exist_ok=True)
-        written = []
+        jobs = []
         for (_, off, _, nbytes), cid in zip(table, self._split_ids):
             i1, i2, i3 = self.cell_indices(cid)
             name = (hostlogic.split_file_name(round_names, i1, i2, i3) if round_names is not None
                     else "%s-%s-%s.fastq" % (self.rounds[0][i1], self.rounds[1][i2], self.rounds[2][i3]))
+            jobs.append((name, off, nbytes))
+
+        def put(job):  # one open / write / close per cell: system calls, which release the interpreter lock
+            name, off, nbytes = job
             with open(os.path.join(out_dir, name), "ab") as fh:
-                fh.write(host[off:off + nbytes].tobytes())
-            written.append((name, nbytes))
-        return written
+                fh.write(memoryview(host)[off:off + nbytes])
+            return name, nbytes
+        if len(jobs) < 64:
+            return [put(j) for j in jobs]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:  # every cell has its own file: no two threads share one
+            return list(pool.map(put, jobs, chunksize=256))
 
     def record_cells(self):
         import numpy as np

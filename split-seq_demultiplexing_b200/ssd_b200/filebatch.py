@@ -312,3 +312,39 @@ def run_files_sharded(dm, path_r1: str, path_r2: str, out_path: str, which: int 
                 os.remove("%s.part%d" % (out_path, r))
     dist.barrier(group=group)
     return int(sums[-1]), stats
+
+
+def run_split_sharded(dm, path_r1: str, path_r2: str, out_dir: str, round_names=None, world: int = 1, group=None):
+    """Split mode (one file per passing cell) on N ranks sharing one pair of files: every rank takes its byte
+    range of both files (plan_shards_device: cut at the same records), decides -m with the other ranks (global_filter), buckets
+    ITS records by cell on the device, and the ranks append their buckets to the per-cell files one after the other, in rank
+    order -- the bytes the single-GPU call writes, since the ranks hold consecutive record ranges (flushBuffers appends the
+    same way, splitseq_utilities.py:15-21).  One batch per rank (the pair must fit world x SSD_BATCH_BYTES).  Returns (number
+    of files this rank wrote to, the rank's stats with the global cell counts)."""
+    import torch.distributed as dist
+    from .distributed import global_filter
+    if world <= 1:
+        plan = [[(0, os.path.getsize(path_r1), 0, os.path.getsize(path_r2))]]
+        rank = 0
+    else:
+        rank = dist.get_rank(group)
+
+        def allgather(values):
+            parts = [None] * world
+            dist.all_gather_object(parts, [int(x) for x in values], group=group)
+            return parts
+        plan = plan_shards_device(path_r1, path_r2, world, rank, device_tile_counts(dm, 0), device_tile_counts(dm, 1), allgather)
+    if any(len(p) != 1 for p in plan):
+        raise ValueError("split mode takes one batch per rank: the files are larger than world x SSD_BATCH_BYTES")
+    o1, n1, o2, n2 = plan[rank][0]
+    dm._check(dm.lib.ssd_load_file_range(dm._ctx, 0, os.fsencode(path_r1), o1, n1))
+    dm._check(dm.lib.ssd_load_file_range(dm._ctx, 1, os.fsencode(path_r2), o2, n2))
+    dm._check(dm.lib.ssd_demux_loaded(dm._ctx))
+    stats = global_filter(dm, world, group=group)
+    n_files = 0
+    for turn in range(world):
+        if turn == rank:
+            n_files = len(dm.write_split_files(out_dir, round_names, stats))
+        if world > 1:
+            dist.barrier(group=group)
+    return n_files, stats

@@ -132,7 +132,7 @@ def test_two_ranks_three_batches_each_equal_one_call(tmp_path):
     assert int(st[0][2]) + int(st[1][2]) == stats["n_retained"]
 
 
-def _cli_worker(rank, world, port, workdir, batch_bytes):
+def _cli_worker(rank, world, port, workdir, batch_bytes, extra=()):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
                       SSD_BATCH_BYTES=str(batch_bytes))
     os.chdir(workdir)
@@ -143,7 +143,7 @@ def _cli_worker(rank, world, port, workdir, batch_bytes):
     pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "split-seq_demultiplexing_b200")
     sys.path.insert(0, pkg)
     sys.argv = ["splitseqdemultiplex_0.2.3.py", "-n", "2", "-e", "1", "-m", "10", "-1", "a", "-2", "b", "-3", "c", "-f", "F.fastq", "-r", "R.fastq",
-                "-o", "results", "-a", "", "-b", "100000", "-p", "True", "-l", "20000"]
+                "-o", "results", "-a", "", "-b", "100000", "-p", "True", "-l", "20000"] + list(extra)
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         runpy.run_path(os.path.join(pkg, "splitseqdemultiplex_0.2.3.py"), run_name="__main__")
@@ -180,3 +180,34 @@ def test_cli_under_two_ranks_matches_the_reference_digest(tmp_path, batch_bytes)
     single = tmp_path / "single.fastq"
     dm.run_files(str(tmp_path / "F.fastq"), str(tmp_path / "R.fastq"), str(single), ssd_b200.EMIT_PASSING, append=False)
     assert out == single.read_bytes()
+
+
+def test_cli_split_and_cell_table_under_two_ranks(tmp_path):
+    """`-v split` and `--cellTable` with one process per GPU: the ranks bucket their record ranges and append to the per-cell
+    files in rank order (the files of the single-GPU call, byte for byte); the per-cell table written by rank 0 after the
+    merged run is the global one."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import ssd_b200
+    from ssd_b200 import hostlogic
+    fu.write_whitelist_files(str(tmp_path))
+    r1, r2 = fu.load_bundled()
+    (tmp_path / "F.fastq").write_bytes(r1)
+    (tmp_path / "R.fastq").write_bytes(r2)
+    mp.spawn(_cli_worker, args=(2, _free_port(), str(tmp_path), 10**9, ("-v", "split")), nprocs=2, join=True)
+    got = {f: (tmp_path / "results" / f).read_bytes() for f in os.listdir(str(tmp_path / "results"))}
+    dm = ssd_b200.Demultiplexer(WL, errors=1, min_count=10)
+    _, stats = dm.run_host(r1, r2, ssd_b200.EMIT_PASSING)
+    single = tmp_path / "single_split"
+    dm.write_split_files(str(single), hostlogic.load_round_names(str(tmp_path)), stats)
+    want = {f: (single / f).read_bytes() for f in os.listdir(str(single))}
+    assert len(want) == 83 and got == want
+    assert "# of results files [83]" in (tmp_path / "stdout_0.txt").read_text()
+    # merged run with the per-cell table
+    import shutil
+    shutil.rmtree(str(tmp_path / "results"))
+    mp.spawn(_cli_worker, args=(2, _free_port(), str(tmp_path), 10**9, ("--cellTable", "cells.tsv")), nprocs=2, join=True)
+    dm.write_cell_table(str(tmp_path / "cells_single.tsv"))
+    assert (tmp_path / "cells.tsv").read_bytes() == (tmp_path / "cells_single.tsv").read_bytes()
