@@ -488,6 +488,7 @@ struct __align__(128) ScanSmem {
     unsigned long long line_base[kBGroups];
     uint32_t tile[kWinSlots];
     uint32_t total[kListSlots], n_listed[kListSlots], list_tile[kListSlots];
+    uint32_t guess_j[kListSlots], guess_n[kListSlots];  // stage A's guess of the record phase of the tile (stage B takes it from here)
     uint32_t warp_tile[kAWarps], halo_sum[2];
     alignas(16) uint32_t mask[kWinWords];     // newline bitmap of the tile in stage A (bit b of word w = byte 32 w + b)
 };
@@ -849,7 +850,32 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         sync_a();  // list complete; warp_tile / halo_sum / mask may be reused
         PROF_T(t2d);
         PROF_ADD(13, t2c, t2d);
-        if (tid == 0) mbar_arrive(&S.list_full[ls]);  // hand the tile to stage B
+        if (warp == 0) {
+            // ---- the guess: a record starts at the first line (of the four candidates, one per lane) that begins with '@' and
+            //      whose second next line begins with '+'.  A wrong guess costs a second pass, never a wrong result.  Made here
+            //      because stage A runs ahead of stage B and has the time. ----
+            const uint32_t n_listed = total + halo_total;
+            uint32_t j_guess = 0xFFFFFFFFu, n_guess = 0;
+            const uint32_t j = (uint32_t)lane + 1u;
+            bool cand = false;
+            if (tile != 0 && n_listed + 1u <= (uint32_t)kMaxLines && j <= 4u && j <= total && j + 2u <= n_listed)
+                cand = s_win[s_lstart[j]] == '@' && s_win[s_lstart[j + 2u]] == '+';
+            const uint32_t cands = __ballot_sync(0xFFFFFFFFu, cand);
+            if (lane == 0) {
+                if (n_listed + 1u <= (uint32_t)kMaxLines) {
+                    if (tile == 0) {
+                        j_guess = 0;
+                        n_guess = args.len ? (total >> 2) + 1u : 0u;
+                    } else if (cands) {
+                        j_guess = (uint32_t)__ffs((int)cands);  // lane + 1
+                        n_guess = ((total - j_guess) >> 2) + 1u;
+                    }
+                }
+                S.guess_j[ls] = j_guess;
+                S.guess_n[ls] = n_guess;
+                mbar_arrive(&S.list_full[ls]);  // hand the tile to stage B
+            }
+        }
         PROF_T(t3);
         PROF_ADD(2, t2, t3);
         return true;
@@ -922,6 +948,48 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                     if (MODE != kScanR2) s4 = s_lstart[j0 + 4];
                     // read 2 only needs line 3 to exist; the generic path raises the overflow flag
                     fast = MODE != kScanR2 || tile_lo + s3 < args.len;
+                }
+            }
+            // ---- read 2: the three windows are packed and ALL their table lookups requested before the header walk, which hides
+            //      the trip to the L2 (the tables do not fit what the shared-memory carve-out leaves of the L1).  A window with one
+            //      byte outside ACGT needs four lookups in the level e - 1 table (match8): they go out in the same batch, for one
+            //      such window per record; records with more take the lookups of match8 afterwards (rare). ----
+            uint32_t code1 = 0, code2 = 0, code3 = 0, dirty = 0, w_seq_e = s2 - 1u;
+            uint32_t v1 = 0xFFu, v2 = 0xFFu, v3 = 0xFFu, x0 = 0xFFu, x1 = 0xFFu, x2 = 0xFFu, x3 = 0xFFu;  // x*: the four lookups of the one dirty window
+            uint32_t da0 = 0, da1 = 0, db0 = 0, db1 = 0, dc0 = 0, dc1 = 0;
+            bool win_ok = false;
+            if (MODE == kScanR2) {
+                win_ok = fast && cfg.fast_wl != 0 && cfg.fast_geom != 0;
+                if (win_ok) win_ok = rstrip2(s_win, s1, w_seq_e);
+                if (win_ok) win_ok = w_seq_e - s1 >= (uint32_t)cfg.need_len;  // truncated read 2 goes the exact way
+                if (win_ok) {
+                    uint32_t y0, y1;
+                    load8(words, s1 + (uint32_t)cfg.b1s, y0, y1);
+                    code1 = pack4(y0, da0) | (pack4(y1, da1) << 8);
+                    load8(words, s1 + (uint32_t)cfg.b2s, y0, y1);
+                    code2 = pack4(y0, db0) | (pack4(y1, db1) << 8);
+                    load8(words, s1 + (uint32_t)cfg.b3s, y0, y1);
+                    code3 = pack4(y0, dc0) | (pack4(y1, dc1) << 8);
+                    dirty = ((da0 | da1) ? 1u : 0u) | ((db0 | db1) ? 2u : 0u) | ((dc0 | dc1) ? 4u : 0u);
+                    if (!(dirty & 1u)) v1 = __ldg(lut_of(cfg, args.lut, 0, cfg.e) + code1);
+                    if (!(dirty & 2u)) v2 = __ldg(lut_of(cfg, args.lut, 1, cfg.e) + code2);
+                    if (!(dirty & 4u)) v3 = __ldg(lut_of(cfg, args.lut, 2, cfg.e) + code3);
+                    if (dirty && (dirty & (dirty - 1u)) == 0u && cfg.e >= 1) {  // exactly one dirty window
+                        const int rd = dirty == 1u ? 0 : (dirty == 2u ? 1 : 2);
+                        const uint32_t dc = rd == 0 ? code1 : (rd == 1 ? code2 : code3);
+                        const uint32_t q0 = rd == 0 ? da0 : (rd == 1 ? db0 : dc0), q1 = rd == 0 ? da1 : (rd == 1 ? db1 : dc1);
+                        const uint32_t inv0 = ~zero_flags(q0) & 0x80808080u, inv1 = ~zero_flags(q1) & 0x80808080u;
+                        if (__popc(inv0) + __popc(inv1) == 1) {
+                            const uint32_t bit = inv0 ? (uint32_t)__ffs((int)inv0) - 1u : 32u + (uint32_t)__ffs((int)inv1) - 1u;
+                            const uint32_t sh = 2u * (bit >> 3), base = dc & ~(3u << sh);
+                            const uint8_t* l = lut_of(cfg, args.lut, rd, cfg.e - 1);
+                            x0 = __ldg(l + base);
+                            x1 = __ldg(l + (base | (1u << sh)));
+                            x2 = __ldg(l + (base | (2u << sh)));
+                            x3 = __ldg(l + (base | (3u << sh)));
+                            dirty |= 8u;  // answered by x0..x3
+                        }
+                    }
                 }
             }
             // header bytes [s0, s0 + hdr_len), one trailing '\r' dropped; token = bytes before the first byte <= 0x20
@@ -1053,29 +1121,24 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                     base_len = hdr_len + (seq_e - s1) + (plus_e - s2) + (qual_e - s3) + 4u;
                 }
             } else {
-                // ---- lineRead = line.rstrip(); the four windows (V2:293-301) ----
-                uint32_t seq_e = s2 - 1u;
-                ok = fast && bad == 0u && cfg.fast_wl != 0 && cfg.fast_geom != 0;
-                if (ok) ok = rstrip2(s_win, s1, seq_e);
-                if (ok) ok = seq_e - s1 >= (uint32_t)cfg.need_len;  // truncated read 2 goes the exact way
+                // ---- lineRead = line.rstrip(); the four windows (V2:293-301): requested above, answered by now ----
+                ok = win_ok && bad == 0u;
                 if (ok) {
                     complete = true;
                     noat = s_win[s0] != '@';
-                    // the three windows are packed first so that their LUT lookups are in flight together
-                    uint32_t x0, x1, da0, da1, db0, db1, dc0, dc1;
-                    load8(words, s1 + (uint32_t)cfg.b1s, x0, x1);
-                    const uint32_t code1 = pack4(x0, da0) | (pack4(x1, da1) << 8);
-                    load8(words, s1 + (uint32_t)cfg.b2s, x0, x1);
-                    const uint32_t code2 = pack4(x0, db0) | (pack4(x1, db1) << 8);
-                    load8(words, s1 + (uint32_t)cfg.b3s, x0, x1);
-                    const uint32_t code3 = pack4(x0, dc0) | (pack4(x1, dc1) << 8);
-                    const uint32_t v1 = __ldg(lut_of(cfg, args.lut, 0, cfg.e) + code1), v2 = __ldg(lut_of(cfg, args.lut, 1, cfg.e) + code2),
-                                   v3 = __ldg(lut_of(cfg, args.lut, 2, cfg.e) + code3);
                     int i1 = v1 == 0xFFu ? -1 : (int)v1, i2 = v2 == 0xFFu ? -1 : (int)v2, i3 = v3 == 0xFFu ? -1 : (int)v3;
-                    if ((da0 | da1 | db0 | db1 | dc0 | dc1) != 0u) {  // some window holds a byte that is not A/C/G/T
-                        if (da0 | da1) i1 = match8(cfg, 0, args.lut, code1, da0, da1);
-                        if (db0 | db1) i2 = match8(cfg, 1, args.lut, code2, db0, db1);
-                        if (dc0 | dc1) i3 = match8(cfg, 2, args.lut, code3, dc0, dc1);
+                    if (dirty) {  // some window holds a byte that is not A/C/G/T
+                        if (dirty & 8u) {
+                            const uint32_t best = min(min(x0, x1), min(x2, x3));
+                            const int ix = best == 0xFFu ? -1 : (int)best;
+                            if (dirty & 1u) i1 = ix;
+                            if (dirty & 2u) i2 = ix;
+                            if (dirty & 4u) i3 = ix;
+                        } else {
+                            if (dirty & 1u) i1 = match8(cfg, 0, args.lut, code1, da0, da1);
+                            if (dirty & 2u) i2 = match8(cfg, 1, args.lut, code2, db0, db1);
+                            if (dirty & 4u) i3 = match8(cfg, 2, args.lut, code3, dc0, dc1);
+                        }
                     }
                     matched = i1 >= 0 && i2 >= 0 && i3 >= 0;  // V2:310-321: all three lists non-empty (the mate check follows in commit())
                     if (matched) {
@@ -1174,23 +1237,8 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         // round robin to the warps instead, which ends the stage sooner but costs a third more instructions
         const uint32_t my_i = (MODE == kScanR2 && SSD_SCAN_R2_SPREAD) ? (uint32_t)lane * kBGWarps + (uint32_t)wb : (uint32_t)tb;
 
-        // ---- the guess: a record starts at the first line (of the four candidates) that begins with '@' and whose second
-        //      next line begins with '+'.  A wrong guess costs a second pass, never a wrong result. ----
-        uint32_t j_guess = 0xFFFFFFFFu, n_guess = 0;
-        if (n_listed + 1u <= (uint32_t)kMaxLines) {
-            if (tile == 0) {
-                j_guess = 0;
-                n_guess = args.len ? (total >> 2) + 1u : 0u;
-            } else {
-                for (uint32_t j = 1; j <= 4u && j <= total && j + 2u <= n_listed; j++) {
-                    if (s_win[s_lstart[j]] == '@' && s_win[s_lstart[j + 2u]] == '+') {
-                        j_guess = j;
-                        n_guess = ((total - j) >> 2) + 1u;
-                        break;
-                    }
-                }
-            }
-        }
+        // the guess of the record phase: made by stage A next to the list
+        const uint32_t j_guess = S.guess_j[ls], n_guess = S.guess_n[ls];
         if (DEFER) {
             // ---- park the results; the commit warp writes them out once the tile's first record number is known ----
             const bool guessed = j_guess != 0xFFFFFFFFu && n_guess <= (uint32_t)kBThreads;
