@@ -457,7 +457,7 @@ constexpr int kComputeWarps = kAWarps + kBWarps;
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kAThreads = kAWarps * 32, kBThreads = kBGWarps * 32;  // kBThreads: threads of ONE stage-B group
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
-constexpr int kScanThreads = kComputeThreads + 96;  // the compute warps + the copy warp + the prefix warp (works in block 0) + the commit warp
+constexpr int kScanThreads = kComputeThreads + 128;  // the compute warps + the copy warp + the prefix warp (works in block 0) + the commit warp + the guess warp
 #ifndef SSD_SCAN_STAGE_SLOTS
 #define SSD_SCAN_STAGE_SLOTS (SSD_SCAN_BGROUPS > 1 ? SSD_SCAN_BGROUPS : 2)
 #endif
@@ -484,11 +484,12 @@ struct __align__(128) ScanSmem {
     uint32_t stage_tile[kStageSlots], stage_total[kStageSlots], stage_guess[kStageSlots], stage_flags[kStageSlots];
     uint16_t lstart[kListSlots][kMaxLines];   // line-start lists of the tiles between stage A and stage B
     unsigned long long full[kWinSlots], empty[kWinSlots];  // mbarriers: bytes landed / window may be refilled
-    unsigned long long list_full[kListSlots], list_empty[kListSlots];  // mbarriers: stage A done with a tile / stage B done with it
+    unsigned long long list_full[kListSlots], list_empty[kListSlots];  // mbarriers: stage A done with a tile (and its phase guessed) / stage B done with it
+    unsigned long long list_done[kListSlots];                          // mbarrier: stage A listed the tile's line starts (over to the guess warp)
     unsigned long long line_base[kBGroups];
     uint32_t tile[kWinSlots];
     uint32_t total[kListSlots], n_listed[kListSlots], list_tile[kListSlots];
-    uint32_t guess_j[kListSlots], guess_n[kListSlots];  // stage A's guess of the record phase of the tile (stage B takes it from here)
+    uint32_t guess_j[kListSlots], guess_n[kListSlots];  // the guess warp's guess of the record phase of the tile (stage B takes it from here)
     uint32_t warp_tile[kAWarps], halo_sum[2];
     alignas(16) uint32_t mask[kWinWords];     // newline bitmap of the tile in stage A (bit b of word w = byte 32 w + b)
 };
@@ -535,6 +536,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         for (int s = 0; s < kListSlots; s++) {
             mbar_init(reinterpret_cast<uint64_t*>(&S.list_full[s]), 1);
             mbar_init(reinterpret_cast<uint64_t*>(&S.list_empty[s]), 1);
+            mbar_init(reinterpret_cast<uint64_t*>(&S.list_done[s]), 1);
         }
         for (int s = 0; s < kStageSlots; s++) {
             mbar_init(reinterpret_cast<uint64_t*>(&S.stage_full[s]), 1);
@@ -544,6 +546,49 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
     __syncthreads();
     volatile unsigned long long* st = args.status;
 
+    if (warp == kComputeWarps + 3) {
+        // ================================ guess warp ================================
+        // Between stage A and stage B: guesses the record phase of every listed tile -- a record starts at the first line (of
+        // the four candidates, one per lane) that begins with '@' and whose second next line begins with '+' -- so that stage B
+        // can work on the records before the tile's line index is known.  A wrong guess costs a second pass, never a wrong
+        // result.  A warp of its own: neither stage pays for the four dependent shared-memory reads.
+        uint32_t ended = 0;
+        for (uint32_t it = 0;; it++) {
+            const uint32_t ws = it % kWinSlots, ls = it % kListSlots;
+            mbar_wait(reinterpret_cast<uint64_t*>(&S.list_done[ls]), (it / kListSlots) & 1u);
+            const uint32_t tile = S.list_tile[ls];
+            if (tile == kNoTile) {  // the end: passed on to the stage-B group whose turn it is
+                if (lane == 0) mbar_arrive(&S.list_full[ls]);
+                if (++ended == (uint32_t)kBGroups) break;
+                continue;
+            }
+            const uint8_t* s_win = S.win[ws];
+            const uint16_t* s_lstart = S.lstart[ls];
+            const uint32_t total = S.total[ls], n_listed = S.n_listed[ls];
+            uint32_t j_guess = 0xFFFFFFFFu, n_guess = 0;
+            const uint32_t j = (uint32_t)lane + 1u;
+            bool cand = false;
+            if (tile != 0 && n_listed + 1u <= (uint32_t)kMaxLines && j <= 4u && j <= total && j + 2u <= n_listed)
+                cand = s_win[s_lstart[j]] == '@' && s_win[s_lstart[j + 2u]] == '+';
+            const uint32_t cands = __ballot_sync(0xFFFFFFFFu, cand);
+            if (lane == 0) {
+                if (n_listed + 1u <= (uint32_t)kMaxLines) {
+                    if (tile == 0) {
+                        j_guess = 0;
+                        n_guess = args.len ? (total >> 2) + 1u : 0u;
+                    } else if (cands) {
+                        j_guess = (uint32_t)__ffs((int)cands);  // lane + 1
+                        n_guess = ((total - j_guess) >> 2) + 1u;
+                    }
+                }
+                S.guess_j[ls] = j_guess;
+                S.guess_n[ls] = n_guess;
+                mbar_arrive(&S.list_full[ls]);  // hand the tile to stage B
+            }
+            __syncwarp();
+        }
+        return;
+    }
     if (warp == kComputeWarps + 2) {
         // ================================ commit warp ================================
         // Stage B parks what it found for a tile's records; this warp waits for the tile's line index, checks that stage B
@@ -752,7 +797,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                 if (k && itk >= (uint32_t)kListSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.list_empty[lk]), ((itk / kListSlots) - 1u) & 1u);
                 if (tid == 0) {
                     S.list_tile[lk] = kNoTile;
-                    mbar_arrive(&S.list_full[lk]);
+                    mbar_arrive(&S.list_done[lk]);  // the guess warp passes the end on to stage B
                 }
             }
             return false;
@@ -850,32 +895,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         sync_a();  // list complete; warp_tile / halo_sum / mask may be reused
         PROF_T(t2d);
         PROF_ADD(13, t2c, t2d);
-        if (warp == 0) {
-            // ---- the guess: a record starts at the first line (of the four candidates, one per lane) that begins with '@' and
-            //      whose second next line begins with '+'.  A wrong guess costs a second pass, never a wrong result.  Made here
-            //      because stage A runs ahead of stage B and has the time. ----
-            const uint32_t n_listed = total + halo_total;
-            uint32_t j_guess = 0xFFFFFFFFu, n_guess = 0;
-            const uint32_t j = (uint32_t)lane + 1u;
-            bool cand = false;
-            if (tile != 0 && n_listed + 1u <= (uint32_t)kMaxLines && j <= 4u && j <= total && j + 2u <= n_listed)
-                cand = s_win[s_lstart[j]] == '@' && s_win[s_lstart[j + 2u]] == '+';
-            const uint32_t cands = __ballot_sync(0xFFFFFFFFu, cand);
-            if (lane == 0) {
-                if (n_listed + 1u <= (uint32_t)kMaxLines) {
-                    if (tile == 0) {
-                        j_guess = 0;
-                        n_guess = args.len ? (total >> 2) + 1u : 0u;
-                    } else if (cands) {
-                        j_guess = (uint32_t)__ffs((int)cands);  // lane + 1
-                        n_guess = ((total - j_guess) >> 2) + 1u;
-                    }
-                }
-                S.guess_j[ls] = j_guess;
-                S.guess_n[ls] = n_guess;
-                mbar_arrive(&S.list_full[ls]);  // hand the tile to stage B
-            }
-        }
+        if (tid == 0) mbar_arrive(&S.list_done[ls]);  // over to the guess warp, then to stage B
         PROF_T(t3);
         PROF_ADD(2, t2, t3);
         return true;
@@ -1237,7 +1257,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         // round robin to the warps instead, which ends the stage sooner but costs a third more instructions
         const uint32_t my_i = (MODE == kScanR2 && SSD_SCAN_R2_SPREAD) ? (uint32_t)lane * kBGWarps + (uint32_t)wb : (uint32_t)tb;
 
-        // the guess of the record phase: made by stage A next to the list
+        // the guess of the record phase: made by the guess warp
         const uint32_t j_guess = S.guess_j[ls], n_guess = S.guess_n[ls];
         if (DEFER) {
             // ---- park the results; the commit warp writes them out once the tile's first record number is known ----
@@ -1250,7 +1270,11 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                 an = 0;
                 o.ann = 0;
             }
+            PROF_T(t6a);
+            PROF_ADD(6, t8, t6a);
             if (it >= (uint32_t)kStageSlots) mbar_wait(reinterpret_cast<uint64_t*>(&S.stage_empty[ss]), ((it / kStageSlots) - 1u) & 1u);
+            PROF_T(t6b);
+            PROF_ADD(3, t6a, t6b);
             StageSlot& G = S.stage[ss];
             const uint32_t fl = (have ? kStHave : 0u) | (ok ? kStOk : 0u) | (noat ? kStNoAt : 0u) | (matched ? kStMatched : 0u) |
                                 (complete ? kStComplete : 0u) | (err_code << 8);
