@@ -267,15 +267,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 constexpr uint32_t kMbarSuspendNs = 20000u;
+#ifndef SSD_MBAR_SLEEP_NS
+#define SSD_MBAR_SLEEP_NS 0
+#endif
+// SLEEP: nanoseconds to stay away from the issue slots after a failed try (0 = poll again at once).  Waiting warps that poll
+// back to back take issue slots from the working ones: the polls were 12-19 % of the scans' warp instructions.
+template <uint32_t SLEEP = SSD_MBAR_SLEEP_NS>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok = 0;
-    while (!ok) {
+    while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)  // the thread may stay suspended this long before it polls again
             : "memory");
+        if (ok) break;
+        if (SLEEP) __nanosleep(SLEEP);
     }
 }
 
