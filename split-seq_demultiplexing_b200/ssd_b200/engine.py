@@ -39,6 +39,27 @@ class _DevArray:
         self._owner = owner
 
 
+class _SplitTable:
+    """The bucket index of split mode as a read-only sequence of (cell string, first byte, None, n bytes).  The arrays stay in
+    numpy (hundreds of thousands of buckets at full size: the tuples and cell strings are made when somebody asks)."""
+
+    def __init__(self, owner, cells, offs, sizes):
+        self._owner, self.cells, self.offsets, self.sizes = owner, cells, offs, sizes
+
+    def __len__(self):
+        return int(self.cells.size)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        if k < 0:
+            k += len(self)
+        return (self._owner.cell_string(int(self.cells[k])), int(self.offsets[k]), None, int(self.sizes[k]))
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+
 class Demultiplexer:
     """One library context = one GPU.  Mirrors the knobs of V2.demultiplex_fun / calc_demux_results."""
 
@@ -251,12 +272,9 @@ class Demultiplexer:
         if nb.value:
             self._check(self.lib.ssd_split_index(self._ctx, cells.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
                                                  first.ctypes.data_as(C.c_void_p), nb.value))
-        table = []
-        self._split_ids = [int(c) for c in cells]  # cell ids of the buckets, in table order
-        for b in range(nb.value):
-            end_off = int(offs[b + 1]) if b + 1 < nb.value else n.value
-            table.append((self.cell_string(int(cells[b])), int(offs[b]), None, end_off - int(offs[b])))
-        return n.value, table, first
+        self._split_ids = cells  # cell ids of the buckets, in table order (numpy)
+        sizes = np.diff(np.append(offs, np.uint64(n.value))).astype(np.uint64) if nb.value else offs
+        return n.value, _SplitTable(self, cells, offs, sizes), first
 
     def write_split_files(self, out_dir: str, round_names=None, stats: Optional[dict] = None) -> List[Tuple[str, int]]:
         """Split mode on disk: after a run, one FASTQ file per passing cell holding that cell's annotated
@@ -274,7 +292,7 @@ class Demultiplexer:
         del out
         os.makedirs(out_dir, exist_ok=True)
         jobs = []
-        for (_, off, _, nbytes), cid in zip(table, self._split_ids):
+        for off, nbytes, cid in zip(table.offsets.tolist(), table.sizes.tolist(), table.cells.tolist()):
             i1, i2, i3 = self.cell_indices(cid)
             name = (hostlogic.split_file_name(round_names, i1, i2, i3) if round_names is not None
                     else "%s-%s-%s.fastq" % (self.rounds[0][i1], self.rounds[1][i2], self.rounds[2][i3]))
