@@ -139,8 +139,25 @@ struct GlobAcc {  // the whole file in global memory (slow path for records that
     size_t len;
     __device__ __forceinline__ bool covers(size_t g) const { return g < len; }
     __device__ __forceinline__ uint32_t byte(size_t g) const { return buf[g]; }
+    // 16 bytes per load once g is aligned (the buffer is 16-byte aligned, ssd_b200.h): the exact path of a record is a chain of
+    // dependent loads, one per byte costs tens of microseconds per record
     __device__ __forceinline__ size_t next_nl(size_t g) const
     {
+        while (g < len && (g & 15u)) {
+            if (buf[g] == '\n') return g;
+            g++;
+        }
+        while (g + 16 <= len) {
+            const uint4 v = *reinterpret_cast<const uint4*>(buf + g);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t t = w[k] ^ 0x0A0A0A0Au;
+                const uint32_t f = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);  // 0x80 in every '\n' byte, exact
+                if (f) return g + 4u * (uint32_t)k + (((uint32_t)__ffs((int)f) - 1u) >> 3);
+            }
+            g += 16;
+        }
         while (g < len && buf[g] != '\n') g++;
         return g;
     }

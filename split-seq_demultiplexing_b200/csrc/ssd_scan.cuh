@@ -499,6 +499,21 @@ struct __align__(128) ScanSmem {
 #define SSD_SCAN_SPECULATE(mode) ((mode) != kScanR2)
 #endif
 
+// -DSSD_ASSERT: invariants of the warp-specialised scan checked on the device (a violation traps: every later call fails with a
+// CUDA error).  compute-sanitizer is not available on the GPU pool, so the parity and fuzz suites are run once per round against
+// a library built this way (profiles/run_assert.sh); off in the shipped build.
+#ifdef SSD_ASSERT
+#define SSD_CHECK(cond)                                                                                   \
+    do {                                                                                                  \
+        if (!(cond)) {                                                                                    \
+            printf("SSD_ASSERT %s:%d block %d thread %d: %s\n", __FILE__, __LINE__, blockIdx.x, threadIdx.x, #cond); \
+            __trap();                                                                                     \
+        }                                                                                                 \
+    } while (0)
+#else
+#define SSD_CHECK(cond)
+#endif
+
 #ifdef SSD_SCAN_PROFILE
 __device__ unsigned long long g_scan_prof[2][16];
 #define PROF_T(var) const long long var = clock64()
@@ -636,7 +651,9 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             const StageSlot& G = S.stage[ss];
             for (uint32_t i = (uint32_t)lane; i < n_rec; i += 32u) {
                 const uint64_t r = r_first + i;
+                SSD_CHECK(i < (uint32_t)kBThreads);
                 const uint32_t sf = G.s0f[i], s0 = sf & 0xFFFFu, fl = sf >> 16;
+                SSD_CHECK(!(fl & kStOk) || r >= args.rec_cap || tile_lo + s0 < args.len);
                 const bool have = fl & kStHave, ok2 = (fl & kStOk) && r < args.rec_cap;  // beyond the capacity: the exact path raises the overflow flag
                 if (MODE == kScanR1) {
                     if (ok2) {
@@ -755,6 +772,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                 break;
             }
             const size_t tile_lo = (size_t)t * kTile;
+            SSD_CHECK(tile_lo < args.len);
             const uint32_t wb = (uint32_t)(args.len - tile_lo < (size_t)kWin ? args.len - tile_lo : (size_t)kWin);
             const uint32_t bulk = wb & ~15u;
             for (uint32_t i = bulk + lane; i < wb; i += 32u) S.win[ws][i] = args.buf[tile_lo + i];
@@ -895,6 +913,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
         sync_a();  // list complete; warp_tile / halo_sum / mask may be reused
         PROF_T(t2d);
         PROF_ADD(13, t2c, t2d);
+        SSD_CHECK(total <= (uint32_t)kTile && halo_total <= (uint32_t)kHalo + 64u && S.list_tile[ls] == tile);
         if (tid == 0) mbar_arrive(&S.list_done[ls]);  // over to the guess warp, then to stage B
         PROF_T(t3);
         PROF_ADD(2, t2, t3);
@@ -960,12 +979,15 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             s0 = 0;
             bool fast = false;
             if (have) {
+                SSD_CHECK(j0 <= n_listed && j0 < (uint32_t)kMaxLines);
                 s0 = s_lstart[j0];
+                SSD_CHECK(s0 <= (uint32_t)kTile && s0 <= win_bytes);  // a record of the tile starts inside the tile
                 if (j0 + (MODE == kScanR2 ? 3u : 4u) <= n_listed) {
                     s1 = s_lstart[j0 + 1];
                     s2 = s_lstart[j0 + 2];
                     s3 = s_lstart[j0 + 3];
                     if (MODE != kScanR2) s4 = s_lstart[j0 + 4];
+                    SSD_CHECK(s0 < s1 && s1 < s2 && s2 < s3 && s3 <= win_bytes && (MODE == kScanR2 || (s3 < s4 && s4 <= win_bytes)));
                     // read 2 only needs line 3 to exist; the generic path raises the overflow flag
                     fast = MODE != kScanR2 || tile_lo + s3 < args.len;
                 }
@@ -1276,6 +1298,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             PROF_T(t6b);
             PROF_ADD(3, t6a, t6b);
             StageSlot& G = S.stage[ss];
+            SSD_CHECK(my_i < (uint32_t)kBThreads && ss < (uint32_t)kStageSlots && (!have || n_guess <= (uint32_t)kBThreads));
             const uint32_t fl = (have ? kStHave : 0u) | (ok ? kStOk : 0u) | (noat ? kStNoAt : 0u) | (matched ? kStMatched : 0u) |
                                 (complete ? kStComplete : 0u) | (err_code << 8);
             G.s0f[my_i] = s0 | (fl << 16);
