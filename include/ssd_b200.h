@@ -177,6 +177,8 @@ int ssd_annotated_file(ssd_ctx *ctx, const char *path_in, const char *out_path, 
  *                         SSD_ERANGE when `capacity` entries do not suffice. */
 int ssd_load_file_range(ssd_ctx *ctx, int slot, const char *path, uint64_t offset, uint64_t length);
 int ssd_loaded_newlines(ssd_ctx *ctx, int slot, int tile_log2, uint32_t *tile_counts, uint64_t capacity, uint64_t *n_tiles);
+/* '\n' bytes of any text on the device (16-byte aligned): what a caller checks an output with (four lines per record). */
+int ssd_count_newlines_device(ssd_ctx *ctx, const void *d_text, size_t len, uint64_t *total);
 int ssd_demux_loaded(ssd_ctx *ctx);
 int ssd_annotated_loaded(ssd_ctx *ctx);
 int ssd_emit_file(ssd_ctx *ctx, int which, const char *out_path, int append, size_t *written);

@@ -1857,6 +1857,26 @@ extern "C" int ssd_anchor_positions(const void* d_text, size_t len, uint32_t n_l
     return ok ? SSD_OK : SSD_ECUDA;
 }
 
+extern "C" int ssd_count_newlines_device(ssd_ctx* c, const void* d_text, size_t len, uint64_t* total)
+{
+    if (!c || !total || (len && !d_text)) return SSD_EINVAL;
+    if ((uintptr_t)d_text & 15u) return fail(c, SSD_EINVAL, "ssd_count_newlines_device: the buffer must be 16-byte aligned");
+    CU(c, cudaSetDevice(c->device));
+    *total = 0;
+    const int tile_log2 = 22;
+    const uint64_t tiles = (len + (1ull << tile_log2) - 1) >> tile_log2;
+    if (tiles == 0) return SSD_OK;
+    OKR(ensure(c, c->b_first, tiles * sizeof(uint32_t)));
+    k_count_newlines<<<(uint32_t)tiles, 256, 0, c->stream>>>((const uint8_t*)d_text, len, tile_log2, (uint32_t*)c->b_first.p);
+    c->n_launches++;
+    CU(c, cudaGetLastError());
+    std::vector<uint32_t> h(tiles);
+    CU(c, cudaMemcpyAsync(h.data(), c->b_first.p, tiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (uint32_t v : h) *total += v;
+    return SSD_OK;
+}
+
 extern "C" int ssd_loaded_newlines(ssd_ctx* c, int slot, int tile_log2, uint32_t* tile_counts, uint64_t capacity, uint64_t* n_tiles)
 {
     if (!c || slot < 0 || slot > 1 || tile_log2 < 12 || tile_log2 > 30 || !n_tiles) return SSD_EINVAL;

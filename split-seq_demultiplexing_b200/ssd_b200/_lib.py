@@ -121,6 +121,7 @@ _SIGS = {
     "ssd_cell_umi_table": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "ssd_anchor_positions": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "ssd_count_newlines_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
     "ssd_loaded_newlines": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "ssd_pack_decision": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "ssd_undecided_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),

@@ -307,13 +307,18 @@ def demux_batches(dm, batches, world: int = 1, group=None, which: int = None, si
             del r1, r2
             yield dev
 
+    held = {"out": None}  # one output buffer for all batches, grown when a batch needs more: tens of GB are not given back and
+                          # asked for again batch after batch
+
     def emit(dev, st):
         need = st["bytes_matched"] if which == L.EMIT_MATCHED else st["bytes_passing"]
-        out = torch.empty(need + 16, dtype=torch.uint8, device=dev)
+        if held["out"] is None or held["out"].numel() < need + 16:
+            held["out"] = None
+            held["out"] = torch.empty(need + 16 + need // 64, dtype=torch.uint8, device=dev)
+        out = held["out"]
         n = dm.emit_device(which, out.data_ptr(), out.numel())
         if sink is not None:
             sink(out[:n], st)
-        del out
 
     return two_pass(dm, phase1, emit, world=world, group=group, timing=timing)
 

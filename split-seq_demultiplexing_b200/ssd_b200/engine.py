@@ -309,6 +309,12 @@ class Demultiplexer:
         with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:  # every cell has its own file: no two threads share one
             return list(pool.map(put, jobs, chunksize=256))
 
+    def count_newlines(self, text) -> int:
+        """Number of line feeds in a uint8 CUDA tensor (16-byte aligned): the framing check of an output, at memory speed."""
+        n = C.c_uint64()
+        self._check(self.lib.ssd_count_newlines_device(self._ctx, C.c_void_p(text.data_ptr() if text.numel() else 0), text.numel(), C.byref(n)))
+        return n.value
+
     def record_cells(self):
         import numpy as np
         n = C.c_uint64()
@@ -560,12 +566,18 @@ def synth_host(spec) -> Tuple[bytes, bytes]:
     return b1.raw[:n1], b2.raw[:n2]
 
 
-def synth_device(dm: Demultiplexer, spec):
-    """Generate on dm's GPU; returns two uint8 CUDA tensors."""
+def synth_device(dm: Demultiplexer, spec, into=None):
+    """Generate on dm's GPU; returns two uint8 CUDA tensors.  into = (buffer 1, buffer 2): uint8 CUDA tensors of at least
+    synth_sizes(spec) + 16 bytes to generate into (batch after batch into the same memory), else two new tensors."""
     import torch
     n1, n2 = synth_sizes(spec)
-    t1 = torch.empty(n1 + 16, dtype=torch.uint8, device="cuda")
-    t2 = torch.empty(n2 + 16, dtype=torch.uint8, device="cuda")
+    if into is not None:
+        t1, t2 = into
+        if t1.numel() < n1 + 16 or t2.numel() < n2 + 16:
+            raise ValueError("synth_device: the buffers are too small for this batch")
+    else:
+        t1 = torch.empty(n1 + 16, dtype=torch.uint8, device="cuda")
+        t2 = torch.empty(n2 + 16, dtype=torch.uint8, device="cuda")
     rc = dm.lib.ssd_synth_generate_device(dm._ctx, C.byref(spec), C.c_void_p(t1.data_ptr()), C.c_void_p(t2.data_ptr()))
     dm._check(rc)
     return t1[:n1], t2[:n2]

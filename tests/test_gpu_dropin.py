@@ -317,3 +317,13 @@ def test_device_learner_empty_raises_value_error(tmp_path):
     p.write_bytes(b"")
     with pytest.raises(ValueError):
         hostlogic.learn_positions_device(str(p))
+
+
+def test_count_newlines_on_the_device():
+    import torch
+    import ssd_b200
+    r1 = fu.load_bundled()[0]
+    dm = ssd_b200.Demultiplexer(WL)
+    for data in (r1, r1[:12345], b"", b"\n" * 100, b"no newline at all"):
+        t = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda() if data else torch.empty(0, dtype=torch.uint8, device="cuda")
+        assert dm.count_newlines(t) == data.count(b"\n")
