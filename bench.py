@@ -498,6 +498,14 @@ def measure_batches(env, cid, cfg, args):
             e1.record()
             e1.synchronize()
             gen_ms[0] += e0.elapsed_time(e1)
+            if env.world > 1:
+                # the ranks' generators do not take the same time: without this, the first collective of the batch would wait
+                # for the slowest generator and the wait would count as the job's time
+                import torch.distributed as dist
+                tb = time.perf_counter()
+                dist.barrier()
+                torch.cuda.synchronize()
+                gen_ms[0] += (time.perf_counter() - tb) * 1e3
             yield d
             del d
             done += nb
