@@ -320,3 +320,46 @@ def test_global_filter_decides_like_one_process(tmp_path, world, exact):
         if exact != 1:
             assert 0 < got[3] < got[4] // 4                        # only the undecided cells' keys were sent
             assert (got[3] > 64) == (exact == 2) or exact == 0
+
+
+def _plan_worker(rank, world, port, out_dir, paths):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ssd_b200 import filebatch
+    filebatch.TILE_LOG2 = 12
+
+    def count(path, offset, length):  # CPU stand-in for filebatch.device_tile_counts (the library counts on the GPU)
+        with open(path, "rb") as fh:
+            fh.seek(offset)
+            buf = np.frombuffer(fh.read(length), dtype=np.uint8)
+        t = 1 << filebatch.TILE_LOG2
+        return np.array([int((buf[k:k + t] == 10).sum()) for k in range(0, len(buf), t)], dtype=np.uint32)
+
+    def allgather(values):
+        parts = [None] * world
+        dist.all_gather_object(parts, [int(x) for x in values])
+        return parts
+    plan = filebatch.plan_shards_device(paths[0], paths[1], world, rank, count, count, allgather, target_bytes=90000)
+    np.save(os.path.join(out_dir, "plan_%d.npy" % rank), np.array([b for per_rank in plan for b in per_rank], dtype=np.int64))
+    dist.destroy_process_group()
+
+
+def test_shard_plan_over_two_processes(tmp_path):
+    """plan_shards_device with the real collective (all_gather_object over gloo, two processes): every rank counts only its own
+    byte ranges, both derive the same plan, and every batch starts at the same record of both files."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fastq_util as fu
+    r1, r2 = fu.load_bundled()
+    p1, p2 = tmp_path / "a.fastq", tmp_path / "b.fastq"
+    p1.write_bytes(r1)
+    p2.write_bytes(r2)
+    mp.spawn(_plan_worker, args=(2, _free_port(), str(tmp_path), (str(p1), str(p2))), nprocs=2, join=True)
+    plans = [np.load(os.path.join(str(tmp_path), "plan_%d.npy" % r)) for r in range(2)]
+    assert (plans[0] == plans[1]).all() and len(plans[0]) >= 8
+    flat = plans[0].tolist()
+    assert flat[0][0] == 0 and flat[0][2] == 0 and flat[-1][0] + flat[-1][1] == len(r1) and flat[-1][2] + flat[-1][3] == len(r2)
+    for (o1, n1, o2, n2), nxt in zip(flat, flat[1:] + [None]):
+        assert r1[o1:o1 + n1].count(b"\n") == r2[o2:o2 + n2].count(b"\n") and r1[o1:o1 + n1].count(b"\n") % 4 == 0
+        assert nxt is None or (o1 + n1 == nxt[0] and o2 + n2 == nxt[2])
