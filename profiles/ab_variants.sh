@@ -7,9 +7,6 @@
 #   bash profiles/ab_variants.sh clean
 VARIANTS=(
   "base||0"
-  "g2t16|-DSSD_SCAN_TILE=16384 -DSSD_SCAN_SLOTS=4 -DSSD_SCAN_BGROUPS=2|1"
-  "g3t16a4|-DSSD_SCAN_TILE=16384 -DSSD_SCAN_SLOTS=5 -DSSD_SCAN_BGROUPS=3 -DSSD_SCAN_BWARPS=6 -DSSD_SCAN_AWARPS=4|0"
-  "g2t16s5|-DSSD_SCAN_TILE=16384 -DSSD_SCAN_SLOTS=5 -DSSD_SCAN_BGROUPS=2|0"
 )
 root=$(cd "$(dirname "$0")/.." && pwd)
 src=$root/split-seq_demultiplexing_b200/csrc

@@ -1,11 +1,12 @@
 // ssd_scan.cuh — single-pass FASTQ record-boundary scan fused with the per-record work (sm_100a).
 //
-// Persistent, warp-specialised blocks (one wave, two per SM) take 24 KiB tiles of the file by ticket.  A copy warp keeps
-// the tiles (plus a 2 KiB halo) arriving in shared memory with bulk copies (TMA); stage A turns newlines into a bitmap
-// through 16-byte vector loads, publishes the tile's newline count (a prefix warp chains the counts into global line
-// indices: decoupled look-back) and lists the line starts; stage B processes every record that starts in the tile, one
-// thread per record, from shared memory, guessing the record phase so that it never waits for the line index; a commit
-// warp writes the parked results out under their record numbers once the index has arrived:
+// Persistent, warp-specialised blocks (one wave, two per SM, 16 warps each) take 24 KiB tiles of the file by ticket.  A copy
+// warp keeps the tiles (plus a 2 KiB halo) arriving in shared memory with bulk copies (TMA); stage A (8 warps) turns newlines
+// into a bitmap through 16-byte vector loads, publishes the tile's newline count (a prefix warp chains the counts into global
+// line indices: decoupled look-back) and lists the line starts; a guess warp guesses the record phase of the tile from the
+// list; stage B (4 warps) processes every record that starts in the tile, one thread per record, from shared memory, on that
+// guess, so that it never waits for the line index, and parks the results; a commit warp checks the guess and writes the parked
+// results out under their record numbers once the index has arrived:
 //   read 1: record offset + a 16-byte descriptor the writer needs (V2:134-141, 246, 249), read-id fingerprint
 //   read 2: UMI / barcode extraction (V2:293-301), first-hit Hamming matching (V2:302-304, 327-329),
 //           mate-id check (V2:350), per-cell histogram, (cell, UMI) keys
