@@ -698,9 +698,9 @@ def main():
     cpu_baseline = None
     if env.rank == 0 and env.world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        # about 10-30 s of CPU work: a quick probe gives the box's rate, the sample is sized for ~12 s (2 M .. 8 M pairs)
+        # about 10-30 s of CPU work: a quick probe gives the box's rate, the sample is sized for ~12 s (2 M .. 6 M pairs: <= 13 GB of host memory)
         probe, _ = oracle_rate(cfg, min(200_000, cfg_pairs(cfg)), cores)
-        n_sample = min(int(os.environ.get("SSD_BENCH_CPU_PAIRS", max(2_000_000, min(8_000_000, int(12 * probe))))), cfg_pairs(cfg))
+        n_sample = min(int(os.environ.get("SSD_BENCH_CPU_PAIRS", max(2_000_000, min(6_000_000, int(12 * probe))))), cfg_pairs(cfg))
         rate, times = oracle_rate(cfg, n_sample, cores)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "first %d pairs of the same synthetic workload, one pass, %d worker threads; C restatement of the "
