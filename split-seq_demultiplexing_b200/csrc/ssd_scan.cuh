@@ -19,8 +19,16 @@
 // against global memory.
 #pragma once
 #include "ssd_device.cuh"
+#include "ssd_match.cuh"
 
 namespace ssd {
+
+// 1: a read 2 whose sequence ends before the last slice does (and any window with several bytes outside ACGT) stays on the
+// fast path -- its windows are matched by the whole warp against the whitelist (coop_first_hit) instead of the record going
+// through the exact path, one thread against global memory.  0: the round-1 behaviour.
+#ifndef SSD_SCAN_SHORT_FAST
+#define SSD_SCAN_SHORT_FAST 0
+#endif
 
 #ifndef SSD_SCAN_TILE
 #define SSD_SCAN_TILE 24576
@@ -97,14 +105,7 @@ __device__ __forceinline__ uint32_t lt_flags(uint32_t x, uint32_t n4) { return ~
 // flags of the bytes [lo, hi) of a word
 __device__ __forceinline__ uint32_t byte_range_flags(uint32_t lo, uint32_t hi) { return (0x80808080u << (8u * lo)) & (0x80808080u >> (8u * (4u - hi))); }
 
-// four bases -> 8-bit 2-bit code (position j at bits 2j); `bad` collects x ^ (the bases those codes stand for)
-__device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t& diff)
-{
-    uint32_t y = (x >> 1) & 0x03030303u;
-    uint32_t sel = (y & 0x3u) | ((y >> 4) & 0x30u) | ((y >> 8) & 0x300u) | ((y >> 12) & 0x3000u);
-    diff = x ^ __byte_perm(0x47544341u, 0u, sel);  // A C T G by code
-    return (y * 0x01041040u) >> 24;
-}
+// pack4 (four bases -> 2-bit codes + the bytes that are not bases): ssd_match.cuh
 
 __device__ __forceinline__ void load8(const uint32_t* words, uint32_t p, uint32_t& a, uint32_t& b)
 {
@@ -430,6 +431,34 @@ __device__ __forceinline__ int match8(const DevCfg& cfg, int round, const uint8_
     return -1;
 }
 
+// First-hit index for the windows the lookup tables do not answer (short read 2: zip() truncation, V2:72-73; several bytes
+// outside ACGT), searched by the whole warp: the lanes that ask (`need`) take turns, 32 whitelist entries are tested at a time
+// (codes = the round's 2-bit whitelist codes in shared memory), the lowest hit wins.  All 32 lanes call; -1 = no entry within e.
+__device__ __forceinline__ int coop_first_hit(const uint16_t* codes, int n_wl, uint32_t e, bool need, uint32_t code, uint32_t valid, uint32_t k, int lane)
+{
+    int res = -1;
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, need);
+    while (todo) {
+        const int src = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        const uint32_t c = __shfl_sync(0xFFFFFFFFu, code, src), v = __shfl_sync(0xFFFFFFFFu, valid, src), kk = __shfl_sync(0xFFFFFFFFu, k, src);
+        int hit = -1;
+        if (kk <= e) {
+            for (int base = 0; base < n_wl; base += 32) {
+                const int i = base + lane;
+                const bool h = i < n_wl && masked_hit(c, codes[i], v, kk, e);
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, h);
+                if (b) {
+                    hit = base + __ffs((int)b) - 1;
+                    break;
+                }
+            }
+        }
+        if (lane == src) res = hit;
+    }
+    return res;
+}
+
 constexpr int kScanR1 = 0;
 constexpr int kScanR2 = 1;
 constexpr int kScanAnn = 2;  // an already annotated FASTQ (MergedCells_1.fastq): V2.calc_demux_results
@@ -493,6 +522,9 @@ struct __align__(128) ScanSmem {
     uint32_t guess_j[kListSlots], guess_n[kListSlots];  // the guess warp's guess of the record phase of the tile (stage B takes it from here)
     uint32_t warp_tile[kAWarps], halo_sum[2];
     alignas(16) uint32_t mask[kWinWords];     // newline bitmap of the tile in stage A (bit b of word w = byte 32 w + b)
+#if SSD_SCAN_SHORT_FAST
+    uint16_t wl_code[3][kMaxWl];              // read 2: the 2-bit whitelist codes of the three rounds (coop_first_hit)
+#endif
 };
 
 // which scans run the per-record work ahead of the line index (read 2 is issue-bound: nothing to hide there)
@@ -559,6 +591,10 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             mbar_init(reinterpret_cast<uint64_t*>(&S.stage_empty[s]), 1);
         }
     }
+#if SSD_SCAN_SHORT_FAST
+    if (MODE == kScanR2)
+        for (int i = tid; i < 3 * kMaxWl; i += kScanThreads) S.wl_code[i / kMaxWl][i % kMaxWl] = cfg.wl_code[i / kMaxWl][i % kMaxWl];
+#endif
     __syncthreads();
     volatile unsigned long long* st = args.status;
 
@@ -1000,12 +1036,16 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             uint32_t code1 = 0, code2 = 0, code3 = 0, dirty = 0, w_seq_e = s2 - 1u;
             uint32_t v1 = 0xFFu, v2 = 0xFFu, v3 = 0xFFu, x0 = 0xFFu, x1 = 0xFFu, x2 = 0xFFu, x3 = 0xFFu;  // x*: the four lookups of the one dirty window
             uint32_t da0 = 0, da1 = 0, db0 = 0, db1 = 0, dc0 = 0, dc1 = 0;
-            bool win_ok = false;
+            bool win_ok = false, shortseq = false;
             if (MODE == kScanR2) {
                 win_ok = fast && cfg.fast_wl != 0 && cfg.fast_geom != 0;
                 if (win_ok) win_ok = rstrip2(s_win, s1, w_seq_e);
+#if SSD_SCAN_SHORT_FAST
+                shortseq = win_ok && w_seq_e - s1 < (uint32_t)cfg.need_len;  // truncated read 2: its windows are matched by the warp below
+#else
                 if (win_ok) win_ok = w_seq_e - s1 >= (uint32_t)cfg.need_len;  // truncated read 2 goes the exact way
-                if (win_ok) {
+#endif
+                if (win_ok && !shortseq) {
                     uint32_t y0, y1;
                     load8(words, s1 + (uint32_t)cfg.b1s, y0, y1);
                     code1 = pack4(y0, da0) | (pack4(y1, da1) << 8);
@@ -1166,10 +1206,52 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             } else {
                 // ---- lineRead = line.rstrip(); the four windows (V2:293-301): requested above, answered by now ----
                 ok = win_ok && bad == 0u;
+#if SSD_SCAN_SHORT_FAST
+                // the windows the tables did not answer -- all three of a short sequence (lineRead[s:e] gives what is there, hamming()
+                // zips to the shorter operand: V2:72-73, 296-301), and dirty windows beyond the one-N case -- go to the whole warp
+                const uint32_t seq_len = w_seq_e - s1;
+                int c1 = -1, c2 = -1, c3 = -1;
+                {
+                    const uint32_t ask = !ok ? 0u : (shortseq ? 7u : ((dirty & 8u) ? 0u : (dirty & 7u)));
+                    if (__any_sync(0xFFFFFFFFu, ask != 0u)) {
+#pragma unroll
+                        for (int rd = 0; rd < 3; rd++) {
+                            const bool need = ((ask >> rd) & 1u) != 0u;
+                            uint32_t c = 0, v = 0, kk = 0;
+                            if (need) {
+                                if (shortseq) {
+                                    const uint32_t bs = (uint32_t)(rd == 0 ? cfg.b1s : (rd == 1 ? cfg.b2s : cfg.b3s));
+                                    const uint32_t n = seq_len > bs ? min(seq_len - bs, 8u) : 0u;  // bytes of the window that exist
+                                    if (n) {
+                                        uint32_t y0, y1, q0, q1;
+                                        load8(words, s1 + bs, y0, y1);
+                                        c = pack4(y0, q0) | (pack4(y1, q1) << 8);
+                                        window_masks(q0, q1, n, v, kk);
+                                    }
+                                } else {
+                                    c = rd == 0 ? code1 : (rd == 1 ? code2 : code3);
+                                    window_masks(rd == 0 ? da0 : (rd == 1 ? db0 : dc0), rd == 0 ? da1 : (rd == 1 ? db1 : dc1), 8u, v, kk);
+                                }
+                            }
+                            const int hit = coop_first_hit(S.wl_code[rd], cfg.n_wl[rd], (uint32_t)cfg.e, need, c, v, kk, lane);
+                            if (rd == 0) c1 = hit;
+                            else if (rd == 1) c2 = hit;
+                            else c3 = hit;
+                        }
+                    }
+                }
+#endif
                 if (ok) {
                     complete = true;
                     noat = s_win[s0] != '@';
                     int i1 = v1 == 0xFFu ? -1 : (int)v1, i2 = v2 == 0xFFu ? -1 : (int)v2, i3 = v3 == 0xFFu ? -1 : (int)v3;
+#if SSD_SCAN_SHORT_FAST
+                    if (shortseq) {
+                        i1 = c1;
+                        i2 = c2;
+                        i3 = c3;
+                    } else
+#endif
                     if (dirty) {  // some window holds a byte that is not A/C/G/T
                         if (dirty & 8u) {
                             const uint32_t best = min(min(x0, x1), min(x2, x3));
@@ -1178,19 +1260,30 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                             if (dirty & 2u) i2 = ix;
                             if (dirty & 4u) i3 = ix;
                         } else {
+#if SSD_SCAN_SHORT_FAST
+                            if (dirty & 1u) i1 = c1;
+                            if (dirty & 2u) i2 = c2;
+                            if (dirty & 4u) i3 = c3;
+#else
                             if (dirty & 1u) i1 = match8(cfg, 0, args.lut, code1, da0, da1);
                             if (dirty & 2u) i2 = match8(cfg, 1, args.lut, code2, db0, db1);
                             if (dirty & 4u) i3 = match8(cfg, 2, args.lut, code3, dc0, dc1);
+#endif
                         }
                     }
                     matched = i1 >= 0 && i2 >= 0 && i3 >= 0;  // V2:310-321: all three lists non-empty (the mate check follows in commit())
                     if (matched) {
                         const uint32_t cell = cell_of(cfg, i1, i2, i3);
-                        // UMI = lineRead[umi_start:umi_end] verbatim (V2:295)
+                        // UMI = lineRead[umi_start:umi_end] verbatim (V2:295): what the sequence holds of it
+#if SSD_SCAN_SHORT_FAST
+                        const uint32_t ulo = min((uint32_t)cfg.us, seq_len), uhi = min((uint32_t)cfg.ue, seq_len);
+                        const uint32_t up = s1 + ulo, ul = uhi - ulo;
+#else
                         const uint32_t up = s1 + (uint32_t)cfg.us;
+                        const uint32_t ul = (uint32_t)cfg.umi_len;
+#endif
                         const uint32_t i0 = up >> 2, sh = (up & 3u) * 8u;
                         const uint32_t w0 = words[i0], w1 = words[i0 + 1], w2 = words[i0 + 2], w3 = words[i0 + 3];
-                        const uint32_t ul = (uint32_t)cfg.umi_len;
                         const uint32_t m0 = ul >= 4u ? 0xFFFFFFFFu : (1u << (8u * ul)) - 1u;
                         const uint32_t m1 = ul >= 8u ? 0xFFFFFFFFu : (ul > 4u ? (1u << (8u * (ul - 4u))) - 1u : 0u);
                         const uint32_t m2 = ul > 8u ? (1u << (8u * (ul - 8u))) - 1u : 0u;
@@ -1199,7 +1292,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                         uint32_t e0, e1, e2;
                         const uint64_t ucode = ((uint64_t)pack4(u0, e0) | ((uint64_t)pack4(u1, e1) << 8) | ((uint64_t)pack4(u2, e2) << 16)) &
                                                ((1ull << cfg.umi_bits) - 1ull);
-                        if (((e0 & m0) | (e1 & m1) | (e2 & m2)) == 0u) {
+                        if (ul == (uint32_t)cfg.umi_len && ((e0 & m0) | (e1 & m1) | (e2 & m2)) == 0u) {
                             o.ann = kAnnRegular | ((uint64_t)cell << kAnnCellShift) | ucode;
                         } else {
                             o.ann = kAnnIrregular | ((uint64_t)cell << kAnnCellShift) | ((uint64_t)(tile_lo + up) << 5) | (uint64_t)ul;
