@@ -314,6 +314,12 @@ int ssd_read_timings(ssd_ctx *ctx, double *ms_per_stage, uint32_t *spans_per_sta
 uint64_t ssd_launch_count(const ssd_ctx *ctx);
 /* Diagnostics: how many times a scan had to be repeated without guessing the record phase. */
 int ssd_scan_repeats(const ssd_ctx *ctx, uint64_t *n);
+/* Diagnostics: which read-2 scan the NEXT batch of this context runs (*short_fast = 1: the variant that keeps short read-2
+ * sequences -- V2:296-301 slices past the end, hamming() zips to the shorter operand, V2:72-73 -- and windows with several
+ * non-ACGT bytes on the fast path), and how many read-2 records of the LAST batch took the exact record-by-record path.  A
+ * context starts without and switches when a batch sent more than 1 record in 1 000 that way (SSD_SCAN_SHORT=0/1 pins it).
+ * Results are the same bytes either way.  Either pointer may be NULL. */
+int ssd_scan_variant(const ssd_ctx *ctx, int *short_fast, uint64_t *exact_records);
 
 /* ---- synthetic read pairs (bench / tests) ---------------------------------------- */
 typedef struct ssd_synth_spec {

@@ -104,6 +104,11 @@ struct ssd_ctx {
     uint64_t rec_cap = 0;
     uint64_t n_rec_r1 = 0, n_rec_r2 = 0, n_rec = 0, n_keys = 0, n_irr = 0;
     bool defer1 = true, defer2 = true;  // scan variant per file: park-and-commit, or (after a failed guess) wait for the line index
+    // read-2 scan variant that keeps short sequences and windows with several non-ACGT bytes on the fast path (k_scan<.., SHORT>):
+    // off until a batch sends more than 1 record in 1 000 down the exact path, then on for the next batches of this context
+    // (SSD_SCAN_SHORT=1: on from the first batch, =0: never)
+    bool short2 = false, short_auto = true;
+    uint64_t n_exact_last = 0;  // read-2 records of the last batch that took the exact path
     uint32_t emit_grid = 148;
     uint64_t n_respec = 0;  // scans repeated without guessing (diagnostics)
     bool phase1_done = false, filter_done = false, unique_done = false;
@@ -548,6 +553,32 @@ int distinct_counts_local(ssd_ctx* c)
     return SSD_OK;
 }
 
+// The scan kernel for a file: the one table the launches AND the shared-memory attributes are taken from.
+template <typename OffT>
+using ScanFn = void (*)(const ScanArgs<OffT>, const DevCfg);
+
+template <typename OffT>
+ScanFn<OffT> scan_kernel(int mode, bool defer, bool shrt)
+{
+    if (mode == kScanR1) return defer ? k_scan<kScanR1, OffT, true, false> : k_scan<kScanR1, OffT, false, false>;
+    if (mode == kScanAnn) return defer ? k_scan<kScanAnn, OffT, true, false> : k_scan<kScanAnn, OffT, false, false>;
+    if (shrt) return defer ? k_scan<kScanR2, OffT, true, true> : k_scan<kScanR2, OffT, false, true>;
+    return defer ? k_scan<kScanR2, OffT, true, false> : k_scan<kScanR2, OffT, false, false>;
+}
+
+template <typename OffT>
+cudaError_t scan_kernel_attributes()
+{
+    for (int mode : {kScanR1, kScanR2, kScanAnn})
+        for (int defer = 0; defer < 2; defer++)
+            for (int shrt = 0; shrt < 2; shrt++) {
+                cudaError_t e = cudaFuncSetAttribute((const void*)scan_kernel<OffT>(mode, defer != 0, shrt != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)sizeof(ScanSmem));
+                if (e != cudaSuccess) return e;
+            }
+    return cudaSuccess;
+}
+
 template <typename OffT>
 int launch_scans(ssd_ctx* c, bool defer1, bool defer2)
 {
@@ -574,8 +605,7 @@ int launch_scans(ssd_ctx* c, bool defer1, bool defer2)
             a.status = (unsigned long long*)c->b_status1.p;
             a.n_tiles = nt1;
             StageTimer t(c, 0);
-            if (defer1) k_scan<kScanAnn, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
-            else k_scan<kScanAnn, OffT, false><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+            scan_kernel<OffT>(kScanAnn, defer1, false)<<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
             c->n_launches++;
         }
         CU(c, cudaGetLastError());
@@ -587,8 +617,7 @@ int launch_scans(ssd_ctx* c, bool defer1, bool defer2)
         a.status = (unsigned long long*)c->b_status1.p;
         a.n_tiles = nt1;
         StageTimer t(c, 0);
-        if (defer1) k_scan<kScanR1, OffT, true><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
-        else k_scan<kScanR1, OffT, false><<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        scan_kernel<OffT>(kScanR1, defer1, false)<<<std::min<uint32_t>(nt1, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         c->n_launches++;
     }
     if (nt2) {
@@ -597,8 +626,7 @@ int launch_scans(ssd_ctx* c, bool defer1, bool defer2)
         a.status = (unsigned long long*)c->b_status2.p;
         a.n_tiles = nt2;
         StageTimer t(c, 1);
-        if (defer2) k_scan<kScanR2, OffT, true><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
-        else k_scan<kScanR2, OffT, false><<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
+        scan_kernel<OffT>(kScanR2, defer2, c->short2)<<<std::min<uint32_t>(nt2, c->scan_grid), kScanThreads, sizeof(ScanSmem), c->stream>>>(a, c->dcfg);
         c->n_launches++;
     }
     CU(c, cudaGetLastError());
@@ -821,18 +849,8 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
         // the scan kernels are persistent: one wave of blocks, each looping over tiles
         cudaDeviceProp prop;
         CUB_(cudaGetDeviceProperties(&prop, c->device));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR1, uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanR2, uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-        CUB_(cudaFuncSetAttribute(k_scan<kScanAnn, uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+        CUB_(scan_kernel_attributes<uint32_t>());  // every kernel scan_kernel() can return
+        CUB_(scan_kernel_attributes<uint64_t>());
         CUB_(cudaFuncSetAttribute(k_emit_tiled<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
         CUB_(cudaFuncSetAttribute(k_emit_tiled<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
         CUB_(cudaFuncSetAttribute(k_emit_stream<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
@@ -840,7 +858,7 @@ extern "C" int ssd_create(const ssd_config* cfg, ssd_ctx** out)
         int per_sm = 0;
         CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_stream<uint32_t>, kStreamThreads, sizeof(StreamSmem)));
         c->emit_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
-        CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<kScanR2, uint32_t, true>, kScanThreads, sizeof(ScanSmem)));
+        CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<uint32_t>(kScanR2, true, false), kScanThreads, sizeof(ScanSmem)));
         c->scan_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::max(per_sm, 1);
     }
     CUB_(cudaMalloc(&c->d_cnt, sizeof(DevCounters)));
@@ -938,6 +956,10 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
     // (records so short that a tile holds more of them than stage B parks at once count as a wrong guess).  The choice is
     // remembered per file for the next batches of this context.
     if (getenv("SSD_SCAN_NODEFER")) c->defer1 = c->defer2 = false;
+    if (const char* sv = getenv("SSD_SCAN_SHORT")) {
+        c->short2 = sv[0] == '1';
+        c->short_auto = false;
+    }
     for (int attempt = 0, overflows = 0; attempt < 5; attempt++) {
         c->rec_cap = cap;
         OKR(ensure(c, c->b_status1, (size_t)(nt1 + 1) * 8));
@@ -981,6 +1003,10 @@ int run_phase1(ssd_ctx* c, const void* d_r1, size_t r1_len, const void* d_r2, si
         std::string tok = token_at(c, c->r2, c->r2_len, off[1]);
         return fail(c, SSD_EKEY, "%s", tok.c_str());
     }
+    // Many read-2 records on the exact path (truncated reads: one thread each, against global memory): the next batches of this
+    // context take the scan variant that keeps them on the fast path.  This batch's results are exact either way.
+    c->n_exact_last = h.n_exact;
+    if (!annotated && c->short_auto && !c->short2 && h.n_exact > 64u && (uint64_t)h.n_exact * 1000u > h.n_records[1]) c->short2 = true;
     c->n_rec_r1 = h.n_records[0];
     c->n_rec_r2 = annotated ? h.n_records[0] : h.n_records[1];
     c->n_rec = std::min(c->n_rec_r1, c->n_rec_r2);
@@ -2397,6 +2423,14 @@ extern "C" int ssd_scan_repeats(const ssd_ctx* c, uint64_t* n)
 {
     if (!c || !n) return SSD_EINVAL;
     *n = c->n_respec;
+    return SSD_OK;
+}
+
+extern "C" int ssd_scan_variant(const ssd_ctx* c, int* short_fast, uint64_t* exact_records)
+{
+    if (!c) return SSD_EINVAL;
+    if (short_fast) *short_fast = c->short2 ? 1 : 0;
+    if (exact_records) *exact_records = c->n_exact_last;
     return SSD_OK;
 }
 

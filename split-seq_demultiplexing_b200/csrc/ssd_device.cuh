@@ -89,7 +89,7 @@ struct DevCounters {
     unsigned long long n_irr;          // irregular keys appended
     unsigned int err_flags;
     unsigned int ticket[2];            // dynamic tile tickets of the two scans
-    unsigned int pad;
+    unsigned int n_exact;              // read-2 records that left the fast path for the exact one (what the host picks the scan variant on)
     // produced by ssd_build_filter; zeroed as one block starting at n_matched
     unsigned long long n_matched, bytes_matched, bytes_passing, n_retained, n_cells, n_passing_cells;
 };

@@ -23,13 +23,6 @@
 
 namespace ssd {
 
-// 1: a read 2 whose sequence ends before the last slice does (and any window with several bytes outside ACGT) stays on the
-// fast path -- its windows are matched by the whole warp against the whitelist (coop_first_hit) instead of the record going
-// through the exact path, one thread against global memory.  0: the round-1 behaviour.
-#ifndef SSD_SCAN_SHORT_FAST
-#define SSD_SCAN_SHORT_FAST 0
-#endif
-
 #ifndef SSD_SCAN_TILE
 #define SSD_SCAN_TILE 24576
 #endif
@@ -522,9 +515,7 @@ struct __align__(128) ScanSmem {
     uint32_t guess_j[kListSlots], guess_n[kListSlots];  // the guess warp's guess of the record phase of the tile (stage B takes it from here)
     uint32_t warp_tile[kAWarps], halo_sum[2];
     alignas(16) uint32_t mask[kWinWords];     // newline bitmap of the tile in stage A (bit b of word w = byte 32 w + b)
-#if SSD_SCAN_SHORT_FAST
-    uint16_t wl_code[3][kMaxWl];              // read 2: the 2-bit whitelist codes of the three rounds (coop_first_hit)
-#endif
+    uint16_t wl_code[3][kMaxWl];              // read 2, SHORT variant: the 2-bit whitelist codes of the three rounds (coop_first_hit)
 };
 
 // which scans run the per-record work ahead of the line index (read 2 is issue-bound: nothing to hide there)
@@ -570,7 +561,11 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 //                 prefix, so a tile learns its global line index with one poll of its own entry
 //   compute warps stage A(i + kDepth): newline bitmap (kept in registers), count (published), line-start list
 //                 stage B(i)         : poll the line index, process the records that start in the tile
-template <int MODE, typename OffT, bool DEFER>
+// SHORT (read 2 only): a read 2 whose sequence ends before the last slice does, and any window with several bytes outside ACGT,
+// stays on the fast path -- its windows are matched by the whole warp against the whitelist (coop_first_hit) -- instead of the
+// record going through the exact path, one thread against global memory.  The host picks the variant per context: it starts
+// without (the common path is 5 % shorter) and switches when a batch sent more than 1 record in 1 000 down the exact path.
+template <int MODE, typename OffT, bool DEFER, bool SHORT = false>
 __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const __grid_constant__ ScanArgs<OffT> args, const __grid_constant__ DevCfg cfg)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -591,10 +586,9 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             mbar_init(reinterpret_cast<uint64_t*>(&S.stage_empty[s]), 1);
         }
     }
-#if SSD_SCAN_SHORT_FAST
-    if (MODE == kScanR2)
+    if constexpr (SHORT && MODE == kScanR2) {
         for (int i = tid; i < 3 * kMaxWl; i += kScanThreads) S.wl_code[i / kMaxWl][i % kMaxWl] = cfg.wl_code[i / kMaxWl][i % kMaxWl];
-#endif
+    }
     __syncthreads();
     volatile unsigned long long* st = args.status;
 
@@ -725,6 +719,7 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                     } else if (have) {
                         R2Out o;
                         bool complete = false;
+                        atomicAdd(&args.cnt->n_exact, 1u);
                         r2_record_generic(ga, args, cfg, r, tile_lo + s0, o, complete, n_rec_r1);
                         if (complete) args.ann[r] = o.ann;
                         const uint32_t st8 = ann_state(o.ann);
@@ -1040,11 +1035,11 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             if (MODE == kScanR2) {
                 win_ok = fast && cfg.fast_wl != 0 && cfg.fast_geom != 0;
                 if (win_ok) win_ok = rstrip2(s_win, s1, w_seq_e);
-#if SSD_SCAN_SHORT_FAST
-                shortseq = win_ok && w_seq_e - s1 < (uint32_t)cfg.need_len;  // truncated read 2: its windows are matched by the warp below
-#else
-                if (win_ok) win_ok = w_seq_e - s1 >= (uint32_t)cfg.need_len;  // truncated read 2 goes the exact way
-#endif
+                if constexpr (SHORT) {
+                    shortseq = win_ok && w_seq_e - s1 < (uint32_t)cfg.need_len;  // truncated read 2: its windows are matched by the warp below
+                } else {
+                    if (win_ok) win_ok = w_seq_e - s1 >= (uint32_t)cfg.need_len;  // truncated read 2 goes the exact way
+                }
                 if (win_ok && !shortseq) {
                     uint32_t y0, y1;
                     load8(words, s1 + (uint32_t)cfg.b1s, y0, y1);
@@ -1206,12 +1201,11 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
             } else {
                 // ---- lineRead = line.rstrip(); the four windows (V2:293-301): requested above, answered by now ----
                 ok = win_ok && bad == 0u;
-#if SSD_SCAN_SHORT_FAST
                 // the windows the tables did not answer -- all three of a short sequence (lineRead[s:e] gives what is there, hamming()
                 // zips to the shorter operand: V2:72-73, 296-301), and dirty windows beyond the one-N case -- go to the whole warp
                 const uint32_t seq_len = w_seq_e - s1;
                 int c1 = -1, c2 = -1, c3 = -1;
-                {
+                if constexpr (SHORT) {
                     const uint32_t ask = !ok ? 0u : (shortseq ? 7u : ((dirty & 8u) ? 0u : (dirty & 7u)));
                     if (__any_sync(0xFFFFFFFFu, ask != 0u)) {
 #pragma unroll
@@ -1240,19 +1234,15 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                         }
                     }
                 }
-#endif
                 if (ok) {
                     complete = true;
                     noat = s_win[s0] != '@';
                     int i1 = v1 == 0xFFu ? -1 : (int)v1, i2 = v2 == 0xFFu ? -1 : (int)v2, i3 = v3 == 0xFFu ? -1 : (int)v3;
-#if SSD_SCAN_SHORT_FAST
-                    if (shortseq) {
+                    if (SHORT && shortseq) {
                         i1 = c1;
                         i2 = c2;
                         i3 = c3;
-                    } else
-#endif
-                    if (dirty) {  // some window holds a byte that is not A/C/G/T
+                    } else if (dirty) {  // some window holds a byte that is not A/C/G/T
                         if (dirty & 8u) {
                             const uint32_t best = min(min(x0, x1), min(x2, x3));
                             const int ix = best == 0xFFu ? -1 : (int)best;
@@ -1260,28 +1250,30 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                             if (dirty & 2u) i2 = ix;
                             if (dirty & 4u) i3 = ix;
                         } else {
-#if SSD_SCAN_SHORT_FAST
-                            if (dirty & 1u) i1 = c1;
-                            if (dirty & 2u) i2 = c2;
-                            if (dirty & 4u) i3 = c3;
-#else
-                            if (dirty & 1u) i1 = match8(cfg, 0, args.lut, code1, da0, da1);
-                            if (dirty & 2u) i2 = match8(cfg, 1, args.lut, code2, db0, db1);
-                            if (dirty & 4u) i3 = match8(cfg, 2, args.lut, code3, dc0, dc1);
-#endif
+                            if constexpr (SHORT) {
+                                if (dirty & 1u) i1 = c1;
+                                if (dirty & 2u) i2 = c2;
+                                if (dirty & 4u) i3 = c3;
+                            } else {
+                                if (dirty & 1u) i1 = match8(cfg, 0, args.lut, code1, da0, da1);
+                                if (dirty & 2u) i2 = match8(cfg, 1, args.lut, code2, db0, db1);
+                                if (dirty & 4u) i3 = match8(cfg, 2, args.lut, code3, dc0, dc1);
+                            }
                         }
                     }
                     matched = i1 >= 0 && i2 >= 0 && i3 >= 0;  // V2:310-321: all three lists non-empty (the mate check follows in commit())
                     if (matched) {
                         const uint32_t cell = cell_of(cfg, i1, i2, i3);
                         // UMI = lineRead[umi_start:umi_end] verbatim (V2:295): what the sequence holds of it
-#if SSD_SCAN_SHORT_FAST
-                        const uint32_t ulo = min((uint32_t)cfg.us, seq_len), uhi = min((uint32_t)cfg.ue, seq_len);
-                        const uint32_t up = s1 + ulo, ul = uhi - ulo;
-#else
-                        const uint32_t up = s1 + (uint32_t)cfg.us;
-                        const uint32_t ul = (uint32_t)cfg.umi_len;
-#endif
+                        uint32_t up, ul;
+                        if constexpr (SHORT) {
+                            const uint32_t ulo = min((uint32_t)cfg.us, seq_len), uhi = min((uint32_t)cfg.ue, seq_len);
+                            up = s1 + ulo;
+                            ul = uhi - ulo;
+                        } else {
+                            up = s1 + (uint32_t)cfg.us;
+                            ul = (uint32_t)cfg.umi_len;
+                        }
                         const uint32_t i0 = up >> 2, sh = (up & 3u) * 8u;
                         const uint32_t w0 = words[i0], w1 = words[i0 + 1], w2 = words[i0 + 2], w3 = words[i0 + 3];
                         const uint32_t m0 = ul >= 4u ? 0xFFFFFFFFu : (1u << (8u * ul)) - 1u;
@@ -1356,7 +1348,10 @@ __global__ void __launch_bounds__(kScanThreads, SSD_SCAN_MINBLOCKS) k_scan(const
                     complete = false;
                 }
                 __syncwarp();
-                if (have && !ok2) r2_record_generic(ga, args, cfg, r, tile_lo + s0, o, complete, n_rec_r1);
+                if (have && !ok2) {
+                    atomicAdd(&args.cnt->n_exact, 1u);
+                    r2_record_generic(ga, args, cfg, r, tile_lo + s0, o, complete, n_rec_r1);
+                }
                 __syncwarp();
                 // ---- results: annotation, histogram, key counts; the regular (cell, UMI) key is the annotation itself
                 //      (the sort reads it from there), irregular keys are collected afterwards by k_collect_irr ----

@@ -111,6 +111,7 @@ _SIGS = {
                                         C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ssd_key_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ssd_scan_repeats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "ssd_scan_variant": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "ssd_owner_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ssd_partition_keys": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_uint64)]),

@@ -342,6 +342,14 @@ class Demultiplexer:
         self._check(self.lib.ssd_scan_repeats(self._ctx, C.byref(n)))
         return n.value
 
+    def scan_variant(self) -> Tuple[bool, int]:
+        """(short_fast, exact_records): whether the NEXT batch's read-2 scan keeps short sequences and windows with several
+        non-ACGT bytes on its fast path (the context turns that on after a batch that sent more than 1 record in 1 000 down the
+        exact record-by-record path; SSD_SCAN_SHORT=0/1 pins it), and how many read-2 records of the LAST batch went that way."""
+        sf, n = C.c_int(), C.c_uint64()
+        self._check(self.lib.ssd_scan_variant(self._ctx, C.byref(sf), C.byref(n)))
+        return bool(sf.value), n.value
+
     def launch_count(self) -> int:
         return int(self.lib.ssd_launch_count(self._ctx))
 

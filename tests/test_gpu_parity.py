@@ -691,6 +691,10 @@ def test_batches_equal_one_call(ssd, orc, filter_mode):
 def test_fuzz_against_oracle(ssd, orc, seed):
     """Seeded random configurations of the adversarial generator (sizes, line endings, header forms, N / tie / junk /
     truncation rates, e, m), CUDA path against the CPU oracle: both outputs byte for byte, per-record cells, counts."""
+    _fuzz(ssd, orc, seed)
+
+
+def _fuzz(ssd, orc, seed):
     import random
     rng = random.Random(1000 + seed)
     n = rng.choice([1, 7, 300, 2500, 12000])
@@ -750,3 +754,78 @@ def test_extract_style_headers_equal_the_reference_script(ssd, orc):
     # a name of one token: ReadName_parts[1] is an IndexError in the script
     with pytest.raises(IndexError):
         ssd.Demultiplexer(WL, errors=1, min_count=1, header_style="extract").run_host(r1.replace(b"@SRR6750041.5 5/1", b"@SRR6750041.5"), r2, ssd.EMIT_MATCHED)
+
+
+# ---- the read-2 scan variant for short sequences (k_scan<.., SHORT>) ------------------------------------------------
+# A context starts with the plain read-2 scan and takes the variant that keeps short sequences and windows with several non-ACGT
+# bytes on the fast path once a batch sent more than 1 record in 1 000 down the exact path; SSD_SCAN_SHORT=1 / 0 pins the choice.
+@pytest.mark.parametrize("case", RULES, ids=["%s-e%d" % (c["name"], c["e"]) for c in RULES])
+def test_rule_cases_short_variant(ssd, case, monkeypatch):
+    monkeypatch.setenv("SSD_SCAN_SHORT", "1")
+    test_rule_cases(ssd, case)
+
+
+@pytest.mark.parametrize("g", ADV, ids=["%s-e%d-m%d" % (g["name"], g["e"], g["m"]) for g in ADV])
+def test_adversarial_short_variant(ssd, g, monkeypatch):
+    monkeypatch.setenv("SSD_SCAN_SHORT", "1")
+    test_adversarial(ssd, g)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_against_oracle_short_variant(ssd, orc, seed, monkeypatch):
+    monkeypatch.setenv("SSD_SCAN_SHORT", "1")
+    _fuzz(ssd, orc, seed)
+
+
+@pytest.mark.parametrize("e,m,kw", [
+    (2, 5, {"p_tie": 0.05, "p_trunc": 0.02, "p_n": 0.03}),
+    (1, 3, {"p_trunc": 0.3, "p_n": 0.01}),
+    (0, 1, {"p_trunc": 0.05, "p_n": 0.02}),
+    (3, 2, {"p_sub": 0.05, "p_n": 0.05, "p_trunc": 0.01, "cell_pool": 300}),
+])
+def test_short_variant_vs_oracle(ssd, orc, monkeypatch, e, m, kw):
+    """Truncated read 2 (V2:296-301 slices past the end; hamming() zips to the shorter operand, V2:72-73), windows with one, two and
+    more N: the variant's warp-wide whitelist search against the oracle, record for record; and it really keeps them off the
+    exact path (the plain scan sends every truncated read there)."""
+    kw = dict(kw)
+    spec = ssd.synth_spec(WL, 30000, seed=0x5407 + e, cell_pool=kw.pop("cell_pool", 2000), **kw)
+    r1, r2 = ssd.synth_host(spec)
+    ref = orc.demultiplex(r1, r2, WL, e, m)
+    exact = {}
+    for pin in ("0", "1"):
+        monkeypatch.setenv("SSD_SCAN_SHORT", pin)
+        dm, merged, passing, stats = run_both(ssd, r1, r2, e, m)
+        assert dm.record_cells().tolist() == ref.rec_cell
+        assert merged == ref.merged1 and passing == ref.passing
+        assert (stats["n_matched"], stats["n_cells"], stats["n_passing_cells"], stats["n_retained"]) == (
+            ref.n_matched, ref.n_cells, ref.n_passing_cells, ref.n_retained)
+        assert dm.cell_table() == {c.decode(): (v[0], v[1]) for c, v in ref.cells.items()}
+        short, exact[pin] = dm.scan_variant()
+        assert short == (pin == "1")
+    assert exact["0"] >= 0.005 * 30000 and exact["1"] * 20 <= exact["0"]
+
+
+def test_scan_variant_follows_the_data(ssd, orc, monkeypatch):
+    """No pin: the first batch with truncated reads runs the plain scan and turns the variant on, the next batch of the context
+    runs it -- the same bytes; a context that only sees whole reads never switches."""
+    monkeypatch.delenv("SSD_SCAN_SHORT", raising=False)
+    r1, r2 = ssd.synth_host(ssd.synth_spec(WL, 40000, seed=0x5408, cell_pool=1500, p_trunc=0.02, p_n=0.01))
+    ref = orc.demultiplex(r1, r2, WL, 2, 4)
+    dm = ssd.Demultiplexer(WL, errors=2, min_count=4)
+    assert dm.scan_variant() == (False, 0)
+    out1, st1 = dm.run_host(r1, r2, ssd.EMIT_PASSING)
+    out1 = out1.tobytes()
+    short, exact1 = dm.scan_variant()
+    assert short and exact1 >= 0.01 * 40000
+    out2, st2 = dm.run_host(r1, r2, ssd.EMIT_PASSING)
+    short, exact2 = dm.scan_variant()
+    assert short and exact2 * 20 <= exact1
+    assert out1 == out2.tobytes() == ref.passing and st1 == st2
+    assert dm.record_cells().tolist() == ref.rec_cell
+    dm.close()
+    c1, c2 = ssd.synth_host(ssd.synth_spec(WL, 40000, seed=0x5409, cell_pool=1500))
+    dm = ssd.Demultiplexer(WL, errors=1, min_count=4)
+    dm.run_host(c1, c2, ssd.EMIT_PASSING)
+    dm.run_host(c1, c2, ssd.EMIT_PASSING)
+    assert dm.scan_variant()[0] is False
+    dm.close()
