@@ -290,6 +290,7 @@ def measure_resident(env, cid, cfg, args):
     stage = dm.read_timings()
     dm.set_timing(False)
     value = env.world * n * args.steps / (ms / 1e3)
+    short_fast, exact_records = dm.scan_variant()  # which read-2 scan the timed steps ran (the context picks it from its data)
 
     in1, in2 = d1.numel(), d2.numel()
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region ----
@@ -461,6 +462,7 @@ def measure_resident(env, cid, cfg, args):
                     "frac": per_kernel[dom]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "per_kernel": per_kernel,
                     "stage_ms_per_step": {k: v[0] / max(1, args.steps) for k, v in stage.items()},
+                    "scan_r2_variant": {"short_fast": bool(short_fast), "exact_path_records_per_step": int(exact_records)},
                     "pipeline": {"algorithmic_bytes_per_step": pipeline_bytes, "achieved": pipeline_gbs, "frac": pipeline_gbs / peak}}
     dm.close()
     d1 = d2 = out = None
@@ -622,7 +624,7 @@ def child_config(cid, steps, timeout_s, scale_env=None):
         keep = {k: line.get(k) for k in ("metric", "value", "unit", "ms_per_step", "steps", "scaling", "config", "gpu_launches", "result")}
         keep["e2e"] = {k: line["e2e"].get(k) for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "pairs_per_step_per_gpu", "note")}
         if line.get("roofline"):
-            keep["roofline"] = {k: line["roofline"].get(k) for k in ("kernel", "achieved", "peak", "frac", "pipeline", "stage_ms_per_step")}
+            keep["roofline"] = {k: line["roofline"].get(k) for k in ("kernel", "achieved", "peak", "frac", "pipeline", "stage_ms_per_step", "scan_r2_variant")}
         keep["wall_s"] = time.perf_counter() - t0
         return keep
     except subprocess.TimeoutExpired:
