@@ -14,9 +14,10 @@
 // The per-record code is written to stay convergent: line boundaries come from a per-tile list of line
 // starts (no searching), headers and barcode windows are handled four bytes at a time with
 // SIMD-in-register tests, loops have warp-uniform trip counts.  Whatever falls outside the fast path's
-// preconditions (control characters in headers, truncated read 2, records longer than the window, more
-// than two trailing blanks, ...) is routed to an exact generic path, first against the window and then
-// against global memory.
+// preconditions (control characters in headers, records longer than the window, more than two trailing
+// blanks, ... and, in the plain read-2 scan, a sequence that ends before the last slice does) is routed
+// to an exact generic path against global memory, one thread per record; the SHORT variant of the read-2
+// scan keeps short sequences on the fast path (the whole warp searches the whitelist for their windows).
 #pragma once
 #include "ssd_device.cuh"
 #include "ssd_match.cuh"
