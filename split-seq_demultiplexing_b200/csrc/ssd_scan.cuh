@@ -518,6 +518,8 @@ struct __align__(128) ScanSmem {
     alignas(16) uint32_t mask[kWinWords];     // newline bitmap of the tile in stage A (bit b of word w = byte 32 w + b)
     uint16_t wl_code[3][kMaxWl];              // read 2, SHORT variant: the 2-bit whitelist codes of the three rounds (coop_first_hit)
 };
+// SSD_SCAN_MINBLOCKS blocks per SM: 227 KB of shared memory per SM, 1 KB per block reserved by the system
+static_assert(SSD_SCAN_MINBLOCKS * (sizeof(ScanSmem) + 1024) <= 227 * 1024, "the scan blocks of one SM do not fit its shared memory");
 
 // which scans run the per-record work ahead of the line index (read 2 is issue-bound: nothing to hide there)
 #ifndef SSD_SCAN_SPECULATE
