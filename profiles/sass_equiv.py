@@ -1,3 +1,12 @@
+"""Instruction-by-instruction comparison of the scan kernels of two cubins (cuobjdump -sass), branch and return targets taken
+relative to the instruction so that code that merely moved compares equal.  Used once, at the end of round 2, to show that the
+templated read-2 scan (k_scan<MODE, OffT, DEFER, SHORT>) is the code of the two libraries that were measured and parity-tested
+on the GPU (-DSSD_SCAN_SHORT_FAST=0 / =1 builds of commit 75545af): output in profiles/r02_short/sass_equivalence.txt.
+
+    nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -cubin -o /tmp/new.cubin csrc/ssd_b200.cu
+    (the same from a checkout of 75545af, without and with -DSSD_SCAN_SHORT_FAST=1 -> /tmp/ref_base.cubin, /tmp/ref_v1.cubin)
+    python profiles/sass_equiv.py [-v]
+"""
 import re, subprocess, sys, difflib
 def sass(cubin, fn):
     out = subprocess.run(["cuobjdump", "-sass", "-fun", fn, cubin], capture_output=True, text=True).stdout
