@@ -162,6 +162,20 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's CPU algorithm on the host cores (oracle/ only: no product code)
 # ------------------------------------------------------------------------------------------------
+def python_reference_figure(cid):
+    """What the UNMODIFIED Python reference (CLI3) did on the head of this workload in the authoring container -- the GPU box
+    has no /root/reference -- as tests/golden/make_reference_on_synthetic.py measured and committed it; None when there is none."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "reference_on_synthetic.json")) as fh:
+            ref = json.load(fh)
+        case = next(c for c in ref["cases"] if c["name"] == "config%d-head" % cid)
+        return {"value": case["pairs_per_s"], "unit": UNIT, "cores": ref["host"]["cores"], "cpu": ref["host"]["cpu"],
+                "where": "authoring container (not this box)", "sample": "first %d pairs of the workload, %s" % (case["pairs"], ref["reference"]),
+                "equals_oracle_output": bool(case["oracle"]["equal"])}
+    except Exception:  # noqa: BLE001 - a quoted figure, never worth a failed run
+        return None
+
+
 def oracle_input(cfg, n_pairs):
     from oracle import ssd_oracle_py as orc
     r1, r2 = orc.synth_pairs(load_whitelist(), n_pairs, seed=cfg["seed"], read_len=READ_LEN, **cfg["spec"])
@@ -205,7 +219,8 @@ def run_reference_arm(args, cid, cfg):
     line = {"impl": "reference", "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": cfg["scaling"],
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "python_reference": python_reference_figure(cid)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "the reference is pure Python and is not present on the GPU box; this is its algorithm restated in C "
@@ -707,7 +722,7 @@ def main():
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "first %d pairs of the same synthetic workload, one pass, %d worker threads; C restatement of the "
                                   "reference (oracle/ssd_oracle.c) — the Python reference itself runs at ~3e3 pairs/s/core" % (n_sample, cores),
-                        "seconds": min(times)}
+                        "seconds": min(times), "python_reference": python_reference_figure(cid)}
 
     if env.rank == 0:
         if cfg["mode"] == "batches":

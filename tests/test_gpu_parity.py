@@ -829,3 +829,23 @@ def test_scan_variant_follows_the_data(ssd, orc, monkeypatch):
     dm.run_host(c1, c2, ssd.EMIT_PASSING)
     assert dm.scan_variant()[0] is False
     dm.close()
+
+
+# ---- the reference CLI itself on the head of the bench workloads (tests/golden/make_reference_on_synthetic.py) -----------------------
+with open(os.path.join(fu.GOLDEN_DIR, "reference_on_synthetic.json")) as _fh:
+    REF_SYNTH = json.load(_fh)["cases"]
+
+
+@pytest.mark.parametrize("case", REF_SYNTH, ids=[c["name"] for c in REF_SYNTH])
+def test_reference_cli_on_the_bench_workloads(ssd, orc, case):
+    """The CUDA path against what the UNMODIFIED reference CLI wrote for the first 200 k pairs of config 2 and the first 100 k of
+    config 3's shape (e=2, N bases, 2/2 ties, truncated read 2): same retained records (canonical SHA-256), same counts -- no
+    oracle in between."""
+    spec = {k: (int(v, 16) if k == "seed" else v) for k, v in case["spec"].items()}
+    a, b = orc.synth_pairs(WL, case["pairs"], read_len=150, **spec)
+    r1, r2 = a.tobytes(), b.tobytes()
+    assert [hashlib.sha256(r1).hexdigest(), hashlib.sha256(r2).hexdigest()] == case["input_sha256"]
+    dm, merged, passing, stats = run_both(ssd, r1, r2, case["e"], case["m"])
+    assert fu.canonical_sha(passing) == case["passing_canonical_sha256"]
+    assert (stats["n_cells"], stats["n_passing_cells"], stats["n_retained"], len(passing)) == (
+        case["cells"], case["passing_cells"], case["retained_records"], case["passing_bytes"])

@@ -189,3 +189,27 @@ def test_oracle_generator_equals_the_products_host_twin(kw):
     assert a.tobytes() == h1 and b.tobytes() == h2
     a1, b1 = orc.synth_pairs(wl, 6000, n_threads=1, **kw)
     assert a1.tobytes() == h1 and b1.tobytes() == h2
+
+
+def _ref_synth_cases():
+    with open(os.path.join(fu.GOLDEN_DIR, "reference_on_synthetic.json")) as fh:
+        return json.load(fh)["cases"]
+
+
+@pytest.mark.parametrize("case", _ref_synth_cases(), ids=lambda c: c["name"])
+def test_oracle_equals_the_reference_cli_on_the_bench_workloads(case):
+    """tests/golden/make_reference_on_synthetic.py ran the UNMODIFIED reference CLI (splitseqdemultiplex_0.2.3.py, 8 worker
+    processes, position detection on) on the head of the synthetic bench workloads (config 2: e=1; config 3: e=2, N bases, 2/2
+    ties, truncated read 2): the oracle, on the same regenerated bytes, gives the same retained records and counts."""
+    import hashlib
+    from oracle import ssd_oracle_py as orc
+    wl = fu.load_whitelist()
+    spec = {k: (int(v, 16) if k == "seed" else v) for k, v in case["spec"].items()}
+    a, b = orc.synth_pairs(wl, case["pairs"], read_len=150, **spec)
+    r1, r2 = a.tobytes(), b.tobytes()
+    assert [hashlib.sha256(r1).hexdigest(), hashlib.sha256(r2).hexdigest()] == case["input_sha256"]
+    for workers in (1, 5):  # the chunking of CLI3:52-64 does not show in the result
+        ref = orc.run_cli(r1, r2, wl, case["e"], case["m"], n_workers=workers, length_fastq=r2.count(b"\n"))
+        assert fu.canonical_sha(ref.passing) == case["passing_canonical_sha256"]
+        assert (ref.n_cells, ref.n_passing_cells, ref.n_retained, len(ref.passing)) == (
+            case["cells"], case["passing_cells"], case["retained_records"], case["passing_bytes"])
