@@ -142,6 +142,14 @@ class Demultiplexer:
         if rc != L.OK:
             _raise(rc, self.lib.ssd_last_error(self._ctx).decode(errors="replace"))
 
+    def _no_records_check(self, st, heads):
+        """A call that found no record at all in non-empty input: if that is because the lines end in a lone '\r' (which the
+        reference's universal-newline reading takes for line ends and the scans do not), say so instead of returning
+        an empty result.  heads() -> the first bytes of the two inputs; only looked at in that case."""
+        if st.n_records_r1 == 0 and st.n_records_r2 == 0:
+            from . import hostlogic
+            hostlogic.reject_lone_cr(*heads())
+
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.ssd_set_stream(self._ctx, C.c_void_p(cuda_stream)))
 
@@ -382,9 +390,11 @@ class Demultiplexer:
             rc = self.lib.ssd_run_host(*args, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n), C.byref(st))
             if rc != L.ERANGE:
                 self._check(rc)
+                self._no_records_check(st, lambda: (bytes(a1[:65536]), bytes(a2[:65536])))
                 return out[: n.value], self.stats()
         else:
             self._check(self.lib.ssd_run_host(*args, None, 0, C.byref(n), C.byref(st)))
+        self._no_records_check(st, lambda: (bytes(a1[:65536]), bytes(a2[:65536])))
         out = np.empty(n.value, dtype=np.uint8)
         if n.value:
             self._check(self.lib.ssd_emit_host(self._ctx, which, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)))
@@ -402,6 +412,11 @@ class Demultiplexer:
         n = C.c_size_t()
         self._check(self.lib.ssd_run_files(self._ctx, os.fsencode(path_r1), os.fsencode(path_r2), which, os.fsencode(out_path), 1 if append else 0,
                                            C.byref(n), C.byref(st)))
+
+        def heads():
+            with open(path_r1, "rb") as f1, open(path_r2, "rb") as f2:
+                return f1.read(65536), f2.read(65536)
+        self._no_records_check(st, heads)
         return n.value, st.as_dict()
 
     def filter_annotated_file(self, path_in: str, out_path: str, append: bool = True):

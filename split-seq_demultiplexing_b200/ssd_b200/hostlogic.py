@@ -152,6 +152,28 @@ def tuned_split_size(length_fastq: int, split_num: int, tries: int = 100) -> int
     return int(size)
 
 
+def lone_cr_in_head(head: bytes) -> bool:
+    """True when the first bytes of a FASTQ file hold a carriage return that is not followed by a line feed (classic Mac line
+    ends).  The reference reads its files with Python's universal newlines, which make such a '\r' a line break; the library's
+    scans break lines at '\n' only, so a file of that kind holds no records for them.  The last byte of the head is
+    not judged (its '\n' may be the next byte)."""
+    i = head.find(b"\r")
+    while 0 <= i < len(head) - 1:
+        if head[i + 1:i + 2] != b"\n":
+            return True
+        i = head.find(b"\r", i + 1)
+    return False
+
+
+def reject_lone_cr(*heads: bytes):
+    """Raise instead of returning an empty result for inputs whose lines end in a lone '\r' (see lone_cr_in_head)."""
+    from .engine import MalformedFastq
+    for k, head in enumerate(heads):
+        if lone_cr_in_head(head):
+            raise MalformedFastq("input %d: lines end in a lone carriage return (classic Mac line ends); convert the file to "
+                                 "\\n or \\r\\n line ends first (the reference's universal-newline reading is not reproduced)" % (k + 1))
+
+
 def summary_lines(n_cells: int, threshold, n_passing: int) -> List[str]:
     """V2:458-459, verbatim."""
     return ["The total number of unique barcodes detected was " + str(n_cells),

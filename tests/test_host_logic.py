@@ -480,3 +480,31 @@ def test_plan_shards_device_cuts_both_files_at_the_same_records(tmp_path, monkey
         if world > 1 and ending == "lf" and target is None:
             sizes = [n1 for _, n1, _, _ in flat]
             assert max(sizes) - min(sizes) < 2000                                # equal byte ranges, moved by less than a record or two
+
+
+def test_lone_carriage_returns_are_told_from_crlf(ssd):
+    """The reference reads with universal newlines (a lone '\\r' ends a line: checked against it in the authoring container, the
+    all-'\\r' copy of a FASTQ pair demultiplexes like the original); the scans break lines at '\\n' only and find no record in
+    such a file, which the host layer reports instead of an empty result (Demultiplexer._no_records_check)."""
+    from ssd_b200 import hostlogic
+    from ssd_b200.engine import MalformedFastq
+    assert hostlogic.lone_cr_in_head(b"@a 1/1\rACGT\r+\rEEEE\r@b 2/1\r")
+    assert hostlogic.lone_cr_in_head(b"@a\r\nAC\rGT\r\n")
+    assert not hostlogic.lone_cr_in_head(b"@a 1/1\r\nACGT\r\n+\r\nEEEE\r\n")
+    assert not hostlogic.lone_cr_in_head(b"@a 1/1\nACGT\n+\nEEEE\n")
+    assert not hostlogic.lone_cr_in_head(b"@a 1/1\nACGT\n+\nEEEE\r")   # the head may end between '\\r' and '\\n'
+    assert not hostlogic.lone_cr_in_head(b"")
+    hostlogic.reject_lone_cr(b"@a\n", b"")
+    with pytest.raises(MalformedFastq) as ei:
+        hostlogic.reject_lone_cr(b"@a\nAC\n", b"@a\rAC\r+\rEE\r")
+    assert "input 2" in str(ei.value) and isinstance(ei.value, ValueError)
+
+    class St:
+        n_records_r1 = 0
+        n_records_r2 = 0
+    dm = ssd.Demultiplexer.__new__(ssd.Demultiplexer)        # the check itself needs no context
+    dm._no_records_check(St, lambda: (b"", b""))
+    with pytest.raises(MalformedFastq):
+        dm._no_records_check(St, lambda: (b"@a\rAC\r+\rEE\r", b"@a\rAC\r+\rEE\r"))
+    St.n_records_r2 = 3                                       # records were found: the heads are not even asked for
+    dm._no_records_check(St, lambda: 1 / 0)
